@@ -1,0 +1,45 @@
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import deepfir_oracle as O
+from oracle.synth import synth_inputs, synth_state_dict
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    info = json.loads(bytes(z["meta"]).decode())
+    return torch.from_numpy(z["out"]), info
+
+
+def case_tensors(info, seed=8):
+    sd = synth_state_dict(info["shapes"], seed=seed)
+    b, h, w = info["bhw"]
+    x, meta = synth_inputs(b, h, w, num_metadata=info["m_attr"], seed=seed)
+    return sd, x, meta
+
+
+def oracle_forward(info, sd, x, meta, nm=O.EXACT):
+    model, kw = info["model"], info["kwargs"]
+    if model == "qrcan":
+        return O.qrcan_forward(x, meta, sd, style=kw.get("style", "modulate"), nm=nm)
+    if model == "qedsr":
+        return O.qedsr_forward(x, meta, sd, res_scale=kw.get("res_scale", 0.1), nm=nm)
+    if model == "qsan":
+        return O.qsan_forward(x, meta, sd, nm=nm)
+    if model == "qhan":
+        return O.qhan_forward(x, meta, sd, nm=nm)
+    raise KeyError(model)
+
+
+def max_norm_err(a, b):
+    """SURVEY.md §8d fp32-mode metric: max|a-b| / max|b|."""
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max()).item()
