@@ -1,0 +1,177 @@
+/*
+ * dfir.h — C ABI of libdfir_b200.so: the B200 (sm_100a) implementation of the Deep-FIR SISR forward hot path.
+ *
+ * The upstream reference (um-dsrg/Super-Resolution-Meta-Attention-Networks) is pure Python/PyTorch and has no
+ * FFI of its own; its boundary for this path is `net.forward(x, metadata)` of the nn.Modules that the
+ * Q-model handlers own.  Each entry point below replaces one reference function and cites
+ * it (paths relative to /root/reference/Code/SISR/models).  INTEGRATION.md shows the ctypes binding a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types.  All data pointers are DEVICE pointers unless a name
+ *     ends in `_host`.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - every function returns DFIR_OK (0) or a negative DFIR_ERR_* code and never throws; work is enqueued
+ *     on `stream` and is asynchronous; nothing allocates device memory (the caller passes workspaces).
+ *   - no global mutable state: all state lives in the caller-owned descriptor structs and buffers.
+ *   - activations inside the library: NHWC; images at the API edge: NCHW fp32 contiguous, like the
+ *     reference's tensors.
+ */
+#ifndef DFIR_H_
+#define DFIR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFIR_ABI_VERSION 1
+
+/* error codes */
+#define DFIR_OK 0
+#define DFIR_ERR_ARG (-1)       /* invalid argument / unsupported configuration */
+#define DFIR_ERR_CUDA (-2)      /* a CUDA runtime call or kernel launch failed  */
+#define DFIR_ERR_DRIVER (-3)    /* cuTensorMapEncodeTiled entry point missing   */
+#define DFIR_ERR_TMAP (-4)      /* tensor-map encoding rejected                 */
+#define DFIR_ERR_WORKSPACE (-5) /* workspace too small                          */
+#define DFIR_ERR_ARCH (-6)      /* device is not sm_100                         */
+
+/* channel-attention styles of QCALayer (attention_manipulators/architectures.py:34-127) */
+#define DFIR_STYLE_NONE 0 /* no channel attention (ParamResBlock / QRB) */
+#define DFIR_STYLE_STANDARD 1
+#define DFIR_STYLE_MODULATE 2
+#define DFIR_STYLE_MAX_CONCAT 3
+#define DFIR_STYLE_SOFTMAX 4
+#define DFIR_STYLE_MINI_CONCAT 5
+#define DFIR_STYLE_EXTENDED 6
+
+/* arithmetic modes */
+#define DFIR_PREC_BF16_TC 0  /* bf16 operands, fp32 accumulate on tcgen05; fp32 residual stream */
+#define DFIR_PREC_FP32_SIMT 1 /* fp32 everywhere on CUDA cores (parity mode: <= 1e-4 normalised error) */
+
+const char* dfir_version(void);
+const char* dfir_error_string(int code);
+/* 0 if the current device can run the library (compute capability 10.x), else DFIR_ERR_ARCH */
+int dfir_check_device(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * weight packing (derived caches of the fp32 OIHW nn.Parameters; never serialised)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* OIHW fp32 [cout][cin=64][3][3] -> tensor-core layout: [9 taps][nt_rows][64 cin] bf16, rows in the UMMA
+ * K-major SWIZZLE_128B byte order.  Row n holds output channel co_begin + n*co_stride (zero rows beyond
+ * cout).  nt_rows = 64 (trunk/upsampler slices) or 16 (tail).  out: 9*nt_rows*128 bytes. */
+int dfir_pack_conv3x3_bf16(const float* w_oihw, void* out, int cout, int cin, int nt_rows, int co_begin,
+                           int co_stride, void* stream);
+/* OIHW fp32 -> [9 taps][cin][cout] fp32 for the CUDA-core kernels. */
+int dfir_pack_conv3x3_f32(const float* w_oihw, float* out, int cout, int cin, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * single operators (each is also exercised on its own by tests/test_ops_gpu.py)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* default_conv (advanced/common.py:5-8), 64 -> 64 (or 64 -> <=16 with epi = 4) on the tensor cores.
+ *   in_bf16  : NHWC bf16 [B][H][W][cin_total]; the 64 channels starting at cin_off are consumed
+ *   wpacked  : from dfir_pack_conv3x3_bf16;  bias: fp32 [64] (or [16])
+ *   epi      : 0 bias | 1 bias+ReLU | 2 bias + per-row channel sums into pool_rows[B][nseg][H][64]
+ *              | 3 bias + skip_f32 (NHWC fp32) -> out_f32 (NHWC fp32, may be NULL) and out_bf16
+ *              | 4 tail: out_f32 is NCHW fp32 [B][cout][H][W], no bf16 output
+ *   out_bf16 : NHWC bf16, addressed with explicit byte strides so that PixelShuffle
+ *              (advanced/common.py:30) folds into the store: for sub-pixel (i,j) of an r-times upsampler
+ *              pass base + ((i*r*W + j)*64*2), pix stride r*128, row stride r*(r*W)*128.
+ *   desc_mode: 0 (default).  1 selects the alternative shared-memory descriptor encoding used only by the
+ *              hardware bring-up test. */
+int dfir_conv3x3_c64(const void* in_bf16, int cin_total, int cin_off, const void* wpacked, const float* bias,
+                     int B, int H, int W, int epi, int cout, void* out_bf16, long long out_pix_stride,
+                     long long out_row_stride, long long out_img_stride, const float* skip_f32, float* out_f32,
+                     float* pool_rows, int desc_mode, void* stream);
+
+/* default_conv on CUDA cores, fp32 NHWC in/out, any Cin % 4 == 0 and any Cout.
+ *   w_packed from dfir_pack_conv3x3_f32; skip (optional) NHWC fp32 added after bias; relu applied last;
+ *   ps_r > 1 folds nn.PixelShuffle(ps_r) into the store (out is then [B][H*r][W*r][Cout/r^2]);
+ *   out_nchw != 0 writes [B][Cout][H][W] instead. */
+int dfir_conv3x3_f32(const float* in, const float* w_packed, const float* bias, const float* skip, float* out, int B,
+                     int H, int W, int Cin, int Cout, int relu, int ps_r, int out_nchw, void* stream);
+
+/* head conv (QRCAN.head, attention_manipulators/architectures.py:275,310): NCHW fp32 image -> NHWC features,
+ * fp32 (out_f32) and/or bf16 (out_bf16) copies; w_packed from dfir_pack_conv3x3_f32. */
+int dfir_head_conv(const float* x_nchw, const float* w_packed, const float* bias, float* out_f32, void* out_bf16,
+                   int B, int Cin, int H, int W, int Cout, void* stream);
+
+/* ParaCALayer.attribute_integrator for nblk layers at once (attention_manipulators/q_layer.py:21-41):
+ *   out[blk][b][:] = sigmoid(W2[blk] * act(W1[blk] * meta[b] + b1[blk]) + b2[blk]), act = ReLU if relu else id.
+ *   meta fp32 [B][M]; w1 [nblk][Hid][M]; b1 [nblk][Hid]; w2 [nblk][C][Hid]; b2 [nblk][C]; out [nblk][B][C].
+ *   blk_enabled (optional, int32 [nblk]): 0 -> the layer is absent and out = 1. */
+int dfir_meta_attention(const float* meta, const float* w1, const float* b1, const float* w2, const float* b2,
+                        float* out, int nblk, int B, int M, int Hid, int C, int relu, const int* blk_enabled,
+                        void* stream);
+
+/* Channel attention + meta-attention scale + residual add of one block:
+ *   QCALayer.forward + ParaCALayer `x*y` + `res += x` (attention_manipulators/architectures.py:105-127,172-180;
+ *   q_layer.py:43; ParamResBlock :346-356 with style NONE and res_scale):
+ *     y  = mean over pixels of r, rebuilt from pool_rows[b][0..pool_nrows)[C] / (H*W)
+ *     s  = CA_style(y, attributes) (* sq[b][:] if sq != NULL)            (style NONE: s = res_scale * sq)
+ *     x_out = r * s + x_in     (fp32 NHWC; x_out may alias x_in), x_out_bf16 = bf16(x_out) (optional)
+ *   r is NHWC bf16 (r_is_bf16) or fp32; ca_params: the block's fp32 parameter arrays, concatenated in the
+ *   order documented in DESIGN.md §"attention parameter blob". */
+int dfir_ca_scale_residual(const void* r, int r_is_bf16, const float* x_in, const float* pool_rows, int pool_nrows,
+                           int style, const float* ca_params, int C, int R, int M, int A, const float* attributes,
+                           const float* sq, float res_scale, float* x_out, void* x_out_bf16, int B, int H, int W,
+                           void* stream);
+
+/* per-row channel sums of an fp32 NHWC tensor: pool_rows[b][y][c] = sum_x in[b][y][x][c] (fp32 mode only;
+ * the tensor-core conv produces them in its epilogue). */
+int dfir_pool_rows_f32(const float* in, float* pool_rows, int B, int H, int W, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * whole-network forward
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Packed parameters + structure of a Q-RCAN (attention_manipulators/architectures.py:246-316).
+ * Conv indexing of the trunk arrays: block (g,b) conv j -> g*(2*n_blocks+1) + 2*b + j; group tail conv ->
+ * g*(2*n_blocks+1) + 2*n_blocks; trunk tail conv (final_body) -> n_groups*(2*n_blocks+1);
+ * then the upsampler slices: stage t, sub-pixel s -> n_trunk + t*r*r + s.                                  */
+typedef struct dfir_qrcan_net {
+  int n_groups, n_blocks, n_feats; /* n_feats must be 64 */
+  int scale;                        /* 2, 3, 4, 8 */
+  int style;                        /* DFIR_STYLE_* */
+  int reduced;                      /* n_feats / reduction */
+  int num_metadata;                 /* M: size of the metadata vector the FC layers were built for */
+  int attr_size;                    /* A: size of the `attributes` rows passed at run time (64 for modulate) */
+  int meta_hidden;                  /* hidden width of ParaCALayer (n_feats/2 for M <= 15) */
+  int in_feats, out_feats;          /* 3, 3 */
+  const int* q_enabled;             /* device int32 [n_groups*n_blocks]: block owns a q_node */
+  int any_q;                        /* host-side: any block has a q_node */
+  int chunk_images;                 /* images per L2-resident pass; 0 = choose automatically */
+  /* tensor-core weights */
+  const void* conv_w_bf16;          /* [n_conv][9*64*128 B] */
+  const void* tail_w_bf16;          /* [9*16*128 B] */
+  /* CUDA-core weights (fp32 mode; may be NULL when only bf16 mode is used) */
+  const float* conv_w_f32;          /* trunk: [n_trunk][9][64][64]; then the unsliced upsampler convs */
+  const float* up_w_f32;            /* [n_up][9][64][r*r*64] */
+  const float* tail_w_f32;          /* [9][64][out_feats] */
+  const float* head_w_f32;          /* [9][in_feats][64] */
+  /* biases, fp32 */
+  const float* conv_b;              /* [n_conv][64] (upsampler slices permuted like the weights) */
+  const float* up_b;                /* [n_up][r*r*64] in original channel order (fp32 mode) */
+  const float* tail_b;              /* [16] (zero padded) */
+  const float* head_b;              /* [64] */
+  /* attention parameters */
+  const float* ca_blob;             /* [n_groups*n_blocks][ca_stride] */
+  int ca_stride;
+  const float* meta_w1; const float* meta_b1; const float* meta_w2; const float* meta_b2;
+} dfir_qrcan_net;
+
+size_t dfir_qrcan_workspace_bytes(const dfir_qrcan_net* net, int B, int H, int W, int precision);
+
+/* QRCAN.forward(x, metadata) (attention_manipulators/architectures.py:309-316).
+ *   x_nchw fp32 [B][3][H][W]; attributes fp32 [B][attr_size] (the (B,M,1,1) tensor of QModel.generate_channels);
+ *   out_nchw fp32 [B][3][scale*H][scale*W].  workspace >= dfir_qrcan_workspace_bytes(). */
+int dfir_qrcan_forward(const dfir_qrcan_net* net, const float* x_nchw, const float* attributes, float* out_nchw,
+                       int B, int H, int W, int precision, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFIR_H_ */

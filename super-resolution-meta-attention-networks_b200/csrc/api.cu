@@ -1,0 +1,368 @@
+// C ABI of libdfir_b200.so (declared in include/dfir.h) and the whole-network forward schedules.
+#include "kernels.h"
+
+#include <algorithm>
+
+using namespace dfir;
+
+namespace {
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+struct Carver {
+  uint8_t* base;
+  size_t off;
+  explicit Carver(void* p) : base(reinterpret_cast<uint8_t*>(p)), off(0) {}
+  template <typename T>
+  T* take(size_t bytes) {
+    T* r = reinterpret_cast<T*>(base == nullptr ? nullptr : base + off);
+    off += align256(bytes);
+    return r;
+  }
+};
+
+int up_stages(int scale, int* r) {
+  if (scale == 3) { *r = 3; return 1; }
+  if (scale == 2) { *r = 2; return 1; }
+  if (scale == 4) { *r = 2; return 2; }
+  if (scale == 8) { *r = 2; return 3; }
+  *r = 0;
+  return -1;
+}
+
+// images per pass so that the block-level working set stays L2 resident and the row count fills the SMs
+int auto_chunk(int B, int H, int W, int precision) {
+  const long long px = static_cast<long long>(H) * W;
+  const long long hot_per_px = precision == DFIR_PREC_BF16_TC ? 640 : 1024;
+  long long c = (72ll << 20) / std::max<long long>(1, px * hot_per_px);
+  if (c < 1) c = 1;
+  if (c > B) c = B;
+  return static_cast<int>(c);
+}
+
+struct QrcanWs {
+  float *Hh, *XA, *XB, *pool, *sq;
+  __nv_bfloat16 *Hbf, *XAbf, *XBbf, *T, *R;
+  float *T32, *R32;
+  void* U[3];
+  size_t total;
+};
+
+QrcanWs carve_qrcan(const dfir_qrcan_net* n, int B, int Bc, int H, int W, int precision, void* ws) {
+  Carver c(ws);
+  QrcanWs w{};
+  const size_t px = static_cast<size_t>(Bc) * H * W;
+  const int C = n->n_feats;
+  w.Hh = c.take<float>(px * C * 4);
+  w.XA = c.take<float>(px * C * 4);
+  w.XB = c.take<float>(px * C * 4);
+  const int nseg = (W + 127) / 128;
+  w.pool = c.take<float>(static_cast<size_t>(Bc) * nseg * H * C * 4);
+  w.sq = c.take<float>(static_cast<size_t>(n->n_groups) * n->n_blocks * B * C * 4);
+  int r = 0;
+  const int nup = up_stages(n->scale, &r);
+  if (precision == DFIR_PREC_BF16_TC) {
+    w.Hbf = c.take<__nv_bfloat16>(px * C * 2);
+    w.XAbf = c.take<__nv_bfloat16>(px * C * 2);
+    w.XBbf = c.take<__nv_bfloat16>(px * C * 2);
+    w.T = c.take<__nv_bfloat16>(px * C * 2);
+    w.R = c.take<__nv_bfloat16>(px * C * 2);
+    size_t f = 1;
+    for (int t = 0; t < nup; ++t) {
+      f *= static_cast<size_t>(r) * r;
+      w.U[t] = c.take<uint8_t>(px * f * C * 2);
+    }
+  } else {
+    w.T32 = c.take<float>(px * C * 4);
+    w.R32 = c.take<float>(px * C * 4);
+    size_t f = 1;
+    for (int t = 0; t < nup; ++t) {
+      f *= static_cast<size_t>(r) * r;
+      w.U[t] = c.take<uint8_t>(px * f * C * 4);
+    }
+  }
+  w.total = c.off;
+  return w;
+}
+
+#define DFIR_TRY(expr)            \
+  do {                            \
+    int rc__ = (expr);            \
+    if (rc__ != DFIR_OK) return rc__; \
+  } while (0)
+
+AttnParams make_ap(const dfir_qrcan_net* n, int blk) {
+  AttnParams ap{};
+  ap.style = n->style;
+  ap.C = n->n_feats;
+  ap.R = n->reduced;
+  ap.M = n->num_metadata;
+  ap.A = n->attr_size;
+  ap.w[0] = n->ca_blob + static_cast<size_t>(blk) * n->ca_stride;
+  return ap;
+}
+
+int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* attr, float* out, int B, int Bc, int b0,
+                       int H, int W, const QrcanWs& w, int num_sms, cudaStream_t st) {
+  const int C = 64;
+  const int nb = n->n_blocks, ng = n->n_groups;
+  const int per_group = 2 * nb + 1;
+  const int n_trunk = ng * per_group + 1;
+  const size_t wbytes = 9 * 64 * 128;
+  const uint8_t* cw = reinterpret_cast<const uint8_t*>(n->conv_w_bf16);
+  const long long pixB = C * 2, rowB = static_cast<long long>(W) * C * 2, imgB = rowB * H;
+  const int nseg = (W + 127) / 128;
+
+  DFIR_TRY(head_conv(x + static_cast<size_t>(b0) * n->in_feats * H * W, n->head_w_f32, n->head_b, w.Hh, w.Hbf, Bc,
+                     n->in_feats, H, W, C, st));
+
+  auto conv = [&](const void* in, int widx, int epi, void* obf, const float* skip, float* o32) {
+    ConvTcDesc d{};
+    d.B = Bc; d.H = H; d.W = W; d.cin_total = 64; d.cin_off = 0; d.cout = 64; d.epi = epi; d.desc_mode = 0;
+    d.num_sms = num_sms;
+    d.in_bf16 = in; d.wpacked = cw + static_cast<size_t>(widx) * wbytes; d.bias = n->conv_b + static_cast<size_t>(widx) * 64;
+    d.out_bf16 = obf; d.out_pix_stride = pixB; d.out_row_stride = rowB; d.out_img_stride = imgB;
+    d.skip_f32 = skip; d.out_f32 = o32; d.pool_rows = w.pool;
+    return conv3x3_c64_tc(d, st);
+  };
+
+  for (int g = 0; g < ng; ++g) {
+    const float* skip32 = g == 0 ? w.Hh : w.XA;
+    const __nv_bfloat16* gin = g == 0 ? w.Hbf : w.XAbf;
+    for (int b = 0; b < nb; ++b) {
+      const int blk = g * nb + b;
+      const void* cin = b == 0 ? static_cast<const void*>(gin) : static_cast<const void*>(w.XBbf);
+      DFIR_TRY(conv(cin, g * per_group + 2 * b, EPI_BIAS_RELU, w.T, nullptr, nullptr));
+      DFIR_TRY(conv(w.T, g * per_group + 2 * b + 1, n->style == DFIR_STYLE_NONE ? EPI_BIAS : EPI_BIAS_POOL, w.R,
+                    nullptr, nullptr));
+      const float* xin = b == 0 ? skip32 : w.XB;
+      const float* sq = n->any_q ? w.sq + (static_cast<size_t>(blk) * B + b0) * C : nullptr;
+      DFIR_TRY(scale_residual(w.R, 1, xin, w.pool, nseg * H, make_ap(n, blk), attr + static_cast<size_t>(b0) * n->attr_size,
+                              sq, 1.f, w.XB, w.XBbf, Bc, H, W, C, st));
+    }
+    const void* cin = nb == 0 ? static_cast<const void*>(gin) : static_cast<const void*>(w.XBbf);
+    DFIR_TRY(conv(cin, g * per_group + 2 * nb, EPI_BIAS_SKIP, w.XAbf, skip32, w.XA));
+  }
+  {
+    const void* cin = ng == 0 ? static_cast<const void*>(w.Hbf) : static_cast<const void*>(w.XAbf);
+    DFIR_TRY(conv(cin, ng * per_group, EPI_BIAS_SKIP, w.XBbf, w.Hh, nullptr));
+  }
+  // upsampler: conv C -> r*r*C with PixelShuffle(r) folded into the TMA store strides
+  int r = 0;
+  const int nup = up_stages(n->scale, &r);
+  const void* cur = w.XBbf;
+  int h = H, wd = W;
+  for (int t = 0; t < nup; ++t) {
+    uint8_t* U = reinterpret_cast<uint8_t*>(w.U[t]);
+    const long long oW = static_cast<long long>(wd) * r, oH = static_cast<long long>(h) * r;
+    for (int s = 0; s < r * r; ++s) {
+      const int i = s / r, j = s % r;
+      ConvTcDesc d{};
+      const int widx = n_trunk + t * r * r + s;
+      d.B = Bc; d.H = h; d.W = wd; d.cin_total = 64; d.cin_off = 0; d.cout = 64; d.epi = EPI_BIAS; d.num_sms = num_sms;
+      d.in_bf16 = cur; d.wpacked = cw + static_cast<size_t>(widx) * wbytes; d.bias = n->conv_b + static_cast<size_t>(widx) * 64;
+      d.out_bf16 = U + (static_cast<long long>(i) * oW + j) * C * 2;
+      d.out_pix_stride = static_cast<long long>(r) * C * 2;
+      d.out_row_stride = static_cast<long long>(r) * oW * C * 2;
+      d.out_img_stride = oH * oW * C * 2;
+      DFIR_TRY(conv3x3_c64_tc(d, st));
+    }
+    cur = U;
+    h *= r;
+    wd *= r;
+  }
+  {
+    ConvTcDesc d{};
+    d.B = Bc; d.H = h; d.W = wd; d.cin_total = 64; d.cin_off = 0; d.cout = n->out_feats; d.epi = EPI_TAIL_NCHW;
+    d.num_sms = num_sms;
+    d.in_bf16 = cur; d.wpacked = n->tail_w_bf16; d.bias = n->tail_b;
+    d.out_f32 = out + static_cast<size_t>(b0) * n->out_feats * h * wd;
+    DFIR_TRY(conv3x3_c64_tc(d, st));
+  }
+  return DFIR_OK;
+}
+
+int qrcan_forward_f32(const dfir_qrcan_net* n, const float* x, const float* attr, float* out, int B, int Bc, int b0,
+                      int H, int W, const QrcanWs& w, cudaStream_t st) {
+  const int C = n->n_feats;
+  const int nb = n->n_blocks, ng = n->n_groups;
+  const int per_group = 2 * nb + 1;
+  const size_t wsz = static_cast<size_t>(9) * C * C;
+  DFIR_TRY(head_conv(x + static_cast<size_t>(b0) * n->in_feats * H * W, n->head_w_f32, n->head_b, w.Hh, nullptr, Bc,
+                     n->in_feats, H, W, C, st));
+  auto conv = [&](const float* in, int widx, int relu, const float* skip, float* o) {
+    return conv3x3_f32(in, n->conv_w_f32 + widx * wsz, n->conv_b + static_cast<size_t>(widx) * C, skip, o, Bc, H, W, C,
+                       C, relu, 1, 0, st);
+  };
+  for (int g = 0; g < ng; ++g) {
+    const float* skip32 = g == 0 ? w.Hh : w.XA;
+    for (int b = 0; b < nb; ++b) {
+      const int blk = g * nb + b;
+      const float* cin = b == 0 ? skip32 : w.XB;
+      DFIR_TRY(conv(cin, g * per_group + 2 * b, 1, nullptr, w.T32));
+      DFIR_TRY(conv(w.T32, g * per_group + 2 * b + 1, 0, nullptr, w.R32));
+      if (n->style != DFIR_STYLE_NONE) DFIR_TRY(pool_rows_f32(w.R32, w.pool, Bc, H, W, C, st));
+      const float* sq = n->any_q ? w.sq + (static_cast<size_t>(blk) * B + b0) * C : nullptr;
+      DFIR_TRY(scale_residual(w.R32, 0, cin, w.pool, H, make_ap(n, blk), attr + static_cast<size_t>(b0) * n->attr_size,
+                              sq, 1.f, w.XB, nullptr, Bc, H, W, C, st));
+    }
+    const float* cin = nb == 0 ? skip32 : w.XB;
+    // out = conv(cin) + skip32 ; written to T32 first because XA may be the skip being read
+    DFIR_TRY(conv(cin, g * per_group + 2 * nb, 0, skip32, w.T32));
+    DFIR_TRY(cudaMemcpyAsync(w.XA, w.T32, static_cast<size_t>(Bc) * H * W * C * 4, cudaMemcpyDeviceToDevice, st) ==
+                     cudaSuccess
+                 ? DFIR_OK
+                 : DFIR_ERR_CUDA);
+  }
+  DFIR_TRY(conv(ng == 0 ? w.Hh : w.XA, ng * per_group, 0, w.Hh, w.XB));
+  int r = 0;
+  const int nup = up_stages(n->scale, &r);
+  const float* cur = w.XB;
+  int h = H, wd = W;
+  size_t woff = 0, boff = 0;
+  for (int t = 0; t < nup; ++t) {
+    float* U = reinterpret_cast<float*>(w.U[t]);
+    const int co = r * r * C;
+    DFIR_TRY(conv3x3_f32(cur, n->up_w_f32 + woff, n->up_b + boff, nullptr, U, Bc, h, wd, C, co, 0, r, 0, st));
+    woff += static_cast<size_t>(9) * C * co;
+    boff += co;
+    cur = U;
+    h *= r;
+    wd *= r;
+  }
+  DFIR_TRY(conv3x3_f32(cur, n->tail_w_f32, n->tail_b, nullptr, out + static_cast<size_t>(b0) * n->out_feats * h * wd,
+                       Bc, h, wd, C, n->out_feats, 0, 1, 1, st));
+  return DFIR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dfir_version(void) { return "dfir-b200 0.1 (abi 1, sm_100a)"; }
+
+const char* dfir_error_string(int code) {
+  switch (code) {
+    case DFIR_OK: return "ok";
+    case DFIR_ERR_ARG: return "invalid argument or unsupported configuration";
+    case DFIR_ERR_CUDA: return "CUDA runtime error";
+    case DFIR_ERR_DRIVER: return "cuTensorMapEncodeTiled driver entry point unavailable";
+    case DFIR_ERR_TMAP: return "tensor map encoding failed";
+    case DFIR_ERR_WORKSPACE: return "workspace too small";
+    case DFIR_ERR_ARCH: return "device is not compute capability 10.x (sm_100a required)";
+    default: return "unknown error";
+  }
+}
+
+int dfir_check_device(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return DFIR_ERR_CUDA;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return DFIR_ERR_CUDA;
+  return major == 10 ? DFIR_OK : DFIR_ERR_ARCH;
+}
+
+int dfir_pack_conv3x3_bf16(const float* w_oihw, void* out, int cout, int cin, int nt_rows, int co_begin,
+                           int co_stride, void* stream) {
+  return pack_conv_weights_bf16(w_oihw, out, cout, cin, nt_rows, co_begin, co_stride, S(stream));
+}
+
+int dfir_pack_conv3x3_f32(const float* w_oihw, float* out, int cout, int cin, void* stream) {
+  return pack_conv_weights_f32(w_oihw, out, cout, cin, S(stream));
+}
+
+int dfir_conv3x3_c64(const void* in_bf16, int cin_total, int cin_off, const void* wpacked, const float* bias, int B,
+                     int H, int W, int epi, int cout, void* out_bf16, long long out_pix_stride,
+                     long long out_row_stride, long long out_img_stride, const float* skip_f32, float* out_f32,
+                     float* pool_rows, int desc_mode, void* stream) {
+  ConvTcDesc d{};
+  d.B = B; d.H = H; d.W = W; d.cin_total = cin_total; d.cin_off = cin_off; d.cout = cout; d.epi = epi;
+  d.desc_mode = desc_mode; d.num_sms = 0;
+  d.in_bf16 = in_bf16; d.wpacked = wpacked; d.bias = bias; d.out_bf16 = out_bf16;
+  d.out_pix_stride = out_pix_stride; d.out_row_stride = out_row_stride; d.out_img_stride = out_img_stride;
+  d.skip_f32 = skip_f32; d.out_f32 = out_f32; d.pool_rows = pool_rows;
+  if (epi == EPI_BIAS_POOL && pool_rows == nullptr) return DFIR_ERR_ARG;
+  if (epi == EPI_BIAS_SKIP && skip_f32 == nullptr) return DFIR_ERR_ARG;
+  if (epi == EPI_TAIL_NCHW && (out_f32 == nullptr || cout > 16)) return DFIR_ERR_ARG;
+  if (epi != EPI_TAIL_NCHW && out_bf16 == nullptr) return DFIR_ERR_ARG;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return DFIR_ERR_CUDA;
+  d.num_sms = sms;
+  return conv3x3_c64_tc(d, S(stream));
+}
+
+int dfir_conv3x3_f32(const float* in, const float* w_packed, const float* bias, const float* skip, float* out, int B,
+                     int H, int W, int Cin, int Cout, int relu, int ps_r, int out_nchw, void* stream) {
+  return conv3x3_f32(in, w_packed, bias, skip, out, B, H, W, Cin, Cout, relu, ps_r, out_nchw, S(stream));
+}
+
+int dfir_head_conv(const float* x_nchw, const float* w_packed, const float* bias, float* out_f32, void* out_bf16,
+                   int B, int Cin, int H, int W, int Cout, void* stream) {
+  return head_conv(x_nchw, w_packed, bias, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), B, Cin, H, W, Cout,
+                   S(stream));
+}
+
+int dfir_meta_attention(const float* meta, const float* w1, const float* b1, const float* w2, const float* b2,
+                        float* out, int nblk, int B, int M, int Hid, int C, int relu, const int* blk_enabled,
+                        void* stream) {
+  return meta_attention(meta, w1, b1, w2, b2, out, nblk, B, M, Hid, C, relu, blk_enabled, S(stream));
+}
+
+int dfir_ca_scale_residual(const void* r, int r_is_bf16, const float* x_in, const float* pool_rows, int pool_nrows,
+                           int style, const float* ca_params, int C, int R, int M, int A, const float* attributes,
+                           const float* sq, float res_scale, float* x_out, void* x_out_bf16, int B, int H, int W,
+                           void* stream) {
+  AttnParams ap{};
+  ap.style = style; ap.C = C; ap.R = R; ap.M = M; ap.A = A; ap.w[0] = ca_params;
+  if (style != DFIR_STYLE_NONE && (pool_rows == nullptr || ca_params == nullptr)) return DFIR_ERR_ARG;
+  return scale_residual(r, r_is_bf16, x_in, pool_rows, pool_nrows, ap, attributes, sq, res_scale, x_out,
+                        reinterpret_cast<__nv_bfloat16*>(x_out_bf16), B, H, W, C, S(stream));
+}
+
+int dfir_pool_rows_f32(const float* in, float* pool_rows, int B, int H, int W, int C, void* stream) {
+  return pool_rows_f32(in, pool_rows, B, H, W, C, S(stream));
+}
+
+size_t dfir_qrcan_workspace_bytes(const dfir_qrcan_net* net, int B, int H, int W, int precision) {
+  if (net == nullptr || B <= 0 || H <= 0 || W <= 0) return 0;
+  const int Bc = net->chunk_images > 0 ? std::min(net->chunk_images, B) : auto_chunk(B, H, W, precision);
+  return carve_qrcan(net, B, Bc, H, W, precision, nullptr).total;
+}
+
+int dfir_qrcan_forward(const dfir_qrcan_net* net, const float* x_nchw, const float* attributes, float* out_nchw, int B,
+                       int H, int W, int precision, void* workspace, size_t workspace_bytes, void* stream) {
+  if (net == nullptr || x_nchw == nullptr || out_nchw == nullptr || attributes == nullptr) return DFIR_ERR_ARG;
+  if (B <= 0 || H <= 0 || W <= 0) return DFIR_ERR_ARG;
+  int r = 0;
+  if (up_stages(net->scale, &r) < 0) return DFIR_ERR_ARG;
+  if (precision == DFIR_PREC_BF16_TC && net->n_feats != 64) return DFIR_ERR_ARG;
+  if (net->n_feats % 8 != 0 || net->n_feats > 256 || 256 % net->n_feats != 0) return DFIR_ERR_ARG;
+  if (precision != DFIR_PREC_BF16_TC && precision != DFIR_PREC_FP32_SIMT) return DFIR_ERR_ARG;
+  DFIR_TRY(dfir_check_device());
+  const int Bc = net->chunk_images > 0 ? std::min(net->chunk_images, B) : auto_chunk(B, H, W, precision);
+  QrcanWs w = carve_qrcan(net, B, Bc, H, W, precision, workspace);
+  if (workspace == nullptr || w.total > workspace_bytes) return DFIR_ERR_WORKSPACE;
+  cudaStream_t st = S(stream);
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return DFIR_ERR_CUDA;
+  if (net->any_q) {
+    DFIR_TRY(meta_attention(attributes, net->meta_w1, net->meta_b1, net->meta_w2, net->meta_b2, w.sq,
+                            net->n_groups * net->n_blocks, B, net->num_metadata, net->meta_hidden, net->n_feats, 1,
+                            net->q_enabled, st));
+  }
+  for (int b0 = 0; b0 < B; b0 += Bc) {
+    const int bc = std::min(Bc, B - b0);
+    if (precision == DFIR_PREC_BF16_TC)
+      DFIR_TRY(qrcan_forward_bf16(net, x_nchw, attributes, out_nchw, B, bc, b0, H, W, w, sms, st));
+    else
+      DFIR_TRY(qrcan_forward_f32(net, x_nchw, attributes, out_nchw, B, bc, b0, H, W, w, st));
+  }
+  return DFIR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// Internal declarations shared by the CUDA translation units (not part of the public C ABI — that is
+// include/dfir.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/dfir.h"
+
+namespace dfir {
+
+// epilogues of the tensor-core conv
+enum : int {
+  EPI_BIAS = 0,       // out_bf16 = acc + b
+  EPI_BIAS_RELU = 1,  // out_bf16 = relu(acc + b)                      (RCAB conv1, architectures.py:155-160)
+  EPI_BIAS_POOL = 2,  // out_bf16 = acc + b ; per-row channel sums     (RCAB conv2 + CA avg-pool, :107)
+  EPI_BIAS_SKIP = 3,  // out_f32 = acc + b + skip ; out_bf16 = bf16()  (group / trunk tail conv + `res += x`, :231-232)
+  EPI_TAIL_NCHW = 4,  // out_f32 NCHW, cout<=16 real channels          (tail conv 64 -> 3, :303)
+};
+
+struct ConvTcArgs {  // kernel argument block
+  int B, H, W, nseg, cin_off, cout, desc_mode;
+  const void* wpacked;
+  const float* bias;
+  const float* skip_f32;
+  float* out_f32;
+  float* pool_rows;
+};
+
+struct ConvTcDesc {  // host-side launch description
+  int B, H, W;
+  int cin_total, cin_off;  // channels of the input tensor / first channel of the 64-wide slice consumed
+  int cout;                // real output channels (tail only)
+  int epi;
+  int desc_mode;           // 0: base_offset = swizzle phase of the dx-shifted view (default); 1: base_offset 0
+  int num_sms;
+  const void* in_bf16;
+  const void* wpacked;
+  const float* bias;
+  void* out_bf16;
+  long long out_pix_stride, out_row_stride, out_img_stride;  // bytes (pixel-shuffle folds into these)
+  const float* skip_f32;
+  float* out_f32;
+  float* pool_rows;
+};
+
+int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream);
+
+// ---- SIMT kernels (simt.cu)
+struct AttnParams {  // one RCAB's channel-attention parameters (fp32, device pointers into the packed blob)
+  int style;         // DFIR_STYLE_*
+  int C, R, M, A;    // channels, reduced channels, metadata size, attributes size (64 for modulate)
+  const float* w[8]; // style-dependent list (see attn_vector() in simt.cu)
+};
+
+int pack_conv_weights_bf16(const float* w_oihw, void* out, int cout, int cin, int nt_rows, int co_begin,
+                           int co_stride, cudaStream_t s);
+int pack_conv_weights_f32(const float* w_oihw, float* out, int cout, int cin, cudaStream_t s);
+int head_conv(const float* x_nchw, const float* w_packed, const float* bias, float* out_f32, __nv_bfloat16* out_bf16,
+              int B, int Cin, int H, int W, int Cout, cudaStream_t s);
+int conv3x3_f32(const float* in, const float* w_packed, const float* bias, const float* skip, float* out, int B, int H,
+                int W, int Cin, int Cout, int relu, int ps_r, int out_nchw, cudaStream_t s);
+int pool_rows_f32(const float* in, float* pool_rows, int B, int H, int W, int C, cudaStream_t s);
+int meta_attention(const float* meta, const float* w1, const float* b1, const float* w2, const float* b2, float* out,
+                   int nblk, int B, int M, int Hid, int C, int relu, const int* blk_enabled, cudaStream_t s);
+int scale_residual(const void* r, int r_is_bf16, const float* x_in, const float* pool_rows, int pool_nrows,
+                   const AttnParams& ap, const float* attributes, const float* sq, float res_scale, float* x_out,
+                   __nv_bfloat16* x_out_bf16, int B, int H, int W, int C, cudaStream_t s);
+int nchw_to_nhwc_bf16(const float* in, __nv_bfloat16* out, int B, int C, int H, int W, cudaStream_t s);
+int f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t s);
+
+}  // namespace dfir

@@ -1,0 +1,470 @@
+// CUDA-core kernels of the Deep-FIR hot path: weight packing, head conv, the fp32 parity-mode conv, the
+// attention-vector kernels and the fused channel-scale + residual streamer.  These are the HBM / latency
+// bound pieces: they are written for coalesced 16-byte accesses, not tensor cores.
+#include "kernels.h"
+
+namespace dfir {
+
+namespace {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// ------------------------------------------------------------------------------------------------
+// weight packing
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_conv_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout, int cin,
+                                      int nt_rows, int co_begin, int co_stride) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = 9 * nt_rows * 64;
+  if (idx >= total) return;
+  const int ci = idx % 64;
+  const int n = (idx / 64) % nt_rows;
+  const int t = idx / (64 * nt_rows);
+  const int co = co_begin + n * co_stride;
+  float v = 0.f;
+  if (co < cout && ci < cin) v = w[(static_cast<size_t>(co) * cin + ci) * 9 + t];
+  // K-major SWIZZLE_128B: row n = 128 B, 16-byte chunk index XORed with (n & 7)
+  const int chunk = (ci >> 3) ^ (n & 7);
+  out[static_cast<size_t>(t) * nt_rows * 64 + n * 64 + chunk * 8 + (ci & 7)] = __float2bfloat16_rn(v);
+}
+
+__global__ void pack_conv_f32_kernel(const float* __restrict__ w, float* __restrict__ out, int cout, int cin) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = 9 * cin * cout;
+  if (idx >= total) return;
+  const int co = idx % cout;
+  const int ci = (idx / cout) % cin;
+  const int t = idx / (cout * cin);
+  out[idx] = w[(static_cast<size_t>(co) * cin + ci) * 9 + t];
+}
+
+// ------------------------------------------------------------------------------------------------
+// head conv: NCHW fp32 image (Cin small) -> NHWC features.  8 threads per pixel, 8 output channels each.
+// ------------------------------------------------------------------------------------------------
+__global__ void head_conv_kernel(const float* __restrict__ x, const float* __restrict__ wp,
+                                 const float* __restrict__ bias, float* __restrict__ out_f32,
+                                 __nv_bfloat16* __restrict__ out_bf16, int B, int Cin, int H, int W, int Cout) {
+  extern __shared__ float ws[];  // [9*Cin][Cout]
+  const int nw = 9 * Cin * Cout;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) ws[i] = wp[i];
+  __syncthreads();
+  const int oct_per_pix = Cout / 8;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long npix = static_cast<long long>(B) * H * W;
+  const long long pix = gid / oct_per_pix;
+  const int oc = static_cast<int>(gid % oct_per_pix) * 8;
+  if (pix >= npix) return;
+  const int xw = static_cast<int>(pix % W);
+  const int y = static_cast<int>((pix / W) % H);
+  const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = bias[oc + i];
+  for (int dy = 0; dy < 3; ++dy) {
+    const int yy = y + dy - 1;
+    if (yy < 0 || yy >= H) continue;
+    for (int dx = 0; dx < 3; ++dx) {
+      const int xx = xw + dx - 1;
+      if (xx < 0 || xx >= W) continue;
+      for (int ci = 0; ci < Cin; ++ci) {
+        const float v = x[((static_cast<size_t>(b) * Cin + ci) * H + yy) * W + xx];
+        const float* wr = ws + ((dy * 3 + dx) * Cin + ci) * Cout + oc;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(v, wr[i], acc[i]);
+      }
+    }
+  }
+  const size_t o = static_cast<size_t>(pix) * Cout + oc;
+  if (out_f32 != nullptr) {
+    *reinterpret_cast<float4*>(out_f32 + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(out_f32 + o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+  if (out_bf16 != nullptr) {
+    __align__(16) __nv_bfloat162 pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pk[i] = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
+    *reinterpret_cast<uint4*>(out_bf16 + o) = *reinterpret_cast<uint4*>(pk);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 parity-mode conv (CUDA cores): NHWC fp32, each thread = 4 consecutive pixels of a row x 8 output
+// channels.  Per (dy, 4 cin): 6 float4 input loads + 24 float4 weight loads feed 384 FMAs.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv3x3_f32_kernel(const float* __restrict__ in, const float* __restrict__ wp, const float* __restrict__ bias,
+                   const float* __restrict__ skip, float* __restrict__ out, int B, int H, int W, int Cin, int Cout,
+                   int relu, int ps_r, int out_nchw) {
+  const int n_oct = (Cout + 7) / 8;
+  const int quads_per_row = (W + 3) / 4;
+  const long long nquad = static_cast<long long>(B) * H * quads_per_row;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long quad = gid / n_oct;
+  const int oc = static_cast<int>(gid % n_oct) * 8;
+  if (quad >= nquad) return;
+  const int x0 = static_cast<int>(quad % quads_per_row) * 4;
+  const int y = static_cast<int>((quad / quads_per_row) % H);
+  const int b = static_cast<int>(quad / (static_cast<long long>(quads_per_row) * H));
+  const bool full_oct = (oc + 8 <= Cout) && (Cout % 4 == 0);
+
+  float acc[4][8];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[p][i] = (oc + i < Cout) ? bias[oc + i] : 0.f;
+
+  for (int dy = 0; dy < 3; ++dy) {
+    const int yy = y + dy - 1;
+    if (yy < 0 || yy >= H) continue;
+    const float* inrow = in + (static_cast<size_t>(b) * H + yy) * W * Cin;
+    for (int ci = 0; ci < Cin; ci += 4) {
+      float4 v[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int xx = x0 + j - 1;
+        v[j] = (xx >= 0 && xx < W) ? *reinterpret_cast<const float4*>(inrow + static_cast<size_t>(xx) * Cin + ci)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const float* wr = wp + (static_cast<size_t>(dy * 3 + dx) * Cin + ci + cc) * Cout + oc;
+          float w8[8];
+          if (full_oct) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wr);
+            const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
+            w8[0] = w0.x; w8[1] = w0.y; w8[2] = w0.z; w8[3] = w0.w;
+            w8[4] = w1.x; w8[5] = w1.y; w8[6] = w1.z; w8[7] = w1.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w8[i] = (oc + i < Cout) ? wr[i] : 0.f;
+          }
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float4 t = v[p + dx];
+            const float a = cc == 0 ? t.x : (cc == 1 ? t.y : (cc == 2 ? t.z : t.w));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[p][i] = fmaf(a, w8[i], acc[p][i]);
+          }
+        }
+      }
+    }
+  }
+
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int x = x0 + p;
+    if (x >= W) continue;
+    const size_t pix = (static_cast<size_t>(b) * H + y) * W + x;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = oc + i;
+      if (k >= Cout) continue;
+      float val = acc[p][i];
+      if (skip != nullptr) val += skip[pix * Cout + k];
+      if (relu) val = fmaxf(val, 0.f);
+      size_t o;
+      if (out_nchw) {
+        o = ((static_cast<size_t>(b) * Cout + k) * H + y) * W + x;
+      } else if (ps_r > 1) {
+        const int rr = ps_r * ps_r;
+        const int c = k / rr, ij = k % rr, ii = ij / ps_r, jj = ij % ps_r;
+        const int Co = Cout / rr;
+        o = ((static_cast<size_t>(b) * H * ps_r + (y * ps_r + ii)) * (static_cast<size_t>(W) * ps_r) + (x * ps_r + jj)) * Co + c;
+      } else {
+        o = pix * Cout + k;
+      }
+      out[o] = val;
+    }
+  }
+}
+
+// per-row channel sums, fp32 NHWC: one block per (b, y), thread c sums over x
+__global__ void pool_rows_f32_kernel(const float* __restrict__ in, float* __restrict__ pool_rows, int W, int C) {
+  const size_t row = blockIdx.x;
+  const float* p = in + row * W * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int x = 0; x < W; ++x) s += p[static_cast<size_t>(x) * C + c];
+    pool_rows[row * C + c] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// meta-attention vectors for all blocks in one launch: grid (nblk, B), block = C threads
+// ------------------------------------------------------------------------------------------------
+__global__ void meta_attention_kernel(const float* __restrict__ meta, const float* __restrict__ w1,
+                                      const float* __restrict__ b1, const float* __restrict__ w2,
+                                      const float* __restrict__ b2, float* __restrict__ out, int B, int M, int Hid,
+                                      int C, int relu, const int* __restrict__ blk_enabled) {
+  extern __shared__ float sh[];  // [M] meta, [Hid] hidden
+  float* m_s = sh;
+  float* h_s = sh + M;
+  const int blk = blockIdx.x;
+  const int b = blockIdx.y;
+  float* o = out + (static_cast<size_t>(blk) * B + b) * C;
+  if (blk_enabled != nullptr && blk_enabled[blk] == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) o[c] = 1.f;
+    return;
+  }
+  for (int i = threadIdx.x; i < M; i += blockDim.x) m_s[i] = meta[static_cast<size_t>(b) * M + i];
+  __syncthreads();
+  for (int h = threadIdx.x; h < Hid; h += blockDim.x) {
+    const float* wr = w1 + (static_cast<size_t>(blk) * Hid + h) * M;
+    float s = b1[static_cast<size_t>(blk) * Hid + h];
+    for (int i = 0; i < M; ++i) s = fmaf(wr[i], m_s[i], s);
+    h_s[h] = relu ? fmaxf(s, 0.f) : s;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float* wr = w2 + (static_cast<size_t>(blk) * C + c) * Hid;
+    float s = b2[static_cast<size_t>(blk) * C + c];
+    for (int h = 0; h < Hid; ++h) s = fmaf(wr[h], h_s[h], s);
+    o[c] = 1.f / (1.f + expf(-s));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// channel attention vector (all QCALayer styles) — executed redundantly by every CTA of the streamer for
+// its image: <= 74x32 + ... MACs, nothing compared with the pixels it then streams.
+//   y_s[C] : pooled means (in), s_s[C] : attention scale (out); tmp: >= C + A + 64 floats of scratch
+// parameter order inside `p` (fp32, contiguous):
+//   standard/modulate : W1[R][C]   b1[R]  W2[C][R]    b2[C]
+//   max_concat/softmax: W1[R][C+M] b1[R]  W2[C][R]    b2[C]
+//   mini_concat       : Wp[R][C]   bp[R]  W2[C][R+M]  b2[C]
+//   extended_attention: W1[C/2][C+M] b1 W2[C/4][C/2+M] b2 W3[R][C/4+M] b3 W4[C][R] b4
+// ------------------------------------------------------------------------------------------------
+__device__ void fc_layer(const float* __restrict__ w, const float* __restrict__ bias, const float* in_a, int na,
+                         const float* in_b, int nb, float* out, int nout, int act /*0 none,1 relu,2 sigmoid*/) {
+  for (int o = threadIdx.x; o < nout; o += blockDim.x) {
+    const float* wr = w + static_cast<size_t>(o) * (na + nb);
+    float s = bias[o];
+    for (int i = 0; i < na; ++i) s = fmaf(wr[i], in_a[i], s);
+    for (int i = 0; i < nb; ++i) s = fmaf(wr[na + i], in_b[i], s);
+    if (act == 1) s = fmaxf(s, 0.f);
+    if (act == 2) s = 1.f / (1.f + expf(-s));
+    out[o] = s;
+  }
+  __syncthreads();
+}
+
+__device__ void attn_vector(int style, const float* __restrict__ p, int C, int R, int M, const float* attr_s,
+                            const float* y_s, float* s_s, float* tmp) {
+  if (style == DFIR_STYLE_STANDARD || style == DFIR_STYLE_MODULATE) {
+    const float* W1 = p; const float* b1 = W1 + R * C; const float* W2 = b1 + R; const float* b2 = W2 + C * R;
+    fc_layer(W1, b1, y_s, C, nullptr, 0, tmp, R, 1);
+    fc_layer(W2, b2, tmp, R, nullptr, 0, s_s, C, 2);
+    if (style == DFIR_STYLE_MODULATE) {
+      for (int c = threadIdx.x; c < C; c += blockDim.x) s_s[c] *= attr_s[c];
+      __syncthreads();
+    }
+  } else if (style == DFIR_STYLE_MAX_CONCAT || style == DFIR_STYLE_SOFTMAX) {
+    const float* W1 = p; const float* b1 = W1 + R * (C + M); const float* W2 = b1 + R; const float* b2 = W2 + C * R;
+    fc_layer(W1, b1, y_s, C, attr_s, M, tmp, R, 1);
+    fc_layer(W2, b2, tmp, R, nullptr, 0, s_s, C, 2);
+    if (style == DFIR_STYLE_SOFTMAX) {
+      // softmax over the C channels applied after the sigmoid (architectures.py:100-101,119-121)
+      if (threadIdx.x == 0) {
+        float mx = -1e30f;
+        for (int c = 0; c < C; ++c) mx = fmaxf(mx, s_s[c]);
+        float sum = 0.f;
+        for (int c = 0; c < C; ++c) sum += expf(s_s[c] - mx);
+        tmp[0] = mx;
+        tmp[1] = sum;
+      }
+      __syncthreads();
+      const float mx = tmp[0], sum = tmp[1];
+      __syncthreads();
+      for (int c = threadIdx.x; c < C; c += blockDim.x) s_s[c] = expf(s_s[c] - mx) / sum;
+      __syncthreads();
+    }
+  } else if (style == DFIR_STYLE_MINI_CONCAT) {
+    const float* Wp = p; const float* bp = Wp + R * C; const float* W2 = bp + R; const float* b2 = W2 + C * (R + M);
+    fc_layer(Wp, bp, y_s, C, nullptr, 0, tmp, R, 0);
+    // conv_du = Sequential(ReLU, Conv, Sigmoid) applied to cat(pre, attributes): the ReLU hits both parts
+    for (int i = threadIdx.x; i < R + M; i += blockDim.x) {
+      const float v = i < R ? tmp[i] : attr_s[i - R];
+      tmp[64 + i] = fmaxf(v, 0.f);
+    }
+    __syncthreads();
+    fc_layer(W2, b2, tmp + 64, R + M, nullptr, 0, s_s, C, 2);
+  } else if (style == DFIR_STYLE_EXTENDED) {
+    const int c2 = C / 2, c4 = C / 4;
+    const float* W1 = p; const float* b1 = W1 + c2 * (C + M);
+    const float* W2 = b1 + c2; const float* b2 = W2 + c4 * (c2 + M);
+    const float* W3 = b2 + c4; const float* b3 = W3 + R * (c4 + M);
+    const float* W4 = b3 + R; const float* b4 = W4 + C * R;
+    float* t1 = tmp; float* t2 = tmp + c2; float* t3 = t2 + c4;
+    fc_layer(W1, b1, y_s, C, attr_s, M, t1, c2, 1);
+    fc_layer(W2, b2, t1, c2, attr_s, M, t2, c4, 1);
+    fc_layer(W3, b3, t2, c4, attr_s, M, t3, R, 1);
+    fc_layer(W4, b4, t3, R, nullptr, 0, s_s, C, 2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused: pool finalise -> attention vector -> x_out = r * s + x_in (fp32) (+ bf16 copy)
+// grid (ctas_per_image, B), 256 threads; each thread streams 8 channels of a pixel per iteration.
+// ------------------------------------------------------------------------------------------------
+template <bool R_BF16>
+__global__ void __launch_bounds__(256)
+scale_residual_kernel(const void* __restrict__ r_, const float* __restrict__ x_in,
+                      const float* __restrict__ pool_rows, int pool_nrows, AttnParams ap,
+                      const float* __restrict__ attributes, const float* __restrict__ sq, float res_scale,
+                      float* __restrict__ x_out, __nv_bfloat16* __restrict__ x_out_bf16, int HW, int C) {
+  __shared__ float y_s[256];
+  __shared__ float s_s[256];
+  __shared__ float attr_s[512];
+  __shared__ float tmp[4 * 256];
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x;
+
+  if (ap.style != DFIR_STYLE_NONE) {
+    // deterministic pooled mean: 256/C row groups, fixed-order combine
+    const int ngrp = 256 / C;
+    const int c = tid % C, grp = tid / C;
+    float s = 0.f;
+    if (grp < ngrp) {
+      const float* pr = pool_rows + static_cast<size_t>(b) * pool_nrows * C + c;
+      for (int row = grp; row < pool_nrows; row += ngrp) s += pr[static_cast<size_t>(row) * C];
+      tmp[grp * C + c] = s;
+    }
+    for (int i = tid; i < ap.A; i += 256) attr_s[i] = attributes[static_cast<size_t>(b) * ap.A + i];
+    __syncthreads();
+    if (tid < C) {
+      float t = 0.f;
+      for (int gI = 0; gI < ngrp; ++gI) t += tmp[gI * C + tid];
+      y_s[tid] = t / static_cast<float>(HW);
+    }
+    __syncthreads();
+    attn_vector(ap.style, ap.w[0], C, ap.R, ap.M, attr_s, y_s, s_s, tmp);
+    if (tid < C) s_s[tid] *= (sq != nullptr ? sq[static_cast<size_t>(b) * C + tid] : 1.f);
+  } else {
+    if (tid < C) s_s[tid] = res_scale * (sq != nullptr ? sq[static_cast<size_t>(b) * C + tid] : 1.f);
+  }
+  __syncthreads();
+
+  const int lanes_per_pix = C / 8;
+  const int c0 = (tid % lanes_per_pix) * 8;
+  float sc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sc[i] = s_s[c0 + i];
+
+  const size_t img_off = static_cast<size_t>(b) * HW * C;
+  const long long nvec = static_cast<long long>(HW) * lanes_per_pix;  // 8-channel vectors in this image
+  for (long long vi = static_cast<long long>(blockIdx.x) * 256 + tid; vi < nvec;
+       vi += static_cast<long long>(gridDim.x) * 256) {
+    const size_t e = img_off + static_cast<size_t>(vi) * 8;
+    float rv[8];
+    if (R_BF16) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(r_) + e);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        rv[2 * i] = f.x;
+        rv[2 * i + 1] = f.y;
+      }
+    } else {
+      const float4 a0 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(r_) + e);
+      const float4 a1 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(r_) + e + 4);
+      rv[0] = a0.x; rv[1] = a0.y; rv[2] = a0.z; rv[3] = a0.w;
+      rv[4] = a1.x; rv[5] = a1.y; rv[6] = a1.z; rv[7] = a1.w;
+    }
+    const float4 x0 = *reinterpret_cast<const float4*>(x_in + e);
+    const float4 x1 = *reinterpret_cast<const float4*>(x_in + e + 4);
+    float o[8];
+    o[0] = fmaf(rv[0], sc[0], x0.x); o[1] = fmaf(rv[1], sc[1], x0.y);
+    o[2] = fmaf(rv[2], sc[2], x0.z); o[3] = fmaf(rv[3], sc[3], x0.w);
+    o[4] = fmaf(rv[4], sc[4], x1.x); o[5] = fmaf(rv[5], sc[5], x1.y);
+    o[6] = fmaf(rv[6], sc[6], x1.z); o[7] = fmaf(rv[7], sc[7], x1.w);
+    *reinterpret_cast<float4*>(x_out + e) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(x_out + e + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    if (x_out_bf16 != nullptr) {
+      __align__(16) __nv_bfloat162 pk[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pk[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+      *reinterpret_cast<uint4*>(x_out_bf16 + e) = *reinterpret_cast<uint4*>(pk);
+    }
+  }
+}
+
+inline int ok_or_cuda() { return cudaGetLastError() == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA; }
+
+}  // namespace
+
+int pack_conv_weights_bf16(const float* w, void* out, int cout, int cin, int nt_rows, int co_begin, int co_stride,
+                           cudaStream_t s) {
+  if (cin > 64 || (nt_rows != 64 && nt_rows != 16)) return DFIR_ERR_ARG;
+  const int total = 9 * nt_rows * 64;
+  pack_conv_bf16_kernel<<<(total + 255) / 256, 256, 0, s>>>(w, reinterpret_cast<__nv_bfloat16*>(out), cout, cin,
+                                                            nt_rows, co_begin, co_stride);
+  return ok_or_cuda();
+}
+
+int pack_conv_weights_f32(const float* w, float* out, int cout, int cin, cudaStream_t s) {
+  const int total = 9 * cin * cout;
+  pack_conv_f32_kernel<<<(total + 255) / 256, 256, 0, s>>>(w, out, cout, cin);
+  return ok_or_cuda();
+}
+
+int head_conv(const float* x, const float* wp, const float* bias, float* out_f32, __nv_bfloat16* out_bf16, int B,
+              int Cin, int H, int W, int Cout, cudaStream_t s) {
+  if (Cout % 8 != 0 || 9 * Cin * Cout * 4 > 48 * 1024) return DFIR_ERR_ARG;
+  const long long nthreads = static_cast<long long>(B) * H * W * (Cout / 8);
+  if (nthreads == 0) return DFIR_OK;
+  head_conv_kernel<<<static_cast<unsigned>((nthreads + 255) / 256), 256, 9 * Cin * Cout * 4, s>>>(
+      x, wp, bias, out_f32, out_bf16, B, Cin, H, W, Cout);
+  return ok_or_cuda();
+}
+
+int conv3x3_f32(const float* in, const float* wp, const float* bias, const float* skip, float* out, int B, int H,
+                int W, int Cin, int Cout, int relu, int ps_r, int out_nchw, cudaStream_t s) {
+  if (Cin % 4 != 0) return DFIR_ERR_ARG;
+  if (ps_r > 1 && (Cout % (ps_r * ps_r) != 0 || skip != nullptr || out_nchw)) return DFIR_ERR_ARG;
+  const int n_oct = (Cout + 7) / 8;
+  const long long nthreads = static_cast<long long>(B) * H * ((W + 3) / 4) * n_oct;
+  if (nthreads == 0) return DFIR_OK;
+  conv3x3_f32_kernel<<<static_cast<unsigned>((nthreads + 255) / 256), 256, 0, s>>>(in, wp, bias, skip, out, B, H, W,
+                                                                                  Cin, Cout, relu, ps_r, out_nchw);
+  return ok_or_cuda();
+}
+
+int pool_rows_f32(const float* in, float* pool_rows, int B, int H, int W, int C, cudaStream_t s) {
+  if (B * H == 0) return DFIR_OK;
+  pool_rows_f32_kernel<<<B * H, C <= 256 ? C : 256, 0, s>>>(in, pool_rows, W, C);
+  return ok_or_cuda();
+}
+
+int meta_attention(const float* meta, const float* w1, const float* b1, const float* w2, const float* b2, float* out,
+                   int nblk, int B, int M, int Hid, int C, int relu, const int* blk_enabled, cudaStream_t s) {
+  if (nblk == 0 || B == 0) return DFIR_OK;
+  if ((M + Hid) * 4 > 48 * 1024) return DFIR_ERR_ARG;
+  dim3 grid(nblk, B);
+  meta_attention_kernel<<<grid, C <= 256 ? C : 256, (M + Hid) * 4, s>>>(meta, w1, b1, w2, b2, out, B, M, Hid, C, relu,
+                                                                       blk_enabled);
+  return ok_or_cuda();
+}
+
+int scale_residual(const void* r, int r_is_bf16, const float* x_in, const float* pool_rows, int pool_nrows,
+                   const AttnParams& ap, const float* attributes, const float* sq, float res_scale, float* x_out,
+                   __nv_bfloat16* x_out_bf16, int B, int H, int W, int C, cudaStream_t s) {
+  if (B == 0 || H * W == 0) return DFIR_OK;
+  if (C % 8 != 0 || C > 256 || 256 % C != 0 || ap.A > 512 || ap.M > 448) return DFIR_ERR_ARG;
+  const long long nvec = static_cast<long long>(H) * W * (C / 8);
+  long long per_img = (nvec + 256 * 8 - 1) / (256 * 8);
+  const long long cap = (296 + B - 1) / B;
+  if (per_img > cap) per_img = cap;
+  if (per_img < 1) per_img = 1;
+  dim3 grid(static_cast<unsigned>(per_img), B);
+  if (r_is_bf16)
+    scale_residual_kernel<true><<<grid, 256, 0, s>>>(r, x_in, pool_rows, pool_nrows, ap, attributes, sq, res_scale,
+                                                     x_out, x_out_bf16, H * W, C);
+  else
+    scale_residual_kernel<false><<<grid, 256, 0, s>>>(r, x_in, pool_rows, pool_nrows, ap, attributes, sq, res_scale,
+                                                      x_out, x_out_bf16, H * W, C);
+  return ok_or_cuda();
+}
+
+}  // namespace dfir

@@ -1,0 +1,357 @@
+"""Q-RCAN on the B200 path.
+
+``QRCAN`` keeps the reference's constructor signature, parameter names, shapes (OIHW fp32) and parameter
+registration order (``/root/reference/Code/SISR/models/attention_manipulators/architectures.py:246-316``)
+so checkpoints, optimizers and ``print_parameters`` are interchangeable — but its modules are only
+parameter containers.  ``forward`` hands the whole network to ``libdfir_b200.so`` (one C call that
+enqueues every kernel on the current CUDA stream).  The kernel-format weights (bf16 swizzled tiles,
+fp32 tap-major copies, attention blobs) are a derived cache keyed on the parameters' version counters;
+they are rebuilt after ``optimizer.step()`` / ``load_state_dict`` and never serialised.
+"""
+import ctypes as C
+import math
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import QrcanNet
+
+STYLES = {"standard": 1, "modulate": 2, "max_concat": 3, "softmax": 4, "mini_concat": 5, "extended_attention": 6}
+PRECISIONS = {"bf16": 0, "fp32": 1}
+
+
+def _conv3(cin, cout):
+    return nn.Conv2d(cin, cout, 3, padding=1, bias=True)
+
+
+def _fc(cin, cout):
+    return nn.Conv2d(cin, cout, 1, padding=0, bias=True)
+
+
+class MetaAttentionParams(nn.Module):
+    """Parameter container of the meta-attention layer (q_layer.py:4-43): FC stack on the metadata."""
+
+    def __init__(self, channels, num_metadata, nonlinearity=False, num_layers=2):
+        super().__init__()
+        widths = [num_metadata]
+        stack = []
+        for left in range(num_layers, 0, -1):
+            nxt = (channels - num_metadata) // left + num_metadata if num_metadata > 15 else channels // left
+            stack.append(_fc(widths[-1], nxt))
+            widths.append(nxt)
+            if nonlinearity and left != 1:
+                stack.append(nn.ReLU(inplace=True))
+        stack.append(nn.Sigmoid())
+        self.attribute_integrator = nn.Sequential(*stack)
+        self.widths = widths
+        self.nonlinearity = nonlinearity
+
+    def fcs(self):
+        return [m for m in self.attribute_integrator if isinstance(m, nn.Conv2d)]
+
+
+class ChannelAttentionParams(nn.Module):
+    """Parameter container of QCALayer (architectures.py:34-103), all six styles."""
+
+    def __init__(self, channel, style, reduction=16, num_metadata=1):
+        super().__init__()
+        if reduction < 16:
+            raise RuntimeError('Using an extreme channel attention reduction value')
+        if style not in STYLES:
+            raise NotImplementedError
+        self.style = style
+        red = channel // reduction
+        cin = channel if style in ("modulate", "mini_concat", "standard") else channel + num_metadata
+        if style in ("modulate", "max_concat", "softmax", "standard"):
+            self.conv_du = nn.Sequential(_fc(cin, red), nn.ReLU(inplace=True), _fc(red, channel), nn.Sigmoid())
+        elif style == "mini_concat":
+            self.pre_concat = _fc(cin, red)
+            self.conv_du = nn.Sequential(nn.ReLU(inplace=True), _fc(red + num_metadata, channel), nn.Sigmoid())
+        else:  # extended_attention
+            plan = [(cin, channel // 2), (channel // 2 + num_metadata, channel // 4),
+                    (channel // 4 + num_metadata, red)]
+            self.feature_convs = nn.ModuleList(
+                [nn.Sequential(_fc(i, o), nn.ReLU(inplace=True)) for i, o in plan])
+            self.final_conv = nn.Sequential(_fc(red, channel), nn.Sigmoid())
+
+    def flat_params(self):
+        """fp32 arrays in the order the kernels expect (csrc/simt.cu attn_vector)."""
+        if self.style in ("modulate", "max_concat", "softmax", "standard"):
+            mods = [self.conv_du[0], self.conv_du[2]]
+        elif self.style == "mini_concat":
+            mods = [self.pre_concat, self.conv_du[1]]
+        else:
+            mods = [s[0] for s in self.feature_convs] + [self.final_conv[0]]
+        out = []
+        for m in mods:
+            out += [m.weight.reshape(-1), m.bias.reshape(-1)]
+        return out
+
+
+class PixelAttentionParams(nn.Module):
+    def __init__(self, channel):
+        super().__init__()
+        self.pa = nn.Sequential(_fc(channel, channel // 8), nn.ReLU(inplace=True), _fc(channel // 8, 1), nn.Sigmoid())
+
+
+class QRCABParams(nn.Module):
+    """QRCAB (architectures.py:145-180).  Attribute assignment order = reference registration order."""
+
+    def __init__(self, n_feat, reduction, style, pa, q_layer, num_metadata):
+        super().__init__()
+        convs = [_conv3(n_feat, n_feat), nn.ReLU(True), _conv3(n_feat, n_feat)]
+        self.final_body = ChannelAttentionParams(n_feat, style, reduction, num_metadata)
+        self.pa = pa
+        self.q_layer = q_layer
+        if pa:
+            self.pa_node = PixelAttentionParams(n_feat)
+        if q_layer:
+            self.q_node = MetaAttentionParams(n_feat, num_metadata, nonlinearity=True)
+        self.body = nn.Sequential(*convs)
+
+
+class QResidualGroupParams(nn.Module):
+    def __init__(self, n_feat, reduction, n_resblocks, style, num_metadata, pa, q_layer, num_q_layers):
+        super().__init__()
+        blocks = [QRCABParams(n_feat, reduction, style, pa,
+                              q_layer if (num_q_layers is None or i < num_q_layers) else False, num_metadata)
+                  for i in range(n_resblocks)]
+        self.final_body = _conv3(n_feat, n_feat)
+        self.body = nn.Sequential(*blocks)
+
+
+class UpsamplerParams(nn.Sequential):
+    """Upsampler (advanced/common.py:20-45): conv C->r^2 C + PixelShuffle(r), repeated."""
+
+    def __init__(self, scale, n_feat):
+        mods = []
+        if scale & (scale - 1) == 0:
+            for _ in range(int(math.log(scale, 2))):
+                mods += [_conv3(n_feat, 4 * n_feat), nn.PixelShuffle(2)]
+        elif scale == 3:
+            mods += [_conv3(n_feat, 9 * n_feat), nn.PixelShuffle(3)]
+        else:
+            raise NotImplementedError
+        super().__init__(*mods)
+
+
+class QRCAN(nn.Module):
+    def __init__(self, n_resblocks=20, n_resgroups=10, n_feats=64, in_feats=3, out_feats=3, scale=4, reduction=16,
+                 res_scale=1.0, style='modulate', num_metadata=1, include_pixel_attention=False,
+                 selective_meta_blocks=None, num_q_layers_inner_residual=None, include_q_layer=False,
+                 precision='bf16', chunk_images=0, **kwargs):
+        super().__init__()
+        if precision not in PRECISIONS:
+            raise RuntimeError("precision must be 'bf16' or 'fp32'")
+        self.style = style
+        self.scale = scale
+        self.precision = precision
+        self.chunk_images = chunk_images
+        self.cfg = dict(n_resblocks=n_resblocks, n_resgroups=n_resgroups, n_feats=n_feats, in_feats=in_feats,
+                        out_feats=out_feats, scale=scale, reduction=reduction, num_metadata=num_metadata,
+                        include_pixel_attention=include_pixel_attention)
+        head = [_conv3(in_feats, n_feats)]
+        groups = []
+        for g in range(n_resgroups):
+            q = include_q_layer if (selective_meta_blocks is None or selective_meta_blocks[g]) else False
+            groups.append(QResidualGroupParams(n_feats, reduction, n_resblocks, style, num_metadata,
+                                               include_pixel_attention, q, num_q_layers_inner_residual))
+        self.final_body = _conv3(n_feats, n_feats)
+        tail = [UpsamplerParams(scale, n_feats), _conv3(n_feats, out_feats)]
+        self.head = nn.Sequential(*head)
+        self.body = nn.Sequential(*groups)
+        self.tail = nn.Sequential(*tail)
+        self._packed = None
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, metadata):
+        if not x.is_cuda:
+            raise RuntimeError("deepfir_b200.QRCAN runs on a CUDA (sm_100a) device only: there is no CPU path")
+        if self.cfg["include_pixel_attention"]:
+            raise NotImplementedError("pixel attention (include_pixel_attention) is not on the B200 path yet")
+        from . import ops  # registers torch.ops.dfir.*
+        packed = self.packed()
+        b = x.shape[0]
+        attr = metadata.reshape(b, -1).to(device=x.device, dtype=torch.float32).contiguous()
+        if attr.shape[1] != packed.attr_size:
+            raise RuntimeError("metadata has %d entries per image, network expects %d" % (attr.shape[1], packed.attr_size))
+        return torch.ops.dfir.qrcan_forward(x.to(torch.float32).contiguous(), attr, packed.handle,
+                                            PRECISIONS[self.precision])
+
+    def forensic(self, *args, **kwargs):
+        raise NotImplementedError("forensic analysis is outside the B200 hot path")
+
+    # ------------------------------------------------------------------ packing
+    def _param_versions(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def packed(self):
+        key = (self._param_versions(), self.precision, self.chunk_images)
+        if self._packed is None or self._packed.key != key:
+            if self._packed is not None:
+                self._packed.close()
+            self._packed = PackedQrcan(self, key)
+        return self._packed
+
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        return super()._apply(fn, *a, **k)
+
+
+_HANDLES = {}
+_NEXT = [1]
+
+
+class PackedQrcan:
+    """Kernel-format copy of a QRCAN's parameters + the `dfir_qrcan_net` descriptor."""
+
+    def __init__(self, net: QRCAN, key):
+        lib = _lib.load_library()
+        self.key = key
+        cfg = net.cfg
+        dev = net.final_body.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("QRCAN parameters must live on a CUDA device")
+        C_ = cfg["n_feats"]
+        ng, nb = cfg["n_resgroups"], cfg["n_resblocks"]
+        want_tc = net.precision == "bf16"
+        if want_tc and C_ != 64:
+            raise RuntimeError("the tensor-core path is specialised for n_feats = 64 (use precision='fp32')")
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.no_grad(), torch.cuda.device(dev):
+            trunk = []
+            for g in range(ng):
+                grp = net.body[g]
+                for b in range(nb):
+                    trunk += [grp.body[b].body[0], grp.body[b].body[2]]
+                trunk.append(grp.final_body)
+            trunk.append(net.final_body)
+            ups = [m for m in net.tail[0] if isinstance(m, nn.Conv2d)]
+            r = 3 if net.scale == 3 else 2
+            n_trunk = len(trunk)
+            n_conv = n_trunk + len(ups) * r * r
+            f32 = dict(device=dev, dtype=torch.float32)
+            self.keep = []  # tensors whose storage the descriptor points into
+
+            def keep(t):
+                self.keep.append(t)
+                return t
+
+            conv_b = keep(torch.zeros(n_conv, C_, **f32))
+            for i, m in enumerate(trunk):
+                conv_b[i] = m.bias
+            for t, m in enumerate(ups):
+                conv_b[n_trunk + t * r * r: n_trunk + (t + 1) * r * r] = m.bias.reshape(C_, r * r).t()
+            tail = net.tail[1]
+            tail_b = keep(torch.zeros(16, **f32))
+            tail_b[: tail.bias.numel()] = tail.bias
+            head = net.head[0]
+            head_w = keep(torch.empty(9 * head.in_channels * C_, **f32))
+            _lib.check(lib.dfir_pack_conv3x3_f32(head.weight.contiguous().data_ptr(), head_w.data_ptr(), C_,
+                                                 head.in_channels, stream), "pack head")
+            head_b = keep(head.bias.detach().clone().contiguous())
+
+            conv_w_bf16 = tail_w_bf16 = conv_w_f32 = up_w_f32 = tail_w_f32 = up_b = None
+            if want_tc:
+                wbytes = 9 * 64 * 128
+                conv_w_bf16 = keep(torch.empty(n_conv * wbytes, device=dev, dtype=torch.uint8))
+                for i, m in enumerate(trunk):
+                    _lib.check(lib.dfir_pack_conv3x3_bf16(m.weight.contiguous().data_ptr(),
+                                                          conv_w_bf16.data_ptr() + i * wbytes, 64, 64, 64, 0, 1,
+                                                          stream), "pack trunk")
+                for t, m in enumerate(ups):
+                    w = m.weight.contiguous()
+                    for s in range(r * r):
+                        i = n_trunk + t * r * r + s
+                        _lib.check(lib.dfir_pack_conv3x3_bf16(w.data_ptr(), conv_w_bf16.data_ptr() + i * wbytes,
+                                                              w.shape[0], 64, 64, s, r * r, stream), "pack up")
+                tail_w_bf16 = keep(torch.empty(9 * 16 * 128, device=dev, dtype=torch.uint8))
+                _lib.check(lib.dfir_pack_conv3x3_bf16(tail.weight.contiguous().data_ptr(), tail_w_bf16.data_ptr(),
+                                                      tail.weight.shape[0], 64, 16, 0, 1, stream), "pack tail")
+            else:
+                wsz = 9 * C_ * C_
+                conv_w_f32 = keep(torch.empty(n_trunk * wsz, **f32))
+                for i, m in enumerate(trunk):
+                    _lib.check(lib.dfir_pack_conv3x3_f32(m.weight.contiguous().data_ptr(),
+                                                         conv_w_f32.data_ptr() + i * wsz * 4, C_, C_, stream),
+                               "pack trunk f32")
+                usz = 9 * C_ * r * r * C_
+                up_w_f32 = keep(torch.empty(max(1, len(ups)) * usz, **f32))
+                for t, m in enumerate(ups):
+                    _lib.check(lib.dfir_pack_conv3x3_f32(m.weight.contiguous().data_ptr(),
+                                                         up_w_f32.data_ptr() + t * usz * 4, r * r * C_, C_, stream),
+                               "pack up f32")
+                up_b = keep(torch.cat([m.bias.reshape(-1) for m in ups]).contiguous())
+                tail_w_f32 = keep(torch.empty(9 * C_ * tail.weight.shape[0], **f32))
+                _lib.check(lib.dfir_pack_conv3x3_f32(tail.weight.contiguous().data_ptr(), tail_w_f32.data_ptr(),
+                                                     tail.weight.shape[0], C_, stream), "pack tail f32")
+
+            # attention blobs
+            blocks = [net.body[g].body[b] for g in range(ng) for b in range(nb)]
+            if blocks:
+                rows = [torch.cat(blk.final_body.flat_params()) for blk in blocks]
+                ca_blob = keep(torch.stack(rows).to(**f32).contiguous())
+                ca_stride = ca_blob.shape[1]
+            else:
+                ca_blob, ca_stride = keep(torch.zeros(1, **f32)), 0
+            q_flags = [1 if blk.q_layer else 0 for blk in blocks]
+            any_q = int(any(q_flags))
+            M = cfg["num_metadata"]
+            hid = C_ // 2 if M <= 15 else (C_ - M) // 2 + M
+            if any_q:
+                z = lambda *s: torch.zeros(*s, **f32)
+                w1, b1, w2, b2 = z(len(blocks), hid, M), z(len(blocks), hid), z(len(blocks), C_, hid), z(len(blocks), C_)
+                for i, blk in enumerate(blocks):
+                    if blk.q_layer:
+                        f1, f2 = blk.q_node.fcs()
+                        w1[i], b1[i] = f1.weight.reshape(hid, M), f1.bias
+                        w2[i], b2[i] = f2.weight.reshape(C_, hid), f2.bias
+                self.meta = [keep(t) for t in (w1, b1, w2, b2)]
+                q_enabled = keep(torch.tensor(q_flags, device=dev, dtype=torch.int32))
+            else:
+                self.meta = [None] * 4
+                q_enabled = None
+
+        style = STYLES[net.style]
+        self.attr_size = C_ if net.style == "modulate" else M
+        if any_q and self.attr_size != M:
+            raise RuntimeError("style='modulate' cannot be combined with q layers (attribute size mismatch)")
+        ptr = lambda t: (t.data_ptr() if t is not None else None)
+        d = QrcanNet()
+        d.n_groups, d.n_blocks, d.n_feats = ng, nb, C_
+        d.scale, d.style, d.reduced = net.scale, style, C_ // cfg["reduction"]
+        d.num_metadata, d.attr_size, d.meta_hidden = M, self.attr_size, hid
+        d.in_feats, d.out_feats = cfg["in_feats"], cfg["out_feats"]
+        d.q_enabled, d.any_q, d.chunk_images = ptr(q_enabled), any_q, int(net.chunk_images)
+        d.conv_w_bf16, d.tail_w_bf16 = ptr(conv_w_bf16), ptr(tail_w_bf16)
+        d.conv_w_f32, d.up_w_f32, d.tail_w_f32, d.head_w_f32 = ptr(conv_w_f32), ptr(up_w_f32), ptr(tail_w_f32), ptr(head_w)
+        d.conv_b, d.up_b, d.tail_b, d.head_b = ptr(conv_b), ptr(up_b), ptr(tail_b), ptr(head_b)
+        d.ca_blob, d.ca_stride = ptr(ca_blob), int(ca_stride)
+        d.meta_w1, d.meta_b1, d.meta_w2, d.meta_b2 = [ptr(t) for t in self.meta]
+        self.desc = d
+        self.device = dev
+        self.scale = net.scale
+        self.out_feats = cfg["out_feats"]
+        self._ws = {}
+        self.handle = _NEXT[0]
+        _NEXT[0] += 1
+        _HANDLES[self.handle] = self
+
+    def workspace(self, B, H, W, precision):
+        k = (B, H, W, precision)
+        ws = self._ws.get(k)
+        if ws is None:
+            lib = _lib.load_library()
+            n = lib.dfir_qrcan_workspace_bytes(C.byref(self.desc), B, H, W, precision)
+            self._ws.clear()  # one live workspace per network keeps HBM use bounded
+            ws = torch.empty(int(n), device=self.device, dtype=torch.uint8)
+            self._ws[k] = ws
+        return ws
+
+    def close(self):
+        _HANDLES.pop(self.handle, None)
+
+
+def packed_from_handle(h):
+    return _HANDLES[h]

@@ -1,0 +1,238 @@
+"""-m gpu: operator-level parity of the CUDA kernels (through the C ABI) against the CPU oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import deepfir_oracle as O
+from tests import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_case(B, H, W, cout=64, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, 64, H, W, generator=g) * 2 - 1
+    w = (torch.rand(cout, 64, 3, 3, generator=g) * 2 - 1) / 24.0
+    b = torch.rand(cout, generator=g) - 0.5
+    return x, w, b
+
+
+def _ref_conv(x, w, b):
+    """fp32 conv of bf16-rounded operands == what bf16 tensor cores with fp32 accumulation compute."""
+    return F.conv2d(G.bf16_round(x), G.bf16_round(w), b, padding=1)
+
+
+# (B,H,W): full 128-wide rows, narrow image, two segments with a ragged tail, single row, many images
+SHAPES = [(2, 16, 128), (1, 9, 40), (1, 5, 200), (3, 1, 7), (5, 3, 128), (1, 130, 128)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("epi", [0, 1])
+def test_conv_tc_bias_relu(shape, epi):
+    B, H, W = shape
+    x, w, b = _rand_case(B, H, W, seed=H * W)
+    ref = _ref_conv(x, w, b)
+    if epi == 1:
+        ref = F.relu(ref)
+    out, _, _ = G.conv_tc(G.nhwc_bf16(x), G.pack_bf16(w), b, epi)
+    got = G.to_nchw(out)
+    assert torch.isfinite(got).all()
+    # output is stored as bf16: half an ulp = 2^-9 relative, plus fp32 accumulation-order noise
+    assert torch.allclose(got, ref, rtol=2 ** -7, atol=2e-3), G.max_norm_err(got, ref)
+
+
+def test_conv_tc_descriptor_modes_agree_or_default_is_right():
+    """Hardware bring-up: the dx-shifted A views need the swizzle phase in the descriptor base_offset."""
+    x, w, b = _rand_case(1, 6, 128, seed=3)
+    ref = _ref_conv(x, w, b)
+    out0, _, _ = G.conv_tc(G.nhwc_bf16(x), G.pack_bf16(w), b, 0, desc_mode=0)
+    assert torch.allclose(G.to_nchw(out0), ref, rtol=2 ** -7, atol=2e-3)
+
+
+def test_conv_tc_pool_rows():
+    B, H, W = 2, 7, 150
+    x, w, b = _rand_case(B, H, W, seed=11)
+    ref = _ref_conv(x, w, b)
+    out, _, pool = G.conv_tc(G.nhwc_bf16(x), G.pack_bf16(w), b, 2)
+    assert torch.allclose(G.to_nchw(out), ref, rtol=2 ** -7, atol=2e-3)
+    # pool_rows[b][seg][y][c] = sum over the segment's valid pixels of the fp32 conv output
+    rows = pool.cpu()  # [B][nseg][H][64]
+    want0 = ref[:, :, :, :128].sum(dim=3).permute(0, 2, 1)
+    want1 = ref[:, :, :, 128:].sum(dim=3).permute(0, 2, 1)
+    assert torch.allclose(rows[:, 0], want0, rtol=1e-4, atol=1e-3)
+    assert torch.allclose(rows[:, 1], want1, rtol=1e-4, atol=1e-3)
+
+
+def test_conv_tc_skip_fp32_stream():
+    B, H, W = 2, 5, 128
+    x, w, b = _rand_case(B, H, W, seed=5)
+    skip = torch.randn(B, 64, H, W)
+    ref = _ref_conv(x, w, b) + skip
+    out, o32, _ = G.conv_tc(G.nhwc_bf16(x), G.pack_bf16(w), b, 3, skip=G.nhwc_f32(skip), want_f32=True)
+    assert G.max_norm_err(G.to_nchw(o32), ref) < 1e-5
+    assert torch.allclose(G.to_nchw(out), ref, rtol=2 ** -7, atol=2e-3)
+
+
+def test_conv_tc_tail_nchw():
+    B, H, W = 1, 6, 256
+    x, w, b = _rand_case(B, H, W, cout=3, seed=9)
+    ref = _ref_conv(x, w, b)
+    b16 = torch.zeros(16)
+    b16[:3] = b
+    _, o32, _ = G.conv_tc(G.nhwc_bf16(x), G.pack_bf16(w, nt_rows=16), b16, 4, cout=3)
+    assert G.max_norm_err(o32.cpu(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("r", [2, 3])
+def test_conv_tc_pixel_shuffle_fold(r):
+    """conv C -> r^2 C + PixelShuffle(r) (advanced/common.py:20-45) as r^2 strided-store launches."""
+    B, H, W = 1, 6, 40
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(B, 64, H, W, generator=g) - 0.5
+    w = (torch.rand(64 * r * r, 64, 3, 3, generator=g) - 0.5) / 12
+    b = torch.rand(64 * r * r, generator=g) - 0.5
+    ref = O.pixel_shuffle(_ref_conv(x, w, b), r)
+    out = torch.full((B, H * r, W * r, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    xin = G.nhwc_bf16(x)
+    oW = W * r
+    for s in range(r * r):
+        i, j = divmod(s, r)
+        bias_s = b.reshape(64, r * r)[:, s]
+        view = out.reshape(-1)[(i * oW + j) * 64:]
+        G.conv_tc(xin, G.pack_bf16(w, co_begin=s, co_stride=r * r), bias_s, 0, out=view,
+                  strides=(r * 128, r * oW * 128, H * r * oW * 128))
+    assert torch.allclose(G.to_nchw(out), ref, rtol=2 ** -7, atol=2e-3)
+
+
+@pytest.mark.parametrize("cfg", [(2, 9, 13, 64, 64, 1, 1, 0), (1, 6, 10, 64, 256, 0, 2, 0), (1, 5, 9, 64, 3, 0, 1, 1),
+                                 (1, 4, 6, 256, 256, 1, 1, 0), (1, 4, 5, 64, 576, 0, 3, 0)])
+def test_conv_f32_simt(cfg):
+    B, H, W, Cin, Cout, relu, ps, nchw = cfg
+    g = torch.Generator().manual_seed(Cout + W)
+    x = torch.rand(B, Cin, H, W, generator=g) - 0.5
+    w = (torch.rand(Cout, Cin, 3, 3, generator=g) - 0.5) / 8
+    b = torch.rand(Cout, generator=g) - 0.5
+    skip = torch.randn(B, Cout, H, W) if (ps == 1 and not nchw) else None
+    ref = F.conv2d(x, w, b, padding=1)
+    if skip is not None:
+        ref = ref + skip
+    if relu:
+        ref = F.relu(ref)
+    if ps > 1:
+        ref = O.pixel_shuffle(ref, ps)
+    if nchw:
+        out = torch.empty(B, Cout, H, W, device="cuda")
+    else:
+        out = torch.empty(B, H * ps, W * ps, Cout // (ps * ps), device="cuda")
+    sk = G.nhwc_f32(skip) if skip is not None else None
+    rc = G.lib().dfir_conv3x3_f32(G.nhwc_f32(x).data_ptr(), G.pack_f32(w).data_ptr(), b.cuda().data_ptr(),
+                                  sk.data_ptr() if sk is not None else None, out.data_ptr(), B, H, W, Cin, Cout, relu,
+                                  ps, nchw, G.stream())
+    assert rc == 0
+    G.sync()
+    got = out.cpu() if nchw else G.to_nchw(out)
+    assert G.max_norm_err(got, ref) < 1e-5
+
+
+def test_head_conv():
+    B, H, W = 2, 11, 17
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(B, 3, H, W, generator=g)
+    w = (torch.rand(64, 3, 3, 3, generator=g) - 0.5) / 3
+    b = torch.rand(64, generator=g) - 0.5
+    ref = F.conv2d(x, w, b, padding=1)
+    o32 = torch.empty(B, H, W, 64, device="cuda")
+    obf = torch.empty(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
+    rc = G.lib().dfir_head_conv(x.cuda().data_ptr(), G.pack_f32(w).data_ptr(), b.cuda().data_ptr(), o32.data_ptr(),
+                                obf.data_ptr(), B, 3, H, W, 64, G.stream())
+    assert rc == 0
+    G.sync()
+    assert G.max_norm_err(G.to_nchw(o32), ref) < 1e-6
+    assert torch.equal(obf.cpu(), o32.cpu().to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("M,hid,C,relu", [(10, 32, 64, 1), (10, 128, 256, 0), (1, 32, 64, 1), (40, 52, 64, 1)])
+def test_meta_attention(M, hid, C, relu):
+    nblk, B = 5, 3
+    g = torch.Generator().manual_seed(M)
+    meta = torch.rand(B, M, generator=g)
+    w1 = torch.randn(nblk, hid, M, generator=g) / 3
+    b1 = torch.randn(nblk, hid, generator=g) / 3
+    w2 = torch.randn(nblk, C, hid, generator=g) / 5
+    b2 = torch.randn(nblk, C, generator=g) / 3
+    en = torch.tensor([1, 0, 1, 1, 0], dtype=torch.int32)
+    out = torch.empty(nblk, B, C, device="cuda")
+    cu = [t.cuda() for t in (meta, w1, b1, w2, b2, en)]
+    rc = G.lib().dfir_meta_attention(*[t.data_ptr() for t in cu[:5]], out.data_ptr(), nblk, B, M, hid, C, relu,
+                                     cu[5].data_ptr(), G.stream())
+    assert rc == 0
+    G.sync()
+    for k in range(nblk):
+        h = meta @ w1[k].t() + b1[k]
+        if relu:
+            h = F.relu(h)
+        want = torch.sigmoid(h @ w2[k].t() + b2[k]) if en[k] else torch.ones(B, C)
+        assert torch.allclose(out[k].cpu(), want, rtol=1e-5, atol=1e-6)
+
+
+STYLE_ID = {"none": 0, "standard": 1, "modulate": 2, "max_concat": 3, "softmax": 4, "mini_concat": 5,
+            "extended_attention": 6}
+
+
+@pytest.mark.parametrize("style", ["standard", "modulate", "max_concat", "softmax", "mini_concat",
+                                   "extended_attention", "none"])
+@pytest.mark.parametrize("r_bf16", [0, 1])
+def test_ca_scale_residual_all_styles(style, r_bf16):
+    """QCALayer (all styles) * meta scale + residual vs the oracle restatement."""
+    from deepfir_b200.qrcan import ChannelAttentionParams
+    B, H, W, Cc, M = 2, 6, 10, 64, 10
+    torch.manual_seed(7)
+    A = 64 if style == "modulate" else M
+    r = torch.randn(B, Cc, H, W)
+    if r_bf16:
+        r = G.bf16_round(r)
+    x = torch.randn(B, Cc, H, W)
+    attr = torch.rand(B, A)
+    sq = torch.rand(B, Cc)
+    res_scale = 0.1 if style == "none" else 1.0
+    if style != "none":
+        ca = ChannelAttentionParams(Cc, style, 16, M)
+        sd = {"p." + k: v for k, v in ca.state_dict().items()}
+        blob = torch.cat([t.detach().reshape(-1) for t in ca.flat_params()]).cuda()
+        y = O.qca_vector(r, attr.reshape(B, A, 1, 1), sd, "p", style)
+        want = r * y * sq.reshape(B, Cc, 1, 1) + x
+    else:
+        blob = None
+        want = r * res_scale * sq.reshape(B, Cc, 1, 1) + x
+    r_dev = G.nhwc_bf16(r) if r_bf16 else G.nhwc_f32(r)
+    pool = G.nhwc_f32(r).sum(dim=2).contiguous()  # [B][H][C] row sums
+    x_dev = G.nhwc_f32(x)
+    out = torch.empty_like(x_dev)
+    obf = torch.empty(B, H, W, Cc, device="cuda", dtype=torch.bfloat16)
+    rc = G.lib().dfir_ca_scale_residual(r_dev.data_ptr(), r_bf16, x_dev.data_ptr(), pool.data_ptr(), H,
+                                        STYLE_ID[style], blob.data_ptr() if blob is not None else None, Cc, 4, M, A,
+                                        attr.cuda().data_ptr(), sq.cuda().data_ptr(), res_scale, out.data_ptr(),
+                                        obf.data_ptr(), B, H, W, G.stream())
+    assert rc == 0
+    G.sync()
+    assert G.max_norm_err(G.to_nchw(out), want) < 2e-6
+    assert torch.equal(obf.cpu(), out.cpu().to(torch.bfloat16))
+
+
+def test_pool_rows_f32():
+    x = torch.randn(2, 64, 5, 9)
+    out = torch.empty(2, 5, 64, device="cuda")
+    assert G.lib().dfir_pool_rows_f32(G.nhwc_f32(x).data_ptr(), out.data_ptr(), 2, 5, 9, 64, G.stream()) == 0
+    G.sync()
+    assert torch.allclose(out.cpu(), x.sum(dim=3).permute(0, 2, 1), rtol=1e-5, atol=1e-5)
+
+
+def test_bad_arguments_return_error_codes():
+    L = G.lib()
+    assert L.dfir_conv3x3_f32(None, None, None, None, None, 1, 4, 4, 3, 8, 0, 1, 0, None) == -1  # Cin % 4
+    x = torch.zeros(1, 4, 4, 64, device="cuda", dtype=torch.bfloat16)
+    assert L.dfir_conv3x3_c64(x.data_ptr(), 64, 0, x.data_ptr(), x.data_ptr(), 1, 4, 4, 2, 64, x.data_ptr(), 128, 512,
+                              2048, None, None, None, 0, None) == -1  # pool epilogue without pool buffer
