@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Deep-FIR hot-path benchmark (contract: see the task's bench.py section / DESIGN.md §Measurement).
+
+Workload (BASELINE.json configs[1]): Q-RCAN x4 (10 groups x 20 RCAB, 64 ch, 10-D blur-kernel metadata),
+batched inference on synthetic 128x128 LR images, 32 images per GPU (256 over 8 GPUs; weak scaling:
+every rank runs the same per-GPU batch, no data-path collective).  One "step" = one forward pass over
+the per-GPU batch.  metric = output megapixels per second, whole job.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+`--impl reference` times the CPU restatement of the reference's own path (oracle port, torch-CPU fp32 on
+all host cores) on a bounded sample of the same workload; rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "super-resolution-meta-attention-networks_b200"))
+
+import torch  # noqa: E402
+
+IMAGES_PER_GPU = 32
+LR = 128
+SCALE = 4
+NET_KW = dict(n_resgroups=10, n_resblocks=20, n_feats=64, scale=SCALE, style="standard", include_q_layer=True)
+FLOP_PER_LR_PIXEL = 31835520            # conv FLOPs of Q-RCAN x4 per LR pixel
+CONV64_FLOP_PER_PIXEL = 2 * 64 * 64 * 9  # one 64->64 3x3 conv
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return dict(hbm_gbs=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as fh:
+            for line in fh:
+                parts = [t.strip() for t in line.split(",")]
+                if len(parts) < 6:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    mx = float(parts[1])
+                except ValueError:
+                    continue
+                for n, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        os.unlink(self.path)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def build_net(device):
+    from SISR.models import ModelInterface
+    torch.manual_seed(8)
+    handler = ModelInterface.define_model(
+        "qrcan", device=device, model_save_dir=tempfile.gettempdir(), eval_mode=True, lr=1e-4,
+        metadata=["blur_kernel"], precision="bf16", **NET_KW)
+    return handler
+
+
+def synth_batch(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.floor(torch.rand(n, 3, LR, LR, generator=g) * 256) / 255.0
+    meta = torch.rand(n, 10, generator=g, dtype=torch.float64) * 0.4
+    keys = [("blur_kernel",) * n] * 10
+    return x, meta, keys
+
+
+def flush_l2(buf):
+    buf.add_(1)
+
+
+def run_ours(args):
+    from deepfir_b200 import _lib
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _lib.load_library()
+    _lib.check(lib.dfir_check_device(), "device check")
+
+    handler = build_net(local)
+    net = handler.net
+    n_img = IMAGES_PER_GPU
+    x_host, meta, keys = synth_batch(n_img, seed=8 + rank)
+    x_pin = x_host.pin_memory()
+    x_dev = x_host.to(dev)
+    attr_dev = handler.generate_channels(x_host, meta, keys).to(dev)
+    l2buf = torch.zeros(192 * 1024 * 1024 // 4, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        with torch.no_grad():
+            return net(x_dev, attr_dev)
+
+    def step_e2e():
+        out, _, _ = handler.run_eval(x_pin, metadata=meta, metadata_keys=keys)  # H2D + forward + D2H
+        return out
+
+    for _ in range(max(args.warmup, 3)):
+        out = step_device()
+    torch.cuda.synchronize()
+
+    # ---------------- device-resident timing: K steps, L2 flushed between steps (flush not timed)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    evs = []
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush_l2(l2buf)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = step_device()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+
+    # ---------------- end to end through the handler API with host buffers
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out_host = step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = t.tolist()
+
+    # ---------------- roofline of the dominant kernel (trunk 64->64 conv), timed alone with CUDA events
+    roof = None
+    if rank == 0:
+        roof = conv_roofline(lib, dev, net)
+    out_mpix_step = world * n_img * (LR * SCALE) ** 2 / 1e6
+    launches = int(lib.dfir_qrcan_launch_count(__import__("ctypes").byref(net.packed().desc), n_img, LR, LR, 0))
+
+    if rank == 0:
+        pk = peaks()
+        ms_step = dev_ms / args.steps
+        value = out_mpix_step / (ms_step / 1e3)
+        cpu = cpu_baseline(sample_images=2)
+        line = {
+            "metric": "Q-RCAN x4 output MPix/s", "value": round(value, 3), "unit": "MPix/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "Q-RCAN x4 (10x20 RCAB, 64 ch, 10-D blur metadata) batched inference, "
+                                   "%d synthetic 128x128 LR images per GPU" % n_img,
+                       "images_per_gpu": n_img, "lr_size": [LR, LR], "scale": SCALE, "precision": "bf16 operands, "
+                       "fp32 accumulate + fp32 residual stream", "l2": "192 MiB buffer rewritten between timed steps",
+                       "sharding": "by image, no data-path collective"},
+            "clocks": clocks,
+            "e2e": {"value": round(out_mpix_step / (e2e_ms / 1e3 / args.steps), 3), "unit": "MPix/s",
+                    "h2d_bytes_per_step": int(x_pin.numel() * 4 + n_img * 10 * 4),
+                    "d2h_bytes_per_step": int(out_host.numel() * 4),
+                    "api": "QRCANHandler.run_eval(x_pinned_host, metadata=, metadata_keys=) -> host tensor"},
+            "gpu_launches": launches * args.steps,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "tflops_conv_algorithmic": round(world * n_img * LR * LR * FLOP_PER_LR_PIXEL / (ms_step / 1e3) / 1e12, 2),
+            "wall_s_timed_region": round(wall, 3),
+            "peaks": pk["source"],
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def conv_roofline(lib, dev, net):
+    """Times the trunk conv kernel alone (CUDA events on the launching stream) at the shape one launch of
+    the forward schedule sees: `chunk` images of 128x128x64, bias+ReLU epilogue."""
+    import ctypes as C
+    from deepfir_b200 import _lib
+    pk = peaks()
+    packed = net.packed()
+    ws_bytes = lib.dfir_qrcan_workspace_bytes(C.byref(packed.desc), IMAGES_PER_GPU, LR, LR, 0)
+    # chunk size the schedule uses (images per L2-resident pass): recover it from the launch count
+    launches = lib.dfir_qrcan_launch_count(C.byref(packed.desc), IMAGES_PER_GPU, LR, LR, 0)
+    per_chunk = 1 + 10 * (20 * 3 + 1) + 1 + 2 * 4 + 1
+    chunks = max(1, (launches - 1) // per_chunk)
+    bc = (IMAGES_PER_GPU + chunks - 1) // chunks
+    a = torch.randn(bc, LR, LR, 64, device=dev).to(torch.bfloat16)
+    b = torch.empty_like(a)
+    wp = torch.empty(9 * 64 * 128, dtype=torch.uint8, device=dev)
+    w = (torch.randn(64, 64, 3, 3, device=dev) / 24).contiguous()
+    bias = torch.zeros(64, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.dfir_pack_conv3x3_bf16(w.data_ptr(), wp.data_ptr(), 64, 64, 64, 0, 1, st), "pack")
+
+    def launch(src, dst):
+        _lib.check(lib.dfir_conv3x3_c64(src.data_ptr(), 64, 0, wp.data_ptr(), bias.data_ptr(), bc, LR, LR, 1, 64,
+                                        dst.data_ptr(), 128, LR * 128, LR * LR * 128, None, None, None, 0, st), "conv")
+    for _ in range(10):
+        launch(a, b)
+        launch(b, a)
+    torch.cuda.synchronize()
+    n = 100
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n // 2):
+        launch(a, b)
+        launch(b, a)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    flops = bc * LR * LR * CONV64_FLOP_PER_PIXEL
+    achieved = flops / (ms / 1e3) / 1e12
+    return {"bound": "tensor", "kernel": "conv3x3_c64_tc_kernel<64, bias+relu>", "achieved": round(achieved, 2),
+            "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": round(achieved / pk["tf_burst"], 4),
+            "traffic": None, "launch_us": round(ms * 1e3, 3), "images_per_launch": bc,
+            "algorithmic_flops_per_launch": flops, "peak_source": pk["source"] + ", burst (kernel timed alone)"}
+
+
+def cpu_baseline(sample_images=2, threads=None):
+    """The reference's path restated on the CPU (oracle port, fp32 torch-CPU == the ATen kernels the
+    reference itself runs on CPU), timed on this box's host cores on a bounded sample."""
+    from oracle import deepfir_oracle as O
+    from deepfir_b200.qrcan import QRCAN
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    torch.manual_seed(8)
+    net = QRCAN(num_metadata=10, **NET_KW)
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    x, meta, _ = synth_batch(sample_images, seed=8)
+    attr = meta.float().reshape(sample_images, 10, 1, 1)
+    with torch.no_grad():
+        O.qrcan_forward(x[:1], attr[:1], sd, style="standard")  # warm-up
+        t0 = time.perf_counter()
+        O.qrcan_forward(x, attr, sd, style="standard")
+        dt = time.perf_counter() - t0
+    mpix = sample_images * (LR * SCALE) ** 2 / 1e6
+    return {"value": round(mpix / dt, 4), "unit": "MPix/s", "cores": threads, "kind": "port",
+            "sample": "%d of the %d images of one step, 1 warm-up image, fp32 torch-CPU oracle (oracle/deepfir_oracle.py)"
+                      % (sample_images, IMAGES_PER_GPU), "seconds": round(dt, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    sample = 2
+    vals = []
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_baseline(sample_images=1)
+    t_all = time.perf_counter()
+    for _ in range(max(1, args.steps)):
+        vals.append(cpu_baseline(sample_images=sample))
+        if time.perf_counter() - t_all > 150:
+            break
+    v = sum(c["value"] for c in vals) / len(vals)
+    cpu = dict(vals[-1])
+    cpu["value"] = round(v, 4)
+    ms = sample * (LR * SCALE) ** 2 / 1e6 / v * 1e3
+    print(json.dumps({
+        "impl": "reference", "metric": "Q-RCAN x4 output MPix/s", "value": round(v, 4), "unit": "MPix/s",
+        "n_gpus": world, "steps": len(vals), "warmup": 1, "ms_per_step": round(ms, 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "Q-RCAN x4 (10x20 RCAB, 64 ch, 10-D blur metadata) batched inference, "
+                               "%d synthetic 128x128 LR images per GPU" % IMAGES_PER_GPU,
+                   "sample": "each step = %d images of the workload on the host CPU" % sample},
+        "cpu_baseline": cpu,
+        "e2e": {"value": round(v, 4), "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -80,8 +80,8 @@ int dfir_pack_conv3x3_f32(const float* w_oihw, float* out, int cout, int cin, vo
  *   out_bf16 : NHWC bf16, addressed with explicit byte strides so that PixelShuffle
  *              (advanced/common.py:30) folds into the store: for sub-pixel (i,j) of an r-times upsampler
  *              pass base + ((i*r*W + j)*64*2), pix stride r*128, row stride r*(r*W)*128.
- *   desc_mode: 0 (default).  1 selects the alternative shared-memory descriptor encoding used only by the
- *              hardware bring-up test. */
+ *   desc_mode: 0 (default).  1 selects the alternative shared-memory descriptor encoding (base_offset =
+ *              swizzle phase) that B200 hardware does NOT want; it exists only for the bring-up test. */
 int dfir_conv3x3_c64(const void* in_bf16, int cin_total, int cin_off, const void* wpacked, const float* bias,
                      int B, int H, int W, int epi, int cout, void* out_bf16, long long out_pix_stride,
                      long long out_row_stride, long long out_img_stride, const float* skip_f32, float* out_f32,
@@ -164,6 +164,8 @@ typedef struct dfir_qrcan_net {
 } dfir_qrcan_net;
 
 size_t dfir_qrcan_workspace_bytes(const dfir_qrcan_net* net, int B, int H, int W, int precision);
+/* number of kernel launches one dfir_qrcan_forward call enqueues (bench.py's `gpu_launches` claim) */
+long long dfir_qrcan_launch_count(const dfir_qrcan_net* net, int B, int H, int W, int precision);
 
 /* QRCAN.forward(x, metadata) (attention_manipulators/architectures.py:309-316).
  *   x_nchw fp32 [B][3][H][W]; attributes fp32 [B][attr_size] (the (B,M,1,1) tensor of QModel.generate_channels);

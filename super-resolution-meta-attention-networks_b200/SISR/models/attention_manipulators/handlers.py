@@ -1,0 +1,84 @@
+"""Handlers of the metadata-conditioned networks (reference:
+Code/SISR/models/attention_manipulators/handlers.py).  Same class names (the registry keys are derived from
+them), constructor arguments and attributes; the networks they own are the B200 implementations in
+`deepfir_b200`.  Extra optional `internal_params` keys understood here: `precision` ('bf16' | 'fp32') and
+`chunk_images`; reference configs that do not carry them load unchanged."""
+import time
+
+import numpy as np
+import torch
+from torch import nn
+
+from SISR.models.attention_manipulators import QModel
+from deepfir_b200.qrcan import QRCAN
+
+
+class QRCANHandler(QModel):
+    """Meta-attention RCAN: 10 residual groups x 20 RCABs by default.  `include_q_layer`,
+    `selective_meta_blocks` (one bool per group) and `num_q_layers_inner_residual` place the
+    meta-attention layers exactly as in the reference (handlers.py:7-40)."""
+
+    def __init__(self, device, model_save_dir, eval_mode=False, lr=1e-4, scale=4, in_features=3, scheduler=None,
+                 scheduler_params=None, style='modulate', perceptual=None, clamp=False, min_mu=-0.2,
+                 max_mu=0.8, n_feats=64, **kwargs):
+        super(QRCANHandler, self).__init__(device=device, model_save_dir=model_save_dir, eval_mode=eval_mode,
+                                           **kwargs)
+        self.net = QRCAN(scale=scale, in_feats=in_features, num_metadata=self.num_metadata,
+                         n_feats=n_feats, style=style, **kwargs)
+        self.colorspace = 'augmented_rgb'
+        self.im_input = 'unmodified'
+        self.activate_device()
+        self.training_setup(lr, scheduler, scheduler_params, perceptual, device)
+        self.model_name = 'qrcan'
+        self.min_mu = min_mu
+        self.max_mu = max_mu
+        self.base_scaler = np.linspace(0, 1, n_feats)
+        self.clamp = clamp
+        self.style = style
+
+    @staticmethod
+    def gaussian(x, mu, sig=0.2):
+        g = (1 / (np.sqrt(2 * np.pi) * sig)) * np.exp(-np.power(x - mu, 2.) / (2 * np.power(sig, 2.)))
+        return torch.from_numpy(g).type(torch.float32)
+
+    def scale_qpi(self, qpi):
+        """'modulate' style: each image's scalar becomes an n_feats-bin Gaussian bump (ref :42-54)."""
+        mu = (qpi * (self.max_mu - self.min_mu)) + self.min_mu
+        rows = torch.stack([self.gaussian(self.base_scaler, mu[i].squeeze().numpy()) for i in range(mu.size(0))])
+        if self.clamp:
+            rows = torch.clamp(rows, 0, 1)
+        return rows.unsqueeze(2).unsqueeze(3)
+
+
+def _pending(name):
+    raise NotImplementedError('%s is not on the B200 path yet (see DESIGN.md, scope table)' % name)
+
+
+class QEDSRHandler(QModel):
+    """Meta-attention EDSR (ref :57-76)."""
+
+    def __init__(self, device, model_save_dir, eval_mode=False, lr=1e-4, scale=4, in_features=3, num_blocks=16,
+                 num_features=64, res_scale=0.1, scheduler=None, scheduler_params=None, perceptual=None, **kwargs):
+        super(QEDSRHandler, self).__init__(device=device, model_save_dir=model_save_dir, eval_mode=eval_mode,
+                                           **kwargs)
+        _pending('qedsr')
+
+
+class QSANHandler(QModel):
+    """Meta-attention SAN (ref :79-153)."""
+
+    def __init__(self, device, model_save_dir, eval_mode=False, lr=1e-4, scale=4, perceptual=None,
+                 max_combined_im_size=160000, scheduler=None, scheduler_params=None, **kwargs):
+        super(QSANHandler, self).__init__(device=device, model_save_dir=model_save_dir, eval_mode=eval_mode,
+                                          **kwargs)
+        _pending('qsan')
+
+
+class QHANHandler(QModel):
+    """Meta-attention HAN (ref :156-171)."""
+
+    def __init__(self, device, model_save_dir, eval_mode=False, lr=1e-4, scale=4, perceptual=None,
+                 scheduler=None, scheduler_params=None, **kwargs):
+        super(QHANHandler, self).__init__(device=device, model_save_dir=model_save_dir, eval_mode=eval_mode,
+                                          **kwargs)
+        _pending('qhan')

@@ -332,6 +332,23 @@ size_t dfir_qrcan_workspace_bytes(const dfir_qrcan_net* net, int B, int H, int W
   return carve_qrcan(net, B, Bc, H, W, precision, nullptr).total;
 }
 
+long long dfir_qrcan_launch_count(const dfir_qrcan_net* net, int B, int H, int W, int precision) {
+  if (net == nullptr || B <= 0) return 0;
+  const int Bc = net->chunk_images > 0 ? std::min(net->chunk_images, B) : auto_chunk(B, H, W, precision);
+  const long long chunks = (B + Bc - 1) / Bc;
+  int r = 0;
+  const int nup = up_stages(net->scale, &r);
+  const long long nb = net->n_blocks, ng = net->n_groups;
+  long long per_chunk;
+  if (precision == DFIR_PREC_BF16_TC) {
+    per_chunk = 1 + ng * (nb * 3 + 1) + 1 + static_cast<long long>(nup) * r * r + 1;
+  } else {
+    const long long pool = net->style != DFIR_STYLE_NONE ? 1 : 0;
+    per_chunk = 1 + ng * (nb * (3 + pool) + 2) + 1 + nup + 1;  // group tail = conv + copy
+  }
+  return chunks * per_chunk + (net->any_q ? 1 : 0);
+}
+
 int dfir_qrcan_forward(const dfir_qrcan_net* net, const float* x_nchw, const float* attributes, float* out_nchw, int B,
                        int H, int W, int precision, void* workspace, size_t workspace_bytes, void* stream) {
   if (net == nullptr || x_nchw == nullptr || out_nchw == nullptr || attributes == nullptr) return DFIR_ERR_ARG;

@@ -11,7 +11,7 @@
 // memory ring with TMA (one box = one row segment of 130 pixels incl. the x halo; out-of-bounds pixels and
 // rows are zero-filled by the TMA unit, which IS the conv's zero padding) and every tap's A operand is
 // just a shifted view of a ring slot: dy picks the slot, dx shifts the descriptor start by dx*128 B
-// (descriptor base_offset = swizzle phase).  The weights of the layer (9 x cout x 128 B) stay resident in
+// (base_offset stays 0: the hardware derives the swizzle phase from the absolute smem address).  The weights of the layer (9 x cout x 128 B) stay resident in
 // shared memory for the CTA's whole life.  Accumulators live in TMEM (4 buffers) so the epilogue of row i
 // overlaps the MMAs of rows i+1..i+3.
 //
@@ -81,7 +81,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
                       ConvTcArgs a) {
   using L = SmemLayout<NT>;
-  extern __shared__ __align__(1024) uint8_t smem[];
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B atoms (TMA and UMMA) need 1024-byte alignment of every tile base
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* wsm = smem + L::off_w;
   uint8_t* ring = smem + L::off_ring;
   uint8_t* stage = smem + L::off_stage;
@@ -176,7 +178,9 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             for (int dx = 0; dx < 3; ++dx) {
               const uint32_t a_u = slot_u + dx * 128;
               const uint32_t b_u = w_u + (dy * 3 + dx) * (NT * 128);
-              const uint32_t boff = a.desc_mode == 0 ? static_cast<uint32_t>(dx) : 0u;
+              // measured on B200: the swizzle XOR is taken from the absolute smem address bits, so a view that
+              // starts dx*128 B into a 1024 B atom needs base_offset 0 (mode 1 = phase is kept for the bring-up test)
+              const uint32_t boff = a.desc_mode == 1 ? static_cast<uint32_t>(dx) : 0u;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint64_t da = make_sw128_kmajor_desc(a_u + k * 32, 1024, boff);
@@ -356,12 +360,14 @@ template <int NT, int EPI>
 static int launch_one(const CUtensorMap& tin, const CUtensorMap& tout, const ConvTcArgs& a, int grid,
                       cudaStream_t stream) {
   using L = SmemLayout<NT>;
-  static bool configured = false;
+  static bool configured[64] = {};  // per device: the attribute lives in the device's context
   auto kern = conv3x3_c64_tc_kernel<NT, EPI>;
-  if (!configured) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return DFIR_ERR_CUDA;
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total + 1024) != cudaSuccess)
       return DFIR_ERR_CUDA;
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   kern<<<grid, kThreads, L::total + 1024, stream>>>(tin, tout, a);
   return cudaGetLastError() == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;

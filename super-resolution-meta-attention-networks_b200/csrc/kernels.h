@@ -32,7 +32,7 @@ struct ConvTcDesc {  // host-side launch description
   int cin_total, cin_off;  // channels of the input tensor / first channel of the 64-wide slice consumed
   int cout;                // real output channels (tail only)
   int epi;
-  int desc_mode;           // 0: base_offset = swizzle phase of the dx-shifted view (default); 1: base_offset 0
+  int desc_mode;           // 0: descriptor base_offset 0 (correct on B200); 1: base_offset = swizzle phase (bring-up test)
   int num_sms;
   const void* in_bf16;
   const void* wpacked;

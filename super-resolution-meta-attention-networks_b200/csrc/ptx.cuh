@@ -169,9 +169,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, K-major operand stored as rows of 128 bytes with the 128B swizzle
-// (8-row x 128 B atoms; SBO = byte distance between consecutive 8-row groups).  `base_offset` is the
-// phase of the first row inside the 1024 B swizzle pattern, (addr >> 7) & 7, needed when the matrix does
-// not start on a 1024 B boundary (the dx-shifted views of the halo row buffer).
+// (8-row x 128 B atoms; SBO = byte distance between consecutive 8-row groups).  `base_offset` stays 0 even
+// for matrices that start k*128 B into a 1024 B swizzle atom (the dx-shifted views of the halo row
+// buffer): measured on B200, the tensor core XORs address bits [7,10) of the ABSOLUTE shared-memory
+// address into the 16-byte chunk index, exactly like the TMA unit wrote them (tools/diag_conv.py).
 __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_offset) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);              // [0,14)  start address >> 4

@@ -62,6 +62,7 @@ PROTOTYPES = {
                                     _i, _i, _i, _vp]),
     "dfir_pool_rows_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "dfir_qrcan_workspace_bytes": (_sz, [C.POINTER(QrcanNet), _i, _i, _i, _i]),
+    "dfir_qrcan_launch_count": (C.c_longlong, [C.POINTER(QrcanNet), _i, _i, _i, _i]),
     "dfir_qrcan_forward": (_i, [C.POINTER(QrcanNet), _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
 }
 

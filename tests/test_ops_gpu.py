@@ -44,12 +44,16 @@ def test_conv_tc_bias_relu(shape, epi):
     assert torch.allclose(got, ref, rtol=2 ** -7, atol=2e-3), G.max_norm_err(got, ref)
 
 
-def test_conv_tc_descriptor_modes_agree_or_default_is_right():
-    """Hardware bring-up: the dx-shifted A views need the swizzle phase in the descriptor base_offset."""
+def test_conv_tc_descriptor_base_offset_is_absolute_address_based():
+    """Hardware bring-up record: the dx-shifted A views start 128/256 B into a swizzle atom.  B200 takes the
+    swizzle phase from the absolute smem address (descriptor base_offset 0, mode 0); encoding the phase
+    in base_offset (mode 1) double-applies it and scrambles the 16-byte channel chunks."""
     x, w, b = _rand_case(1, 6, 128, seed=3)
     ref = _ref_conv(x, w, b)
     out0, _, _ = G.conv_tc(G.nhwc_bf16(x), G.pack_bf16(w), b, 0, desc_mode=0)
     assert torch.allclose(G.to_nchw(out0), ref, rtol=2 ** -7, atol=2e-3)
+    out1, _, _ = G.conv_tc(G.nhwc_bf16(x), G.pack_bf16(w), b, 0, desc_mode=1)
+    assert not torch.allclose(G.to_nchw(out1), ref, rtol=2 ** -7, atol=2e-3)
 
 
 def test_conv_tc_pool_rows():
@@ -128,7 +132,8 @@ def test_conv_f32_simt(cfg):
     else:
         out = torch.empty(B, H * ps, W * ps, Cout // (ps * ps), device="cuda")
     sk = G.nhwc_f32(skip) if skip is not None else None
-    rc = G.lib().dfir_conv3x3_f32(G.nhwc_f32(x).data_ptr(), G.pack_f32(w).data_ptr(), b.cuda().data_ptr(),
+    xd, wd, bd = G.nhwc_f32(x), G.pack_f32(w), b.cuda()
+    rc = G.lib().dfir_conv3x3_f32(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(),
                                   sk.data_ptr() if sk is not None else None, out.data_ptr(), B, H, W, Cin, Cout, relu,
                                   ps, nchw, G.stream())
     assert rc == 0
@@ -146,7 +151,8 @@ def test_head_conv():
     ref = F.conv2d(x, w, b, padding=1)
     o32 = torch.empty(B, H, W, 64, device="cuda")
     obf = torch.empty(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
-    rc = G.lib().dfir_head_conv(x.cuda().data_ptr(), G.pack_f32(w).data_ptr(), b.cuda().data_ptr(), o32.data_ptr(),
+    xd, wd, bd = x.cuda(), G.pack_f32(w), b.cuda()
+    rc = G.lib().dfir_head_conv(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), o32.data_ptr(),
                                 obf.data_ptr(), B, 3, H, W, 64, G.stream())
     assert rc == 0
     G.sync()
@@ -212,9 +218,10 @@ def test_ca_scale_residual_all_styles(style, r_bf16):
     x_dev = G.nhwc_f32(x)
     out = torch.empty_like(x_dev)
     obf = torch.empty(B, H, W, Cc, device="cuda", dtype=torch.bfloat16)
+    attr_d, sq_d = attr.cuda(), sq.cuda()
     rc = G.lib().dfir_ca_scale_residual(r_dev.data_ptr(), r_bf16, x_dev.data_ptr(), pool.data_ptr(), H,
                                         STYLE_ID[style], blob.data_ptr() if blob is not None else None, Cc, 4, M, A,
-                                        attr.cuda().data_ptr(), sq.cuda().data_ptr(), res_scale, out.data_ptr(),
+                                        attr_d.data_ptr(), sq_d.data_ptr(), res_scale, out.data_ptr(),
                                         obf.data_ptr(), B, H, W, G.stream())
     assert rc == 0
     G.sync()
@@ -225,7 +232,8 @@ def test_ca_scale_residual_all_styles(style, r_bf16):
 def test_pool_rows_f32():
     x = torch.randn(2, 64, 5, 9)
     out = torch.empty(2, 5, 64, device="cuda")
-    assert G.lib().dfir_pool_rows_f32(G.nhwc_f32(x).data_ptr(), out.data_ptr(), 2, 5, 9, 64, G.stream()) == 0
+    xd = G.nhwc_f32(x)
+    assert G.lib().dfir_pool_rows_f32(xd.data_ptr(), out.data_ptr(), 2, 5, 9, 64, G.stream()) == 0
     G.sync()
     assert torch.allclose(out.cpu(), x.sum(dim=3).permute(0, 2, 1), rtol=1e-5, atol=1e-5)
 
