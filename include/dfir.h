@@ -80,12 +80,30 @@ int dfir_pack_conv3x3_f32(const float* w_oihw, float* out, int cout, int cin, vo
  *   out_bf16 : NHWC bf16, addressed with explicit byte strides so that PixelShuffle
  *              (advanced/common.py:30) folds into the store: for sub-pixel (i,j) of an r-times upsampler
  *              pass base + ((i*r*W + j)*64*2), pix stride r*128, row stride r*(r*W)*128.
- *   desc_mode: 0 (default).  1 selects the alternative shared-memory descriptor encoding (base_offset =
- *              swizzle phase) that B200 hardware does NOT want; it exists only for the bring-up test. */
+ *   desc_mode: reserved, must be 0 (an alternative shared-memory descriptor encoding used during hardware
+ *              bring-up lived here; see DESIGN.md "descriptor base_offset"). */
 int dfir_conv3x3_c64(const void* in_bf16, int cin_total, int cin_off, const void* wpacked, const float* bias,
                      int B, int H, int W, int epi, int cout, void* out_bf16, long long out_pix_stride,
                      long long out_row_stride, long long out_img_stride, const float* skip_f32, float* out_f32,
                      float* pool_rows, int desc_mode, void* stream);
+
+/* RCAB conv2 with the channel-attention vector computed in its tail (QRCAB.body[2] + QCALayer up to the
+ * `x * y`, attention_manipulators/architectures.py:105-125,173-175; ParaCALayer scale folded in):
+ *   out_bf16 = conv(in) + bias (NHWC bf16, dense);  pool_rows[B][nseg][H][64] = per-row channel sums;
+ *   svec_out[b][c] = CA_style(mean_b, attributes[b]) * (sq ? sq[b][c] : 1), written by the last CTA that
+ *   finishes image b.  img_counter: int32 [B], zero on entry (the kernel leaves it zero again). */
+int dfir_conv3x3_c64_ca(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
+                        void* out_bf16, float* pool_rows, int style, const float* ca_params, int R, int M, int A,
+                        const float* attributes, const float* sq, float* svec_out, int* img_counter, void* stream);
+
+/* Conv whose operand is formed on the fly from the previous block: x' = r * svec[b] + x_in
+ * (`res * y` and `res += x`, attention_manipulators/architectures.py:127,179; q_layer.py:43), then
+ * default_conv(x').  r: NHWC bf16; x_in: NHWC fp32 residual stream; x_out (optional, must not alias x_in):
+ * NHWC fp32 copy of x'.  epi: 1 (bias+ReLU -> out_bf16) or 3 (bias + skip_f32 -> out_f32 [optional] and
+ * out_bf16). */
+int dfir_conv3x3_c64_fused(const void* r_bf16, const float* x_in, const float* svec, float* x_out,
+                           const void* wpacked, const float* bias, int B, int H, int W, int epi, void* out_bf16,
+                           const float* skip_f32, float* out_f32, void* stream);
 
 /* default_conv on CUDA cores, fp32 NHWC in/out, any Cin % 4 == 0 and any Cout.
  *   w_packed from dfir_pack_conv3x3_f32; skip (optional) NHWC fp32 added after bias; relu applied last;

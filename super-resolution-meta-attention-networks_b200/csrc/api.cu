@@ -42,7 +42,8 @@ int auto_chunk(int B, int H, int W, int precision) {
 }
 
 struct QrcanWs {
-  float *Hh, *XA, *XB, *pool, *sq;
+  float *Hh, *XA, *XB, *XB1, *pool, *sq, *svec;
+  int* counters;
   __nv_bfloat16 *Hbf, *XAbf, *XBbf, *T, *R;
   float *T32, *R32;
   void* U[3];
@@ -60,12 +61,15 @@ QrcanWs carve_qrcan(const dfir_qrcan_net* n, int B, int Bc, int H, int W, int pr
   const int nseg = (W + 127) / 128;
   w.pool = c.take<float>(static_cast<size_t>(Bc) * nseg * H * C * 4);
   w.sq = c.take<float>(static_cast<size_t>(n->n_groups) * n->n_blocks * B * C * 4);
+  w.svec = c.take<float>(static_cast<size_t>(Bc) * C * 4);
+  w.counters = c.take<int>(static_cast<size_t>(Bc) * 4);
   int r = 0;
   const int nup = up_stages(n->scale, &r);
   if (precision == DFIR_PREC_BF16_TC) {
     w.Hbf = c.take<__nv_bfloat16>(px * C * 2);
     w.XAbf = c.take<__nv_bfloat16>(px * C * 2);
     w.XBbf = c.take<__nv_bfloat16>(px * C * 2);
+    w.XB1 = c.take<float>(px * C * 4);
     w.T = c.take<__nv_bfloat16>(px * C * 2);
     w.R = c.take<__nv_bfloat16>(px * C * 2);
     size_t f = 1;
@@ -112,41 +116,68 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
   const size_t wbytes = 9 * 64 * 128;
   const uint8_t* cw = reinterpret_cast<const uint8_t*>(n->conv_w_bf16);
   const long long pixB = C * 2, rowB = static_cast<long long>(W) * C * 2, imgB = rowB * H;
-  const int nseg = (W + 127) / 128;
 
   DFIR_TRY(head_conv(x + static_cast<size_t>(b0) * n->in_feats * H * W, n->head_w_f32, n->head_b, w.Hh, w.Hbf, Bc,
                      n->in_feats, H, W, C, st));
 
-  auto conv = [&](const void* in, int widx, int epi, void* obf, const float* skip, float* o32) {
+  // One launch description shared by all trunk convs; the lambdas below fill in what differs.
+  auto base = [&](int widx, int epi) {
     ConvTcDesc d{};
-    d.B = Bc; d.H = H; d.W = W; d.cin_total = 64; d.cin_off = 0; d.cout = 64; d.epi = epi; d.desc_mode = 0;
+    d.B = Bc; d.H = H; d.W = W; d.cin_total = 64; d.cin_off = 0; d.cout = 64; d.epi = epi; d.in_mode = IN_TMA;
     d.num_sms = num_sms;
-    d.in_bf16 = in; d.wpacked = cw + static_cast<size_t>(widx) * wbytes; d.bias = n->conv_b + static_cast<size_t>(widx) * 64;
-    d.out_bf16 = obf; d.out_pix_stride = pixB; d.out_row_stride = rowB; d.out_img_stride = imgB;
-    d.skip_f32 = skip; d.out_f32 = o32; d.pool_rows = w.pool;
-    return conv3x3_c64_tc(d, st);
+    d.wpacked = cw + static_cast<size_t>(widx) * wbytes; d.bias = n->conv_b + static_cast<size_t>(widx) * 64;
+    d.out_pix_stride = pixB; d.out_row_stride = rowB; d.out_img_stride = imgB;
+    d.pool_rows = w.pool;
+    return d;
   };
+  const float* attr_c = attr + static_cast<size_t>(b0) * n->attr_size;
+  const bool has_ca = n->style != DFIR_STYLE_NONE;
 
   for (int g = 0; g < ng; ++g) {
-    const float* skip32 = g == 0 ? w.Hh : w.XA;
-    const __nv_bfloat16* gin = g == 0 ? w.Hbf : w.XAbf;
+    const float* skip32 = g == 0 ? w.Hh : w.XA;            // group input (fp32 stream), kept for `res += x`
+    const __nv_bfloat16* gin = g == 0 ? w.Hbf : w.XAbf;    // its bf16 copy = operand of the first conv
+    const float* xcur = skip32;                             // x_b: fp32 stream entering block b
     for (int b = 0; b < nb; ++b) {
       const int blk = g * nb + b;
-      const void* cin = b == 0 ? static_cast<const void*>(gin) : static_cast<const void*>(w.XBbf);
-      DFIR_TRY(conv(cin, g * per_group + 2 * b, EPI_BIAS_RELU, w.T, nullptr, nullptr));
-      DFIR_TRY(conv(w.T, g * per_group + 2 * b + 1, n->style == DFIR_STYLE_NONE ? EPI_BIAS : EPI_BIAS_POOL, w.R,
-                    nullptr, nullptr));
-      const float* xin = b == 0 ? skip32 : w.XB;
-      const float* sq = n->any_q ? w.sq + (static_cast<size_t>(blk) * B + b0) * C : nullptr;
-      DFIR_TRY(scale_residual(w.R, 1, xin, w.pool, nseg * H, make_ap(n, blk), attr + static_cast<size_t>(b0) * n->attr_size,
-                              sq, 1.f, w.XB, w.XBbf, Bc, H, W, C, st));
+      // conv1: t = relu(conv(x_b)).  For b > 0 the operand x_b = r_{b-1} * s_{b-1} + x_{b-1} is formed on the
+      // fly (IN_FUSED) and written out as the new fp32 stream.
+      ConvTcDesc c1 = base(g * per_group + 2 * b, EPI_BIAS_RELU);
+      c1.out_bf16 = w.T;
+      if (b == 0) {
+        c1.in_bf16 = gin;
+      } else {
+        float* xnew = (b & 1) ? w.XB : w.XB1;
+        c1.in_mode = IN_FUSED; c1.r_bf16 = w.R; c1.xin_f32 = xcur; c1.xout_f32 = xnew; c1.svec_in = w.svec;
+        xcur = xnew;
+      }
+      DFIR_TRY(conv3x3_c64_tc(c1, st));
+      // conv2: r = conv(t), pooled rows, and (last CTA per image) s_b = CA(mean r) * meta scale
+      ConvTcDesc c2 = base(g * per_group + 2 * b + 1, has_ca ? EPI_BIAS_POOL : EPI_BIAS);
+      c2.in_bf16 = w.T; c2.out_bf16 = w.R;
+      if (has_ca) {
+        c2.svec_out = w.svec; c2.img_counter = w.counters;
+        c2.ca_params = n->ca_blob + static_cast<size_t>(blk) * n->ca_stride;
+        c2.ca_style = n->style; c2.ca_R = n->reduced; c2.ca_M = n->num_metadata; c2.ca_A = n->attr_size;
+        c2.attributes = attr_c;
+        c2.sq = n->any_q ? w.sq + (static_cast<size_t>(blk) * B + b0) * C : nullptr;
+      }
+      DFIR_TRY(conv3x3_c64_tc(c2, st));
     }
-    const void* cin = nb == 0 ? static_cast<const void*>(gin) : static_cast<const void*>(w.XBbf);
-    DFIR_TRY(conv(cin, g * per_group + 2 * nb, EPI_BIAS_SKIP, w.XAbf, skip32, w.XA));
+    // group tail conv + `res += x` (group input): its operand is x_nb = r * s + x_{nb-1}, again fused
+    ConvTcDesc ct = base(g * per_group + 2 * nb, EPI_BIAS_SKIP);
+    ct.out_bf16 = w.XAbf; ct.skip_f32 = skip32; ct.out_f32 = w.XA;
+    if (nb == 0) {
+      ct.in_bf16 = gin;
+    } else {
+      ct.in_mode = IN_FUSED; ct.r_bf16 = w.R; ct.xin_f32 = xcur; ct.xout_f32 = nullptr; ct.svec_in = w.svec;
+    }
+    DFIR_TRY(conv3x3_c64_tc(ct, st));
   }
   {
-    const void* cin = ng == 0 ? static_cast<const void*>(w.Hbf) : static_cast<const void*>(w.XAbf);
-    DFIR_TRY(conv(cin, ng * per_group, EPI_BIAS_SKIP, w.XBbf, w.Hh, nullptr));
+    ConvTcDesc cf = base(ng * per_group, EPI_BIAS_SKIP);
+    cf.in_bf16 = ng == 0 ? w.Hbf : w.XAbf;
+    cf.out_bf16 = w.XBbf; cf.skip_f32 = w.Hh; cf.out_f32 = nullptr;
+    DFIR_TRY(conv3x3_c64_tc(cf, st));
   }
   // upsampler: conv C -> r*r*C with PixelShuffle(r) folded into the TMA store strides
   int r = 0;
@@ -161,6 +192,7 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
       ConvTcDesc d{};
       const int widx = n_trunk + t * r * r + s;
       d.B = Bc; d.H = h; d.W = wd; d.cin_total = 64; d.cin_off = 0; d.cout = 64; d.epi = EPI_BIAS; d.num_sms = num_sms;
+      d.in_mode = IN_TMA;
       d.in_bf16 = cur; d.wpacked = cw + static_cast<size_t>(widx) * wbytes; d.bias = n->conv_b + static_cast<size_t>(widx) * 64;
       d.out_bf16 = U + (static_cast<long long>(i) * oW + j) * C * 2;
       d.out_pix_stride = static_cast<long long>(r) * C * 2;
@@ -278,14 +310,57 @@ int dfir_conv3x3_c64(const void* in_bf16, int cin_total, int cin_off, const void
                      float* pool_rows, int desc_mode, void* stream) {
   ConvTcDesc d{};
   d.B = B; d.H = H; d.W = W; d.cin_total = cin_total; d.cin_off = cin_off; d.cout = cout; d.epi = epi;
-  d.desc_mode = desc_mode; d.num_sms = 0;
+  d.in_mode = IN_TMA; d.num_sms = 0;
   d.in_bf16 = in_bf16; d.wpacked = wpacked; d.bias = bias; d.out_bf16 = out_bf16;
   d.out_pix_stride = out_pix_stride; d.out_row_stride = out_row_stride; d.out_img_stride = out_img_stride;
   d.skip_f32 = skip_f32; d.out_f32 = out_f32; d.pool_rows = pool_rows;
+  if (desc_mode != 0) return DFIR_ERR_ARG;  // reserved (hardware bring-up variants were removed)
   if (epi == EPI_BIAS_POOL && pool_rows == nullptr) return DFIR_ERR_ARG;
   if (epi == EPI_BIAS_SKIP && skip_f32 == nullptr) return DFIR_ERR_ARG;
   if (epi == EPI_TAIL_NCHW && (out_f32 == nullptr || cout > 16)) return DFIR_ERR_ARG;
   if (epi != EPI_TAIL_NCHW && out_bf16 == nullptr) return DFIR_ERR_ARG;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return DFIR_ERR_CUDA;
+  d.num_sms = sms;
+  return conv3x3_c64_tc(d, S(stream));
+}
+
+int dfir_conv3x3_c64_ca(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
+                        void* out_bf16, float* pool_rows, int style, const float* ca_params, int R, int M, int A,
+                        const float* attributes, const float* sq, float* svec_out, int* img_counter, void* stream) {
+  if (in_bf16 == nullptr || out_bf16 == nullptr || pool_rows == nullptr || svec_out == nullptr ||
+      img_counter == nullptr || ca_params == nullptr || style == DFIR_STYLE_NONE)
+    return DFIR_ERR_ARG;
+  ConvTcDesc d{};
+  d.B = B; d.H = H; d.W = W; d.cin_total = 64; d.cin_off = 0; d.cout = 64; d.epi = EPI_BIAS_POOL; d.in_mode = IN_TMA;
+  d.in_bf16 = in_bf16; d.wpacked = wpacked; d.bias = bias; d.out_bf16 = out_bf16;
+  d.out_pix_stride = 128; d.out_row_stride = static_cast<long long>(W) * 128;
+  d.out_img_stride = static_cast<long long>(H) * W * 128;
+  d.pool_rows = pool_rows; d.svec_out = svec_out; d.img_counter = img_counter; d.ca_params = ca_params;
+  d.ca_style = style; d.ca_R = R; d.ca_M = M; d.ca_A = A; d.attributes = attributes; d.sq = sq;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return DFIR_ERR_CUDA;
+  d.num_sms = sms;
+  return conv3x3_c64_tc(d, S(stream));
+}
+
+int dfir_conv3x3_c64_fused(const void* r_bf16, const float* x_in, const float* svec, float* x_out,
+                           const void* wpacked, const float* bias, int B, int H, int W, int epi, void* out_bf16,
+                           const float* skip_f32, float* out_f32, void* stream) {
+  if (epi != EPI_BIAS_RELU && epi != EPI_BIAS_SKIP) return DFIR_ERR_ARG;
+  if (epi == EPI_BIAS_SKIP && skip_f32 == nullptr) return DFIR_ERR_ARG;
+  if (out_bf16 == nullptr) return DFIR_ERR_ARG;
+  ConvTcDesc d{};
+  d.B = B; d.H = H; d.W = W; d.cin_total = 64; d.cin_off = 0; d.cout = 64; d.epi = epi; d.in_mode = IN_FUSED;
+  d.r_bf16 = r_bf16; d.xin_f32 = x_in; d.svec_in = svec; d.xout_f32 = x_out;
+  d.wpacked = wpacked; d.bias = bias; d.out_bf16 = out_bf16;
+  d.out_pix_stride = 128; d.out_row_stride = static_cast<long long>(W) * 128;
+  d.out_img_stride = static_cast<long long>(H) * W * 128;
+  d.skip_f32 = skip_f32; d.out_f32 = out_f32;
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess ||
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
@@ -341,7 +416,7 @@ long long dfir_qrcan_launch_count(const dfir_qrcan_net* net, int B, int H, int W
   const long long nb = net->n_blocks, ng = net->n_groups;
   long long per_chunk;
   if (precision == DFIR_PREC_BF16_TC) {
-    per_chunk = 1 + ng * (nb * 3 + 1) + 1 + static_cast<long long>(nup) * r * r + 1;
+    per_chunk = 1 + ng * (nb * 2 + 1) + 1 + static_cast<long long>(nup) * r * r + 1;
   } else {
     const long long pool = net->style != DFIR_STYLE_NONE ? 1 : 0;
     per_chunk = 1 + ng * (nb * (3 + pool) + 2) + 1 + nup + 1;  // group tail = conv + copy
@@ -366,6 +441,9 @@ int dfir_qrcan_forward(const dfir_qrcan_net* net, const float* x_nchw, const flo
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess ||
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return DFIR_ERR_CUDA;
+  if (precision == DFIR_PREC_BF16_TC &&
+      cudaMemsetAsync(w.counters, 0, static_cast<size_t>(Bc) * sizeof(int), st) != cudaSuccess)
     return DFIR_ERR_CUDA;
   if (net->any_q) {
     DFIR_TRY(meta_attention(attributes, net->meta_w1, net->meta_b1, net->meta_w2, net->meta_b2, w.sq,

@@ -1,0 +1,100 @@
+// Channel-attention vector of QCALayer (all styles) as a cooperative device routine, usable from any
+// thread group: `G` supplies the group's thread id, size and barrier.
+//   reference: /root/reference/Code/SISR/models/attention_manipulators/architectures.py:105-125
+// parameter order inside `p` (fp32, contiguous) for C channels, R = C/reduction, M metadata entries:
+//   standard/modulate : W1[R][C]     b1[R]   W2[C][R]       b2[C]
+//   max_concat/softmax: W1[R][C+M]   b1[R]   W2[C][R]       b2[C]
+//   mini_concat       : Wp[R][C]     bp[R]   W2[C][R+M]     b2[C]
+//   extended_attention: W1[C/2][C+M] b1  W2[C/4][C/2+M] b2  W3[R][C/4+M] b3  W4[C][R] b4
+#pragma once
+#include "../../include/dfir.h"
+
+namespace dfir {
+
+struct BlockGroup {  // the whole thread block
+  __device__ __forceinline__ int tid() const { return threadIdx.x; }
+  __device__ __forceinline__ int size() const { return blockDim.x; }
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+
+struct NamedGroup {  // a subset of warps synchronised through a named barrier
+  int t, n, id;
+  __device__ __forceinline__ int tid() const { return t; }
+  __device__ __forceinline__ int size() const { return n; }
+  __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+};
+
+template <class G>
+__device__ void fc_layer(const G& g, const float* __restrict__ w, const float* __restrict__ bias, const float* in_a,
+                         int na, const float* in_b, int nb, float* out, int nout,
+                         int act /*0 none, 1 relu, 2 sigmoid*/) {
+  for (int o = g.tid(); o < nout; o += g.size()) {
+    const float* wr = w + static_cast<size_t>(o) * (na + nb);
+    float s = bias[o];
+    for (int i = 0; i < na; ++i) s = fmaf(wr[i], in_a[i], s);
+    for (int i = 0; i < nb; ++i) s = fmaf(wr[na + i], in_b[i], s);
+    if (act == 1) s = fmaxf(s, 0.f);
+    if (act == 2) s = 1.f / (1.f + expf(-s));
+    out[o] = s;
+  }
+  g.sync();
+}
+
+// y_s[C]: pooled means (in);  s_s[C]: attention scale (out);  attr_s[A]: this image's attributes;
+// tmp: >= 64 + C + M floats of scratch.  All pointers are shared memory visible to the whole group.
+template <class G>
+__device__ void attn_vector(const G& g, int style, const float* __restrict__ p, int C, int R, int M,
+                            const float* attr_s, const float* y_s, float* s_s, float* tmp) {
+  if (style == DFIR_STYLE_STANDARD || style == DFIR_STYLE_MODULATE) {
+    const float* W1 = p; const float* b1 = W1 + R * C; const float* W2 = b1 + R; const float* b2 = W2 + C * R;
+    fc_layer(g, W1, b1, y_s, C, nullptr, 0, tmp, R, 1);
+    fc_layer(g, W2, b2, tmp, R, nullptr, 0, s_s, C, 2);
+    if (style == DFIR_STYLE_MODULATE) {
+      for (int c = g.tid(); c < C; c += g.size()) s_s[c] *= attr_s[c];
+      g.sync();
+    }
+  } else if (style == DFIR_STYLE_MAX_CONCAT || style == DFIR_STYLE_SOFTMAX) {
+    const float* W1 = p; const float* b1 = W1 + R * (C + M); const float* W2 = b1 + R; const float* b2 = W2 + C * R;
+    fc_layer(g, W1, b1, y_s, C, attr_s, M, tmp, R, 1);
+    fc_layer(g, W2, b2, tmp, R, nullptr, 0, s_s, C, 2);
+    if (style == DFIR_STYLE_SOFTMAX) {
+      // softmax over the C channels applied AFTER the sigmoid (architectures.py:100-101,119-121)
+      if (g.tid() == 0) {
+        float mx = -1e30f;
+        for (int c = 0; c < C; ++c) mx = fmaxf(mx, s_s[c]);
+        float sum = 0.f;
+        for (int c = 0; c < C; ++c) sum += expf(s_s[c] - mx);
+        tmp[0] = mx;
+        tmp[1] = sum;
+      }
+      g.sync();
+      const float mx = tmp[0], sum = tmp[1];
+      g.sync();
+      for (int c = g.tid(); c < C; c += g.size()) s_s[c] = expf(s_s[c] - mx) / sum;
+      g.sync();
+    }
+  } else if (style == DFIR_STYLE_MINI_CONCAT) {
+    const float* Wp = p; const float* bp = Wp + R * C; const float* W2 = bp + R; const float* b2 = W2 + C * (R + M);
+    fc_layer(g, Wp, bp, y_s, C, nullptr, 0, tmp, R, 0);
+    // conv_du = Sequential(ReLU, Conv, Sigmoid) on cat(pre, attributes): the ReLU hits both parts
+    for (int i = g.tid(); i < R + M; i += g.size()) {
+      const float v = i < R ? tmp[i] : attr_s[i - R];
+      tmp[64 + i] = fmaxf(v, 0.f);
+    }
+    g.sync();
+    fc_layer(g, W2, b2, tmp + 64, R + M, nullptr, 0, s_s, C, 2);
+  } else if (style == DFIR_STYLE_EXTENDED) {
+    const int c2 = C / 2, c4 = C / 4;
+    const float* W1 = p; const float* b1 = W1 + c2 * (C + M);
+    const float* W2 = b1 + c2; const float* b2 = W2 + c4 * (c2 + M);
+    const float* W3 = b2 + c4; const float* b3 = W3 + R * (c4 + M);
+    const float* W4 = b3 + R; const float* b4 = W4 + C * R;
+    float* t1 = tmp; float* t2 = tmp + c2; float* t3 = t2 + c4;
+    fc_layer(g, W1, b1, y_s, C, attr_s, M, t1, c2, 1);
+    fc_layer(g, W2, b2, t1, c2, attr_s, M, t2, c4, 1);
+    fc_layer(g, W3, b3, t2, c4, attr_s, M, t3, R, 1);
+    fc_layer(g, W4, b4, t3, R, nullptr, 0, s_s, C, 2);
+  }
+}
+
+}  // namespace dfir

@@ -18,13 +18,27 @@ enum : int {
   EPI_TAIL_NCHW = 4,  // out_f32 NCHW, cout<=16 real channels          (tail conv 64 -> 3, :303)
 };
 
+enum : int { IN_TMA = 0, IN_FUSED = 1 };  // input modes of the tensor-core conv (see conv_tc.cu)
+
 struct ConvTcArgs {  // kernel argument block
-  int B, H, W, nseg, cin_off, cout, desc_mode;
+  int B, H, W, nseg, cin_off, cout;
   const void* wpacked;
   const float* bias;
   const float* skip_f32;
   float* out_f32;
   float* pool_rows;
+  // IN_FUSED: conv input = r * svec_in[b] + xin   (xout = fp32 copy of it for the rows the CTA owns)
+  const __nv_bfloat16* r_bf16;
+  const float* xin_f32;
+  float* xout_f32;
+  const float* svec_in;
+  // attention tail of EPI_BIAS_POOL (optional): svec_out[b][64] = CA(mean(r)) * sq[b]
+  float* svec_out;
+  int* img_counter;
+  const float* ca_params;
+  const float* attributes;
+  const float* sq;
+  int ca_style, ca_R, ca_M, ca_A;
 };
 
 struct ConvTcDesc {  // host-side launch description
@@ -32,7 +46,7 @@ struct ConvTcDesc {  // host-side launch description
   int cin_total, cin_off;  // channels of the input tensor / first channel of the 64-wide slice consumed
   int cout;                // real output channels (tail only)
   int epi;
-  int desc_mode;           // 0: descriptor base_offset 0 (correct on B200); 1: base_offset = swizzle phase (bring-up test)
+  int in_mode;             // IN_TMA | IN_FUSED
   int num_sms;
   const void* in_bf16;
   const void* wpacked;
@@ -42,6 +56,16 @@ struct ConvTcDesc {  // host-side launch description
   const float* skip_f32;
   float* out_f32;
   float* pool_rows;
+  const void* r_bf16;      // IN_FUSED
+  const float* xin_f32;
+  float* xout_f32;
+  const float* svec_in;
+  float* svec_out;         // attention tail (EPI_BIAS_POOL)
+  int* img_counter;
+  const float* ca_params;
+  const float* attributes;
+  const float* sq;
+  int ca_style, ca_R, ca_M, ca_A;
 };
 
 int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream);

@@ -2,6 +2,7 @@
 // attention-vector kernels and the fused channel-scale + residual streamer.  These are the HBM / latency
 // bound pieces: they are written for coalesced 16-byte accesses, not tensor cores.
 #include "kernels.h"
+#include "attn.cuh"
 
 namespace dfir {
 
@@ -224,84 +225,6 @@ __global__ void meta_attention_kernel(const float* __restrict__ meta, const floa
 }
 
 // ------------------------------------------------------------------------------------------------
-// channel attention vector (all QCALayer styles) — executed redundantly by every CTA of the streamer for
-// its image: <= 74x32 + ... MACs, nothing compared with the pixels it then streams.
-//   y_s[C] : pooled means (in), s_s[C] : attention scale (out); tmp: >= C + A + 64 floats of scratch
-// parameter order inside `p` (fp32, contiguous):
-//   standard/modulate : W1[R][C]   b1[R]  W2[C][R]    b2[C]
-//   max_concat/softmax: W1[R][C+M] b1[R]  W2[C][R]    b2[C]
-//   mini_concat       : Wp[R][C]   bp[R]  W2[C][R+M]  b2[C]
-//   extended_attention: W1[C/2][C+M] b1 W2[C/4][C/2+M] b2 W3[R][C/4+M] b3 W4[C][R] b4
-// ------------------------------------------------------------------------------------------------
-__device__ void fc_layer(const float* __restrict__ w, const float* __restrict__ bias, const float* in_a, int na,
-                         const float* in_b, int nb, float* out, int nout, int act /*0 none,1 relu,2 sigmoid*/) {
-  for (int o = threadIdx.x; o < nout; o += blockDim.x) {
-    const float* wr = w + static_cast<size_t>(o) * (na + nb);
-    float s = bias[o];
-    for (int i = 0; i < na; ++i) s = fmaf(wr[i], in_a[i], s);
-    for (int i = 0; i < nb; ++i) s = fmaf(wr[na + i], in_b[i], s);
-    if (act == 1) s = fmaxf(s, 0.f);
-    if (act == 2) s = 1.f / (1.f + expf(-s));
-    out[o] = s;
-  }
-  __syncthreads();
-}
-
-__device__ void attn_vector(int style, const float* __restrict__ p, int C, int R, int M, const float* attr_s,
-                            const float* y_s, float* s_s, float* tmp) {
-  if (style == DFIR_STYLE_STANDARD || style == DFIR_STYLE_MODULATE) {
-    const float* W1 = p; const float* b1 = W1 + R * C; const float* W2 = b1 + R; const float* b2 = W2 + C * R;
-    fc_layer(W1, b1, y_s, C, nullptr, 0, tmp, R, 1);
-    fc_layer(W2, b2, tmp, R, nullptr, 0, s_s, C, 2);
-    if (style == DFIR_STYLE_MODULATE) {
-      for (int c = threadIdx.x; c < C; c += blockDim.x) s_s[c] *= attr_s[c];
-      __syncthreads();
-    }
-  } else if (style == DFIR_STYLE_MAX_CONCAT || style == DFIR_STYLE_SOFTMAX) {
-    const float* W1 = p; const float* b1 = W1 + R * (C + M); const float* W2 = b1 + R; const float* b2 = W2 + C * R;
-    fc_layer(W1, b1, y_s, C, attr_s, M, tmp, R, 1);
-    fc_layer(W2, b2, tmp, R, nullptr, 0, s_s, C, 2);
-    if (style == DFIR_STYLE_SOFTMAX) {
-      // softmax over the C channels applied after the sigmoid (architectures.py:100-101,119-121)
-      if (threadIdx.x == 0) {
-        float mx = -1e30f;
-        for (int c = 0; c < C; ++c) mx = fmaxf(mx, s_s[c]);
-        float sum = 0.f;
-        for (int c = 0; c < C; ++c) sum += expf(s_s[c] - mx);
-        tmp[0] = mx;
-        tmp[1] = sum;
-      }
-      __syncthreads();
-      const float mx = tmp[0], sum = tmp[1];
-      __syncthreads();
-      for (int c = threadIdx.x; c < C; c += blockDim.x) s_s[c] = expf(s_s[c] - mx) / sum;
-      __syncthreads();
-    }
-  } else if (style == DFIR_STYLE_MINI_CONCAT) {
-    const float* Wp = p; const float* bp = Wp + R * C; const float* W2 = bp + R; const float* b2 = W2 + C * (R + M);
-    fc_layer(Wp, bp, y_s, C, nullptr, 0, tmp, R, 0);
-    // conv_du = Sequential(ReLU, Conv, Sigmoid) applied to cat(pre, attributes): the ReLU hits both parts
-    for (int i = threadIdx.x; i < R + M; i += blockDim.x) {
-      const float v = i < R ? tmp[i] : attr_s[i - R];
-      tmp[64 + i] = fmaxf(v, 0.f);
-    }
-    __syncthreads();
-    fc_layer(W2, b2, tmp + 64, R + M, nullptr, 0, s_s, C, 2);
-  } else if (style == DFIR_STYLE_EXTENDED) {
-    const int c2 = C / 2, c4 = C / 4;
-    const float* W1 = p; const float* b1 = W1 + c2 * (C + M);
-    const float* W2 = b1 + c2; const float* b2 = W2 + c4 * (c2 + M);
-    const float* W3 = b2 + c4; const float* b3 = W3 + R * (c4 + M);
-    const float* W4 = b3 + R; const float* b4 = W4 + C * R;
-    float* t1 = tmp; float* t2 = tmp + c2; float* t3 = t2 + c4;
-    fc_layer(W1, b1, y_s, C, attr_s, M, t1, c2, 1);
-    fc_layer(W2, b2, t1, c2, attr_s, M, t2, c4, 1);
-    fc_layer(W3, b3, t2, c4, attr_s, M, t3, R, 1);
-    fc_layer(W4, b4, t3, R, nullptr, 0, s_s, C, 2);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // fused: pool finalise -> attention vector -> x_out = r * s + x_in (fp32) (+ bf16 copy)
 // grid (ctas_per_image, B), 256 threads; each thread streams 8 channels of a pixel per iteration.
 // ------------------------------------------------------------------------------------------------
@@ -336,7 +259,7 @@ scale_residual_kernel(const void* __restrict__ r_, const float* __restrict__ x_i
       y_s[tid] = t / static_cast<float>(HW);
     }
     __syncthreads();
-    attn_vector(ap.style, ap.w[0], C, ap.R, ap.M, attr_s, y_s, s_s, tmp);
+    attn_vector(BlockGroup{}, ap.style, ap.w[0], C, ap.R, ap.M, attr_s, y_s, s_s, tmp);
     if (tid < C) s_s[tid] *= (sq != nullptr ? sq[static_cast<size_t>(b) * C + tid] : 1.f);
   } else {
     if (tid < C) s_s[tid] = res_scale * (sq != nullptr ? sq[static_cast<size_t>(b) * C + tid] : 1.f);

@@ -1,0 +1,104 @@
+"""Micro-benchmarks on the GPU box: trunk conv and scale-residual vs images per launch, and the full
+forward vs chunk size.  Prints one line per measurement."""
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "super-resolution-meta-attention-networks_b200"))
+import torch
+from deepfir_b200 import _lib
+from deepfir_b200.qrcan import QRCAN
+
+lib = _lib.load_library()
+dev = torch.device("cuda")
+LR = int(os.environ.get("LR", "128"))
+st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def timeit(fn, n=60, warm=10):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3  # us
+
+
+BCS = tuple(int(t) for t in os.environ.get("BC", "1,2,4,7,8,9,16,32,64").split(","))
+NREP = [60, 10]
+
+
+def conv_sweep(epi):
+    wp = torch.empty(9 * 64 * 128, dtype=torch.uint8, device=dev)
+    w = (torch.randn(64, 64, 3, 3, device=dev) / 24).contiguous()
+    bias = torch.zeros(64, device=dev)
+    _lib.check(lib.dfir_pack_conv3x3_bf16(w.data_ptr(), wp.data_ptr(), 64, 64, 64, 0, 1, st()), "pack")
+    for bc in BCS:
+        a = torch.randn(bc, LR, LR, 64, device=dev).to(torch.bfloat16)
+        b = torch.empty_like(a)
+        pool = torch.empty(bc, LR, 64, device=dev)
+        flip = [a, b]
+
+        def launch():
+            src, dst = flip
+            _lib.check(lib.dfir_conv3x3_c64(src.data_ptr(), 64, 0, wp.data_ptr(), bias.data_ptr(), bc, LR, LR, epi, 64,
+                                            dst.data_ptr(), 128, LR * 128, LR * LR * 128, None, None, pool.data_ptr(),
+                                            0, st()), "conv")
+            flip.reverse()
+        us = timeit(launch, NREP[0], NREP[1])
+        fl = bc * LR * LR * 2 * 64 * 64 * 9
+        rows = bc * LR / 148.0
+        print("conv epi=%d bc=%3d: %8.2f us  %7.1f TFLOP/s  rows/CTA %.2f  us/row-slot %.3f" %
+              (epi, bc, us, fl / us / 1e6, rows, us / max(1.0, -(-bc * LR // 148))))
+
+
+def sr_sweep():
+    for bc in (1, 4, 7, 8, 16, 32):
+        r = torch.randn(bc, LR, LR, 64, device=dev).to(torch.bfloat16)
+        x = torch.randn(bc, LR, LR, 64, device=dev)
+        xb = torch.empty(bc, LR, LR, 64, device=dev, dtype=torch.bfloat16)
+        pool = torch.randn(bc, LR, 64, device=dev)
+        blob = torch.randn(4 * 64 + 4 + 64 * 4 + 64, device=dev) / 8
+        attr = torch.rand(bc, 10, device=dev)
+        sq = torch.rand(bc, 64, device=dev)
+
+        def launch():
+            _lib.check(lib.dfir_ca_scale_residual(r.data_ptr(), 1, x.data_ptr(), pool.data_ptr(), LR, 1, blob.data_ptr(),
+                                                  64, 4, 10, 10, attr.data_ptr(), sq.data_ptr(), 1.0, x.data_ptr(),
+                                                  xb.data_ptr(), bc, LR, LR, st()), "sr")
+        us = timeit(launch)
+        byt = bc * LR * LR * 64 * 12
+        print("scale_residual bc=%3d: %8.2f us  %7.1f GB/s (12 B/elem algorithmic)" % (bc, us, byt / us / 1e3))
+
+
+def forward_sweep():
+    torch.manual_seed(8)
+    B = 32
+    x = torch.rand(B, 3, LR, LR, device=dev)
+    meta = torch.rand(B, 10, 1, 1, device=dev) * 0.4
+    for chunk in (4, 7, 8, 9, 16, 32):
+        net = QRCAN(n_resgroups=10, n_resblocks=20, style="standard", num_metadata=10, include_q_layer=True,
+                    precision="bf16", chunk_images=chunk).to(dev).eval()
+        with torch.no_grad():
+            us = timeit(lambda: net(x, meta), n=3, warm=2)
+        print("forward B=32 chunk=%2d: %8.2f ms  %7.1f MPix/s" % (chunk, us / 1e3, B * (4 * LR) ** 2 / us))
+        del net
+
+
+which = sys.argv[1:] or ["conv", "sr", "fwd"]
+if "conv" in which:
+    conv_sweep(1)
+    conv_sweep(2)
+if "sr" in which:
+    sr_sweep()
+if "fwd" in which:
+    forward_sweep()
+if "one" in which:  # few launches of selected shapes, for ncu (BC=32 python tools/conv_bench.py one)
+    NREP[:] = [4, 2]
+    conv_sweep(int(os.environ.get("EPI", "1")))
