@@ -87,23 +87,19 @@ int dfir_conv3x3_c64(const void* in_bf16, int cin_total, int cin_off, const void
                      long long out_row_stride, long long out_img_stride, const float* skip_f32, float* out_f32,
                      float* pool_rows, int desc_mode, void* stream);
 
-/* RCAB conv2 with the channel-attention vector computed in its tail (QRCAB.body[2] + QCALayer up to the
- * `x * y`, attention_manipulators/architectures.py:105-125,173-175; ParaCALayer scale folded in):
- *   out_bf16 = conv(in) + bias (NHWC bf16, dense);  pool_rows[B][nseg][H][64] = per-row channel sums;
- *   svec_out[b][c] = CA_style(mean_b, attributes[b]) * (sq ? sq[b][c] : 1), written by the last CTA that
- *   finishes image b.  img_counter: int32 [B], zero on entry (the kernel leaves it zero again). */
-int dfir_conv3x3_c64_ca(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
-                        void* out_bf16, float* pool_rows, int style, const float* ca_params, int R, int M, int A,
-                        const float* attributes, const float* sq, float* svec_out, int* img_counter, void* stream);
-
-/* Conv whose operand is formed on the fly from the previous block: x' = r * svec[b] + x_in
- * (`res * y` and `res += x`, attention_manipulators/architectures.py:127,179; q_layer.py:43), then
- * default_conv(x').  r: NHWC bf16; x_in: NHWC fp32 residual stream; x_out (optional, must not alias x_in):
- * NHWC fp32 copy of x'.  epi: 1 (bias+ReLU -> out_bf16) or 3 (bias + skip_f32 -> out_f32 [optional] and
- * out_bf16). */
-int dfir_conv3x3_c64_fused(const void* r_bf16, const float* x_in, const float* svec, float* x_out,
-                           const void* wpacked, const float* bias, int B, int H, int W, int epi, void* out_bf16,
-                           const float* skip_f32, float* out_f32, void* stream);
+/* Conv whose operand is formed on the fly from the previous block (the channel-attention / meta-attention
+ * scale and the residual add of QRCAB, attention_manipulators/architectures.py:105-127,172-180; q_layer.py:43;
+ * ParamResBlock :346-356 with style NONE):
+ *     s[b]  = CA_style(mean over pixels of r_b, attributes[b]) * (sq ? sq[b] : 1)   (style NONE: res_scale * sq)
+ *     x'    = r * s[b] + x_in ;   out = default_conv(bf16(x'))
+ *   r: NHWC bf16; pool_rows[B][nseg][H][64]: per-row channel sums of r (from dfir_conv3x3_c64 epi 2);
+ *   x_in: NHWC fp32 residual stream; x_out (optional, must not alias x_in): NHWC fp32 copy of x';
+ *   ca_params: the block's QCALayer parameters (DESIGN.md "attention parameter blob"), R = 64/reduction.
+ *   epi: 1 (bias+ReLU -> out_bf16) or 3 (bias + skip_f32 -> out_f32 [optional] and out_bf16). */
+int dfir_conv3x3_c64_fused(const void* r_bf16, const float* x_in, float* x_out, const float* pool_rows, int style,
+                           const float* ca_params, int R, int M, int A, const float* attributes, const float* sq,
+                           float res_scale, const void* wpacked, const float* bias, int B, int H, int W, int epi,
+                           void* out_bf16, const float* skip_f32, float* out_f32, void* stream);
 
 /* default_conv on CUDA cores, fp32 NHWC in/out, any Cin % 4 == 0 and any Cout.
  *   w_packed from dfir_pack_conv3x3_f32; skip (optional) NHWC fp32 added after bias; relu applied last;

@@ -42,8 +42,7 @@ int auto_chunk(int B, int H, int W, int precision) {
 }
 
 struct QrcanWs {
-  float *Hh, *XA, *XB, *XB1, *pool, *sq, *svec;
-  int* counters;
+  float *Hh, *XA, *XB, *XB1, *pool, *sq;
   __nv_bfloat16 *Hbf, *XAbf, *XBbf, *T, *R;
   float *T32, *R32;
   void* U[3];
@@ -61,8 +60,6 @@ QrcanWs carve_qrcan(const dfir_qrcan_net* n, int B, int Bc, int H, int W, int pr
   const int nseg = (W + 127) / 128;
   w.pool = c.take<float>(static_cast<size_t>(Bc) * nseg * H * C * 4);
   w.sq = c.take<float>(static_cast<size_t>(n->n_groups) * n->n_blocks * B * C * 4);
-  w.svec = c.take<float>(static_cast<size_t>(Bc) * C * 4);
-  w.counters = c.take<int>(static_cast<size_t>(Bc) * 4);
   int r = 0;
   const int nup = up_stages(n->scale, &r);
   if (precision == DFIR_PREC_BF16_TC) {
@@ -131,7 +128,14 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
     return d;
   };
   const float* attr_c = attr + static_cast<size_t>(b0) * n->attr_size;
-  const bool has_ca = n->style != DFIR_STYLE_NONE;
+  // operand of a fused conv: x_{b} = r_{b-1} * s_{b-1} + x_{b-1}, with s_{b-1} evaluated in the kernel prologue
+  auto fuse_in = [&](ConvTcDesc& d, int prev_blk, const float* xprev, float* xnew) {
+    d.in_mode = IN_FUSED; d.r_bf16 = w.R; d.xin_f32 = xprev; d.xout_f32 = xnew;
+    d.ca_style = n->style; d.ca_R = n->reduced; d.ca_M = n->num_metadata; d.ca_A = n->attr_size;
+    d.ca_params = n->ca_blob + static_cast<size_t>(prev_blk) * n->ca_stride;
+    d.attributes = attr_c; d.res_scale = 1.f;
+    d.sq = n->any_q ? w.sq + (static_cast<size_t>(prev_blk) * B + b0) * C : nullptr;
+  };
 
   for (int g = 0; g < ng; ++g) {
     const float* skip32 = g == 0 ? w.Hh : w.XA;            // group input (fp32 stream), kept for `res += x`
@@ -139,28 +143,21 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
     const float* xcur = skip32;                             // x_b: fp32 stream entering block b
     for (int b = 0; b < nb; ++b) {
       const int blk = g * nb + b;
-      // conv1: t = relu(conv(x_b)).  For b > 0 the operand x_b = r_{b-1} * s_{b-1} + x_{b-1} is formed on the
-      // fly (IN_FUSED) and written out as the new fp32 stream.
+      // conv1: t = relu(conv(x_b)).  For b > 0 the operand x_b is formed on the fly (IN_FUSED) and written
+      // out as the new fp32 stream.
       ConvTcDesc c1 = base(g * per_group + 2 * b, EPI_BIAS_RELU);
       c1.out_bf16 = w.T;
       if (b == 0) {
         c1.in_bf16 = gin;
       } else {
         float* xnew = (b & 1) ? w.XB : w.XB1;
-        c1.in_mode = IN_FUSED; c1.r_bf16 = w.R; c1.xin_f32 = xcur; c1.xout_f32 = xnew; c1.svec_in = w.svec;
+        fuse_in(c1, blk - 1, xcur, xnew);
         xcur = xnew;
       }
       DFIR_TRY(conv3x3_c64_tc(c1, st));
-      // conv2: r = conv(t), pooled rows, and (last CTA per image) s_b = CA(mean r) * meta scale
-      ConvTcDesc c2 = base(g * per_group + 2 * b + 1, has_ca ? EPI_BIAS_POOL : EPI_BIAS);
+      // conv2: r = conv(t) + per-row pooled sums (the avg-pool of the channel attention)
+      ConvTcDesc c2 = base(g * per_group + 2 * b + 1, EPI_BIAS_POOL);
       c2.in_bf16 = w.T; c2.out_bf16 = w.R;
-      if (has_ca) {
-        c2.svec_out = w.svec; c2.img_counter = w.counters;
-        c2.ca_params = n->ca_blob + static_cast<size_t>(blk) * n->ca_stride;
-        c2.ca_style = n->style; c2.ca_R = n->reduced; c2.ca_M = n->num_metadata; c2.ca_A = n->attr_size;
-        c2.attributes = attr_c;
-        c2.sq = n->any_q ? w.sq + (static_cast<size_t>(blk) * B + b0) * C : nullptr;
-      }
       DFIR_TRY(conv3x3_c64_tc(c2, st));
     }
     // group tail conv + `res += x` (group input): its operand is x_nb = r * s + x_{nb-1}, again fused
@@ -169,7 +166,7 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
     if (nb == 0) {
       ct.in_bf16 = gin;
     } else {
-      ct.in_mode = IN_FUSED; ct.r_bf16 = w.R; ct.xin_f32 = xcur; ct.xout_f32 = nullptr; ct.svec_in = w.svec;
+      fuse_in(ct, g * nb + nb - 1, xcur, nullptr);
     }
     DFIR_TRY(conv3x3_c64_tc(ct, st));
   }
@@ -327,36 +324,18 @@ int dfir_conv3x3_c64(const void* in_bf16, int cin_total, int cin_off, const void
   return conv3x3_c64_tc(d, S(stream));
 }
 
-int dfir_conv3x3_c64_ca(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
-                        void* out_bf16, float* pool_rows, int style, const float* ca_params, int R, int M, int A,
-                        const float* attributes, const float* sq, float* svec_out, int* img_counter, void* stream) {
-  if (in_bf16 == nullptr || out_bf16 == nullptr || pool_rows == nullptr || svec_out == nullptr ||
-      img_counter == nullptr || ca_params == nullptr || style == DFIR_STYLE_NONE)
-    return DFIR_ERR_ARG;
-  ConvTcDesc d{};
-  d.B = B; d.H = H; d.W = W; d.cin_total = 64; d.cin_off = 0; d.cout = 64; d.epi = EPI_BIAS_POOL; d.in_mode = IN_TMA;
-  d.in_bf16 = in_bf16; d.wpacked = wpacked; d.bias = bias; d.out_bf16 = out_bf16;
-  d.out_pix_stride = 128; d.out_row_stride = static_cast<long long>(W) * 128;
-  d.out_img_stride = static_cast<long long>(H) * W * 128;
-  d.pool_rows = pool_rows; d.svec_out = svec_out; d.img_counter = img_counter; d.ca_params = ca_params;
-  d.ca_style = style; d.ca_R = R; d.ca_M = M; d.ca_A = A; d.attributes = attributes; d.sq = sq;
-  int dev = 0, sms = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess ||
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-    return DFIR_ERR_CUDA;
-  d.num_sms = sms;
-  return conv3x3_c64_tc(d, S(stream));
-}
-
-int dfir_conv3x3_c64_fused(const void* r_bf16, const float* x_in, const float* svec, float* x_out,
-                           const void* wpacked, const float* bias, int B, int H, int W, int epi, void* out_bf16,
-                           const float* skip_f32, float* out_f32, void* stream) {
+int dfir_conv3x3_c64_fused(const void* r_bf16, const float* x_in, float* x_out, const float* pool_rows, int style,
+                           const float* ca_params, int R, int M, int A, const float* attributes, const float* sq,
+                           float res_scale, const void* wpacked, const float* bias, int B, int H, int W, int epi,
+                           void* out_bf16, const float* skip_f32, float* out_f32, void* stream) {
   if (epi != EPI_BIAS_RELU && epi != EPI_BIAS_SKIP) return DFIR_ERR_ARG;
   if (epi == EPI_BIAS_SKIP && skip_f32 == nullptr) return DFIR_ERR_ARG;
-  if (out_bf16 == nullptr) return DFIR_ERR_ARG;
+  if (out_bf16 == nullptr || r_bf16 == nullptr || x_in == nullptr) return DFIR_ERR_ARG;
   ConvTcDesc d{};
   d.B = B; d.H = H; d.W = W; d.cin_total = 64; d.cin_off = 0; d.cout = 64; d.epi = epi; d.in_mode = IN_FUSED;
-  d.r_bf16 = r_bf16; d.xin_f32 = x_in; d.svec_in = svec; d.xout_f32 = x_out;
+  d.r_bf16 = r_bf16; d.xin_f32 = x_in; d.xout_f32 = x_out; d.pool_rows = const_cast<float*>(pool_rows);
+  d.ca_style = style; d.ca_params = ca_params; d.ca_R = R; d.ca_M = M; d.ca_A = A; d.attributes = attributes;
+  d.sq = sq; d.res_scale = res_scale;
   d.wpacked = wpacked; d.bias = bias; d.out_bf16 = out_bf16;
   d.out_pix_stride = 128; d.out_row_stride = static_cast<long long>(W) * 128;
   d.out_img_stride = static_cast<long long>(H) * W * 128;
@@ -441,9 +420,6 @@ int dfir_qrcan_forward(const dfir_qrcan_net* net, const float* x_nchw, const flo
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess ||
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-    return DFIR_ERR_CUDA;
-  if (precision == DFIR_PREC_BF16_TC &&
-      cudaMemsetAsync(w.counters, 0, static_cast<size_t>(Bc) * sizeof(int), st) != cudaSuccess)
     return DFIR_ERR_CUDA;
   if (net->any_q) {
     DFIR_TRY(meta_attention(attributes, net->meta_w1, net->meta_b1, net->meta_w2, net->meta_b2, w.sq,

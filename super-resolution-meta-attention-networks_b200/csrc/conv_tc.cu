@@ -26,8 +26,8 @@
 //              (fp32 residual stream), form x', write it back as the new fp32 stream for the rows the CTA
 //              owns, and deposit bf16(x') straight into the swizzled ring slot the tensor core reads.  The
 //              separate elementwise pass (and its 12 B/element of traffic) disappears (448 threads).
-// Attention tail (EPI_BIAS_POOL with a.svec_out): the last CTA to finish an image's rows turns the per-row
-// pooled sums into the block's attention vector s = CA(mean) * meta_scale (attn.cuh) for that image.
+//              The attention vector s = CA_style(pooled mean, attributes) * meta_scale (attn.cuh) is
+//              evaluated by the same warps in the kernel prologue, hidden behind the weight load.
 #include "ptx.cuh"
 #include "kernels.h"
 #include "attn.cuh"
@@ -49,6 +49,7 @@ constexpr int kAcc = 4;                      // TMEM accumulator buffers
 constexpr int kStageBytes = 128 * 128;       // one output row segment, bf16
 constexpr int kThreads = 192;            // IN_TMA
 constexpr int kThreadsFused = 192 + 256;  // + two transform groups of 4 warps
+constexpr int kMaxBandImages = 8;         // a CTA's row band may touch at most this many images (IN_FUSED)
 
 template <int NT>
 struct SmemLayout {
@@ -59,8 +60,8 @@ struct SmemLayout {
   static constexpr int off_bias = off_stage + 2 * kStageBytes;
   static constexpr int off_pool = off_bias + 64 * 4;
   static constexpr int off_attn = off_pool + 4 * 64 * 4;          // y[64] s[64] attr[512] tmp[1024] flag
-  static constexpr int off_svec = off_attn + (64 + 64 + 512 + 1024 + 4) * 4;  // s of the image(s) in flight, 2x64
-  static constexpr int off_bars = off_svec + 2 * 64 * 4;
+  static constexpr int off_svec = off_attn + (64 + 64 + 512 + 1024 + 4) * 4;  // s of the images of this band
+  static constexpr int off_bars = off_svec + kMaxBandImages * 64 * 4;
   static constexpr int n_bars = 2 * kSlots + 2 * kAcc + 1;
   static constexpr int off_tmem = off_bars + n_bars * 8;
   static constexpr int total = off_tmem + 16;
@@ -216,12 +217,57 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       // ===================== fused input transform (IN_FUSED only; warps 6..13) =====================
       if constexpr (INMODE == IN_FUSED) {
         const int tt = threadIdx.x - kThreads;  // 0..255
-        const int tg = tt >> 7;                 // group: handles ring sequence indices n = tg (mod 2)
+        // ---- prologue (overlaps the weight load): attention vectors of the images this band touches.
+        //      s[b] = CA_style(mean over pixels of r_b, attributes[b]) * meta_scale[b]; the pooled mean is
+        //      rebuilt from the per-row sums in a fixed order, so it is bit-identical in every CTA.
+        const int rows_img = nseg * H;
+        const int b_first = g0 / rows_img, b_last = (g1 - 1) / rows_img;
+        {
+          float* y_s = attn_s;
+          float* s_s = attn_s + 64;
+          float* attr_s = attn_s + 128;
+          float* tmp = attn_s + 128 + 512;
+          const NamedGroup grp{tt, 256, 5};
+          for (int b = b_first; b <= b_last; ++b) {
+            float* s_img = svec_s + (b - b_first) * 64;
+            if (a.ca_style == DFIR_STYLE_NONE) {
+              if (tt < 64) s_img[tt] = a.res_scale * (a.sq != nullptr ? a.sq[static_cast<size_t>(b) * 64 + tt] : 1.f);
+              grp.sync();
+              continue;
+            }
+            const int cq = tt & 15, rg = tt >> 4;  // channel quad, row group (16 groups)
+            const float4* pr = reinterpret_cast<const float4*>(a.pool_rows + static_cast<size_t>(b) * rows_img * 64) + cq;
+            float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int row = rg; row < rows_img; row += 16) {
+              const float4 v = pr[static_cast<size_t>(row) * 16];
+              acc4.x += v.x; acc4.y += v.y; acc4.z += v.z; acc4.w += v.w;
+            }
+            reinterpret_cast<float4*>(tmp)[rg * 16 + cq] = acc4;
+            for (int i = tt; i < a.ca_A; i += 256) attr_s[i] = a.attributes[static_cast<size_t>(b) * a.ca_A + i];
+            grp.sync();
+            if (tt < 64) {
+              float t = 0.f;
+#pragma unroll
+              for (int k = 0; k < 16; ++k) t += tmp[k * 64 + tt];
+              y_s[tt] = t / (static_cast<float>(H) * static_cast<float>(a.W));
+            }
+            grp.sync();
+            attn_vector(grp, a.ca_style, a.ca_params, 64, a.ca_R, a.ca_M, attr_s, y_s, s_s, tmp);
+            if (tt < 64) s_img[tt] = s_s[tt] * (a.sq != nullptr ? a.sq[static_cast<size_t>(b) * 64 + tt] : 1.f);
+            grp.sync();
+          }
+        }
+        // ---- row transform: two groups of 128 threads alternate ring rows.  Thread = (4-channel group c4,
+        //      pixel p0 + 8j): a warp covers 2 pixels x 64 channels per instruction, so the fp32 stream is
+        //      read and written in fully coalesced 512 B requests and r in 256 B requests.
+        const int tg = tt >> 7;
         const int tl = tt & 127;
-        float* s_loc = svec_s + tg * 64;
+        const int c4 = tl & 15, p0 = tl >> 4;
         const int n_last = padded(g1 - 1) + 1 - pr_first;
         const int pc_first = padded(g0), pc_last = padded(g1 - 1);
+        const uint32_t sw_chunk = static_cast<uint32_t>(c4 >> 1), sw_half = static_cast<uint32_t>(c4 & 1) * 8u;
         int cur_b = -1;
+        float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int n = tg; n <= n_last; n += 2) {
           const int pr = pr_first + n;
           const int slot = n % kSlots;
@@ -230,60 +276,50 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           const int b = col / nseg;
           const int seg = col % nseg;
           const bool row_ok = yy >= 0 && yy < H;
-          const bool owned = row_ok && pr >= pc_first && pr <= pc_last;
-          if (row_ok && b != cur_b) {  // (group-uniform) fetch this image's attention vector
-            named_bar_sync(3 + tg, 128);
-            if (tl < 64) s_loc[tl] = a.svec_in[static_cast<size_t>(b) * 64 + tl];
-            named_bar_sync(3 + tg, 128);
+          const bool owned = row_ok && pr >= pc_first && pr <= pc_last && a.xout_f32 != nullptr;
+          if (row_ok && b != cur_b) {
+            sc = *reinterpret_cast<const float4*>(svec_s + (b - b_first) * 64 + c4 * 4);
             cur_b = b;
           }
           mbar_wait(&empty[slot], ((n / kSlots) & 1) ^ 1);
           uint8_t* srow = ring + slot * kSlotBytes;
-          for (int p = tl; p < kBoxPix; p += 128) {
-            const int x = seg * 128 - 1 + p;
-            uint4* dst = reinterpret_cast<uint4*>(srow + p * 128);
-            if (row_ok && x >= 0 && x < a.W) {
-              const size_t e = ((static_cast<size_t>(b) * H + yy) * a.W + x) * 64;
-              const bool wr = owned && p >= 1 && p <= 128 && a.xout_f32 != nullptr;
+          const size_t row_e = (static_cast<size_t>(b) * H + (row_ok ? yy : 0)) * a.W * 64;
+          const int xbase = seg * 128 - 1;
+#pragma unroll 1
+          for (int j0 = 0; j0 < 17; j0 += 4) {
+            uint2 rr[4];
+            float4 xx[4];
+            bool ok[4];
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {  // two halves of 32 channels bound the register footprint
-                uint4 rr[4];
-                float4 xx[8];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) rr[i] = *reinterpret_cast<const uint4*>(a.r_bf16 + e + h * 32 + i * 8);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) xx[i] = *reinterpret_cast<const float4*>(a.xin_f32 + e + h * 32 + i * 4);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
-                  const float* sc = s_loc + h * 32 + i * 8;
-                  float o[8];
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float2 f = __bfloat1622float2(hb[j]);
-                    const float4 xv = xx[2 * i + (j >> 1)];
-                    const float xa = (j & 1) ? xv.z : xv.x;
-                    const float xb = (j & 1) ? xv.w : xv.y;
-                    o[2 * j] = fmaf(f.x, sc[2 * j], xa);
-                    o[2 * j + 1] = fmaf(f.y, sc[2 * j + 1], xb);
-                  }
-                  if (wr) {
-                    float4* xo = reinterpret_cast<float4*>(a.xout_f32 + e + h * 32 + i * 8);
-                    xo[0] = make_float4(o[0], o[1], o[2], o[3]);
-                    xo[1] = make_float4(o[4], o[5], o[6], o[7]);
-                  }
-                  uint4 pk;
-                  pk.x = pack_bf16x2(o[0], o[1]);
-                  pk.y = pack_bf16x2(o[2], o[3]);
-                  pk.z = pack_bf16x2(o[4], o[5]);
-                  pk.w = pack_bf16x2(o[6], o[7]);
-                  dst[(h * 4 + i) ^ (p & 7)] = pk;
-                }
+            for (int u = 0; u < 4; ++u) {
+              const int p = p0 + 8 * (j0 + u);
+              const int x = xbase + p;
+              ok[u] = row_ok && p < kBoxPix && x >= 0 && x < a.W;
+              if (ok[u]) {
+                const size_t e = row_e + static_cast<size_t>(x) * 64 + c4 * 4;
+                rr[u] = *reinterpret_cast<const uint2*>(a.r_bf16 + e);
+                xx[u] = *reinterpret_cast<const float4*>(a.xin_f32 + e);
               }
-            } else {
-              const uint4 z = make_uint4(0u, 0u, 0u, 0u);  // zero padding (rows -1 / H, columns -1 / W)
+            }
 #pragma unroll
-              for (int c = 0; c < 8; ++c) dst[c] = z;
+            for (int u = 0; u < 4; ++u) {
+              const int p = p0 + 8 * (j0 + u);
+              if (p >= kBoxPix) continue;
+              uint2 pk = make_uint2(0u, 0u);  // zero padding (rows -1 / H, columns -1 / W)
+              if (ok[u]) {
+                const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[u].x));
+                const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[u].y));
+                float4 o;
+                o.x = fmaf(f0.x, sc.x, xx[u].x);
+                o.y = fmaf(f0.y, sc.y, xx[u].y);
+                o.z = fmaf(f1.x, sc.z, xx[u].z);
+                o.w = fmaf(f1.y, sc.w, xx[u].w);
+                if (owned && p >= 1 && p <= 128)
+                  *reinterpret_cast<float4*>(a.xout_f32 + row_e + static_cast<size_t>(xbase + p) * 64 + c4 * 4) = o;
+                pk.x = pack_bf16x2(o.x, o.y);
+                pk.y = pack_bf16x2(o.z, o.w);
+              }
+              *reinterpret_cast<uint2*>(srow + p * 128 + ((sw_chunk ^ static_cast<uint32_t>(p & 7)) << 4) + sw_half) = pk;
             }
           }
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core's async proxy
@@ -399,49 +435,6 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               const float s = ((pool_s[et] + pool_s[64 + et]) + pool_s[128 + et]) + pool_s[192 + et];
               a.pool_rows[(static_cast<size_t>(col) * a.H + y) * 64 + et] = s;
             }
-            // ---- attention tail: when this CTA has finished its share of image b, count it in; the last
-            // CTA of the image reduces the pooled rows (fixed order) and evaluates the attention vector.
-            const bool img_done = (g + 1 == g1) || (((g + 1) / H) / nseg != b);
-            if (a.svec_out != nullptr && img_done) {
-              const int rows_img = nseg * H;
-              int* flag = reinterpret_cast<int*>(attn_s + 64 + 64 + 512 + 1024);
-              __threadfence();
-              named_bar_sync(1, 128);
-              if (et == 0) {
-                const long long ga = static_cast<long long>(b) * rows_img, gb = ga + rows_img - 1;
-                const int i_first = static_cast<int>(((ga + 1) * gridDim.x - 1) / G);
-                const int i_last = static_cast<int>(((gb + 1) * gridDim.x - 1) / G);
-                const int old = atomicAdd(a.img_counter + b, 1);
-                const int last = old == (i_last - i_first);
-                if (last) a.img_counter[b] = 0;  // self-resetting: ready for the next layer
-                *flag = last;
-              }
-              named_bar_sync(2, 128);
-              if (*flag) {
-                __threadfence();
-                float* y_s = attn_s;
-                float* s_s = attn_s + 64;
-                float* attr_s = attn_s + 128;
-                float* tmp = attn_s + 128 + 512;
-                const NamedGroup grp{et, 128, 5};
-                {
-                  const int c = et & 63, half = et >> 6;
-                  const float* pr = a.pool_rows + static_cast<size_t>(b) * rows_img * 64 + c;
-                  float sum = 0.f;
-                  for (int row = half; row < rows_img; row += 2) sum += pr[static_cast<size_t>(row) * 64];
-                  tmp[half * 64 + c] = sum;
-                }
-                for (int i = et; i < a.ca_A; i += 128) attr_s[i] = a.attributes[static_cast<size_t>(b) * a.ca_A + i];
-                grp.sync();
-                if (et < 64) y_s[et] = (tmp[et] + tmp[64 + et]) / (static_cast<float>(H) * static_cast<float>(a.W));
-                grp.sync();
-                attn_vector(grp, a.ca_style, a.ca_params, 64, a.ca_R, a.ca_M, attr_s, y_s, s_s, tmp);
-                if (et < 64)
-                  a.svec_out[static_cast<size_t>(b) * 64 + et] =
-                      s_s[et] * (a.sq != nullptr ? a.sq[static_cast<size_t>(b) * 64 + et] : 1.f);
-              }
-              named_bar_sync(1, 128);  // keep *flag / attn scratch stable until everyone has read it
-            }
           }
         }
       }
@@ -514,7 +507,11 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   if (d.B <= 0 || d.H <= 0 || d.W <= 0) return DFIR_OK;
   if (d.cin_total % 64 != 0 || d.cin_off % 64 != 0) return DFIR_ERR_ARG;
   const bool fused = d.in_mode == IN_FUSED;
-  if (fused && (d.r_bf16 == nullptr || d.xin_f32 == nullptr || d.svec_in == nullptr || d.cin_total != 64))
+  if (fused && (d.r_bf16 == nullptr || d.xin_f32 == nullptr || d.cin_total != 64 || d.xin_f32 == d.xout_f32))
+    return DFIR_ERR_ARG;
+  if (fused && d.ca_style != DFIR_STYLE_NONE &&
+      (d.pool_rows == nullptr || d.ca_params == nullptr || d.ca_A > 512 || d.ca_M > 448 ||
+       (d.ca_A > 0 && d.attributes == nullptr)))
     return DFIR_ERR_ARG;
   if (!fused && d.in_bf16 == nullptr) return DFIR_ERR_ARG;
   CUtensorMap tin, tout;
@@ -549,9 +546,7 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   a.r_bf16 = reinterpret_cast<const __nv_bfloat16*>(d.r_bf16);
   a.xin_f32 = d.xin_f32;
   a.xout_f32 = d.xout_f32;
-  a.svec_in = d.svec_in;
-  a.svec_out = d.svec_out;
-  a.img_counter = d.img_counter;
+  a.res_scale = d.res_scale;
   a.ca_params = d.ca_params;
   a.attributes = d.attributes;
   a.sq = d.sq;
@@ -559,12 +554,11 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   a.ca_R = d.ca_R;
   a.ca_M = d.ca_M;
   a.ca_A = d.ca_A;
-  if (d.svec_out != nullptr &&
-      (d.epi != EPI_BIAS_POOL || d.img_counter == nullptr || d.ca_params == nullptr || d.ca_A > 512 || d.ca_M > 448))
-    return DFIR_ERR_ARG;
   const long long G = static_cast<long long>(d.B) * a.nseg * d.H;
   int grid = d.num_sms > 0 ? d.num_sms : 148;
   if (G < grid) grid = static_cast<int>(G);
+  // IN_FUSED keeps the attention vectors of every image a band touches in shared memory
+  if (fused && (G + grid - 1) / grid > static_cast<long long>(kMaxBandImages - 1) * a.nseg * d.H) return DFIR_ERR_ARG;
   if (fused) {
     switch (d.epi) {
       case EPI_BIAS_RELU: return launch_one<64, EPI_BIAS_RELU, IN_FUSED>(tin, tout, a, grid, stream);

@@ -27,17 +27,15 @@ struct ConvTcArgs {  // kernel argument block
   const float* skip_f32;
   float* out_f32;
   float* pool_rows;
-  // IN_FUSED: conv input = r * svec_in[b] + xin   (xout = fp32 copy of it for the rows the CTA owns)
+  // IN_FUSED: conv input = r * s[b] + xin (xout = fp32 copy of it for the rows the CTA owns), with
+  // s[b] = CA_style(mean(r_b) from pool_rows, attributes[b]) * sq[b]   (style NONE: s = res_scale * sq)
   const __nv_bfloat16* r_bf16;
   const float* xin_f32;
   float* xout_f32;
-  const float* svec_in;
-  // attention tail of EPI_BIAS_POOL (optional): svec_out[b][64] = CA(mean(r)) * sq[b]
-  float* svec_out;
-  int* img_counter;
   const float* ca_params;
   const float* attributes;
   const float* sq;
+  float res_scale;
   int ca_style, ca_R, ca_M, ca_A;
 };
 
@@ -59,12 +57,10 @@ struct ConvTcDesc {  // host-side launch description
   const void* r_bf16;      // IN_FUSED
   const float* xin_f32;
   float* xout_f32;
-  const float* svec_in;
-  float* svec_out;         // attention tail (EPI_BIAS_POOL)
-  int* img_counter;
-  const float* ca_params;
+  const float* ca_params;   // IN_FUSED: attention vector inputs (pool_rows above holds the pooled row sums)
   const float* attributes;
   const float* sq;
+  float res_scale;
   int ca_style, ca_R, ca_M, ca_A;
 };
 

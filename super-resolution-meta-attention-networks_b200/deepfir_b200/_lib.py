@@ -55,8 +55,8 @@ PROTOTYPES = {
     "dfir_pack_conv3x3_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "dfir_pack_conv3x3_f32": (_i, [_vp, _vp, _i, _i, _vp]),
     "dfir_conv3x3_c64": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _ll, _ll, _ll, _vp, _vp, _vp, _i, _vp]),
-    "dfir_conv3x3_c64_ca": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
-    "dfir_conv3x3_c64_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "dfir_conv3x3_c64_fused": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _i,
+                                    _vp, _vp, _vp, _vp]),
     "dfir_conv3x3_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dfir_head_conv": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "dfir_meta_attention": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),

@@ -95,68 +95,54 @@ def test_conv_tc_tail_nchw():
 
 
 @pytest.mark.parametrize("shape", [(2, 16, 128), (3, 5, 40), (1, 7, 200), (9, 2, 20)])
-@pytest.mark.parametrize("epi", [1, 3])
-def test_conv_tc_fused_scale_residual_input(shape, epi):
-    """IN_FUSED: conv(r * s + x) with x' written back as the new fp32 stream
-    (QRCAB `res * y`, `res += x` fused into the next conv; architectures.py:127,172-180)."""
+@pytest.mark.parametrize("epi,style", [(1, "standard"), (3, "standard"), (1, "max_concat"), (3, "softmax"),
+                                       (1, "mini_concat"), (1, "extended_attention"), (3, "modulate"), (1, "none")])
+def test_conv_tc_fused_scale_residual_input(shape, epi, style):
+    """IN_FUSED: s = QCALayer(mean r, attributes) * meta scale; x' = r * s + x written back as the new fp32
+    stream; out = conv(x') (QRCAB `res * y`, `res += x` fused into the next conv;
+    architectures.py:105-127,172-180)."""
+    from deepfir_b200.qrcan import ChannelAttentionParams
     B, H, W = shape
+    M = 10
+    A = 64 if style == "modulate" else M
+    torch.manual_seed(W + epi)
     g = torch.Generator().manual_seed(W + epi)
     r = G.bf16_round(torch.randn(B, 64, H, W, generator=g))
     x = torch.randn(B, 64, H, W, generator=g)
-    sv = torch.rand(B, 64, generator=g)
+    attr = torch.rand(B, A, generator=g)
+    sq = torch.rand(B, 64, generator=g)
+    if style != "none":
+        ca = ChannelAttentionParams(64, style, 16, M)
+        sd = {"p." + k: v for k, v in ca.state_dict().items()}
+        blob = torch.cat([t.detach().reshape(-1) for t in ca.flat_params()]).cuda()
+        sv = O.qca_vector(r, attr.reshape(B, A, 1, 1), sd, "p", style).reshape(B, 64) * sq
+    else:
+        blob = None
+        sv = 0.1 * sq
     _, w, b = _rand_case(1, 1, 1, seed=W)
     xp = r * sv.reshape(B, 64, 1, 1) + x
     ref = _ref_conv(xp, w, b)
     skip = torch.randn(B, 64, H, W, generator=g) if epi == 3 else None
     ref = F.relu(ref) if epi == 1 else ref + skip
-    r_d, x_d, s_d, w_d, b_d = G.nhwc_bf16(r), G.nhwc_f32(x), sv.cuda(), G.pack_bf16(w), b.cuda()
+    nseg = (W + 127) // 128
+    pool = torch.stack([r[:, :, :, 128 * s_:128 * (s_ + 1)].sum(dim=3).permute(0, 2, 1) for s_ in range(nseg)], 1)
+    pool_d = pool.contiguous().cuda()  # [B][nseg][H][64]
+    r_d, x_d, w_d, b_d, attr_d, sq_d = G.nhwc_bf16(r), G.nhwc_f32(x), G.pack_bf16(w), b.cuda(), attr.cuda(), sq.cuda()
     x_out = torch.full((B, H, W, 64), float("nan"), device="cuda")
     out = torch.full((B, H, W, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
     o32 = torch.full((B, H, W, 64), float("nan"), device="cuda") if epi == 3 else None
     sk_d = G.nhwc_f32(skip) if skip is not None else None
-    rc = G.lib().dfir_conv3x3_c64_fused(r_d.data_ptr(), x_d.data_ptr(), s_d.data_ptr(), x_out.data_ptr(),
-                                        w_d.data_ptr(), b_d.data_ptr(), B, H, W, epi, out.data_ptr(),
-                                        sk_d.data_ptr() if sk_d is not None else None,
-                                        o32.data_ptr() if o32 is not None else None, G.stream())
+    rc = G.lib().dfir_conv3x3_c64_fused(
+        r_d.data_ptr(), x_d.data_ptr(), x_out.data_ptr(), pool_d.data_ptr(), STYLE_ID[style],
+        blob.data_ptr() if blob is not None else None, 4, M, A, attr_d.data_ptr(), sq_d.data_ptr(), 0.1,
+        w_d.data_ptr(), b_d.data_ptr(), B, H, W, epi, out.data_ptr(),
+        sk_d.data_ptr() if sk_d is not None else None, o32.data_ptr() if o32 is not None else None, G.stream())
     assert rc == 0
     G.sync()
-    assert G.max_norm_err(G.to_nchw(x_out), xp) < 1e-6          # the fp32 stream is exact (one fma)
+    assert G.max_norm_err(G.to_nchw(x_out), xp) < 2e-6          # the fp32 stream: one fma per element
     assert torch.allclose(G.to_nchw(out), ref, rtol=2 ** -7, atol=4e-3)
-    if o32 is not None:
-        assert G.max_norm_err(G.to_nchw(o32), ref) < 1e-5
-
-
-@pytest.mark.parametrize("style", ["standard", "max_concat", "softmax", "mini_concat", "extended_attention",
-                                   "modulate"])
-def test_conv_tc_attention_tail(style):
-    """EPI_BIAS_POOL + attention tail: the last CTA of each image evaluates QCALayer on the pooled mean."""
-    from deepfir_b200.qrcan import ChannelAttentionParams
-    B, H, W, M = 5, 12, 150, 10
-    A = 64 if style == "modulate" else M
-    torch.manual_seed(3)
-    x, w, b = _rand_case(B, H, W, seed=21)
-    ref = _ref_conv(x, w, b)
-    ca = ChannelAttentionParams(64, style, 16, M)
-    sd = {"p." + k: v for k, v in ca.state_dict().items()}
-    attr = torch.rand(B, A)
-    sq = torch.rand(B, 64)
-    want = O.qca_vector(ref, attr.reshape(B, A, 1, 1), sd, "p", style).reshape(B, 64) * sq
-    blob = torch.cat([t.detach().reshape(-1) for t in ca.flat_params()]).cuda()
-    x_d, w_d, b_d, attr_d, sq_d = G.nhwc_bf16(x), G.pack_bf16(w), b.cuda(), attr.cuda(), sq.cuda()
-    out = torch.empty(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
-    pool = torch.empty(B, 2, H, 64, device="cuda")
-    svec = torch.full((B, 64), float("nan"), device="cuda")
-    cnt = torch.zeros(B, dtype=torch.int32, device="cuda")
-    for _ in range(2):  # twice: the counters must reset themselves
-        rc = G.lib().dfir_conv3x3_c64_ca(x_d.data_ptr(), w_d.data_ptr(), b_d.data_ptr(), B, H, W, out.data_ptr(),
-                                         pool.data_ptr(), STYLE_ID[style], blob.data_ptr(), 4, M, A, attr_d.data_ptr(),
-                                         sq_d.data_ptr(), svec.data_ptr(), cnt.data_ptr(), G.stream())
-        assert rc == 0
-        G.sync()
-        assert int(cnt.abs().sum()) == 0
-        assert torch.allclose(svec.cpu(), want, rtol=2e-4, atol=2e-6), (svec.cpu() - want).abs().max()
-        svec.fill_(float("nan"))
-    assert torch.allclose(G.to_nchw(out), ref, rtol=2 ** -7, atol=2e-3)
+    if o32 is not None:  # rare 1-ulp bf16 flips of x' (fma on the GPU vs mul+add in the oracle) cost ~1e-5
+        assert G.max_norm_err(G.to_nchw(o32), ref) < 1e-4
 
 
 @pytest.mark.parametrize("r", [2, 3])
@@ -315,5 +301,5 @@ def test_bad_arguments_return_error_codes():
                               2048, None, None, None, 0, None) == -1  # pool epilogue without pool buffer
     assert L.dfir_conv3x3_c64(x.data_ptr(), 64, 0, x.data_ptr(), x.data_ptr(), 1, 4, 4, 0, 64, x.data_ptr(), 128, 512,
                               2048, None, None, None, 1, None) == -1  # reserved desc_mode
-    assert L.dfir_conv3x3_c64_fused(x.data_ptr(), None, None, None, x.data_ptr(), x.data_ptr(), 1, 4, 4, 1,
-                                    x.data_ptr(), None, None, None) == -1  # fused input without x_in / svec
+    assert L.dfir_conv3x3_c64_fused(x.data_ptr(), None, None, None, 0, None, 4, 10, 10, None, None, 1.0, x.data_ptr(),
+                                    x.data_ptr(), 1, 4, 4, 1, x.data_ptr(), None, None, None) == -1  # no x_in
