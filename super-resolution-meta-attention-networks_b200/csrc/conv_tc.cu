@@ -7,25 +7,31 @@
 // weights pre-packed per tap as [tap][cout][cin] bf16 in the UMMA K-major SWIZZLE_128B byte order.
 //
 // GEMM view: D[M = 128 pixels of one image row][N = cout] += A[M][K = 64 cin] * B[N][K] for each of the 9
-// taps (K total = 576).  No im2col is ever materialised: a persistent CTA streams input rows into a shared
-// memory ring with TMA (one box = one row segment of 130 pixels incl. the x halo; out-of-bounds pixels and
-// rows are zero-filled by the TMA unit, which IS the conv's zero padding) and every tap's A operand is
-// just a shifted view of a ring slot: dy picks the slot, dx shifts the descriptor start by dx*128 B
-// (base_offset stays 0: the hardware derives the swizzle phase from the absolute smem address).  The weights of the layer (9 x cout x 128 B) stay resident in
-// shared memory for the CTA's whole life.  Accumulators live in TMEM (4 buffers) so the epilogue of row i
-// overlaps the MMAs of rows i+1..i+3.
+// taps (K total = 576).  No im2col is ever materialised.  A persistent CTA streams input rows into a small
+// shared-memory ring (TMA: one box = one row segment of 130 pixels incl. the x halo; out-of-bounds pixels
+// and rows are zero-filled by the TMA unit, which IS the conv's zero padding).
+//
+// Operand placement (measured, profiles/r01_*): the tensor core fetches shared-memory operands at only
+// ~64 B/clk/SM, so an SS-mode MMA of this shape (A 4 KB + B 2 KB per 32-clk instruction) is operand-fetch
+// bound at 1/3 of peak.  The A operand therefore lives in TENSOR MEMORY: four loader warps copy every ring
+// row into TMEM three times, shifted by dx = 0,1,2 pixels (lane m <- pixel m + dx; 32 columns = the pixel's
+// 64 bf16 channels), with ordinary swizzle-aware LDS.128 + tcgen05.st.  A tap's A operand is then just a
+// TMEM address: dy picks the row slot, dx the copy, k the 8-column slice; the MMAs (tcgen05.mma, A from
+// TMEM) only pull the 2 KB weight tile from shared memory.  The weights of the layer (9 x cout x 128 B)
+// stay resident in shared memory for the CTA's whole life.  TMEM budget (512 columns): 2 accumulators
+// (2 x 64) + 4 row slots x 3 copies x 32 columns.
 //
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + tcgen05.mma issuer, warps 2-5 = epilogue
-// (TMEM -> registers -> fused bias/ReLU/skip/pool -> swizzled smem -> TMA store).
+// (TMEM -> registers -> fused bias/ReLU/skip/pool -> swizzled smem -> TMA store), warps 6-9 = A loaders.
 //
 // Input modes
-//   IN_TMA   : the input rows are bf16 NHWC in HBM/L2 and arrive by TMA (192 threads).
+//   IN_TMA   : the input rows are bf16 NHWC in HBM/L2 and arrive by TMA (320 threads).
 //   IN_FUSED : the input of the conv is x' = r * s + x, i.e. the previous block's channel-attention scale
 //              and residual add (QRCAB: `res * y` twice and `res += x`, architectures.py:127,172-180;
 //              q_layer.py:43).  Eight extra warps (two groups that alternate rows) read r (bf16) and x
 //              (fp32 residual stream), form x', write it back as the new fp32 stream for the rows the CTA
-//              owns, and deposit bf16(x') straight into the swizzled ring slot the tensor core reads.  The
-//              separate elementwise pass (and its 12 B/element of traffic) disappears (448 threads).
+//              owns, and deposit bf16(x') into the swizzled ring slot.  The separate elementwise pass (and
+//              its 12 B/element of traffic) disappears (576 threads).
 //              The attention vector s = CA_style(pooled mean, attributes) * meta_scale (attn.cuh) is
 //              evaluated by the same warps in the kernel prologue, hidden behind the weight load.
 #include "ptx.cuh"
@@ -40,16 +46,20 @@ using namespace ptx;
 
 namespace {
 
-constexpr int kSlots = 6;                    // input-row ring depth
+constexpr int kSlots = 4;                    // smem input-row ring depth (producer -> A loaders)
 constexpr int kSlotPix = 136;                // 130 px used (128 + 2 halo), rounded up to 8 px = 1024 B
 constexpr int kSlotBytes = kSlotPix * 128;   // 17408, multiple of 1024
 constexpr int kBoxPix = 130;
 constexpr int kRowBytes = kBoxPix * 128;     // bytes one TMA row load delivers
-constexpr int kAcc = 4;                      // TMEM accumulator buffers
+constexpr int kAcc = 2;                      // TMEM accumulator buffers
+constexpr int kARows = 4;                    // TMEM A-operand row slots (3 live + 1 being filled)
+constexpr int kAColBase = 128;               // first TMEM column of the A region
+constexpr int kAColsPerRow = 96;             // 3 dx copies x 32 columns
+constexpr int kTmemCols = 512;
 constexpr int kStageBytes = 128 * 128;       // one output row segment, bf16
-constexpr int kThreads = 192;            // IN_TMA
-constexpr int kThreadsFused = 192 + 256;  // + two transform groups of 4 warps
-constexpr int kMaxBandImages = 8;         // a CTA's row band may touch at most this many images (IN_FUSED)
+constexpr int kThreads = 320;                // IN_TMA: producer, MMA, 4 epilogue, 4 loader warps
+constexpr int kThreadsFused = 320 + 256;     // + two transform groups of 4 warps
+constexpr int kMaxBandImages = 8;            // a CTA's row band may touch at most this many images (IN_FUSED)
 
 template <int NT>
 struct SmemLayout {
@@ -59,20 +69,20 @@ struct SmemLayout {
   static constexpr int off_stage = off_ring + kSlots * kSlotBytes;
   static constexpr int off_bias = off_stage + 2 * kStageBytes;
   static constexpr int off_pool = off_bias + 64 * 4;
-  static constexpr int off_attn = off_pool + 4 * 64 * 4;          // y[64] s[64] attr[512] tmp[1024] flag
-  static constexpr int off_svec = off_attn + (64 + 64 + 512 + 1024 + 4) * 4;  // s of the images of this band
+  static constexpr int off_attn = off_pool + 4 * 64 * 4;                         // y[64] s[64] attr[512] tmp[1024]
+  static constexpr int off_svec = off_attn + (64 + 64 + 512 + 1024 + 4) * 4;     // s of the images of this band
   static constexpr int off_bars = off_svec + kMaxBandImages * 64 * 4;
-  static constexpr int n_bars = 2 * kSlots + 2 * kAcc + 1;
+  static constexpr int n_bars = 2 * kSlots + 2 * kARows + 2 * kAcc + 1;
   static constexpr int off_tmem = off_bars + n_bars * 8;
   static constexpr int total = off_tmem + 16;
 };
 
-// butterfly transpose-reduce: on entry lane l holds v[0..63] (channel values of its pixel, already masked);
-// on exit v[0], v[1] hold the sums over the warp's 32 pixels of channels 2*l and 2*l+1.
-__device__ __forceinline__ void warp_channel_sums(float (&v)[64], int lane) {
+// butterfly transpose-reduce over 32 values: on entry lane l holds v[0..31] (channel values of its pixel,
+// already masked); on exit v[0] holds the sum over the warp's 32 pixels of channel l.
+__device__ __forceinline__ void warp_channel_sums32(float (&v)[32], int lane) {
 #pragma unroll
   for (int step = 0; step < 5; ++step) {
-    const int n = 64 >> step;       // values held before this step
+    const int n = 32 >> step;  // values held before this step
     const int mask = 16 >> step;
     const bool upper = (lane & mask) != 0;
 #pragma unroll
@@ -107,11 +117,13 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   float* attn_s = reinterpret_cast<float*>(smem + L::off_attn);
   float* svec_s = reinterpret_cast<float*>(smem + L::off_svec);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::off_bars);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kSlots;
-  uint64_t* tfull = bars + 2 * kSlots;
-  uint64_t* tempty = bars + 2 * kSlots + kAcc;
-  uint64_t* wbar = bars + 2 * kSlots + 2 * kAcc;
+  uint64_t* full = bars;                                   // ring slot filled      (producer/transform -> loaders)
+  uint64_t* empty = full + kSlots;                         // ring slot drained     (loaders -> producer/transform)
+  uint64_t* afull = empty + kSlots;                        // TMEM A row slot ready (loaders -> MMA)
+  uint64_t* aempty = afull + kARows;                       // TMEM A row slot free  (MMA commit -> loaders)
+  uint64_t* tfull = aempty + kARows;                       // accumulator ready     (MMA commit -> epilogue)
+  uint64_t* tempty = tfull + kAcc;                         // accumulator drained   (epilogue -> MMA)
+  uint64_t* wbar = tempty + kAcc;                          // weights landed
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + L::off_tmem);
 
   const int warp = threadIdx.x >> 5;
@@ -127,13 +139,18 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   // padded row index of output row g: col*(H+2) + y + 1
   auto padded = [&](int g) { return (g / H) * Hp + (g % H) + 1; };
   const int pr_first = (g0 < g1) ? padded(g0) - 1 : 0;
+  const int n_last = (g0 < g1) ? padded(g1 - 1) + 1 - pr_first : -1;  // last ring sequence index
 
   if (threadIdx.x == 0) {
-    prefetch_tmap(&tmap_in);
+    if (INMODE == IN_TMA) prefetch_tmap(&tmap_in);
     if (EPI != EPI_TAIL_NCHW) prefetch_tmap(&tmap_out);
     for (int i = 0; i < kSlots; ++i) {
       mbar_init(&full[i], INMODE == IN_FUSED ? 128 : 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], 4);
+    }
+    for (int i = 0; i < kARows; ++i) {
+      mbar_init(&afull[i], 4);
+      mbar_init(&aempty[i], 1);
     }
     for (int i = 0; i < kAcc; ++i) {
       mbar_init(&tfull[i], 1);
@@ -143,7 +160,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
     fence_barrier_init();
   }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + NT) bias_s[threadIdx.x - 64] = a.bias[threadIdx.x - 64];
-  if (warp == 1) tmem_alloc<kAcc * NT>(tmem_holder);
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_holder);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -155,66 +172,96 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       if (elect_one()) {
         mbar_arrive_expect_tx(wbar, L::w_bytes);
         bulk_load_1d(wsm, a.wpacked, L::w_bytes, wbar);
-        const int pr_last = INMODE == IN_FUSED ? pr_first - 1 : padded(g1 - 1) + 1;
-        for (int pr = pr_first, n = 0; pr <= pr_last; ++pr, ++n) {
-          const int slot = n % kSlots;
-          const uint32_t use = n / kSlots;
-          mbar_wait(&empty[slot], (use & 1) ^ 1);
-          const int col = pr / Hp;
-          const int yy = pr % Hp - 1;
-          const int b = col / nseg;
-          const int seg = col % nseg;
-          mbar_arrive_expect_tx(&full[slot], kRowBytes);
-          tma_load_4d(ring + slot * kSlotBytes, &tmap_in, &full[slot], a.cin_off, seg * 128 - 1, yy, b);
+        if constexpr (INMODE == IN_TMA) {
+          for (int n = 0; n <= n_last; ++n) {
+            const int pr = pr_first + n;
+            const int slot = n % kSlots;
+            mbar_wait(&empty[slot], ((n / kSlots) & 1) ^ 1);
+            const int col = pr / Hp;
+            const int yy = pr % Hp - 1;
+            mbar_arrive_expect_tx(&full[slot], kRowBytes);
+            tma_load_4d(ring + slot * kSlotBytes, &tmap_in, &full[slot], a.cin_off, (col % nseg) * 128 - 1, yy,
+                        col / nseg);
+          }
         }
       }
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
-      // The whole warp runs the loop so that control flow and descriptor arithmetic stay warp-uniform
-      // (uniform registers feed UTCHMMA directly); only the elected lane issues tcgen05 instructions.
+      // The whole warp runs the loop so that control flow and address arithmetic stay warp-uniform; only the
+      // elected lane issues tcgen05 instructions.
       const bool leader = elect_one();
       constexpr uint32_t idesc = make_idesc_bf16_f32(128, NT);
-      const uint64_t da_base = make_sw128_kmajor_desc(smem_u32(ring), 1024, 0);
       const uint64_t db_base = make_sw128_kmajor_desc(smem_u32(wsm), 1024, 0);
       mbar_wait(wbar, 0);
-      int released = 0;  // next ring sequence index to hand back to the producer
+      int released = 0;  // next A-row sequence index to hand back to the loaders
       for (int g = g0, it = 0; g < g1; ++g, ++it) {
-        const int nc = padded(g) - pr_first;  // ring sequence index of the centre row
+        const int nc = padded(g) - pr_first;  // sequence index of the centre row
         const int acc = it % kAcc;
         mbar_wait(&tempty[acc], (((it / kAcc) & 1) ^ 1));
-        uint32_t slot_off[3];
+        uint32_t a_col[3];
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
           const int n = nc - 1 + dy;
-          const int slot = n % kSlots;
-          mbar_wait(&full[slot], (n / kSlots) & 1);
-          slot_off[dy] = static_cast<uint32_t>(slot * (kSlotBytes >> 4));
+          mbar_wait(&afull[n % kARows], (n / kARows) & 1);
+          a_col[dy] = tmem_base + kAColBase + (n % kARows) * kAColsPerRow;
         }
         tcgen05_fence_after();
         if (leader) {
           const uint32_t d_tmem = tmem_base + acc * NT;
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
-            const uint64_t da_row = da_base + slot_off[dy];
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                // start-address field is in 16-byte units: +8 per pixel (dx), +2 per 16-channel k-step
-                const uint64_t da = da_row + static_cast<uint32_t>(dx * 8 + k * 2);
                 const uint64_t db = db_base + static_cast<uint32_t>(((dy * 3 + dx) * NT * 128 + k * 32) >> 4);
-                umma_f16_ss(d_tmem, da, db, idesc, (dy | dx | k) != 0 ? 1u : 0u);
+                umma_f16_ts(d_tmem, a_col[dy] + dx * 32 + k * 8, db, idesc, (dy | dx | k) != 0 ? 1u : 0u);
               }
             }
           }
           umma_commit(&tfull[acc]);
-          for (int rel = released; rel <= nc - 1; ++rel) umma_commit(&empty[rel % kSlots]);
+          for (int rel = released; rel <= nc - 1; ++rel) umma_commit(&aempty[rel % kARows]);
         }
         released = nc > released ? nc : released;
         __syncwarp();
       }
-    } else if (warp >= 6) {
-      // ===================== fused input transform (IN_FUSED only; warps 6..13) =====================
+    } else if (warp >= 6 && warp < 10) {
+      // ===================== A loaders: smem ring row -> 3 dx-shifted copies in TMEM =====================
+      const int q = warp & 3;        // TMEM lane quarter this warp may access (warps 6,7,8,9 -> 2,3,0,1)
+      const int m = q * 32 + lane;   // output pixel = TMEM lane
+      for (int n = 0; n <= n_last; ++n) {
+        const int slot = n % kSlots;
+        const int as = n % kARows;
+        mbar_wait(&full[slot], (n / kSlots) & 1);
+        mbar_wait(&aempty[as], ((n / kARows) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint8_t* srow = ring + slot * kSlotBytes;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kAColBase + as * kAColsPerRow;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int p = m + dx;  // ring pixel feeding output pixel m for this tap column
+          const uint4* src = reinterpret_cast<const uint4*>(srow + p * 128);
+          uint32_t v[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 t = src[c ^ (p & 7)];
+            v[4 * c + 0] = t.x;
+            v[4 * c + 1] = t.y;
+            v[4 * c + 2] = t.z;
+            v[4 * c + 3] = t.w;
+          }
+          tmem_st_32x32b_x32(t_row + dx * 32, v);
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&afull[as]);
+          mbar_arrive(&empty[slot]);
+        }
+      }
+    } else if (warp >= 10) {
+      // ===================== fused input transform (IN_FUSED only; warps 10..17) =====================
       if constexpr (INMODE == IN_FUSED) {
         const int tt = threadIdx.x - kThreads;  // 0..255
         // ---- prologue (overlaps the weight load): attention vectors of the images this band touches.
@@ -263,7 +310,6 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         const int tg = tt >> 7;
         const int tl = tt & 127;
         const int c4 = tl & 15, p0 = tl >> 4;
-        const int n_last = padded(g1 - 1) + 1 - pr_first;
         const int pc_first = padded(g0), pc_last = padded(g1 - 1);
         const uint32_t sw_chunk = static_cast<uint32_t>(c4 >> 1), sw_half = static_cast<uint32_t>(c4 & 1) * 8u;
         int cur_b = -1;
@@ -281,30 +327,34 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             sc = *reinterpret_cast<const float4*>(svec_s + (b - b_first) * 64 + c4 * 4);
             cur_b = b;
           }
-          mbar_wait(&empty[slot], ((n / kSlots) & 1) ^ 1);
           uint8_t* srow = ring + slot * kSlotBytes;
           const size_t row_e = (static_cast<size_t>(b) * H + (row_ok ? yy : 0)) * a.W * 64;
           const int xbase = seg * 128 - 1;
+          bool waited = false;
 #pragma unroll 1
-          for (int j0 = 0; j0 < 17; j0 += 4) {
-            uint2 rr[4];
-            float4 xx[4];
-            bool ok[4];
+          for (int j0 = 0; j0 < 17; j0 += 9) {  // pixels p0 + 8j, j = 0..16, in two batches of loads
+            uint2 rr[9];
+            float4 xx[9];
+            bool ok[9];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 9; ++u) {
               const int p = p0 + 8 * (j0 + u);
               const int x = xbase + p;
-              ok[u] = row_ok && p < kBoxPix && x >= 0 && x < a.W;
+              ok[u] = row_ok && (j0 + u) < 17 && p < kBoxPix && x >= 0 && x < a.W;
               if (ok[u]) {
                 const size_t e = row_e + static_cast<size_t>(x) * 64 + c4 * 4;
                 rr[u] = *reinterpret_cast<const uint2*>(a.r_bf16 + e);
                 xx[u] = *reinterpret_cast<const float4*>(a.xin_f32 + e);
               }
             }
+            if (!waited) {  // the ring slot is only needed once the loads are in flight
+              mbar_wait(&empty[slot], ((n / kSlots) & 1) ^ 1);
+              waited = true;
+            }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 9; ++u) {
               const int p = p0 + 8 * (j0 + u);
-              if (p >= kBoxPix) continue;
+              if ((j0 + u) >= 17 || p >= kBoxPix) continue;
               uint2 pk = make_uint2(0u, 0u);  // zero padding (rows -1 / H, columns -1 / W)
               if (ok[u]) {
                 const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[u].x));
@@ -322,7 +372,6 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               *reinterpret_cast<uint2*>(srow + p * 128 + ((sw_chunk ^ static_cast<uint32_t>(p & 7)) << 4) + sw_half) = pk;
             }
           }
-          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core's async proxy
           mbar_arrive(&full[slot]);
         }
       }
@@ -342,87 +391,79 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         mbar_wait(&tfull[acc], (it / kAcc) & 1);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * NT;
-        float v[NT];
-        if constexpr (NT == 64) {
-          uint32_t r0[32], r1[32];
-          tmem_ld_32x32b_x32(taddr, r0);
-          tmem_ld_32x32b_x32(taddr + 32, r1);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            v[i] = __uint_as_float(r0[i]);
-            v[32 + i] = __uint_as_float(r1[i]);
-          }
-        } else {
+
+        if constexpr (EPI == EPI_TAIL_NCHW) {
           uint32_t r0[16];
           tmem_ld_32x32b_x16(taddr, r0);
           tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r0[i]);
-        }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
-
-#pragma unroll
-        for (int i = 0; i < NT; ++i) v[i] += bias_s[i];
-
-        if constexpr (EPI == EPI_TAIL_NCHW) {
-          // fp32 NCHW output, a.cout real channels (<= NT)
-          if (valid) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (valid) {  // fp32 NCHW output, a.cout real channels (<= NT)
             const size_t plane = static_cast<size_t>(a.H) * a.W;
             float* o = a.out_f32 + (static_cast<size_t>(b) * a.cout) * plane + static_cast<size_t>(y) * a.W + x;
 #pragma unroll
             for (int c = 0; c < NT; ++c)
-              if (c < a.cout) o[c * plane] = v[c];
+              if (c < a.cout) o[c * plane] = __uint_as_float(r0[c]) + bias_s[c];
           }
         } else {
-          if constexpr (EPI == EPI_BIAS_RELU) {
-#pragma unroll
-            for (int i = 0; i < NT; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if constexpr (EPI == EPI_BIAS_SKIP) {
-            if (valid) {
-              const size_t pix = (static_cast<size_t>(b) * a.H + y) * a.W + x;
-              const float4* sk = reinterpret_cast<const float4*>(a.skip_f32 + pix * 64);
-              float4* o = reinterpret_cast<float4*>(a.out_f32 + pix * 64);
-#pragma unroll
-              for (int c = 0; c < 16; ++c) {
-                const float4 s = sk[c];
-                v[4 * c + 0] += s.x;
-                v[4 * c + 1] += s.y;
-                v[4 * c + 2] += s.z;
-                v[4 * c + 3] += s.w;
-                if (a.out_f32 != nullptr) o[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-              }
-            }
-          }
-          // ---- bf16 row segment -> swizzled staging -> TMA store
           const int sb = it & 1;
           uint8_t* st = stage + sb * kStageBytes;
-          if (et == 0) tma_store_wait_read<1>();
+          if (et == 0) tma_store_wait_read<1>();  // the TMA store that read this staging buffer has drained it
           named_bar_sync(1, 128);
-          {
+          const size_t pix = (static_cast<size_t>(b) * a.H + y) * a.W + x;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {  // two halves of 32 channels bound the register footprint
+            uint32_t rv[32];
+            tmem_ld_32x32b_x32(taddr + h * 32, rv);
+            tmem_ld_wait();
+            if (h == 1) {  // accumulator fully read: hand it back to the MMA warp
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty[acc]);
+            }
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rv[i]) + bias_s[h * 32 + i];
+            if constexpr (EPI == EPI_BIAS_RELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if constexpr (EPI == EPI_BIAS_SKIP) {
+              if (valid) {
+                const float4* sk = reinterpret_cast<const float4*>(a.skip_f32 + pix * 64 + h * 32);
+                float4* o = reinterpret_cast<float4*>(a.out_f32 + pix * 64 + h * 32);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  const float4 s = sk[c];
+                  v[4 * c + 0] += s.x;
+                  v[4 * c + 1] += s.y;
+                  v[4 * c + 2] += s.z;
+                  v[4 * c + 3] += s.w;
+                  if (a.out_f32 != nullptr) o[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                }
+              }
+            }
+            // bf16 -> swizzled staging row
             uint4* row = reinterpret_cast<uint4*>(st + m * 128);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < 4; ++c) {
               uint4 pk;
               pk.x = pack_bf16x2(v[8 * c + 0], v[8 * c + 1]);
               pk.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
               pk.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
               pk.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
-              row[c ^ (m & 7)] = pk;
+              row[(h * 4 + c) ^ (m & 7)] = pk;
             }
-          }
-          if constexpr (EPI == EPI_BIAS_POOL) {
-            // per-row channel sums of the fp32 (pre-rounding) conv output, garbage pixels masked
-            if (!valid) {
+            if constexpr (EPI == EPI_BIAS_POOL) {
+              // per-row channel sums of the fp32 (pre-rounding) conv output, garbage pixels masked
+              if (!valid) {
 #pragma unroll
-              for (int i = 0; i < NT; ++i) v[i] = 0.f;
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+              }
+              warp_channel_sums32(v, lane);
+              pool_s[q * 64 + h * 32 + lane] = v[0];
             }
-            warp_channel_sums(v, lane);
-            pool_s[q * 64 + 2 * lane] = v[0];
-            pool_s[q * 64 + 2 * lane + 1] = v[1];
           }
           fence_proxy_async_smem();
           named_bar_sync(2, 128);
@@ -446,7 +487,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc<kAcc * NT>(tmem_base);
+    tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
