@@ -54,6 +54,9 @@ const char* dfir_version(void);
 const char* dfir_error_string(int code);
 /* 0 if the current device can run the library (compute capability 10.x), else DFIR_ERR_ARCH */
 int dfir_check_device(void);
+/* Synchronises the device and copies the 8-word pipeline watchdog record to out8_host ({0,...} = no barrier wait
+ * ever timed out; else {1, wait tag, blockIdx, threadIdx, parity, barrier lo, barrier hi, 0}); optionally clears it. */
+int dfir_debug_watchdog(unsigned int* out8_host, int reset);
 
 /* ------------------------------------------------------------------------------------------------
  * weight packing (derived caches of the fp32 OIHW nn.Parameters; never serialised)

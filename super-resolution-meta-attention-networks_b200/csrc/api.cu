@@ -284,6 +284,8 @@ const char* dfir_error_string(int code) {
   }
 }
 
+int dfir_debug_watchdog(unsigned int* out8_host, int reset) { return debug_watchdog(out8_host, reset); }
+
 int dfir_check_device(void) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return DFIR_ERR_CUDA;

@@ -39,8 +39,12 @@
 #include "attn.cuh"
 
 #include <cuda_bf16.h>
+#include <cstdio>
+#include <cstdlib>
 
 namespace dfir {
+
+__device__ unsigned int g_dfir_progress[16];
 
 using namespace ptx;
 
@@ -165,6 +169,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  const bool probe = a.debug_probe != 0 && blockIdx.x == 0 && lane == 0;
 
   if (g0 < g1) {
     if (warp == 0) {
@@ -176,7 +181,8 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           for (int n = 0; n <= n_last; ++n) {
             const int pr = pr_first + n;
             const int slot = n % kSlots;
-            mbar_wait(&empty[slot], ((n / kSlots) & 1) ^ 1);
+            if (probe) g_dfir_progress[0] = n + 1;
+            mbar_wait(&empty[slot], ((n / kSlots) & 1) ^ 1, 1);
             const int col = pr / Hp;
             const int yy = pr % Hp - 1;
             mbar_arrive_expect_tx(&full[slot], kRowBytes);
@@ -192,20 +198,24 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       const bool leader = elect_one();
       constexpr uint32_t idesc = make_idesc_bf16_f32(128, NT);
       const uint64_t db_base = make_sw128_kmajor_desc(smem_u32(wsm), 1024, 0);
-      mbar_wait(wbar, 0);
+      mbar_wait(wbar, 0, 2);
       int released = 0;  // next A-row sequence index to hand back to the loaders
       for (int g = g0, it = 0; g < g1; ++g, ++it) {
         const int nc = padded(g) - pr_first;  // sequence index of the centre row
+        const int nc_next = (g + 1 < g1) ? padded(g + 1) - pr_first : n_last + 2;
         const int acc = it % kAcc;
-        mbar_wait(&tempty[acc], (((it / kAcc) & 1) ^ 1));
+        if (probe) g_dfir_progress[1] = it + 1;
+        mbar_wait(&tempty[acc], (((it / kAcc) & 1) ^ 1), 3);
+        if (probe) g_dfir_progress[2] = it + 1;
         uint32_t a_col[3];
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
           const int n = nc - 1 + dy;
-          mbar_wait(&afull[n % kARows], (n / kARows) & 1);
+          mbar_wait(&afull[n % kARows], (n / kARows) & 1, 4);
           a_col[dy] = tmem_base + kAColBase + (n % kARows) * kAColsPerRow;
         }
         tcgen05_fence_after();
+        if (probe) g_dfir_progress[3] = it + 1;
         if (leader) {
           const uint32_t d_tmem = tmem_base + acc * NT;
 #pragma unroll
@@ -220,9 +230,12 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             }
           }
           umma_commit(&tfull[acc]);
-          for (int rel = released; rel <= nc - 1; ++rel) umma_commit(&aempty[rel % kARows]);
+          // rows the NEXT centre no longer needs go back to the loaders: everything below next - 1 (at an
+          // image boundary that also frees the last row and the bottom pad row of the finished image —
+          // keeping them would deadlock the 4-slot TMEM row ring)
+          for (int rel = released; rel <= nc_next - 2; ++rel) umma_commit(&aempty[rel % kARows]);
         }
-        released = nc > released ? nc : released;
+        released = nc_next - 1 > released ? nc_next - 1 : released;
         __syncwarp();
       }
     } else if (warp >= 6 && warp < 10) {
@@ -232,8 +245,9 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       for (int n = 0; n <= n_last; ++n) {
         const int slot = n % kSlots;
         const int as = n % kARows;
-        mbar_wait(&full[slot], (n / kSlots) & 1);
-        mbar_wait(&aempty[as], ((n / kARows) & 1) ^ 1);
+        if (probe) g_dfir_progress[4 + q] = n + 1;
+        mbar_wait(&full[slot], (n / kSlots) & 1, 5);
+        mbar_wait(&aempty[as], ((n / kARows) & 1) ^ 1, 6);
         tcgen05_fence_after();
         const uint8_t* srow = ring + slot * kSlotBytes;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kAColBase + as * kAColsPerRow;
@@ -348,7 +362,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               }
             }
             if (!waited) {  // the ring slot is only needed once the loads are in flight
-              mbar_wait(&empty[slot], ((n / kSlots) & 1) ^ 1);
+              mbar_wait(&empty[slot], ((n / kSlots) & 1) ^ 1, 7);
               waited = true;
             }
 #pragma unroll
@@ -388,7 +402,8 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         const int x = seg * 128 + m;
         const bool valid = x < a.W;
         const int acc = it % kAcc;
-        mbar_wait(&tfull[acc], (it / kAcc) & 1);
+        if (probe) g_dfir_progress[8 + q] = it + 1;
+        mbar_wait(&tfull[acc], (it / kAcc) & 1, 8);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * NT;
 
@@ -544,6 +559,23 @@ static int launch_one(const CUtensorMap& tin, const CUtensorMap& tout, const Con
   return cudaGetLastError() == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
 }
 
+int debug_watchdog(unsigned int* out8, int reset) {
+  if (cudaMemcpyFromSymbol(out8, g_dfir_watchdog, 8 * sizeof(unsigned int)) != cudaSuccess) return DFIR_ERR_CUDA;
+  if (reset == 2) {  // debugging: also print the block-0 progress probes
+    unsigned int pg[16];
+    if (cudaMemcpyFromSymbol(pg, g_dfir_progress, sizeof(pg)) == cudaSuccess) {
+      printf("progress:");
+      for (int i = 0; i < 16; ++i) printf(" %u", pg[i]);
+      printf("\n");
+    }
+  }
+  if (reset) {
+    unsigned int z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyToSymbol(g_dfir_watchdog, z, sizeof(z)) != cudaSuccess) return DFIR_ERR_CUDA;
+  }
+  return DFIR_OK;
+}
+
 int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   if (d.B <= 0 || d.H <= 0 || d.W <= 0) return DFIR_OK;
   if (d.cin_total % 64 != 0 || d.cin_off % 64 != 0) return DFIR_ERR_ARG;
@@ -588,6 +620,7 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   a.xin_f32 = d.xin_f32;
   a.xout_f32 = d.xout_f32;
   a.res_scale = d.res_scale;
+  a.debug_probe = getenv("DFIR_DEBUG_PROBE") != nullptr ? 1 : 0;
   a.ca_params = d.ca_params;
   a.attributes = d.attributes;
   a.sq = d.sq;
@@ -597,6 +630,7 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   a.ca_A = d.ca_A;
   const long long G = static_cast<long long>(d.B) * a.nseg * d.H;
   int grid = d.num_sms > 0 ? d.num_sms : 148;
+  if (const char* e = getenv("DFIR_NUM_SMS")) grid = atoi(e) > 0 ? atoi(e) : grid;  // debugging aid
   if (G < grid) grid = static_cast<int>(G);
   // IN_FUSED keeps the attention vectors of every image a band touches in shared memory
   if (fused && (G + grid - 1) / grid > static_cast<long long>(kMaxBandImages - 1) * a.nseg * d.H) return DFIR_ERR_ARG;

@@ -37,6 +37,7 @@ struct ConvTcArgs {  // kernel argument block
   const float* sq;
   float res_scale;
   int ca_style, ca_R, ca_M, ca_A;
+  int debug_probe;
 };
 
 struct ConvTcDesc {  // host-side launch description
@@ -65,6 +66,7 @@ struct ConvTcDesc {  // host-side launch description
 };
 
 int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream);
+int debug_watchdog(unsigned int* out8, int reset);
 
 // ---- SIMT kernels (simt.cu)
 struct AttnParams {  // one RCAB's channel-attention parameters (fp32, device pointers into the packed blob)

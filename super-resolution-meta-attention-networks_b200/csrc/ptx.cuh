@@ -53,11 +53,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (cudaErrorLaunchFailure) instead of hanging the GPU box.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded wait: a protocol bug must not hang the GPU box.  On timeout the first offender records
+// {1, tag, blockIdx.x, threadIdx.x, parity} in g_dfir_watchdog (read back with dfir_debug_watchdog) and the wait
+// gives up, so the kernel drains (with garbage results) instead of spinning forever.
+__device__ unsigned int g_dfir_watchdog[8];
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
   uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++polls > (1u << 24)) __trap();
+    if (++polls > (1u << 22)) {
+      if (atomicCAS(&g_dfir_watchdog[0], 0u, 1u) == 0u) {
+        g_dfir_watchdog[1] = tag;
+        g_dfir_watchdog[2] = blockIdx.x;
+        g_dfir_watchdog[3] = threadIdx.x;
+        g_dfir_watchdog[4] = parity;
+        g_dfir_watchdog[5] = static_cast<uint32_t>(*reinterpret_cast<volatile uint64_t*>(bar) & 0xffffffffu);
+        g_dfir_watchdog[6] = static_cast<uint32_t>(*reinterpret_cast<volatile uint64_t*>(bar) >> 32);
+      }
+      return;
+    }
   }
 }
 

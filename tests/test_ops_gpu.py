@@ -26,7 +26,9 @@ def _ref_conv(x, w, b):
 
 
 # (B,H,W): full 128-wide rows, narrow image, two segments with a ragged tail, single row, many images
-SHAPES = [(2, 16, 128), (1, 9, 40), (1, 5, 200), (3, 1, 7), (5, 3, 128), (1, 130, 128)]
+# ... and row bands that run across image boundaries with several rows per CTA (TMEM row-slot recycling)
+SHAPES = [(2, 16, 128), (1, 9, 40), (1, 5, 200), (3, 1, 7), (5, 3, 128), (1, 130, 128), (3, 160, 128), (40, 9, 64),
+          (2, 75, 300)]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
