@@ -161,6 +161,7 @@ typedef struct dfir_qrcan_net {
   const int* q_enabled;             /* device int32 [n_groups*n_blocks]: block owns a q_node */
   int any_q;                        /* host-side: any block has a q_node */
   int chunk_images;                 /* images per L2-resident pass; 0 = choose automatically */
+  int fuse_scale_residual;          /* 1: fold `r*s + x` into the next conv (dfir_conv3x3_c64_fused); 0: streamer kernel */
   /* tensor-core weights */
   const void* conv_w_bf16;          /* [n_conv][9*64*128 B] */
   const void* tail_w_bf16;          /* [9*16*128 B] */

@@ -31,11 +31,12 @@ int up_stages(int scale, int* r) {
   return -1;
 }
 
-// images per pass so that the block-level working set stays L2 resident and the row count fills the SMs
+// Images per pass.  Every trunk kernel carries ~12 us of fill/drain latency, so today fewer, larger passes
+// beat L2-resident ones (profiles/r01_summary.md): a pass is only split to bound the workspace (~6 GiB).
 int auto_chunk(int B, int H, int W, int precision) {
   const long long px = static_cast<long long>(H) * W;
-  const long long hot_per_px = precision == DFIR_PREC_BF16_TC ? 640 : 1024;
-  long long c = (72ll << 20) / std::max<long long>(1, px * hot_per_px);
+  const long long ws_per_px = precision == DFIR_PREC_BF16_TC ? 4200 : 6500;  // incl. the upsampler buffers
+  long long c = (6ll << 30) / std::max<long long>(1, px * ws_per_px);
   if (c < 1) c = 1;
   if (c > B) c = B;
   return static_cast<int>(c);
@@ -128,6 +129,7 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
     return d;
   };
   const float* attr_c = attr + static_cast<size_t>(b0) * n->attr_size;
+  const int nseg = (W + 127) / 128;
   // operand of a fused conv: x_{b} = r_{b-1} * s_{b-1} + x_{b-1}, with s_{b-1} evaluated in the kernel prologue
   auto fuse_in = [&](ConvTcDesc& d, int prev_blk, const float* xprev, float* xnew) {
     d.in_mode = IN_FUSED; d.r_bf16 = w.R; d.xin_f32 = xprev; d.xout_f32 = xnew;
@@ -136,6 +138,10 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
     d.attributes = attr_c; d.res_scale = 1.f;
     d.sq = n->any_q ? w.sq + (static_cast<size_t>(prev_blk) * B + b0) * C : nullptr;
   };
+  // Two schedules for the block chain.  fuse = 1 folds `r * s + x` into the next conv's input path (one
+  // launch and 12 B/element less per block, but the in-kernel transform is latency bound today); fuse = 0
+  // (default) runs it as the bandwidth-shaped streamer kernel (measurements: profiles/r01_summary.md).
+  const bool fuse = n->fuse_scale_residual != 0;
 
   for (int g = 0; g < ng; ++g) {
     const float* skip32 = g == 0 ? w.Hh : w.XA;            // group input (fp32 stream), kept for `res += x`
@@ -143,30 +149,39 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
     const float* xcur = skip32;                             // x_b: fp32 stream entering block b
     for (int b = 0; b < nb; ++b) {
       const int blk = g * nb + b;
-      // conv1: t = relu(conv(x_b)).  For b > 0 the operand x_b is formed on the fly (IN_FUSED) and written
-      // out as the new fp32 stream.
+      // conv1: t = relu(conv(x_b))
       ConvTcDesc c1 = base(g * per_group + 2 * b, EPI_BIAS_RELU);
       c1.out_bf16 = w.T;
       if (b == 0) {
         c1.in_bf16 = gin;
-      } else {
+      } else if (fuse) {
         float* xnew = (b & 1) ? w.XB : w.XB1;
         fuse_in(c1, blk - 1, xcur, xnew);
         xcur = xnew;
+      } else {
+        c1.in_bf16 = w.XBbf;
       }
       DFIR_TRY(conv3x3_c64_tc(c1, st));
       // conv2: r = conv(t) + per-row pooled sums (the avg-pool of the channel attention)
       ConvTcDesc c2 = base(g * per_group + 2 * b + 1, EPI_BIAS_POOL);
       c2.in_bf16 = w.T; c2.out_bf16 = w.R;
       DFIR_TRY(conv3x3_c64_tc(c2, st));
+      if (!fuse) {
+        // x_{b+1} = r * s + x_b  (fp32 stream, in place after the first block) + bf16 copy for the next conv
+        const float* sq = n->any_q ? w.sq + (static_cast<size_t>(blk) * B + b0) * C : nullptr;
+        DFIR_TRY(scale_residual(w.R, 1, b == 0 ? skip32 : w.XB, w.pool, nseg * H, make_ap(n, blk), attr_c, sq, 1.f,
+                                w.XB, w.XBbf, Bc, H, W, C, st));
+      }
     }
-    // group tail conv + `res += x` (group input): its operand is x_nb = r * s + x_{nb-1}, again fused
+    // group tail conv + `res += x` (group input)
     ConvTcDesc ct = base(g * per_group + 2 * nb, EPI_BIAS_SKIP);
     ct.out_bf16 = w.XAbf; ct.skip_f32 = skip32; ct.out_f32 = w.XA;
     if (nb == 0) {
       ct.in_bf16 = gin;
-    } else {
+    } else if (fuse) {
       fuse_in(ct, g * nb + nb - 1, xcur, nullptr);
+    } else {
+      ct.in_bf16 = w.XBbf;
     }
     DFIR_TRY(conv3x3_c64_tc(ct, st));
   }
@@ -397,7 +412,7 @@ long long dfir_qrcan_launch_count(const dfir_qrcan_net* net, int B, int H, int W
   const long long nb = net->n_blocks, ng = net->n_groups;
   long long per_chunk;
   if (precision == DFIR_PREC_BF16_TC) {
-    per_chunk = 1 + ng * (nb * 2 + 1) + 1 + static_cast<long long>(nup) * r * r + 1;
+    per_chunk = 1 + ng * (nb * (net->fuse_scale_residual ? 2 : 3) + 1) + 1 + static_cast<long long>(nup) * r * r + 1;
   } else {
     const long long pool = net->style != DFIR_STYLE_NONE ? 1 : 0;
     per_chunk = 1 + ng * (nb * (3 + pool) + 2) + 1 + nup + 1;  // group tail = conv + copy

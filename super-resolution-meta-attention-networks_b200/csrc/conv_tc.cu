@@ -50,7 +50,7 @@ using namespace ptx;
 
 namespace {
 
-constexpr int kSlots = 4;                    // smem input-row ring depth (producer -> A loaders)
+constexpr int kSlots = 6;                    // smem input-row ring depth (producer -> A loaders): deep = HBM prefetch
 constexpr int kSlotPix = 136;                // 130 px used (128 + 2 halo), rounded up to 8 px = 1024 B
 constexpr int kSlotBytes = kSlotPix * 128;   // 17408, multiple of 1024
 constexpr int kBoxPix = 130;

@@ -36,6 +36,7 @@ class QrcanNet(C.Structure):
         ("num_metadata", C.c_int), ("attr_size", C.c_int), ("meta_hidden", C.c_int),
         ("in_feats", C.c_int), ("out_feats", C.c_int),
         ("q_enabled", C.c_void_p), ("any_q", C.c_int), ("chunk_images", C.c_int),
+        ("fuse_scale_residual", C.c_int),
         ("conv_w_bf16", C.c_void_p), ("tail_w_bf16", C.c_void_p),
         ("conv_w_f32", C.c_void_p), ("up_w_f32", C.c_void_p), ("tail_w_f32", C.c_void_p),
         ("head_w_f32", C.c_void_p),

@@ -140,7 +140,7 @@ class QRCAN(nn.Module):
     def __init__(self, n_resblocks=20, n_resgroups=10, n_feats=64, in_feats=3, out_feats=3, scale=4, reduction=16,
                  res_scale=1.0, style='modulate', num_metadata=1, include_pixel_attention=False,
                  selective_meta_blocks=None, num_q_layers_inner_residual=None, include_q_layer=False,
-                 precision='bf16', chunk_images=0, **kwargs):
+                 precision='bf16', chunk_images=0, fuse_scale_residual=False, **kwargs):
         super().__init__()
         if precision not in PRECISIONS:
             raise RuntimeError("precision must be 'bf16' or 'fp32'")
@@ -148,6 +148,7 @@ class QRCAN(nn.Module):
         self.scale = scale
         self.precision = precision
         self.chunk_images = chunk_images
+        self.fuse_scale_residual = bool(fuse_scale_residual)
         self.cfg = dict(n_resblocks=n_resblocks, n_resgroups=n_resgroups, n_feats=n_feats, in_feats=in_feats,
                         out_feats=out_feats, scale=scale, reduction=reduction, num_metadata=num_metadata,
                         include_pixel_attention=include_pixel_attention)
@@ -187,7 +188,7 @@ class QRCAN(nn.Module):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def packed(self):
-        key = (self._param_versions(), self.precision, self.chunk_images)
+        key = (self._param_versions(), self.precision, self.chunk_images, self.fuse_scale_residual)
         if self._packed is None or self._packed.key != key:
             if self._packed is not None:
                 self._packed.close()
@@ -324,6 +325,7 @@ class PackedQrcan:
         d.num_metadata, d.attr_size, d.meta_hidden = M, self.attr_size, hid
         d.in_feats, d.out_feats = cfg["in_feats"], cfg["out_feats"]
         d.q_enabled, d.any_q, d.chunk_images = ptr(q_enabled), any_q, int(net.chunk_images)
+        d.fuse_scale_residual = int(net.fuse_scale_residual)
         d.conv_w_bf16, d.tail_w_bf16 = ptr(conv_w_bf16), ptr(tail_w_bf16)
         d.conv_w_f32, d.up_w_f32, d.tail_w_f32, d.head_w_f32 = ptr(conv_w_f32), ptr(up_w_f32), ptr(tail_w_f32), ptr(head_w)
         d.conv_b, d.up_b, d.tail_b, d.head_b = ptr(conv_b), ptr(up_b), ptr(tail_b), ptr(head_b)

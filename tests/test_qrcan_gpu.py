@@ -10,9 +10,9 @@ pytestmark = pytest.mark.gpu
 QRCAN_CASES = [n for n in golden_names() if n.startswith("qrcan") and "pa_" not in n]
 
 
-def _build(info, precision):
+def _build(info, precision, **extra):
     from deepfir_b200.qrcan import QRCAN
-    net = QRCAN(precision=precision, **info["kwargs"])
+    net = QRCAN(precision=precision, **extra, **info["kwargs"])
     sd, x, meta = case_tensors(info)
     net.load_state_dict(sd, strict=True)
     return net.cuda().eval(), x, meta
@@ -72,6 +72,20 @@ def test_qrcan_bf16_full_depth_psnr_delta():
     assert p >= 56.4, p
     pol, pol_err = _policy_error(info, ref)
     assert max_norm_err(out, ref) <= 2.0 * pol_err + 1e-4
+
+
+@pytest.mark.parametrize("name", ["qrcan_standard_g2b2", "qrcan_extended_scale8", "qrcan_mini_concat"])
+def test_fused_schedule_matches_streamer_schedule(name):
+    """fuse_scale_residual=True (r*s+x folded into the next conv) computes the same network."""
+    ref, info = load_golden(name)
+    net_a, x, meta = _build(info, "bf16")
+    net_b, _, _ = _build(info, "bf16", fuse_scale_residual=True)
+    with torch.no_grad():
+        a = net_a(x.cuda(), meta.cuda()).cpu()
+        b = net_b(x.cuda(), meta.cuda()).cpu()
+    _, pol_err = _policy_error(info, ref)
+    assert max_norm_err(b, ref) <= 2.0 * pol_err + 1e-4
+    assert max_norm_err(a, b) <= 2.0 * pol_err + 1e-4
 
 
 def test_batch_composition_does_not_change_an_image():

@@ -58,6 +58,32 @@ def conv_sweep(epi):
               (epi, bc, us, fl / us / 1e6, rows, us / max(1.0, -(-bc * LR // 148))))
 
 
+def fused_sweep():
+    wp = torch.empty(9 * 64 * 128, dtype=torch.uint8, device=dev)
+    w = (torch.randn(64, 64, 3, 3, device=dev) / 24).contiguous()
+    bias = torch.zeros(64, device=dev)
+    _lib.check(lib.dfir_pack_conv3x3_bf16(w.data_ptr(), wp.data_ptr(), 64, 64, 64, 0, 1, st()), "pack")
+    blob = torch.randn(4 * 64 + 4 + 64 * 4 + 64, device=dev) / 8
+    for bc in BCS:
+        r = torch.randn(bc, LR, LR, 64, device=dev).to(torch.bfloat16)
+        x = torch.randn(bc, LR, LR, 64, device=dev)
+        xo = torch.empty_like(x)
+        t = torch.empty_like(r)
+        pool = torch.randn(bc, LR, 64, device=dev)
+        attr = torch.rand(bc, 10, device=dev)
+        sq = torch.rand(bc, 64, device=dev)
+
+        def launch():
+            _lib.check(lib.dfir_conv3x3_c64_fused(r.data_ptr(), x.data_ptr(), xo.data_ptr(), pool.data_ptr(), 1,
+                                                  blob.data_ptr(), 4, 10, 10, attr.data_ptr(), sq.data_ptr(), 1.0,
+                                                  wp.data_ptr(), bias.data_ptr(), bc, LR, LR, 1, t.data_ptr(), None,
+                                                  None, st()), "fused")
+        us = timeit(launch, NREP[0], NREP[1])
+        fl = bc * LR * LR * 2 * 64 * 64 * 9
+        byt = bc * LR * LR * 64 * 12
+        print("fused conv bc=%3d: %8.2f us  %7.1f TFLOP/s  %7.1f GB/s (12 B/elem)" % (bc, us, fl / us / 1e6, byt / us / 1e3))
+
+
 def sr_sweep():
     for bc in (1, 4, 7, 8, 16, 32):
         r = torch.randn(bc, LR, LR, 64, device=dev).to(torch.bfloat16)
@@ -95,6 +121,8 @@ which = sys.argv[1:] or ["conv", "sr", "fwd"]
 if "conv" in which:
     conv_sweep(1)
     conv_sweep(2)
+if "fused" in which:
+    fused_sweep()
 if "sr" in which:
     sr_sweep()
 if "fwd" in which:
