@@ -78,7 +78,8 @@ int dfir_pack_conv3x3_f32(const float* w_oihw, float* out, int cout, int cin, vo
  *   in_bf16  : NHWC bf16 [B][H][W][cin_total]; the 64 channels starting at cin_off are consumed
  *   wpacked  : from dfir_pack_conv3x3_bf16;  bias: fp32 [64] (or [16])
  *   epi      : 0 bias | 1 bias+ReLU | 2 bias + per-row channel sums into pool_rows[B][nseg][H][64]
- *              | 3 bias + skip_f32 (NHWC fp32) -> out_f32 (NHWC fp32, may be NULL) and out_bf16
+ *              | 3 bias + skip_f32 (NHWC fp32) -> out_f32 (NHWC fp32, may be NULL) and out_bf16 (TMA store;
+ *                works with strided outputs; dfir_conv3x3_c64_scale_skip is the fast dense variant)
  *              | 4 tail: out_f32 is NCHW fp32 [B][cout][H][W], no bf16 output
  *   out_bf16 : NHWC bf16, addressed with explicit byte strides so that PixelShuffle
  *              (advanced/common.py:30) folds into the store: for sub-pixel (i,j) of an r-times upsampler
@@ -103,6 +104,28 @@ int dfir_conv3x3_c64_fused(const void* r_bf16, const float* x_in, float* x_out, 
                            const float* ca_params, int R, int M, int A, const float* attributes, const float* sq,
                            float res_scale, const void* wpacked, const float* bias, int B, int H, int W, int epi,
                            void* out_bf16, const float* skip_f32, float* out_f32, void* stream);
+
+/* --- pool-by-linearity trio (the default Q-RCAN schedule) -------------------------------------------------
+ * The channel attention of an RCAB needs mean_pixels(r), r = conv2(t).  That mean is linear in t, so it
+ * follows from a few sums of t = relu(conv1(x)) — before conv2 runs — and conv2's epilogue can apply the
+ * attention scale and the residual add itself (QRCAB.forward, attention_manipulators/architectures.py:172-180).
+ *
+ * dfir_conv3x3_c64_stats : RCAB conv1 (`body[0]` + ReLU, :155-160): out_bf16 = t (dense NHWC) and, of the
+ *   bf16-rounded t: pool_rows[B][nseg][H][64] (per-row channel sums), col_first/col_last[B][H][64] (t at x = 0
+ *   and x = W-1 of every row).
+ * dfir_ca_from_stats     : QCALayer (:105-125) on mean(conv2(t)) reconstructed from those sums, times the
+ *   meta-attention scale sq (q_layer.py:39-43): svec[B][64].  w2_packed/bias2 = conv2's packed weights / bias.
+ * dfir_conv3x3_c64_scale_skip : RCAB conv2 + `res * y` (twice) + `res += x` (:173-179), also the group / trunk
+ *   tail conv with svec = NULL (:231-232, :312-313): out_f32 = (conv(in) + bias) * svec[b] + skip_f32 (NHWC fp32,
+ *   may alias skip_f32, may be NULL), out_bf16 = bf16(out_f32) (dense NHWC). */
+int dfir_conv3x3_c64_stats(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
+                           void* out_bf16, float* pool_rows, float* col_first, float* col_last, void* stream);
+int dfir_ca_from_stats(const float* pool_rows, const float* col_first, const float* col_last, const void* w2_packed,
+                       const float* bias2, int style, const float* ca_params, int R, int M, int A,
+                       const float* attributes, const float* sq, float* svec, int B, int H, int W, void* stream);
+int dfir_conv3x3_c64_scale_skip(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
+                                const float* svec, const float* skip_f32, float* out_f32, void* out_bf16,
+                                void* stream);
 
 /* default_conv on CUDA cores, fp32 NHWC in/out, any Cin % 4 == 0 and any Cout.
  *   w_packed from dfir_pack_conv3x3_f32; skip (optional) NHWC fp32 added after bias; relu applied last;
@@ -161,7 +184,7 @@ typedef struct dfir_qrcan_net {
   const int* q_enabled;             /* device int32 [n_groups*n_blocks]: block owns a q_node */
   int any_q;                        /* host-side: any block has a q_node */
   int chunk_images;                 /* images per L2-resident pass; 0 = choose automatically */
-  int fuse_scale_residual;          /* 1: fold `r*s + x` into the next conv (dfir_conv3x3_c64_fused); 0: streamer kernel */
+  int schedule;                     /* block chain: 0 pool-by-linearity (default), 1 fused-in, 2 streamer */
   /* tensor-core weights */
   const void* conv_w_bf16;          /* [n_conv][9*64*128 B] */
   const void* tail_w_bf16;          /* [9*16*128 B] */

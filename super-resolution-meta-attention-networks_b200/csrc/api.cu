@@ -43,7 +43,7 @@ int auto_chunk(int B, int H, int W, int precision) {
 }
 
 struct QrcanWs {
-  float *Hh, *XA, *XB, *XB1, *pool, *sq;
+  float *Hh, *XA, *XB, *XB1, *pool, *sq, *colf, *coll, *svec;
   __nv_bfloat16 *Hbf, *XAbf, *XBbf, *T, *R;
   float *T32, *R32;
   void* U[3];
@@ -61,6 +61,9 @@ QrcanWs carve_qrcan(const dfir_qrcan_net* n, int B, int Bc, int H, int W, int pr
   const int nseg = (W + 127) / 128;
   w.pool = c.take<float>(static_cast<size_t>(Bc) * nseg * H * C * 4);
   w.sq = c.take<float>(static_cast<size_t>(n->n_groups) * n->n_blocks * B * C * 4);
+  w.colf = c.take<float>(static_cast<size_t>(Bc) * H * C * 4);
+  w.coll = c.take<float>(static_cast<size_t>(Bc) * H * C * 4);
+  w.svec = c.take<float>(static_cast<size_t>(Bc) * C * 4);
   int r = 0;
   const int nup = up_stages(n->scale, &r);
   if (precision == DFIR_PREC_BF16_TC) {
@@ -138,10 +141,13 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
     d.attributes = attr_c; d.res_scale = 1.f;
     d.sq = n->any_q ? w.sq + (static_cast<size_t>(prev_blk) * B + b0) * C : nullptr;
   };
-  // Two schedules for the block chain.  fuse = 1 folds `r * s + x` into the next conv's input path (one
-  // launch and 12 B/element less per block, but the in-kernel transform is latency bound today); fuse = 0
-  // (default) runs it as the bandwidth-shaped streamer kernel (measurements: profiles/r01_summary.md).
-  const bool fuse = n->fuse_scale_residual != 0;
+  // Three schedules for the block chain (net->schedule):
+  //   0 (default) pool-by-linearity: conv1 also emits the sums of t that determine the block's channel
+  //     attention, a tiny kernel turns them into s, and conv2's epilogue computes x <- (conv2(t)+b)*s + x
+  //     directly: r never exists in memory and there is no elementwise pass.
+  //   1 fused-in : `r*s + x` folded into the next conv's input path (dfir_conv3x3_c64_fused).
+  //   2 streamer : separate bandwidth-shaped elementwise kernel (dfir_ca_scale_residual).
+  const int sched = n->schedule;
 
   for (int g = 0; g < ng; ++g) {
     const float* skip32 = g == 0 ? w.Hh : w.XA;            // group input (fp32 stream), kept for `res += x`
@@ -149,12 +155,13 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
     const float* xcur = skip32;                             // x_b: fp32 stream entering block b
     for (int b = 0; b < nb; ++b) {
       const int blk = g * nb + b;
+      const float* sq = n->any_q ? w.sq + (static_cast<size_t>(blk) * B + b0) * C : nullptr;
       // conv1: t = relu(conv(x_b))
-      ConvTcDesc c1 = base(g * per_group + 2 * b, EPI_BIAS_RELU);
-      c1.out_bf16 = w.T;
+      ConvTcDesc c1 = base(g * per_group + 2 * b, sched == 0 ? EPI_RELU_STATS : EPI_BIAS_RELU);
+      c1.out_bf16 = w.T; c1.col_first = w.colf; c1.col_last = w.coll;
       if (b == 0) {
         c1.in_bf16 = gin;
-      } else if (fuse) {
+      } else if (sched == 1) {
         float* xnew = (b & 1) ? w.XB : w.XB1;
         fuse_in(c1, blk - 1, xcur, xnew);
         xcur = xnew;
@@ -162,23 +169,33 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
         c1.in_bf16 = w.XBbf;
       }
       DFIR_TRY(conv3x3_c64_tc(c1, st));
+      if (sched == 0) {
+        const int w2 = g * per_group + 2 * b + 1;
+        DFIR_TRY(ca_from_stats(w.pool, w.colf, w.coll, cw + static_cast<size_t>(w2) * wbytes,
+                               n->conv_b + static_cast<size_t>(w2) * 64, make_ap(n, blk), attr_c, sq, w.svec, Bc, H, W, st));
+        // conv2 + attention scale + residual: x_{b+1} = (conv(t) + b) * s + x_b (fp32, in place after block 0)
+        ConvTcDesc c2 = base(w2, EPI_SCALE_SKIP);
+        c2.in_bf16 = w.T; c2.svec = w.svec; c2.skip_f32 = b == 0 ? skip32 : w.XB; c2.out_f32 = w.XB;
+        c2.out_bf16 = w.XBbf;
+        DFIR_TRY(conv3x3_c64_tc(c2, st));
+        continue;
+      }
       // conv2: r = conv(t) + per-row pooled sums (the avg-pool of the channel attention)
       ConvTcDesc c2 = base(g * per_group + 2 * b + 1, EPI_BIAS_POOL);
       c2.in_bf16 = w.T; c2.out_bf16 = w.R;
       DFIR_TRY(conv3x3_c64_tc(c2, st));
-      if (!fuse) {
+      if (sched == 2) {
         // x_{b+1} = r * s + x_b  (fp32 stream, in place after the first block) + bf16 copy for the next conv
-        const float* sq = n->any_q ? w.sq + (static_cast<size_t>(blk) * B + b0) * C : nullptr;
         DFIR_TRY(scale_residual(w.R, 1, b == 0 ? skip32 : w.XB, w.pool, nseg * H, make_ap(n, blk), attr_c, sq, 1.f,
                                 w.XB, w.XBbf, Bc, H, W, C, st));
       }
     }
     // group tail conv + `res += x` (group input)
-    ConvTcDesc ct = base(g * per_group + 2 * nb, EPI_BIAS_SKIP);
-    ct.out_bf16 = w.XAbf; ct.skip_f32 = skip32; ct.out_f32 = w.XA;
+    ConvTcDesc ct = base(g * per_group + 2 * nb, EPI_SCALE_SKIP);
+    ct.out_bf16 = w.XAbf; ct.skip_f32 = skip32; ct.out_f32 = w.XA; ct.svec = nullptr;
     if (nb == 0) {
       ct.in_bf16 = gin;
-    } else if (fuse) {
+    } else if (sched == 1) {
       fuse_in(ct, g * nb + nb - 1, xcur, nullptr);
     } else {
       ct.in_bf16 = w.XBbf;
@@ -186,7 +203,7 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
     DFIR_TRY(conv3x3_c64_tc(ct, st));
   }
   {
-    ConvTcDesc cf = base(ng * per_group, EPI_BIAS_SKIP);
+    ConvTcDesc cf = base(ng * per_group, EPI_SCALE_SKIP);
     cf.in_bf16 = ng == 0 ? w.Hbf : w.XAbf;
     cf.out_bf16 = w.XBbf; cf.skip_f32 = w.Hh; cf.out_f32 = nullptr;
     DFIR_TRY(conv3x3_c64_tc(cf, st));
@@ -365,6 +382,52 @@ int dfir_conv3x3_c64_fused(const void* r_bf16, const float* x_in, float* x_out, 
   return conv3x3_c64_tc(d, S(stream));
 }
 
+int dfir_conv3x3_c64_stats(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
+                           void* out_bf16, float* pool_rows, float* col_first, float* col_last, void* stream) {
+  if (in_bf16 == nullptr || out_bf16 == nullptr) return DFIR_ERR_ARG;
+  ConvTcDesc d{};
+  d.B = B; d.H = H; d.W = W; d.cin_total = 64; d.cin_off = 0; d.cout = 64; d.epi = EPI_RELU_STATS; d.in_mode = IN_TMA;
+  d.in_bf16 = in_bf16; d.wpacked = wpacked; d.bias = bias; d.out_bf16 = out_bf16;
+  d.out_pix_stride = 128; d.out_row_stride = static_cast<long long>(W) * 128;
+  d.out_img_stride = static_cast<long long>(H) * W * 128;
+  d.pool_rows = pool_rows; d.col_first = col_first; d.col_last = col_last;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return DFIR_ERR_CUDA;
+  d.num_sms = sms;
+  return conv3x3_c64_tc(d, S(stream));
+}
+
+int dfir_ca_from_stats(const float* pool_rows, const float* col_first, const float* col_last, const void* w2_packed,
+                       const float* bias2, int style, const float* ca_params, int R, int M, int A,
+                       const float* attributes, const float* sq, float* svec, int B, int H, int W, void* stream) {
+  AttnParams ap{};
+  ap.style = style; ap.C = 64; ap.R = R; ap.M = M; ap.A = A; ap.w[0] = ca_params;
+  if (pool_rows == nullptr || col_first == nullptr || col_last == nullptr || w2_packed == nullptr ||
+      ca_params == nullptr || svec == nullptr)
+    return DFIR_ERR_ARG;
+  return ca_from_stats(pool_rows, col_first, col_last, w2_packed, bias2, ap, attributes, sq, svec, B, H, W, S(stream));
+}
+
+int dfir_conv3x3_c64_scale_skip(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
+                                const float* svec, const float* skip_f32, float* out_f32, void* out_bf16,
+                                void* stream) {
+  if (in_bf16 == nullptr || out_bf16 == nullptr || skip_f32 == nullptr) return DFIR_ERR_ARG;
+  ConvTcDesc d{};
+  d.B = B; d.H = H; d.W = W; d.cin_total = 64; d.cin_off = 0; d.cout = 64; d.epi = EPI_SCALE_SKIP; d.in_mode = IN_TMA;
+  d.in_bf16 = in_bf16; d.wpacked = wpacked; d.bias = bias; d.out_bf16 = out_bf16;
+  d.out_pix_stride = 128; d.out_row_stride = static_cast<long long>(W) * 128;
+  d.out_img_stride = static_cast<long long>(H) * W * 128;
+  d.svec = svec; d.skip_f32 = skip_f32; d.out_f32 = out_f32;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return DFIR_ERR_CUDA;
+  d.num_sms = sms;
+  return conv3x3_c64_tc(d, S(stream));
+}
+
 int dfir_conv3x3_f32(const float* in, const float* w_packed, const float* bias, const float* skip, float* out, int B,
                      int H, int W, int Cin, int Cout, int relu, int ps_r, int out_nchw, void* stream) {
   return conv3x3_f32(in, w_packed, bias, skip, out, B, H, W, Cin, Cout, relu, ps_r, out_nchw, S(stream));
@@ -412,7 +475,7 @@ long long dfir_qrcan_launch_count(const dfir_qrcan_net* net, int B, int H, int W
   const long long nb = net->n_blocks, ng = net->n_groups;
   long long per_chunk;
   if (precision == DFIR_PREC_BF16_TC) {
-    per_chunk = 1 + ng * (nb * (net->fuse_scale_residual ? 2 : 3) + 1) + 1 + static_cast<long long>(nup) * r * r + 1;
+    per_chunk = 1 + ng * (nb * (net->schedule == 1 ? 2 : 3) + 1) + 1 + static_cast<long long>(nup) * r * r + 1;
   } else {
     const long long pool = net->style != DFIR_STYLE_NONE ? 1 : 0;
     per_chunk = 1 + ng * (nb * (3 + pool) + 2) + 1 + nup + 1;  // group tail = conv + copy

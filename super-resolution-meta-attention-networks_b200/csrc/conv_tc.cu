@@ -147,7 +147,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
 
   if (threadIdx.x == 0) {
     if (INMODE == IN_TMA) prefetch_tmap(&tmap_in);
-    if (EPI != EPI_TAIL_NCHW) prefetch_tmap(&tmap_out);
+    if (EPI != EPI_TAIL_NCHW && EPI != EPI_SCALE_SKIP) prefetch_tmap(&tmap_out);
     for (int i = 0; i < kSlots; ++i) {
       mbar_init(&full[i], INMODE == IN_FUSED ? 128 : 1);
       mbar_init(&empty[i], 4);
@@ -169,7 +169,13 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-  const bool probe = a.debug_probe != 0 && blockIdx.x == 0 && lane == 0;
+  const bool probe = (a.debug_probe & 1) != 0 && blockIdx.x == 0 && lane == 0;
+  const bool exp_skip_store = (a.debug_probe & 2) != 0;  // timing experiments only (wrong results)
+  const bool exp_one_copy = (a.debug_probe & 4) != 0;
+  const bool exp_no_copy = (a.debug_probe & 8) != 0;
+  const bool exp_no_epi = (a.debug_probe & 32) != 0;
+  const bool exp_n192 = (a.debug_probe & 64) != 0;   // 12 MMAs of N=192 per row (timing only)
+  const bool exp_n128 = (a.debug_probe & 128) != 0;  // 18 MMAs of N=128 per row (timing only)
 
   if (g0 < g1) {
     if (warp == 0) {
@@ -216,7 +222,27 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         }
         tcgen05_fence_after();
         if (probe) g_dfir_progress[3] = it + 1;
-        if (leader) {
+        if (leader && (exp_n192 || exp_n128)) {
+          if constexpr (NT == 64) {
+            constexpr uint32_t id192 = make_idesc_bf16_f32(128, 192);
+            constexpr uint32_t id128 = make_idesc_bf16_f32(128, 128);
+            const int reps = exp_n192 ? 1 : 2;
+            for (int rpt = 0; rpt < reps; ++rpt)
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t db = db_base + static_cast<uint32_t>(((dx * 3) * NT * 128 + k * 32) >> 4);
+                  umma_f16_ts(tmem_base, a_col[1] + dx * 32 + k * 8, db, exp_n192 ? id192 : id128, 1u);
+                }
+            if (!exp_n192)
+              for (int k = 0; k < 6; ++k)
+                umma_f16_ts(tmem_base, a_col[1] + k * 8, db_base + static_cast<uint32_t>((k * 32) >> 4), id128, 1u);
+            for (int rel = released; rel <= nc - 1; ++rel) umma_commit(&aempty[rel % kARows]);
+            umma_commit(&tfull[acc]);
+            for (int rel = (released > nc ? released : nc); rel <= nc_next - 2; ++rel) umma_commit(&aempty[rel % kARows]);
+          }
+        } else if (leader) {
           const uint32_t d_tmem = tmem_base + acc * NT;
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
@@ -228,13 +254,18 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
                 umma_f16_ts(d_tmem, a_col[dy] + dx * 32 + k * 8, db, idesc, (dy | dx | k) != 0 ? 1u : 0u);
               }
             }
+            if (dy == 0) {
+              // the top row (and anything older) is dead as soon as the dy = 0 taps have executed: hand its TMEM
+              // slot back now so that the loaders refill it while the remaining 24 MMAs of this row run
+              for (int rel = released; rel <= nc - 1; ++rel) umma_commit(&aempty[rel % kARows]);
+            }
           }
           umma_commit(&tfull[acc]);
-          // rows the NEXT centre no longer needs go back to the loaders: everything below next - 1 (at an
-          // image boundary that also frees the last row and the bottom pad row of the finished image —
-          // keeping them would deadlock the 4-slot TMEM row ring)
-          for (int rel = released; rel <= nc_next - 2; ++rel) umma_commit(&aempty[rel % kARows]);
+          // at an image boundary the next centre also skips the last row and the bottom pad row of the finished
+          // image — keeping them would deadlock the 4-slot TMEM row ring
+          for (int rel = (released > nc ? released : nc); rel <= nc_next - 2; ++rel) umma_commit(&aempty[rel % kARows]);
         }
+        released = nc > released ? nc : released;
         released = nc_next - 1 > released ? nc_next - 1 : released;
         __syncwarp();
       }
@@ -251,6 +282,20 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         tcgen05_fence_after();
         const uint8_t* srow = ring + slot * kSlotBytes;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kAColBase + as * kAColsPerRow;
+        if (exp_no_copy) {
+        } else if (exp_one_copy) {
+          const int p = m + 1;
+          const uint4* src = reinterpret_cast<const uint4*>(srow + p * 128);
+          uint32_t v[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 t = src[c ^ (p & 7)];
+            v[4 * c + 0] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+          }
+          tmem_st_32x32b_x32(t_row, v);
+          tmem_st_32x32b_x32(t_row + 32, v);
+          tmem_st_32x32b_x32(t_row + 64, v);
+        } else {
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
           const int p = m + dx;  // ring pixel feeding output pixel m for this tap column
@@ -265,6 +310,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             v[4 * c + 3] = t.w;
           }
           tmem_st_32x32b_x32(t_row + dx * 32, v);
+        }
         }
         tmem_st_wait();
         tcgen05_fence_before();
@@ -405,6 +451,12 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         if (probe) g_dfir_progress[8 + q] = it + 1;
         mbar_wait(&tfull[acc], (it / kAcc) & 1, 8);
         tcgen05_fence_after();
+        if (exp_no_epi) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+          continue;
+        }
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * NT;
 
         if constexpr (EPI == EPI_TAIL_NCHW) {
@@ -420,6 +472,59 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
 #pragma unroll
             for (int c = 0; c < NT; ++c)
               if (c < a.cout) o[c * plane] = __uint_as_float(r0[c]) + bias_s[c];
+          }
+        } else if constexpr (EPI == EPI_SCALE_SKIP) {
+          // v = (acc + bias) * s[b][c]; fp32 tile in smem (chunk-rotated: conflict free), then a coalesced pass
+          // adds the fp32 skip and writes the fp32 stream + its bf16 copy straight to global memory.
+          float* tile = reinterpret_cast<float*>(stage);  // [128 px][64] fp32 = 32 KB = both staging buffers
+          const float* sv = a.svec != nullptr ? a.svec + static_cast<size_t>(b) * 64 : nullptr;
+          named_bar_sync(1, 128);  // previous row's coalesced pass has finished reading the tile
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t rv[32];
+            tmem_ld_32x32b_x32(taddr + h * 32, rv);
+            tmem_ld_wait();
+            if (h == 1) {
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty[acc]);
+            }
+            float4* trow = reinterpret_cast<float4*>(tile + m * 64);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float4 o;
+              const int ch = h * 32 + c * 4;
+              o.x = __uint_as_float(rv[4 * c + 0]) + bias_s[ch + 0];
+              o.y = __uint_as_float(rv[4 * c + 1]) + bias_s[ch + 1];
+              o.z = __uint_as_float(rv[4 * c + 2]) + bias_s[ch + 2];
+              o.w = __uint_as_float(rv[4 * c + 3]) + bias_s[ch + 3];
+              if (sv != nullptr) {
+                const float4 s4 = *reinterpret_cast<const float4*>(sv + ch);
+                o.x *= s4.x; o.y *= s4.y; o.z *= s4.z; o.w *= s4.w;
+              }
+              trow[((h * 8 + c) + m) & 15] = o;
+            }
+          }
+          named_bar_sync(2, 128);
+          {
+            const int npx = min(128, a.W - seg * 128);  // valid pixels of this row segment
+            const size_t row_e = ((static_cast<size_t>(b) * a.H + y) * a.W + seg * 128) * 64;
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+              const int idx = i * 128 + et;  // float4 index inside the tile: pixel = idx / 16, chunk = idx % 16
+              const int p = idx >> 4, c4 = idx & 15;
+              if (p < npx) {
+                float4 o = reinterpret_cast<const float4*>(tile + p * 64)[(c4 + p) & 15];
+                const size_t e = row_e + static_cast<size_t>(p) * 64 + c4 * 4;
+                const float4 sk = *reinterpret_cast<const float4*>(a.skip_f32 + e);
+                o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
+                if (a.out_f32 != nullptr) *reinterpret_cast<float4*>(a.out_f32 + e) = o;
+                uint2 pk;
+                pk.x = pack_bf16x2(o.x, o.y);
+                pk.y = pack_bf16x2(o.z, o.w);
+                *reinterpret_cast<uint2*>(a.out_bf16_direct + e) = pk;
+              }
+            }
           }
         } else {
           const int sb = it & 1;
@@ -440,9 +545,26 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             float v[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rv[i]) + bias_s[h * 32 + i];
-            if constexpr (EPI == EPI_BIAS_RELU) {
+            if constexpr (EPI == EPI_BIAS_RELU || EPI == EPI_RELU_STATS) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if constexpr (EPI == EPI_RELU_STATS) {
+              // statistics are taken of the bf16-ROUNDED t, i.e. of exactly what the next conv consumes
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+              if (valid && (x == 0 || x == a.W - 1)) {
+                float* dst = (x == 0 ? a.col_first : a.col_last) + (static_cast<size_t>(b) * a.H + y) * 64 + h * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                  *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                if (a.W == 1) {  // the only column is both first and last
+                  float* d2 = a.col_last + (static_cast<size_t>(b) * a.H + y) * 64 + h * 32;
+#pragma unroll
+                  for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(d2 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                }
+              }
             }
             if constexpr (EPI == EPI_BIAS_SKIP) {
               if (valid) {
@@ -461,6 +583,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             }
             // bf16 -> swizzled staging row
             uint4* row = reinterpret_cast<uint4*>(st + m * 128);
+            if (!exp_skip_store)
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               uint4 pk;
@@ -470,8 +593,8 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               pk.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
               row[(h * 4 + c) ^ (m & 7)] = pk;
             }
-            if constexpr (EPI == EPI_BIAS_POOL) {
-              // per-row channel sums of the fp32 (pre-rounding) conv output, garbage pixels masked
+            if constexpr (EPI == EPI_BIAS_POOL || EPI == EPI_RELU_STATS) {
+              // per-row channel sums (EPI_BIAS_POOL: of the fp32 conv output; EPI_RELU_STATS: of rounded t)
               if (!valid) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -482,11 +605,11 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           }
           fence_proxy_async_smem();
           named_bar_sync(2, 128);
-          if (et == 0) {
+          if (et == 0 && !exp_skip_store) {
             tma_store_4d(&tmap_out, st, 0, seg * 128, y, b);
             tma_store_commit();
           }
-          if constexpr (EPI == EPI_BIAS_POOL) {
+          if constexpr (EPI == EPI_BIAS_POOL || EPI == EPI_RELU_STATS) {
             if (et < 64) {
               const float s = ((pool_s[et] + pool_s[64 + et]) + pool_s[128 + et]) + pool_s[192 + et];
               a.pool_rows[(static_cast<size_t>(col) * a.H + y) * 64 + et] = s;
@@ -494,7 +617,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           }
         }
       }
-      if (EPI != EPI_TAIL_NCHW && et == 0) tma_store_wait<0>();
+      if (EPI != EPI_TAIL_NCHW && EPI != EPI_SCALE_SKIP && et == 0) tma_store_wait<0>();
     }
   }
 
@@ -587,6 +710,11 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
        (d.ca_A > 0 && d.attributes == nullptr)))
     return DFIR_ERR_ARG;
   if (!fused && d.in_bf16 == nullptr) return DFIR_ERR_ARG;
+  if (d.epi == EPI_SCALE_SKIP && (d.skip_f32 == nullptr || d.out_bf16 == nullptr || d.out_pix_stride != 128 ||
+                                  d.out_row_stride != static_cast<long long>(d.W) * 128))
+    return DFIR_ERR_ARG;  // the direct-store epilogue writes dense NHWC
+  if (d.epi == EPI_RELU_STATS && (d.pool_rows == nullptr || d.col_first == nullptr || d.col_last == nullptr))
+    return DFIR_ERR_ARG;
   CUtensorMap tin, tout;
   int rc = DFIR_OK;
   if (!fused) {
@@ -616,11 +744,15 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   a.skip_f32 = d.skip_f32;
   a.out_f32 = d.out_f32;
   a.pool_rows = d.pool_rows;
+  a.col_first = d.col_first;
+  a.col_last = d.col_last;
+  a.svec = d.svec;
+  a.out_bf16_direct = reinterpret_cast<__nv_bfloat16*>(d.out_bf16);
   a.r_bf16 = reinterpret_cast<const __nv_bfloat16*>(d.r_bf16);
   a.xin_f32 = d.xin_f32;
   a.xout_f32 = d.xout_f32;
   a.res_scale = d.res_scale;
-  a.debug_probe = getenv("DFIR_DEBUG_PROBE") != nullptr ? 1 : 0;
+  a.debug_probe = getenv("DFIR_DEBUG_PROBE") != nullptr ? atoi(getenv("DFIR_DEBUG_PROBE")) : 0;
   a.ca_params = d.ca_params;
   a.attributes = d.attributes;
   a.sq = d.sq;
@@ -638,6 +770,7 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
     switch (d.epi) {
       case EPI_BIAS_RELU: return launch_one<64, EPI_BIAS_RELU, IN_FUSED>(tin, tout, a, grid, stream);
       case EPI_BIAS_SKIP: return launch_one<64, EPI_BIAS_SKIP, IN_FUSED>(tin, tout, a, grid, stream);
+      case EPI_SCALE_SKIP: return launch_one<64, EPI_SCALE_SKIP, IN_FUSED>(tin, tout, a, grid, stream);
       default: return DFIR_ERR_ARG;
     }
   }
@@ -646,6 +779,8 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
     case EPI_BIAS_RELU: return launch_one<64, EPI_BIAS_RELU, IN_TMA>(tin, tout, a, grid, stream);
     case EPI_BIAS_POOL: return launch_one<64, EPI_BIAS_POOL, IN_TMA>(tin, tout, a, grid, stream);
     case EPI_BIAS_SKIP: return launch_one<64, EPI_BIAS_SKIP, IN_TMA>(tin, tout, a, grid, stream);
+    case EPI_RELU_STATS: return launch_one<64, EPI_RELU_STATS, IN_TMA>(tin, tout, a, grid, stream);
+    case EPI_SCALE_SKIP: return launch_one<64, EPI_SCALE_SKIP, IN_TMA>(tin, tout, a, grid, stream);
     case EPI_TAIL_NCHW: return launch_one<16, EPI_TAIL_NCHW, IN_TMA>(tin, tout, a, grid, stream);
     default: return DFIR_ERR_ARG;
   }

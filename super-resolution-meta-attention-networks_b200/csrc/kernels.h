@@ -16,6 +16,10 @@ enum : int {
   EPI_BIAS_POOL = 2,  // out_bf16 = acc + b ; per-row channel sums     (RCAB conv2 + CA avg-pool, :107)
   EPI_BIAS_SKIP = 3,  // out_f32 = acc + b + skip ; out_bf16 = bf16()  (group / trunk tail conv + `res += x`, :231-232)
   EPI_TAIL_NCHW = 4,  // out_f32 NCHW, cout<=16 real channels          (tail conv 64 -> 3, :303)
+  EPI_RELU_STATS = 5, // RCAB conv1: out_bf16 = t = relu(acc + b) plus the sums of t that determine the channel
+                      // attention of the block BEFORE its second conv runs (pool-by-linearity)
+  EPI_SCALE_SKIP = 6, // RCAB conv2 / group conv: out_f32 = (acc + b) * s[b][c] + skip ; out_bf16 = bf16(out_f32)
+                      // i.e. QCALayer/ParaCALayer `x * y` and `res += x` in the epilogue (:127,179; q_layer.py:43)
 };
 
 enum : int { IN_TMA = 0, IN_FUSED = 1 };  // input modes of the tensor-core conv (see conv_tc.cu)
@@ -27,6 +31,10 @@ struct ConvTcArgs {  // kernel argument block
   const float* skip_f32;
   float* out_f32;
   float* pool_rows;
+  float* col_first;         // EPI_RELU_STATS: t at x = 0 / x = W-1 of every row, fp32 [B][H][64]
+  float* col_last;
+  const float* svec;        // EPI_SCALE_SKIP: per-image channel scale [B][64] (nullptr = 1)
+  __nv_bfloat16* out_bf16_direct;  // EPI_SCALE_SKIP writes its bf16 copy with plain coalesced stores
   // IN_FUSED: conv input = r * s[b] + xin (xout = fp32 copy of it for the rows the CTA owns), with
   // s[b] = CA_style(mean(r_b) from pool_rows, attributes[b]) * sq[b]   (style NONE: s = res_scale * sq)
   const __nv_bfloat16* r_bf16;
@@ -55,6 +63,9 @@ struct ConvTcDesc {  // host-side launch description
   const float* skip_f32;
   float* out_f32;
   float* pool_rows;
+  float* col_first;
+  float* col_last;
+  const float* svec;
   const void* r_bf16;      // IN_FUSED
   const float* xin_f32;
   float* xout_f32;
@@ -88,6 +99,9 @@ int meta_attention(const float* meta, const float* w1, const float* b1, const fl
 int scale_residual(const void* r, int r_is_bf16, const float* x_in, const float* pool_rows, int pool_nrows,
                    const AttnParams& ap, const float* attributes, const float* sq, float res_scale, float* x_out,
                    __nv_bfloat16* x_out_bf16, int B, int H, int W, int C, cudaStream_t s);
+int ca_from_stats(const float* pool_rows, const float* col_first, const float* col_last, const void* w2_packed,
+                  const float* bias2, const AttnParams& ap, const float* attributes, const float* sq, float* svec, int B,
+                  int H, int W, cudaStream_t s);
 int nchw_to_nhwc_bf16(const float* in, __nv_bfloat16* out, int B, int C, int H, int W, cudaStream_t s);
 int f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t s);
 

@@ -311,6 +311,104 @@ scale_residual_kernel(const void* __restrict__ r_, const float* __restrict__ x_i
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Channel attention of an RCAB from statistics of t = relu(conv1(x)), i.e. BEFORE conv2 runs.
+//   mean over pixels of r = conv2(t) is linear in t:
+//     mean(r)[co] = b2[co] + (1/HW) * sum_{tap,ci} W2[co][ci][tap] * S[tap][ci],
+//     S[tap][ci]  = sum over the pixels of t[ci] that the tap (dy,dx) reads inside the image
+//                 = T - (row excluded by dy) - (column excluded by dx) + (their corner)
+//   with T = total sum, first/last row sums and first/last column sums of t.  conv2's epilogue can then apply
+//   the attention scale and the residual add itself, and r never goes to memory.
+// grid = B images, 256 threads.  All reductions run in a fixed order (bit-reproducible).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ca_from_stats_kernel(const float* __restrict__ pool_rows, const float* __restrict__ col_first,
+                     const float* __restrict__ col_last, const __nv_bfloat16* __restrict__ w2,
+                     const float* __restrict__ bias2, AttnParams ap, const float* __restrict__ attributes,
+                     const float* __restrict__ sq, float* __restrict__ svec, int H, int W, int nseg) {
+  __shared__ float part[4][5][64];  // partial sums: T, R0, RL, C0, CL by 4 row groups
+  __shared__ float S[9][64];
+  __shared__ float y_s[64];
+  __shared__ float s_s[64];
+  __shared__ float attr_s[512];
+  __shared__ float tmp[1024];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int c = tid & 63, grp = tid >> 6;
+  const float* pr = pool_rows + static_cast<size_t>(b) * nseg * H * 64;
+  const float* cf = col_first + static_cast<size_t>(b) * H * 64;
+  const float* cl = col_last + static_cast<size_t>(b) * H * 64;
+  {
+    float t = 0.f, c0 = 0.f, c1 = 0.f;
+    for (int seg = 0; seg < nseg; ++seg)
+      for (int y = grp; y < H; y += 4) t += pr[(static_cast<size_t>(seg) * H + y) * 64 + c];
+    for (int y = grp; y < H; y += 4) {
+      c0 += cf[static_cast<size_t>(y) * 64 + c];
+      c1 += cl[static_cast<size_t>(y) * 64 + c];
+    }
+    float r0 = 0.f, rl = 0.f;
+    if (grp == 0)
+      for (int seg = 0; seg < nseg; ++seg) {
+        r0 += pr[(static_cast<size_t>(seg) * H + 0) * 64 + c];
+        rl += pr[(static_cast<size_t>(seg) * H + (H - 1)) * 64 + c];
+      }
+    part[grp][0][c] = t; part[grp][1][c] = r0; part[grp][2][c] = rl; part[grp][3][c] = c0; part[grp][4][c] = c1;
+  }
+  for (int i = tid; i < ap.A; i += 256) attr_s[i] = attributes[static_cast<size_t>(b) * ap.A + i];
+  __syncthreads();
+  if (tid < 64) {
+    const float T = ((part[0][0][c] + part[1][0][c]) + part[2][0][c]) + part[3][0][c];
+    const float R0 = part[0][1][c], RL = part[0][2][c];
+    const float C0 = ((part[0][3][c] + part[1][3][c]) + part[2][3][c]) + part[3][3][c];
+    const float CL = ((part[0][4][c] + part[1][4][c]) + part[2][4][c]) + part[3][4][c];
+    const float k00 = cf[c], k0w = cl[c];                                  // t[0][0], t[0][W-1]
+    const float kh0 = cf[static_cast<size_t>(H - 1) * 64 + c], khw = cl[static_cast<size_t>(H - 1) * 64 + c];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        // tap offset (oy,ox) = (dy-1,dx-1): oy=-1 never reads the last row, oy=+1 never the first row (same for x)
+        const float rowx = dy == 0 ? RL : (dy == 2 ? R0 : 0.f);
+        const float colx = dx == 0 ? CL : (dx == 2 ? C0 : 0.f);
+        float corner = 0.f;
+        if (dy == 0 && dx == 0) corner = khw;
+        if (dy == 0 && dx == 2) corner = kh0;
+        if (dy == 2 && dx == 0) corner = k0w;
+        if (dy == 2 && dx == 2) corner = k00;
+        S[dy * 3 + dx][c] = T - rowx - colx + corner;
+      }
+  }
+  __syncthreads();
+  {
+    // y[co] = b2[co] + (1/HW) * sum W2[co][:][tap] . S[tap][:]; 4 threads per output channel split the taps.
+    const int co = tid >> 2, part4 = tid & 3;
+    float acc = 0.f;
+    for (int tap = part4; tap < 9; tap += 4) {
+      const __nv_bfloat16* wr = w2 + (static_cast<size_t>(tap) * 64 + co) * 64;  // one swizzled 128-byte row
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(wr + ((ch ^ (co & 7)) << 3));
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h2[j]);
+          acc = fmaf(f.x, S[tap][ch * 8 + 2 * j], acc);
+          acc = fmaf(f.y, S[tap][ch * 8 + 2 * j + 1], acc);
+        }
+      }
+    }
+    tmp[tid] = acc;
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const float tot = ((tmp[4 * tid] + tmp[4 * tid + 1]) + tmp[4 * tid + 2]) + tmp[4 * tid + 3];
+    y_s[tid] = bias2[tid] + tot / (static_cast<float>(H) * static_cast<float>(W));
+  }
+  __syncthreads();
+  attn_vector(BlockGroup{}, ap.style, ap.w[0], 64, ap.R, ap.M, attr_s, y_s, s_s, tmp);
+  if (tid < 64) svec[static_cast<size_t>(b) * 64 + tid] = s_s[tid] * (sq != nullptr ? sq[static_cast<size_t>(b) * 64 + tid] : 1.f);
+}
+
 inline int ok_or_cuda() { return cudaGetLastError() == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA; }
 
 }  // namespace
@@ -365,6 +463,16 @@ int meta_attention(const float* meta, const float* w1, const float* b1, const fl
   dim3 grid(nblk, B);
   meta_attention_kernel<<<grid, C <= 256 ? C : 256, (M + Hid) * 4, s>>>(meta, w1, b1, w2, b2, out, B, M, Hid, C, relu,
                                                                        blk_enabled);
+  return ok_or_cuda();
+}
+
+int ca_from_stats(const float* pool_rows, const float* col_first, const float* col_last, const void* w2_packed,
+                  const float* bias2, const AttnParams& ap, const float* attributes, const float* sq, float* svec, int B,
+                  int H, int W, cudaStream_t s) {
+  if (B == 0) return DFIR_OK;
+  if (ap.C != 64 || ap.A > 512 || ap.M > 448 || ap.style == DFIR_STYLE_NONE) return DFIR_ERR_ARG;
+  ca_from_stats_kernel<<<B, 256, 0, s>>>(pool_rows, col_first, col_last, reinterpret_cast<const __nv_bfloat16*>(w2_packed),
+                                         bias2, ap, attributes, sq, svec, H, W, (W + 127) / 128);
   return ok_or_cuda();
 }
 

@@ -19,6 +19,8 @@ from ._lib import QrcanNet
 
 STYLES = {"standard": 1, "modulate": 2, "max_concat": 3, "softmax": 4, "mini_concat": 5, "extended_attention": 6}
 PRECISIONS = {"bf16": 0, "fp32": 1}
+# block-chain schedules of the bf16 path (csrc/api.cu): pool-by-linearity, fused-in, streamer
+SCHEDULES = {"linear": 0, "fused": 1, "streamer": 2}
 
 
 def _conv3(cin, cout):
@@ -140,7 +142,7 @@ class QRCAN(nn.Module):
     def __init__(self, n_resblocks=20, n_resgroups=10, n_feats=64, in_feats=3, out_feats=3, scale=4, reduction=16,
                  res_scale=1.0, style='modulate', num_metadata=1, include_pixel_attention=False,
                  selective_meta_blocks=None, num_q_layers_inner_residual=None, include_q_layer=False,
-                 precision='bf16', chunk_images=0, fuse_scale_residual=False, **kwargs):
+                 precision='bf16', chunk_images=0, schedule='linear', **kwargs):
         super().__init__()
         if precision not in PRECISIONS:
             raise RuntimeError("precision must be 'bf16' or 'fp32'")
@@ -148,7 +150,9 @@ class QRCAN(nn.Module):
         self.scale = scale
         self.precision = precision
         self.chunk_images = chunk_images
-        self.fuse_scale_residual = bool(fuse_scale_residual)
+        if schedule not in SCHEDULES:
+            raise RuntimeError("schedule must be one of %s" % sorted(SCHEDULES))
+        self.schedule = schedule
         self.cfg = dict(n_resblocks=n_resblocks, n_resgroups=n_resgroups, n_feats=n_feats, in_feats=in_feats,
                         out_feats=out_feats, scale=scale, reduction=reduction, num_metadata=num_metadata,
                         include_pixel_attention=include_pixel_attention)
@@ -188,7 +192,7 @@ class QRCAN(nn.Module):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def packed(self):
-        key = (self._param_versions(), self.precision, self.chunk_images, self.fuse_scale_residual)
+        key = (self._param_versions(), self.precision, self.chunk_images, self.schedule)
         if self._packed is None or self._packed.key != key:
             if self._packed is not None:
                 self._packed.close()
@@ -325,7 +329,7 @@ class PackedQrcan:
         d.num_metadata, d.attr_size, d.meta_hidden = M, self.attr_size, hid
         d.in_feats, d.out_feats = cfg["in_feats"], cfg["out_feats"]
         d.q_enabled, d.any_q, d.chunk_images = ptr(q_enabled), any_q, int(net.chunk_images)
-        d.fuse_scale_residual = int(net.fuse_scale_residual)
+        d.schedule = SCHEDULES[net.schedule]
         d.conv_w_bf16, d.tail_w_bf16 = ptr(conv_w_bf16), ptr(tail_w_bf16)
         d.conv_w_f32, d.up_w_f32, d.tail_w_f32, d.head_w_f32 = ptr(conv_w_f32), ptr(up_w_f32), ptr(tail_w_f32), ptr(head_w)
         d.conv_b, d.up_b, d.tail_b, d.head_b = ptr(conv_b), ptr(up_b), ptr(tail_b), ptr(head_b)

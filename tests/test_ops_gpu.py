@@ -147,6 +147,62 @@ def test_conv_tc_fused_scale_residual_input(shape, epi, style):
         assert G.max_norm_err(G.to_nchw(o32), ref) < 1e-4
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 128), (3, 5, 40), (1, 7, 200), (9, 2, 20), (2, 1, 1), (1, 1, 9), (1, 6, 1)])
+@pytest.mark.parametrize("style", ["standard", "max_concat", "extended_attention"])
+def test_pool_by_linearity_trio(shape, style):
+    """conv1+stats -> ca_from_stats -> conv2 with scale+skip epilogue == QRCAB.forward
+    (attention_manipulators/architectures.py:172-180) including degenerate 1-pixel-wide/high images."""
+    from deepfir_b200.qrcan import ChannelAttentionParams
+    B, H, W = shape
+    M = A = 10
+    torch.manual_seed(H * 31 + W)
+    g = torch.Generator().manual_seed(H * 31 + W)
+    x = torch.randn(B, 64, H, W, generator=g)
+    xin = G.bf16_round(x)
+    w1 = (torch.rand(64, 64, 3, 3, generator=g) - 0.5) / 12
+    w2 = (torch.rand(64, 64, 3, 3, generator=g) - 0.5) / 12
+    b1 = torch.rand(64, generator=g) - 0.5
+    b2 = torch.rand(64, generator=g) - 0.5
+    attr = torch.rand(B, A, generator=g)
+    sq = torch.rand(B, 64, generator=g)
+    ca = ChannelAttentionParams(64, style, 16, M)
+    sd = {"p." + k: v for k, v in ca.state_dict().items()}
+    blob = torch.cat([t.detach().reshape(-1) for t in ca.flat_params()]).cuda()
+    # oracle: the block exactly as the reference computes it (on bf16-rounded conv operands)
+    t = G.bf16_round(F.relu(_ref_conv(xin, w1, b1)))
+    r = _ref_conv(t, w2, b2)
+    sv = O.qca_vector(r, attr.reshape(B, A, 1, 1), sd, "p", style).reshape(B, 64) * sq
+    want = r * sv.reshape(B, 64, 1, 1) + x
+    nseg = (W + 127) // 128
+    x_bf, x32 = G.nhwc_bf16(xin), G.nhwc_f32(x)
+    w1p, w2p, b1d, b2d, attr_d, sq_d = G.pack_bf16(w1), G.pack_bf16(w2), b1.cuda(), b2.cuda(), attr.cuda(), sq.cuda()
+    t_d = torch.empty(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
+    pool = torch.full((B, nseg, H, 64), float("nan"), device="cuda")
+    cf = torch.full((B, H, 64), float("nan"), device="cuda")
+    cl = torch.full((B, H, 64), float("nan"), device="cuda")
+    svec = torch.full((B, 64), float("nan"), device="cuda")
+    out32 = torch.full((B, H, W, 64), float("nan"), device="cuda")
+    outbf = torch.empty(B, H, W, 64, device="cuda", dtype=torch.bfloat16)
+    L = G.lib()
+    assert L.dfir_conv3x3_c64_stats(x_bf.data_ptr(), w1p.data_ptr(), b1d.data_ptr(), B, H, W, t_d.data_ptr(),
+                                    pool.data_ptr(), cf.data_ptr(), cl.data_ptr(), G.stream()) == 0
+    assert L.dfir_ca_from_stats(pool.data_ptr(), cf.data_ptr(), cl.data_ptr(), w2p.data_ptr(), b2d.data_ptr(),
+                                STYLE_ID[style], blob.data_ptr(), 4, M, A, attr_d.data_ptr(), sq_d.data_ptr(),
+                                svec.data_ptr(), B, H, W, G.stream()) == 0
+    assert L.dfir_conv3x3_c64_scale_skip(t_d.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), B, H, W, svec.data_ptr(),
+                                         x32.data_ptr(), out32.data_ptr(), outbf.data_ptr(), G.stream()) == 0
+    G.sync()
+    assert torch.equal(G.to_nchw(t_d), t)                                  # conv1 output, bit exact after rounding
+    assert torch.allclose(svec.cpu(), sv, rtol=3e-4, atol=3e-6), (svec.cpu() - sv).abs().max()
+    assert G.max_norm_err(G.to_nchw(out32), want) < 2e-4
+    assert torch.equal(outbf.cpu(), out32.cpu().to(torch.bfloat16))
+    # group-conv use: no scale vector, in-place stream update
+    assert L.dfir_conv3x3_c64_scale_skip(t_d.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), B, H, W, None,
+                                         x32.data_ptr(), x32.data_ptr(), outbf.data_ptr(), G.stream()) == 0
+    G.sync()
+    assert G.max_norm_err(G.to_nchw(x32), r + x) < 1e-5
+
+
 @pytest.mark.parametrize("r", [2, 3])
 def test_conv_tc_pixel_shuffle_fold(r):
     """conv C -> r^2 C + PixelShuffle(r) (advanced/common.py:20-45) as r^2 strided-store launches."""

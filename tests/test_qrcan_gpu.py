@@ -74,12 +74,15 @@ def test_qrcan_bf16_full_depth_psnr_delta():
     assert max_norm_err(out, ref) <= 2.0 * pol_err + 1e-4
 
 
-@pytest.mark.parametrize("name", ["qrcan_standard_g2b2", "qrcan_extended_scale8", "qrcan_mini_concat"])
-def test_fused_schedule_matches_streamer_schedule(name):
-    """fuse_scale_residual=True (r*s+x folded into the next conv) computes the same network."""
+@pytest.mark.parametrize("name", ["qrcan_standard_g2b2", "qrcan_extended_scale8", "qrcan_mini_concat",
+                                  "qrcan_max_concat_scale3"])
+@pytest.mark.parametrize("schedule", ["fused", "streamer"])
+def test_alternative_schedules_compute_the_same_network(name, schedule):
+    """the three block-chain schedules (pool-by-linearity [default], fused-in, streamer) agree within the bf16
+    policy error."""
     ref, info = load_golden(name)
     net_a, x, meta = _build(info, "bf16")
-    net_b, _, _ = _build(info, "bf16", fuse_scale_residual=True)
+    net_b, _, _ = _build(info, "bf16", schedule=schedule)
     with torch.no_grad():
         a = net_a(x.cuda(), meta.cuda()).cpu()
         b = net_b(x.cuda(), meta.cuda()).cpu()
