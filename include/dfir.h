@@ -116,8 +116,10 @@ int dfir_conv3x3_c64_fused(const void* r_bf16, const float* x_in, float* x_out, 
  * dfir_ca_from_stats     : QCALayer (:105-125) on mean(conv2(t)) reconstructed from those sums, times the
  *   meta-attention scale sq (q_layer.py:39-43): svec[B][64].  w2_packed/bias2 = conv2's packed weights / bias.
  * dfir_conv3x3_c64_scale_skip : RCAB conv2 + `res * y` (twice) + `res += x` (:173-179), also the group / trunk
- *   tail conv with svec = NULL (:231-232, :312-313): out_f32 = (conv(in) + bias) * svec[b] + skip_f32 (NHWC fp32,
- *   may alias skip_f32, may be NULL), out_bf16 = bf16(out_f32) (dense NHWC). */
+ *   tail conv (:231-232, :312-313): out_f32 = (conv(in) + bias) * s[b] + skip_f32 (NHWC fp32, may alias skip_f32,
+ *   may be NULL), out_bf16 = bf16(out_f32) (dense NHWC).  The scale s is, in this order of precedence:
+ *   style != DFIR_STYLE_NONE -> evaluated INSIDE the kernel from pool_rows/col_first/col_last (what
+ *   dfir_ca_from_stats computes, times sq) while the pipeline fills; else svec[B][64] if not NULL; else 1. */
 int dfir_conv3x3_c64_stats(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
                            void* out_bf16, float* pool_rows, float* col_first, float* col_last, void* stream);
 int dfir_ca_from_stats(const float* pool_rows, const float* col_first, const float* col_last, const void* w2_packed,
@@ -125,7 +127,9 @@ int dfir_ca_from_stats(const float* pool_rows, const float* col_first, const flo
                        const float* attributes, const float* sq, float* svec, int B, int H, int W, void* stream);
 int dfir_conv3x3_c64_scale_skip(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
                                 const float* svec, const float* skip_f32, float* out_f32, void* out_bf16,
-                                void* stream);
+                                const float* pool_rows, const float* col_first, const float* col_last, int style,
+                                const float* ca_params, int R, int M, int A, const float* attributes,
+                                const float* sq, void* stream);
 
 /* default_conv on CUDA cores, fp32 NHWC in/out, any Cin % 4 == 0 and any Cout.
  *   w_packed from dfir_pack_conv3x3_f32; skip (optional) NHWC fp32 added after bias; relu applied last;

@@ -171,12 +171,13 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
       DFIR_TRY(conv3x3_c64_tc(c1, st));
       if (sched == 0) {
         const int w2 = g * per_group + 2 * b + 1;
-        DFIR_TRY(ca_from_stats(w.pool, w.colf, w.coll, cw + static_cast<size_t>(w2) * wbytes,
-                               n->conv_b + static_cast<size_t>(w2) * 64, make_ap(n, blk), attr_c, sq, w.svec, Bc, H, W, st));
-        // conv2 + attention scale + residual: x_{b+1} = (conv(t) + b) * s + x_b (fp32, in place after block 0)
+        // conv2 + attention scale + residual: x_{b+1} = (conv(t) + b) * s + x_b (fp32, in place after block 0);
+        // s is evaluated from the statistics of t inside the kernel while its pipeline fills.
         ConvTcDesc c2 = base(w2, EPI_SCALE_SKIP);
-        c2.in_bf16 = w.T; c2.svec = w.svec; c2.skip_f32 = b == 0 ? skip32 : w.XB; c2.out_f32 = w.XB;
-        c2.out_bf16 = w.XBbf;
+        c2.in_bf16 = w.T; c2.skip_f32 = b == 0 ? skip32 : w.XB; c2.out_f32 = w.XB; c2.out_bf16 = w.XBbf;
+        c2.col_first = w.colf; c2.col_last = w.coll;
+        c2.ca_style = n->style; c2.ca_R = n->reduced; c2.ca_M = n->num_metadata; c2.ca_A = n->attr_size;
+        c2.ca_params = n->ca_blob + static_cast<size_t>(blk) * n->ca_stride; c2.attributes = attr_c; c2.sq = sq;
         DFIR_TRY(conv3x3_c64_tc(c2, st));
         continue;
       }
@@ -412,7 +413,9 @@ int dfir_ca_from_stats(const float* pool_rows, const float* col_first, const flo
 
 int dfir_conv3x3_c64_scale_skip(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
                                 const float* svec, const float* skip_f32, float* out_f32, void* out_bf16,
-                                void* stream) {
+                                const float* pool_rows, const float* col_first, const float* col_last, int style,
+                                const float* ca_params, int R, int M, int A, const float* attributes,
+                                const float* sq, void* stream) {
   if (in_bf16 == nullptr || out_bf16 == nullptr || skip_f32 == nullptr) return DFIR_ERR_ARG;
   ConvTcDesc d{};
   d.B = B; d.H = H; d.W = W; d.cin_total = 64; d.cin_off = 0; d.cout = 64; d.epi = EPI_SCALE_SKIP; d.in_mode = IN_TMA;
@@ -420,6 +423,9 @@ int dfir_conv3x3_c64_scale_skip(const void* in_bf16, const void* wpacked, const 
   d.out_pix_stride = 128; d.out_row_stride = static_cast<long long>(W) * 128;
   d.out_img_stride = static_cast<long long>(H) * W * 128;
   d.svec = svec; d.skip_f32 = skip_f32; d.out_f32 = out_f32;
+  d.pool_rows = const_cast<float*>(pool_rows); d.col_first = const_cast<float*>(col_first);
+  d.col_last = const_cast<float*>(col_last);
+  d.ca_style = style; d.ca_params = ca_params; d.ca_R = R; d.ca_M = M; d.ca_A = A; d.attributes = attributes; d.sq = sq;
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess ||
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
@@ -475,7 +481,7 @@ long long dfir_qrcan_launch_count(const dfir_qrcan_net* net, int B, int H, int W
   const long long nb = net->n_blocks, ng = net->n_groups;
   long long per_chunk;
   if (precision == DFIR_PREC_BF16_TC) {
-    per_chunk = 1 + ng * (nb * (net->schedule == 1 ? 2 : 3) + 1) + 1 + static_cast<long long>(nup) * r * r + 1;
+    per_chunk = 1 + ng * (nb * (net->schedule == 2 ? 3 : 2) + 1) + 1 + static_cast<long long>(nup) * r * r + 1;
   } else {
     const long long pool = net->style != DFIR_STYLE_NONE ? 1 : 0;
     per_chunk = 1 + ng * (nb * (3 + pool) + 2) + 1 + nup + 1;  // group tail = conv + copy

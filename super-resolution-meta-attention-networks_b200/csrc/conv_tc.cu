@@ -440,6 +440,97 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       const int q = warp & 3;          // TMEM lane quarter this warp may read
       const int m = q * 32 + lane;     // pixel within the 128-px row segment
       const int et = threadIdx.x - 64; // 0..127
+      const int rows_img_e = nseg * H;
+      const int bimg_first = g0 / rows_img_e;
+      if constexpr (EPI == EPI_SCALE_SKIP) {
+        // ---- pool-by-linearity: while the pipeline fills, the epilogue warps turn the sums of
+        // t = relu(conv1(x)) left by the previous kernel into this block's attention vectors
+        //   mean(conv2(t))[co] = b[co] + (1/HW) sum_{tap,ci} W[co][ci][tap] * S[tap][ci]
+        // (W = this conv's weights, already on their way into shared memory), then QCALayer * meta scale.
+        if (a.ca_style != DFIR_STYLE_NONE) {
+          float* y_s = attn_s;
+          float* s_s = attn_s + 64;
+          float* attr_s = attn_s + 128;
+          float* tmp = attn_s + 128 + 512;  // 1024 floats
+          const NamedGroup grp{et, 128, 5};
+          const int bimg_last = (g1 - 1) / rows_img_e;
+          const int c = et & 63, half = et >> 6;
+          mbar_wait(wbar, 0, 9);  // conv weights have landed in smem (generic-proxy reads below)
+          for (int b = bimg_first; b <= bimg_last; ++b) {
+            const float* pr = a.pool_rows + static_cast<size_t>(b) * rows_img_e * 64;
+            const float* cf = a.col_first + static_cast<size_t>(b) * H * 64;
+            const float* cl = a.col_last + static_cast<size_t>(b) * H * 64;
+            float t = 0.f, c0 = 0.f, c1 = 0.f;
+#pragma unroll 8
+            for (int row = half; row < rows_img_e; row += 2) t += pr[static_cast<size_t>(row) * 64 + c];
+#pragma unroll 8
+            for (int yy = half; yy < H; yy += 2) {
+              c0 += cf[static_cast<size_t>(yy) * 64 + c];
+              c1 += cl[static_cast<size_t>(yy) * 64 + c];
+            }
+            tmp[half * 64 + c] = t;
+            tmp[128 + half * 64 + c] = c0;
+            tmp[256 + half * 64 + c] = c1;
+            for (int i = et; i < a.ca_A; i += 128) attr_s[i] = a.attributes[static_cast<size_t>(b) * a.ca_A + i];
+            grp.sync();
+            float* S = tmp + 384;  // [9][64]
+            if (et < 64) {
+              const float T = tmp[c] + tmp[64 + c];
+              const float C0 = tmp[128 + c] + tmp[192 + c], CL = tmp[256 + c] + tmp[320 + c];
+              float R0 = 0.f, RL = 0.f;
+              for (int sg = 0; sg < nseg; ++sg) {
+                R0 += pr[(static_cast<size_t>(sg) * H) * 64 + c];
+                RL += pr[(static_cast<size_t>(sg) * H + (H - 1)) * 64 + c];
+              }
+              const float k00 = cf[c], k0w = cl[c];
+              const float kh0 = cf[static_cast<size_t>(H - 1) * 64 + c], khw = cl[static_cast<size_t>(H - 1) * 64 + c];
+#pragma unroll
+              for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                  const float rowx = dy == 0 ? RL : (dy == 2 ? R0 : 0.f);
+                  const float colx = dx == 0 ? CL : (dx == 2 ? C0 : 0.f);
+                  float corner = 0.f;
+                  if (dy == 0 && dx == 0) corner = khw;
+                  if (dy == 0 && dx == 2) corner = kh0;
+                  if (dy == 2 && dx == 0) corner = k0w;
+                  if (dy == 2 && dx == 2) corner = k00;
+                  S[(dy * 3 + dx) * 64 + c] = T - rowx - colx + corner;
+                }
+            }
+            grp.sync();
+            {
+              // 2 threads per output channel split the taps; weights come from the swizzled smem tiles
+              const int co = et >> 1, part2 = et & 1;
+              float acc = 0.f;
+              for (int tap = part2; tap < 9; tap += 2) {
+                const uint8_t* wr = wsm + (tap * 64 + co) * 128;
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                  const uint4 raw = *reinterpret_cast<const uint4*>(wr + ((ch ^ (co & 7)) << 4));
+                  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = __bfloat1622float2(h2[j]);
+                    acc = fmaf(f.x, S[tap * 64 + ch * 8 + 2 * j], acc);
+                    acc = fmaf(f.y, S[tap * 64 + ch * 8 + 2 * j + 1], acc);
+                  }
+                }
+              }
+              tmp[et] = acc;  // tmp[0..127] (the T/C partials are dead by now)
+            }
+            grp.sync();
+            if (et < 64)
+              y_s[et] = bias_s[et] + (tmp[2 * et] + tmp[2 * et + 1]) / (static_cast<float>(H) * static_cast<float>(a.W));
+            grp.sync();
+            attn_vector(grp, a.ca_style, a.ca_params, 64, a.ca_R, a.ca_M, attr_s, y_s, s_s, tmp);
+            if (et < 64)
+              svec_s[(b - bimg_first) * 64 + et] =
+                  s_s[et] * (a.sq != nullptr ? a.sq[static_cast<size_t>(b) * 64 + et] : 1.f);
+            grp.sync();
+          }
+        }
+      }
       for (int g = g0, it = 0; g < g1; ++g, ++it) {
         const int col = g / H;
         const int y = g % H;
@@ -449,6 +540,30 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         const bool valid = x < a.W;
         const int acc = it % kAcc;
         if (probe) g_dfir_progress[8 + q] = it + 1;
+        // EPI_SCALE_SKIP: the fp32 skip values of this row are fetched (coalesced, 16 x 16 B per thread) BEFORE
+        // waiting for the accumulator, so their latency hides behind the MMAs of the row.
+        float4 skv[EPI == EPI_SCALE_SKIP ? 16 : 1];
+        if constexpr (EPI == EPI_SCALE_SKIP) {
+          if (g + 2 < g1) {  // pull the skip row needed two iterations from now into L2 (2 x 128 B lines per thread)
+            const int g2 = g + 2, col2 = g2 / H;
+            const size_t e2 = ((static_cast<size_t>(col2 / nseg) * a.H + (g2 % H)) * a.W + (col2 % nseg) * 128) * 64;
+            const int npx2 = min(128, a.W - (col2 % nseg) * 128);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const int line = k * 128 + et;  // 256 lines of 128 B = one 128-px fp32 row
+              if (line * 32 < npx2 * 64)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.skip_f32 + e2 + static_cast<size_t>(line) * 32));
+            }
+          }
+          const int npx = min(128, a.W - seg * 128);
+          const size_t row_e = ((static_cast<size_t>(b) * a.H + y) * a.W + seg * 128) * 64;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int idx = i * 128 + et;
+            skv[i] = (idx >> 4) < npx ? *reinterpret_cast<const float4*>(a.skip_f32 + row_e + static_cast<size_t>(idx) * 4)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         mbar_wait(&tfull[acc], (it / kAcc) & 1, 8);
         tcgen05_fence_after();
         if (exp_no_epi) {
@@ -477,7 +592,8 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           // v = (acc + bias) * s[b][c]; fp32 tile in smem (chunk-rotated: conflict free), then a coalesced pass
           // adds the fp32 skip and writes the fp32 stream + its bf16 copy straight to global memory.
           float* tile = reinterpret_cast<float*>(stage);  // [128 px][64] fp32 = 32 KB = both staging buffers
-          const float* sv = a.svec != nullptr ? a.svec + static_cast<size_t>(b) * 64 : nullptr;
+          const float* sv = a.ca_style != DFIR_STYLE_NONE ? svec_s + (b - bimg_first) * 64
+                                                          : (a.svec != nullptr ? a.svec + static_cast<size_t>(b) * 64 : nullptr);
           named_bar_sync(1, 128);  // previous row's coalesced pass has finished reading the tile
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -509,14 +625,14 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           {
             const int npx = min(128, a.W - seg * 128);  // valid pixels of this row segment
             const size_t row_e = ((static_cast<size_t>(b) * a.H + y) * a.W + seg * 128) * 64;
-#pragma unroll 4
+#pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int idx = i * 128 + et;  // float4 index inside the tile: pixel = idx / 16, chunk = idx % 16
               const int p = idx >> 4, c4 = idx & 15;
               if (p < npx) {
                 float4 o = reinterpret_cast<const float4*>(tile + p * 64)[(c4 + p) & 15];
                 const size_t e = row_e + static_cast<size_t>(p) * 64 + c4 * 4;
-                const float4 sk = *reinterpret_cast<const float4*>(a.skip_f32 + e);
+                const float4 sk = skv[i];
                 o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
                 if (a.out_f32 != nullptr) *reinterpret_cast<float4*>(a.out_f32 + e) = o;
                 uint2 pk;
@@ -713,6 +829,10 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   if (d.epi == EPI_SCALE_SKIP && (d.skip_f32 == nullptr || d.out_bf16 == nullptr || d.out_pix_stride != 128 ||
                                   d.out_row_stride != static_cast<long long>(d.W) * 128))
     return DFIR_ERR_ARG;  // the direct-store epilogue writes dense NHWC
+  if (d.epi == EPI_SCALE_SKIP && d.ca_style != DFIR_STYLE_NONE &&
+      (d.pool_rows == nullptr || d.col_first == nullptr || d.col_last == nullptr || d.ca_params == nullptr ||
+       d.ca_A > 512 || d.ca_M > 448 || (d.ca_A > 0 && d.attributes == nullptr)))
+    return DFIR_ERR_ARG;
   if (d.epi == EPI_RELU_STATS && (d.pool_rows == nullptr || d.col_first == nullptr || d.col_last == nullptr))
     return DFIR_ERR_ARG;
   CUtensorMap tin, tout;
@@ -765,7 +885,9 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   if (const char* e = getenv("DFIR_NUM_SMS")) grid = atoi(e) > 0 ? atoi(e) : grid;  // debugging aid
   if (G < grid) grid = static_cast<int>(G);
   // IN_FUSED keeps the attention vectors of every image a band touches in shared memory
-  if (fused && (G + grid - 1) / grid > static_cast<long long>(kMaxBandImages - 1) * a.nseg * d.H) return DFIR_ERR_ARG;
+  if ((fused || (d.epi == EPI_SCALE_SKIP && d.ca_style != DFIR_STYLE_NONE)) &&
+      (G + grid - 1) / grid > static_cast<long long>(kMaxBandImages - 1) * a.nseg * d.H)
+    return DFIR_ERR_ARG;
   if (fused) {
     switch (d.epi) {
       case EPI_BIAS_RELU: return launch_one<64, EPI_BIAS_RELU, IN_FUSED>(tin, tout, a, grid, stream);
