@@ -146,10 +146,11 @@ int dfir_head_conv(const float* x_nchw, const float* w_packed, const float* bias
 /* ParaCALayer.attribute_integrator for nblk layers at once (attention_manipulators/q_layer.py:21-41):
  *   out[blk][b][:] = sigmoid(W2[blk] * act(W1[blk] * meta[b] + b1[blk]) + b2[blk]), act = ReLU if relu else id.
  *   meta fp32 [B][M]; w1 [nblk][Hid][M]; b1 [nblk][Hid]; w2 [nblk][C][Hid]; b2 [nblk][C]; out [nblk][B][C].
- *   blk_enabled (optional, int32 [nblk]): 0 -> the layer is absent and out = 1. */
+ *   blk_enabled (optional, int32 [nblk]): 0 -> the layer is absent and out = 1.  out_scale multiplies every
+ *   output (ParamResBlock's res_scale folded into the meta scale; 1 otherwise). */
 int dfir_meta_attention(const float* meta, const float* w1, const float* b1, const float* w2, const float* b2,
                         float* out, int nblk, int B, int M, int Hid, int C, int relu, const int* blk_enabled,
-                        void* stream);
+                        float out_scale, void* stream);
 
 /* Channel attention + meta-attention scale + residual add of one block:
  *   QCALayer.forward + ParaCALayer `x*y` + `res += x` (attention_manipulators/architectures.py:105-127,172-180;
@@ -172,9 +173,10 @@ int dfir_pool_rows_f32(const float* in, float* pool_rows, int B, int H, int W, i
  * whole-network forward
  * ---------------------------------------------------------------------------------------------- */
 
-/* Packed parameters + structure of a Q-RCAN (attention_manipulators/architectures.py:246-316).
- * Conv indexing of the trunk arrays: block (g,b) conv j -> g*(2*n_blocks+1) + 2*b + j; group tail conv ->
- * g*(2*n_blocks+1) + 2*n_blocks; trunk tail conv (final_body) -> n_groups*(2*n_blocks+1);
+/* Packed parameters + structure of a Q-RCAN (attention_manipulators/architectures.py:246-316) or, with
+ * style = DFIR_STYLE_NONE, n_groups = 1 and no_group_conv = 1, of a Q-EDSR (:359-399: ParamResBlock chain).
+ * Conv indexing of the trunk arrays (P = 2*n_blocks + 1, or 2*n_blocks when no_group_conv): block (g,b) conv j
+ * -> g*P + 2*b + j; group tail conv -> g*P + 2*n_blocks; trunk tail conv (final_body) -> n_groups*P;
  * then the upsampler slices: stage t, sub-pixel s -> n_trunk + t*r*r + s.                                  */
 typedef struct dfir_qrcan_net {
   int n_groups, n_blocks, n_feats; /* n_feats must be 64 */
@@ -189,6 +191,9 @@ typedef struct dfir_qrcan_net {
   int any_q;                        /* host-side: any block has a q_node */
   int chunk_images;                 /* images per L2-resident pass; 0 = choose automatically */
   int schedule;                     /* block chain: 0 pool-by-linearity (default), 1 fused-in, 2 streamer */
+  int no_group_conv;                /* 1: groups have no tail conv / group skip (Q-EDSR: one flat chain of blocks) */
+  int meta_relu;                    /* ReLU between the two FC layers of the meta-attention MLP (q_layer.py:33-34) */
+  float res_scale;                  /* ParamResBlock res_scale (style NONE only; QRCAB ignores it) */
   /* tensor-core weights */
   const void* conv_w_bf16;          /* [n_conv][9*64*128 B] */
   const void* tail_w_bf16;          /* [9*16*128 B] */

@@ -10,7 +10,7 @@ import torch
 from torch import nn
 
 from SISR.models.attention_manipulators import QModel
-from deepfir_b200.qrcan import QRCAN
+from deepfir_b200.qrcan import QEDSR, QRCAN
 
 
 class QRCANHandler(QModel):
@@ -55,13 +55,22 @@ def _pending(name):
 
 
 class QEDSRHandler(QModel):
-    """Meta-attention EDSR (ref :57-76)."""
+    """Meta-attention EDSR (ref :57-76): ParamResBlock chain, every block scaled by its meta-attention vector."""
 
     def __init__(self, device, model_save_dir, eval_mode=False, lr=1e-4, scale=4, in_features=3, num_blocks=16,
                  num_features=64, res_scale=0.1, scheduler=None, scheduler_params=None, perceptual=None, **kwargs):
         super(QEDSRHandler, self).__init__(device=device, model_save_dir=model_save_dir, eval_mode=eval_mode,
                                            **kwargs)
-        _pending('qedsr')
+        if num_features != 64:  # the tensor-core kernels are specialised for 64 channels; wider nets run fp32
+            kwargs.setdefault('precision', 'fp32')
+        self.net = QEDSR(scale=scale, in_features=in_features, num_features=num_features, num_blocks=num_blocks,
+                         res_scale=res_scale, input_para=self.num_metadata, **kwargs)
+        self.colorspace = 'augmented_rgb'
+        self.im_input = 'unmodified'
+        self.activate_device()
+        self.model_name = 'qedsr'
+        self.criterion = nn.L1Loss()
+        self.training_setup(lr, scheduler, scheduler_params, perceptual, device)
 
 
 class QSANHandler(QModel):

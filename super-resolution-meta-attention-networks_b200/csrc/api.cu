@@ -112,8 +112,9 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
                        int H, int W, const QrcanWs& w, int num_sms, cudaStream_t st) {
   const int C = 64;
   const int nb = n->n_blocks, ng = n->n_groups;
-  const int per_group = 2 * nb + 1;
+  const int per_group = 2 * nb + (n->no_group_conv ? 0 : 1);
   const int n_trunk = ng * per_group + 1;
+  const bool has_ca = n->style != DFIR_STYLE_NONE;
   const size_t wbytes = 9 * 64 * 128;
   const uint8_t* cw = reinterpret_cast<const uint8_t*>(n->conv_w_bf16);
   const long long pixB = C * 2, rowB = static_cast<long long>(W) * C * 2, imgB = rowB * H;
@@ -157,7 +158,7 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
       const int blk = g * nb + b;
       const float* sq = n->any_q ? w.sq + (static_cast<size_t>(blk) * B + b0) * C : nullptr;
       // conv1: t = relu(conv(x_b))
-      ConvTcDesc c1 = base(g * per_group + 2 * b, sched == 0 ? EPI_RELU_STATS : EPI_BIAS_RELU);
+      ConvTcDesc c1 = base(g * per_group + 2 * b, (sched == 0 && has_ca) ? EPI_RELU_STATS : EPI_BIAS_RELU);
       c1.out_bf16 = w.T; c1.col_first = w.colf; c1.col_last = w.coll;
       if (b == 0) {
         c1.in_bf16 = gin;
@@ -175,14 +176,18 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
         // s is evaluated from the statistics of t inside the kernel while its pipeline fills.
         ConvTcDesc c2 = base(w2, EPI_SCALE_SKIP);
         c2.in_bf16 = w.T; c2.skip_f32 = b == 0 ? skip32 : w.XB; c2.out_f32 = w.XB; c2.out_bf16 = w.XBbf;
-        c2.col_first = w.colf; c2.col_last = w.coll;
-        c2.ca_style = n->style; c2.ca_R = n->reduced; c2.ca_M = n->num_metadata; c2.ca_A = n->attr_size;
-        c2.ca_params = n->ca_blob + static_cast<size_t>(blk) * n->ca_stride; c2.attributes = attr_c; c2.sq = sq;
+        if (has_ca) {
+          c2.col_first = w.colf; c2.col_last = w.coll; c2.epi_stats = 1;
+          c2.ca_style = n->style; c2.ca_R = n->reduced; c2.ca_M = n->num_metadata; c2.ca_A = n->attr_size;
+          c2.ca_params = n->ca_blob + static_cast<size_t>(blk) * n->ca_stride; c2.attributes = attr_c; c2.sq = sq;
+        } else {
+          c2.svec = sq;  // ParamResBlock: s = res_scale * meta scale (meta_attention already folded res_scale in)
+        }
         DFIR_TRY(conv3x3_c64_tc(c2, st));
         continue;
       }
       // conv2: r = conv(t) + per-row pooled sums (the avg-pool of the channel attention)
-      ConvTcDesc c2 = base(g * per_group + 2 * b + 1, EPI_BIAS_POOL);
+      ConvTcDesc c2 = base(g * per_group + 2 * b + 1, has_ca ? EPI_BIAS_POOL : EPI_BIAS);
       c2.in_bf16 = w.T; c2.out_bf16 = w.R;
       DFIR_TRY(conv3x3_c64_tc(c2, st));
       if (sched == 2) {
@@ -191,6 +196,7 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
                                 w.XB, w.XBbf, Bc, H, W, C, st));
       }
     }
+    if (n->no_group_conv) continue;  // Q-EDSR: the chain of blocks runs straight into the trunk tail conv
     // group tail conv + `res += x` (group input)
     ConvTcDesc ct = base(g * per_group + 2 * nb, EPI_SCALE_SKIP);
     ct.out_bf16 = w.XAbf; ct.skip_f32 = skip32; ct.out_f32 = w.XA; ct.svec = nullptr;
@@ -205,7 +211,7 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
   }
   {
     ConvTcDesc cf = base(ng * per_group, EPI_SCALE_SKIP);
-    cf.in_bf16 = ng == 0 ? w.Hbf : w.XAbf;
+    cf.in_bf16 = (ng == 0 || (n->no_group_conv && nb == 0)) ? w.Hbf : (n->no_group_conv ? w.XBbf : w.XAbf);
     cf.out_bf16 = w.XBbf; cf.skip_f32 = w.Hh; cf.out_f32 = nullptr;
     DFIR_TRY(conv3x3_c64_tc(cf, st));
   }
@@ -249,7 +255,7 @@ int qrcan_forward_f32(const dfir_qrcan_net* n, const float* x, const float* attr
                       int H, int W, const QrcanWs& w, cudaStream_t st) {
   const int C = n->n_feats;
   const int nb = n->n_blocks, ng = n->n_groups;
-  const int per_group = 2 * nb + 1;
+  const int per_group = 2 * nb + (n->no_group_conv ? 0 : 1);
   const size_t wsz = static_cast<size_t>(9) * C * C;
   DFIR_TRY(head_conv(x + static_cast<size_t>(b0) * n->in_feats * H * W, n->head_w_f32, n->head_b, w.Hh, nullptr, Bc,
                      n->in_feats, H, W, C, st));
@@ -269,6 +275,7 @@ int qrcan_forward_f32(const dfir_qrcan_net* n, const float* x, const float* attr
       DFIR_TRY(scale_residual(w.R32, 0, cin, w.pool, H, make_ap(n, blk), attr + static_cast<size_t>(b0) * n->attr_size,
                               sq, 1.f, w.XB, nullptr, Bc, H, W, C, st));
     }
+    if (n->no_group_conv) continue;
     const float* cin = nb == 0 ? skip32 : w.XB;
     // out = conv(cin) + skip32 ; written to T32 first because XA may be the skip being read
     DFIR_TRY(conv(cin, g * per_group + 2 * nb, 0, skip32, w.T32));
@@ -277,10 +284,14 @@ int qrcan_forward_f32(const dfir_qrcan_net* n, const float* x, const float* attr
                  ? DFIR_OK
                  : DFIR_ERR_CUDA);
   }
-  DFIR_TRY(conv(ng == 0 ? w.Hh : w.XA, ng * per_group, 0, w.Hh, w.XB));
+  {
+    const float* fin = (ng == 0 || (n->no_group_conv && nb == 0)) ? w.Hh : (n->no_group_conv ? w.XB : w.XA);
+    // XB may be the operand: write the trunk tail output to R32, which the upsampler then reads
+    DFIR_TRY(conv(fin, ng * per_group, 0, w.Hh, w.R32));
+  }
   int r = 0;
   const int nup = up_stages(n->scale, &r);
-  const float* cur = w.XB;
+  const float* cur = w.R32;
   int h = H, wd = W;
   size_t woff = 0, boff = 0;
   for (int t = 0; t < nup; ++t) {
@@ -426,6 +437,7 @@ int dfir_conv3x3_c64_scale_skip(const void* in_bf16, const void* wpacked, const 
   d.pool_rows = const_cast<float*>(pool_rows); d.col_first = const_cast<float*>(col_first);
   d.col_last = const_cast<float*>(col_last);
   d.ca_style = style; d.ca_params = ca_params; d.ca_R = R; d.ca_M = M; d.ca_A = A; d.attributes = attributes; d.sq = sq;
+  d.epi_stats = style != DFIR_STYLE_NONE ? 1 : 0;
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess ||
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
@@ -447,8 +459,8 @@ int dfir_head_conv(const float* x_nchw, const float* w_packed, const float* bias
 
 int dfir_meta_attention(const float* meta, const float* w1, const float* b1, const float* w2, const float* b2,
                         float* out, int nblk, int B, int M, int Hid, int C, int relu, const int* blk_enabled,
-                        void* stream) {
-  return meta_attention(meta, w1, b1, w2, b2, out, nblk, B, M, Hid, C, relu, blk_enabled, S(stream));
+                        float out_scale, void* stream) {
+  return meta_attention(meta, w1, b1, w2, b2, out, nblk, B, M, Hid, C, relu, blk_enabled, out_scale, S(stream));
 }
 
 int dfir_ca_scale_residual(const void* r, int r_is_bf16, const float* x_in, const float* pool_rows, int pool_nrows,
@@ -481,10 +493,11 @@ long long dfir_qrcan_launch_count(const dfir_qrcan_net* net, int B, int H, int W
   const long long nb = net->n_blocks, ng = net->n_groups;
   long long per_chunk;
   if (precision == DFIR_PREC_BF16_TC) {
-    per_chunk = 1 + ng * (nb * (net->schedule == 2 ? 3 : 2) + 1) + 1 + static_cast<long long>(nup) * r * r + 1;
+    per_chunk = 1 + ng * (nb * (net->schedule == 2 ? 3 : 2) + (net->no_group_conv ? 0 : 1)) + 1 +
+                static_cast<long long>(nup) * r * r + 1;
   } else {
     const long long pool = net->style != DFIR_STYLE_NONE ? 1 : 0;
-    per_chunk = 1 + ng * (nb * (3 + pool) + 2) + 1 + nup + 1;  // group tail = conv + copy
+    per_chunk = 1 + ng * (nb * (3 + pool) + (net->no_group_conv ? 0 : 2)) + 1 + nup + 1;  // group tail = conv + copy
   }
   return chunks * per_chunk + (net->any_q ? 1 : 0);
 }
@@ -509,8 +522,8 @@ int dfir_qrcan_forward(const dfir_qrcan_net* net, const float* x_nchw, const flo
     return DFIR_ERR_CUDA;
   if (net->any_q) {
     DFIR_TRY(meta_attention(attributes, net->meta_w1, net->meta_b1, net->meta_w2, net->meta_b2, w.sq,
-                            net->n_groups * net->n_blocks, B, net->num_metadata, net->meta_hidden, net->n_feats, 1,
-                            net->q_enabled, st));
+                            net->n_groups * net->n_blocks, B, net->num_metadata, net->meta_hidden, net->n_feats,
+                            net->meta_relu, net->q_enabled, net->style == DFIR_STYLE_NONE ? net->res_scale : 1.f, st));
   }
   for (int b0 = 0; b0 < B; b0 += Bc) {
     const int bc = std::min(Bc, B - b0);

@@ -447,7 +447,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         // t = relu(conv1(x)) left by the previous kernel into this block's attention vectors
         //   mean(conv2(t))[co] = b[co] + (1/HW) sum_{tap,ci} W[co][ci][tap] * S[tap][ci]
         // (W = this conv's weights, already on their way into shared memory), then QCALayer * meta scale.
-        if (a.ca_style != DFIR_STYLE_NONE) {
+        if (a.epi_stats) {
           float* y_s = attn_s;
           float* s_s = attn_s + 64;
           float* attr_s = attn_s + 128;
@@ -592,7 +592,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           // v = (acc + bias) * s[b][c]; fp32 tile in smem (chunk-rotated: conflict free), then a coalesced pass
           // adds the fp32 skip and writes the fp32 stream + its bf16 copy straight to global memory.
           float* tile = reinterpret_cast<float*>(stage);  // [128 px][64] fp32 = 32 KB = both staging buffers
-          const float* sv = a.ca_style != DFIR_STYLE_NONE ? svec_s + (b - bimg_first) * 64
+          const float* sv = a.epi_stats ? svec_s + (b - bimg_first) * 64
                                                           : (a.svec != nullptr ? a.svec + static_cast<size_t>(b) * 64 : nullptr);
           named_bar_sync(1, 128);  // previous row's coalesced pass has finished reading the tile
 #pragma unroll
@@ -829,8 +829,8 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   if (d.epi == EPI_SCALE_SKIP && (d.skip_f32 == nullptr || d.out_bf16 == nullptr || d.out_pix_stride != 128 ||
                                   d.out_row_stride != static_cast<long long>(d.W) * 128))
     return DFIR_ERR_ARG;  // the direct-store epilogue writes dense NHWC
-  if (d.epi == EPI_SCALE_SKIP && d.ca_style != DFIR_STYLE_NONE &&
-      (d.pool_rows == nullptr || d.col_first == nullptr || d.col_last == nullptr || d.ca_params == nullptr ||
+  if (d.epi == EPI_SCALE_SKIP && d.epi_stats &&
+      (fused || d.ca_style == DFIR_STYLE_NONE || d.pool_rows == nullptr || d.col_first == nullptr || d.col_last == nullptr || d.ca_params == nullptr ||
        d.ca_A > 512 || d.ca_M > 448 || (d.ca_A > 0 && d.attributes == nullptr)))
     return DFIR_ERR_ARG;
   if (d.epi == EPI_RELU_STATS && (d.pool_rows == nullptr || d.col_first == nullptr || d.col_last == nullptr))
@@ -872,6 +872,7 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   a.xin_f32 = d.xin_f32;
   a.xout_f32 = d.xout_f32;
   a.res_scale = d.res_scale;
+  a.epi_stats = d.epi_stats;
   a.debug_probe = getenv("DFIR_DEBUG_PROBE") != nullptr ? atoi(getenv("DFIR_DEBUG_PROBE")) : 0;
   a.ca_params = d.ca_params;
   a.attributes = d.attributes;
@@ -885,7 +886,7 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   if (const char* e = getenv("DFIR_NUM_SMS")) grid = atoi(e) > 0 ? atoi(e) : grid;  // debugging aid
   if (G < grid) grid = static_cast<int>(G);
   // IN_FUSED keeps the attention vectors of every image a band touches in shared memory
-  if ((fused || (d.epi == EPI_SCALE_SKIP && d.ca_style != DFIR_STYLE_NONE)) &&
+  if ((fused || (d.epi == EPI_SCALE_SKIP && d.epi_stats)) &&
       (G + grid - 1) / grid > static_cast<long long>(kMaxBandImages - 1) * a.nseg * d.H)
     return DFIR_ERR_ARG;
   if (fused) {

@@ -45,6 +45,7 @@ struct ConvTcArgs {  // kernel argument block
   const float* sq;
   float res_scale;
   int ca_style, ca_R, ca_M, ca_A;
+  int epi_stats;            // EPI_SCALE_SKIP: evaluate the attention vector from the statistics of t in-kernel
   int debug_probe;
 };
 
@@ -74,6 +75,7 @@ struct ConvTcDesc {  // host-side launch description
   const float* sq;
   float res_scale;
   int ca_style, ca_R, ca_M, ca_A;
+  int epi_stats;
 };
 
 int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream);
@@ -95,7 +97,8 @@ int conv3x3_f32(const float* in, const float* w_packed, const float* bias, const
                 int W, int Cin, int Cout, int relu, int ps_r, int out_nchw, cudaStream_t s);
 int pool_rows_f32(const float* in, float* pool_rows, int B, int H, int W, int C, cudaStream_t s);
 int meta_attention(const float* meta, const float* w1, const float* b1, const float* w2, const float* b2, float* out,
-                   int nblk, int B, int M, int Hid, int C, int relu, const int* blk_enabled, cudaStream_t s);
+                   int nblk, int B, int M, int Hid, int C, int relu, const int* blk_enabled, float out_scale,
+                   cudaStream_t s);
 int scale_residual(const void* r, int r_is_bf16, const float* x_in, const float* pool_rows, int pool_nrows,
                    const AttnParams& ap, const float* attributes, const float* sq, float res_scale, float* x_out,
                    __nv_bfloat16* x_out_bf16, int B, int H, int W, int C, cudaStream_t s);

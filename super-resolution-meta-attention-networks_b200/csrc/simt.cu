@@ -196,7 +196,7 @@ __global__ void pool_rows_f32_kernel(const float* __restrict__ in, float* __rest
 __global__ void meta_attention_kernel(const float* __restrict__ meta, const float* __restrict__ w1,
                                       const float* __restrict__ b1, const float* __restrict__ w2,
                                       const float* __restrict__ b2, float* __restrict__ out, int B, int M, int Hid,
-                                      int C, int relu, const int* __restrict__ blk_enabled) {
+                                      int C, int relu, const int* __restrict__ blk_enabled, float out_scale) {
   extern __shared__ float sh[];  // [M] meta, [Hid] hidden
   float* m_s = sh;
   float* h_s = sh + M;
@@ -204,7 +204,7 @@ __global__ void meta_attention_kernel(const float* __restrict__ meta, const floa
   const int b = blockIdx.y;
   float* o = out + (static_cast<size_t>(blk) * B + b) * C;
   if (blk_enabled != nullptr && blk_enabled[blk] == 0) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) o[c] = 1.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) o[c] = out_scale;
     return;
   }
   for (int i = threadIdx.x; i < M; i += blockDim.x) m_s[i] = meta[static_cast<size_t>(b) * M + i];
@@ -220,7 +220,7 @@ __global__ void meta_attention_kernel(const float* __restrict__ meta, const floa
     const float* wr = w2 + (static_cast<size_t>(blk) * C + c) * Hid;
     float s = b2[static_cast<size_t>(blk) * C + c];
     for (int h = 0; h < Hid; ++h) s = fmaf(wr[h], h_s[h], s);
-    o[c] = 1.f / (1.f + expf(-s));
+    o[c] = out_scale / (1.f + expf(-s));
   }
 }
 
@@ -457,12 +457,13 @@ int pool_rows_f32(const float* in, float* pool_rows, int B, int H, int W, int C,
 }
 
 int meta_attention(const float* meta, const float* w1, const float* b1, const float* w2, const float* b2, float* out,
-                   int nblk, int B, int M, int Hid, int C, int relu, const int* blk_enabled, cudaStream_t s) {
+                   int nblk, int B, int M, int Hid, int C, int relu, const int* blk_enabled, float out_scale,
+                   cudaStream_t s) {
   if (nblk == 0 || B == 0) return DFIR_OK;
   if ((M + Hid) * 4 > 48 * 1024) return DFIR_ERR_ARG;
   dim3 grid(nblk, B);
   meta_attention_kernel<<<grid, C <= 256 ? C : 256, (M + Hid) * 4, s>>>(meta, w1, b1, w2, b2, out, B, M, Hid, C, relu,
-                                                                       blk_enabled);
+                                                                       blk_enabled, out_scale);
   return ok_or_cuda();
 }
 

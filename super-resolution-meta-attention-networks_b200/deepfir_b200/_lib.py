@@ -36,7 +36,7 @@ class QrcanNet(C.Structure):
         ("num_metadata", C.c_int), ("attr_size", C.c_int), ("meta_hidden", C.c_int),
         ("in_feats", C.c_int), ("out_feats", C.c_int),
         ("q_enabled", C.c_void_p), ("any_q", C.c_int), ("chunk_images", C.c_int),
-        ("schedule", C.c_int),
+        ("schedule", C.c_int), ("no_group_conv", C.c_int), ("meta_relu", C.c_int), ("res_scale", C.c_float),
         ("conv_w_bf16", C.c_void_p), ("tail_w_bf16", C.c_void_p),
         ("conv_w_f32", C.c_void_p), ("up_w_f32", C.c_void_p), ("tail_w_f32", C.c_void_p),
         ("head_w_f32", C.c_void_p),
@@ -65,7 +65,7 @@ PROTOTYPES = {
                                          _i, _vp, _vp, _vp]),
     "dfir_conv3x3_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dfir_head_conv": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "dfir_meta_attention": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "dfir_meta_attention": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _f, _vp]),
     "dfir_ca_scale_residual": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp,
                                     _i, _i, _i, _vp]),
     "dfir_pool_rows_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

@@ -17,7 +17,7 @@ from torch import nn
 from . import _lib
 from ._lib import QrcanNet
 
-STYLES = {"standard": 1, "modulate": 2, "max_concat": 3, "softmax": 4, "mini_concat": 5, "extended_attention": 6}
+STYLES = {"none": 0, "standard": 1, "modulate": 2, "max_concat": 3, "softmax": 4, "mini_concat": 5, "extended_attention": 6}
 PRECISIONS = {"bf16": 0, "fp32": 1}
 # block-chain schedules of the bf16 path (csrc/api.cu): pool-by-linearity, fused-in, streamer
 SCHEDULES = {"linear": 0, "fused": 1, "streamer": 2}
@@ -172,8 +172,9 @@ class QRCAN(nn.Module):
     # ------------------------------------------------------------------ forward
     def forward(self, x, metadata):
         if not x.is_cuda:
-            raise RuntimeError("deepfir_b200.QRCAN runs on a CUDA (sm_100a) device only: there is no CPU path")
-        if self.cfg["include_pixel_attention"]:
+            raise RuntimeError("deepfir_b200.%s runs on a CUDA (sm_100a) device only: there is no CPU path"
+                               % type(self).__name__)
+        if self.cfg.get("include_pixel_attention"):
             raise NotImplementedError("pixel attention (include_pixel_attention) is not on the B200 path yet")
         from . import ops  # registers torch.ops.dfir.*
         packed = self.packed()
@@ -188,6 +189,24 @@ class QRCAN(nn.Module):
         raise NotImplementedError("forensic analysis is outside the B200 hot path")
 
     # ------------------------------------------------------------------ packing
+    def _pack_spec(self):
+        cfg = self.cfg
+        ng, nb, C_, M = cfg["n_resgroups"], cfg["n_resblocks"], cfg["n_feats"], cfg["num_metadata"]
+        trunk = []
+        for g in range(ng):
+            grp = self.body[g]
+            for b in range(nb):
+                trunk += [grp.body[b].body[0], grp.body[b].body[2]]
+            trunk.append(grp.final_body)
+        trunk.append(self.final_body)
+        blocks = [self.body[g].body[b] for g in range(ng) for b in range(nb)]
+        return dict(
+            cfg=dict(cfg, style=self.style, no_group_conv=0, meta_relu=1, res_scale=1.0,
+                     meta_hidden=(C_ // 2 if M <= 15 else (C_ - M) // 2 + M)),
+            head=self.head[0], trunk=trunk, ups=[m for m in self.tail[0] if isinstance(m, nn.Conv2d)],
+            tail=self.tail[1], ca=[blk.final_body.flat_params() for blk in blocks],
+            meta=[tuple(blk.q_node.fcs()) if blk.q_layer else None for blk in blocks])
+
     def _param_versions(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
@@ -204,6 +223,56 @@ class QRCAN(nn.Module):
         return super()._apply(fn, *a, **k)
 
 
+class QEDSRBlockParams(nn.Module):
+    """ParamResBlock (architectures.py:332-356): conv-ReLU-conv, * res_scale, * meta-attention, += x."""
+
+    def __init__(self, n_feats, n_params, q_layer_nonlinearity):
+        super().__init__()
+        self.body = nn.Sequential(_conv3(n_feats, n_feats), nn.ReLU(True), _conv3(n_feats, n_feats))
+        self.attention_layer = MetaAttentionParams(n_feats, n_params, nonlinearity=q_layer_nonlinearity)
+
+
+class QEDSR(QRCAN):
+    """Q-EDSR on the B200 path (reference architectures.py:359-399): same constructor, parameter names, shapes
+    and order.  Runs through the same C entry point as Q-RCAN with style NONE: one flat chain of blocks whose
+    scale is res_scale * sigmoid(FC(FC(meta)))."""
+
+    def __init__(self, in_features=3, out_features=3, num_features=64, input_para=1, num_blocks=16, scale=4,
+                 res_scale=0.1, q_layer_nonlinearity=False, precision='bf16', chunk_images=0, schedule='linear',
+                 **kwargs):
+        nn.Module.__init__(self)
+        if precision not in PRECISIONS:
+            raise RuntimeError("precision must be 'bf16' or 'fp32'")
+        if schedule not in SCHEDULES:
+            raise RuntimeError("schedule must be one of %s" % sorted(SCHEDULES))
+        self.style = "none"
+        self.scale = scale
+        self.precision = precision
+        self.chunk_images = chunk_images
+        self.schedule = schedule
+        M = input_para
+        self.cfg = dict(n_resblocks=num_blocks, n_resgroups=1, n_feats=num_features, in_feats=in_features,
+                        out_feats=out_features, scale=scale, reduction=16, num_metadata=M, style="none",
+                        no_group_conv=1, meta_relu=int(bool(q_layer_nonlinearity)), res_scale=float(res_scale),
+                        meta_hidden=(num_features // 2 if M <= 15 else (num_features - M) // 2 + M))
+        self.head = _conv3(in_features, num_features)
+        blocks = [QEDSRBlockParams(num_features, M, q_layer_nonlinearity) for _ in range(num_blocks)]
+        self.final_body = _conv3(num_features, num_features)
+        tail = [UpsamplerParams(scale, num_features), _conv3(num_features, out_features)]
+        self.body = nn.Sequential(*blocks)
+        self.tail = nn.Sequential(*tail)
+        self._packed = None
+
+    def _pack_spec(self):
+        trunk = []
+        for blk in self.body:
+            trunk += [blk.body[0], blk.body[2]]
+        trunk.append(self.final_body)
+        return dict(cfg=self.cfg, head=self.head, trunk=trunk,
+                    ups=[m for m in self.tail[0] if isinstance(m, nn.Conv2d)], tail=self.tail[1],
+                    ca=[None for _ in self.body], meta=[tuple(blk.attention_layer.fcs()) for blk in self.body])
+
+
 _HANDLES = {}
 _NEXT = [1]
 
@@ -211,28 +280,23 @@ _NEXT = [1]
 class PackedQrcan:
     """Kernel-format copy of a QRCAN's parameters + the `dfir_qrcan_net` descriptor."""
 
-    def __init__(self, net: QRCAN, key):
+    def __init__(self, net, key):
         lib = _lib.load_library()
         self.key = key
-        cfg = net.cfg
-        dev = net.final_body.weight.device
+        spec = net._pack_spec()
+        cfg = spec["cfg"]
+        dev = spec["head"].weight.device
         if dev.type != "cuda":
-            raise RuntimeError("QRCAN parameters must live on a CUDA device")
+            raise RuntimeError("network parameters must live on a CUDA device")
         C_ = cfg["n_feats"]
         ng, nb = cfg["n_resgroups"], cfg["n_resblocks"]
         want_tc = net.precision == "bf16"
         if want_tc and C_ != 64:
-            raise RuntimeError("the tensor-core path is specialised for n_feats = 64 (use precision='fp32')")
+            raise RuntimeError("the tensor-core path is specialised for 64 feature channels (use precision='fp32')")
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         with torch.no_grad(), torch.cuda.device(dev):
-            trunk = []
-            for g in range(ng):
-                grp = net.body[g]
-                for b in range(nb):
-                    trunk += [grp.body[b].body[0], grp.body[b].body[2]]
-                trunk.append(grp.final_body)
-            trunk.append(net.final_body)
-            ups = [m for m in net.tail[0] if isinstance(m, nn.Conv2d)]
+            trunk = spec["trunk"]
+            ups = spec["ups"]
             r = 3 if net.scale == 3 else 2
             n_trunk = len(trunk)
             n_conv = n_trunk + len(ups) * r * r
@@ -248,10 +312,10 @@ class PackedQrcan:
                 conv_b[i] = m.bias
             for t, m in enumerate(ups):
                 conv_b[n_trunk + t * r * r: n_trunk + (t + 1) * r * r] = m.bias.reshape(C_, r * r).t()
-            tail = net.tail[1]
+            tail = spec["tail"]
             tail_b = keep(torch.zeros(16, **f32))
             tail_b[: tail.bias.numel()] = tail.bias
-            head = net.head[0]
+            head = spec["head"]
             head_w = keep(torch.empty(9 * head.in_channels * C_, **f32))
             _lib.check(lib.dfir_pack_conv3x3_f32(head.weight.contiguous().data_ptr(), head_w.data_ptr(), C_,
                                                  head.in_channels, stream), "pack head")
@@ -267,10 +331,10 @@ class PackedQrcan:
                                                           stream), "pack trunk")
                 for t, m in enumerate(ups):
                     w = m.weight.contiguous()
-                    for s in range(r * r):
-                        i = n_trunk + t * r * r + s
+                    for s_ in range(r * r):
+                        i = n_trunk + t * r * r + s_
                         _lib.check(lib.dfir_pack_conv3x3_bf16(w.data_ptr(), conv_w_bf16.data_ptr() + i * wbytes,
-                                                              w.shape[0], 64, 64, s, r * r, stream), "pack up")
+                                                              w.shape[0], 64, 64, s_, r * r, stream), "pack up")
                 tail_w_bf16 = keep(torch.empty(9 * 16 * 128, device=dev, dtype=torch.uint8))
                 _lib.check(lib.dfir_pack_conv3x3_bf16(tail.weight.contiguous().data_ptr(), tail_w_bf16.data_ptr(),
                                                       tail.weight.shape[0], 64, 16, 0, 1, stream), "pack tail")
@@ -293,23 +357,24 @@ class PackedQrcan:
                                                      tail.weight.shape[0], C_, stream), "pack tail f32")
 
             # attention blobs
-            blocks = [net.body[g].body[b] for g in range(ng) for b in range(nb)]
-            if blocks:
-                rows = [torch.cat(blk.final_body.flat_params()) for blk in blocks]
-                ca_blob = keep(torch.stack(rows).to(**f32).contiguous())
+            ca_rows = spec["ca"]          # per block: list of flat fp32 tensors, or None (no channel attention)
+            metas = spec["meta"]          # per block: (fc1, fc2) or None
+            nblk = len(ca_rows)
+            if nblk and ca_rows[0] is not None:
+                ca_blob = keep(torch.stack([torch.cat(rw) for rw in ca_rows]).to(**f32).contiguous())
                 ca_stride = ca_blob.shape[1]
             else:
-                ca_blob, ca_stride = keep(torch.zeros(1, **f32)), 0
-            q_flags = [1 if blk.q_layer else 0 for blk in blocks]
+                ca_blob, ca_stride = keep(torch.zeros(8, **f32)), 0
+            q_flags = [0 if m is None else 1 for m in metas]
             any_q = int(any(q_flags))
             M = cfg["num_metadata"]
-            hid = C_ // 2 if M <= 15 else (C_ - M) // 2 + M
+            hid = cfg["meta_hidden"]
             if any_q:
-                z = lambda *s: torch.zeros(*s, **f32)
-                w1, b1, w2, b2 = z(len(blocks), hid, M), z(len(blocks), hid), z(len(blocks), C_, hid), z(len(blocks), C_)
-                for i, blk in enumerate(blocks):
-                    if blk.q_layer:
-                        f1, f2 = blk.q_node.fcs()
+                z = lambda *shape: torch.zeros(*shape, **f32)
+                w1, b1, w2, b2 = z(nblk, hid, M), z(nblk, hid), z(nblk, C_, hid), z(nblk, C_)
+                for i, m in enumerate(metas):
+                    if m is not None:
+                        f1, f2 = m
                         w1[i], b1[i] = f1.weight.reshape(hid, M), f1.bias
                         w2[i], b2[i] = f2.weight.reshape(C_, hid), f2.bias
                 self.meta = [keep(t) for t in (w1, b1, w2, b2)]
@@ -318,18 +383,19 @@ class PackedQrcan:
                 self.meta = [None] * 4
                 q_enabled = None
 
-        style = STYLES[net.style]
-        self.attr_size = C_ if net.style == "modulate" else M
+        style = STYLES[cfg["style"]]
+        self.attr_size = C_ if cfg["style"] == "modulate" else M
         if any_q and self.attr_size != M:
             raise RuntimeError("style='modulate' cannot be combined with q layers (attribute size mismatch)")
         ptr = lambda t: (t.data_ptr() if t is not None else None)
         d = QrcanNet()
         d.n_groups, d.n_blocks, d.n_feats = ng, nb, C_
-        d.scale, d.style, d.reduced = net.scale, style, C_ // cfg["reduction"]
+        d.scale, d.style, d.reduced = net.scale, style, max(1, C_ // cfg["reduction"])
         d.num_metadata, d.attr_size, d.meta_hidden = M, self.attr_size, hid
         d.in_feats, d.out_feats = cfg["in_feats"], cfg["out_feats"]
         d.q_enabled, d.any_q, d.chunk_images = ptr(q_enabled), any_q, int(net.chunk_images)
         d.schedule = SCHEDULES[net.schedule]
+        d.no_group_conv, d.meta_relu, d.res_scale = int(cfg["no_group_conv"]), int(cfg["meta_relu"]), float(cfg["res_scale"])
         d.conv_w_bf16, d.tail_w_bf16 = ptr(conv_w_bf16), ptr(tail_w_bf16)
         d.conv_w_f32, d.up_w_f32, d.tail_w_f32, d.head_w_f32 = ptr(conv_w_f32), ptr(up_w_f32), ptr(tail_w_f32), ptr(head_w)
         d.conv_b, d.up_b, d.tail_b, d.head_b = ptr(conv_b), ptr(up_b), ptr(tail_b), ptr(head_b)

@@ -36,6 +36,15 @@ def test_state_dict_layout_matches_reference(name):
     assert all(v.dtype == torch.float32 for v in sd.values())
 
 
+@pytest.mark.parametrize("name", [n for n in golden_names() if n.startswith("qedsr")])
+def test_qedsr_state_dict_layout_matches_reference(name):
+    from deepfir_b200.qrcan import QEDSR
+    _, info = load_golden(name)
+    sd = QEDSR(**info["kwargs"]).state_dict()
+    assert list(sd.keys()) == list(info["shapes"].keys())
+    assert all(list(v.shape) == info["shapes"][k] for k, v in sd.items())
+
+
 def test_forward_refuses_cpu_tensors_and_unsupported_options():
     from deepfir_b200.qrcan import QRCAN, ChannelAttentionParams
     net = QRCAN(n_resgroups=1, n_resblocks=1, style="standard", num_metadata=10)
@@ -109,7 +118,7 @@ def test_generate_channels_matches_oracle_and_modulate_style():
 
 def test_pending_handlers_fail_loudly():
     from SISR.models import ModelInterface
-    for name in ("qedsr", "qsan", "qhan"):
+    for name in ("qsan", "qhan"):
         with pytest.raises(NotImplementedError):
             ModelInterface.define_model(name, device=torch.device("cpu"), model_save_dir="/tmp", eval_mode=True)
 

@@ -11,8 +11,9 @@ QRCAN_CASES = [n for n in golden_names() if n.startswith("qrcan") and "pa_" not 
 
 
 def _build(info, precision, **extra):
-    from deepfir_b200.qrcan import QRCAN
-    net = QRCAN(precision=precision, **extra, **info["kwargs"])
+    from deepfir_b200.qrcan import QEDSR, QRCAN
+    cls = QEDSR if info["model"] == "qedsr" else QRCAN
+    net = cls(precision=precision, **extra, **info["kwargs"])
     sd, x, meta = case_tensors(info)
     net.load_state_dict(sd, strict=True)
     return net.cuda().eval(), x, meta
@@ -27,6 +28,26 @@ def test_qrcan_fp32_mode_matches_reference_golden(name):
         out = net(x.cuda(), meta.cuda()).cpu()
     assert out.shape == ref.shape
     assert max_norm_err(out, ref) <= 1e-4
+
+
+@pytest.mark.parametrize("name", ["qedsr_f64_b3", "qedsr_f256_b2_nl"])
+def test_qedsr_fp32_mode_matches_reference_golden(name):
+    """Q-EDSR (ParamResBlock chain, 64 and 256 features, with/without the meta MLP's ReLU), fp32 mode <= 1e-4."""
+    ref, info = load_golden(name)
+    net, x, meta = _build(info, "fp32")
+    with torch.no_grad():
+        out = net(x.cuda(), meta.cuda()).cpu()
+    assert max_norm_err(out, ref) <= 1e-4
+
+
+@pytest.mark.parametrize("schedule", ["linear", "fused", "streamer"])
+def test_qedsr_bf16_mode_matches_reference_golden(schedule):
+    ref, info = load_golden("qedsr_f64_b3")
+    net, x, meta = _build(info, "bf16", schedule=schedule)
+    with torch.no_grad():
+        out = net(x.cuda(), meta.cuda()).cpu()
+    _, pol_err = _policy_error(info, ref)
+    assert max_norm_err(out, ref) <= 2.0 * pol_err + 1e-4, (max_norm_err(out, ref), pol_err)
 
 
 def _policy_error(info, ref):
