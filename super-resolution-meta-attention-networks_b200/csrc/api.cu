@@ -150,10 +150,11 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
   //   2 streamer : separate bandwidth-shaped elementwise kernel (dfir_ca_scale_residual).
   const int sched = n->schedule;
 
+  const float* xcur = w.Hh;
   for (int g = 0; g < ng; ++g) {
     const float* skip32 = g == 0 ? w.Hh : w.XA;            // group input (fp32 stream), kept for `res += x`
     const __nv_bfloat16* gin = g == 0 ? w.Hbf : w.XAbf;    // its bf16 copy = operand of the first conv
-    const float* xcur = skip32;                             // x_b: fp32 stream entering block b
+    xcur = skip32;                                          // x_b: fp32 stream entering block b
     for (int b = 0; b < nb; ++b) {
       const int blk = g * nb + b;
       const float* sq = n->any_q ? w.sq + (static_cast<size_t>(blk) * B + b0) * C : nullptr;
@@ -212,6 +213,7 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
   {
     ConvTcDesc cf = base(ng * per_group, EPI_SCALE_SKIP);
     cf.in_bf16 = (ng == 0 || (n->no_group_conv && nb == 0)) ? w.Hbf : (n->no_group_conv ? w.XBbf : w.XAbf);
+    if (sched == 1 && n->no_group_conv && ng > 0 && nb > 0) fuse_in(cf, ng * nb - 1, xcur, nullptr);  // last x never materialised
     cf.out_bf16 = w.XBbf; cf.skip_f32 = w.Hh; cf.out_f32 = nullptr;
     DFIR_TRY(conv3x3_c64_tc(cf, st));
   }

@@ -297,14 +297,14 @@ def test_meta_attention(M, hid, C, relu):
     out = torch.empty(nblk, B, C, device="cuda")
     cu = [t.cuda() for t in (meta, w1, b1, w2, b2, en)]
     rc = G.lib().dfir_meta_attention(*[t.data_ptr() for t in cu[:5]], out.data_ptr(), nblk, B, M, hid, C, relu,
-                                     cu[5].data_ptr(), G.stream())
+                                     cu[5].data_ptr(), 0.5, G.stream())
     assert rc == 0
     G.sync()
     for k in range(nblk):
         h = meta @ w1[k].t() + b1[k]
         if relu:
             h = F.relu(h)
-        want = torch.sigmoid(h @ w2[k].t() + b2[k]) if en[k] else torch.ones(B, C)
+        want = 0.5 * (torch.sigmoid(h @ w2[k].t() + b2[k]) if en[k] else torch.ones(B, C))
         assert torch.allclose(out[k].cpu(), want, rtol=1e-5, atol=1e-6)
 
 
