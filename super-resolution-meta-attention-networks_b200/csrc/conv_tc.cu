@@ -50,7 +50,7 @@ using namespace ptx;
 
 namespace {
 
-constexpr int kSlots = 6;                    // smem input-row ring depth (producer -> A loaders): deep = HBM prefetch
+constexpr int kSlots = 4;                    // smem input-row ring depth (producer -> A loaders)
 constexpr int kSlotPix = 136;                // 130 px used (128 + 2 halo), rounded up to 8 px = 1024 B
 constexpr int kSlotBytes = kSlotPix * 128;   // 17408, multiple of 1024
 constexpr int kBoxPix = 130;
@@ -71,7 +71,8 @@ struct SmemLayout {
   static constexpr int off_w = 0;
   static constexpr int off_ring = off_w + ((w_bytes + 1023) / 1024) * 1024;
   static constexpr int off_stage = off_ring + kSlots * kSlotBytes;
-  static constexpr int off_bias = off_stage + 2 * kStageBytes;
+  static constexpr int off_skip = off_stage + 2 * kStageBytes;   // EPI_SCALE_SKIP: fp32 skip row (cp.async target)
+  static constexpr int off_bias = off_skip + 128 * 64 * 4;
   static constexpr int off_pool = off_bias + 64 * 4;
   static constexpr int off_attn = off_pool + 4 * 64 * 4;                         // y[64] s[64] attr[512] tmp[1024]
   static constexpr int off_svec = off_attn + (64 + 64 + 512 + 1024 + 4) * 4;     // s of the images of this band
@@ -116,6 +117,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   uint8_t* wsm = smem + L::off_w;
   uint8_t* ring = smem + L::off_ring;
   uint8_t* stage = smem + L::off_stage;
+  float* skipbuf = reinterpret_cast<float*>(smem + L::off_skip);
   float* bias_s = reinterpret_cast<float*>(smem + L::off_bias);
   float* pool_s = reinterpret_cast<float*>(smem + L::off_pool);
   float* attn_s = reinterpret_cast<float*>(smem + L::off_attn);
@@ -176,6 +178,9 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   const bool exp_no_epi = (a.debug_probe & 32) != 0;
   const bool exp_n192 = (a.debug_probe & 64) != 0;   // 12 MMAs of N=192 per row (timing only)
   const bool exp_n128 = (a.debug_probe & 128) != 0;  // 18 MMAs of N=128 per row (timing only)
+  const bool exp_no_skipld = (a.debug_probe & 256) != 0;
+  const bool exp_no_f32st = (a.debug_probe & 512) != 0;
+  const bool exp_no_bfst = (a.debug_probe & 1024) != 0;
 
   if (g0 < g1) {
     if (warp == 0) {
@@ -442,6 +447,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       const int et = threadIdx.x - 64; // 0..127
       const int rows_img_e = nseg * H;
       const int bimg_first = g0 / rows_img_e;
+      int cur_img = -1;
       if constexpr (EPI == EPI_SCALE_SKIP) {
         // ---- pool-by-linearity: while the pipeline fills, the epilogue warps turn the sums of
         // t = relu(conv1(x)) left by the previous kernel into this block's attention vectors
@@ -540,10 +546,27 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         const bool valid = x < a.W;
         const int acc = it % kAcc;
         if (probe) g_dfir_progress[8 + q] = it + 1;
-        // EPI_SCALE_SKIP: the fp32 skip values of this row are fetched (coalesced, 16 x 16 B per thread) BEFORE
-        // waiting for the accumulator, so their latency hides behind the MMAs of the row.
-        float4 skv[EPI == EPI_SCALE_SKIP ? 16 : 1];
+        // EPI_SCALE_SKIP: the fp32 skip row travels global -> smem with cp.async (16 x 16 B per thread, coalesced,
+        // no registers held): the copy for row it+1 is issued at the end of row it, so its latency hides behind
+        // the accumulator wait and the TMEM read of the next row.  Each thread later reads back exactly the
+        // 16-byte slots it copied itself, so no barrier is needed, only cp.async.wait_group.
+        auto issue_skip = [&](int gg) {
+          const int colg = gg / H;
+          const int segg = colg % nseg;
+          const int npxg = min(128, a.W - segg * 128);
+          const float* src = a.skip_f32 + ((static_cast<size_t>(colg / nseg) * a.H + (gg % H)) * a.W + segg * 128) * 64;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int idx = i * 128 + et;
+            if ((idx >> 4) < npxg && !exp_no_skipld)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(skipbuf + idx * 4)),
+                           "l"(src + static_cast<size_t>(idx) * 4)
+                           : "memory");
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        };
         if constexpr (EPI == EPI_SCALE_SKIP) {
+          if (it == 0) issue_skip(g);
           if (g + 2 < g1) {  // pull the skip row needed two iterations from now into L2 (2 x 128 B lines per thread)
             const int g2 = g + 2, col2 = g2 / H;
             const size_t e2 = ((static_cast<size_t>(col2 / nseg) * a.H + (g2 % H)) * a.W + (col2 % nseg) * 128) * 64;
@@ -554,14 +577,6 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               if (line * 32 < npx2 * 64)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(a.skip_f32 + e2 + static_cast<size_t>(line) * 32));
             }
-          }
-          const int npx = min(128, a.W - seg * 128);
-          const size_t row_e = ((static_cast<size_t>(b) * a.H + y) * a.W + seg * 128) * 64;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int idx = i * 128 + et;
-            skv[i] = (idx >> 4) < npx ? *reinterpret_cast<const float4*>(a.skip_f32 + row_e + static_cast<size_t>(idx) * 4)
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         mbar_wait(&tfull[acc], (it / kAcc) & 1, 8);
@@ -589,12 +604,22 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               if (c < a.cout) o[c * plane] = __uint_as_float(r0[c]) + bias_s[c];
           }
         } else if constexpr (EPI == EPI_SCALE_SKIP) {
-          // v = (acc + bias) * s[b][c]; fp32 tile in smem (chunk-rotated: conflict free), then a coalesced pass
-          // adds the fp32 skip and writes the fp32 stream + its bf16 copy straight to global memory.
+          // v = acc * s + bias * s into an fp32 tile in smem (chunk-rotated: conflict free for both the pixel-major
+          // writes and the coalesced reads), then a coalesced pass adds the fp32 skip row and writes the fp32
+          // stream + its bf16 copy straight to global memory.
           float* tile = reinterpret_cast<float*>(stage);  // [128 px][64] fp32 = 32 KB = both staging buffers
-          const float* sv = a.epi_stats ? svec_s + (b - bimg_first) * 64
-                                                          : (a.svec != nullptr ? a.svec + static_cast<size_t>(b) * 64 : nullptr);
-          named_bar_sync(1, 128);  // previous row's coalesced pass has finished reading the tile
+          float* sc_s = pool_s;                           // [64] scale, [64] bias*scale of the current image
+          named_bar_sync(1, 128);  // previous row's coalesced pass has finished with the tile (and with sc_s)
+          if (b != cur_img) {      // (uniform) new image: stage its scale vector
+            if (et < 64) {
+              const float sc = a.epi_stats ? svec_s[(b - bimg_first) * 64 + et]
+                                           : (a.svec != nullptr ? a.svec[static_cast<size_t>(b) * 64 + et] : 1.f);
+              sc_s[et] = sc;
+              sc_s[64 + et] = bias_s[et] * sc;
+            }
+            cur_img = b;
+            named_bar_sync(2, 128);
+          }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t rv[32];
@@ -606,41 +631,44 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               if (lane == 0) mbar_arrive(&tempty[acc]);
             }
             float4* trow = reinterpret_cast<float4*>(tile + m * 64);
+            const float4* sc4 = reinterpret_cast<const float4*>(sc_s) + h * 8;
+            const float4* bs4 = reinterpret_cast<const float4*>(sc_s + 64) + h * 8;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
+              const float4 s4 = sc4[c], b4 = bs4[c];
               float4 o;
-              const int ch = h * 32 + c * 4;
-              o.x = __uint_as_float(rv[4 * c + 0]) + bias_s[ch + 0];
-              o.y = __uint_as_float(rv[4 * c + 1]) + bias_s[ch + 1];
-              o.z = __uint_as_float(rv[4 * c + 2]) + bias_s[ch + 2];
-              o.w = __uint_as_float(rv[4 * c + 3]) + bias_s[ch + 3];
-              if (sv != nullptr) {
-                const float4 s4 = *reinterpret_cast<const float4*>(sv + ch);
-                o.x *= s4.x; o.y *= s4.y; o.z *= s4.z; o.w *= s4.w;
-              }
-              trow[((h * 8 + c) + m) & 15] = o;
+              o.x = fmaf(__uint_as_float(rv[4 * c + 0]), s4.x, b4.x);
+              o.y = fmaf(__uint_as_float(rv[4 * c + 1]), s4.y, b4.y);
+              o.z = fmaf(__uint_as_float(rv[4 * c + 2]), s4.z, b4.z);
+              o.w = fmaf(__uint_as_float(rv[4 * c + 3]), s4.w, b4.w);
+              trow[(h * 8 + c + m) & 15] = o;
             }
           }
           named_bar_sync(2, 128);
           {
             const int npx = min(128, a.W - seg * 128);  // valid pixels of this row segment
-            const size_t row_e = ((static_cast<size_t>(b) * a.H + y) * a.W + seg * 128) * 64;
+            const int c4 = et & 15, pq = et >> 4;       // this thread: 4-channel group c4 of pixels pq + 8 i
+            const size_t e0 = ((static_cast<size_t>(b) * a.H + y) * a.W + seg * 128 + pq) * 64 + c4 * 4;
+            float* o32 = a.out_f32 != nullptr ? a.out_f32 + e0 : nullptr;
+            __nv_bfloat16* obf = a.out_bf16_direct + e0;
+            const float4* t4 = reinterpret_cast<const float4*>(tile);
+            const float4* sk4 = reinterpret_cast<const float4*>(skipbuf) + et;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const int idx = i * 128 + et;  // float4 index inside the tile: pixel = idx / 16, chunk = idx % 16
-              const int p = idx >> 4, c4 = idx & 15;
+              const int p = i * 8 + pq;
               if (p < npx) {
-                float4 o = reinterpret_cast<const float4*>(tile + p * 64)[(c4 + p) & 15];
-                const size_t e = row_e + static_cast<size_t>(p) * 64 + c4 * 4;
-                const float4 sk = skv[i];
+                float4 o = t4[p * 16 + ((c4 + p) & 15)];
+                const float4 sk = sk4[i * 128];
                 o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
-                if (a.out_f32 != nullptr) *reinterpret_cast<float4*>(a.out_f32 + e) = o;
+                if (o32 != nullptr && !exp_no_f32st) *reinterpret_cast<float4*>(o32 + i * 512) = o;
                 uint2 pk;
                 pk.x = pack_bf16x2(o.x, o.y);
                 pk.y = pack_bf16x2(o.z, o.w);
-                *reinterpret_cast<uint2*>(a.out_bf16_direct + e) = pk;
+                if (!exp_no_bfst) *reinterpret_cast<uint2*>(obf + i * 512) = pk;
               }
             }
+            if (g + 1 < g1) issue_skip(g + 1);  // this thread's slots are free again: refill them for the next row
           }
         } else {
           const int sb = it & 1;
@@ -666,9 +694,9 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
             }
             if constexpr (EPI == EPI_RELU_STATS) {
-              // statistics are taken of the bf16-ROUNDED t, i.e. of exactly what the next conv consumes
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+              // statistics of t in fp32 (before the bf16 rounding of the store): the rounding noise averages out
+              // over the image (relative effect on the pooled mean ~1e-5) and the fp32 value is what the
+              // reference's own pooled mean is made of
               if (valid && (x == 0 || x == a.W - 1)) {
                 float* dst = (x == 0 ? a.col_first : a.col_last) + (static_cast<size_t>(b) * a.H + y) * 64 + h * 32;
 #pragma unroll
