@@ -239,7 +239,7 @@ def conv_roofline(lib, dev, net):
     ws_bytes = lib.dfir_qrcan_workspace_bytes(C.byref(packed.desc), IMAGES_PER_GPU, LR, LR, 0)
     # chunk size the schedule uses (images per L2-resident pass): recover it from the launch count
     launches = lib.dfir_qrcan_launch_count(C.byref(packed.desc), IMAGES_PER_GPU, LR, LR, 0)
-    per_chunk = 1 + 10 * (20 * 3 + 1) + 1 + 2 * 4 + 1
+    per_chunk = 1 + 10 * (20 * 2 + 1) + 1 + 2 * 4 + 1  # default schedule: 2 launches per RCAB
     chunks = max(1, (launches - 1) // per_chunk)
     bc = (IMAGES_PER_GPU + chunks - 1) // chunks
     a = torch.randn(bc, LR, LR, 64, device=dev).to(torch.bfloat16)
@@ -268,9 +268,12 @@ def conv_roofline(lib, dev, net):
     ms = e0.elapsed_time(e1) / n
     flops = bc * LR * LR * CONV64_FLOP_PER_PIXEL
     achieved = flops / (ms / 1e3) / 1e12
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full capture
+    # summarised in profiles/r01_conv_ts_mode_ncu.md (32 images per launch; algorithmic bytes = 2 x 67.1 MB)
+    traffic = 89651456 if bc == 32 else None
     return {"bound": "tensor", "kernel": "conv3x3_c64_tc_kernel<64, bias+relu>", "achieved": round(achieved, 2),
             "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": round(achieved / pk["tf_burst"], 4),
-            "traffic": None, "launch_us": round(ms * 1e3, 3), "images_per_launch": bc,
+            "traffic": traffic, "launch_us": round(ms * 1e3, 3), "images_per_launch": bc,
             "algorithmic_flops_per_launch": flops, "peak_source": pk["source"] + ", burst (kernel timed alone)"}
 
 
