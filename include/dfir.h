@@ -223,6 +223,54 @@ long long dfir_qrcan_launch_count(const dfir_qrcan_net* net, int B, int H, int W
 int dfir_qrcan_forward(const dfir_qrcan_net* net, const float* x_nchw, const float* attributes, float* out_nchw,
                        int B, int H, int W, int precision, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Staged execution of the same schedule (the state lives in the caller's workspace; requires one pass, i.e.
+ * chunk_images = 0/B and a workspace for B images).  stages is a mask: 1 head conv, 2 groups [g_begin, g_end),
+ * 4 trunk tail conv + head skip, 8 upsampler + tail conv.  Used by the host code of Q-HAN / Q-SAN, whose extra
+ * layers sit between these stages (attention_manipulators/architectures.py:447-467, 514-540).
+ *   feat_in_f32  (optional, NHWC fp32): replaces the stream entering g_begin (stages & 2), the trunk-tail input
+ *                (stages & 4 without 2) or the upsampler input (stages == 8)
+ *   group_out_f32(optional): fp32 NHWC copy of the stream after every executed group, [g_end-g_begin][B][H][W][C]
+ *   feat_out_f32 (optional): fp32 NHWC copy of the stream after the last executed group, or of the head output */
+int dfir_qrcan_stages(const dfir_qrcan_net* net, int stages, int g_begin, int g_end, const float* x_nchw,
+                      const float* attributes, const float* feat_in_f32, float* group_out_f32, float* feat_out_f32,
+                      float* out_nchw, int B, int H, int W, int precision, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Q-HAN / Q-SAN layers (fp32 NHWC; HBM- or latency-bound kernels, csrc/san_han.cu)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* out = x * svec[b][c] (svec optional) + alpha * add (add optional): SOCA's `y * x` (advanced/SAN_blocks.py:302) and
+ * the share-source skips `+ gamma * residual` (attention_manipulators/architectures.py:459). */
+int dfir_channel_scale(const float* x, const float* svec, const float* add, float alpha, float* out, int B, int HW,
+                       int C, void* stream);
+
+/* LAM_Module.forward (advanced/HAN_blocks.py:24-37): N feature maps (map n at stack + n*map_stride_elems, each
+ * [B][HW][C] fp32) -> out [B][HW][N*C] with out[..., n*C+c] = gamma * sum_j softmax_j(max_j E[n] - E[n][j]) X_j + X_n,
+ * E = Gram matrix over (pixel, channel). */
+size_t dfir_lam_scratch_bytes(int B, int N);
+int dfir_lam(const float* stack, long long map_stride_elems, float gamma, float* out, void* scratch, int N, int B,
+             int HW, int C, void* stream);
+
+/* CSAM_Module.forward (advanced/HAN_blocks.py:59-76): out = x * (gamma * sigmoid(conv3d_3x3x3(x as a (C,H,W)
+ * volume) + bias)) + x; w27 = conv.weight[0][0] flattened (channel, y, x). */
+int dfir_csam(const float* x, const float* w27, float bias, float gamma, float* out, int B, int H, int W, int C,
+              void* stream);
+
+/* SOCA.forward up to its channel scale (advanced/SAN_blocks.py:261-300; Covpool / Sqrtm of advanced/mpncov.py:12-76):
+ * covariance pooling over the (centre-cropped when >= 1000) image without materialising the MxM centring matrix,
+ * 5 Newton-Schulz iterations, mean over dim 1, FC-ReLU-FC-sigmoid (mlp_params: W1[R][64] b1[R] W2[64][R] b2[64]). */
+size_t dfir_soca_scratch_bytes(int B);
+int dfir_soca(const float* x, const float* mlp_params, int R, float* svec, void* scratch, int B, int H, int W, int C,
+              void* stream);
+
+/* Nonlocal_CA.forward (advanced/SAN_blocks.py:314-336) with _NonLocalBlockND._embedded_gaussian (:104-148) on each
+ * of the 2x2 regions: theta/phi/g 1x1 convs (w_tpg [24][64], b_tpg [24]: theta rows 0-7, phi 8-15, g 16-23),
+ * 2x2 max-pool of phi and g (always on), softmax attention, W 1x1 conv (w_out [64][8]) + x. */
+size_t dfir_nonlocal_scratch_bytes(int B, int H, int W);
+int dfir_nonlocal(const float* x, const float* w_tpg, const float* b_tpg, const float* w_out, const float* b_out,
+                  float* out, void* scratch, int B, int H, int W, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

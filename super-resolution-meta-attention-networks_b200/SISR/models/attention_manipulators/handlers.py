@@ -10,6 +10,7 @@ import torch
 from torch import nn
 
 from SISR.models.attention_manipulators import QModel
+from deepfir_b200.han_san import QHAN, QSAN
 from deepfir_b200.qrcan import QEDSR, QRCAN
 
 
@@ -50,10 +51,6 @@ class QRCANHandler(QModel):
         return rows.unsqueeze(2).unsqueeze(3)
 
 
-def _pending(name):
-    raise NotImplementedError('%s is not on the B200 path yet (see DESIGN.md, scope table)' % name)
-
-
 class QEDSRHandler(QModel):
     """Meta-attention EDSR (ref :57-76): ParamResBlock chain, every block scaled by its meta-attention vector."""
 
@@ -74,20 +71,66 @@ class QEDSRHandler(QModel):
 
 
 class QSANHandler(QModel):
-    """Meta-attention SAN (ref :79-153)."""
+    """Meta-attention SAN (ref :79-153).  Evaluation always goes through `forward_chop`: four overlapping
+    quadrants (10 px of overlap), each run through the network if smaller than `max_combined_im_size`, else
+    chopped again; the inner halves are stitched back together."""
 
     def __init__(self, device, model_save_dir, eval_mode=False, lr=1e-4, scale=4, perceptual=None,
                  max_combined_im_size=160000, scheduler=None, scheduler_params=None, **kwargs):
         super(QSANHandler, self).__init__(device=device, model_save_dir=model_save_dir, eval_mode=eval_mode,
                                           **kwargs)
-        _pending('qsan')
+        extra = {k: kwargs[k] for k in ('precision', 'schedule') if k in kwargs}
+        self.net = QSAN(scale=scale, input_para=self.num_metadata, **extra)  # like the reference: fixed 20 x 10 trunk
+        self.scale = scale
+        self.colorspace = 'rgb'
+        self.im_input = 'unmodified'
+        self.activate_device()
+        self.training_setup(lr, scheduler, scheduler_params, perceptual, device)
+        self.max_combined_im_size = max_combined_im_size
+        self.model_name = 'qsan'
+
+    def forward_chop(self, x, extra_channels, shave=10):
+        b, c, h, w = x.size()
+        h_half, w_half = h // 2, w // 2
+        h_size, w_size = h_half + shave, w_half + shave
+        quadrants = [x[:, :, 0:h_size, 0:w_size], x[:, :, 0:h_size, (w - w_size):w],
+                     x[:, :, (h - h_size):h, 0:w_size], x[:, :, (h - h_size):h, (w - w_size):w]]
+        if w_size * h_size < self.max_combined_im_size:
+            sr = [self.run_chopped_eval(q, extra_channels) for q in quadrants]
+        else:
+            sr = [self.forward_chop(q, extra_channels, shave=shave) for q in quadrants]
+        s = self.scale
+        h, w, h_half, w_half, h_size, w_size = s * h, s * w, s * h_half, s * w_half, s * h_size, s * w_size
+        output = x.new(b, c, h, w)
+        output[:, :, 0:h_half, 0:w_half] = sr[0][:, :, 0:h_half, 0:w_half]
+        output[:, :, 0:h_half, w_half:w] = sr[1][:, :, 0:h_half, (w_size - w + w_half):w_size]
+        output[:, :, h_half:h, 0:w_half] = sr[2][:, :, (h_size - h + h_half):h_size, 0:w_half]
+        output[:, :, h_half:h, w_half:w] = sr[3][:, :, (h_size - h + h_half):h_size, (w_size - w + w_half):w_size]
+        return output
+
+    def run_eval(self, x, y=None, request_loss=False, metadata=None, metadata_keys=None, timing=False, *args, **kwargs):
+        extra_channels = self.generate_channels(x, metadata, metadata_keys).to(self.device)
+        tic = time.perf_counter()
+        sr_image = self.forward_chop(x, extra_channels)
+        elapsed = time.perf_counter() - tic
+        loss = self.criterion(sr_image, y) if request_loss else None
+        return sr_image, loss, elapsed if timing else None
+
+    def run_chopped_eval(self, x, extra_channels):
+        return super().run_eval(x.contiguous(), y=None, request_loss=False, extra_channels=extra_channels)[0]
 
 
 class QHANHandler(QModel):
-    """Meta-attention HAN (ref :156-171)."""
+    """Meta-attention HAN (ref :156-171): Q-RCAN groups + layer attention + channel-spatial attention."""
 
     def __init__(self, device, model_save_dir, eval_mode=False, lr=1e-4, scale=4, perceptual=None,
                  scheduler=None, scheduler_params=None, **kwargs):
         super(QHANHandler, self).__init__(device=device, model_save_dir=model_save_dir, eval_mode=eval_mode,
                                           **kwargs)
-        _pending('qhan')
+        extra = {k: kwargs[k] for k in ('precision', 'schedule') if k in kwargs}
+        self.net = QHAN(scale=scale, num_metadata=self.num_metadata, **extra)
+        self.colorspace = 'rgb'
+        self.im_input = 'unmodified'
+        self.activate_device()
+        self.training_setup(lr, scheduler, scheduler_params, perceptual, device)
+        self.model_name = 'qhan'

@@ -108,8 +108,18 @@ AttnParams make_ap(const dfir_qrcan_net* n, int blk) {
   return ap;
 }
 
+// stage mask of the forward schedules
+enum : int { ST_HEAD = 1, ST_GROUPS = 2, ST_TRUNK_TAIL = 4, ST_UPSAMPLE = 8, ST_ALL = 15 };
+
+struct StageArgs {
+  int stages = ST_ALL;
+  int g_begin = 0, g_end = 0;     // groups to run (ST_GROUPS)
+  int from_xa = 0;                // the stream entering g_begin is in XA/XAbf (external features), not the head output
+  float* group_out = nullptr;     // optional: fp32 NHWC copy of the stream after every executed group
+};
+
 int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* attr, float* out, int B, int Bc, int b0,
-                       int H, int W, const QrcanWs& w, int num_sms, cudaStream_t st) {
+                       int H, int W, const QrcanWs& w, int num_sms, const StageArgs& sa, cudaStream_t st) {
   const int C = 64;
   const int nb = n->n_blocks, ng = n->n_groups;
   const int per_group = 2 * nb + (n->no_group_conv ? 0 : 1);
@@ -119,8 +129,10 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
   const uint8_t* cw = reinterpret_cast<const uint8_t*>(n->conv_w_bf16);
   const long long pixB = C * 2, rowB = static_cast<long long>(W) * C * 2, imgB = rowB * H;
 
-  DFIR_TRY(head_conv(x + static_cast<size_t>(b0) * n->in_feats * H * W, n->head_w_f32, n->head_b, w.Hh, w.Hbf, Bc,
-                     n->in_feats, H, W, C, st));
+  if (sa.stages & ST_HEAD)
+    DFIR_TRY(head_conv(x + static_cast<size_t>(b0) * n->in_feats * H * W, n->head_w_f32, n->head_b, w.Hh, w.Hbf, Bc,
+                       n->in_feats, H, W, C, st));
+  const size_t feat_bytes = static_cast<size_t>(Bc) * H * W * C * 4;
 
   // One launch description shared by all trunk convs; the lambdas below fill in what differs.
   auto base = [&](int widx, int epi) {
@@ -151,9 +163,11 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
   const int sched = n->schedule;
 
   const float* xcur = w.Hh;
-  for (int g = 0; g < ng; ++g) {
-    const float* skip32 = g == 0 ? w.Hh : w.XA;            // group input (fp32 stream), kept for `res += x`
-    const __nv_bfloat16* gin = g == 0 ? w.Hbf : w.XAbf;    // its bf16 copy = operand of the first conv
+  const int gb = (sa.stages & ST_GROUPS) ? sa.g_begin : 0, ge = (sa.stages & ST_GROUPS) ? sa.g_end : 0;
+  for (int g = gb; g < ge; ++g) {
+    const bool from_head = g == 0 && !sa.from_xa;
+    const float* skip32 = from_head ? w.Hh : w.XA;         // group input (fp32 stream), kept for `res += x`
+    const __nv_bfloat16* gin = from_head ? w.Hbf : w.XAbf; // its bf16 copy = operand of the first conv
     xcur = skip32;                                          // x_b: fp32 stream entering block b
     for (int b = 0; b < nb; ++b) {
       const int blk = g * nb + b;
@@ -197,7 +211,13 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
                                 w.XB, w.XBbf, Bc, H, W, C, st));
       }
     }
-    if (n->no_group_conv) continue;  // Q-EDSR: the chain of blocks runs straight into the trunk tail conv
+    if (n->no_group_conv) {  // Q-EDSR / Q-SAN groups: the chain of blocks has no tail conv of its own
+      if (sa.group_out != nullptr && sched != 1 && nb > 0 &&
+          cudaMemcpyAsync(sa.group_out + static_cast<size_t>(g - gb) * Bc * H * W * C, w.XB, feat_bytes,
+                          cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return DFIR_ERR_CUDA;
+      continue;
+    }
     // group tail conv + `res += x` (group input)
     ConvTcDesc ct = base(g * per_group + 2 * nb, EPI_SCALE_SKIP);
     ct.out_bf16 = w.XAbf; ct.skip_f32 = skip32; ct.out_f32 = w.XA; ct.svec = nullptr;
@@ -209,14 +229,19 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
       ct.in_bf16 = w.XBbf;
     }
     DFIR_TRY(conv3x3_c64_tc(ct, st));
+    if (sa.group_out != nullptr &&
+        cudaMemcpyAsync(sa.group_out + static_cast<size_t>(g - gb) * Bc * H * W * C, w.XA, feat_bytes,
+                        cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      return DFIR_ERR_CUDA;
   }
-  {
+  if (sa.stages & ST_TRUNK_TAIL) {
     ConvTcDesc cf = base(ng * per_group, EPI_SCALE_SKIP);
     cf.in_bf16 = (ng == 0 || (n->no_group_conv && nb == 0)) ? w.Hbf : (n->no_group_conv ? w.XBbf : w.XAbf);
     if (sched == 1 && n->no_group_conv && ng > 0 && nb > 0) fuse_in(cf, ng * nb - 1, xcur, nullptr);  // last x never materialised
     cf.out_bf16 = w.XBbf; cf.skip_f32 = w.Hh; cf.out_f32 = nullptr;
     DFIR_TRY(conv3x3_c64_tc(cf, st));
   }
+  if (!(sa.stages & ST_UPSAMPLE)) return DFIR_OK;
   // upsampler: conv C -> r*r*C with PixelShuffle(r) folded into the TMA store strides
   int r = 0;
   const int nup = up_stages(n->scale, &r);
@@ -254,19 +279,22 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
 }
 
 int qrcan_forward_f32(const dfir_qrcan_net* n, const float* x, const float* attr, float* out, int B, int Bc, int b0,
-                      int H, int W, const QrcanWs& w, cudaStream_t st) {
+                      int H, int W, const QrcanWs& w, const StageArgs& sa, cudaStream_t st) {
   const int C = n->n_feats;
   const int nb = n->n_blocks, ng = n->n_groups;
   const int per_group = 2 * nb + (n->no_group_conv ? 0 : 1);
   const size_t wsz = static_cast<size_t>(9) * C * C;
-  DFIR_TRY(head_conv(x + static_cast<size_t>(b0) * n->in_feats * H * W, n->head_w_f32, n->head_b, w.Hh, nullptr, Bc,
-                     n->in_feats, H, W, C, st));
+  if (sa.stages & ST_HEAD)
+    DFIR_TRY(head_conv(x + static_cast<size_t>(b0) * n->in_feats * H * W, n->head_w_f32, n->head_b, w.Hh, nullptr, Bc,
+                       n->in_feats, H, W, C, st));
+  const size_t feat_bytes = static_cast<size_t>(Bc) * H * W * C * 4;
+  const int gb = (sa.stages & ST_GROUPS) ? sa.g_begin : 0, ge = (sa.stages & ST_GROUPS) ? sa.g_end : 0;
   auto conv = [&](const float* in, int widx, int relu, const float* skip, float* o) {
     return conv3x3_f32(in, n->conv_w_f32 + widx * wsz, n->conv_b + static_cast<size_t>(widx) * C, skip, o, Bc, H, W, C,
                        C, relu, 1, 0, st);
   };
-  for (int g = 0; g < ng; ++g) {
-    const float* skip32 = g == 0 ? w.Hh : w.XA;
+  for (int g = gb; g < ge; ++g) {
+    const float* skip32 = (g == 0 && !sa.from_xa) ? w.Hh : w.XA;
     for (int b = 0; b < nb; ++b) {
       const int blk = g * nb + b;
       const float* cin = b == 0 ? skip32 : w.XB;
@@ -277,7 +305,13 @@ int qrcan_forward_f32(const dfir_qrcan_net* n, const float* x, const float* attr
       DFIR_TRY(scale_residual(w.R32, 0, cin, w.pool, H, make_ap(n, blk), attr + static_cast<size_t>(b0) * n->attr_size,
                               sq, 1.f, w.XB, nullptr, Bc, H, W, C, st));
     }
-    if (n->no_group_conv) continue;
+    if (n->no_group_conv) {
+      if (sa.group_out != nullptr && nb > 0 &&
+          cudaMemcpyAsync(sa.group_out + static_cast<size_t>(g - gb) * Bc * H * W * C, w.XB, feat_bytes,
+                          cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return DFIR_ERR_CUDA;
+      continue;
+    }
     const float* cin = nb == 0 ? skip32 : w.XB;
     // out = conv(cin) + skip32 ; written to T32 first because XA may be the skip being read
     DFIR_TRY(conv(cin, g * per_group + 2 * nb, 0, skip32, w.T32));
@@ -285,12 +319,17 @@ int qrcan_forward_f32(const dfir_qrcan_net* n, const float* x, const float* attr
                      cudaSuccess
                  ? DFIR_OK
                  : DFIR_ERR_CUDA);
+    if (sa.group_out != nullptr &&
+        cudaMemcpyAsync(sa.group_out + static_cast<size_t>(g - gb) * Bc * H * W * C, w.XA, feat_bytes,
+                        cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      return DFIR_ERR_CUDA;
   }
-  {
+  if (sa.stages & ST_TRUNK_TAIL) {
     const float* fin = (ng == 0 || (n->no_group_conv && nb == 0)) ? w.Hh : (n->no_group_conv ? w.XB : w.XA);
     // XB may be the operand: write the trunk tail output to R32, which the upsampler then reads
     DFIR_TRY(conv(fin, ng * per_group, 0, w.Hh, w.R32));
   }
+  if (!(sa.stages & ST_UPSAMPLE)) return DFIR_OK;
   int r = 0;
   const int nup = up_stages(n->scale, &r);
   const float* cur = w.R32;
@@ -504,6 +543,92 @@ long long dfir_qrcan_launch_count(const dfir_qrcan_net* net, int B, int H, int W
   return chunks * per_chunk + (net->any_q ? 1 : 0);
 }
 
+int dfir_qrcan_stages(const dfir_qrcan_net* net, int stages, int g_begin, int g_end, const float* x_nchw,
+                      const float* attributes, const float* feat_in_f32, float* group_out_f32, float* feat_out_f32,
+                      float* out_nchw, int B, int H, int W, int precision, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  if (net == nullptr || B <= 0 || H <= 0 || W <= 0 || (stages & ~ST_ALL) != 0 || stages == 0) return DFIR_ERR_ARG;
+  if ((stages & ST_HEAD) && x_nchw == nullptr) return DFIR_ERR_ARG;
+  if ((stages & ST_GROUPS) && (g_begin < 0 || g_end > net->n_groups || g_begin > g_end || attributes == nullptr))
+    return DFIR_ERR_ARG;
+  if ((stages & ST_UPSAMPLE) && out_nchw == nullptr) return DFIR_ERR_ARG;
+  int r = 0;
+  if (up_stages(net->scale, &r) < 0) return DFIR_ERR_ARG;
+  if (precision == DFIR_PREC_BF16_TC && net->n_feats != 64) return DFIR_ERR_ARG;
+  if (precision != DFIR_PREC_BF16_TC && precision != DFIR_PREC_FP32_SIMT) return DFIR_ERR_ARG;
+  DFIR_TRY(dfir_check_device());
+  const int Bc = net->chunk_images > 0 ? std::min(net->chunk_images, B) : auto_chunk(B, H, W, precision);
+  if (Bc != B) return DFIR_ERR_ARG;  // staged execution keeps its state in the workspace: one pass only
+  QrcanWs w = carve_qrcan(net, B, Bc, H, W, precision, workspace);
+  if (workspace == nullptr || w.total > workspace_bytes) return DFIR_ERR_WORKSPACE;
+  cudaStream_t st = S(stream);
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return DFIR_ERR_CUDA;
+  const int C = net->n_feats;
+  const size_t feat_n = static_cast<size_t>(B) * H * W * C;
+  const bool tc = precision == DFIR_PREC_BF16_TC;
+  StageArgs sa;
+  sa.stages = stages; sa.g_begin = g_begin; sa.g_end = g_end; sa.group_out = group_out_f32;
+  if (feat_in_f32 != nullptr) {
+    if (stages & ST_GROUPS) {  // external features become the stream entering g_begin
+      if (cudaMemcpyAsync(w.XA, feat_in_f32, feat_n * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return DFIR_ERR_CUDA;
+      if (tc) DFIR_TRY(f32_to_bf16(w.XA, w.XAbf, static_cast<long long>(feat_n), st));
+      sa.from_xa = 1;
+    } else if (stages & ST_TRUNK_TAIL) {
+      if (cudaMemcpyAsync(w.XA, feat_in_f32, feat_n * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return DFIR_ERR_CUDA;
+      if (tc) DFIR_TRY(f32_to_bf16(w.XA, w.XAbf, static_cast<long long>(feat_n), st));
+    } else if (stages & ST_UPSAMPLE) {  // external features are the trunk output feeding the upsampler
+      if (tc) DFIR_TRY(f32_to_bf16(feat_in_f32, w.XBbf, static_cast<long long>(feat_n), st));
+      else if (cudaMemcpyAsync(w.R32, feat_in_f32, feat_n * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return DFIR_ERR_CUDA;
+    }
+  }
+  if ((stages & ST_GROUPS) && net->any_q) {
+    DFIR_TRY(meta_attention(attributes, net->meta_w1, net->meta_b1, net->meta_w2, net->meta_b2, w.sq,
+                            net->n_groups * net->n_blocks, B, net->num_metadata, net->meta_hidden, net->n_feats,
+                            net->meta_relu, net->q_enabled, net->style == DFIR_STYLE_NONE ? net->res_scale : 1.f, st));
+  }
+  if (tc) DFIR_TRY(qrcan_forward_bf16(net, x_nchw, attributes, out_nchw, B, B, 0, H, W, w, sms, sa, st));
+  else DFIR_TRY(qrcan_forward_f32(net, x_nchw, attributes, out_nchw, B, B, 0, H, W, w, sa, st));
+  if (feat_out_f32 != nullptr) {
+    const float* src = nullptr;
+    if ((stages & ST_GROUPS) && g_end > g_begin) src = (net->no_group_conv && net->n_blocks > 0) ? w.XB : w.XA;
+    else if (stages & ST_HEAD) src = w.Hh;
+    if (src == nullptr) return DFIR_ERR_ARG;
+    if (cudaMemcpyAsync(feat_out_f32, src, feat_n * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return DFIR_ERR_CUDA;
+  }
+  return DFIR_OK;
+}
+
+int dfir_channel_scale(const float* x, const float* svec, const float* add, float alpha, float* out, int B, int HW,
+                       int C, void* stream) {
+  return channel_scale(x, svec, add, alpha, out, B, HW, C, S(stream));
+}
+
+size_t dfir_lam_scratch_bytes(int B, int N) { return lam_scratch_floats(B, N) * 4; }
+int dfir_lam(const float* stack, long long map_stride_elems, float gamma, float* out, void* scratch, int N, int B,
+             int HW, int C, void* stream) {
+  return lam_forward(stack, map_stride_elems, gamma, out, reinterpret_cast<float*>(scratch), N, B, HW, C, S(stream));
+}
+
+int dfir_csam(const float* x, const float* w27, float bias, float gamma, float* out, int B, int H, int W, int C,
+              void* stream) {
+  return csam_forward(x, w27, bias, gamma, out, B, H, W, C, S(stream));
+}
+
+size_t dfir_soca_scratch_bytes(int B) { return soca_scratch_floats(B) * 4; }
+int dfir_soca(const float* x, const float* mlp_params, int R, float* svec, void* scratch, int B, int H, int W, int C,
+              void* stream) {
+  return soca_forward(x, mlp_params, R, svec, reinterpret_cast<float*>(scratch), B, H, W, C, S(stream));
+}
+
+size_t dfir_nonlocal_scratch_bytes(int B, int H, int W) { return nonlocal_scratch_floats(B, H, W) * 4; }
+int dfir_nonlocal(const float* x, const float* w_tpg, const float* b_tpg, const float* w_out, const float* b_out,
+                  float* out, void* scratch, int B, int H, int W, int C, void* stream) {
+  return nonlocal_forward(x, w_tpg, b_tpg, w_out, b_out, out, reinterpret_cast<float*>(scratch), B, H, W, C, S(stream));
+}
+
 int dfir_qrcan_forward(const dfir_qrcan_net* net, const float* x_nchw, const float* attributes, float* out_nchw, int B,
                        int H, int W, int precision, void* workspace, size_t workspace_bytes, void* stream) {
   if (net == nullptr || x_nchw == nullptr || out_nchw == nullptr || attributes == nullptr) return DFIR_ERR_ARG;
@@ -527,12 +652,14 @@ int dfir_qrcan_forward(const dfir_qrcan_net* net, const float* x_nchw, const flo
                             net->n_groups * net->n_blocks, B, net->num_metadata, net->meta_hidden, net->n_feats,
                             net->meta_relu, net->q_enabled, net->style == DFIR_STYLE_NONE ? net->res_scale : 1.f, st));
   }
+  StageArgs all;
+  all.g_end = net->n_groups;
   for (int b0 = 0; b0 < B; b0 += Bc) {
     const int bc = std::min(Bc, B - b0);
     if (precision == DFIR_PREC_BF16_TC)
-      DFIR_TRY(qrcan_forward_bf16(net, x_nchw, attributes, out_nchw, B, bc, b0, H, W, w, sms, st));
+      DFIR_TRY(qrcan_forward_bf16(net, x_nchw, attributes, out_nchw, B, bc, b0, H, W, w, sms, all, st));
     else
-      DFIR_TRY(qrcan_forward_f32(net, x_nchw, attributes, out_nchw, B, bc, b0, H, W, w, st));
+      DFIR_TRY(qrcan_forward_f32(net, x_nchw, attributes, out_nchw, B, bc, b0, H, W, w, all, st));
   }
   return DFIR_OK;
 }

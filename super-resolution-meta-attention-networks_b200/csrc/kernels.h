@@ -105,6 +105,20 @@ int scale_residual(const void* r, int r_is_bf16, const float* x_in, const float*
 int ca_from_stats(const float* pool_rows, const float* col_first, const float* col_last, const void* w2_packed,
                   const float* bias2, const AttnParams& ap, const float* attributes, const float* sq, float* svec, int B,
                   int H, int W, cudaStream_t s);
+// ---- Q-HAN / Q-SAN layers (san_han.cu)
+int channel_scale(const float* x, const float* svec, const float* add, float alpha, float* out, int B, long long HW,
+                  int C, cudaStream_t s);
+int lam_forward(const float* stack, long long map_stride, float gamma, float* out, float* scratch, int N, int B, int HW,
+                int C, cudaStream_t s);
+size_t lam_scratch_floats(int B, int N);
+int csam_forward(const float* x, const float* w27, float bias, float gamma, float* out, int B, int H, int W, int C,
+                 cudaStream_t s);
+int soca_forward(const float* x, const float* mlp, int R, float* svec, float* scratch, int B, int H, int W, int C,
+                 cudaStream_t s);
+size_t soca_scratch_floats(int B);
+int nonlocal_forward(const float* x, const float* wq, const float* bq, const float* wW, const float* bW, float* out,
+                     float* scratch, int B, int H, int W, int C, cudaStream_t s);
+size_t nonlocal_scratch_floats(int B, int H, int W);
 int nchw_to_nhwc_bf16(const float* in, __nv_bfloat16* out, int B, int C, int H, int W, cudaStream_t s);
 int f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t s);
 

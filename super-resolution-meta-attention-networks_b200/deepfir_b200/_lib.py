@@ -71,6 +71,15 @@ PROTOTYPES = {
     "dfir_pool_rows_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "dfir_qrcan_workspace_bytes": (_sz, [C.POINTER(QrcanNet), _i, _i, _i, _i]),
     "dfir_qrcan_launch_count": (C.c_longlong, [C.POINTER(QrcanNet), _i, _i, _i, _i]),
+    "dfir_qrcan_stages": (_i, [C.POINTER(QrcanNet), _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "dfir_channel_scale": (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp]),
+    "dfir_lam_scratch_bytes": (_sz, [_i, _i]),
+    "dfir_lam": (_i, [_vp, _ll, _f, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "dfir_csam": (_i, [_vp, _vp, _f, _f, _vp, _i, _i, _i, _i, _vp]),
+    "dfir_soca_scratch_bytes": (_sz, [_i]),
+    "dfir_soca": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "dfir_nonlocal_scratch_bytes": (_sz, [_i, _i, _i]),
+    "dfir_nonlocal": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "dfir_qrcan_forward": (_i, [C.POINTER(QrcanNet), _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
 }
 

@@ -45,6 +45,15 @@ def test_qedsr_state_dict_layout_matches_reference(name):
     assert all(list(v.shape) == info["shapes"][k] for k, v in sd.items())
 
 
+@pytest.mark.parametrize("name", ["qsan_g2b2", "qhan_b1"])
+def test_qsan_qhan_state_dict_layout_matches_reference(name):
+    from deepfir_b200.han_san import QHAN, QSAN
+    _, info = load_golden(name)
+    sd = (QSAN if info["model"] == "qsan" else QHAN)(**info["kwargs"]).state_dict()
+    assert list(sd.keys()) == list(info["shapes"].keys())
+    assert all(list(v.shape) == info["shapes"][k] for k, v in sd.items())
+
+
 def test_forward_refuses_cpu_tensors_and_unsupported_options():
     from deepfir_b200.qrcan import QRCAN, ChannelAttentionParams
     net = QRCAN(n_resgroups=1, n_resblocks=1, style="standard", num_metadata=10)
@@ -116,11 +125,15 @@ def test_generate_channels_matches_oracle_and_modulate_style():
         assert torch.allclose(g, O.scale_qpi(q.float().reshape(2, 1, 1, 1)), rtol=1e-6)
 
 
-def test_pending_handlers_fail_loudly():
+def test_all_q_handlers_construct_on_cpu_and_refuse_cpu_forward():
     from SISR.models import ModelInterface
-    for name in ("qsan", "qhan"):
-        with pytest.raises(NotImplementedError):
-            ModelInterface.define_model(name, device=torch.device("cpu"), model_save_dir="/tmp", eval_mode=True)
+    for name, n_params in (("qedsr", None), ("qsan", 16353288), ("qhan", 16564545)):
+        h = ModelInterface.define_model(name, device=torch.device("cpu"), model_save_dir="/tmp", eval_mode=True,
+                                        metadata=["blur_kernel"])
+        if n_params is not None:
+            assert h.print_parameters() == n_params  # parameter counts of the reference
+        with pytest.raises(RuntimeError):
+            h.net(torch.zeros(1, 3, 8, 8), torch.zeros(1, 10, 1, 1))
 
 
 @pytest.mark.skipif(not reference_available(), reason="live reference only exists in the build container")

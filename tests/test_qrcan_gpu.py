@@ -11,8 +11,9 @@ QRCAN_CASES = [n for n in golden_names() if n.startswith("qrcan") and "pa_" not 
 
 
 def _build(info, precision, **extra):
+    from deepfir_b200.han_san import QHAN, QSAN
     from deepfir_b200.qrcan import QEDSR, QRCAN
-    cls = QEDSR if info["model"] == "qedsr" else QRCAN
+    cls = {"qedsr": QEDSR, "qrcan": QRCAN, "qsan": QSAN, "qhan": QHAN}[info["model"]]
     net = cls(precision=precision, **extra, **info["kwargs"])
     sd, x, meta = case_tensors(info)
     net.load_state_dict(sd, strict=True)
@@ -48,6 +49,60 @@ def test_qedsr_bf16_mode_matches_reference_golden(schedule):
         out = net(x.cuda(), meta.cuda()).cpu()
     _, pol_err = _policy_error(info, ref)
     assert max_norm_err(out, ref) <= 2.0 * pol_err + 1e-4, (max_norm_err(out, ref), pol_err)
+
+
+@pytest.mark.parametrize("name", ["qsan_g2b2", "qhan_b1"])
+def test_qsan_qhan_fp32_mode_matches_reference_golden(name):
+    """Q-SAN (non-local attention, SOCA with covariance pooling + Newton-Schulz) and Q-HAN (LAM, CSAM) against
+    the reference's outputs; the zero-initialised branches (gamma, W) are randomised in the fixtures."""
+    ref, info = load_golden(name)
+    net, x, meta = _build(info, "fp32")
+    with torch.no_grad():
+        out = net(x.cuda(), meta.cuda()).cpu()
+    assert out.shape == ref.shape
+    assert max_norm_err(out, ref) <= 1e-4, max_norm_err(out, ref)
+
+
+@pytest.mark.parametrize("name", ["qsan_g2b2", "qhan_b1"])
+def test_qsan_qhan_bf16_mode_matches_reference_golden(name):
+    ref, info = load_golden(name)
+    net, x, meta = _build(info, "bf16")
+    with torch.no_grad():
+        out = net(x.cuda(), meta.cuda()).cpu()
+    _, pol_err = _policy_error(info, ref)
+    assert max_norm_err(out, ref) <= 2.0 * pol_err + 1e-4, (max_norm_err(out, ref), pol_err)
+
+
+def test_qsan_handler_forward_chop_matches_oracle_chop():
+    """QSANHandler.run_eval always chops into 4 overlapping quadrants (ref handlers.py:99-150)."""
+    import tempfile
+    from SISR.models import ModelInterface
+    from oracle.synth import synth_state_dict, synth_inputs
+    h = ModelInterface.define_model("qsan", device=0, model_save_dir=tempfile.gettempdir(), eval_mode=True,
+                                    metadata=["blur_kernel"], precision="fp32", max_combined_im_size=20000)
+    sd = synth_state_dict({k: list(v.shape) for k, v in h.net.state_dict().items()}, seed=3)
+    h.net.load_state_dict(sd)
+    x, meta = synth_inputs(1, 26, 30, 10, seed=3)
+    keys = [("blur_kernel",)] * 10
+    out, _, _ = h.run_eval(x, metadata=meta.reshape(1, 10).double(), metadata_keys=keys)
+    # oracle: the same chop/stitch around the oracle network
+    info = dict(model="qsan", kwargs={})
+
+    def net_fn(q):
+        with torch.no_grad():
+            return O.qsan_forward(q, meta, sd)
+    b, c, hh, ww = x.shape
+    hs, ws_ = hh // 2 + 10, ww // 2 + 10
+    quads = [x[:, :, :hs, :ws_], x[:, :, :hs, ww - ws_:], x[:, :, hh - hs:, :ws_], x[:, :, hh - hs:, ww - ws_:]]
+    sr = [net_fn(q) for q in quads]
+    s = 4
+    H2, W2, hh2, wh2, hs2, ws2 = s * hh, s * ww, s * (hh // 2), s * (ww // 2), s * hs, s * ws_
+    want = torch.empty(b, c, H2, W2)
+    want[:, :, :hh2, :wh2] = sr[0][:, :, :hh2, :wh2]
+    want[:, :, :hh2, wh2:] = sr[1][:, :, :hh2, ws2 - W2 + wh2:]
+    want[:, :, hh2:, :wh2] = sr[2][:, :, hs2 - H2 + hh2:, :wh2]
+    want[:, :, hh2:, wh2:] = sr[3][:, :, hs2 - H2 + hh2:, ws2 - W2 + wh2:]
+    assert max_norm_err(out.cpu(), want) <= 1e-4
 
 
 def _policy_error(info, ref):
