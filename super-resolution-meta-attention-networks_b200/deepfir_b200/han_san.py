@@ -65,7 +65,7 @@ class _StagedNet(nn.Module):
             wt = conv.weight.detach().contiguous()
             w = torch.empty(9 * wt.shape[1] * wt.shape[0], device=wt.device, dtype=torch.float32)
             _lib.check(lib.dfir_pack_conv3x3_f32(wt.data_ptr(), w.data_ptr(), wt.shape[0], wt.shape[1],
-                                                 _stream(wt.device)), "pack " + name)
+                                                 _stream(wt.device)), "pack %s" % (name,))
             self._side[name] = w
         return w
 
@@ -76,7 +76,7 @@ class _StagedNet(nn.Module):
         w = self._packed_f32(name, conv)
         _lib.check(lib.dfir_conv3x3_f32(x.data_ptr(), w.data_ptr(), conv.bias.detach().data_ptr(),
                                         skip.data_ptr() if skip is not None else None, out.data_ptr(), B, H, W, Cin,
-                                        conv.out_channels, 0, 1, 0, _stream(x.device)), "conv " + name)
+                                        conv.out_channels, 0, 1, 0, _stream(x.device)), "conv %s" % (name,))
         return out
 
     def _scale_add(self, x, svec=None, add=None, alpha=1.0):
