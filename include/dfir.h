@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DFIR_ABI_VERSION 1
+#define DFIR_ABI_VERSION 2
 
 /* error codes */
 #define DFIR_OK 0
@@ -211,6 +211,12 @@ typedef struct dfir_qrcan_net {
   const float* ca_blob;             /* [n_groups*n_blocks][ca_stride] */
   int ca_stride;
   const float* meta_w1; const float* meta_b1; const float* meta_w2; const float* meta_b2;
+  /* training only (may be NULL for inference): weights of the data-gradient convolutions, i.e. the same layouts
+   * built from the transposed, 180-degree rotated kernels */
+  const void* conv_wT_bf16;         /* [n_conv][9*64*128 B]: trunk convs, then the upsampler slices */
+  const float* conv_wT_f32;         /* [n_trunk][9][C][C] */
+  const float* up_wT_f32;           /* [n_up][9][r*r*C][C] */
+  const float* tail_wT_f32;         /* [9][out_feats][C] (both precisions: the 3 -> C gradient conv runs on CUDA cores) */
 } dfir_qrcan_net;
 
 size_t dfir_qrcan_workspace_bytes(const dfir_qrcan_net* net, int B, int H, int W, int precision);
@@ -235,6 +241,82 @@ int dfir_qrcan_stages(const dfir_qrcan_net* net, int stages, int g_begin, int g_
                       const float* attributes, const float* feat_in_f32, float* group_out_f32, float* feat_out_f32,
                       float* out_nchw, int B, int H, int W, int precision, void* workspace, size_t workspace_bytes,
                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * training step: forward with saved activations + backward
+ *   (BaseModel.run_train / standard_update, models/__init__.py:466-489: forward, L1 loss, loss.backward(), Adam)
+ * The loss, the optimizer and the scheduler stay in PyTorch (they own the fp32 nn.Parameters); the library computes
+ * the network forward and every parameter gradient.  Supported: Q-RCAN with style none / standard / modulate /
+ * max_concat and Q-EDSR (flat chain), n_feats = 64 on the tensor-core path, any width in fp32 mode.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Device pointers to the fp32 nn.Parameter storages of a network — or, with the same shape, to their gradient
+ * buffers.  `conv_w` ... `meta` are arrays of pointers that live in DEVICE memory (the kernels read them), indexed
+ * like the trunk arrays of dfir_qrcan_net; ca/meta hold 4 pointers per block: QCALayer.conv_du {0.weight, 0.bias,
+ * 2.weight, 2.bias} and ParaCALayer.attribute_integrator {FC1 weight, bias, FC2 weight, bias} (NULL entries for
+ * blocks without a q layer).  All tensors keep the reference's OIHW / [out][in] layouts. */
+typedef struct dfir_qrcan_params {
+  float* const* conv_w;  /* [n_trunk] OIHW [C][C][3][3] */
+  float* const* conv_b;  /* [n_trunk] [C] */
+  float* const* up_w;    /* [n_up]    OIHW [r*r*C][C][3][3] */
+  float* const* up_b;    /* [n_up]    [r*r*C] */
+  float* tail_w; float* tail_b; /* [out_feats][C][3][3], [out_feats] */
+  float* head_w; float* head_b; /* [C][in_feats][3][3], [C] */
+  float* const* ca;      /* [n_groups*n_blocks*4] or NULL (style none) */
+  float* const* meta;    /* [n_groups*n_blocks*4] or NULL (no q layers) */
+} dfir_qrcan_params;
+
+/* Rebuilds every kernel-format buffer of `net` (the pointers inside dfir_qrcan_net, written although declared const)
+ * from the fp32 parameters in a handful of launches: what must happen after each optimizer.step().
+ * with_backward != 0 also fills the conv_wT_* / up_wT_* / tail_wT_* buffers. */
+int dfir_qrcan_repack(const dfir_qrcan_net* net, const dfir_qrcan_params* params, int precision, int with_backward,
+                      void* stream);
+
+/* Workspace of one training step (activation stash of the forward + scratch of the backward). */
+size_t dfir_qrcan_train_workspace_bytes(const dfir_qrcan_net* net, int B, int H, int W, int precision);
+
+/* QRCAN.forward in training mode: same result as dfir_qrcan_forward up to the stated tolerance (bf16 mode: r is
+ * rounded to bf16 before the attention scale), every activation the backward needs stays in `workspace`. */
+int dfir_qrcan_train_forward(const dfir_qrcan_net* net, const float* x_nchw, const float* attributes, float* out_nchw,
+                             int B, int H, int W, int precision, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of the above for grad_out_nchw = dL/d out (fp32 [B][out_feats][sH][sW]).  Writes (not accumulates) the
+ * gradient of every parameter through the pointers in `grads`.  Must follow dfir_qrcan_train_forward on the same
+ * workspace and the same x / attributes. */
+int dfir_qrcan_train_backward(const dfir_qrcan_net* net, const dfir_qrcan_params* grads, const float* x_nchw,
+                              const float* attributes, const float* grad_out_nchw, int B, int H, int W, int precision,
+                              void* workspace, size_t workspace_bytes, void* stream);
+/* kernel launches of one forward + backward (bench.py's gpu_launches claim for the training step) */
+long long dfir_qrcan_train_launch_count(const dfir_qrcan_net* net, int B, int H, int W, int precision);
+
+/* single operators of the backward, exercised one by one by tests/test_train_gpu.py */
+
+/* Weight + bias gradient of a 64 -> 64 3x3 conv on the tensor cores.  dy: bf16 NHWC with explicit byte strides
+ * (0 = dense); x: dense bf16 NHWC; dw: fp32 OIHW rows co_begin + n*co_stride (n < 64) of a [*][64][3][3] tensor;
+ * db likewise.  scratch >= dfir_conv3x3_wgrad_scratch_bytes(). */
+size_t dfir_conv3x3_wgrad_scratch_bytes(int B, int H, int W, int Cin, int Cout, int precision);
+int dfir_conv3x3_wgrad_c64(const void* dy_bf16, long long dy_pix_stride, long long dy_row_stride,
+                           long long dy_img_stride, const void* x_bf16, int B, int H, int W, float* dw_oihw, float* db,
+                           int co_begin, int co_stride, void* scratch, size_t scratch_bytes, void* stream);
+/* the same on CUDA cores in fp32 for any Cin % 4 == 0 / Cout (dense NHWC operands) */
+int dfir_conv3x3_wgrad_f32(const float* dy, const float* x, int B, int H, int W, int Cin, int Cout, float* dw_oihw,
+                           float* db, void* scratch, size_t scratch_bytes, void* stream);
+/* Data gradient of a 64 -> 64 conv on the tensor cores: out = conv(dy, wT) [* (mask > 0)] [+ skip].
+ *   wT_packed: dfir_pack_conv3x3_bf16_ex(transpose = 1).  With mask_bf16 (saved ReLU output) the result is written as
+ *   bf16 only; otherwise out_f32 = conv + skip_f32 (skip optional, may alias out_f32) and out_bf16 = its bf16 copy. */
+int dfir_conv3x3_c64_dgrad(const void* dy_bf16, long long dy_pix_stride, long long dy_row_stride,
+                           long long dy_img_stride, const void* wT_packed, const void* mask_bf16, const float* skip_f32,
+                           float* out_f32, void* out_bf16, int B, int H, int W, void* stream);
+/* dfir_pack_conv3x3_bf16 with the data-gradient option: transpose != 0 packs rows = input channels, columns = output
+ * channels co_begin + k*co_stride, taps mirrored. */
+int dfir_pack_conv3x3_bf16_ex(const float* w_oihw, void* out, int cout, int nt_rows, int co_begin, int co_stride,
+                              int transpose, void* stream);
+/* weight gradients of the 3-channel convs: tail_mode 0 = head conv (img = network input, feat = dL/d head output,
+ * fp32), 1 = tail conv (img = dL/d output, feat = tail input; feat_is_bf16 selects its type). */
+size_t dfir_conv3x3_wgrad_small_scratch_bytes(int B, int H, int C);
+int dfir_conv3x3_wgrad_small(const float* img_nchw, const void* feat_nhwc, int feat_is_bf16, int B, int H, int W, int C,
+                             int C3, int tail_mode, float* dw_oihw, float* db, void* scratch, size_t scratch_bytes,
+                             void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Q-HAN / Q-SAN layers (fp32 NHWC; HBM- or latency-bound kernels, csrc/san_han.cu)

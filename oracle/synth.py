@@ -48,3 +48,21 @@ def synth_inputs(batch, height, width, num_metadata=10, seed=8):
     x = torch.from_numpy(x.astype(np.float32))
     meta = torch.from_numpy(meta.astype(np.float32)).reshape(batch, num_metadata, 1, 1)
     return x, meta
+
+
+def synth_target(shape, seed=8):
+    """deterministic HR target for the training-step cases (L1 loss against it)"""
+    rs = np.random.RandomState(seed + 2000)
+    return torch.from_numpy(rs.uniform(0, 1, size=tuple(shape)).astype(np.float32))
+
+
+N_PROJ = 8
+
+
+def grad_projections(name, g):
+    """dot products of a gradient with N_PROJ deterministic Gaussian directions (seeded by the parameter name):
+    the compact fingerprint stored in tests/golden/grads_*.npz"""
+    seed = int.from_bytes(name.encode()[-8:].rjust(8, b"\0"), "little") % (2 ** 31)
+    rs = np.random.RandomState(seed)
+    flat = g.detach().double().reshape(-1).numpy()
+    return np.array([float(np.dot(rs.standard_normal(flat.size), flat)) for _ in range(N_PROJ)])

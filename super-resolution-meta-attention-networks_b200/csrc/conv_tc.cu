@@ -165,7 +165,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
     mbar_init(wbar, 1);
     fence_barrier_init();
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + NT) bias_s[threadIdx.x - 64] = a.bias[threadIdx.x - 64];
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + NT) bias_s[threadIdx.x - 64] = a.bias != nullptr ? a.bias[threadIdx.x - 64] : 0.f;
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_holder);
   tcgen05_fence_before();
   __syncthreads();
@@ -550,7 +550,9 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         // no registers held): the copy for row it+1 is issued at the end of row it, so its latency hides behind
         // the accumulator wait and the TMEM read of the next row.  Each thread later reads back exactly the
         // 16-byte slots it copied itself, so no barrier is needed, only cp.async.wait_group.
+        const bool has_skip = a.skip_f32 != nullptr;  // dgrad launches without a skip: out = acc * s + b * s
         auto issue_skip = [&](int gg) {
+          if (!has_skip) return;
           const int colg = gg / H;
           const int segg = colg % nseg;
           const int npxg = min(128, a.W - segg * 128);
@@ -567,7 +569,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         };
         if constexpr (EPI == EPI_SCALE_SKIP) {
           if (it == 0) issue_skip(g);
-          if (g + 2 < g1) {  // pull the skip row needed two iterations from now into L2 (2 x 128 B lines per thread)
+          if (has_skip && g + 2 < g1) {  // pull the skip row needed two iterations from now into L2 (2 x 128 B lines per thread)
             const int g2 = g + 2, col2 = g2 / H;
             const size_t e2 = ((static_cast<size_t>(col2 / nseg) * a.H + (g2 % H)) * a.W + (col2 % nseg) * 128) * 64;
             const int npx2 = min(128, a.W - (col2 % nseg) * 128);
@@ -659,8 +661,10 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               const int p = i * 8 + pq;
               if (p < npx) {
                 float4 o = t4[p * 16 + ((c4 + p) & 15)];
-                const float4 sk = sk4[i * 128];
-                o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
+                if (has_skip) {
+                  const float4 sk = sk4[i * 128];
+                  o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
+                }
                 if (o32 != nullptr && !exp_no_f32st) *reinterpret_cast<float4*>(o32 + i * 512) = o;
                 uint2 pk;
                 pk.x = pack_bf16x2(o.x, o.y);
@@ -707,6 +711,23 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
 #pragma unroll
                   for (int i = 0; i < 32; i += 4)
                     *reinterpret_cast<float4*>(d2 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                }
+              }
+            }
+            if constexpr (EPI == EPI_RELU_MASK) {
+              // backward of ReLU: keep the gradient where the saved forward activation t is positive
+              if (valid) {
+                const uint4* mk = reinterpret_cast<const uint4*>(a.mask_bf16 + pix * 64 + h * 32);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const uint4 raw = mk[c];
+                  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = __bfloat1622float2(h2[j]);
+                    if (!(f.x > 0.f)) v[8 * c + 2 * j] = 0.f;
+                    if (!(f.y > 0.f)) v[8 * c + 2 * j + 1] = 0.f;
+                  }
                 }
               }
             }
@@ -854,21 +875,25 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
        (d.ca_A > 0 && d.attributes == nullptr)))
     return DFIR_ERR_ARG;
   if (!fused && d.in_bf16 == nullptr) return DFIR_ERR_ARG;
-  if (d.epi == EPI_SCALE_SKIP && (d.skip_f32 == nullptr || d.out_bf16 == nullptr || d.out_pix_stride != 128 ||
+  if (d.epi == EPI_SCALE_SKIP && (d.out_bf16 == nullptr || d.out_pix_stride != 128 ||
                                   d.out_row_stride != static_cast<long long>(d.W) * 128))
     return DFIR_ERR_ARG;  // the direct-store epilogue writes dense NHWC
   if (d.epi == EPI_SCALE_SKIP && d.epi_stats &&
       (fused || d.ca_style == DFIR_STYLE_NONE || d.pool_rows == nullptr || d.col_first == nullptr || d.col_last == nullptr || d.ca_params == nullptr ||
        d.ca_A > 512 || d.ca_M > 448 || (d.ca_A > 0 && d.attributes == nullptr)))
     return DFIR_ERR_ARG;
+  if (d.epi == EPI_RELU_MASK && d.mask_bf16 == nullptr) return DFIR_ERR_ARG;
   if (d.epi == EPI_RELU_STATS && (d.pool_rows == nullptr || d.col_first == nullptr || d.col_last == nullptr))
     return DFIR_ERR_ARG;
   CUtensorMap tin, tout;
   int rc = DFIR_OK;
   if (!fused) {
-    rc = make_tmap_nhwc_bf16(&tin, d.in_bf16, d.cin_total, d.W, d.H, d.B, static_cast<long long>(d.cin_total) * 2,
-                             static_cast<long long>(d.W) * d.cin_total * 2,
-                             static_cast<long long>(d.H) * d.W * d.cin_total * 2, kBoxPix);
+    // dense NHWC unless explicit byte strides are given (backward of the upsampler: one sub-pixel phase of a
+    // PixelShuffle output is a strided view, advanced/common.py:30)
+    const long long ips = d.in_pix_stride > 0 ? d.in_pix_stride : static_cast<long long>(d.cin_total) * 2;
+    const long long irs = d.in_row_stride > 0 ? d.in_row_stride : static_cast<long long>(d.W) * d.cin_total * 2;
+    const long long iis = d.in_img_stride > 0 ? d.in_img_stride : static_cast<long long>(d.H) * d.W * d.cin_total * 2;
+    rc = make_tmap_nhwc_bf16(&tin, d.in_bf16, d.cin_total, d.W, d.H, d.B, ips, irs, iis, kBoxPix);
     if (rc != DFIR_OK) return rc;
   }
   if (d.epi != EPI_TAIL_NCHW) {
@@ -895,6 +920,7 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   a.col_first = d.col_first;
   a.col_last = d.col_last;
   a.svec = d.svec;
+  a.mask_bf16 = reinterpret_cast<const __nv_bfloat16*>(d.mask_bf16);
   a.out_bf16_direct = reinterpret_cast<__nv_bfloat16*>(d.out_bf16);
   a.r_bf16 = reinterpret_cast<const __nv_bfloat16*>(d.r_bf16);
   a.xin_f32 = d.xin_f32;
@@ -931,6 +957,7 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
     case EPI_BIAS_POOL: return launch_one<64, EPI_BIAS_POOL, IN_TMA>(tin, tout, a, grid, stream);
     case EPI_BIAS_SKIP: return launch_one<64, EPI_BIAS_SKIP, IN_TMA>(tin, tout, a, grid, stream);
     case EPI_RELU_STATS: return launch_one<64, EPI_RELU_STATS, IN_TMA>(tin, tout, a, grid, stream);
+    case EPI_RELU_MASK: return launch_one<64, EPI_RELU_MASK, IN_TMA>(tin, tout, a, grid, stream);
     case EPI_SCALE_SKIP: return launch_one<64, EPI_SCALE_SKIP, IN_TMA>(tin, tout, a, grid, stream);
     case EPI_TAIL_NCHW: return launch_one<16, EPI_TAIL_NCHW, IN_TMA>(tin, tout, a, grid, stream);
     default: return DFIR_ERR_ARG;

@@ -20,6 +20,7 @@ enum : int {
                       // attention of the block BEFORE its second conv runs (pool-by-linearity)
   EPI_SCALE_SKIP = 6, // RCAB conv2 / group conv: out_f32 = (acc + b) * s[b][c] + skip ; out_bf16 = bf16(out_f32)
                       // i.e. QCALayer/ParaCALayer `x * y` and `res += x` in the epilogue (:127,179; q_layer.py:43)
+  EPI_RELU_MASK = 7,  // backward of conv-ReLU: out_bf16 = (acc + b) where the saved activation mask_bf16 > 0, else 0
 };
 
 enum : int { IN_TMA = 0, IN_FUSED = 1 };  // input modes of the tensor-core conv (see conv_tc.cu)
@@ -34,6 +35,7 @@ struct ConvTcArgs {  // kernel argument block
   float* col_first;         // EPI_RELU_STATS: t at x = 0 / x = W-1 of every row, fp32 [B][H][64]
   float* col_last;
   const float* svec;        // EPI_SCALE_SKIP: per-image channel scale [B][64] (nullptr = 1)
+  const __nv_bfloat16* mask_bf16;  // EPI_RELU_MASK: saved forward activation (dense NHWC)
   __nv_bfloat16* out_bf16_direct;  // EPI_SCALE_SKIP writes its bf16 copy with plain coalesced stores
   // IN_FUSED: conv input = r * s[b] + xin (xout = fp32 copy of it for the rows the CTA owns), with
   // s[b] = CA_style(mean(r_b) from pool_rows, attributes[b]) * sq[b]   (style NONE: s = res_scale * sq)
@@ -57,6 +59,8 @@ struct ConvTcDesc {  // host-side launch description
   int in_mode;             // IN_TMA | IN_FUSED
   int num_sms;
   const void* in_bf16;
+  long long in_pix_stride = 0, in_row_stride = 0, in_img_stride = 0;  // bytes; 0 = dense NHWC
+  const void* mask_bf16 = nullptr;                                     // EPI_RELU_MASK
   const void* wpacked;
   const float* bias;
   void* out_bf16;
@@ -94,7 +98,7 @@ int pack_conv_weights_f32(const float* w_oihw, float* out, int cout, int cin, cu
 int head_conv(const float* x_nchw, const float* w_packed, const float* bias, float* out_f32, __nv_bfloat16* out_bf16,
               int B, int Cin, int H, int W, int Cout, cudaStream_t s);
 int conv3x3_f32(const float* in, const float* w_packed, const float* bias, const float* skip, float* out, int B, int H,
-                int W, int Cin, int Cout, int relu, int ps_r, int out_nchw, cudaStream_t s);
+                int W, int Cin, int Cout, int relu, int ps_r, int out_nchw, cudaStream_t s, const float* mask = nullptr);
 int pool_rows_f32(const float* in, float* pool_rows, int B, int H, int W, int C, cudaStream_t s);
 int meta_attention(const float* meta, const float* w1, const float* b1, const float* w2, const float* b2, float* out,
                    int nblk, int B, int M, int Hid, int C, int relu, const int* blk_enabled, float out_scale,
@@ -119,6 +123,39 @@ size_t soca_scratch_floats(int B);
 int nonlocal_forward(const float* x, const float* wq, const float* bq, const float* wW, const float* bW, float* out,
                      float* scratch, int B, int H, int W, int C, cudaStream_t s);
 size_t nonlocal_scratch_floats(int B, int H, int W);
+// ---- training step (train_kernels.cu, wgrad_mma.cu)
+int pack_bf16_multi(const float* const* tbl, const float* direct, void* out, int n_tiles, int cout, int nt_rows,
+                    int per_src, int transpose, cudaStream_t s, int j0 = 0);
+int pack_f32_multi(const float* const* tbl, const float* direct, float* out, int n, int cout, int cin, int transpose,
+                   cudaStream_t s);
+int gather_strided(const float* const* tbl, const float* direct, int tbl_stride, int tbl_off, float* out, int n_rows,
+                   int n, int per_src, int src_stride, long long out_stride, cudaStream_t s);
+int bwd_reduce_chunks(int HW);
+int bwd_reduce_gr(const float* g, const void* r, int r_is_bf16, float* part, int B, int HW, int C, cudaStream_t s);
+int ca_backward(const float* part, const float* pool_rows, int pool_nrows, int HW, const AttnParams& ap,
+                const float* attributes, const float* sq, float out_scale, float* svec, float* dyv, float* sig,
+                int sig_stride, int B, cudaStream_t s);
+int form_dr(const float* g, const float* svec, const float* dyv, void* dr, int dr_is_bf16, int B, int HW, int C,
+            cudaStream_t s);
+int add_f32(const float* a, const float* b, float* out, void* out_bf16, long long n, cudaStream_t s);
+int pixel_unshuffle_f32(const float* in, float* out, int B, int h, int w, int C, int r, cudaStream_t s);
+int wgrad_f32_chunks(int B, int H, int Cin, int Cout);
+size_t wgrad_scratch_floats(int S, int Cin, int Cout);
+int wgrad_f32(const float* dY, const float* X, float* scratch, int B, int H, int W, int Cin, int Cout, cudaStream_t s,
+              int* S_out);
+int wgrad_reduce(const float* part, const float* dbpart, int S, int Cin, int n_rows, float* const* w_tbl, int w_idx,
+                 float* w_direct, float* const* b_tbl, int b_idx, float* b_direct, int co_begin, int co_stride,
+                 cudaStream_t s);
+size_t wgrad_small_scratch_floats(int B, int H, int C);
+int wgrad_small(const float* I, const void* F, int f_is_bf16, float* scratch, int B, int H, int W, int C, int C3,
+                int tail_mode, float* dw, float* db, cudaStream_t s);
+int attn_param_grads(const float* sig, int sig_stride, const float* attributes, int A, const float* meta_w1,
+                     const float* meta_b1, const float* meta_w2, const int* q_enabled, float* const* ca_g,
+                     float* const* meta_g, int nblk, int B, int C, int R, int M, int Hid, int style, int meta_relu,
+                     cudaStream_t s);
+int wgrad_c64_grid(int B, int H, int W, int num_sms);
+int wgrad_c64_bf16(const void* dy, long long dy_pix, long long dy_row, long long dy_img, const void* x, float* scratch,
+                   int B, int H, int W, int num_sms, cudaStream_t s, int* S_out);
 int nchw_to_nhwc_bf16(const float* in, __nv_bfloat16* out, int B, int C, int H, int W, cudaStream_t s);
 int f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t s);
 

@@ -58,7 +58,7 @@ __global__ void head_conv_kernel(const float* __restrict__ x, const float* __res
   const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
   float acc[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = bias[oc + i];
+  for (int i = 0; i < 8; ++i) acc[i] = bias != nullptr ? bias[oc + i] : 0.f;
   for (int dy = 0; dy < 3; ++dy) {
     const int yy = y + dy - 1;
     if (yy < 0 || yy >= H) continue;
@@ -93,7 +93,7 @@ __global__ void head_conv_kernel(const float* __restrict__ x, const float* __res
 __global__ void __launch_bounds__(256)
 conv3x3_f32_kernel(const float* __restrict__ in, const float* __restrict__ wp, const float* __restrict__ bias,
                    const float* __restrict__ skip, float* __restrict__ out, int B, int H, int W, int Cin, int Cout,
-                   int relu, int ps_r, int out_nchw) {
+                   int relu, int ps_r, int out_nchw, const float* __restrict__ mask) {
   const int n_oct = (Cout + 7) / 8;
   const int quads_per_row = (W + 3) / 4;
   const long long nquad = static_cast<long long>(B) * H * quads_per_row;
@@ -110,7 +110,7 @@ conv3x3_f32_kernel(const float* __restrict__ in, const float* __restrict__ wp, c
 #pragma unroll
   for (int p = 0; p < 4; ++p)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[p][i] = (oc + i < Cout) ? bias[oc + i] : 0.f;
+    for (int i = 0; i < 8; ++i) acc[p][i] = (bias != nullptr && oc + i < Cout) ? bias[oc + i] : 0.f;
 
   for (int dy = 0; dy < 3; ++dy) {
     const int yy = y + dy - 1;
@@ -163,6 +163,7 @@ conv3x3_f32_kernel(const float* __restrict__ in, const float* __restrict__ wp, c
       float val = acc[p][i];
       if (skip != nullptr) val += skip[pix * Cout + k];
       if (relu) val = fmaxf(val, 0.f);
+      if (mask != nullptr && !(mask[pix * Cout + k] > 0.f)) val = 0.f;  // ReLU backward against the saved activation
       size_t o;
       if (out_nchw) {
         o = ((static_cast<size_t>(b) * Cout + k) * H + y) * W + x;
@@ -439,14 +440,14 @@ int head_conv(const float* x, const float* wp, const float* bias, float* out_f32
 }
 
 int conv3x3_f32(const float* in, const float* wp, const float* bias, const float* skip, float* out, int B, int H,
-                int W, int Cin, int Cout, int relu, int ps_r, int out_nchw, cudaStream_t s) {
+                int W, int Cin, int Cout, int relu, int ps_r, int out_nchw, cudaStream_t s, const float* mask) {
   if (Cin % 4 != 0) return DFIR_ERR_ARG;
   if (ps_r > 1 && (Cout % (ps_r * ps_r) != 0 || skip != nullptr || out_nchw)) return DFIR_ERR_ARG;
   const int n_oct = (Cout + 7) / 8;
   const long long nthreads = static_cast<long long>(B) * H * ((W + 3) / 4) * n_oct;
   if (nthreads == 0) return DFIR_OK;
   conv3x3_f32_kernel<<<static_cast<unsigned>((nthreads + 255) / 256), 256, 0, s>>>(in, wp, bias, skip, out, B, H, W,
-                                                                                  Cin, Cout, relu, ps_r, out_nchw);
+                                                                                  Cin, Cout, relu, ps_r, out_nchw, mask);
   return ok_or_cuda();
 }
 

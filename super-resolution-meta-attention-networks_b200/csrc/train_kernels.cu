@@ -1,0 +1,750 @@
+// CUDA-core kernels of the TRAINING step (BaseModel.run_train -> loss.backward(),
+// /root/reference/Code/SISR/models/__init__.py:466-489): everything in the backward pass that is not a dense
+// contraction.  These are HBM- or latency-bound: reductions of g*r for the channel-attention gradient, the
+// attention-MLP backward on [B][C] vectors, elementwise gradient forming, the fp32 parity-mode weight gradient, the
+// 3-channel head/tail weight gradients, and the batched (pointer-table driven) re-packing of the fp32 parameters
+// into kernel layouts after every optimizer step.
+#include "kernels.h"
+
+#include <algorithm>
+
+namespace dfir {
+
+namespace {
+
+inline int ok_or_cuda3() { return cudaGetLastError() == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA; }
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <>
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+  __align__(16) __nv_bfloat162 pk[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pk[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<uint4*>(pk);
+}
+
+// ------------------------------------------------------------------------------------------------
+// parameter re-packing driven by device pointer tables (one launch per category instead of one per layer)
+// ------------------------------------------------------------------------------------------------
+// blockIdx.y = j-th packed tile.  Source tensor = tbl[j / per_src] (or `direct`), OIHW fp32 [cout][64][3][3].
+//   forward  : tile row n <-> output channel co = (j % per_src) + n * per_src, column k <-> input channel
+//   transpose: the data-gradient conv: row n <-> INPUT channel, column k <-> output channel of the slice, taps
+//              mirrored (correlation with the 180-degree rotated kernel)
+__global__ void pack_bf16_multi_kernel(const float* const* __restrict__ tbl, const float* __restrict__ direct,
+                                       __nv_bfloat16* __restrict__ out, int cout, int nt_rows, int per_src,
+                                       int transpose, int j0) {
+  const int j = blockIdx.y + j0;
+  const float* w = tbl != nullptr ? tbl[j / per_src] : direct;
+  const int slice = j % per_src;
+  __nv_bfloat16* o = out + static_cast<size_t>(blockIdx.y) * 9 * nt_rows * 64;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 9 * nt_rows * 64) return;
+  const int k = idx % 64;
+  const int n = (idx / 64) % nt_rows;
+  const int t = idx / (64 * nt_rows);
+  float v = 0.f;
+  if (!transpose) {
+    const int co = slice + n * per_src;
+    if (co < cout) v = w[(static_cast<size_t>(co) * 64 + k) * 9 + t];
+  } else {
+    const int co = slice + k * per_src;
+    if (co < cout && n < 64) v = w[(static_cast<size_t>(co) * 64 + n) * 9 + (8 - t)];
+  }
+  const int chunk = (k >> 3) ^ (n & 7);
+  o[static_cast<size_t>(t) * nt_rows * 64 + n * 64 + chunk * 8 + (k & 7)] = __float2bfloat16_rn(v);
+}
+
+// fp32 layouts: forward [9][Cin][Cout]; transpose [9][Cout][Cin] with mirrored taps (the dgrad conv's weights)
+__global__ void pack_f32_multi_kernel(const float* const* __restrict__ tbl, const float* __restrict__ direct,
+                                      float* __restrict__ out, int cout, int cin, int transpose) {
+  const int j = blockIdx.y;
+  const float* w = tbl != nullptr ? tbl[j] : direct;
+  float* o = out + static_cast<size_t>(j) * 9 * cin * cout;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 9 * cin * cout) return;
+  if (!transpose) {
+    const int co = idx % cout, ci = (idx / cout) % cin, t = idx / (cout * cin);
+    o[idx] = w[(static_cast<size_t>(co) * cin + ci) * 9 + t];
+  } else {
+    const int ci = idx % cin, co = (idx / cin) % cout, t = idx / (cout * cin);
+    o[idx] = w[(static_cast<size_t>(co) * cin + ci) * 9 + (8 - t)];
+  }
+}
+
+// out[j*out_stride + i] = src[s + i*src_stride], src = tbl[(j / per_src)*tbl_stride + tbl_off] (NULL entry -> 0),
+// s = j % per_src
+__global__ void gather_strided_kernel(const float* const* __restrict__ tbl, const float* __restrict__ direct,
+                                      int tbl_stride, int tbl_off, float* __restrict__ out, int n, int per_src,
+                                      int src_stride, long long out_stride) {
+  const int j = blockIdx.y;
+  const float* src = tbl != nullptr ? tbl[static_cast<size_t>(j / per_src) * tbl_stride + tbl_off] : direct;
+  const int s = j % per_src;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[static_cast<size_t>(j) * out_stride + i] = src != nullptr ? src[s + static_cast<size_t>(i) * src_stride] : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// part[b][chunk][c] = sum over the chunk's pixels of g * r      (d loss / d attention scale, before the batch of
+// tiny MLP backward kernels).  HBM-bound: reads 4 + sizeof(T) bytes per element once, fully coalesced.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+bwd_reduce_gr_kernel(const float* __restrict__ g, const T* __restrict__ r, float* __restrict__ part, int HW, int C,
+                     int nchunk) {
+  __shared__ float sh[2048];
+  const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  const int lpp = C / 8, npl = 256 / lpp;
+  const int c0 = (tid % lpp) * 8, pl = tid / lpp;
+  const int ppc = (HW + nchunk - 1) / nchunk;
+  const int p0 = chunk * ppc, p1 = min(HW, p0 + ppc);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const size_t img = static_cast<size_t>(b) * HW * C;
+  for (int p = p0 + pl; p < p1; p += npl) {
+    const size_t e = img + static_cast<size_t>(p) * C + c0;
+    float gv[8], rv[8];
+    load8<float>(g + e, gv);
+    load8<T>(r + e, rv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(gv[i], rv[i], acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sh[pl * C + c0 + i] = acc[i];
+  __syncthreads();
+  for (int c = tid; c < C; c += 256) {
+    float t = 0.f;
+    for (int k = 0; k < npl; ++k) t += sh[k * C + c];
+    part[(static_cast<size_t>(b) * nchunk + chunk) * C + c] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward of the block's scale vector s = QCALayer(mean(r), attributes) * meta_scale for image b = blockIdx.x
+// (attention_manipulators/architectures.py:105-127, q_layer.py:39-43), styles NONE / STANDARD / MODULATE /
+// MAX_CONCAT.  Emits what the two full-tensor passes need (s and the constant dL/dr contribution of the mean) and
+// the per-image signals from which attn_param_grads_kernel forms the parameter gradients in a fixed order.
+//   sig[b] = { y[C], h[R], dz2[C], dh[R], dzq[C] }
+// ------------------------------------------------------------------------------------------------
+struct CaBwdArgs {
+  const float* part; int nchunk;
+  const float* pool_rows; int pool_nrows; int HW;
+  int style, C, R, M, A;
+  const float* ca;          // W1[R][Cin] b1[R] W2[C][R] b2[C]
+  const float* attributes;  // [B][A]
+  const float* sq;          // [B][C] meta scale of this block incl. out_scale, or nullptr
+  float out_scale;          // factor folded into sq (ParamResBlock res_scale), 1 otherwise
+  float* svec; float* dyv; float* sig; int sig_stride;
+};
+
+__global__ void __launch_bounds__(128) ca_backward_kernel(CaBwdArgs a) {
+  __shared__ float ds[256], y[256], dz2[256], attr[512], h[64], dh[64], tmp[512];
+  const int b = blockIdx.x, tid = threadIdx.x, C = a.C, R = a.R;
+  for (int c = tid; c < C; c += 128) {
+    float t = 0.f;
+    for (int k = 0; k < a.nchunk; ++k) t += a.part[(static_cast<size_t>(b) * a.nchunk + k) * C + c];
+    ds[c] = t;
+  }
+  float* sig = a.sig + static_cast<size_t>(b) * a.sig_stride;
+  if (a.style == DFIR_STYLE_NONE) {
+    __syncthreads();
+    for (int c = tid; c < C; c += 128) {
+      const float sqv = a.sq != nullptr ? a.sq[static_cast<size_t>(b) * C + c] : a.out_scale;
+      a.svec[static_cast<size_t>(b) * C + c] = sqv;
+      const float sg = sqv / a.out_scale;  // sigmoid output
+      sig[2 * C + 2 * R + c] = a.sq != nullptr ? ds[c] * a.out_scale * sg * (1.f - sg) : 0.f;
+    }
+    return;
+  }
+  const int Cin = (a.style == DFIR_STYLE_MAX_CONCAT) ? C + a.M : C;
+  const float* W1 = a.ca; const float* b1 = W1 + R * Cin; const float* W2 = b1 + R; const float* b2 = W2 + C * R;
+  // pooled mean, same fixed summation order as the forward streamer (simt.cu scale_residual_kernel)
+  {
+    const int ngrp = 256 / C;
+    for (int i = tid; i < ngrp * C; i += 128) {
+      const int c = i % C, grp = i / C;
+      const float* pr = a.pool_rows + static_cast<size_t>(b) * a.pool_nrows * C + c;
+      float s = 0.f;
+      for (int row = grp; row < a.pool_nrows; row += ngrp) s += pr[static_cast<size_t>(row) * C];
+      tmp[i] = s;
+    }
+    for (int i = tid; i < a.A; i += 128) attr[i] = a.attributes[static_cast<size_t>(b) * a.A + i];
+    __syncthreads();
+    for (int c = tid; c < C; c += 128) {
+      float t = 0.f;
+      for (int gI = 0; gI < ngrp; ++gI) t += tmp[gI * C + c];
+      y[c] = t / static_cast<float>(a.HW);
+    }
+    __syncthreads();
+  }
+  for (int j = tid; j < R; j += 128) {
+    const float* wr = W1 + static_cast<size_t>(j) * Cin;
+    float s = b1[j];
+    for (int i = 0; i < C; ++i) s = fmaf(wr[i], y[i], s);
+    for (int i = C; i < Cin; ++i) s = fmaf(wr[i], attr[i - C], s);
+    h[j] = fmaxf(s, 0.f);
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += 128) {
+    const float* wr = W2 + static_cast<size_t>(c) * R;
+    float s = b2[c];
+    for (int j = 0; j < R; ++j) s = fmaf(wr[j], h[j], s);
+    const float sg = 1.f / (1.f + expf(-s));
+    const float mod = a.style == DFIR_STYLE_MODULATE ? attr[c] : 1.f;
+    const float sqv = a.sq != nullptr ? a.sq[static_cast<size_t>(b) * C + c] : 1.f;
+    const float s_ca = sg * mod;
+    a.svec[static_cast<size_t>(b) * C + c] = s_ca * sqv;
+    const float d_sca = ds[c] * sqv;
+    const float d_sq = ds[c] * s_ca;
+    const float sgq = sqv / a.out_scale;
+    sig[2 * C + 2 * R + c] = a.sq != nullptr ? d_sq * a.out_scale * sgq * (1.f - sgq) : 0.f;
+    dz2[c] = d_sca * mod * sg * (1.f - sg);
+  }
+  __syncthreads();
+  for (int j = tid; j < R; j += 128) {
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s = fmaf(W2[static_cast<size_t>(c) * R + j], dz2[c], s);
+    dh[j] = h[j] > 0.f ? s : 0.f;
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += 128) {
+    float s = 0.f;
+    for (int j = 0; j < R; ++j) s = fmaf(W1[static_cast<size_t>(j) * Cin + c], dh[j], s);
+    a.dyv[static_cast<size_t>(b) * C + c] = s / static_cast<float>(a.HW);
+    sig[c] = y[c];
+    sig[C + R + c] = dz2[c];
+  }
+  for (int j = tid; j < R; j += 128) {
+    sig[C + j] = h[j];
+    sig[2 * C + R + j] = dh[j];
+  }
+}
+
+// dr = g * s[b][c] + dyv[b][c]   (dL/d conv2 output of the block), written in the operand format T
+template <typename T>
+__global__ void __launch_bounds__(256)
+form_dr_kernel(const float* __restrict__ g, const float* __restrict__ svec, const float* __restrict__ dyv,
+               T* __restrict__ dr, int HW, int C) {
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int lpp = C / 8;
+  const int c0 = (tid % lpp) * 8;
+  float sc[8], ad[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sc[i] = svec[static_cast<size_t>(b) * C + c0 + i];
+    ad[i] = dyv != nullptr ? dyv[static_cast<size_t>(b) * C + c0 + i] : 0.f;
+  }
+  const size_t img = static_cast<size_t>(b) * HW * C;
+  const long long nvec = static_cast<long long>(HW) * lpp;
+  for (long long vi = static_cast<long long>(blockIdx.x) * 256 + tid; vi < nvec;
+       vi += static_cast<long long>(gridDim.x) * 256) {
+    const size_t e = img + static_cast<size_t>(vi) * 8;
+    float gv[8], o[8];
+    load8<float>(g + e, gv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(gv[i], sc[i], ad[i]);
+    store8<T>(dr + e, o);
+  }
+}
+
+// out32 = a + b (either may alias out32), optional bf16 copy
+__global__ void add_f32_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out,
+                               uint2* __restrict__ out_bf16, long long n4) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 x = a[i], y = b[i];
+    const float4 o = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+    out[i] = o;
+    if (out_bf16 != nullptr) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      out_bf16[i] = pk;
+    }
+  }
+}
+
+// inverse of nn.PixelShuffle(r) on NHWC fp32: in [B][h*r][w*r][C] -> out [B][h][w][C*r*r], channel c*r*r + i*r + j
+__global__ void pixel_unshuffle_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int h, int w,
+                                           int C, int r) {
+  const long long n = static_cast<long long>(B) * h * w * C * r * r;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < n;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(idx % (C * r * r));
+    const long long pix = idx / (C * r * r);
+    const int x = static_cast<int>(pix % w), y = static_cast<int>((pix / w) % h), b = static_cast<int>(pix / (static_cast<long long>(w) * h));
+    const int c = k / (r * r), ij = k % (r * r), i = ij / r, j = ij % r;
+    out[idx] = in[((static_cast<size_t>(b) * h * r + (y * r + i)) * (static_cast<size_t>(w) * r) + (x * r + j)) * C + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 parity-mode weight gradient of a 3x3 conv: part[s][tap][ci][co] = sum over the CTA's rows of
+// dY[p][co] * X[p + tap][ci] (zero padded), dbpart[s][co] = sum dY[p][co].
+// grid (S row chunks, Cin/16, Cout/64), 256 threads: thread = (4 output channels, 1 input channel) x 9 taps.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+wgrad_f32_kernel(const float* __restrict__ dY, const float* __restrict__ X, float* __restrict__ part,
+                 float* __restrict__ dbpart, int B, int H, int W, int Cin, int Cout) {
+  __shared__ __align__(16) float dys[32][64];
+  __shared__ float xs[3][34][16];
+  const int tid = threadIdx.x;
+  const int cq = tid & 15, ci = tid >> 4;
+  const int S = gridDim.x, s = blockIdx.x;
+  const int ci0 = blockIdx.y * 16, co0 = blockIdx.z * 64;
+  const long long rows = static_cast<long long>(B) * H;
+  const long long r0 = rows * s / S, r1 = rows * (s + 1) / S;
+  float acc[9][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[t][k] = 0.f;
+  float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long row = r0; row < r1; ++row) {
+    const int b = static_cast<int>(row / H), y = static_cast<int>(row % H);
+    for (int x0 = 0; x0 < W; x0 += 32) {
+      for (int i = tid; i < 32 * 64; i += 256) {
+        const int px = i >> 6, c = i & 63;
+        const int x = x0 + px;
+        dys[px][c] = (x < W && co0 + c < Cout) ? dY[((static_cast<size_t>(b) * H + y) * W + x) * Cout + co0 + c] : 0.f;
+      }
+      for (int i = tid; i < 3 * 34 * 16; i += 256) {
+        const int c = i & 15, px = (i >> 4) % 34, dy = i / (34 * 16);
+        const int yy = y + dy - 1, xx = x0 + px - 1;
+        xs[dy][px][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W && ci0 + c < Cin)
+                            ? X[((static_cast<size_t>(b) * H + yy) * W + xx) * Cin + ci0 + c] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int px = 0; px < 32; ++px) {
+        const float4 d4 = *reinterpret_cast<const float4*>(&dys[px][cq * 4]);
+        dbacc[0] += d4.x; dbacc[1] += d4.y; dbacc[2] += d4.z; dbacc[3] += d4.w;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const float xv = xs[dy][px + dx][ci];
+            acc[dy * 3 + dx][0] = fmaf(d4.x, xv, acc[dy * 3 + dx][0]);
+            acc[dy * 3 + dx][1] = fmaf(d4.y, xv, acc[dy * 3 + dx][1]);
+            acc[dy * 3 + dx][2] = fmaf(d4.z, xv, acc[dy * 3 + dx][2]);
+            acc[dy * 3 + dx][3] = fmaf(d4.w, xv, acc[dy * 3 + dx][3]);
+          }
+      }
+      __syncthreads();
+    }
+  }
+  if (ci0 + ci < Cin) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int co = co0 + cq * 4 + k;
+        if (co < Cout) part[((static_cast<size_t>(s) * 9 + t) * Cin + ci0 + ci) * Cout + co] = acc[t][k];
+      }
+  }
+  if (blockIdx.y == 0 && ci == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int co = co0 + cq * 4 + k;
+      if (co < Cout) dbpart[static_cast<size_t>(s) * Cout + co] = dbacc[k];
+    }
+  }
+}
+
+// dW[co][ci][tap] (OIHW, co = co_begin + n*co_stride) = sum_s part[s][tap][ci][n];  db likewise.  Destinations are
+// read from the gradient pointer tables on the device (w_tbl[w_idx] / b_tbl[b_idx]) or given directly.
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ dbpart, int S, int Cin,
+                                    int n_rows, float* const* __restrict__ w_tbl, int w_idx, float* w_direct,
+                                    float* const* __restrict__ b_tbl, int b_idx, float* b_direct, int co_begin,
+                                    int co_stride) {
+  float* dw = w_tbl != nullptr ? w_tbl[w_idx] : w_direct;
+  float* db = b_tbl != nullptr ? b_tbl[b_idx] : b_direct;
+  const int total = 9 * Cin * n_rows;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < total) {
+    const int n = idx % n_rows, ci = (idx / n_rows) % Cin, tap = idx / (n_rows * Cin);
+    float t = 0.f;
+    for (int s = 0; s < S; ++s) t += part[static_cast<size_t>(s) * total + idx];
+    if (dw != nullptr) dw[(static_cast<size_t>(co_begin + n * co_stride) * Cin + ci) * 9 + tap] = t;
+  }
+  if (idx < n_rows && db != nullptr) {
+    float t = 0.f;
+    for (int s = 0; s < S; ++s) t += dbpart[static_cast<size_t>(s) * n_rows + idx];
+    db[co_begin + idx * co_stride] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradients of the two 3-channel convs (head 3 -> C, tail C -> 3): correlation of a small NCHW fp32 image
+// I[B][3][H][W] with an NHWC feature map F[B][H][W][C]:
+//     K[c3][t][c] = sum_q F[q][c] * I[c3][q + off(t)],   Fsum[c] = sum_q F[q][c],   Isum[c3] = sum_q I[c3][q]
+// grid (S row chunks, C/64), 256 threads = 64 channels x 4 pixel lanes.  Partials are reduced by
+// wgrad_small_reduce_kernel:  head  dW[co][ci][tap] = K[ci][tap][co],   db = Fsum
+//                             tail  dW[co][ci][tap] = K[co][8-tap][ci], db = Isum
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+wgrad_small_kernel(const float* __restrict__ I, const T* __restrict__ F, float* __restrict__ kpart,
+                   float* __restrict__ fsum_part, float* __restrict__ isum_part, int B, int H, int W, int C, int C3) {
+  extern __shared__ float sm[];  // is[C3][3][W+2] then red[4][28][64]
+  float* is = sm;
+  float* red = sm + 3 * 3 * (W + 2);
+  const int tid = threadIdx.x, c = tid & 63, pl = tid >> 6;
+  const int S = gridDim.x, s = blockIdx.x, cb = blockIdx.y * 64;
+  const long long rows = static_cast<long long>(B) * H;
+  const long long r0 = rows * s / S, r1 = rows * (s + 1) / S;
+  float acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+  float fs = 0.f, isum = 0.f;
+  const int Wp = W + 2;
+  for (long long row = r0; row < r1; ++row) {
+    const int b = static_cast<int>(row / H), y = static_cast<int>(row % H);
+    __syncthreads();
+    for (int i = tid; i < 9 * Wp; i += 256) {
+      const int px = i % Wp, dy = (i / Wp) % 3, c3 = i / (3 * Wp);
+      const int yy = y + dy - 1, xx = px - 1;
+      is[i] = (c3 < C3 && yy >= 0 && yy < H && xx >= 0 && xx < W) ? I[((static_cast<size_t>(b) * C3 + c3) * H + yy) * W + xx] : 0.f;
+    }
+    __syncthreads();
+    if (tid < C3) {
+      float t = 0.f;
+      for (int x = 0; x < W; ++x) t += is[(tid * 3 + 1) * Wp + x + 1];
+      isum += t;
+    }
+    const T* frow = F + (static_cast<size_t>(b) * H + y) * W * C + cb + c;
+    for (int x = pl; x < W; x += 4) {
+      const float f = static_cast<float>(frow[static_cast<size_t>(x) * C]);
+      fs += f;
+#pragma unroll
+      for (int c3 = 0; c3 < 3; ++c3)
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) acc[c3 * 9 + dy * 3 + dx] = fmaf(f, is[(c3 * 3 + dy) * Wp + x + dx], acc[c3 * 9 + dy * 3 + dx]);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 27; ++i) red[(pl * 28 + i) * 64 + c] = acc[i];
+  red[(pl * 28 + 27) * 64 + c] = fs;
+  __syncthreads();
+  if (pl == 0) {
+    for (int i = 0; i < 28; ++i) {
+      const float t = ((red[(0 * 28 + i) * 64 + c] + red[(1 * 28 + i) * 64 + c]) + red[(2 * 28 + i) * 64 + c]) +
+                      red[(3 * 28 + i) * 64 + c];
+      if (i < 27) kpart[(static_cast<size_t>(s) * 27 + i) * C + cb + c] = t;
+      else fsum_part[static_cast<size_t>(s) * C + cb + c] = t;
+    }
+  }
+  if (tid < C3 && blockIdx.y == 0) isum_part[static_cast<size_t>(s) * 4 + tid] = isum;
+}
+
+__global__ void wgrad_small_reduce_kernel(const float* __restrict__ kpart, const float* __restrict__ fsum_part,
+                                          const float* __restrict__ isum_part, int S, int C, int C3, int tail_mode,
+                                          float* __restrict__ dw, float* __restrict__ db) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = C3 * 9 * C;
+  if (idx < total) {
+    const int c = idx % C, t = (idx / C) % 9, c3 = idx / (9 * C);
+    float v = 0.f;
+    for (int s = 0; s < S; ++s) v += kpart[(static_cast<size_t>(s) * 27 + c3 * 9 + t) * C + c];
+    if (tail_mode) dw[(static_cast<size_t>(c3) * C + c) * 9 + (8 - t)] = v;   // [co=c3][ci=c][tap]
+    else dw[(static_cast<size_t>(c) * C3 + c3) * 9 + t] = v;                   // [co=c][ci=c3][tap]
+  }
+  const int nb = tail_mode ? C3 : C;
+  if (idx < nb) {
+    float v = 0.f;
+    for (int s = 0; s < S; ++s) v += tail_mode ? isum_part[static_cast<size_t>(s) * 4 + idx] : fsum_part[static_cast<size_t>(s) * C + idx];
+    db[idx] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Parameter gradients of every block's attention MLPs from the stored per-image signals: grid = nblk CTAs,
+// each loops over the batch in a fixed order (deterministic).  Dynamic smem: hq[B][Hid], dhq[B][Hid].
+// ------------------------------------------------------------------------------------------------
+struct AttnGradArgs {
+  const float* sig; int sig_stride;      // [nblk][B][sig_stride]
+  const float* attributes; int A;        // [B][A]
+  const float* meta_w1; const float* meta_b1; const float* meta_w2;  // packed [nblk][Hid][M], [nblk][Hid], [nblk][C][Hid]
+  const int* q_enabled;
+  float* const* ca_g;                    // [nblk*4] W1, b1, W2, b2 gradients (nullptr table = no channel attention)
+  float* const* meta_g;                  // [nblk*4] FC1 w, b, FC2 w, b gradients (NULL entries where no q layer)
+  int B, C, R, M, Hid, style, meta_relu;
+};
+
+__global__ void __launch_bounds__(256) attn_param_grads_kernel(AttnGradArgs a) {
+  extern __shared__ float sm[];
+  const int blk = blockIdx.x, tid = threadIdx.x;
+  const int B = a.B, C = a.C, R = a.R, M = a.M, Hid = a.Hid;
+  const float* sig = a.sig + static_cast<size_t>(blk) * B * a.sig_stride;
+  const int o_y = 0, o_h = C, o_dz2 = C + R, o_dh = 2 * C + R, o_dzq = 2 * C + 2 * R;
+  if (a.style != DFIR_STYLE_NONE && a.ca_g != nullptr) {
+    const int Cin = (a.style == DFIR_STYLE_MAX_CONCAT) ? C + M : C;
+    float* gW1 = a.ca_g[blk * 4 + 0]; float* gb1 = a.ca_g[blk * 4 + 1];
+    float* gW2 = a.ca_g[blk * 4 + 2]; float* gb2 = a.ca_g[blk * 4 + 3];
+    for (int e = tid; e < C * R; e += 256) {
+      const int c = e / R, j = e % R;
+      float t = 0.f;
+      for (int b = 0; b < B; ++b) t = fmaf(sig[b * a.sig_stride + o_dz2 + c], sig[b * a.sig_stride + o_h + j], t);
+      gW2[e] = t;
+    }
+    for (int c = tid; c < C; c += 256) {
+      float t = 0.f;
+      for (int b = 0; b < B; ++b) t += sig[b * a.sig_stride + o_dz2 + c];
+      gb2[c] = t;
+    }
+    for (int e = tid; e < R * Cin; e += 256) {
+      const int j = e / Cin, i = e % Cin;
+      float t = 0.f;
+      for (int b = 0; b < B; ++b) {
+        const float in = i < C ? sig[b * a.sig_stride + o_y + i] : a.attributes[static_cast<size_t>(b) * a.A + (i - C)];
+        t = fmaf(sig[b * a.sig_stride + o_dh + j], in, t);
+      }
+      gW1[e] = t;
+    }
+    for (int j = tid; j < R; j += 256) {
+      float t = 0.f;
+      for (int b = 0; b < B; ++b) t += sig[b * a.sig_stride + o_dh + j];
+      gb1[j] = t;
+    }
+  }
+  if (a.meta_g == nullptr || a.q_enabled == nullptr || a.q_enabled[blk] == 0) return;
+  float* gV1 = a.meta_g[blk * 4 + 0]; float* gc1 = a.meta_g[blk * 4 + 1];
+  float* gV2 = a.meta_g[blk * 4 + 2]; float* gc2 = a.meta_g[blk * 4 + 3];
+  if (gV1 == nullptr) return;
+  const float* V1 = a.meta_w1 + static_cast<size_t>(blk) * Hid * M;
+  const float* c1 = a.meta_b1 + static_cast<size_t>(blk) * Hid;
+  const float* V2 = a.meta_w2 + static_cast<size_t>(blk) * C * Hid;
+  float* hq = sm;             // [B][Hid]
+  float* dhq = sm + B * Hid;  // [B][Hid]
+  for (int e = tid; e < B * Hid; e += 256) {
+    const int b = e / Hid, j = e % Hid;
+    float s = c1[j];
+    for (int i = 0; i < M; ++i) s = fmaf(V1[j * M + i], a.attributes[static_cast<size_t>(b) * a.A + i], s);
+    const float hv = a.meta_relu ? fmaxf(s, 0.f) : s;
+    hq[e] = hv;
+    float d = 0.f;
+    for (int c = 0; c < C; ++c) d = fmaf(V2[static_cast<size_t>(c) * Hid + j], sig[b * a.sig_stride + o_dzq + c], d);
+    dhq[e] = (a.meta_relu && !(s > 0.f)) ? 0.f : d;
+  }
+  __syncthreads();
+  for (int e = tid; e < C * Hid; e += 256) {
+    const int c = e / Hid, j = e % Hid;
+    float t = 0.f;
+    for (int b = 0; b < B; ++b) t = fmaf(sig[b * a.sig_stride + o_dzq + c], hq[b * Hid + j], t);
+    gV2[e] = t;
+  }
+  for (int c = tid; c < C; c += 256) {
+    float t = 0.f;
+    for (int b = 0; b < B; ++b) t += sig[b * a.sig_stride + o_dzq + c];
+    gc2[c] = t;
+  }
+  for (int e = tid; e < Hid * M; e += 256) {
+    const int j = e / M, i = e % M;
+    float t = 0.f;
+    for (int b = 0; b < B; ++b) t = fmaf(dhq[b * Hid + j], a.attributes[static_cast<size_t>(b) * a.A + i], t);
+    gV1[e] = t;
+  }
+  for (int j = tid; j < Hid; j += 256) {
+    float t = 0.f;
+    for (int b = 0; b < B; ++b) t += dhq[b * Hid + j];
+    gc1[j] = t;
+  }
+}
+
+unsigned grid_for(long long n, int per_block = 256, long long cap = 148 * 16) {
+  long long g = (n + per_block - 1) / per_block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<unsigned>(g);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ host wrappers
+int pack_bf16_multi(const float* const* tbl, const float* direct, void* out, int n_tiles, int cout, int nt_rows,
+                    int per_src, int transpose, cudaStream_t s, int j0) {
+  if (n_tiles <= 0) return DFIR_OK;
+  dim3 grid((9 * nt_rows * 64 + 255) / 256, n_tiles);
+  pack_bf16_multi_kernel<<<grid, 256, 0, s>>>(tbl, direct, reinterpret_cast<__nv_bfloat16*>(out), cout, nt_rows, per_src,
+                                              transpose, j0);
+  return ok_or_cuda3();
+}
+
+int pack_f32_multi(const float* const* tbl, const float* direct, float* out, int n, int cout, int cin, int transpose,
+                   cudaStream_t s) {
+  if (n <= 0) return DFIR_OK;
+  dim3 grid((9 * cin * cout + 255) / 256, n);
+  pack_f32_multi_kernel<<<grid, 256, 0, s>>>(tbl, direct, out, cout, cin, transpose);
+  return ok_or_cuda3();
+}
+
+int gather_strided(const float* const* tbl, const float* direct, int tbl_stride, int tbl_off, float* out, int n_rows,
+                   int n, int per_src, int src_stride, long long out_stride, cudaStream_t s) {
+  if (n_rows <= 0 || n <= 0) return DFIR_OK;
+  dim3 grid(std::min((n + 255) / 256, 64), n_rows);
+  gather_strided_kernel<<<grid, 256, 0, s>>>(tbl, direct, tbl_stride, tbl_off, out, n, per_src, src_stride, out_stride);
+  return ok_or_cuda3();
+}
+
+int bwd_reduce_chunks(int HW) { return std::max(1, std::min(32, HW / 256)); }
+
+int bwd_reduce_gr(const float* g, const void* r, int r_is_bf16, float* part, int B, int HW, int C, cudaStream_t s) {
+  if (C % 8 != 0 || C > 256 || 256 % (C / 8) != 0) return DFIR_ERR_ARG;
+  const int nchunk = bwd_reduce_chunks(HW);
+  dim3 grid(nchunk, B);
+  if (r_is_bf16)
+    bwd_reduce_gr_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(g, reinterpret_cast<const __nv_bfloat16*>(r), part, HW, C, nchunk);
+  else
+    bwd_reduce_gr_kernel<float><<<grid, 256, 0, s>>>(g, reinterpret_cast<const float*>(r), part, HW, C, nchunk);
+  return ok_or_cuda3();
+}
+
+int ca_backward(const float* part, const float* pool_rows, int pool_nrows, int HW, const AttnParams& ap,
+                const float* attributes, const float* sq, float out_scale, float* svec, float* dyv, float* sig,
+                int sig_stride, int B, cudaStream_t s) {
+  if (ap.C > 256 || 256 % ap.C != 0 || ap.R > 64 || ap.A > 512) return DFIR_ERR_ARG;
+  if (ap.style != DFIR_STYLE_NONE && ap.style != DFIR_STYLE_STANDARD && ap.style != DFIR_STYLE_MODULATE &&
+      ap.style != DFIR_STYLE_MAX_CONCAT)
+    return DFIR_ERR_ARG;
+  CaBwdArgs a{};
+  a.part = part; a.nchunk = bwd_reduce_chunks(HW); a.pool_rows = pool_rows; a.pool_nrows = pool_nrows; a.HW = HW;
+  a.style = ap.style; a.C = ap.C; a.R = ap.R; a.M = ap.M; a.A = ap.A; a.ca = ap.w[0];
+  a.attributes = attributes; a.sq = sq; a.out_scale = out_scale; a.svec = svec; a.dyv = dyv; a.sig = sig;
+  a.sig_stride = sig_stride;
+  ca_backward_kernel<<<B, 128, 0, s>>>(a);
+  return ok_or_cuda3();
+}
+
+int form_dr(const float* g, const float* svec, const float* dyv, void* dr, int dr_is_bf16, int B, int HW, int C,
+            cudaStream_t s) {
+  const long long nvec = static_cast<long long>(HW) * (C / 8);
+  long long per_img = std::max<long long>(1, std::min<long long>((nvec + 2047) / 2048, (592 + B - 1) / B));
+  dim3 grid(static_cast<unsigned>(per_img), B);
+  if (dr_is_bf16) form_dr_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(g, svec, dyv, reinterpret_cast<__nv_bfloat16*>(dr), HW, C);
+  else form_dr_kernel<float><<<grid, 256, 0, s>>>(g, svec, dyv, reinterpret_cast<float*>(dr), HW, C);
+  return ok_or_cuda3();
+}
+
+int add_f32(const float* a, const float* b, float* out, void* out_bf16, long long n, cudaStream_t s) {
+  if (n % 4 != 0) return DFIR_ERR_ARG;
+  if (n == 0) return DFIR_OK;
+  add_f32_kernel<<<grid_for(n / 4), 256, 0, s>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
+                                                 reinterpret_cast<float4*>(out), reinterpret_cast<uint2*>(out_bf16), n / 4);
+  return ok_or_cuda3();
+}
+
+int pixel_unshuffle_f32(const float* in, float* out, int B, int h, int w, int C, int r, cudaStream_t s) {
+  const long long n = static_cast<long long>(B) * h * w * C * r * r;
+  if (n == 0) return DFIR_OK;
+  pixel_unshuffle_f32_kernel<<<grid_for(n), 256, 0, s>>>(in, out, B, h, w, C, r);
+  return ok_or_cuda3();
+}
+
+int wgrad_f32_chunks(int B, int H, int Cin, int Cout) {
+  const long long rows = static_cast<long long>(B) * H;
+  const long long per = static_cast<long long>(9) * Cin * Cout * 4;
+  long long S = std::min<long long>(rows, std::max<long long>(1, (48ll << 20) / per));
+  const long long tiles = static_cast<long long>((Cin + 15) / 16) * ((Cout + 63) / 64);
+  S = std::min<long long>(S, std::max<long long>(1, 592 / tiles));
+  return static_cast<int>(std::max<long long>(1, S));
+}
+
+size_t wgrad_scratch_floats(int S, int Cin, int Cout) { return static_cast<size_t>(S) * (9ull * Cin * Cout + Cout); }
+
+int wgrad_f32(const float* dY, const float* X, float* scratch, int B, int H, int W, int Cin, int Cout, cudaStream_t s,
+              int* S_out) {
+  const int S = wgrad_f32_chunks(B, H, Cin, Cout);
+  *S_out = S;
+  dim3 grid(S, (Cin + 15) / 16, (Cout + 63) / 64);
+  float* dbpart = scratch + static_cast<size_t>(S) * 9 * Cin * Cout;
+  wgrad_f32_kernel<<<grid, 256, 0, s>>>(dY, X, scratch, dbpart, B, H, W, Cin, Cout);
+  return ok_or_cuda3();
+}
+
+int wgrad_reduce(const float* part, const float* dbpart, int S, int Cin, int n_rows, float* const* w_tbl, int w_idx,
+                 float* w_direct, float* const* b_tbl, int b_idx, float* b_direct, int co_begin, int co_stride,
+                 cudaStream_t s) {
+  const int total = 9 * Cin * n_rows;
+  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(part, dbpart, S, Cin, n_rows, w_tbl, w_idx, w_direct, b_tbl,
+                                                          b_idx, b_direct, co_begin, co_stride);
+  return ok_or_cuda3();
+}
+
+int wgrad_small_chunks(int B, int H) { return static_cast<int>(std::min<long long>(static_cast<long long>(B) * H, 296)); }
+size_t wgrad_small_scratch_floats(int B, int H, int C) {
+  return static_cast<size_t>(wgrad_small_chunks(B, H)) * (27ull * C + C + 4);
+}
+
+int wgrad_small(const float* I, const void* F, int f_is_bf16, float* scratch, int B, int H, int W, int C, int C3,
+                int tail_mode, float* dw, float* db, cudaStream_t s) {
+  if (C % 64 != 0 || C3 > 3 || C3 < 1) return DFIR_ERR_ARG;
+  const int S = wgrad_small_chunks(B, H);
+  float* kpart = scratch;
+  float* fsum = kpart + static_cast<size_t>(S) * 27 * C;
+  float* isum = fsum + static_cast<size_t>(S) * C;
+  const size_t smem = (static_cast<size_t>(9) * (W + 2) + 4 * 28 * 64) * 4;
+  if (smem > 200 * 1024) return DFIR_ERR_ARG;
+  dim3 grid(S, C / 64);
+  if (f_is_bf16) {
+    auto k = wgrad_small_kernel<__nv_bfloat16>;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+      return DFIR_ERR_CUDA;
+    k<<<grid, 256, smem, s>>>(I, reinterpret_cast<const __nv_bfloat16*>(F), kpart, fsum, isum, B, H, W, C, C3);
+  } else {
+    auto k = wgrad_small_kernel<float>;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+      return DFIR_ERR_CUDA;
+    k<<<grid, 256, smem, s>>>(I, reinterpret_cast<const float*>(F), kpart, fsum, isum, B, H, W, C, C3);
+  }
+  if (cudaGetLastError() != cudaSuccess) return DFIR_ERR_CUDA;
+  const int total = C3 * 9 * C;
+  wgrad_small_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(kpart, fsum, isum, S, C, C3, tail_mode, dw, db);
+  return ok_or_cuda3();
+}
+
+int attn_param_grads(const float* sig, int sig_stride, const float* attributes, int A, const float* meta_w1,
+                     const float* meta_b1, const float* meta_w2, const int* q_enabled, float* const* ca_g,
+                     float* const* meta_g, int nblk, int B, int C, int R, int M, int Hid, int style, int meta_relu,
+                     cudaStream_t s) {
+  if (nblk <= 0) return DFIR_OK;
+  AttnGradArgs a{};
+  a.sig = sig; a.sig_stride = sig_stride; a.attributes = attributes; a.A = A; a.meta_w1 = meta_w1; a.meta_b1 = meta_b1;
+  a.meta_w2 = meta_w2; a.q_enabled = q_enabled; a.ca_g = ca_g; a.meta_g = meta_g; a.B = B; a.C = C; a.R = R; a.M = M;
+  a.Hid = Hid; a.style = style; a.meta_relu = meta_relu;
+  const size_t smem = static_cast<size_t>(2) * B * std::max(1, Hid) * 4;
+  if (smem > 160 * 1024) return DFIR_ERR_ARG;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(attn_param_grads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+    return DFIR_ERR_CUDA;
+  attn_param_grads_kernel<<<nblk, 256, smem, s>>>(a);
+  return ok_or_cuda3();
+}
+
+}  // namespace dfir

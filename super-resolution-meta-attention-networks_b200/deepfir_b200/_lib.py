@@ -43,6 +43,17 @@ class QrcanNet(C.Structure):
         ("conv_b", C.c_void_p), ("up_b", C.c_void_p), ("tail_b", C.c_void_p), ("head_b", C.c_void_p),
         ("ca_blob", C.c_void_p), ("ca_stride", C.c_int),
         ("meta_w1", C.c_void_p), ("meta_b1", C.c_void_p), ("meta_w2", C.c_void_p), ("meta_b2", C.c_void_p),
+        ("conv_wT_bf16", C.c_void_p), ("conv_wT_f32", C.c_void_p), ("up_wT_f32", C.c_void_p),
+        ("tail_wT_f32", C.c_void_p),
+    ]
+
+
+class QrcanParams(C.Structure):
+    """mirror of `dfir_qrcan_params` (include/dfir.h): device pointer tables of the fp32 parameters / gradients."""
+    _fields_ = [
+        ("conv_w", C.c_void_p), ("conv_b", C.c_void_p), ("up_w", C.c_void_p), ("up_b", C.c_void_p),
+        ("tail_w", C.c_void_p), ("tail_b", C.c_void_p), ("head_w", C.c_void_p), ("head_b", C.c_void_p),
+        ("ca", C.c_void_p), ("meta", C.c_void_p),
     ]
 
 
@@ -80,6 +91,19 @@ PROTOTYPES = {
     "dfir_soca": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     "dfir_nonlocal_scratch_bytes": (_sz, [_i, _i, _i]),
     "dfir_nonlocal": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "dfir_qrcan_repack": (_i, [C.POINTER(QrcanNet), C.POINTER(QrcanParams), _i, _i, _vp]),
+    "dfir_qrcan_train_workspace_bytes": (_sz, [C.POINTER(QrcanNet), _i, _i, _i, _i]),
+    "dfir_qrcan_train_forward": (_i, [C.POINTER(QrcanNet), _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "dfir_qrcan_train_backward": (_i, [C.POINTER(QrcanNet), C.POINTER(QrcanParams), _vp, _vp, _vp, _i, _i, _i, _i, _vp,
+                                       _sz, _vp]),
+    "dfir_qrcan_train_launch_count": (C.c_longlong, [C.POINTER(QrcanNet), _i, _i, _i, _i]),
+    "dfir_conv3x3_wgrad_scratch_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "dfir_conv3x3_wgrad_c64": (_i, [_vp, _ll, _ll, _ll, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _sz, _vp]),
+    "dfir_conv3x3_wgrad_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "dfir_conv3x3_c64_dgrad": (_i, [_vp, _ll, _ll, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "dfir_pack_conv3x3_bf16_ex": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "dfir_conv3x3_wgrad_small_scratch_bytes": (_sz, [_i, _i, _i]),
+    "dfir_conv3x3_wgrad_small": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "dfir_qrcan_forward": (_i, [C.POINTER(QrcanNet), _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
 }
 

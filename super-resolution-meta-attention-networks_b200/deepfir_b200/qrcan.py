@@ -77,8 +77,8 @@ class ChannelAttentionParams(nn.Module):
                 [nn.Sequential(_fc(i, o), nn.ReLU(inplace=True)) for i, o in plan])
             self.final_conv = nn.Sequential(_fc(red, channel), nn.Sigmoid())
 
-    def flat_params(self):
-        """fp32 arrays in the order the kernels expect (csrc/simt.cu attn_vector)."""
+    def param_list(self):
+        """the nn.Parameters in the order the kernels expect (csrc/attn.cuh)"""
         if self.style in ("modulate", "max_concat", "softmax", "standard"):
             mods = [self.conv_du[0], self.conv_du[2]]
         elif self.style == "mini_concat":
@@ -87,8 +87,12 @@ class ChannelAttentionParams(nn.Module):
             mods = [s[0] for s in self.feature_convs] + [self.final_conv[0]]
         out = []
         for m in mods:
-            out += [m.weight.reshape(-1), m.bias.reshape(-1)]
+            out += [m.weight, m.bias]
         return out
+
+    def flat_params(self):
+        """fp32 arrays in the order the kernels expect (csrc/simt.cu attn_vector)."""
+        return [p.reshape(-1) for p in self.param_list()]
 
 
 class PixelAttentionParams(nn.Module):
@@ -177,11 +181,15 @@ class QRCAN(nn.Module):
         if self.cfg.get("include_pixel_attention"):
             raise NotImplementedError("pixel attention (include_pixel_attention) is not on the B200 path yet")
         from . import ops  # registers torch.ops.dfir.*
-        packed = self.packed()
+        training = torch.is_grad_enabled() and next(self.parameters()).requires_grad
+        packed = self.packed(training=training)
         b = x.shape[0]
         attr = metadata.reshape(b, -1).to(device=x.device, dtype=torch.float32).contiguous()
         if attr.shape[1] != packed.attr_size:
             raise RuntimeError("metadata has %d entries per image, network expects %d" % (attr.shape[1], packed.attr_size))
+        if training:  # forward with saved activations; backward fills every parameter's .grad (deepfir_b200/train.py)
+            from .train import qrcan_train_apply
+            return qrcan_train_apply(self, packed, x.to(torch.float32).contiguous(), attr)
         return torch.ops.dfir.qrcan_forward(x.to(torch.float32).contiguous(), attr, packed.handle,
                                             PRECISIONS[self.precision])
 
@@ -205,18 +213,29 @@ class QRCAN(nn.Module):
                      meta_hidden=(C_ // 2 if M <= 15 else (C_ - M) // 2 + M)),
             head=self.head[0], trunk=trunk, ups=[m for m in self.tail[0] if isinstance(m, nn.Conv2d)],
             tail=self.tail[1], ca=[blk.final_body.flat_params() for blk in blocks],
+            ca_params=[blk.final_body.param_list() for blk in blocks],
             meta=[tuple(blk.q_node.fcs()) if blk.q_layer else None for blk in blocks])
 
-    def _param_versions(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
-
-    def packed(self):
-        key = (self._param_versions(), self.precision, self.chunk_images, self.schedule)
-        if self._packed is None or self._packed.key != key:
-            if self._packed is not None:
-                self._packed.close()
-            self._packed = PackedQrcan(self, key)
-        return self._packed
+    def packed(self, training=False):
+        """Kernel-format parameters.  Rebuilt from scratch when a parameter's storage moved (`.to()`, new module);
+        when only the values changed (optimizer.step(), load_state_dict) they are refreshed in place by one C call
+        (`dfir_qrcan_repack`) driven by device pointer tables."""
+        params = list(self.parameters())
+        skey = (tuple(p.data_ptr() for p in params), self.precision, self.chunk_images, self.schedule)
+        vers = tuple(p._version for p in params)
+        pk = self._packed
+        if pk is None or pk.key != skey or (pk.versions != vers and not pk.can_repack):
+            if pk is not None:
+                pk.close()
+            pk = self._packed = PackedQrcan(self, skey)
+            pk.versions = vers
+        if training and not pk.train_ready:
+            pk.enable_training(self)
+            pk.versions = None
+        if pk.versions != vers:
+            pk.repack()
+            pk.versions = vers
+        return pk
 
     def _apply(self, fn, *a, **k):
         self._packed = None
@@ -270,7 +289,8 @@ class QEDSR(QRCAN):
         trunk.append(self.final_body)
         return dict(cfg=self.cfg, head=self.head, trunk=trunk,
                     ups=[m for m in self.tail[0] if isinstance(m, nn.Conv2d)], tail=self.tail[1],
-                    ca=[None for _ in self.body], meta=[tuple(blk.attention_layer.fcs()) for blk in self.body])
+                    ca=[None for _ in self.body], ca_params=[None for _ in self.body],
+                    meta=[tuple(blk.attention_layer.fcs()) for blk in self.body])
 
 
 _HANDLES = {}
@@ -405,10 +425,104 @@ class PackedQrcan:
         self.device = dev
         self.scale = net.scale
         self.out_feats = cfg["out_feats"]
+        self.precision = PRECISIONS[net.precision]
         self._ws = {}
+        self.versions = None
+        self.train_ready = False
+        self.grads = None
+        # device pointer tables of the fp32 parameters: lets the C side refresh every kernel-format buffer in a few
+        # launches (styles whose attention block has the 4-tensor layout; the others are rebuilt from Python)
+        self.can_repack = "ca_params" in spec and cfg["style"] in ("none", "standard", "modulate", "max_concat",
+                                                                   "softmax")
+        if self.can_repack:
+            self._spec_params = dict(
+                conv_w=[m.weight for m in trunk], conv_b=[m.bias for m in trunk],
+                up_w=[m.weight for m in ups], up_b=[m.bias for m in ups],
+                tail_w=tail.weight, tail_b=tail.bias, head_w=head.weight, head_b=head.bias,
+                ca=(None if ca_stride == 0 else [p for blk in spec["ca_params"] for p in blk]),
+                meta=(None if not any_q else
+                      [t for m in metas for t in ((None,) * 4 if m is None else (m[0].weight, m[0].bias, m[1].weight, m[1].bias))]))
+            self.param_tables, self.params_struct = self._make_tables(lambda p: p.data_ptr())
         self.handle = _NEXT[0]
         _NEXT[0] += 1
         _HANDLES[self.handle] = self
+
+    # ------------------------------------------------------------------ pointer tables / training
+    def _make_tables(self, addr):
+        """QrcanParams whose table entries are addr(parameter) (0 for absent tensors); returns (tensors kept alive,
+        ctypes struct)"""
+        sp = self._spec_params
+        keep = {}
+
+        def table(lst):
+            if lst is None or len(lst) == 0:
+                return None
+            t = torch.tensor([0 if p is None else addr(p) for p in lst], dtype=torch.int64, device=self.device)
+            return t
+
+        ps = _lib.QrcanParams()
+        for name in ("conv_w", "conv_b", "up_w", "up_b", "ca", "meta"):
+            keep[name] = table(sp[name])
+            setattr(ps, name, None if keep[name] is None else keep[name].data_ptr())
+        for name in ("tail_w", "tail_b", "head_w", "head_b"):
+            setattr(ps, name, addr(sp[name]))
+        return keep, ps
+
+    def repack(self):
+        lib = _lib.load_library()
+        with torch.cuda.device(self.device):
+            stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(lib.dfir_qrcan_repack(C.byref(self.desc), C.byref(self.params_struct), self.precision,
+                                             int(self.train_ready), stream), "repack")
+
+    def enable_training(self, net):
+        """Buffers that only a training step needs: data-gradient weight layouts, one flat gradient buffer with a
+        view per parameter, and the gradient pointer tables."""
+        if not self.can_repack:
+            raise NotImplementedError("training on the B200 path supports the channel-attention styles "
+                                      "none/standard/modulate/max_concat")
+        d = self.desc
+        dev = self.device
+        C_ = d.n_feats
+        r = 3 if self.scale == 3 else 2
+        n_up = len(self._spec_params["up_w"])
+        n_trunk = len(self._spec_params["conv_w"])
+        with torch.cuda.device(dev):
+            if self.precision == 0:
+                self.wT = [torch.empty((n_trunk + n_up * r * r) * 9 * 64 * 128, device=dev, dtype=torch.uint8)]
+                d.conv_wT_bf16 = self.wT[0].data_ptr()
+            else:
+                self.wT = [torch.empty(n_trunk * 9 * C_ * C_, device=dev, dtype=torch.float32),
+                           torch.empty(max(1, n_up) * 9 * r * r * C_ * C_, device=dev, dtype=torch.float32)]
+                d.conv_wT_f32, d.up_wT_f32 = self.wT[0].data_ptr(), self.wT[1].data_ptr()
+            self.wT.append(torch.empty(9 * self.out_feats * C_, device=dev, dtype=torch.float32))
+            d.tail_wT_f32 = self.wT[-1].data_ptr()
+            params = list(net.parameters())
+            offs, total = {}, 0
+            for p in params:
+                offs[id(p)] = total
+                total += (p.numel() + 3) // 4 * 4  # 16-byte aligned views
+            self.grad_params = params
+            self.grad_flat = [torch.zeros(total, device=dev, dtype=torch.float32) for _ in range(2)]
+            self.grad_views, self.grad_tables = [], []
+            for flat in self.grad_flat:
+                base = flat.data_ptr()
+                self.grad_views.append([flat[offs[id(p)]: offs[id(p)] + p.numel()].view(p.shape) for p in params])
+                self.grad_tables.append(self._make_tables(lambda p, base=base: base + 4 * offs[id(p)]))
+        self.train_ready = True
+
+    def train_workspace(self, B, H, W):
+        k = ("train", B, H, W)
+        ws = self._ws.get(k)
+        if ws is None:
+            lib = _lib.load_library()
+            n = lib.dfir_qrcan_train_workspace_bytes(C.byref(self.desc), B, H, W, self.precision)
+            if n == 0:
+                raise NotImplementedError("this network configuration has no training path on the B200 library")
+            self._ws.clear()
+            ws = torch.empty(int(n), device=self.device, dtype=torch.uint8)
+            self._ws[k] = ws
+        return ws
 
     def workspace(self, B, H, W, precision):
         k = (B, H, W, precision)

@@ -11,7 +11,30 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("grads_"))
+
+
+def grad_golden_names():
+    return sorted(f[6:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f.startswith("grads_"))
+
+
+def load_grad_golden(name):
+    """(loss, {parameter name: (norm, projections[8])}) of the reference's own backward pass"""
+    z = np.load(os.path.join(GOLDEN_DIR, "grads_" + name + ".npz"))
+    names = json.loads(bytes(z["names"]).decode())
+    return float(z["loss"]), {k: (float(z["norms"][i]), z["proj"][i]) for i, k in enumerate(names)}
+
+
+def oracle_grads(info, sd, x, meta):
+    """loss and parameter gradients of the oracle under the reference's training criterion (L1, mean) against the
+    deterministic target: autograd through the CPU restatement"""
+    from oracle.synth import synth_target
+    leaves = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    out = oracle_forward(info, leaves, x, meta)
+    y = synth_target(out.shape)
+    loss = torch.nn.functional.l1_loss(out, y)
+    loss.backward()
+    return float(loss.detach()), out.detach(), y, {k: v.grad for k, v in leaves.items() if v.grad is not None}
 
 
 def load_golden(name):
