@@ -224,11 +224,15 @@ class BaseModel(nn.Module):
 
     # -- optimisation setup ------------------------------------------------------------------
     def define_optimizer(self, lr=1e-4, optimizer_params=None):
-        params = filter(lambda p: p.requires_grad, self.net.parameters())
+        params = [p for p in self.net.parameters() if p.requires_grad]
+        # same Adam as the reference (:291-299); on CUDA parameters the single-kernel ("fused") implementation is
+        # selected: the default per-tensor loop costs ~10 ms per step over Q-RCAN's 1648 parameter tensors
+        extra = dict(fused=True) if params and all(p.is_cuda for p in params) else {}
         if optimizer_params is not None:
-            self.optimizer = optim.Adam(params, lr=lr, betas=(optimizer_params['beta_1'], optimizer_params['beta_2']))
+            self.optimizer = optim.Adam(params, lr=lr, betas=(optimizer_params['beta_1'], optimizer_params['beta_2']),
+                                        **extra)
         else:
-            self.optimizer = optim.Adam(params, lr=lr)
+            self.optimizer = optim.Adam(params, lr=lr, **extra)
 
     def define_scheduler(self, scheduler, scheduler_params):
         sched = optim.lr_scheduler

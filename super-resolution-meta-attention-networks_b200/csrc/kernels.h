@@ -105,7 +105,7 @@ int meta_attention(const float* meta, const float* w1, const float* b1, const fl
                    cudaStream_t s);
 int scale_residual(const void* r, int r_is_bf16, const float* x_in, const float* pool_rows, int pool_nrows,
                    const AttnParams& ap, const float* attributes, const float* sq, float res_scale, float* x_out,
-                   __nv_bfloat16* x_out_bf16, int B, int H, int W, int C, cudaStream_t s);
+                   __nv_bfloat16* x_out_bf16, int B, int H, int W, int C, cudaStream_t s, float* y_out = nullptr);
 int ca_from_stats(const float* pool_rows, const float* col_first, const float* col_last, const void* w2_packed,
                   const float* bias2, const AttnParams& ap, const float* attributes, const float* sq, float* svec, int B,
                   int H, int W, cudaStream_t s);
@@ -131,10 +131,10 @@ int pack_f32_multi(const float* const* tbl, const float* direct, float* out, int
 int gather_strided(const float* const* tbl, const float* direct, int tbl_stride, int tbl_off, float* out, int n_rows,
                    int n, int per_src, int src_stride, long long out_stride, cudaStream_t s);
 int bwd_reduce_chunks(int HW);
-int bwd_reduce_gr(const float* g, const void* r, int r_is_bf16, float* part, int B, int HW, int C, cudaStream_t s);
-int ca_backward(const float* part, const float* pool_rows, int pool_nrows, int HW, const AttnParams& ap,
-                const float* attributes, const float* sq, float out_scale, float* svec, float* dyv, float* sig,
-                int sig_stride, int B, cudaStream_t s);
+int bwd_reduce_ca(const float* g, const void* r, int r_is_bf16, float* part, unsigned int* tickets,
+                  const float* pool_rows, int pool_nrows, const float* ymean, int HW, const AttnParams& ap,
+                  const float* attributes, const float* sq, float out_scale, float* svec, float* dyv, float* sig,
+                  int sig_stride, int B, cudaStream_t s);
 int form_dr(const float* g, const float* svec, const float* dyv, void* dr, int dr_is_bf16, int B, int HW, int C,
             cudaStream_t s);
 int add_f32(const float* a, const float* b, float* out, void* out_bf16, long long n, cudaStream_t s);

@@ -234,7 +234,8 @@ __global__ void __launch_bounds__(256)
 scale_residual_kernel(const void* __restrict__ r_, const float* __restrict__ x_in,
                       const float* __restrict__ pool_rows, int pool_nrows, AttnParams ap,
                       const float* __restrict__ attributes, const float* __restrict__ sq, float res_scale,
-                      float* __restrict__ x_out, __nv_bfloat16* __restrict__ x_out_bf16, int HW, int C) {
+                      float* __restrict__ x_out, __nv_bfloat16* __restrict__ x_out_bf16, int HW, int C,
+                      float* __restrict__ y_out) {
   __shared__ float y_s[256];
   __shared__ float s_s[256];
   __shared__ float attr_s[512];
@@ -258,6 +259,7 @@ scale_residual_kernel(const void* __restrict__ r_, const float* __restrict__ x_i
       float t = 0.f;
       for (int gI = 0; gI < ngrp; ++gI) t += tmp[gI * C + tid];
       y_s[tid] = t / static_cast<float>(HW);
+      if (y_out != nullptr && blockIdx.x == 0) y_out[static_cast<size_t>(b) * C + tid] = y_s[tid];  // saved for backward
     }
     __syncthreads();
     attn_vector(BlockGroup{}, ap.style, ap.w[0], C, ap.R, ap.M, attr_s, y_s, s_s, tmp);
@@ -480,7 +482,7 @@ int ca_from_stats(const float* pool_rows, const float* col_first, const float* c
 
 int scale_residual(const void* r, int r_is_bf16, const float* x_in, const float* pool_rows, int pool_nrows,
                    const AttnParams& ap, const float* attributes, const float* sq, float res_scale, float* x_out,
-                   __nv_bfloat16* x_out_bf16, int B, int H, int W, int C, cudaStream_t s) {
+                   __nv_bfloat16* x_out_bf16, int B, int H, int W, int C, cudaStream_t s, float* y_out) {
   if (B == 0 || H * W == 0) return DFIR_OK;
   if (C % 8 != 0 || C > 256 || 256 % C != 0 || ap.A > 512 || ap.M > 448) return DFIR_ERR_ARG;
   const long long nvec = static_cast<long long>(H) * W * (C / 8);
@@ -491,10 +493,10 @@ int scale_residual(const void* r, int r_is_bf16, const float* x_in, const float*
   dim3 grid(static_cast<unsigned>(per_img), B);
   if (r_is_bf16)
     scale_residual_kernel<true><<<grid, 256, 0, s>>>(r, x_in, pool_rows, pool_nrows, ap, attributes, sq, res_scale,
-                                                     x_out, x_out_bf16, H * W, C);
+                                                     x_out, x_out_bf16, H * W, C, y_out);
   else
     scale_residual_kernel<false><<<grid, 256, 0, s>>>(r, x_in, pool_rows, pool_nrows, ap, attributes, sq, res_scale,
-                                                      x_out, x_out_bf16, H * W, C);
+                                                      x_out, x_out_bf16, H * W, C, y_out);
   return ok_or_cuda();
 }
 

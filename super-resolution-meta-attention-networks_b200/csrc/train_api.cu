@@ -59,6 +59,7 @@ struct TrainWs {
   uint8_t *DR, *DZ, *Gop, *DFop;     // operand-format gradients
   float* wpart; size_t wpart_floats; // weight-gradient partial sums
   float *red, *svec, *dyv, *sig; int sig_stride;
+  float* ymean; unsigned int* tickets;   // [nblk][B][C] pooled means saved by the forward; per-image tickets
   uint8_t* DUop[2]; float* DU32; float* DYF;
   float* small;
   size_t total;
@@ -132,6 +133,8 @@ TrainWs carve_train(const dfir_qrcan_net* n, int B, int H, int W, int precision,
   w.dyv = c.take<float>(static_cast<size_t>(B) * C * 4);
   w.sig_stride = 3 * C + 2 * std::max(1, n->reduced);
   w.sig = c.take<float>(static_cast<size_t>(nblk) * B * w.sig_stride * 4);
+  w.ymean = c.take<float>(static_cast<size_t>(nblk) * B * C * 4);
+  w.tickets = c.take<unsigned int>(static_cast<size_t>(B) * 4);
   w.DUop[0] = c.take<uint8_t>(top * elt);
   w.DUop[1] = c.take<uint8_t>(top / (static_cast<size_t>(r) * r) * elt);
   if (tc) w.DU32 = c.take<float>(top / (static_cast<size_t>(r) * r) * 4);
@@ -168,6 +171,7 @@ struct Ctx {
   float* pool(int k) const { return w.pool + static_cast<size_t>(k) * w.pool_stride; }
   const float* sq(int k) const { return n->any_q ? w.sq + static_cast<size_t>(k) * B * C : nullptr; }
   float* sig(int k) const { return w.sig + static_cast<size_t>(k) * B * w.sig_stride; }
+  float* ymean(int k) const { return w.ymean + static_cast<size_t>(k) * B * C; }
 };
 
 int make_ctx(Ctx& c, const dfir_qrcan_net* n, int B, int H, int W, int precision, void* ws, size_t ws_bytes, void* stream) {
@@ -232,7 +236,7 @@ int train_forward_tc(const Ctx& c, const float* x, const float* attr, float* out
       DFIR_TRY(conv3x3_c64_tc(c2, c.st));
       uint8_t* next_bf = (b + 1 < c.nb) ? c.XIN(k + 1) : c.XLAST(g);
       DFIR_TRY(scale_residual(c.R(k), 1, b == 0 ? skip32 : w.XB, c.pool(k), c.nseg * H, make_ap(n, k), attr, c.sq(k), 1.f,
-                              w.XB, reinterpret_cast<__nv_bfloat16*>(next_bf), c.B, H, W, C, c.st));
+                              w.XB, reinterpret_cast<__nv_bfloat16*>(next_bf), c.B, H, W, C, c.st, c.ymean(k)));
     }
     if (!n->no_group_conv) {
       const int wg = g * c.per_group + 2 * c.nb;
@@ -295,7 +299,7 @@ int train_forward_f32(const Ctx& c, const float* x, const float* attr, float* ou
       if (c.has_ca) DFIR_TRY(pool_rows_f32(F32(c.R(k)), c.pool(k), B, H, W, C, c.st));
       float* next = (b + 1 < c.nb) ? F32(c.XIN(k + 1)) : F32(c.XLAST(g));
       DFIR_TRY(scale_residual(c.R(k), 0, F32(c.XIN(k)), c.pool(k), H, make_ap(n, k), attr, c.sq(k), 1.f, next, nullptr, B,
-                              H, W, C, c.st));
+                              H, W, C, c.st, c.ymean(k)));
     }
     if (!n->no_group_conv) {
       float* o = (g + 1 < c.ng) ? F32(c.XIN((g + 1) * c.nb)) : F32(c.TRUNK_IN());
@@ -395,9 +399,8 @@ int train_backward_tc(const Ctx& c, const dfir_qrcan_params* gr, const float* x,
     for (int b = c.nb - 1; b >= 0; --b) {
       const int k = g * c.nb + b;
       const int w1 = g * c.per_group + 2 * b, w2 = w1 + 1;
-      DFIR_TRY(bwd_reduce_gr(gsp, c.R(k), 1, w.red, B, HW, C, c.st));
-      DFIR_TRY(ca_backward(w.red, c.pool(k), c.nseg * H, HW, make_ap(n, k), attr, c.sq(k), out_scale, w.svec, w.dyv,
-                           c.sig(k), w.sig_stride, B, c.st));
+      DFIR_TRY(bwd_reduce_ca(gsp, c.R(k), 1, w.red, w.tickets, c.pool(k), c.nseg * H, c.has_ca ? c.ymean(k) : nullptr, HW,
+                             make_ap(n, k), attr, c.sq(k), out_scale, w.svec, w.dyv, c.sig(k), w.sig_stride, B, c.st));
       DFIR_TRY(form_dr(gsp, w.svec, c.has_ca ? w.dyv : nullptr, w.DR, 1, B, HW, C, c.st));
       DFIR_TRY(wgrad_tc(c, gr, w.DR, c.T(k), w2));
       {
@@ -467,9 +470,8 @@ int train_backward_f32(const Ctx& c, const dfir_qrcan_params* gr, const float* x
     for (int b = c.nb - 1; b >= 0; --b) {
       const int k = g * c.nb + b;
       const int w1 = g * c.per_group + 2 * b, w2 = w1 + 1;
-      DFIR_TRY(bwd_reduce_gr(gsp, c.R(k), 0, w.red, B, HW, C, c.st));
-      DFIR_TRY(ca_backward(w.red, c.pool(k), H, HW, make_ap(n, k), attr, c.sq(k), out_scale, w.svec, w.dyv, c.sig(k),
-                           w.sig_stride, B, c.st));
+      DFIR_TRY(bwd_reduce_ca(gsp, c.R(k), 0, w.red, w.tickets, c.pool(k), H, c.has_ca ? c.ymean(k) : nullptr, HW,
+                             make_ap(n, k), attr, c.sq(k), out_scale, w.svec, w.dyv, c.sig(k), w.sig_stride, B, c.st));
       DFIR_TRY(form_dr(gsp, w.svec, c.has_ca ? w.dyv : nullptr, w.DR, 0, B, HW, C, c.st));
       DFIR_TRY(wgrad_f(c, gr, F32(w.DR), F32(c.T(k)), w2));
       DFIR_TRY(dgrad(F32(w.DR), w2, nullptr, F32(c.T(k)), F32(w.DZ)));
@@ -595,11 +597,11 @@ long long dfir_qrcan_train_launch_count(const dfir_qrcan_net* n, int B, int H, i
   const long long ca = n->style != DFIR_STYLE_NONE ? 1 : 0;
   if (precision == DFIR_PREC_BF16_TC) {
     const long long fwd = 1 + (n->any_q ? 1 : 0) + nblk * 3 + ngc + 1 + nup * r * r + 1;
-    const long long bwd = 3 + nup * r * r * 3 + 3 + ngc * 4 + nblk * 9 + 1 + 2 + 1;
+    const long long bwd = 3 + nup * r * r * 3 + 3 + ngc * 4 + nblk * 8 + 1 + 2 + 1;
     return fwd + bwd;
   }
   const long long fwd = 1 + (n->any_q ? 1 : 0) + nblk * (3 + ca) + ngc + 1 + nup + 1;
-  const long long bwd = 3 + nup * 4 + 3 + ngc * 4 + nblk * 9 + 1 + 2 + 1;
+  const long long bwd = 3 + nup * 4 + 3 + ngc * 4 + nblk * 8 + 1 + 2 + 1;
   return fwd + bwd;
 }
 
@@ -618,6 +620,7 @@ int dfir_qrcan_train_backward(const dfir_qrcan_net* net, const dfir_qrcan_params
   if (grads == nullptr || x == nullptr || attributes == nullptr || grad_out == nullptr) return DFIR_ERR_ARG;
   Ctx c;
   DFIR_TRY(make_ctx(c, net, B, H, W, precision, workspace, workspace_bytes, stream));
+  if (cudaMemsetAsync(c.w.tickets, 0, static_cast<size_t>(B) * 4, c.st) != cudaSuccess) return DFIR_ERR_CUDA;
   if (c.tc && (net->conv_wT_bf16 == nullptr || net->tail_wT_f32 == nullptr)) return DFIR_ERR_ARG;
   if (!c.tc && (net->conv_wT_f32 == nullptr || net->up_wT_f32 == nullptr || net->tail_wT_f32 == nullptr)) return DFIR_ERR_ARG;
   return c.tc ? train_backward_tc(c, grads, x, attributes, grad_out) : train_backward_f32(c, grads, x, attributes, grad_out);

@@ -112,10 +112,12 @@ __global__ void gather_strided_kernel(const float* const* __restrict__ tbl, cons
 // part[b][chunk][c] = sum over the chunk's pixels of g * r      (d loss / d attention scale, before the batch of
 // tiny MLP backward kernels).  HBM-bound: reads 4 + sizeof(T) bytes per element once, fully coalesced.
 // ------------------------------------------------------------------------------------------------
+struct CaBwdArgs;
+__device__ void ca_backward_image(const CaBwdArgs& a, const int b, const int tid, const int NT);
+
 template <typename T>
-__global__ void __launch_bounds__(256)
-bwd_reduce_gr_kernel(const float* __restrict__ g, const T* __restrict__ r, float* __restrict__ part, int HW, int C,
-                     int nchunk) {
+__device__ __forceinline__ void bwd_reduce_gr_body(const float* __restrict__ g, const T* __restrict__ r,
+                                                   float* __restrict__ part, int HW, int C, int nchunk) {
   __shared__ float sh[2048];
   const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
   const int lpp = C / 8, npl = 256 / lpp;
@@ -158,20 +160,21 @@ struct CaBwdArgs {
   const float* sq;          // [B][C] meta scale of this block incl. out_scale, or nullptr
   float out_scale;          // factor folded into sq (ParamResBlock res_scale), 1 otherwise
   float* svec; float* dyv; float* sig; int sig_stride;
+  const float* ymean;       // [B][C] pooled means saved by the forward (optional; else rebuilt from pool_rows)
 };
 
-__global__ void __launch_bounds__(128) ca_backward_kernel(CaBwdArgs a) {
+__device__ void ca_backward_image(const CaBwdArgs& a, const int b, const int tid, const int NT) {
   __shared__ float ds[256], y[256], dz2[256], attr[512], h[64], dh[64], tmp[512];
-  const int b = blockIdx.x, tid = threadIdx.x, C = a.C, R = a.R;
-  for (int c = tid; c < C; c += 128) {
+  const int C = a.C, R = a.R;
+  for (int c = tid; c < C; c += NT) {
     float t = 0.f;
-    for (int k = 0; k < a.nchunk; ++k) t += a.part[(static_cast<size_t>(b) * a.nchunk + k) * C + c];
+    for (int k = 0; k < a.nchunk; ++k) t += __ldcg(&a.part[(static_cast<size_t>(b) * a.nchunk + k) * C + c]);
     ds[c] = t;
   }
   float* sig = a.sig + static_cast<size_t>(b) * a.sig_stride;
   if (a.style == DFIR_STYLE_NONE) {
     __syncthreads();
-    for (int c = tid; c < C; c += 128) {
+    for (int c = tid; c < C; c += NT) {
       const float sqv = a.sq != nullptr ? a.sq[static_cast<size_t>(b) * C + c] : a.out_scale;
       a.svec[static_cast<size_t>(b) * C + c] = sqv;
       const float sg = sqv / a.out_scale;  // sigmoid output
@@ -181,26 +184,30 @@ __global__ void __launch_bounds__(128) ca_backward_kernel(CaBwdArgs a) {
   }
   const int Cin = (a.style == DFIR_STYLE_MAX_CONCAT) ? C + a.M : C;
   const float* W1 = a.ca; const float* b1 = W1 + R * Cin; const float* W2 = b1 + R; const float* b2 = W2 + C * R;
-  // pooled mean, same fixed summation order as the forward streamer (simt.cu scale_residual_kernel)
-  {
+  // pooled mean: saved by the forward, or rebuilt in the same fixed summation order as the forward streamer
+  if (a.ymean != nullptr) {
+    for (int c = tid; c < C; c += NT) y[c] = a.ymean[static_cast<size_t>(b) * C + c];
+    for (int i = tid; i < a.A; i += NT) attr[i] = a.attributes[static_cast<size_t>(b) * a.A + i];
+    __syncthreads();
+  } else {
     const int ngrp = 256 / C;
-    for (int i = tid; i < ngrp * C; i += 128) {
+    for (int i = tid; i < ngrp * C; i += NT) {
       const int c = i % C, grp = i / C;
       const float* pr = a.pool_rows + static_cast<size_t>(b) * a.pool_nrows * C + c;
       float s = 0.f;
       for (int row = grp; row < a.pool_nrows; row += ngrp) s += pr[static_cast<size_t>(row) * C];
       tmp[i] = s;
     }
-    for (int i = tid; i < a.A; i += 128) attr[i] = a.attributes[static_cast<size_t>(b) * a.A + i];
+    for (int i = tid; i < a.A; i += NT) attr[i] = a.attributes[static_cast<size_t>(b) * a.A + i];
     __syncthreads();
-    for (int c = tid; c < C; c += 128) {
+    for (int c = tid; c < C; c += NT) {
       float t = 0.f;
       for (int gI = 0; gI < ngrp; ++gI) t += tmp[gI * C + c];
       y[c] = t / static_cast<float>(a.HW);
     }
     __syncthreads();
   }
-  for (int j = tid; j < R; j += 128) {
+  for (int j = tid; j < R; j += NT) {
     const float* wr = W1 + static_cast<size_t>(j) * Cin;
     float s = b1[j];
     for (int i = 0; i < C; ++i) s = fmaf(wr[i], y[i], s);
@@ -208,7 +215,7 @@ __global__ void __launch_bounds__(128) ca_backward_kernel(CaBwdArgs a) {
     h[j] = fmaxf(s, 0.f);
   }
   __syncthreads();
-  for (int c = tid; c < C; c += 128) {
+  for (int c = tid; c < C; c += NT) {
     const float* wr = W2 + static_cast<size_t>(c) * R;
     float s = b2[c];
     for (int j = 0; j < R; ++j) s = fmaf(wr[j], h[j], s);
@@ -224,23 +231,42 @@ __global__ void __launch_bounds__(128) ca_backward_kernel(CaBwdArgs a) {
     dz2[c] = d_sca * mod * sg * (1.f - sg);
   }
   __syncthreads();
-  for (int j = tid; j < R; j += 128) {
+  for (int j = tid; j < R; j += NT) {
     float s = 0.f;
     for (int c = 0; c < C; ++c) s = fmaf(W2[static_cast<size_t>(c) * R + j], dz2[c], s);
     dh[j] = h[j] > 0.f ? s : 0.f;
   }
   __syncthreads();
-  for (int c = tid; c < C; c += 128) {
+  for (int c = tid; c < C; c += NT) {
     float s = 0.f;
     for (int j = 0; j < R; ++j) s = fmaf(W1[static_cast<size_t>(j) * Cin + c], dh[j], s);
     a.dyv[static_cast<size_t>(b) * C + c] = s / static_cast<float>(a.HW);
     sig[c] = y[c];
     sig[C + R + c] = dz2[c];
   }
-  for (int j = tid; j < R; j += 128) {
+  for (int j = tid; j < R; j += NT) {
     sig[C + j] = h[j];
     sig[2 * C + R + j] = dh[j];
   }
+}
+
+// One launch for "ds = sum g*r" and the attention-MLP backward: the chunk CTA that finishes an image last (atomic
+// ticket per image, self-resetting) runs ca_backward_image for it.  Deterministic: the partials are combined in chunk
+// order whoever does it.
+template <typename T>
+__global__ void __launch_bounds__(256)
+bwd_reduce_ca_kernel(const float* __restrict__ g, const T* __restrict__ r, float* __restrict__ part, int HW, int C,
+                     int nchunk, CaBwdArgs a, unsigned int* __restrict__ tickets) {
+  bwd_reduce_gr_body<T>(g, r, part, HW, C, nchunk);
+  __shared__ unsigned int last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&tickets[blockIdx.y], 1u) == static_cast<unsigned>(nchunk - 1) ? 1u : 0u;
+  __syncthreads();
+  if (last == 0u) return;
+  __threadfence();
+  if (threadIdx.x == 0) tickets[blockIdx.y] = 0u;
+  ca_backward_image(a, blockIdx.y, threadIdx.x, 256);
 }
 
 // dr = g * s[b][c] + dyv[b][c]   (dL/d conv2 output of the block), written in the operand format T
@@ -377,24 +403,42 @@ wgrad_f32_kernel(const float* __restrict__ dY, const float* __restrict__ X, floa
 
 // dW[co][ci][tap] (OIHW, co = co_begin + n*co_stride) = sum_s part[s][tap][ci][n];  db likewise.  Destinations are
 // read from the gradient pointer tables on the device (w_tbl[w_idx] / b_tbl[b_idx]) or given directly.
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ dbpart, int S, int Cin,
-                                    int n_rows, float* const* __restrict__ w_tbl, int w_idx, float* w_direct,
-                                    float* const* __restrict__ b_tbl, int b_idx, float* b_direct, int co_begin,
-                                    int co_stride) {
-  float* dw = w_tbl != nullptr ? w_tbl[w_idx] : w_direct;
-  float* db = b_tbl != nullptr ? b_tbl[b_idx] : b_direct;
+// 256 threads = 64 outputs x 4 groups of partials; every group sums its partials s = grp, grp+4, ... with 8 loads in
+// flight, the four group sums are combined in a fixed order (deterministic).  Output index space: the 9*Cin*n_rows
+// weight entries followed by the n_rows bias entries.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ dbpart, int S, int Cin, int n_rows,
+                    float* const* __restrict__ w_tbl, int w_idx, float* w_direct, float* const* __restrict__ b_tbl,
+                    int b_idx, float* b_direct, int co_begin, int co_stride) {
+  __shared__ float red[4][64];
   const int total = 9 * Cin * n_rows;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < total) {
-    const int n = idx % n_rows, ci = (idx / n_rows) % Cin, tap = idx / (n_rows * Cin);
-    float t = 0.f;
-    for (int s = 0; s < S; ++s) t += part[static_cast<size_t>(s) * total + idx];
-    if (dw != nullptr) dw[(static_cast<size_t>(co_begin + n * co_stride) * Cin + ci) * 9 + tap] = t;
+  const int o = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int idx = blockIdx.x * 64 + o;
+  float t = 0.f;
+  if (idx < total + n_rows) {
+    const float* src = idx < total ? part + idx : dbpart + (idx - total);
+    const size_t stride = idx < total ? static_cast<size_t>(total) : static_cast<size_t>(n_rows);
+    int s = grp;
+    for (; s + 28 < S; s += 32) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = src[static_cast<size_t>(s + 4 * u) * stride];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t += v[u];
+    }
+    for (; s < S; s += 4) t += src[static_cast<size_t>(s) * stride];
   }
-  if (idx < n_rows && db != nullptr) {
-    float t = 0.f;
-    for (int s = 0; s < S; ++s) t += dbpart[static_cast<size_t>(s) * n_rows + idx];
-    db[co_begin + idx * co_stride] = t;
+  red[grp][o] = t;
+  __syncthreads();
+  if (grp != 0 || idx >= total + n_rows) return;
+  const float sum = ((red[0][o] + red[1][o]) + red[2][o]) + red[3][o];
+  if (idx < total) {
+    float* dw = w_tbl != nullptr ? w_tbl[w_idx] : w_direct;
+    const int n = idx % n_rows, ci = (idx / n_rows) % Cin, tap = idx / (n_rows * Cin);
+    if (dw != nullptr) dw[(static_cast<size_t>(co_begin + n * co_stride) * Cin + ci) * 9 + tap] = sum;
+  } else {
+    float* db = b_tbl != nullptr ? b_tbl[b_idx] : b_direct;
+    if (db != nullptr) db[co_begin + (idx - total) * co_stride] = sum;
   }
 }
 
@@ -615,20 +659,12 @@ int gather_strided(const float* const* tbl, const float* direct, int tbl_stride,
 
 int bwd_reduce_chunks(int HW) { return std::max(1, std::min(32, HW / 256)); }
 
-int bwd_reduce_gr(const float* g, const void* r, int r_is_bf16, float* part, int B, int HW, int C, cudaStream_t s) {
+int bwd_reduce_ca(const float* g, const void* r, int r_is_bf16, float* part, unsigned int* tickets,
+                  const float* pool_rows, int pool_nrows, const float* ymean, int HW, const AttnParams& ap,
+                  const float* attributes, const float* sq, float out_scale, float* svec, float* dyv, float* sig,
+                  int sig_stride, int B, cudaStream_t s) {
+  const int C = ap.C;
   if (C % 8 != 0 || C > 256 || 256 % (C / 8) != 0) return DFIR_ERR_ARG;
-  const int nchunk = bwd_reduce_chunks(HW);
-  dim3 grid(nchunk, B);
-  if (r_is_bf16)
-    bwd_reduce_gr_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(g, reinterpret_cast<const __nv_bfloat16*>(r), part, HW, C, nchunk);
-  else
-    bwd_reduce_gr_kernel<float><<<grid, 256, 0, s>>>(g, reinterpret_cast<const float*>(r), part, HW, C, nchunk);
-  return ok_or_cuda3();
-}
-
-int ca_backward(const float* part, const float* pool_rows, int pool_nrows, int HW, const AttnParams& ap,
-                const float* attributes, const float* sq, float out_scale, float* svec, float* dyv, float* sig,
-                int sig_stride, int B, cudaStream_t s) {
   if (ap.C > 256 || 256 % ap.C != 0 || ap.R > 64 || ap.A > 512) return DFIR_ERR_ARG;
   if (ap.style != DFIR_STYLE_NONE && ap.style != DFIR_STYLE_STANDARD && ap.style != DFIR_STYLE_MODULATE &&
       ap.style != DFIR_STYLE_MAX_CONCAT)
@@ -638,7 +674,13 @@ int ca_backward(const float* part, const float* pool_rows, int pool_nrows, int H
   a.style = ap.style; a.C = ap.C; a.R = ap.R; a.M = ap.M; a.A = ap.A; a.ca = ap.w[0];
   a.attributes = attributes; a.sq = sq; a.out_scale = out_scale; a.svec = svec; a.dyv = dyv; a.sig = sig;
   a.sig_stride = sig_stride;
-  ca_backward_kernel<<<B, 128, 0, s>>>(a);
+  a.ymean = ymean;
+  const int nchunk = a.nchunk;
+  dim3 grid(nchunk, B);
+  if (r_is_bf16)
+    bwd_reduce_ca_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(g, reinterpret_cast<const __nv_bfloat16*>(r), part, HW, C, nchunk, a, tickets);
+  else
+    bwd_reduce_ca_kernel<float><<<grid, 256, 0, s>>>(g, reinterpret_cast<const float*>(r), part, HW, C, nchunk, a, tickets);
   return ok_or_cuda3();
 }
 
@@ -691,8 +733,8 @@ int wgrad_f32(const float* dY, const float* X, float* scratch, int B, int H, int
 int wgrad_reduce(const float* part, const float* dbpart, int S, int Cin, int n_rows, float* const* w_tbl, int w_idx,
                  float* w_direct, float* const* b_tbl, int b_idx, float* b_direct, int co_begin, int co_stride,
                  cudaStream_t s) {
-  const int total = 9 * Cin * n_rows;
-  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(part, dbpart, S, Cin, n_rows, w_tbl, w_idx, w_direct, b_tbl,
+  const int total = 9 * Cin * n_rows + n_rows;
+  wgrad_reduce_kernel<<<(total + 63) / 64, 256, 0, s>>>(part, dbpart, S, Cin, n_rows, w_tbl, w_idx, w_direct, b_tbl,
                                                           b_idx, b_direct, co_begin, co_stride);
   return ok_or_cuda3();
 }

@@ -12,8 +12,8 @@
 // CTAs in a fixed order (deterministic) and stores OIHW.  (The tcgen05 form needs MN-major shared-memory
 // descriptors; DESIGN.md lists it as the next step for this kernel.)
 //
-// Shared memory: ring of 4 X rows (130 px incl. the x halo, 128-byte rows, 16-byte chunks XOR-swizzled by the row
-// index so that ldmatrix is bank-conflict free) + 2 dY row buffers, filled by cp.async one row ahead.
+// Shared memory: ring of 5 X rows (130 px incl. the x halo, 128-byte rows, 16-byte chunks XOR-swizzled by the row
+// index so that ldmatrix is bank-conflict free) + 3 dY row buffers, filled by cp.async two rows ahead.
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -25,7 +25,9 @@ constexpr int kWgThreads = 384;  // 9 MMA warps (one per tap) + 3 helper warps (
                                  // allocated per 4 warps, so 9 warps would not get more registers than 12
 constexpr int kXSlotBytes = 130 * 128;
 constexpr int kDyBytes = 128 * 128;
-constexpr int kWgSmem = 4 * kXSlotBytes + 2 * kDyBytes;
+constexpr int kXSlots = 5;   // 3 live rows + 2 in flight
+constexpr int kDyBufs = 3;   // current + 2 in flight
+constexpr int kWgSmem = kXSlots * kXSlotBytes + kDyBufs * kDyBytes;
 
 struct WgradArgs {
   const uint8_t* dy;  // bf16, byte strides below
@@ -57,7 +59,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_c64_mma_kernel(WgradArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* xring = smem;
-  uint8_t* dybuf = smem + 4 * kXSlotBytes;
+  uint8_t* dybuf = smem + kXSlots * kXSlotBytes;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = a.H, W = a.W, nseg = a.nseg;
   const long long G = static_cast<long long>(a.B) * nseg * H;
@@ -75,7 +77,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_c64_mma_kernel(WgradArgs 
   float dbacc = 0.f;  // helper warps: bias gradient of channel (tid - 288) & 63
 
   auto load_x_row = [&](int b, int yy, int seg) {
-    uint8_t* slot = xring + ((yy + 1) & 3) * kXSlotBytes;
+    uint8_t* slot = xring + ((yy + 1) % kXSlots) * kXSlotBytes;
     const bool row_ok = yy >= 0 && yy < H;
     for (int i = tid; i < 130 * 8; i += kWgThreads) {
       const int p = i >> 3, ch = i & 7;
@@ -104,31 +106,37 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_c64_mma_kernel(WgradArgs 
   for (int g = g0, it = 0; g < g1; ++g, ++it) {
     const int col = g / H, y = g % H;
     const int b = col / nseg, seg = col % nseg;
-    if (it == 0 || y == 0) {  // start of a (image, segment) column: nothing was prefetched
+    if (it == 0 || y == 0) {  // start of a (image, segment) column: nothing is in flight
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();
       load_x_row(b, y - 1, seg);
       load_x_row(b, y, seg);
       load_x_row(b, y + 1, seg);
-      load_dy_row(b, y, seg, it & 1);
+      load_dy_row(b, y, seg, it % kDyBufs);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (g + 1 < g1 && y + 1 < H) {
+        load_x_row(b, y + 2, seg);
+        load_dy_row(b, y + 1, seg, (it + 1) % kDyBufs);
+      }
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the newest group: this row is complete
     __syncthreads();
-    if (g + 1 < g1 && y + 1 < H) {  // next row of the same column: one new X row + its dY row
-      load_x_row(b, y + 2, seg);
-      load_dy_row(b, y + 1, seg, (it + 1) & 1);
-      asm volatile("cp.async.commit_group;" ::: "memory");
+    if (g + 2 < g1 && y + 2 < H) {  // two rows ahead: one new X row + its dY row
+      load_x_row(b, y + 3, seg);
+      load_dy_row(b, y + 2, seg, (it + 2) % kDyBufs);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     const int npx = min(128, W - seg * 128);
     const int ksteps = (npx + 15) >> 4;
-    const uint32_t dy_s = ptx::smem_u32(dybuf + (it & 1) * kDyBytes);
-    const uint32_t x_s = ptx::smem_u32(xring + ((y + tdy) & 3) * kXSlotBytes);  // row y + tdy - 1
+    const uint32_t dy_s = ptx::smem_u32(dybuf + (it % kDyBufs) * kDyBytes);
+    const uint32_t x_s = ptx::smem_u32(xring + ((y + tdy) % kXSlots) * kXSlotBytes);  // row y + tdy - 1
     const int q = lane >> 3, r8 = lane & 7;
     if (warp >= 9) {
       // bias gradient: column sums of the dY row straight from shared memory (threads 288..351, one channel each)
       const int co = tid - 288;
       if (co < 64) {
-        const uint8_t* base = dybuf + (it & 1) * kDyBytes + (co & 7) * 2;
+        const uint8_t* base = dybuf + (it % kDyBufs) * kDyBytes + (co & 7) * 2;
         const int ch = co >> 3;
         for (int p = 0; p < npx; ++p)
           dbacc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(base + p * 128 + ((ch ^ (p & 7)) << 4)));

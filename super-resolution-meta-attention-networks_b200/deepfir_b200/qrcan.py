@@ -232,7 +232,9 @@ class QRCAN(nn.Module):
         if training and not pk.train_ready:
             pk.enable_training(self)
             pk.versions = None
-        if pk.versions != vers:
+        if training and getattr(self, "cuda_graphs", True):
+            pk.versions = None  # the step graph re-packs the parameters itself (deepfir_b200/train.py)
+        elif pk.versions != vers:
             pk.repack()
             pk.versions = vers
         return pk
@@ -429,7 +431,8 @@ class PackedQrcan:
         self._ws = {}
         self.versions = None
         self.train_ready = False
-        self.grads = None
+        self.step_graphs = {}
+        self.ws_owner = None
         # device pointer tables of the fp32 parameters: lets the C side refresh every kernel-format buffer in a few
         # launches (styles whose attention block has the 4-tensor layout; the others are rebuilt from Python)
         self.can_repack = "ca_params" in spec and cfg["style"] in ("none", "standard", "modulate", "max_concat",
