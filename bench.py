@@ -104,6 +104,107 @@ def build_net(device):
     return handler
 
 
+TRAIN_BATCH = 16                        # BASELINE.json configs[3]: 16 x 64x64 LR patches per GPU
+TRAIN_LR = 64
+TRAIN_FLOP_PER_STEP = 3 * FLOP_PER_LR_PIXEL * TRAIN_BATCH * TRAIN_LR * TRAIN_LR  # fwd + dgrad + wgrad
+
+
+def train_step_bench(local, dev, world, dist, steps, warmup):
+    """Q-RCAN x4 bf16 training step (configs[3]) through `QRCANHandler.run_train`: H2D of the LR/HR patches from pinned
+    memory, forward, L1 loss, backward (all parameter gradients), gradient all-reduce over NCCL when world > 1, Adam,
+    cosine scheduler, D2H of the loss.  Returns per-step times: wall clock of the API call (max over ranks) and the
+    device time of forward+loss+backward+Adam on device-resident patches (CUDA events)."""
+    from SISR.models import ModelInterface
+    torch.manual_seed(8)
+    h = ModelInterface.define_model(
+        "qrcan", device=local, model_save_dir=tempfile.gettempdir(), eval_mode=False, lr=1e-4,
+        metadata=["blur_kernel"], precision="bf16", scheduler="cosine_annealing_warm_restarts",
+        scheduler_params=dict(t_mult=1, restart_period=125000, lr_min=1e-7), **NET_KW)
+    g = torch.Generator().manual_seed(88 + int(os.environ.get("RANK", "0")))
+    x = torch.rand(TRAIN_BATCH, 3, TRAIN_LR, TRAIN_LR, generator=g).pin_memory()
+    y = torch.rand(TRAIN_BATCH, 3, TRAIN_LR * SCALE, TRAIN_LR * SCALE, generator=g).pin_memory()
+    meta = torch.rand(TRAIN_BATCH, 10, generator=g, dtype=torch.float64) * 0.4
+    keys = [("blur_kernel",) * TRAIN_BATCH] * 10
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    losses = []
+    for _ in range(max(warmup, 3)):
+        loss, _ = h.run_train(x, y, metadata=meta, metadata_keys=keys, keep_on_device=True)
+        losses.append(float(loss))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss, _ = h.run_train(x, y, metadata=meta, metadata_keys=keys, keep_on_device=True)
+        losses.append(float(loss))
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / steps
+    # device time with the patches already in HBM
+    xd, yd = x.to(dev), y.to(dev)
+    attr = h.generate_channels(x, meta, keys).to(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        out = h.net(xd, attr)
+        l = h.criterion(out, yd)
+        h.optimizer.zero_grad()
+        l.backward()
+        h.optimizer.step()
+    e1.record()
+    barrier()
+    dev_ms = e0.elapsed_time(e1) / steps
+    t = torch.tensor([wall_ms, dev_ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall_ms, dev_ms = t.tolist()
+    import ctypes as C
+    from deepfir_b200 import _lib
+    launches = int(_lib.load_library().dfir_qrcan_train_launch_count(C.byref(h.net.packed(training=True).desc),
+                                                                      TRAIN_BATCH, TRAIN_LR, TRAIN_LR, 0))
+    pk = peaks()
+    res = {"workload": "Q-RCAN x4 (10x20 RCAB, 64 ch) bf16 training step, batch %d x %dx%d LR patches per GPU, L1, "
+                       "Adam, cosine-restart scheduler%s" % (TRAIN_BATCH, TRAIN_LR, TRAIN_LR,
+                                                             ", gradient all-reduce over NCCL" if world > 1 else ""),
+           "ms_per_step": round(wall_ms, 3), "ms_per_step_device_resident": round(dev_ms, 3), "unit": "ms",
+           "api": "QRCANHandler.run_train(x_pinned, y_pinned, metadata=, metadata_keys=, keep_on_device=True)",
+           "h2d_bytes_per_step": int(x.numel() * 4 + y.numel() * 4 + TRAIN_BATCH * 10 * 4), "d2h_bytes_per_step": 4,
+           "gpu_launches_per_step": launches, "cuda_graphs": True,
+           "tflops_algorithmic": round(TRAIN_FLOP_PER_STEP / (dev_ms / 1e3) / 1e12, 1),
+           "frac_of_bf16_peak": round(TRAIN_FLOP_PER_STEP / (dev_ms / 1e3) / 1e12 / pk["tf_sustained"], 4),
+           "loss_first_last": [round(losses[0], 5), round(losses[-1], 5)]}
+    del h
+    torch.cuda.empty_cache()
+    return res
+
+
+def cpu_train_baseline(threads=None):
+    """one training step of the reference's path on the host CPU: autograd through the oracle port (forward, L1,
+    backward) on ONE 64x64 patch of the 16-patch batch"""
+    from oracle import deepfir_oracle as O
+    from deepfir_b200.qrcan import QRCAN
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    torch.manual_seed(8)
+    net = QRCAN(num_metadata=10, **NET_KW)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(8)
+    x = torch.rand(1, 3, TRAIN_LR, TRAIN_LR, generator=g)
+    y = torch.rand(1, 3, TRAIN_LR * SCALE, TRAIN_LR * SCALE, generator=g)
+    attr = (torch.rand(1, 10, generator=g) * 0.4).reshape(1, 10, 1, 1)
+    t0 = time.perf_counter()
+    out = O.qrcan_forward(x, attr, sd, style="standard")
+    torch.nn.functional.l1_loss(out, y).backward()
+    dt = time.perf_counter() - t0
+    return {"value": round(dt * 1e3, 1), "unit": "ms", "cores": threads, "kind": "port",
+            "sample": "forward + L1 + backward of 1 of the %d patches of a step (no warm-up, no optimizer), fp32 torch-CPU "
+                      "autograd through oracle/deepfir_oracle.py; a full step is ~%dx this" % (TRAIN_BATCH, TRAIN_BATCH)}
+
+
 def synth_batch(n, seed):
     g = torch.Generator().manual_seed(seed)
     x = torch.floor(torch.rand(n, 3, LR, LR, generator=g) * 256) / 255.0
@@ -177,7 +278,8 @@ def run_ours(args):
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
 
     # ---------------- end to end through the handler API with host buffers
-    step_e2e()
+    for _ in range(3):  # the caching host allocator needs two live result buffers before the loop is steady
+        out_host = step_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -185,6 +287,7 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    d2h_bytes = out_host.numel() * 4
     t = torch.tensor([dev_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -194,6 +297,10 @@ def run_ours(args):
     roof = None
     if rank == 0:
         roof = conv_roofline(lib, dev, net)
+    # ---------------- training step (BASELINE.json metric part 2: "train step ms")
+    del out, out_host, l2buf
+    torch.cuda.empty_cache()
+    train = train_step_bench(local, dev, world, dist, steps=max(args.steps, 5), warmup=args.warmup)
     out_mpix_step = world * n_img * (LR * SCALE) ** 2 / 1e6
     launches = int(lib.dfir_qrcan_launch_count(__import__("ctypes").byref(net.packed().desc), n_img, LR, LR, 0))
 
@@ -214,11 +321,12 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": round(out_mpix_step / (e2e_ms / 1e3 / args.steps), 3), "unit": "MPix/s",
                     "h2d_bytes_per_step": int(x_pin.numel() * 4 + n_img * 10 * 4),
-                    "d2h_bytes_per_step": int(out_host.numel() * 4),
+                    "d2h_bytes_per_step": int(d2h_bytes),
                     "api": "QRCANHandler.run_eval(x_pinned_host, metadata=, metadata_keys=) -> host tensor"},
             "gpu_launches": launches * args.steps,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "train": dict(train, cpu_baseline=cpu_train_baseline()),
             "tflops_conv_algorithmic": round(world * n_img * LR * LR * FLOP_PER_LR_PIXEL / (ms_step / 1e3) / 1e12, 2),
             "wall_s_timed_region": round(wall, 3),
             "peaks": pk["source"],

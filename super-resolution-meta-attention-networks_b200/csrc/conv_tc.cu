@@ -526,8 +526,11 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               tmp[et] = acc;  // tmp[0..127] (the T/C partials are dead by now)
             }
             grp.sync();
-            if (et < 64)
+            if (et < 64) {
               y_s[et] = bias_s[et] + (tmp[2 * et] + tmp[2 * et + 1]) / (static_cast<float>(H) * static_cast<float>(a.W));
+              // training forward: the backward needs the pooled mean (every CTA touching image b writes the same bits)
+              if (a.ymean_out != nullptr) a.ymean_out[static_cast<size_t>(b) * 64 + et] = y_s[et];
+            }
             grp.sync();
             attn_vector(grp, a.ca_style, a.ca_params, 64, a.ca_R, a.ca_M, attr_s, y_s, s_s, tmp);
             if (et < 64)
@@ -611,13 +614,15 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           // stream + its bf16 copy straight to global memory.
           float* tile = reinterpret_cast<float*>(stage);  // [128 px][64] fp32 = 32 KB = both staging buffers
           float* sc_s = pool_s;                           // [64] scale, [64] bias*scale of the current image
+          const bool save_r = a.r_out != nullptr;         // training forward: tile = acc + b, scale applied below
           named_bar_sync(1, 128);  // previous row's coalesced pass has finished with the tile (and with sc_s)
           if (b != cur_img) {      // (uniform) new image: stage its scale vector
             if (et < 64) {
               const float sc = a.epi_stats ? svec_s[(b - bimg_first) * 64 + et]
                                            : (a.svec != nullptr ? a.svec[static_cast<size_t>(b) * 64 + et] : 1.f);
-              sc_s[et] = sc;
-              sc_s[64 + et] = bias_s[et] * sc;
+              sc_s[et] = save_r ? 1.f : sc;
+              sc_s[64 + et] = save_r ? bias_s[et] : bias_s[et] * sc;
+              sc_s[128 + et] = sc;
             }
             cur_img = b;
             named_bar_sync(2, 128);
@@ -655,12 +660,21 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             __nv_bfloat16* obf = a.out_bf16_direct + e0;
             const float4* t4 = reinterpret_cast<const float4*>(tile);
             const float4* sk4 = reinterpret_cast<const float4*>(skipbuf) + et;
+            const float4 sr4 = reinterpret_cast<const float4*>(sc_s + 128)[c4];
+            __nv_bfloat16* rbf = save_r ? a.r_out + e0 : nullptr;
             asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int p = i * 8 + pq;
               if (p < npx) {
                 float4 o = t4[p * 16 + ((c4 + p) & 15)];
+                if (save_r) {  // r = conv + b goes out as bf16 for the backward; the stream gets r * s + skip
+                  uint2 rk;
+                  rk.x = pack_bf16x2(o.x, o.y);
+                  rk.y = pack_bf16x2(o.z, o.w);
+                  *reinterpret_cast<uint2*>(rbf + i * 512) = rk;
+                  o.x *= sr4.x; o.y *= sr4.y; o.z *= sr4.z; o.w *= sr4.w;
+                }
                 if (has_skip) {
                   const float4 sk = sk4[i * 128];
                   o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
@@ -921,6 +935,8 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   a.col_last = d.col_last;
   a.svec = d.svec;
   a.mask_bf16 = reinterpret_cast<const __nv_bfloat16*>(d.mask_bf16);
+  a.r_out = reinterpret_cast<__nv_bfloat16*>(d.r_out);
+  a.ymean_out = d.ymean_out;
   a.out_bf16_direct = reinterpret_cast<__nv_bfloat16*>(d.out_bf16);
   a.r_bf16 = reinterpret_cast<const __nv_bfloat16*>(d.r_bf16);
   a.xin_f32 = d.xin_f32;

@@ -14,6 +14,7 @@
 #include "kernels.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 using namespace dfir;
 
@@ -52,7 +53,8 @@ int up_stages(int scale, int* r) {
 struct TrainWs {
   uint8_t* act; size_t slot_bytes;   // activation stash, operand format (bf16 on the tensor-core path, else fp32)
   uint8_t* U[3];                     // upsampler stage outputs, operand format
-  float* pool; size_t pool_stride;   // [nblk][B*nseg*H*C] pooled row sums of r
+  float* pool; size_t pool_stride;   // [B*nseg*H*C] pooled row sums (scratch of the forward)
+  float *colf, *coll;                // [B*H*C] first / last column of t (pool-by-linearity statistics)
   float* sq;                         // [nblk][B][C] meta-attention scales
   float *Hh, *XA, *XB;               // fp32 streams (tensor-core path only)
   float *G, *gs, *dF32;              // fp32 gradients of the group stream / block stream / trunk output
@@ -99,7 +101,9 @@ TrainWs carve_train(const dfir_qrcan_net* n, int B, int H, int W, int precision,
   }
   const size_t top = feat * f;  // elements of the largest upsampler output
   w.pool_stride = static_cast<size_t>(B) * nseg * H * C;
-  w.pool = c.take<float>(w.pool_stride * nblk * 4);
+  w.pool = c.take<float>(w.pool_stride * 4);
+  w.colf = c.take<float>(static_cast<size_t>(B) * H * C * 4);
+  w.coll = c.take<float>(static_cast<size_t>(B) * H * C * 4);
   w.sq = c.take<float>(static_cast<size_t>(nblk) * B * C * 4);
   if (tc) {
     w.Hh = c.take<float>(feat * 4);
@@ -168,7 +172,7 @@ struct Ctx {
   uint8_t* XLAST(int g) const { return slot(3 * nblk + g); }
   uint8_t* TRUNK_IN() const { return n->no_group_conv ? XLAST(0) : slot(3 * nblk + ng); }
   uint8_t* F() const { return slot(3 * nblk + ng + 1); }
-  float* pool(int k) const { return w.pool + static_cast<size_t>(k) * w.pool_stride; }
+  float* pool(int) const { return w.pool; }
   const float* sq(int k) const { return n->any_q ? w.sq + static_cast<size_t>(k) * B * C : nullptr; }
   float* sig(int k) const { return w.sig + static_cast<size_t>(k) * B * w.sig_stride; }
   float* ymean(int k) const { return w.ymean + static_cast<size_t>(k) * B * C; }
@@ -216,6 +220,16 @@ const uint8_t* tc_wT(const Ctx& c, int widx) {
 }
 const float* tc_b(const Ctx& c, int widx) { return c.n->conv_b + static_cast<size_t>(widx) * 64; }
 
+// block schedule of the training forward: pool-by-linearity (2 launches per RCAB) once a CTA's band is long enough to
+// hide the attention prologue, else the streamer (3 launches)
+bool train_linear_schedule(int B, int H, int W, int sms) {
+  if (const char* e = getenv("DFIR_TRAIN_SCHEDULE")) {  // test hook: "linear" | "streamer"
+    if (e[0] == 'l') return true;
+    if (e[0] == 's') return false;
+  }
+  return static_cast<long long>(B) * ((W + 127) / 128) * H >= 16ll * std::max(1, sms);
+}
+
 // =============================================================================================== forward
 int train_forward_tc(const Ctx& c, const float* x, const float* attr, float* out) {
   const dfir_qrcan_net* n = c.n;
@@ -223,20 +237,45 @@ int train_forward_tc(const Ctx& c, const float* x, const float* attr, float* out
   const int H = c.H, W = c.W, C = 64;
   DFIR_TRY(head_conv(x, n->head_w_f32, n->head_b, w.Hh, reinterpret_cast<__nv_bfloat16*>(c.XIN(0)), c.B, n->in_feats, H,
                      W, C, c.st));
+  const bool linear = train_linear_schedule(c.B, H, W, c.sms);
   for (int g = 0; g < c.ng; ++g) {
     const float* skip32 = g == 0 ? w.Hh : w.XA;
     for (int b = 0; b < c.nb; ++b) {
       const int k = g * c.nb + b;
       const int w1 = g * c.per_group + 2 * b, w2 = w1 + 1;
-      ConvTcDesc c1 = tc_desc(c, tc_w(c, w1), tc_b(c, w1), EPI_BIAS_RELU, H, W);
-      c1.in_bf16 = c.XIN(k); c1.out_bf16 = c.T(k);
-      DFIR_TRY(conv3x3_c64_tc(c1, c.st));
-      ConvTcDesc c2 = tc_desc(c, tc_w(c, w2), tc_b(c, w2), c.has_ca ? EPI_BIAS_POOL : EPI_BIAS, H, W);
-      c2.in_bf16 = c.T(k); c2.out_bf16 = c.R(k); c2.pool_rows = c.pool(k);
-      DFIR_TRY(conv3x3_c64_tc(c2, c.st));
       uint8_t* next_bf = (b + 1 < c.nb) ? c.XIN(k + 1) : c.XLAST(g);
-      DFIR_TRY(scale_residual(c.R(k), 1, b == 0 ? skip32 : w.XB, c.pool(k), c.nseg * H, make_ap(n, k), attr, c.sq(k), 1.f,
-                              w.XB, reinterpret_cast<__nv_bfloat16*>(next_bf), c.B, H, W, C, c.st, c.ymean(k)));
+      if (!linear) {
+        // streamer schedule: conv1, conv2 (+ pooled row sums), one bandwidth-shaped pass x' = r*s + x.  Measured at
+        // 16 x 64x64 (7 rows per CTA): 12.8 ms per forward against 15.0 ms for the pool-by-linearity pair, whose
+        // in-kernel attention prologue (~10 us) no longer hides behind the short pipeline.
+        ConvTcDesc c1 = tc_desc(c, tc_w(c, w1), tc_b(c, w1), EPI_BIAS_RELU, H, W);
+        c1.in_bf16 = c.XIN(k); c1.out_bf16 = c.T(k);
+        DFIR_TRY(conv3x3_c64_tc(c1, c.st));
+        ConvTcDesc c2 = tc_desc(c, tc_w(c, w2), tc_b(c, w2), c.has_ca ? EPI_BIAS_POOL : EPI_BIAS, H, W);
+        c2.in_bf16 = c.T(k); c2.out_bf16 = c.R(k); c2.pool_rows = w.pool;
+        DFIR_TRY(conv3x3_c64_tc(c2, c.st));
+        DFIR_TRY(scale_residual(c.R(k), 1, b == 0 ? skip32 : w.XB, w.pool, c.nseg * H, make_ap(n, k), attr, c.sq(k), 1.f,
+                                w.XB, reinterpret_cast<__nv_bfloat16*>(next_bf), c.B, H, W, C, c.st, c.ymean(k)));
+        continue;
+      }
+      // pool-by-linearity, as in inference: conv1 emits the statistics of t, conv2's prologue turns
+      // them into the attention vector and its epilogue writes x' = r*s + x — plus, for the backward, r and mean(r)
+      ConvTcDesc c1 = tc_desc(c, tc_w(c, w1), tc_b(c, w1), c.has_ca ? EPI_RELU_STATS : EPI_BIAS_RELU, H, W);
+      c1.in_bf16 = c.XIN(k); c1.out_bf16 = c.T(k);
+      c1.pool_rows = w.pool; c1.col_first = w.colf; c1.col_last = w.coll;
+      DFIR_TRY(conv3x3_c64_tc(c1, c.st));
+      ConvTcDesc c2 = tc_desc(c, tc_w(c, w2), tc_b(c, w2), EPI_SCALE_SKIP, H, W);
+      c2.in_bf16 = c.T(k); c2.skip_f32 = b == 0 ? skip32 : w.XB; c2.out_f32 = w.XB; c2.out_bf16 = next_bf;
+      c2.r_out = c.R(k);
+      if (c.has_ca) {
+        c2.pool_rows = w.pool; c2.col_first = w.colf; c2.col_last = w.coll; c2.epi_stats = 1;
+        c2.ca_style = n->style; c2.ca_R = std::max(1, n->reduced); c2.ca_M = n->num_metadata; c2.ca_A = n->attr_size;
+        c2.ca_params = n->ca_blob + static_cast<size_t>(k) * n->ca_stride; c2.attributes = attr; c2.sq = c.sq(k);
+        c2.ymean_out = c.ymean(k);
+      } else {
+        c2.svec = c.sq(k);
+      }
+      DFIR_TRY(conv3x3_c64_tc(c2, c.st));
     }
     if (!n->no_group_conv) {
       const int wg = g * c.per_group + 2 * c.nb;
@@ -596,7 +635,7 @@ long long dfir_qrcan_train_launch_count(const dfir_qrcan_net* n, int B, int H, i
   const long long ngc = n->no_group_conv ? 0 : n->n_groups;
   const long long ca = n->style != DFIR_STYLE_NONE ? 1 : 0;
   if (precision == DFIR_PREC_BF16_TC) {
-    const long long fwd = 1 + (n->any_q ? 1 : 0) + nblk * 3 + ngc + 1 + nup * r * r + 1;
+    const long long fwd = 1 + (n->any_q ? 1 : 0) + nblk * (train_linear_schedule(B, H, W, 148) ? 2 : 3) + ngc + 1 + nup * r * r + 1;
     const long long bwd = 3 + nup * r * r * 3 + 3 + ngc * 4 + nblk * 8 + 1 + 2 + 1;
     return fwd + bwd;
   }

@@ -204,6 +204,24 @@ def test_train_step_bf16_gradients_close_to_oracle(name):
     print("bf16 worst relative gradient error", worst)
 
 
+def test_train_forward_schedules_agree(monkeypatch):
+    """the training forward has two block schedules (streamer for short bands, pool-by-linearity for long ones): same
+    loss and gradients up to bf16 rounding of r"""
+    _, info = load_golden("qrcan_standard_g2b2")
+    res = {}
+    for sched in ("streamer", "linear"):
+        monkeypatch.setenv("DFIR_TRAIN_SCHEDULE", sched)
+        net, sd, x, meta = _build(info, "bf16")
+        net.cuda_graphs = False
+        _, _, y, _ = oracle_grads(info, sd, x, meta)
+        res[sched] = _step_grads(net, x, meta, y)
+    assert abs(res["linear"][0] - res["streamer"][0]) <= 1e-3 * abs(res["streamer"][0])
+    gmax = max(float(v.norm()) for v in res["streamer"][2].values())
+    for k, g in res["linear"][2].items():
+        ref = res["streamer"][2][k]
+        assert float((g - ref).norm()) <= 3e-2 * float(ref.norm()) + 1e-3 * gmax, k
+
+
 def test_gradients_accumulate_without_zero_grad():
     _, info = load_golden("qrcan_noq_scale2")
     net, sd, x, meta = _build(info, "fp32")
