@@ -171,6 +171,10 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  // Programmatic dependent launch: the next conv of the chain may become resident as soon as this CTA retires; its
+  // barrier set-up, TMEM allocation and weight load then overlap the tail of this grid.  Everything that reads what
+  // the previous kernel wrote (activation rows, statistics, skip rows) sits behind grid_dep_wait().
+  if (threadIdx.x == 0) grid_dep_launch();
   const bool probe = (a.debug_probe & 1) != 0 && blockIdx.x == 0 && lane == 0;
   const bool exp_skip_store = (a.debug_probe & 2) != 0;  // timing experiments only (wrong results)
   const bool exp_one_copy = (a.debug_probe & 4) != 0;
@@ -187,7 +191,8 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       // ===================== TMA producer =====================
       if (elect_one()) {
         mbar_arrive_expect_tx(wbar, L::w_bytes);
-        bulk_load_1d(wsm, a.wpacked, L::w_bytes, wbar);
+        bulk_load_1d(wsm, a.wpacked, L::w_bytes, wbar);  // weights are not produced by the previous kernel
+        grid_dep_wait();
         if constexpr (INMODE == IN_TMA) {
           for (int n = 0; n <= n_last; ++n) {
             const int pr = pr_first + n;
@@ -328,6 +333,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
     } else if (warp >= 10) {
       // ===================== fused input transform (IN_FUSED only; warps 10..17) =====================
       if constexpr (INMODE == IN_FUSED) {
+        grid_dep_wait();
         const int tt = threadIdx.x - kThreads;  // 0..255
         // ---- prologue (overlaps the weight load): attention vectors of the images this band touches.
         //      s[b] = CA_style(mean over pixels of r_b, attributes[b]) * meta_scale[b]; the pooled mean is
@@ -448,6 +454,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       const int rows_img_e = nseg * H;
       const int bimg_first = g0 / rows_img_e;
       int cur_img = -1;
+      grid_dep_wait();
       if constexpr (EPI == EPI_SCALE_SKIP) {
         // ---- pool-by-linearity: while the pipeline fills, the epilogue warps turn the sums of
         // t = relu(conv1(x)) left by the previous kernel into this block's attention vectors
@@ -857,8 +864,18 @@ static int launch_one(const CUtensorMap& tin, const CUtensorMap& tout, const Con
       return DFIR_ERR_CUDA;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  kern<<<grid, INMODE == IN_FUSED ? kThreadsFused : kThreads, L::total + 1024, stream>>>(tin, tout, a);
-  return cudaGetLastError() == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
+  static const bool use_pdl = getenv("DFIR_PDL") == nullptr || atoi(getenv("DFIR_PDL")) != 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(INMODE == IN_FUSED ? kThreadsFused : kThreads);
+  cfg.dynamicSmemBytes = L::total + 1024;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, tin, tout, a) == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
 }
 
 int debug_watchdog(unsigned int* out8, int reset) {
