@@ -63,6 +63,7 @@ constexpr int kTmemCols = 512;
 constexpr int kStageBytes = 128 * 128;       // one output row segment, bf16
 constexpr int kThreads = 320;                // IN_TMA: producer, MMA, 4 epilogue, 4 loader warps
 constexpr int kThreadsFused = 320 + 256;     // + two transform groups of 4 warps
+constexpr int kThreadsTwoEpi = 320 + 128;    // EPI_SCALE_SKIP (IN_TMA): + a second epilogue group (warps 10-13)
 constexpr int kMaxBandImages = 8;            // a CTA's row band may touch at most this many images (IN_FUSED)
 
 template <int NT>
@@ -74,7 +75,7 @@ struct SmemLayout {
   static constexpr int off_skip = off_stage + 2 * kStageBytes;   // EPI_SCALE_SKIP: fp32 skip row (cp.async target)
   static constexpr int off_bias = off_skip + 128 * 64 * 4;
   static constexpr int off_pool = off_bias + 64 * 4;
-  static constexpr int off_attn = off_pool + 4 * 64 * 4;                         // y[64] s[64] attr[512] tmp[1024]
+  static constexpr int off_attn = off_pool + 8 * 64 * 4;                         // y[64] s[64] attr[512] tmp[1024]
   static constexpr int off_svec = off_attn + (64 + 64 + 512 + 1024 + 4) * 4;     // s of the images of this band
   static constexpr int off_bars = off_svec + kMaxBandImages * 64 * 4;
   static constexpr int n_bars = 2 * kSlots + 2 * kARows + 2 * kAcc + 1;
@@ -106,8 +107,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 }  // namespace
 
+template <int EPI, int INMODE>
+constexpr int conv_threads() {
+  return INMODE == IN_FUSED ? kThreadsFused : (EPI == EPI_SCALE_SKIP ? kThreadsTwoEpi : kThreads);
+}
+
 template <int NT, int EPI, int INMODE>
-__global__ void __launch_bounds__(INMODE == IN_FUSED ? kThreadsFused : kThreads, 1)
+__global__ void __launch_bounds__(conv_threads<EPI, INMODE>(), 1)
 conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
                       ConvTcArgs a) {
   using L = SmemLayout<NT>;
@@ -330,7 +336,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           mbar_arrive(&empty[slot]);
         }
       }
-    } else if (warp >= 10) {
+    } else if (warp >= 10 && !(EPI == EPI_SCALE_SKIP && INMODE == IN_TMA)) {
       // ===================== fused input transform (IN_FUSED only; warps 10..17) =====================
       if constexpr (INMODE == IN_FUSED) {
         grid_dep_wait();
@@ -447,10 +453,15 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         }
       }
     } else {
-      // ===================== epilogue (warps 2..5) =====================
+      // ===================== epilogue (warps 2..5; EPI_SCALE_SKIP with TMA input: a second group, warps 10..13) ======
+      // EPI_SCALE_SKIP moves 10 B per element through the epilogue and is latency bound in one group (measured
+      // 3 us per row against 1.1 us of MMAs), so two groups take alternate rows (= alternate accumulators).
+      constexpr bool kTwoEpi = EPI == EPI_SCALE_SKIP && INMODE == IN_TMA;
+      constexpr int kEpiGroups = kTwoEpi ? 2 : 1;
+      const int egrp = (kTwoEpi && warp >= 10) ? 1 : 0;
       const int q = warp & 3;          // TMEM lane quarter this warp may read
       const int m = q * 32 + lane;     // pixel within the 128-px row segment
-      const int et = threadIdx.x - 64; // 0..127
+      const int et = egrp ? threadIdx.x - 320 : threadIdx.x - 64;  // 0..127 within the group
       const int rows_img_e = nseg * H;
       const int bimg_first = g0 / rows_img_e;
       int cur_img = -1;
@@ -460,7 +471,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         // t = relu(conv1(x)) left by the previous kernel into this block's attention vectors
         //   mean(conv2(t))[co] = b[co] + (1/HW) sum_{tap,ci} W[co][ci][tap] * S[tap][ci]
         // (W = this conv's weights, already on their way into shared memory), then QCALayer * meta scale.
-        if (a.epi_stats) {
+        if (a.epi_stats && egrp == 0) {
           float* y_s = attn_s;
           float* s_s = attn_s + 64;
           float* attr_s = attn_s + 128;
@@ -547,7 +558,10 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           }
         }
       }
-      for (int g = g0, it = 0; g < g1; ++g, ++it) {
+      if constexpr (kTwoEpi) {
+        if (a.epi_stats) named_bar_sync(6, 256);  // the attention vectors (svec_s) of group 0 are visible to group 1
+      }
+      for (int g = g0 + egrp, it = egrp; g < g1; g += kEpiGroups, it += kEpiGroups) {
         const int col = g / H;
         const int y = g % H;
         const int b = col / nseg;
@@ -556,31 +570,33 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         const bool valid = x < a.W;
         const int acc = it % kAcc;
         if (probe) g_dfir_progress[8 + q] = it + 1;
-        // EPI_SCALE_SKIP: the fp32 skip row travels global -> smem with cp.async (16 x 16 B per thread, coalesced,
-        // no registers held): the copy for row it+1 is issued at the end of row it, so its latency hides behind
-        // the accumulator wait and the TMEM read of the next row.  Each thread later reads back exactly the
-        // 16-byte slots it copied itself, so no barrier is needed, only cp.async.wait_group.
+        // EPI_SCALE_SKIP: the fp32 skip row travels global -> smem with cp.async in two halves of 32 channels (8 x 16 B
+        // per thread and half, coalesced, no registers held): the copy for the next half is issued as soon as the
+        // current one has been consumed, so its latency hides behind the barriers, the TMEM read and the tile writes.
+        // Each thread later reads back exactly the 16-byte slots it copied itself, so no barrier is needed, only
+        // cp.async.wait_group.
         const bool has_skip = a.skip_f32 != nullptr;  // dgrad launches without a skip: out = acc * s + b * s
-        auto issue_skip = [&](int gg) {
+        float* skipbuf_g = skipbuf + egrp * (128 * 32);
+        auto issue_skip = [&](int gg, int hh) {
           if (!has_skip) return;
           const int colg = gg / H;
           const int segg = colg % nseg;
           const int npxg = min(128, a.W - segg * 128);
-          const float* src = a.skip_f32 + ((static_cast<size_t>(colg / nseg) * a.H + (gg % H)) * a.W + segg * 128) * 64;
+          const float* src = a.skip_f32 + ((static_cast<size_t>(colg / nseg) * a.H + (gg % H)) * a.W + segg * 128) * 64 + hh * 32;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int idx = i * 128 + et;
-            if ((idx >> 4) < npxg && !exp_no_skipld)
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(skipbuf + idx * 4)),
-                           "l"(src + static_cast<size_t>(idx) * 4)
+          for (int i = 0; i < 8; ++i) {
+            const int idx = i * 128 + et;  // pixel idx >> 3, 16-byte chunk idx & 7
+            if ((idx >> 3) < npxg && !exp_no_skipld)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(skipbuf_g + idx * 4)),
+                           "l"(src + static_cast<size_t>(idx >> 3) * 64 + (idx & 7) * 4)
                            : "memory");
           }
           asm volatile("cp.async.commit_group;" ::: "memory");
         };
         if constexpr (EPI == EPI_SCALE_SKIP) {
-          if (it == 0) issue_skip(g);
-          if (has_skip && g + 2 < g1) {  // pull the skip row needed two iterations from now into L2 (2 x 128 B lines per thread)
-            const int g2 = g + 2, col2 = g2 / H;
+          if (it == egrp) issue_skip(g, 0);
+          if (has_skip && g + 2 * kEpiGroups < g1) {  // pull the skip row this group needs two rows from now into L2
+            const int g2 = g + 2 * kEpiGroups, col2 = g2 / H;
             const size_t e2 = ((static_cast<size_t>(col2 / nseg) * a.H + (g2 % H)) * a.W + (col2 % nseg) * 128) * 64;
             const int npx2 = min(128, a.W - (col2 % nseg) * 128);
 #pragma unroll
@@ -616,26 +632,29 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               if (c < a.cout) o[c * plane] = __uint_as_float(r0[c]) + bias_s[c];
           }
         } else if constexpr (EPI == EPI_SCALE_SKIP) {
-          // v = acc * s + bias * s into an fp32 tile in smem (chunk-rotated: conflict free for both the pixel-major
-          // writes and the coalesced reads), then a coalesced pass adds the fp32 skip row and writes the fp32
-          // stream + its bf16 copy straight to global memory.
-          float* tile = reinterpret_cast<float*>(stage);  // [128 px][64] fp32 = 32 KB = both staging buffers
-          float* sc_s = pool_s;                           // [64] scale, [64] bias*scale of the current image
+          // Per half of 32 channels: v = acc * s + bias * s (or r = acc + bias when the training forward saves r) into
+          // an fp32 tile in smem (chunk-rotated: conflict free for the pixel-major writes and the coalesced reads),
+          // then a coalesced pass adds the fp32 skip and writes the fp32 stream + its bf16 copy to global memory.
+          float* tile = reinterpret_cast<float*>(stage) + egrp * (128 * 32);  // [128 px][32] fp32 = 16 KB per group
+          float* sc_s = pool_s + egrp * 192;              // [64] scale, [64] bias*scale, [64] real scale
           const bool save_r = a.r_out != nullptr;         // training forward: tile = acc + b, scale applied below
-          named_bar_sync(1, 128);  // previous row's coalesced pass has finished with the tile (and with sc_s)
-          if (b != cur_img) {      // (uniform) new image: stage its scale vector
-            if (et < 64) {
-              const float sc = a.epi_stats ? svec_s[(b - bimg_first) * 64 + et]
-                                           : (a.svec != nullptr ? a.svec[static_cast<size_t>(b) * 64 + et] : 1.f);
-              sc_s[et] = save_r ? 1.f : sc;
-              sc_s[64 + et] = save_r ? bias_s[et] : bias_s[et] * sc;
-              sc_s[128 + et] = sc;
-            }
-            cur_img = b;
-            named_bar_sync(2, 128);
-          }
-#pragma unroll
+          const uint32_t bar_a = 1 + 2 * egrp, bar_b = 2 + 2 * egrp;
+          const int npx = min(128, a.W - seg * 128);      // valid pixels of this row segment
+          const int c4 = et & 7, pq = et >> 3;            // this thread: 4-channel group c4 of pixels pq + 16 i
+#pragma unroll 1
           for (int h = 0; h < 2; ++h) {
+            named_bar_sync(bar_a, 128);  // the previous coalesced pass has finished with the tile (and with sc_s)
+            if (h == 0 && b != cur_img) {  // (uniform) new image: stage its scale vector
+              if (et < 64) {
+                const float sc = a.epi_stats ? svec_s[(b - bimg_first) * 64 + et]
+                                             : (a.svec != nullptr ? a.svec[static_cast<size_t>(b) * 64 + et] : 1.f);
+                sc_s[et] = save_r ? 1.f : sc;
+                sc_s[64 + et] = save_r ? bias_s[et] : bias_s[et] * sc;
+                sc_s[128 + et] = sc;
+              }
+              cur_img = b;
+              named_bar_sync(bar_b, 128);
+            }
             uint32_t rv[32];
             tmem_ld_32x32b_x32(taddr + h * 32, rv);
             tmem_ld_wait();
@@ -644,7 +663,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               __syncwarp();
               if (lane == 0) mbar_arrive(&tempty[acc]);
             }
-            float4* trow = reinterpret_cast<float4*>(tile + m * 64);
+            float4* trow = reinterpret_cast<float4*>(tile + m * 32);
             const float4* sc4 = reinterpret_cast<const float4*>(sc_s) + h * 8;
             const float4* bs4 = reinterpret_cast<const float4*>(sc_s + 64) + h * 8;
 #pragma unroll
@@ -655,45 +674,44 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               o.y = fmaf(__uint_as_float(rv[4 * c + 1]), s4.y, b4.y);
               o.z = fmaf(__uint_as_float(rv[4 * c + 2]), s4.z, b4.z);
               o.w = fmaf(__uint_as_float(rv[4 * c + 3]), s4.w, b4.w);
-              trow[(h * 8 + c + m) & 15] = o;
+              trow[(c + m) & 7] = o;
             }
-          }
-          named_bar_sync(2, 128);
-          {
-            const int npx = min(128, a.W - seg * 128);  // valid pixels of this row segment
-            const int c4 = et & 15, pq = et >> 4;       // this thread: 4-channel group c4 of pixels pq + 8 i
-            const size_t e0 = ((static_cast<size_t>(b) * a.H + y) * a.W + seg * 128 + pq) * 64 + c4 * 4;
+            named_bar_sync(bar_b, 128);
+            const size_t e0 = ((static_cast<size_t>(b) * a.H + y) * a.W + seg * 128 + pq) * 64 + h * 32 + c4 * 4;
             float* o32 = a.out_f32 != nullptr ? a.out_f32 + e0 : nullptr;
             __nv_bfloat16* obf = a.out_bf16_direct + e0;
-            const float4* t4 = reinterpret_cast<const float4*>(tile);
-            const float4* sk4 = reinterpret_cast<const float4*>(skipbuf) + et;
-            const float4 sr4 = reinterpret_cast<const float4*>(sc_s + 128)[c4];
             __nv_bfloat16* rbf = save_r ? a.r_out + e0 : nullptr;
+            const float4* t4 = reinterpret_cast<const float4*>(tile);
+            const float4* sk4 = reinterpret_cast<const float4*>(skipbuf_g) + et;
+            const float4 sr4 = reinterpret_cast<const float4*>(sc_s + 128)[h * 8 + c4];
             asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int p = i * 8 + pq;
+            for (int i = 0; i < 8; ++i) {
+              const int p = i * 16 + pq;
               if (p < npx) {
-                float4 o = t4[p * 16 + ((c4 + p) & 15)];
+                float4 o = t4[p * 8 + ((c4 + p) & 7)];
                 if (save_r) {  // r = conv + b goes out as bf16 for the backward; the stream gets r * s + skip
                   uint2 rk;
                   rk.x = pack_bf16x2(o.x, o.y);
                   rk.y = pack_bf16x2(o.z, o.w);
-                  *reinterpret_cast<uint2*>(rbf + i * 512) = rk;
+                  *reinterpret_cast<uint2*>(rbf + i * 1024) = rk;
                   o.x *= sr4.x; o.y *= sr4.y; o.z *= sr4.z; o.w *= sr4.w;
                 }
                 if (has_skip) {
                   const float4 sk = sk4[i * 128];
                   o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
                 }
-                if (o32 != nullptr && !exp_no_f32st) *reinterpret_cast<float4*>(o32 + i * 512) = o;
+                if (o32 != nullptr && !exp_no_f32st) *reinterpret_cast<float4*>(o32 + i * 1024) = o;
                 uint2 pk;
                 pk.x = pack_bf16x2(o.x, o.y);
                 pk.y = pack_bf16x2(o.z, o.w);
-                if (!exp_no_bfst) *reinterpret_cast<uint2*>(obf + i * 512) = pk;
+                if (!exp_no_bfst) *reinterpret_cast<uint2*>(obf + i * 1024) = pk;
               }
             }
-            if (g + 1 < g1) issue_skip(g + 1);  // this thread's slots are free again: refill them for the next row
+            // this thread's skip slots are free again: refill them for the next half (of this row or of the next row
+            // this group owns)
+            if (h == 0) issue_skip(g, 1);
+            else if (g + kEpiGroups < g1) issue_skip(g + kEpiGroups, 0);
           }
         } else {
           const int sb = it & 1;
@@ -867,7 +885,7 @@ static int launch_one(const CUtensorMap& tin, const CUtensorMap& tout, const Con
   static const bool use_pdl = getenv("DFIR_PDL") == nullptr || atoi(getenv("DFIR_PDL")) != 0;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(INMODE == IN_FUSED ? kThreadsFused : kThreads);
+  cfg.blockDim = dim3(conv_threads<EPI, INMODE>());
   cfg.dynamicSmemBytes = L::total + 1024;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
