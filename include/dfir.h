@@ -164,6 +164,14 @@ int dfir_ca_scale_residual(const void* r, int r_is_bf16, const float* x_in, cons
                            int style, const float* ca_params, int C, int R, int M, int A, const float* attributes,
                            const float* sq, float res_scale, float* x_out, void* x_out_bf16, int B, int H, int W,
                            void* stream);
+/* The same with PALayer between the channel attention and the meta attention (QRCAB.forward,
+ * attention_manipulators/architectures.py:172-180 with include_pixel_attention):
+ *     u = r * CA(y) ;  u <- u * sigmoid(W2 relu(W1 u + b1) + b2)  (per pixel) ;  x_out = u * sq + x_in
+ * pa_params: W1[8][64] b1[8] W2[8] b2[1] (fp32); C must be 64, style != none. */
+int dfir_ca_pa_scale_residual(const void* r, int r_is_bf16, const float* x_in, const float* pool_rows, int pool_nrows,
+                              int style, const float* ca_params, const float* pa_params, int R, int M, int A,
+                              const float* attributes, const float* sq, float* x_out, void* x_out_bf16, int B, int H,
+                              int W, void* stream);
 
 /* per-row channel sums of an fp32 NHWC tensor: pool_rows[b][y][c] = sum_x in[b][y][x][c] (fp32 mode only;
  * the tensor-core conv produces them in its epilogue). */
@@ -217,6 +225,11 @@ typedef struct dfir_qrcan_net {
   const float* conv_wT_f32;         /* [n_trunk][9][C][C] */
   const float* up_wT_f32;           /* [n_up][9][r*r*C][C] */
   const float* tail_wT_f32;         /* [9][out_feats][C] (both precisions: the 3 -> C gradient conv runs on CUDA cores) */
+  /* PALayer (attention_manipulators/architectures.py:13-26), present when include_pixel_attention: per block
+   * pa.0.weight[8][64], pa.0.bias[8], pa.2.weight[8], pa.2.bias[1]; NULL = no pixel attention.  n_feats must be 64;
+   * the block chain then runs the streamer schedule (schedule is ignored). */
+  const float* pa_blob;             /* [n_groups*n_blocks][pa_stride] */
+  int pa_stride;
 } dfir_qrcan_net;
 
 size_t dfir_qrcan_workspace_bytes(const dfir_qrcan_net* net, int B, int H, int W, int precision);

@@ -160,7 +160,8 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
   //     directly: r never exists in memory and there is no elementwise pass.
   //   1 fused-in : `r*s + x` folded into the next conv's input path (dfir_conv3x3_c64_fused).
   //   2 streamer : separate bandwidth-shaped elementwise kernel (dfir_ca_scale_residual).
-  const int sched = n->schedule;
+  const int sched = n->pa_blob != nullptr ? 2 : n->schedule;  // pixel attention lives in the streamer kernel
+  auto pa_of = [&](int blk) { return n->pa_blob != nullptr ? n->pa_blob + static_cast<size_t>(blk) * n->pa_stride : nullptr; };
 
   const float* xcur = w.Hh;
   const int gb = (sa.stages & ST_GROUPS) ? sa.g_begin : 0, ge = (sa.stages & ST_GROUPS) ? sa.g_end : 0;
@@ -208,7 +209,7 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
       if (sched == 2) {
         // x_{b+1} = r * s + x_b  (fp32 stream, in place after the first block) + bf16 copy for the next conv
         DFIR_TRY(scale_residual(w.R, 1, b == 0 ? skip32 : w.XB, w.pool, nseg * H, make_ap(n, blk), attr_c, sq, 1.f,
-                                w.XB, w.XBbf, Bc, H, W, C, st));
+                                w.XB, w.XBbf, Bc, H, W, C, st, nullptr, pa_of(blk)));
       }
     }
     if (n->no_group_conv) {  // Q-EDSR / Q-SAN groups: the chain of blocks has no tail conv of its own
@@ -303,7 +304,8 @@ int qrcan_forward_f32(const dfir_qrcan_net* n, const float* x, const float* attr
       if (n->style != DFIR_STYLE_NONE) DFIR_TRY(pool_rows_f32(w.R32, w.pool, Bc, H, W, C, st));
       const float* sq = n->any_q ? w.sq + (static_cast<size_t>(blk) * B + b0) * C : nullptr;
       DFIR_TRY(scale_residual(w.R32, 0, cin, w.pool, H, make_ap(n, blk), attr + static_cast<size_t>(b0) * n->attr_size,
-                              sq, 1.f, w.XB, nullptr, Bc, H, W, C, st));
+                              sq, 1.f, w.XB, nullptr, Bc, H, W, C, st, nullptr,
+                              n->pa_blob != nullptr ? n->pa_blob + static_cast<size_t>(blk) * n->pa_stride : nullptr));
     }
     if (n->no_group_conv) {
       if (sa.group_out != nullptr && nb > 0 &&
@@ -515,6 +517,17 @@ int dfir_ca_scale_residual(const void* r, int r_is_bf16, const float* x_in, cons
                         reinterpret_cast<__nv_bfloat16*>(x_out_bf16), B, H, W, C, S(stream));
 }
 
+int dfir_ca_pa_scale_residual(const void* r, int r_is_bf16, const float* x_in, const float* pool_rows, int pool_nrows,
+                              int style, const float* ca_params, const float* pa_params, int R, int M, int A,
+                              const float* attributes, const float* sq, float* x_out, void* x_out_bf16, int B, int H,
+                              int W, void* stream) {
+  AttnParams ap{};
+  ap.style = style; ap.C = 64; ap.R = R; ap.M = M; ap.A = A; ap.w[0] = ca_params;
+  if (style == DFIR_STYLE_NONE || pool_rows == nullptr || ca_params == nullptr || pa_params == nullptr) return DFIR_ERR_ARG;
+  return scale_residual(r, r_is_bf16, x_in, pool_rows, pool_nrows, ap, attributes, sq, 1.f, x_out,
+                        reinterpret_cast<__nv_bfloat16*>(x_out_bf16), B, H, W, 64, S(stream), nullptr, pa_params);
+}
+
 int dfir_pool_rows_f32(const float* in, float* pool_rows, int B, int H, int W, int C, void* stream) {
   return pool_rows_f32(in, pool_rows, B, H, W, C, S(stream));
 }
@@ -534,7 +547,7 @@ long long dfir_qrcan_launch_count(const dfir_qrcan_net* net, int B, int H, int W
   const long long nb = net->n_blocks, ng = net->n_groups;
   long long per_chunk;
   if (precision == DFIR_PREC_BF16_TC) {
-    per_chunk = 1 + ng * (nb * (net->schedule == 2 ? 3 : 2) + (net->no_group_conv ? 0 : 1)) + 1 +
+    per_chunk = 1 + ng * (nb * ((net->schedule == 2 || net->pa_blob != nullptr) ? 3 : 2) + (net->no_group_conv ? 0 : 1)) + 1 +
                 static_cast<long long>(nup) * r * r + 1;
   } else {
     const long long pool = net->style != DFIR_STYLE_NONE ? 1 : 0;

@@ -109,7 +109,8 @@ int meta_attention(const float* meta, const float* w1, const float* b1, const fl
                    cudaStream_t s);
 int scale_residual(const void* r, int r_is_bf16, const float* x_in, const float* pool_rows, int pool_nrows,
                    const AttnParams& ap, const float* attributes, const float* sq, float res_scale, float* x_out,
-                   __nv_bfloat16* x_out_bf16, int B, int H, int W, int C, cudaStream_t s, float* y_out = nullptr);
+                   __nv_bfloat16* x_out_bf16, int B, int H, int W, int C, cudaStream_t s, float* y_out = nullptr,
+                   const float* pa = nullptr);
 int ca_from_stats(const float* pool_rows, const float* col_first, const float* col_last, const void* w2_packed,
                   const float* bias2, const AttnParams& ap, const float* attributes, const float* sq, float* svec, int B,
                   int H, int W, cudaStream_t s);

@@ -235,13 +235,16 @@ scale_residual_kernel(const void* __restrict__ r_, const float* __restrict__ x_i
                       const float* __restrict__ pool_rows, int pool_nrows, AttnParams ap,
                       const float* __restrict__ attributes, const float* __restrict__ sq, float res_scale,
                       float* __restrict__ x_out, __nv_bfloat16* __restrict__ x_out_bf16, int HW, int C,
-                      float* __restrict__ y_out) {
+                      float* __restrict__ y_out, const float* __restrict__ pa) {
   __shared__ float y_s[256];
   __shared__ float s_s[256];
   __shared__ float attr_s[512];
   __shared__ float tmp[4 * 256];
+  __shared__ float pa_s[8 * 64 + 8 + 8 + 4];  // PALayer: W1[8][64] b1[8] W2[8] b2 (C == 64 only)
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
+  if (pa != nullptr)
+    for (int i = tid; i < 8 * 64 + 17; i += 256) pa_s[i] = pa[i];
 
   if (ap.style != DFIR_STYLE_NONE) {
     // deterministic pooled mean: 256/C row groups, fixed-order combine
@@ -263,7 +266,8 @@ scale_residual_kernel(const void* __restrict__ r_, const float* __restrict__ x_i
     }
     __syncthreads();
     attn_vector(BlockGroup{}, ap.style, ap.w[0], C, ap.R, ap.M, attr_s, y_s, s_s, tmp);
-    if (tid < C) s_s[tid] *= (sq != nullptr ? sq[static_cast<size_t>(b) * C + tid] : 1.f);
+    // with pixel attention the meta scale is applied after it (QRCAB.forward, architectures.py:174-178)
+    if (tid < C && pa == nullptr) s_s[tid] *= (sq != nullptr ? sq[static_cast<size_t>(b) * C + tid] : 1.f);
   } else {
     if (tid < C) s_s[tid] = res_scale * (sq != nullptr ? sq[static_cast<size_t>(b) * C + tid] : 1.f);
   }
@@ -277,6 +281,70 @@ scale_residual_kernel(const void* __restrict__ r_, const float* __restrict__ x_i
 
   const size_t img_off = static_cast<size_t>(b) * HW * C;
   const long long nvec = static_cast<long long>(HW) * lanes_per_pix;  // 8-channel vectors in this image
+  if (pa != nullptr) {
+    // PALayer (architectures.py:13-26): r <- r * sigmoid(W2 relu(W1 r + b1) + b2), one scalar per pixel, between the
+    // channel attention and the meta attention.  The 8 threads of a pixel each hold 8 channels: partial 64 -> 8
+    // products, butterfly over the 8 lanes, then every lane evaluates the 8 -> 1 layer.
+    float sqv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sqv[i] = (ap.style != DFIR_STYLE_NONE && sq != nullptr) ? sq[static_cast<size_t>(b) * C + c0 + i] : 1.f;
+    for (long long base = static_cast<long long>(blockIdx.x) * 256; base < nvec;
+         base += static_cast<long long>(gridDim.x) * 256) {
+      const long long vi = base + tid;
+      const bool active = vi < nvec;
+      const size_t e = img_off + static_cast<size_t>(active ? vi : 0) * 8;
+      float u[8];
+      if (R_BF16) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(r_) + e);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(h[i]);
+          u[2 * i] = f.x;
+          u[2 * i + 1] = f.y;
+        }
+      } else {
+        const float4 a0 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(r_) + e);
+        const float4 a1 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(r_) + e + 4);
+        u[0] = a0.x; u[1] = a0.y; u[2] = a0.z; u[3] = a0.w; u[4] = a1.x; u[5] = a1.y; u[6] = a1.z; u[7] = a1.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) u[i] *= sc[i];
+      float hsum[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t = fmaf(pa_s[j * 64 + c0 + i], u[i], t);
+        hsum[j] = t;
+      }
+#pragma unroll
+      for (int mask = 1; mask < 8; mask <<= 1)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hsum[j] += __shfl_xor_sync(0xffffffffu, hsum[j], mask);
+      float z = pa_s[8 * 64 + 16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z = fmaf(pa_s[8 * 64 + 8 + j], fmaxf(hsum[j] + pa_s[8 * 64 + j], 0.f), z);
+      const float pmap = 1.f / (1.f + expf(-z));
+      if (active) {
+        const float4 x0 = *reinterpret_cast<const float4*>(x_in + e);
+        const float4 x1 = *reinterpret_cast<const float4*>(x_in + e + 4);
+        const float xi[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaf(u[i] * pmap, sqv[i], xi[i]);
+        *reinterpret_cast<float4*>(x_out + e) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(x_out + e + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        if (x_out_bf16 != nullptr) {
+          __align__(16) __nv_bfloat162 pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pk[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+          *reinterpret_cast<uint4*>(x_out_bf16 + e) = *reinterpret_cast<uint4*>(pk);
+        }
+      }
+    }
+    return;
+  }
   for (long long vi = static_cast<long long>(blockIdx.x) * 256 + tid; vi < nvec;
        vi += static_cast<long long>(gridDim.x) * 256) {
     const size_t e = img_off + static_cast<size_t>(vi) * 8;
@@ -482,8 +550,9 @@ int ca_from_stats(const float* pool_rows, const float* col_first, const float* c
 
 int scale_residual(const void* r, int r_is_bf16, const float* x_in, const float* pool_rows, int pool_nrows,
                    const AttnParams& ap, const float* attributes, const float* sq, float res_scale, float* x_out,
-                   __nv_bfloat16* x_out_bf16, int B, int H, int W, int C, cudaStream_t s, float* y_out) {
+                   __nv_bfloat16* x_out_bf16, int B, int H, int W, int C, cudaStream_t s, float* y_out, const float* pa) {
   if (B == 0 || H * W == 0) return DFIR_OK;
+  if (pa != nullptr && (C != 64 || ap.style == DFIR_STYLE_NONE)) return DFIR_ERR_ARG;
   if (C % 8 != 0 || C > 256 || 256 % C != 0 || ap.A > 512 || ap.M > 448) return DFIR_ERR_ARG;
   const long long nvec = static_cast<long long>(H) * W * (C / 8);
   long long per_img = (nvec + 256 * 8 - 1) / (256 * 8);
@@ -493,10 +562,10 @@ int scale_residual(const void* r, int r_is_bf16, const float* x_in, const float*
   dim3 grid(static_cast<unsigned>(per_img), B);
   if (r_is_bf16)
     scale_residual_kernel<true><<<grid, 256, 0, s>>>(r, x_in, pool_rows, pool_nrows, ap, attributes, sq, res_scale,
-                                                     x_out, x_out_bf16, H * W, C, y_out);
+                                                     x_out, x_out_bf16, H * W, C, y_out, pa);
   else
     scale_residual_kernel<false><<<grid, 256, 0, s>>>(r, x_in, pool_rows, pool_nrows, ap, attributes, sq, res_scale,
-                                                      x_out, x_out_bf16, H * W, C, y_out);
+                                                      x_out, x_out_bf16, H * W, C, y_out, pa);
   return ok_or_cuda();
 }
 

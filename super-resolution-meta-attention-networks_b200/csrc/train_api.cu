@@ -71,6 +71,7 @@ bool train_supported(const dfir_qrcan_net* n, int precision) {
   int r = 0;
   if (n == nullptr || up_stages(n->scale, &r) < 0) return false;
   if (n->n_groups < 1 || n->n_blocks < 1) return false;
+  if (n->pa_blob != nullptr) return false;  // pixel attention has no backward kernels yet
   if (n->no_group_conv && n->n_groups != 1) return false;
   if (n->style != DFIR_STYLE_NONE && n->style != DFIR_STYLE_STANDARD && n->style != DFIR_STYLE_MODULATE &&
       n->style != DFIR_STYLE_MAX_CONCAT)

@@ -45,6 +45,7 @@ class QrcanNet(C.Structure):
         ("meta_w1", C.c_void_p), ("meta_b1", C.c_void_p), ("meta_w2", C.c_void_p), ("meta_b2", C.c_void_p),
         ("conv_wT_bf16", C.c_void_p), ("conv_wT_f32", C.c_void_p), ("up_wT_f32", C.c_void_p),
         ("tail_wT_f32", C.c_void_p),
+        ("pa_blob", C.c_void_p), ("pa_stride", C.c_int),
     ]
 
 
@@ -79,6 +80,8 @@ PROTOTYPES = {
     "dfir_meta_attention": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _f, _vp]),
     "dfir_ca_scale_residual": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp,
                                     _i, _i, _i, _vp]),
+    "dfir_ca_pa_scale_residual": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i,
+                                       _vp]),
     "dfir_pool_rows_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "dfir_qrcan_workspace_bytes": (_sz, [C.POINTER(QrcanNet), _i, _i, _i, _i]),
     "dfir_qrcan_launch_count": (C.c_longlong, [C.POINTER(QrcanNet), _i, _i, _i, _i]),

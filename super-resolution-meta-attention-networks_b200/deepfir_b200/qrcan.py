@@ -178,8 +178,6 @@ class QRCAN(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("deepfir_b200.%s runs on a CUDA (sm_100a) device only: there is no CPU path"
                                % type(self).__name__)
-        if self.cfg.get("include_pixel_attention"):
-            raise NotImplementedError("pixel attention (include_pixel_attention) is not on the B200 path yet")
         from . import ops  # registers torch.ops.dfir.*
         training = torch.is_grad_enabled() and next(self.parameters()).requires_grad
         packed = self.packed(training=training)
@@ -214,6 +212,7 @@ class QRCAN(nn.Module):
             head=self.head[0], trunk=trunk, ups=[m for m in self.tail[0] if isinstance(m, nn.Conv2d)],
             tail=self.tail[1], ca=[blk.final_body.flat_params() for blk in blocks],
             ca_params=[blk.final_body.param_list() for blk in blocks],
+            pa=[(blk.pa_node.pa[0], blk.pa_node.pa[2]) if blk.pa else None for blk in blocks],
             meta=[tuple(blk.q_node.fcs()) if blk.q_layer else None for blk in blocks])
 
     def packed(self, training=False):
@@ -405,6 +404,15 @@ class PackedQrcan:
                 self.meta = [None] * 4
                 q_enabled = None
 
+            # pixel attention (PALayer) parameters, one row per block
+            pas = spec.get("pa") or []
+            pa_blob = None
+            if any(p is not None for p in pas):
+                if C_ != 64 or not all(p is not None for p in pas):
+                    raise NotImplementedError("pixel attention is implemented for 64-feature Q-RCAN blocks")
+                pa_blob = keep(torch.stack([torch.cat([f1.weight.reshape(-1), f1.bias.reshape(-1), f2.weight.reshape(-1),
+                                                       f2.bias.reshape(-1)]) for f1, f2 in pas]).to(**f32).contiguous())
+
         style = STYLES[cfg["style"]]
         self.attr_size = C_ if cfg["style"] == "modulate" else M
         if any_q and self.attr_size != M:
@@ -423,6 +431,7 @@ class PackedQrcan:
         d.conv_b, d.up_b, d.tail_b, d.head_b = ptr(conv_b), ptr(up_b), ptr(tail_b), ptr(head_b)
         d.ca_blob, d.ca_stride = ptr(ca_blob), int(ca_stride)
         d.meta_w1, d.meta_b1, d.meta_w2, d.meta_b2 = [ptr(t) for t in self.meta]
+        d.pa_blob, d.pa_stride = ptr(pa_blob), (int(pa_blob.shape[1]) if pa_blob is not None else 0)
         self.desc = d
         self.device = dev
         self.scale = net.scale
@@ -435,8 +444,8 @@ class PackedQrcan:
         self.ws_owner = None
         # device pointer tables of the fp32 parameters: lets the C side refresh every kernel-format buffer in a few
         # launches (styles whose attention block has the 4-tensor layout; the others are rebuilt from Python)
-        self.can_repack = "ca_params" in spec and cfg["style"] in ("none", "standard", "modulate", "max_concat",
-                                                                   "softmax")
+        self.can_repack = "ca_params" in spec and pa_blob is None and cfg["style"] in ("none", "standard", "modulate",
+                                                                                        "max_concat", "softmax")
         if self.can_repack:
             self._spec_params = dict(
                 conv_w=[m.weight for m in trunk], conv_b=[m.bias for m in trunk],

@@ -26,6 +26,17 @@ def max_over_ranks(value: float, device=None) -> float:
     return float(t.item())
 
 
+def allreduce_mean_(flat: torch.Tensor) -> torch.Tensor:
+    """data-parallel training's one exchange step: average the flat gradient buffer over all ranks, in place (NCCL on
+    GPUs, gloo in the CPU tests).  No-op outside torch.distributed or with a single rank."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return flat
+    dist.all_reduce(flat)
+    flat.div_(dist.get_world_size())
+    return flat
+
+
 def run_sharded(forward_fn, x, meta, rank: int, world: int):
     """forward_fn(x_slice, meta_slice) on this rank's slice; returns (start, stop, output_slice)"""
     a, b = shard_range(x.shape[0], rank, world)

@@ -13,6 +13,7 @@ import ctypes as C
 import torch
 
 from . import _lib
+from .sharding import allreduce_mean_
 
 
 def _stream(dev):
@@ -124,10 +125,8 @@ class _QrcanTrain(torch.autograd.Function):
                 x, attr = ctx.saved_tensors
                 _run_backward(lib, packed, gstruct, x, attr, gout, ctx.ws)
         flat = packed.grad_flat[which]
-        if getattr(net, "ddp_allreduce", True) and torch.distributed.is_available() \
-                and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-            torch.distributed.all_reduce(flat)
-            flat.div_(torch.distributed.get_world_size())
+        if getattr(net, "ddp_allreduce", True):
+            allreduce_mean_(flat)
         views = packed.grad_views[which]
         acc_p, acc_g = [], []
         for p, g in zip(params, views):

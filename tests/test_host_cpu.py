@@ -210,3 +210,50 @@ def test_shard_range_properties():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+_DDP_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "super-resolution-meta-attention-networks_b200"))
+from deepfir_b200.sharding import allreduce_mean_, env_rank_world, shard_range
+from oracle.synth import synth_target
+from tests.golden_util import load_golden, case_tensors, oracle_forward
+rank, world, _ = env_rank_world()
+dist.init_process_group("gloo", rank=rank, world_size=world)
+ref, info = load_golden("qrcan_standard_g2b2")
+sd, x, meta = case_tensors(info)            # 2 images: one per rank
+y = synth_target(ref.shape)
+
+
+def grads(xs, ms, ys):
+    leaves = {{k: v.clone().requires_grad_(True) for k, v in sd.items()}}
+    torch.nn.functional.l1_loss(oracle_forward(info, leaves, xs, ms), ys).backward()
+    return torch.cat([leaves[k].grad.reshape(-1) for k in sorted(leaves)])
+
+
+a, b = shard_range(x.shape[0], rank, world)
+flat = grads(x[a:b], meta[a:b], y[a:b])      # this rank's gradient of ITS mean-L1 loss, one flat buffer
+allreduce_mean_(flat)                        # the data-parallel exchange step
+full = grads(x, meta, y)                     # what one process sees on the whole batch
+err = float((flat - full).norm() / full.norm())
+assert err < 1e-5, err
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_rank_gradient_allreduce_equals_full_batch_gradient_on_gloo():
+    """training N>1 path on CPU (gloo, world 2): per-rank mean-L1 gradients, averaged over ranks through the flat
+    buffer all-reduce the GPU path uses (deepfir_b200/train.py), equal the full-batch gradient (SURVEY.md §8e)."""
+    with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as fh:
+        fh.write(_DDP_WORKER.format(root=ROOT))
+        script = fh.name
+    try:
+        res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                              "--master-addr", "127.0.0.1", "--master-port", "29533", script],
+                             capture_output=True, text=True, timeout=300,
+                             env=dict(os.environ, OMP_NUM_THREADS="2", PYTHONDONTWRITEBYTECODE="1"))
+    finally:
+        os.unlink(script)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count("ok") == 2

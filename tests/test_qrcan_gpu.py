@@ -7,7 +7,7 @@ from tests.golden_util import case_tensors, golden_names, load_golden, max_norm_
 
 pytestmark = pytest.mark.gpu
 
-QRCAN_CASES = [n for n in golden_names() if n.startswith("qrcan") and "pa_" not in n]
+QRCAN_CASES = [n for n in golden_names() if n.startswith("qrcan")]  # incl. pixel attention + selective q layers
 
 
 def _build(info, precision, **extra):
