@@ -24,6 +24,20 @@ struct NamedGroup {  // a subset of warps synchronised through a named barrier
   __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 };
 
+// number of fp32 parameters of one block's QCALayer in the order above
+__host__ __device__ inline int attn_param_count(int style, int C, int R, int M) {
+  switch (style) {
+    case DFIR_STYLE_STANDARD:
+    case DFIR_STYLE_MODULATE: return R * C + R + C * R + C;
+    case DFIR_STYLE_MAX_CONCAT:
+    case DFIR_STYLE_SOFTMAX: return R * (C + M) + R + C * R + C;
+    case DFIR_STYLE_MINI_CONCAT: return R * C + R + C * (R + M) + C;
+    case DFIR_STYLE_EXTENDED:
+      return (C / 2) * (C + M) + C / 2 + (C / 4) * (C / 2 + M) + C / 4 + R * (C / 4 + M) + R + C * R + C;
+    default: return 0;
+  }
+}
+
 template <class G>
 __device__ void fc_layer(const G& g, const float* __restrict__ w, const float* __restrict__ bias, const float* in_a,
                          int na, const float* in_b, int nb, float* out, int nout,

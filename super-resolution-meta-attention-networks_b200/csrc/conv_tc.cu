@@ -882,7 +882,7 @@ static int launch_one(const CUtensorMap& tin, const CUtensorMap& tout, const Con
       return DFIR_ERR_CUDA;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  static const bool use_pdl = getenv("DFIR_PDL") == nullptr || atoi(getenv("DFIR_PDL")) != 0;
+  static const bool use_pdl = getenv("DFIR_PDL") == nullptr || (atoi(getenv("DFIR_PDL")) & 1) != 0;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(conv_threads<EPI, INMODE>());
@@ -898,6 +898,12 @@ static int launch_one(const CUtensorMap& tin, const CUtensorMap& tout, const Con
 
 int debug_watchdog(unsigned int* out8, int reset) {
   if (cudaMemcpyFromSymbol(out8, g_dfir_watchdog, 8 * sizeof(unsigned int)) != cudaSuccess) return DFIR_ERR_CUDA;
+  if (out8[0] == 0u) {  // nothing recorded by the conv: report the weight-gradient kernel's record (tags 21-26)
+    if (wgrad_tc_watchdog(out8, reset) != DFIR_OK) return DFIR_ERR_CUDA;
+  } else if (reset) {
+    unsigned int dummy[8];
+    wgrad_tc_watchdog(dummy, reset);
+  }
   if (reset == 2) {  // debugging: also print the block-0 progress probes
     unsigned int pg[16];
     if (cudaMemcpyFromSymbol(pg, g_dfir_progress, sizeof(pg)) == cudaSuccess) {

@@ -160,7 +160,13 @@ int attn_param_grads(const float* sig, int sig_stride, const float* attributes, 
                      cudaStream_t s);
 int wgrad_c64_grid(int B, int H, int W, int num_sms);
 int wgrad_c64_bf16(const void* dy, long long dy_pix, long long dy_row, long long dy_img, const void* x, float* scratch,
-                   int B, int H, int W, int num_sms, cudaStream_t s, int* S_out);
+                   int B, int H, int W, int num_sms, cudaStream_t s, int* S_out);   // mma.sync version
+int wgrad_c64_tc(const void* dy, long long dy_pix, long long dy_row, long long dy_img, const void* x, float* scratch, int B,
+                 int H, int W, int num_sms, cudaStream_t s, int* S_out);            // tcgen05 version (default)
+int wgrad_tc_watchdog(unsigned int* out8, int reset);
+// dispatcher: DFIR_WGRAD=mma selects the mma.sync kernel
+int wgrad_c64(const void* dy, long long dy_pix, long long dy_row, long long dy_img, const void* x, float* scratch, int B,
+              int H, int W, int num_sms, cudaStream_t s, int* S_out);
 int nchw_to_nhwc_bf16(const float* in, __nv_bfloat16* out, int B, int C, int H, int W, cudaStream_t s);
 int f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t s);
 

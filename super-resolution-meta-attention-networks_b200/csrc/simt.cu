@@ -3,6 +3,8 @@
 // bound pieces: they are written for coalesced 16-byte accesses, not tensor cores.
 #include "kernels.h"
 #include "attn.cuh"
+#include "launch.cuh"
+#include "ptx.cuh"
 
 namespace dfir {
 
@@ -241,10 +243,19 @@ scale_residual_kernel(const void* __restrict__ r_, const float* __restrict__ x_i
   __shared__ float attr_s[512];
   __shared__ float tmp[4 * 256];
   __shared__ float pa_s[8 * 64 + 8 + 8 + 4];  // PALayer: W1[8][64] b1[8] W2[8] b2 (C == 64 only)
+  __shared__ float caw_s[1024];               // this block's attention-MLP parameters (when they fit)
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
+  // constants first: under programmatic dependent launch this part overlaps the tail of the previous kernel
   if (pa != nullptr)
     for (int i = tid; i < 8 * 64 + 17; i += 256) pa_s[i] = pa[i];
+  const int n_caw = attn_param_count(ap.style, C, ap.R, ap.M);
+  const float* ca_w = ap.w[0];
+  if (n_caw > 0 && n_caw <= 1024) {
+    for (int i = tid; i < n_caw; i += 256) caw_s[i] = ap.w[0][i];
+    ca_w = caw_s;
+  }
+  ptx::grid_dep_wait();  // (no early launch_dependents: a resident, waiting successor would starve our later waves)
 
   if (ap.style != DFIR_STYLE_NONE) {
     // deterministic pooled mean: 256/C row groups, fixed-order combine
@@ -265,7 +276,7 @@ scale_residual_kernel(const void* __restrict__ r_, const float* __restrict__ x_i
       if (y_out != nullptr && blockIdx.x == 0) y_out[static_cast<size_t>(b) * C + tid] = y_s[tid];  // saved for backward
     }
     __syncthreads();
-    attn_vector(BlockGroup{}, ap.style, ap.w[0], C, ap.R, ap.M, attr_s, y_s, s_s, tmp);
+    attn_vector(BlockGroup{}, ap.style, ca_w, C, ap.R, ap.M, attr_s, y_s, s_s, tmp);
     // with pixel attention the meta scale is applied after it (QRCAB.forward, architectures.py:174-178)
     if (tid < C && pa == nullptr) s_s[tid] *= (sq != nullptr ? sq[static_cast<size_t>(b) * C + tid] : 1.f);
   } else {
@@ -560,13 +571,12 @@ int scale_residual(const void* r, int r_is_bf16, const float* x_in, const float*
   if (per_img > cap) per_img = cap;
   if (per_img < 1) per_img = 1;
   dim3 grid(static_cast<unsigned>(per_img), B);
+  const int HW = H * W;
   if (r_is_bf16)
-    scale_residual_kernel<true><<<grid, 256, 0, s>>>(r, x_in, pool_rows, pool_nrows, ap, attributes, sq, res_scale,
-                                                     x_out, x_out_bf16, H * W, C, y_out, pa);
-  else
-    scale_residual_kernel<false><<<grid, 256, 0, s>>>(r, x_in, pool_rows, pool_nrows, ap, attributes, sq, res_scale,
-                                                      x_out, x_out_bf16, H * W, C, y_out, pa);
-  return ok_or_cuda();
+    return launch_pdl(PDL_SIMT, scale_residual_kernel<true>, grid, dim3(256), 0, s, r, x_in, pool_rows, pool_nrows, ap, attributes, sq,
+                      res_scale, x_out, x_out_bf16, HW, C, y_out, pa) == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
+  return launch_pdl(PDL_SIMT, scale_residual_kernel<false>, grid, dim3(256), 0, s, r, x_in, pool_rows, pool_nrows, ap, attributes, sq,
+                    res_scale, x_out, x_out_bf16, HW, C, y_out, pa) == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
 }
 
 }  // namespace dfir

@@ -368,7 +368,7 @@ int train_forward_f32(const Ctx& c, const float* x, const float* attr, float* ou
 // weight + bias gradient of trunk conv `widx` (tensor-core path): dy, xin bf16 dense NHWC
 int wgrad_tc(const Ctx& c, const dfir_qrcan_params* gr, const void* dy, const void* xin, int widx) {
   int S_ = 0;
-  DFIR_TRY(wgrad_c64_bf16(dy, 0, 0, 0, xin, c.w.wpart, c.B, c.H, c.W, c.sms, c.st, &S_));
+  DFIR_TRY(wgrad_c64(dy, 0, 0, 0, xin, c.w.wpart, c.B, c.H, c.W, c.sms, c.st, &S_));
   return wgrad_reduce(c.w.wpart, c.w.wpart + static_cast<size_t>(S_) * 9 * 64 * 64, S_, 64, 64, gr->conv_w, widx, nullptr,
                       gr->conv_b, widx, nullptr, 0, 1, c.st);
 }
@@ -406,7 +406,7 @@ int train_backward_tc(const Ctx& c, const dfir_qrcan_params* gr, const float* x,
       const long long ps = static_cast<long long>(r) * C * 2, rs = static_cast<long long>(r) * wd * C * 2;
       const long long is = static_cast<long long>(h) * wd * C * 2;
       int S_ = 0;
-      DFIR_TRY(wgrad_c64_bf16(slice, ps, rs, is, X, w.wpart, B, hh, ww, c.sms, c.st, &S_));
+      DFIR_TRY(wgrad_c64(slice, ps, rs, is, X, w.wpart, B, hh, ww, c.sms, c.st, &S_));
       DFIR_TRY(wgrad_reduce(w.wpart, w.wpart + static_cast<size_t>(S_) * 9 * 64 * 64, S_, 64, 64, gr->up_w, t, nullptr,
                             gr->up_b, t, nullptr, s, r * r, c.st));
       ConvTcDesc d = tc_desc(c, tc_wT(c, c.n_trunk + t * r * r + s), nullptr, EPI_SCALE_SKIP, hh, ww);
@@ -683,7 +683,7 @@ int dfir_conv3x3_wgrad_c64(const void* dy, long long dps, long long drs, long lo
     return DFIR_ERR_CUDA;
   int S_ = 0;
   float* sc = reinterpret_cast<float*>(scratch);
-  DFIR_TRY(wgrad_c64_bf16(dy, dps, drs, dis, x, sc, B, H, W, std::min(sms, 160), S(stream), &S_));
+  DFIR_TRY(wgrad_c64(dy, dps, drs, dis, x, sc, B, H, W, std::min(sms, 160), S(stream), &S_));
   return wgrad_reduce(sc, sc + static_cast<size_t>(S_) * 9 * 64 * 64, S_, 64, 64, nullptr, 0, dw, nullptr, 0, db, co_begin,
                       co_stride, S(stream));
 }

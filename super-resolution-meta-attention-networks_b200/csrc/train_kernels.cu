@@ -5,6 +5,9 @@
 // 3-channel head/tail weight gradients, and the batched (pointer-table driven) re-packing of the fp32 parameters
 // into kernel layouts after every optimizer step.
 #include "kernels.h"
+#include "attn.cuh"
+#include "launch.cuh"
+#include "ptx.cuh"
 
 #include <algorithm>
 
@@ -257,6 +260,13 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bwd_reduce_ca_kernel(const float* __restrict__ g, const T* __restrict__ r, float* __restrict__ part, int HW, int C,
                      int nchunk, CaBwdArgs a, unsigned int* __restrict__ tickets) {
+  // constants first (overlaps the previous kernel's tail under programmatic dependent launch)
+  __shared__ float caw_s[1024];
+  const int n_caw = attn_param_count(a.style, a.C, a.R, a.M);
+  const bool caw_in_smem = n_caw > 0 && n_caw <= 1024;
+  if (caw_in_smem)
+    for (int i = threadIdx.x; i < n_caw; i += 256) caw_s[i] = a.ca[i];
+  ptx::grid_dep_wait();  // (no early launch_dependents: a resident, waiting successor would starve our later waves)
   bwd_reduce_gr_body<T>(g, r, part, HW, C, nchunk);
   __shared__ unsigned int last;
   __threadfence();
@@ -266,7 +276,9 @@ bwd_reduce_ca_kernel(const float* __restrict__ g, const T* __restrict__ r, float
   if (last == 0u) return;
   __threadfence();
   if (threadIdx.x == 0) tickets[blockIdx.y] = 0u;
-  ca_backward_image(a, blockIdx.y, threadIdx.x, 256);
+  CaBwdArgs la = a;
+  if (caw_in_smem) la.ca = caw_s;
+  ca_backward_image(la, blockIdx.y, threadIdx.x, 256);
 }
 
 // dr = g * s[b][c] + dyv[b][c]   (dL/d conv2 output of the block), written in the operand format T
@@ -274,6 +286,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 form_dr_kernel(const float* __restrict__ g, const float* __restrict__ svec, const float* __restrict__ dyv,
                T* __restrict__ dr, int HW, int C) {
+  ptx::grid_dep_wait();  // (no early launch_dependents: a resident, waiting successor would starve our later waves)
   const int b = blockIdx.y, tid = threadIdx.x;
   const int lpp = C / 8;
   const int c0 = (tid % lpp) * 8;
@@ -299,6 +312,7 @@ form_dr_kernel(const float* __restrict__ g, const float* __restrict__ svec, cons
 // out32 = a + b (either may alias out32), optional bf16 copy
 __global__ void add_f32_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out,
                                uint2* __restrict__ out_bf16, long long n4) {
+  ptx::grid_dep_wait();  // (no early launch_dependents: a resident, waiting successor would starve our later waves)
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 x = a[i], y = b[i];
@@ -410,6 +424,7 @@ __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ dbpart, int S, int Cin, int n_rows,
                     float* const* __restrict__ w_tbl, int w_idx, float* w_direct, float* const* __restrict__ b_tbl,
                     int b_idx, float* b_direct, int co_begin, int co_stride) {
+  ptx::grid_dep_wait();  // (no early launch_dependents: a resident, waiting successor would starve our later waves)
   __shared__ float red[4][64];
   const int total = 9 * Cin * n_rows;
   const int o = threadIdx.x & 63, grp = threadIdx.x >> 6;
@@ -678,10 +693,10 @@ int bwd_reduce_ca(const float* g, const void* r, int r_is_bf16, float* part, uns
   const int nchunk = a.nchunk;
   dim3 grid(nchunk, B);
   if (r_is_bf16)
-    bwd_reduce_ca_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(g, reinterpret_cast<const __nv_bfloat16*>(r), part, HW, C, nchunk, a, tickets);
-  else
-    bwd_reduce_ca_kernel<float><<<grid, 256, 0, s>>>(g, reinterpret_cast<const float*>(r), part, HW, C, nchunk, a, tickets);
-  return ok_or_cuda3();
+    return launch_pdl(PDL_SIMT, bwd_reduce_ca_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, g, reinterpret_cast<const __nv_bfloat16*>(r),
+                      part, HW, C, nchunk, a, tickets) == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
+  return launch_pdl(PDL_SIMT, bwd_reduce_ca_kernel<float>, grid, dim3(256), 0, s, g, reinterpret_cast<const float*>(r), part, HW, C,
+                    nchunk, a, tickets) == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
 }
 
 int form_dr(const float* g, const float* svec, const float* dyv, void* dr, int dr_is_bf16, int B, int HW, int C,
@@ -689,17 +704,19 @@ int form_dr(const float* g, const float* svec, const float* dyv, void* dr, int d
   const long long nvec = static_cast<long long>(HW) * (C / 8);
   long long per_img = std::max<long long>(1, std::min<long long>((nvec + 2047) / 2048, (592 + B - 1) / B));
   dim3 grid(static_cast<unsigned>(per_img), B);
-  if (dr_is_bf16) form_dr_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(g, svec, dyv, reinterpret_cast<__nv_bfloat16*>(dr), HW, C);
-  else form_dr_kernel<float><<<grid, 256, 0, s>>>(g, svec, dyv, reinterpret_cast<float*>(dr), HW, C);
-  return ok_or_cuda3();
+  if (dr_is_bf16)
+    return launch_pdl(PDL_SIMT, form_dr_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, g, svec, dyv, reinterpret_cast<__nv_bfloat16*>(dr),
+                      HW, C) == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
+  return launch_pdl(PDL_SIMT, form_dr_kernel<float>, grid, dim3(256), 0, s, g, svec, dyv, reinterpret_cast<float*>(dr), HW, C) ==
+                 cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
 }
 
 int add_f32(const float* a, const float* b, float* out, void* out_bf16, long long n, cudaStream_t s) {
   if (n % 4 != 0) return DFIR_ERR_ARG;
   if (n == 0) return DFIR_OK;
-  add_f32_kernel<<<grid_for(n / 4), 256, 0, s>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
-                                                 reinterpret_cast<float4*>(out), reinterpret_cast<uint2*>(out_bf16), n / 4);
-  return ok_or_cuda3();
+  return launch_pdl(PDL_SIMT, add_f32_kernel, dim3(grid_for(n / 4)), dim3(256), 0, s, reinterpret_cast<const float4*>(a),
+                    reinterpret_cast<const float4*>(b), reinterpret_cast<float4*>(out), reinterpret_cast<uint2*>(out_bf16),
+                    n / 4) == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
 }
 
 int pixel_unshuffle_f32(const float* in, float* out, int B, int h, int w, int C, int r, cudaStream_t s) {
@@ -734,9 +751,8 @@ int wgrad_reduce(const float* part, const float* dbpart, int S, int Cin, int n_r
                  float* w_direct, float* const* b_tbl, int b_idx, float* b_direct, int co_begin, int co_stride,
                  cudaStream_t s) {
   const int total = 9 * Cin * n_rows + n_rows;
-  wgrad_reduce_kernel<<<(total + 63) / 64, 256, 0, s>>>(part, dbpart, S, Cin, n_rows, w_tbl, w_idx, w_direct, b_tbl,
-                                                          b_idx, b_direct, co_begin, co_stride);
-  return ok_or_cuda3();
+  return launch_pdl(PDL_SIMT, wgrad_reduce_kernel, dim3((total + 63) / 64), dim3(256), 0, s, part, dbpart, S, Cin, n_rows, w_tbl,
+                    w_idx, w_direct, b_tbl, b_idx, b_direct, co_begin, co_stride) == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
 }
 
 int wgrad_small_chunks(int B, int H) { return static_cast<int>(std::min<long long>(static_cast<long long>(B) * H, 296)); }

@@ -16,6 +16,7 @@
 // index so that ldmatrix is bank-conflict free) + 3 dY row buffers, filled by cp.async two rows ahead.
 #include "kernels.h"
 #include "ptx.cuh"
+#include "launch.cuh"
 
 namespace dfir {
 
@@ -58,6 +59,8 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_c64_mma_kernel(WgradArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
   uint8_t* xring = smem;
   uint8_t* dybuf = smem + kXSlots * kXSlotBytes;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -220,8 +223,7 @@ int wgrad_c64_bf16(const void* dy, long long dy_pix, long long dy_row, long long
   a.part = scratch;
   a.dbpart = scratch + static_cast<size_t>(grid) * 9 * 64 * 64;
   a.B = B; a.H = H; a.W = W; a.nseg = (W + 127) / 128;
-  wgrad_c64_mma_kernel<<<grid, kWgThreads, kWgSmem, s>>>(a);
-  return cudaGetLastError() == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
+  return launch_pdl(PDL_WGRAD, wgrad_c64_mma_kernel, dim3(grid), dim3(kWgThreads), kWgSmem, s, a) == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
 }
 
 }  // namespace dfir
