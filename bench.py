@@ -294,9 +294,9 @@ def run_ours(args):
     dev_ms, e2e_ms = t.tolist()
 
     # ---------------- roofline of the dominant kernel (trunk 64->64 conv), timed alone with CUDA events
-    roof = None
+    roof = roof_conv1 = None
     if rank == 0:
-        roof = conv_roofline(lib, dev, net)
+        roof, roof_conv1 = conv_roofline(lib, dev, net)
     # ---------------- training step (BASELINE.json metric part 2: "train step ms")
     del out, out_host, l2buf
     torch.cuda.empty_cache()
@@ -325,6 +325,7 @@ def run_ours(args):
                     "api": "QRCANHandler.run_eval(x_pinned_host, metadata=, metadata_keys=) -> host tensor"},
             "gpu_launches": launches * args.steps,
             "roofline": roof,
+            "roofline_conv1": roof_conv1,
             "cpu_baseline": cpu,
             "train": dict(train, cpu_baseline=cpu_train_baseline()),
             "tflops_conv_algorithmic": round(world * n_img * LR * LR * FLOP_PER_LR_PIXEL / (ms_step / 1e3) / 1e12, 2),
@@ -378,11 +379,44 @@ def conv_roofline(lib, dev, net):
     achieved = flops / (ms / 1e3) / 1e12
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full capture
     # summarised in profiles/r01_conv_ts_mode_ncu.md (32 images per launch; algorithmic bytes = 2 x 67.1 MB)
-    traffic = 89651456 if bc == 32 else None
-    return {"bound": "tensor", "kernel": "conv3x3_c64_tc_kernel<64, bias+relu>", "achieved": round(achieved, 2),
-            "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": round(achieved / pk["tf_burst"], 4),
-            "traffic": traffic, "launch_us": round(ms * 1e3, 3), "images_per_launch": bc,
-            "algorithmic_flops_per_launch": flops, "peak_source": pk["source"] + ", burst (kernel timed alone)"}
+    # profiles/r01_tc_kernels_ncu.md (conv1 with statistics, 32 images per launch): 71.7 MB read + 20.9 MB written
+    traffic = 92612352 if bc == 32 else None
+    conv1 = {"bound": "tensor", "kernel": "conv3x3_c64_tc_kernel<64, bias+relu> (RCAB conv1)", "achieved": round(achieved, 2),
+             "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": round(achieved / pk["tf_burst"], 4),
+             "traffic": traffic, "launch_us": round(ms * 1e3, 3), "images_per_launch": bc,
+             "algorithmic_flops_per_launch": flops, "peak_source": pk["source"] + ", burst (kernel timed alone)"}
+
+    # RCAB conv2 + channel/meta attention scale + residual add (EPI_SCALE_SKIP): the kernel with the largest share of
+    # the step (profiles/r01_launches_infer_summary.md: 62 %).  It moves the fp32 residual stream and is bound by
+    # memory traffic: algorithmic bytes per element = t 2 (in) + x 4 (in) + x 4 (out) + bf16(x) 2 (out) = 12 B.
+    t_in = torch.randn(bc, LR, LR, 64, device=dev).to(torch.bfloat16)
+    x32 = torch.randn(bc, LR, LR, 64, device=dev)
+    xbf = torch.empty_like(t_in)
+    sv = torch.rand(bc, 64, device=dev)
+
+    def launch2():
+        _lib.check(lib.dfir_conv3x3_c64_scale_skip(t_in.data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR,
+                                                   sv.data_ptr(), x32.data_ptr(), x32.data_ptr(), xbf.data_ptr(), None,
+                                                   None, None, 0, None, 4, 10, 10, None, None, st), "scale_skip")
+    for _ in range(10):
+        launch2()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        launch2()
+    e1.record()
+    torch.cuda.synchronize()
+    ms2 = e0.elapsed_time(e1) / n
+    byt = bc * LR * LR * 64 * 12
+    gbs = byt / (ms2 / 1e3) / 1e9
+    # same capture file (conv2_ss): dram 251.7 MB read + 154.8 MB written per launch = the algorithmic bytes
+    conv2 = {"bound": "hbm", "kernel": "conv3x3_c64_tc_kernel<64, scale+skip> (RCAB conv2 + attention scale + residual)",
+             "achieved": round(gbs, 1), "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(gbs / pk["hbm_gbs"], 4),
+             "traffic": 406514688 if bc == 32 else None, "launch_us": round(ms2 * 1e3, 3), "images_per_launch": bc,
+             "algorithmic_bytes_per_launch": byt, "tensor_tflops": round(flops / (ms2 / 1e3) / 1e12, 1),
+             "peak_source": pk["source"] + " (STREAM-style copy)"}
+    return conv2, conv1
 
 
 def cpu_baseline(sample_images=2, threads=None):

@@ -150,7 +150,8 @@ int wgrad_f32(const float* dY, const float* X, float* scratch, int B, int H, int
               int* S_out);
 int wgrad_reduce(const float* part, const float* dbpart, int S, int Cin, int n_rows, float* const* w_tbl, int w_idx,
                  float* w_direct, float* const* b_tbl, int b_idx, float* b_direct, int co_begin, int co_stride,
-                 cudaStream_t s);
+                 cudaStream_t s, int co_major = 0);
+int wgrad_c64_co_major();  // 1 when the selected 64-channel weight-gradient kernel writes [tap][co][ci] partials
 size_t wgrad_small_scratch_floats(int B, int H, int C);
 int wgrad_small(const float* I, const void* F, int f_is_bf16, float* scratch, int B, int H, int W, int C, int C3,
                 int tail_mode, float* dw, float* db, cudaStream_t s);

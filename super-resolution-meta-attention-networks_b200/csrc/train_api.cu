@@ -370,7 +370,7 @@ int wgrad_tc(const Ctx& c, const dfir_qrcan_params* gr, const void* dy, const vo
   int S_ = 0;
   DFIR_TRY(wgrad_c64(dy, 0, 0, 0, xin, c.w.wpart, c.B, c.H, c.W, c.sms, c.st, &S_));
   return wgrad_reduce(c.w.wpart, c.w.wpart + static_cast<size_t>(S_) * 9 * 64 * 64, S_, 64, 64, gr->conv_w, widx, nullptr,
-                      gr->conv_b, widx, nullptr, 0, 1, c.st);
+                      gr->conv_b, widx, nullptr, 0, 1, c.st, wgrad_c64_co_major());
 }
 
 int wgrad_f(const Ctx& c, const dfir_qrcan_params* gr, const float* dy, const float* xin, int widx) {
@@ -408,7 +408,7 @@ int train_backward_tc(const Ctx& c, const dfir_qrcan_params* gr, const float* x,
       int S_ = 0;
       DFIR_TRY(wgrad_c64(slice, ps, rs, is, X, w.wpart, B, hh, ww, c.sms, c.st, &S_));
       DFIR_TRY(wgrad_reduce(w.wpart, w.wpart + static_cast<size_t>(S_) * 9 * 64 * 64, S_, 64, 64, gr->up_w, t, nullptr,
-                            gr->up_b, t, nullptr, s, r * r, c.st));
+                            gr->up_b, t, nullptr, s, r * r, c.st, wgrad_c64_co_major()));
       ConvTcDesc d = tc_desc(c, tc_wT(c, c.n_trunk + t * r * r + s), nullptr, EPI_SCALE_SKIP, hh, ww);
       d.in_bf16 = slice; d.in_pix_stride = ps; d.in_row_stride = rs; d.in_img_stride = is;
       d.skip_f32 = s == 0 ? nullptr : dX32; d.out_f32 = dX32; d.out_bf16 = dXbf;
@@ -685,7 +685,7 @@ int dfir_conv3x3_wgrad_c64(const void* dy, long long dps, long long drs, long lo
   float* sc = reinterpret_cast<float*>(scratch);
   DFIR_TRY(wgrad_c64(dy, dps, drs, dis, x, sc, B, H, W, std::min(sms, 160), S(stream), &S_));
   return wgrad_reduce(sc, sc + static_cast<size_t>(S_) * 9 * 64 * 64, S_, 64, 64, nullptr, 0, dw, nullptr, 0, db, co_begin,
-                      co_stride, S(stream));
+                      co_stride, S(stream), wgrad_c64_co_major());
 }
 
 int dfir_conv3x3_wgrad_f32(const float* dy, const float* x, int B, int H, int W, int Cin, int Cout, float* dw, float* db,

@@ -423,7 +423,7 @@ wgrad_f32_kernel(const float* __restrict__ dY, const float* __restrict__ X, floa
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ dbpart, int S, int Cin, int n_rows,
                     float* const* __restrict__ w_tbl, int w_idx, float* w_direct, float* const* __restrict__ b_tbl,
-                    int b_idx, float* b_direct, int co_begin, int co_stride) {
+                    int b_idx, float* b_direct, int co_begin, int co_stride, int co_major) {
   ptx::grid_dep_wait();  // (no early launch_dependents: a resident, waiting successor would starve our later waves)
   __shared__ float red[4][64];
   const int total = 9 * Cin * n_rows;
@@ -449,7 +449,10 @@ wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ db
   const float sum = ((red[0][o] + red[1][o]) + red[2][o]) + red[3][o];
   if (idx < total) {
     float* dw = w_tbl != nullptr ? w_tbl[w_idx] : w_direct;
-    const int n = idx % n_rows, ci = (idx / n_rows) % Cin, tap = idx / (n_rows * Cin);
+    // partial layout: [tap][ci][n] (CUDA-core / mma.sync kernels) or [tap][n][ci] (tcgen05 kernel)
+    const int tap = idx / (n_rows * Cin);
+    const int n = co_major ? (idx / Cin) % n_rows : idx % n_rows;
+    const int ci = co_major ? idx % Cin : (idx / n_rows) % Cin;
     if (dw != nullptr) dw[(static_cast<size_t>(co_begin + n * co_stride) * Cin + ci) * 9 + tap] = sum;
   } else {
     float* db = b_tbl != nullptr ? b_tbl[b_idx] : b_direct;
@@ -749,10 +752,10 @@ int wgrad_f32(const float* dY, const float* X, float* scratch, int B, int H, int
 
 int wgrad_reduce(const float* part, const float* dbpart, int S, int Cin, int n_rows, float* const* w_tbl, int w_idx,
                  float* w_direct, float* const* b_tbl, int b_idx, float* b_direct, int co_begin, int co_stride,
-                 cudaStream_t s) {
+                 cudaStream_t s, int co_major) {
   const int total = 9 * Cin * n_rows + n_rows;
   return launch_pdl(PDL_SIMT, wgrad_reduce_kernel, dim3((total + 63) / 64), dim3(256), 0, s, part, dbpart, S, Cin, n_rows, w_tbl,
-                    w_idx, w_direct, b_tbl, b_idx, b_direct, co_begin, co_stride) == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
+                    w_idx, w_direct, b_tbl, b_idx, b_direct, co_begin, co_stride, co_major) == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
 }
 
 int wgrad_small_chunks(int B, int H) { return static_cast<int>(std::min<long long>(static_cast<long long>(B) * H, 296)); }

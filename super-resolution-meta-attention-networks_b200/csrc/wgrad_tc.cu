@@ -16,8 +16,9 @@
 // 9 x 64 x 64 gradient of the CTA's band of rows in tensor memory; they are written once at the end and reduced over
 // CTAs by wgrad_reduce_kernel in a fixed order.
 //
-// Warp roles: 0 TMA producer (X rows with halo into a 5-slot ring, dY rows into 3 slots), 1 MMA issuer, 2-3 bias
-// gradient (column sums of the dY tiles), 4-7 epilogue (TMEM -> partial sums in global memory).
+// Warp roles: 0 TMA producer (X rows with halo into a 5-slot ring, dY rows into 3 slots), 1 MMA issuer, 2-5 bias
+// gradient while the rows stream (column sums of the dY tiles, 16-byte shared-memory loads), then the epilogue
+// (TMEM -> partial sums in global memory).
 #include "kernels.h"
 #include "launch.cuh"
 #include "ptx.cuh"
@@ -35,11 +36,11 @@ constexpr int kXS = 5;                    // X row ring
 constexpr int kDS = 3;                    // dY row slots
 constexpr int kXSlotB = 136 * 128;        // 130 px used, multiple of 1024
 constexpr int kDSlotB = 128 * 128;
-constexpr int kWtThreads = 256;
-constexpr int kWtSmem = kXS * kXSlotB + kDS * kDSlotB + 256 + 1024;
+constexpr int kWtThreads = 192;            // producer, MMA, 4 x (bias gradient during the loop, then epilogue)
+constexpr int kWtSmem = kXS * kXSlotB + kDS * kDSlotB + 256 + 16 * 64 * 4 + 1024;
 
 struct WgradTcArgs {
-  float* part;    // [grid][9][64 ci][64 co]
+  float* part;    // [grid][9][64 co][64 ci]
   float* dbpart;  // [grid][64]
   int B, H, W, nseg;
 };
@@ -74,6 +75,7 @@ wgrad_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   uint64_t* dempty = dfull + kDS;
   uint64_t* accfull = dempty + kDS;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(accfull + 1);
+  float* red = reinterpret_cast<float*>(dring + kDS * kDSlotB + 256);  // [16 pixel lanes][64 co]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = a.H, nseg = a.nseg;
@@ -89,7 +91,7 @@ wgrad_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     prefetch_tmap(&tmap_x);
     prefetch_tmap(&tmap_dy);
     for (int i = 0; i < kXS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
-    for (int i = 0; i < kDS; ++i) { mbar_init(&dfull[i], 1); mbar_init(&dempty[i], 3); }  // MMA commit + 2 bias warps
+    for (int i = 0; i < kDS; ++i) { mbar_init(&dfull[i], 1); mbar_init(&dempty[i], 5); }  // MMA commit + 4 bias warps
     mbar_init(accfull, 1);
     fence_barrier_init();
   }
@@ -165,50 +167,63 @@ wgrad_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         __syncwarp();
       }
       if (leader) umma_commit(accfull);
-    } else if (warp < 4) {
-      // ===================== bias gradient: column sums of the dY tiles =====================
-      const int co = threadIdx.x - 64;  // 0..63
-      float acc = 0.f;
-      for (int g = g0, it = 0; g < g1; ++g, ++it) {
-        const int ds = it % kDS;
-        mbar_wait(&dfull[ds], (it / kDS) & 1, 25);
-        const int seg = (g / H) % nseg;
-        const int npx = min(128, a.W - seg * 128);
-        const uint8_t* base = dring + ds * kDSlotB + (co & 7) * 2;
-        const int ch = co >> 3;
-        for (int p = 0; p < npx; ++p)
-          acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(base + p * 128 + ((ch ^ (p & 7)) << 4)));
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&dempty[ds]);
-      }
-      a.dbpart[static_cast<size_t>(blockIdx.x) * 64 + co] = acc;
     } else {
-      // ===================== epilogue: TMEM -> partial sums =====================
+      // ===================== bias gradient while the rows stream, then the epilogue =====================
       const int q = warp & 3;
       const int L = q * 32 + lane;  // TMEM lane
+      {
+        const int et = threadIdx.x - 64;     // 0..127
+        const int ch = et & 7, pl = et >> 3;  // 8 channels (one 16-byte chunk) x 16 pixel lanes
+        float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int g = g0, it = 0; g < g1; ++g, ++it) {
+          const int ds = it % kDS;
+          mbar_wait(&dfull[ds], (it / kDS) & 1, 25);
+          const int seg = (g / H) % nseg;
+          const int npx = min(128, a.W - seg * 128);
+          const uint8_t* base = dring + ds * kDSlotB;
+          for (int p = pl; p < npx; p += 16) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(base + p * 128 + ((ch ^ (p & 7)) << 4));
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __bfloat1622float2(h2[j]);
+              acc8[2 * j] += f.x;
+              acc8[2 * j + 1] += f.y;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&dempty[ds]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[pl * 64 + ch * 8 + j] = acc8[j];
+        named_bar_sync(1, 128);
+        if (et < 64) {
+          float t = 0.f;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) t += red[k * 64 + et];
+          a.dbpart[static_cast<size_t>(blockIdx.x) * 64 + et] = t;
+        }
+      }
       mbar_wait(accfull, 0, 26);
       tcgen05_fence_after();
+      // partial layout [tap][co][ci]: for a fixed accumulator column (co) the 32 lanes of a warp hold 32 consecutive
+      // ci, so every store instruction writes one full 128-byte line
       float* pbase = a.part + static_cast<size_t>(blockIdx.x) * 9 * 64 * 64;
 #pragma unroll 1
       for (int dy = 0; dy < 3; ++dy) {
-        // 128-lane accumulator: lane = dx*64 + ci (dx in {0,1}), column = co
-        {
-          float* dst = pbase + (static_cast<size_t>(dy * 3 + (L >> 6)) * 64 + (L & 63)) * 64;
+        {  // 128-lane accumulator: lane = dx*64 + ci (dx in {0,1}), column = co
+          float* dst = pbase + static_cast<size_t>(dy * 3 + (L >> 6)) * 64 * 64 + (L & 63);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t rv[32];
             tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + dy * 64 + h * 32, rv);
             tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-              *reinterpret_cast<float4*>(dst + h * 32 + 4 * c) =
-                  make_float4(__uint_as_float(rv[4 * c]), __uint_as_float(rv[4 * c + 1]), __uint_as_float(rv[4 * c + 2]),
-                              __uint_as_float(rv[4 * c + 3]));
+            for (int c = 0; c < 32; ++c) dst[(h * 32 + c) * 64] = __uint_as_float(rv[c]);
           }
         }
-        // 64-row accumulator (M = 64): row r lives in lane (r % 16) + 32 * (r / 16); tap dx = 2
-        {
-          float* dst = pbase + (static_cast<size_t>(dy * 3 + 2) * 64 + (q * 16 + (lane & 15))) * 64;
+        {  // 64-row accumulator (M = 64): row r lives in lane (r % 16) + 32 * (r / 16); tap dx = 2
+          float* dst = pbase + static_cast<size_t>(dy * 3 + 2) * 64 * 64 + (q * 16 + (lane & 15));
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t rv[32];
@@ -216,10 +231,7 @@ wgrad_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             tmem_ld_wait();
             if (lane < 16) {
 #pragma unroll
-              for (int c = 0; c < 8; ++c)
-                *reinterpret_cast<float4*>(dst + h * 32 + 4 * c) =
-                    make_float4(__uint_as_float(rv[4 * c]), __uint_as_float(rv[4 * c + 1]),
-                                __uint_as_float(rv[4 * c + 2]), __uint_as_float(rv[4 * c + 3]));
+              for (int c = 0; c < 32; ++c) dst[(h * 32 + c) * 64] = __uint_as_float(rv[c]);
             }
           }
         }
@@ -276,9 +288,15 @@ int wgrad_tc_watchdog(unsigned int* out8, int reset) {
   return DFIR_OK;
 }
 
+static bool wgrad_use_mma() {
+  static const bool use_mma = getenv("DFIR_WGRAD") != nullptr && getenv("DFIR_WGRAD")[0] == 'm';
+  return use_mma;
+}
+int wgrad_c64_co_major() { return wgrad_use_mma() ? 0 : 1; }
+
 int wgrad_c64(const void* dy, long long dy_pix, long long dy_row, long long dy_img, const void* x, float* scratch, int B,
               int H, int W, int num_sms, cudaStream_t s, int* S_out) {
-  static const bool use_mma = getenv("DFIR_WGRAD") != nullptr && getenv("DFIR_WGRAD")[0] == 'm';
+  const bool use_mma = wgrad_use_mma();
   return use_mma ? wgrad_c64_bf16(dy, dy_pix, dy_row, dy_img, x, scratch, B, H, W, num_sms, s, S_out)
                  : wgrad_c64_tc(dy, dy_pix, dy_row, dy_img, x, scratch, B, H, W, num_sms, s, S_out);
 }

@@ -179,7 +179,7 @@ class QRCAN(nn.Module):
             raise RuntimeError("deepfir_b200.%s runs on a CUDA (sm_100a) device only: there is no CPU path"
                                % type(self).__name__)
         from . import ops  # registers torch.ops.dfir.*
-        training = torch.is_grad_enabled() and next(self.parameters()).requires_grad
+        training = torch.is_grad_enabled() and self.head_weight().requires_grad
         packed = self.packed(training=training)
         b = x.shape[0]
         attr = metadata.reshape(b, -1).to(device=x.device, dtype=torch.float32).contiguous()
@@ -190,6 +190,10 @@ class QRCAN(nn.Module):
             return qrcan_train_apply(self, packed, x.to(torch.float32).contiguous(), attr)
         return torch.ops.dfir.qrcan_forward(x.to(torch.float32).contiguous(), attr, packed.handle,
                                             PRECISIONS[self.precision])
+
+    def head_weight(self):
+        head = self.head
+        return (head[0] if isinstance(head, nn.Sequential) else head).weight
 
     def forensic(self, *args, **kwargs):
         raise NotImplementedError("forensic analysis is outside the B200 hot path")
@@ -219,7 +223,9 @@ class QRCAN(nn.Module):
         """Kernel-format parameters.  Rebuilt from scratch when a parameter's storage moved (`.to()`, new module);
         when only the values changed (optimizer.step(), load_state_dict) they are refreshed in place by one C call
         (`dfir_qrcan_repack`) driven by device pointer tables."""
-        params = list(self.parameters())
+        params = self.__dict__.get("_plist")
+        if params is None:  # walking the module tree costs milliseconds per call: cached until `_apply` / load_state_dict
+            params = self.__dict__["_plist"] = list(self.parameters())
         skey = (tuple(p.data_ptr() for p in params), self.precision, self.chunk_images, self.schedule)
         vers = tuple(p._version for p in params)
         pk = self._packed
@@ -240,7 +246,12 @@ class QRCAN(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._packed = None
+        self.__dict__.pop("_plist", None)
         return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self.__dict__.pop("_plist", None)  # (assign=True replaces the Parameter objects)
+        return super().load_state_dict(*a, **k)
 
 
 class QEDSRBlockParams(nn.Module):

@@ -15,5 +15,9 @@ x = torch.rand(B, 3, LR, LR, device="cuda"); meta = torch.rand(B, 10, 1, 1, devi
 with torch.no_grad():
     for _ in range(reps):
         out = net(x, meta)
-torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()   # ncu --profile-from-start off: list only this forward
+    out = net(x, meta)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
 print("ok", out.shape, float(out.abs().mean()))

@@ -12,7 +12,12 @@ g = torch.Generator().manual_seed(8)
 x = torch.rand(16, 3, 64, 64, generator=g); y = torch.rand(16, 3, 256, 256, generator=g)
 meta = torch.rand(16, 10, generator=g, dtype=torch.float64) * 0.4
 keys = [("blur_kernel",) * 16] * 10
+h.net.cuda_graphs = False          # plain launches: every kernel shows up under its own name in the ncu list
 for _ in range(2):
     loss, _ = h.run_train(x, y, metadata=meta, metadata_keys=keys, keep_on_device=True)
 torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()   # ncu --profile-from-start off: only the third step is listed
+loss, _ = h.run_train(x, y, metadata=meta, metadata_keys=keys, keep_on_device=True)
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
 print("loss", float(loss))
