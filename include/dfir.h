@@ -131,6 +131,21 @@ int dfir_conv3x3_c64_scale_skip(const void* in_bf16, const void* wpacked, const 
                                 const float* ca_params, int R, int M, int A, const float* attributes,
                                 const float* sq, void* stream);
 
+/* K-chunked convolutions for feature widths above 64 (Q-EDSR with 128/192/256 features, architectures.py:359-399):
+ * a C -> C conv is a (C/64) x (C/64) block matrix of 64 -> 64 convs over 64-channel planes; the input-chunk sums are
+ * accumulated in fp32 by re-launching the tensor-core kernel with the running sum as its skip input:
+ *     out_f32 = conv(in) * svec[b] + bias * svec[b] + skip_f32  [ReLU]      (svec NULL = 1, bias/skip NULL = 0)
+ *     out_bf16 = bf16(out_f32)       (dense NHWC, 64 channels; out_f32 may be NULL and may alias skip_f32)
+ * With svec = res_scale * meta scale and skip = the fp32 stream this is ParamResBlock's `res * y + x` (:352-355)
+ * accumulated in place. */
+int dfir_conv3x3_c64_accumulate(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
+                                const float* svec, const float* skip_f32, float* out_f32, void* out_bf16, int relu,
+                                void* stream);
+/* tail conv 64 -> cout (<= 16) writing / accumulating into fp32 NCHW [B][cout][H][W]; wpacked from
+ * dfir_pack_conv3x3_bf16 with nt_rows = 16 */
+int dfir_conv3x3_c64_tail(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W, int cout,
+                          float* out_nchw, int accumulate, void* stream);
+
 /* default_conv on CUDA cores, fp32 NHWC in/out, any Cin % 4 == 0 and any Cout.
  *   w_packed from dfir_pack_conv3x3_f32; skip (optional) NHWC fp32 added after bias; relu applied last;
  *   ps_r > 1 folds nn.PixelShuffle(ps_r) into the store (out is then [B][H*r][W*r][Cout/r^2]);

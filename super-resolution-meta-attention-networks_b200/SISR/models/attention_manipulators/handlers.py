@@ -58,7 +58,7 @@ class QEDSRHandler(QModel):
                  num_features=64, res_scale=0.1, scheduler=None, scheduler_params=None, perceptual=None, **kwargs):
         super(QEDSRHandler, self).__init__(device=device, model_save_dir=model_save_dir, eval_mode=eval_mode,
                                            **kwargs)
-        if num_features != 64:  # the tensor-core kernels are specialised for 64 channels; wider nets run fp32
+        if num_features % 64 != 0:  # the tensor-core kernels work on 64-channel planes; other widths run fp32
             kwargs.setdefault('precision', 'fp32')
         self.net = QEDSR(scale=scale, in_features=in_features, num_features=num_features, num_blocks=num_blocks,
                          res_scale=res_scale, input_para=self.num_metadata, **kwargs)

@@ -489,6 +489,38 @@ int dfir_conv3x3_c64_scale_skip(const void* in_bf16, const void* wpacked, const 
   return conv3x3_c64_tc(d, S(stream));
 }
 
+int dfir_conv3x3_c64_accumulate(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
+                                const float* svec, const float* skip_f32, float* out_f32, void* out_bf16, int relu,
+                                void* stream) {
+  if (in_bf16 == nullptr || wpacked == nullptr || out_bf16 == nullptr) return DFIR_ERR_ARG;
+  ConvTcDesc d{};
+  d.B = B; d.H = H; d.W = W; d.cin_total = 64; d.cin_off = 0; d.cout = 64; d.epi = EPI_SCALE_SKIP; d.in_mode = IN_TMA;
+  d.in_bf16 = in_bf16; d.wpacked = wpacked; d.bias = bias; d.out_bf16 = out_bf16;
+  d.out_pix_stride = 128; d.out_row_stride = static_cast<long long>(W) * 128;
+  d.out_img_stride = static_cast<long long>(H) * W * 128;
+  d.svec = svec; d.skip_f32 = skip_f32; d.out_f32 = out_f32; d.relu_out = relu ? 1 : 0;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return DFIR_ERR_CUDA;
+  d.num_sms = sms;
+  return conv3x3_c64_tc(d, S(stream));
+}
+
+int dfir_conv3x3_c64_tail(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W, int cout,
+                          float* out_nchw, int accumulate, void* stream) {
+  if (in_bf16 == nullptr || wpacked == nullptr || out_nchw == nullptr || cout < 1 || cout > 16) return DFIR_ERR_ARG;
+  ConvTcDesc d{};
+  d.B = B; d.H = H; d.W = W; d.cin_total = 64; d.cin_off = 0; d.cout = cout; d.epi = EPI_TAIL_NCHW; d.in_mode = IN_TMA;
+  d.in_bf16 = in_bf16; d.wpacked = wpacked; d.bias = bias; d.out_f32 = out_nchw; d.tail_accumulate = accumulate ? 1 : 0;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return DFIR_ERR_CUDA;
+  d.num_sms = sms;
+  return conv3x3_c64_tc(d, S(stream));
+}
+
 int dfir_conv3x3_f32(const float* in, const float* w_packed, const float* bias, const float* skip, float* out, int B,
                      int H, int W, int Cin, int Cout, int relu, int ps_r, int out_nchw, void* stream) {
   return conv3x3_f32(in, w_packed, bias, skip, out, B, H, W, Cin, Cout, relu, ps_r, out_nchw, S(stream));

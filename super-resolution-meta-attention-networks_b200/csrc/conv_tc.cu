@@ -629,7 +629,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             float* o = a.out_f32 + (static_cast<size_t>(b) * a.cout) * plane + static_cast<size_t>(y) * a.W + x;
 #pragma unroll
             for (int c = 0; c < NT; ++c)
-              if (c < a.cout) o[c * plane] = __uint_as_float(r0[c]) + bias_s[c];
+              if (c < a.cout) o[c * plane] = __uint_as_float(r0[c]) + bias_s[c] + (a.tail_accumulate ? o[c * plane] : 0.f);
           }
         } else if constexpr (EPI == EPI_SCALE_SKIP) {
           // Per half of 32 channels: v = acc * s + bias * s (or r = acc + bias when the training forward saves r) into
@@ -700,6 +700,9 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
                 if (has_skip) {
                   const float4 sk = sk4[i * 128];
                   o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
+                }
+                if (a.relu_out) {
+                  o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                 }
                 if (o32 != nullptr && !exp_no_f32st) *reinterpret_cast<float4*>(o32 + i * 1024) = o;
                 uint2 pk;
@@ -978,6 +981,8 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   a.mask_bf16 = reinterpret_cast<const __nv_bfloat16*>(d.mask_bf16);
   a.r_out = reinterpret_cast<__nv_bfloat16*>(d.r_out);
   a.ymean_out = d.ymean_out;
+  a.relu_out = d.relu_out;
+  a.tail_accumulate = d.tail_accumulate;
   a.out_bf16_direct = reinterpret_cast<__nv_bfloat16*>(d.out_bf16);
   a.r_bf16 = reinterpret_cast<const __nv_bfloat16*>(d.r_bf16);
   a.xin_f32 = d.xin_f32;

@@ -38,6 +38,8 @@ struct ConvTcArgs {  // kernel argument block
   const __nv_bfloat16* mask_bf16;  // EPI_RELU_MASK: saved forward activation (dense NHWC)
   __nv_bfloat16* r_out;            // EPI_SCALE_SKIP (training forward): bf16 copy of acc + b, i.e. r before the scale
   float* ymean_out;                // EPI_SCALE_SKIP with epi_stats: pooled mean of r per image [B][64]
+  int relu_out;                    // EPI_SCALE_SKIP: ReLU after the skip add (last K-chunk of a wide conv + ReLU)
+  int tail_accumulate;             // EPI_TAIL_NCHW: add to what out_f32 already holds (K-chunks of a wide tail conv)
   __nv_bfloat16* out_bf16_direct;  // EPI_SCALE_SKIP writes its bf16 copy with plain coalesced stores
   // IN_FUSED: conv input = r * s[b] + xin (xout = fp32 copy of it for the rows the CTA owns), with
   // s[b] = CA_style(mean(r_b) from pool_rows, attributes[b]) * sq[b]   (style NONE: s = res_scale * sq)
@@ -65,6 +67,7 @@ struct ConvTcDesc {  // host-side launch description
   const void* mask_bf16 = nullptr;                                     // EPI_RELU_MASK
   void* r_out = nullptr;                                               // EPI_SCALE_SKIP: save r (training forward)
   float* ymean_out = nullptr;                                          // EPI_SCALE_SKIP + epi_stats: save mean(r)
+  int relu_out = 0, tail_accumulate = 0;                               // see ConvTcArgs
   const void* wpacked;
   const float* bias;
   void* out_bf16;

@@ -294,6 +294,30 @@ class QEDSR(QRCAN):
         self.tail = nn.Sequential(*tail)
         self._packed = None
 
+    def forward(self, x, metadata):
+        wide = self.precision == "bf16" and self.cfg["n_feats"] > 64 and self.cfg["n_feats"] % 64 == 0
+        if not wide:
+            return super().forward(x, metadata)
+        # 128 / 192 / 256 features: 64-channel planes through the tensor-core kernels (deepfir_b200/wide.py)
+        if not x.is_cuda:
+            raise RuntimeError("deepfir_b200.QEDSR runs on a CUDA (sm_100a) device only: there is no CPU path")
+        if torch.is_grad_enabled() and self.head.weight.requires_grad:
+            raise NotImplementedError("training wide Q-EDSR on the tensor cores is not implemented; use precision='fp32'")
+        from .wide import WideQEDSR
+        params = self.__dict__.get("_plist")
+        if params is None:
+            params = self.__dict__["_plist"] = list(self.parameters())
+        key = (tuple(p.data_ptr() for p in params), tuple(p._version for p in params))
+        if self.__dict__.get("_wide_key") != key:
+            self.__dict__["_wide"] = WideQEDSR(self)
+            self.__dict__["_wide_key"] = key
+        b = x.shape[0]
+        attr = metadata.reshape(b, -1).to(device=x.device, dtype=torch.float32).contiguous()
+        if attr.shape[1] != self.cfg["num_metadata"]:
+            raise RuntimeError("metadata has %d entries per image, network expects %d" % (attr.shape[1], self.cfg["num_metadata"]))
+        with torch.no_grad(), torch.cuda.device(x.device):
+            return self.__dict__["_wide"].forward(x.to(torch.float32).contiguous(), attr)
+
     def _pack_spec(self):
         trunk = []
         for blk in self.body:

@@ -181,6 +181,28 @@ def test_batch_composition_does_not_change_an_image():
     assert torch.equal(full[0], full[4])
 
 
+def test_host_results_stay_valid_while_referenced(tmp_path):
+    """run_eval returns host tensors in pooled page-locked buffers: a buffer is only handed out again after the caller
+    dropped every reference to the previous result, so results held across calls never change"""
+    from SISR.models import ModelInterface
+    torch.manual_seed(8)
+    h = ModelInterface.define_model("qrcan", device=0, model_save_dir=str(tmp_path), eval_mode=True,
+                                    metadata=["blur_kernel"], n_resgroups=1, n_resblocks=1, n_feats=64, scale=2,
+                                    style="standard", include_q_layer=True)
+    g = torch.Generator().manual_seed(1)
+    meta = torch.rand(2, 10, generator=g, dtype=torch.float64) * 0.4
+    keys = [("blur_kernel",) * 2] * 10
+    xs = [torch.rand(2, 3, 16, 16, generator=g) for _ in range(6)]
+    held = [h.run_eval(x, metadata=meta, metadata_keys=keys)[0] for x in xs]      # six live results
+    copies = [t.clone() for t in held]
+    for x in xs:                                                                   # more calls while they are alive
+        h.run_eval(x, metadata=meta, metadata_keys=keys)
+    assert len({t.data_ptr() for t in held}) == 6
+    for t, c in zip(held, copies):
+        assert torch.equal(t, c)
+    assert all(t.is_pinned() for t in held[:4])
+
+
 def test_state_dict_roundtrip_and_repack():
     """weights are re-packed when parameters change (the packed tiles are a cache, never saved)."""
     ref, info = load_golden("qrcan_noq_scale2")
@@ -195,3 +217,37 @@ def test_state_dict_roundtrip_and_repack():
         c = net(x.cuda(), meta.cuda())
     assert not torch.equal(a, b)
     assert torch.equal(a, c)
+
+
+def test_qedsr_256_features_on_the_tensor_cores_matches_reference_golden():
+    """the published Q-EDSR width (256 features, BASELINE.json configs[2]) as 4 x 4 blocks of the 64-channel tcgen05 conv
+    with fp32 accumulation over input chunks (deepfir_b200/wide.py): deviation explained by the bf16 storage policy"""
+    ref, info = load_golden("qedsr_f256_b2_nl")
+    net, x, meta = _build(info, "bf16")
+    with torch.no_grad():
+        out = net(x.cuda(), meta.cuda()).cpu()
+    assert out.shape == ref.shape and torch.isfinite(out).all()
+    _, pol_err = _policy_error(info, ref)
+    assert max_norm_err(out, ref) <= 2.0 * pol_err + 1e-4, (max_norm_err(out, ref), pol_err)
+    assert O.psnr(out, ref, max_value=1.0) >= 50.0
+
+
+@pytest.mark.parametrize("feats,scale,shape", [(128, 2, (2, 9, 150)), (192, 3, (1, 7, 20)), (256, 4, (1, 16, 136))])
+def test_qedsr_wide_widths_scales_and_ragged_rows_against_oracle(feats, scale, shape):
+    """other plane counts (2, 3, 4), upsampler factors and row widths that are not multiples of the 128-pixel tile"""
+    from deepfir_b200.qrcan import QEDSR
+    torch.manual_seed(3)
+    kw = dict(num_blocks=2, num_features=feats, input_para=10, scale=scale, res_scale=0.1, q_layer_nonlinearity=True)
+    net = QEDSR(precision="bf16", **kw)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    b, h, w = shape
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(b, 3, h, w, generator=g)
+    meta = torch.rand(b, 10, 1, 1, generator=g) * 0.4
+    with torch.no_grad():
+        want = O.qedsr_forward(x, meta, sd, res_scale=0.1)
+        pol = O.qedsr_forward(x, meta, sd, res_scale=0.1, nm=O.Numerics(torch.bfloat16))
+        out = net.cuda().eval()(x.cuda(), meta.cuda()).cpu()
+    pol_err = max_norm_err(pol, want)
+    assert out.shape == want.shape
+    assert max_norm_err(out, want) <= 2.0 * pol_err + 1e-4, (max_norm_err(out, want), pol_err)
