@@ -205,6 +205,15 @@ def cpu_train_baseline(threads=None):
                       "autograd through oracle/deepfir_oracle.py; a full step is ~%dx this" % (TRAIN_BATCH, TRAIN_BATCH)}
 
 
+def workload_config(n_img=None):
+    n_img = n_img or IMAGES_PER_GPU
+    return {"workload": "Q-RCAN x4 (10x20 RCAB, 64 ch, 10-D blur metadata) batched inference, "
+                        "%d synthetic 128x128 LR images per GPU" % n_img,
+            "images_per_gpu": n_img, "lr_size": [LR, LR], "scale": SCALE, "precision": "bf16 operands, "
+            "fp32 accumulate + fp32 residual stream", "l2": "192 MiB buffer rewritten between timed steps",
+            "sharding": "by image, no data-path collective"}
+
+
 def synth_batch(n, seed):
     g = torch.Generator().manual_seed(seed)
     x = torch.floor(torch.rand(n, 3, LR, LR, generator=g) * 256) / 255.0
@@ -313,11 +322,7 @@ def run_ours(args):
             "metric": "Q-RCAN x4 output MPix/s", "value": round(value, 3), "unit": "MPix/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "Q-RCAN x4 (10x20 RCAB, 64 ch, 10-D blur metadata) batched inference, "
-                                   "%d synthetic 128x128 LR images per GPU" % n_img,
-                       "images_per_gpu": n_img, "lr_size": [LR, LR], "scale": SCALE, "precision": "bf16 operands, "
-                       "fp32 accumulate + fp32 residual stream", "l2": "192 MiB buffer rewritten between timed steps",
-                       "sharding": "by image, no data-path collective"},
+            "config": workload_config(n_img),
             "clocks": clocks,
             "e2e": {"value": round(out_mpix_step / (e2e_ms / 1e3 / args.steps), 3), "unit": "MPix/s",
                     "h2d_bytes_per_step": int(x_pin.numel() * 4 + n_img * 10 * 4),
@@ -464,9 +469,8 @@ def run_reference(args):
         "impl": "reference", "metric": "Q-RCAN x4 output MPix/s", "value": round(v, 4), "unit": "MPix/s",
         "n_gpus": world, "steps": len(vals), "warmup": 1, "ms_per_step": round(ms, 2), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Q-RCAN x4 (10x20 RCAB, 64 ch, 10-D blur metadata) batched inference, "
-                               "%d synthetic 128x128 LR images per GPU" % IMAGES_PER_GPU,
-                   "sample": "each step = %d images of the workload on the host CPU" % sample},
+        "config": dict(workload_config(), precision="fp32 (the reference's arithmetic)", l2="n/a (host CPU)",
+                       sample="each step = %d images of the workload on the host CPU" % sample),
         "cpu_baseline": cpu,
         "e2e": {"value": round(v, 4), "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))

@@ -188,6 +188,14 @@ int dfir_ca_pa_scale_residual(const void* r, int r_is_bf16, const float* x_in, c
                               const float* attributes, const float* sq, float* x_out, void* x_out_bf16, int B, int H,
                               int W, void* stream);
 
+/* Post-processing of an SR batch on the device — what ModelInterface.net_run_and_process does with numpy on the host
+ * (models/__init__.py:138-169; sr_tools/image_manipulation.py:56-157, im_type 'jpg'):
+ *   rgb_clipped = clip(x, lo, hi);  ycbcr = [0.299 r + 0.587 g + 0.114 b,  128/255 + (-0.168736 r - 0.331264 g + 0.5 b),
+ *                                            128/255 + (0.5 r - 0.418688 g - 0.081312 b)]  of the clipped values.
+ * x, rgb_clipped, ycbcr: fp32 NCHW [B][3][HW].  Bit-identical to the numpy expressions (separately rounded fp32 ops). */
+int dfir_postprocess_rgb(const float* x_nchw, float* rgb_clipped, float* ycbcr, int B, long long HW, float lo, float hi,
+                         void* stream);
+
 /* per-row channel sums of an fp32 NHWC tensor: pool_rows[b][y][c] = sum_x in[b][y][x][c] (fp32 mode only;
  * the tensor-core conv produces them in its epilogue). */
 int dfir_pool_rows_f32(const float* in, float* pool_rows, int B, int H, int W, int C, void* stream);

@@ -560,6 +560,12 @@ int dfir_ca_pa_scale_residual(const void* r, int r_is_bf16, const float* x_in, c
                         reinterpret_cast<__nv_bfloat16*>(x_out_bf16), B, H, W, 64, S(stream), nullptr, pa_params);
 }
 
+int dfir_postprocess_rgb(const float* x_nchw, float* rgb_clipped, float* ycbcr, int B, long long HW, float lo, float hi,
+                         void* stream) {
+  if (x_nchw == nullptr || rgb_clipped == nullptr || ycbcr == nullptr) return DFIR_ERR_ARG;
+  return postprocess_rgb(x_nchw, rgb_clipped, ycbcr, B, HW, lo, hi, S(stream));
+}
+
 int dfir_pool_rows_f32(const float* in, float* pool_rows, int B, int H, int W, int C, void* stream) {
   return pool_rows_f32(in, pool_rows, B, H, W, C, S(stream));
 }

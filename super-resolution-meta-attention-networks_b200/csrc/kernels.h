@@ -107,6 +107,7 @@ int head_conv(const float* x_nchw, const float* w_packed, const float* bias, flo
 int conv3x3_f32(const float* in, const float* w_packed, const float* bias, const float* skip, float* out, int B, int H,
                 int W, int Cin, int Cout, int relu, int ps_r, int out_nchw, cudaStream_t s, const float* mask = nullptr);
 int pool_rows_f32(const float* in, float* pool_rows, int B, int H, int W, int C, cudaStream_t s);
+int postprocess_rgb(const float* x, float* rgb, float* ycc, int B, long long HW, float lo, float hi, cudaStream_t s);
 int meta_attention(const float* meta, const float* w1, const float* b1, const float* w2, const float* b2, float* out,
                    int nblk, int B, int M, int Hid, int C, int relu, const int* blk_enabled, float out_scale,
                    cudaStream_t s);

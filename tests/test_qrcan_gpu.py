@@ -251,3 +251,27 @@ def test_qedsr_wide_widths_scales_and_ragged_rows_against_oracle(feats, scale, s
     pol_err = max_norm_err(pol, want)
     assert out.shape == want.shape
     assert max_norm_err(out, want) <= 2.0 * pol_err + 1e-4, (max_norm_err(out, want), pol_err)
+
+
+def test_net_run_and_process_device_postprocessing_is_bit_identical_to_the_host_path(tmp_path):
+    """ModelInterface.net_run_and_process: clip + RGB->YCbCr run on the GPU (dfir_postprocess_rgb); both returned arrays
+    must equal, bit for bit, what the reference's numpy post-processing gives on the same network output"""
+    import numpy as np
+    from SISR.models import ModelInterface
+    torch.manual_seed(8)
+    mi = ModelInterface.__new__(ModelInterface)
+    mi.model = ModelInterface.define_model("qrcan", device=0, model_save_dir=str(tmp_path), eval_mode=True,
+                                           metadata=["blur_kernel"], n_resgroups=1, n_resblocks=2, n_feats=64, scale=4,
+                                           style="standard", include_q_layer=True, precision="fp32")
+    mi.configuration = {"input": "unmodified", "colorspace": mi.model.colorspace}
+    g = torch.Generator().manual_seed(5)
+    lr = torch.rand(3, 3, 20, 28, generator=g) * 1.6 - 0.3          # pushes outputs outside [0,1]: the clip matters
+    meta = torch.rand(3, 10, generator=g, dtype=torch.float64) * 0.4
+    keys = [("blur_kernel",) * 3] * 10
+    rgb, ycc, loss, timing = mi.net_run_and_process(lr=lr, hr=None, metadata=meta, metadata_keys=keys)
+    raw = mi.model.run_eval(lr, metadata=meta, metadata_keys=keys)[0]
+    want_rgb, want_ycc, _, _ = mi._host_postprocess(raw, None, None)
+    assert isinstance(rgb, np.ndarray) and rgb.dtype == np.float32 and rgb.shape == (3, 3, 80, 112)
+    assert rgb.min() >= 0.0 and rgb.max() <= 1.0
+    assert np.array_equal(rgb, want_rgb)
+    assert np.array_equal(ycc, want_ycc)
