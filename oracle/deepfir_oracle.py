@@ -211,6 +211,46 @@ def qedsr_forward(x: Tensor, meta: Tensor, sd: SD, res_scale: float = 0.1, nm: N
 
 
 # --------------------------------------------------------------------------------------------
+# non-meta baselines RCAN / EDSR (advanced/architectures.py) — SURVEY.md §8f rank 3
+# --------------------------------------------------------------------------------------------
+def rcan_forward(x: Tensor, sd: SD, nm: Numerics = EXACT) -> Tensor:
+    """RCAN.forward (advanced/architectures.py:159-164) with RCAB (:71-74: conv-ReLU-conv-CALayer, `res += x`),
+    CALayer (:30-33: avg-pool -> FC-ReLU-FC-sigmoid -> `x * y`) and ResidualGroup (:107-110).  The trunk tail conv
+    is the last entry of `body`."""
+    ngroups = _count(sd, r"body\.(\d+)\.body\.0\.body\.0\.weight$")
+    h = conv3x3(x, sd, "head.0", nm)
+    res = h
+    for g in range(ngroups):
+        gp = "body.%d" % g
+        nblocks = _count(sd, re.escape(gp) + r"\.body\.(\d+)\.body\.0\.weight$")
+        r = res
+        for b in range(nblocks):
+            p = "%s.body.%d.body" % (gp, b)
+            t = conv3x3(F.relu(conv3x3(r, sd, p + ".0", nm)), sd, p + ".2", nm)
+            y = t.mean(dim=(2, 3), keepdim=True)
+            y = torch.sigmoid(fc(F.relu(fc(y, sd, p + ".3.conv_du.0")), sd, p + ".3.conv_du.2"))
+            r = t * y + r
+        res = conv3x3(r, sd, "%s.body.%d" % (gp, nblocks), nm) + res
+    res = conv3x3(res, sd, "body.%d" % ngroups, nm) + h
+    scale = _tail_scale(sd)
+    return conv3x3(upsampler(res, sd, "tail.0", scale, nm), sd, "tail.1", nm)
+
+
+def edsr_forward(x: Tensor, sd: SD, res_scale: float = 0.1, nm: Numerics = EXACT) -> Tensor:
+    """EDSR.forward (advanced/architectures.py:221-226) with ResBlock (advanced/common.py:68-72:
+    `res = body(x).mul(res_scale); res += x`)."""
+    nblocks = _count(sd, r"body\.(\d+)\.body\.0\.weight$")
+    h = conv3x3(x, sd, "head.0", nm)
+    res = h
+    for b in range(nblocks):
+        p = "body.%d.body" % b
+        res = conv3x3(F.relu(conv3x3(res, sd, p + ".0", nm)), sd, p + ".2", nm) * res_scale + res
+    res = conv3x3(res, sd, "body.%d" % nblocks, nm) + h
+    scale = _tail_scale(sd)
+    return conv3x3(upsampler(res, sd, "tail.0", scale, nm), sd, "tail.1", nm)
+
+
+# --------------------------------------------------------------------------------------------
 # Q-SAN pieces (SOCA second-order attention; non-local region attention)
 # --------------------------------------------------------------------------------------------
 def covpool(x: Tensor) -> Tensor:

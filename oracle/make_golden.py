@@ -52,12 +52,16 @@ CASES = {
                                        q_layer_nonlinearity=True), (1, 12, 12), 10),
     "qsan_g2b2": ("qsan", dict(n_resgroups=2, n_resblocks=2, input_para=10, scale=4), (2, 16, 12), 10),
     "qhan_b1": ("qhan", dict(n_resgroups=10, n_resblocks=1, num_metadata=10, scale=4), (1, 8, 8), 10),
+    # non-meta baselines (advanced/architectures.py): same kernels with the meta scale == 1
+    "rcan_g2b2": ("rcan", dict(n_resgroups=2, n_resblocks=2, scale=4), (2, 20, 24), 1),
+    "edsr_f64_b3": ("edsr", dict(num_blocks=3, net_features=64, scale=2, res_scale=0.1), (2, 12, 20), 1),
 }
 
 
 def build_reference(model, kwargs):
     arch = import_reference_architectures()
-    cls = {"qrcan": arch.QRCAN, "qedsr": arch.QEDSR, "qsan": arch.QSAN, "qhan": arch.QHAN}[model]
+    cls = {"qrcan": arch.QRCAN, "qedsr": arch.QEDSR, "qsan": arch.QSAN, "qhan": arch.QHAN,
+           "rcan": arch._ref_advanced.RCAN, "edsr": arch._ref_advanced.EDSR}[model]
     torch.manual_seed(8)
     return cls(**kwargs).eval()
 
@@ -70,7 +74,7 @@ def run_case(name):
     net.load_state_dict(sd, strict=True)
     x, meta = synth_inputs(b, h, w, num_metadata=m_attr, seed=8)
     with torch.no_grad():
-        out = net(x, meta)
+        out = net(x) if model in ("rcan", "edsr") else net(x, meta)
     return shapes, out
 
 

@@ -19,7 +19,7 @@ from oracle.make_golden import CASES, GOLDEN_DIR, build_reference
 from oracle.synth import N_PROJ, grad_projections, synth_inputs, synth_state_dict, synth_target
 
 GRAD_CASES = ["qrcan_standard_g2b2", "qrcan_noq_scale2", "qrcan_modulate", "qrcan_max_concat_scale3", "qedsr_f64_b3",
-              "qedsr_f256_b2_nl"]
+              "qedsr_f256_b2_nl", "rcan_g2b2", "edsr_f64_b3"]
 
 
 def summarize(grads):
@@ -35,7 +35,7 @@ def run_case(name):
     shapes = {k: list(v.shape) for k, v in net.state_dict().items()}
     net.load_state_dict(synth_state_dict(shapes, seed=8), strict=True)
     x, meta = synth_inputs(b, h, w, num_metadata=m_attr, seed=8)
-    out = net(x, meta)
+    out = net(x) if model in ("rcan", "edsr") else net(x, meta)
     y = synth_target(out.shape)
     loss = torch.nn.L1Loss()(out, y)
     net.zero_grad()

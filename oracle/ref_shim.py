@@ -59,6 +59,7 @@ def import_reference_architectures():
         import importlib
         arch = importlib.import_module("SISR.models.attention_manipulators.architectures")
         handlers = importlib.import_module("SISR.models.attention_manipulators.handlers")
+        advanced = importlib.import_module("SISR.models.advanced.architectures")
         ref_mods = {k: v for k, v in sys.modules.items() if k == "SISR" or k.startswith("SISR.")
                     or k == "sr_tools" or k.startswith("sr_tools.")}
     finally:
@@ -70,5 +71,6 @@ def import_reference_architectures():
     for k, v in ref_mods.items():
         sys.modules["_ref." + k] = v
     arch._ref_handlers = handlers
+    arch._ref_advanced = advanced
     _ARCH = arch
     return arch

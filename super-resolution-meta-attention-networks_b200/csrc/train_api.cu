@@ -611,8 +611,7 @@ int dfir_qrcan_repack(const dfir_qrcan_net* n, const dfir_qrcan_params* p, int p
       off += sizes[k];
     }
   }
-  if (n->any_q) {
-    if (p->meta == nullptr) return DFIR_ERR_ARG;
+  if (n->any_q && p->meta != nullptr) {  // (no table: every block is scaled by the constant out_scale, e.g. EDSR)
     const float* const* mt = const_cast<const float* const*>(p->meta);
     const int hid = n->meta_hidden, M = n->num_metadata;
     DFIR_TRY(gather_strided(mt, nullptr, 4, 0, const_cast<float*>(n->meta_w1), nblk, hid * M, 1, 1, static_cast<long long>(hid) * M, st));

@@ -423,9 +423,12 @@ class PackedQrcan:
                 ca_blob, ca_stride = keep(torch.zeros(8, **f32)), 0
             q_flags = [0 if m is None else 1 for m in metas]
             any_q = int(any(q_flags))
+            # blocks scaled by a constant (EDSR's ResBlock: res_scale, no meta-attention): the scale buffer of a block
+            # without a q layer holds out_scale, so an all-disabled table gives exactly that
+            const_scale = bool(cfg.get("constant_block_scale")) and not any_q
             M = cfg["num_metadata"]
             hid = cfg["meta_hidden"]
-            if any_q:
+            if any_q or const_scale:
                 z = lambda *shape: torch.zeros(*shape, **f32)
                 w1, b1, w2, b2 = z(nblk, hid, M), z(nblk, hid), z(nblk, C_, hid), z(nblk, C_)
                 for i, m in enumerate(metas):
@@ -435,6 +438,7 @@ class PackedQrcan:
                         w2[i], b2[i] = f2.weight.reshape(C_, hid), f2.bias
                 self.meta = [keep(t) for t in (w1, b1, w2, b2)]
                 q_enabled = keep(torch.tensor(q_flags, device=dev, dtype=torch.int32))
+                any_q = 1
             else:
                 self.meta = [None] * 4
                 q_enabled = None
@@ -487,7 +491,7 @@ class PackedQrcan:
                 up_w=[m.weight for m in ups], up_b=[m.bias for m in ups],
                 tail_w=tail.weight, tail_b=tail.bias, head_w=head.weight, head_b=head.bias,
                 ca=(None if ca_stride == 0 else [p for blk in spec["ca_params"] for p in blk]),
-                meta=(None if not any_q else
+                meta=(None if not any(q_flags) else
                       [t for m in metas for t in ((None,) * 4 if m is None else (m[0].weight, m[0].bias, m[1].weight, m[1].bias))]))
             self.param_tables, self.params_struct = self._make_tables(lambda p: p.data_ptr())
         self.handle = _NEXT[0]

@@ -12,8 +12,9 @@ QRCAN_CASES = [n for n in golden_names() if n.startswith("qrcan")]  # incl. pixe
 
 def _build(info, precision, **extra):
     from deepfir_b200.han_san import QHAN, QSAN
+    from deepfir_b200.baselines import EDSR, RCAN
     from deepfir_b200.qrcan import QEDSR, QRCAN
-    cls = {"qedsr": QEDSR, "qrcan": QRCAN, "qsan": QSAN, "qhan": QHAN}[info["model"]]
+    cls = {"qedsr": QEDSR, "qrcan": QRCAN, "qsan": QSAN, "qhan": QHAN, "rcan": RCAN, "edsr": EDSR}[info["model"]]
     net = cls(precision=precision, **extra, **info["kwargs"])
     sd, x, meta = case_tensors(info)
     net.load_state_dict(sd, strict=True)
@@ -275,3 +276,37 @@ def test_net_run_and_process_device_postprocessing_is_bit_identical_to_the_host_
     assert rgb.min() >= 0.0 and rgb.max() <= 1.0
     assert np.array_equal(rgb, want_rgb)
     assert np.array_equal(ycc, want_ycc)
+
+
+@pytest.mark.parametrize("name", ["rcan_g2b2", "edsr_f64_b3"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_non_meta_baselines_match_reference_golden(name, precision):
+    """RCAN / EDSR (advanced/architectures.py) through the Q-net kernels with the meta scale == 1:
+    forward(x) without metadata, fp32 mode <= 1e-4, bf16 mode within the storage-policy error"""
+    ref, info = load_golden(name)
+    net, x, meta = _build(info, precision)
+    with torch.no_grad():
+        out = net(x.cuda()).cpu()
+    assert out.shape == ref.shape
+    if precision == "fp32":
+        assert max_norm_err(out, ref) <= 1e-4
+    else:
+        _, pol_err = _policy_error(info, ref)
+        assert max_norm_err(out, ref) <= 2.0 * pol_err + 1e-4, (max_norm_err(out, ref), pol_err)
+
+
+def test_rcan_handler_through_the_registry(tmp_path):
+    """`[model] name = 'rcan'` dispatches to the B200 path: run_eval and one run_train step through the handler"""
+    from SISR.models import ModelInterface
+    torch.manual_seed(8)
+    h = ModelInterface.define_model("edsr", device=0, model_save_dir=str(tmp_path), eval_mode=False, lr=1e-3,
+                                    num_blocks=2, scale=2)
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(2, 3, 16, 16, generator=g)
+    y = torch.nn.functional.interpolate(x, scale_factor=2, mode="bicubic", align_corners=False).clamp(0, 1)
+    out, _, _ = h.run_eval(x)
+    assert out.shape == (2, 3, 32, 32) and not out.is_cuda
+    l0, _ = h.run_train(x, y)
+    for _ in range(8):
+        l1, _ = h.run_train(x, y)
+    assert float(l1) < float(l0)

@@ -153,8 +153,9 @@ def test_wgrad_small_head_and_tail(tail_mode, feat_bf16):
 
 # ------------------------------------------------------------------------------------------------ whole step
 def _build(info, precision):
+    from deepfir_b200.baselines import EDSR, RCAN
     from deepfir_b200.qrcan import QEDSR, QRCAN
-    cls = {"qedsr": QEDSR, "qrcan": QRCAN}[info["model"]]
+    cls = {"qedsr": QEDSR, "qrcan": QRCAN, "rcan": RCAN, "edsr": EDSR}[info["model"]]
     net = cls(precision=precision, **info["kwargs"])
     sd, x, meta = case_tensors(info)
     net.load_state_dict(sd, strict=True)
