@@ -191,6 +191,9 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   const bool exp_no_skipld = (a.debug_probe & 256) != 0;
   const bool exp_no_f32st = (a.debug_probe & 512) != 0;
   const bool exp_no_bfst = (a.debug_probe & 1024) != 0;
+  const bool exp_no_pf = (a.debug_probe & 2048) != 0;      // no L2 prefetch of the skip rows
+  const bool exp_no_tile = (a.debug_probe & 4096) != 0;    // scale+skip epilogue: TMEM reads and barriers only
+  const bool exp_no_pass = (a.debug_probe & 8192) != 0;    // scale+skip epilogue: no coalesced pass
 
   if (g0 < g1) {
     if (warp == 0) {
@@ -595,7 +598,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         };
         if constexpr (EPI == EPI_SCALE_SKIP) {
           if (it == egrp) issue_skip(g, 0);
-          if (has_skip && g + 2 * kEpiGroups < g1) {  // pull the skip row this group needs two rows from now into L2
+          if (has_skip && !exp_no_pf && g + 2 * kEpiGroups < g1) {  // pull the skip row this group needs two rows from now into L2
             const int g2 = g + 2 * kEpiGroups, col2 = g2 / H;
             const size_t e2 = ((static_cast<size_t>(col2 / nseg) * a.H + (g2 % H)) * a.W + (col2 % nseg) * 128) * 64;
             const int npx2 = min(128, a.W - (col2 % nseg) * 128);
@@ -648,34 +651,34 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           // epilogue).
           uint32_t rv[32];
           auto write_tile = [&](int h) {
+            if (exp_no_tile) return;
+            // plain copy: scale and bias are applied in the pass, where each thread owns one 4-channel group
             float4* trow = reinterpret_cast<float4*>(tile + m * 32);
-            const float4* sc4 = reinterpret_cast<const float4*>(sc_s) + h * 8;
-            const float4* bs4 = reinterpret_cast<const float4*>(sc_s + 64) + h * 8;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 s4 = sc4[c], b4 = bs4[c];
-              float4 o;
-              o.x = fmaf(__uint_as_float(rv[4 * c + 0]), s4.x, b4.x);
-              o.y = fmaf(__uint_as_float(rv[4 * c + 1]), s4.y, b4.y);
-              o.z = fmaf(__uint_as_float(rv[4 * c + 2]), s4.z, b4.z);
-              o.w = fmaf(__uint_as_float(rv[4 * c + 3]), s4.w, b4.w);
-              trow[(c + m) & 7] = o;
-            }
+            for (int c = 0; c < 8; ++c)
+              trow[(c + m) & 7] = make_float4(__uint_as_float(rv[4 * c + 0]), __uint_as_float(rv[4 * c + 1]),
+                                              __uint_as_float(rv[4 * c + 2]), __uint_as_float(rv[4 * c + 3]));
           };
           auto pass = [&](int h) {
+            if (exp_no_tile || exp_no_pass) return;
             const size_t e0 = ((static_cast<size_t>(b) * a.H + y) * a.W + seg * 128 + pq) * 64 + h * 32 + c4 * 4;
             float* o32 = a.out_f32 != nullptr ? a.out_f32 + e0 : nullptr;
             __nv_bfloat16* obf = a.out_bf16_direct + e0;
             __nv_bfloat16* rbf = save_r ? a.r_out + e0 : nullptr;
             const float4* t4 = reinterpret_cast<const float4*>(tile);
             const float4* sk4 = reinterpret_cast<const float4*>(skipbuf_g) + et;
+            const float4 s4 = reinterpret_cast<const float4*>(sc_s)[h * 8 + c4];
+            const float4 b4 = reinterpret_cast<const float4*>(sc_s + 64)[h * 8 + c4];
             const float4 sr4 = reinterpret_cast<const float4*>(sc_s + 128)[h * 8 + c4];
             asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int p = i * 16 + pq;
               if (p < npx) {
-                float4 o = t4[p * 8 + ((c4 + p) & 7)];
+                const float4 tv = t4[p * 8 + ((c4 + p) & 7)];
+                float4 o;
+                o.x = fmaf(tv.x, s4.x, b4.x); o.y = fmaf(tv.y, s4.y, b4.y);
+                o.z = fmaf(tv.z, s4.z, b4.z); o.w = fmaf(tv.w, s4.w, b4.w);
                 if (save_r) {  // r = conv + b goes out as bf16 for the backward; the stream gets r * s + skip
                   uint2 rk;
                   rk.x = pack_bf16x2(o.x, o.y);
