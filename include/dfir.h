@@ -282,15 +282,17 @@ int dfir_qrcan_stages(const dfir_qrcan_net* net, int stages, int g_begin, int g_
  * training step: forward with saved activations + backward
  *   (BaseModel.run_train / standard_update, models/__init__.py:466-489: forward, L1 loss, loss.backward(), Adam)
  * The loss, the optimizer and the scheduler stay in PyTorch (they own the fp32 nn.Parameters); the library computes
- * the network forward and every parameter gradient.  Supported: Q-RCAN with style none / standard / modulate /
- * max_concat and Q-EDSR (flat chain), n_feats = 64 on the tensor-core path, any width in fp32 mode.
+ * the network forward and every parameter gradient.  Supported: Q-RCAN with every channel-attention style (no pixel
+ * attention) and Q-EDSR (flat chain), n_feats = 64 on the tensor-core path, any width in fp32 mode.
  * ---------------------------------------------------------------------------------------------- */
 
 /* Device pointers to the fp32 nn.Parameter storages of a network — or, with the same shape, to their gradient
  * buffers.  `conv_w` ... `meta` are arrays of pointers that live in DEVICE memory (the kernels read them), indexed
- * like the trunk arrays of dfir_qrcan_net; ca/meta hold 4 pointers per block: QCALayer.conv_du {0.weight, 0.bias,
- * 2.weight, 2.bias} and ParaCALayer.attribute_integrator {FC1 weight, bias, FC2 weight, bias} (NULL entries for
- * blocks without a q layer).  All tensors keep the reference's OIHW / [out][in] layouts. */
+ * like the trunk arrays of dfir_qrcan_net.  ca holds 8 pointers per block: (weight, bias) of the QCALayer's up to four FC
+ * layers in forward order (standard / modulate / max_concat / softmax: conv_du.0, conv_du.2; mini_concat: pre_concat,
+ * conv_du.1; extended_attention: feature_convs.{0,1,2}.0, final_conv.0; unused entries NULL).  meta holds 4 pointers per
+ * block: ParaCALayer.attribute_integrator {FC1 weight, bias, FC2 weight, bias} (NULL entries for blocks without a q
+ * layer).  All tensors keep the reference's OIHW / [out][in] layouts. */
 typedef struct dfir_qrcan_params {
   float* const* conv_w;  /* [n_trunk] OIHW [C][C][3][3] */
   float* const* conv_b;  /* [n_trunk] [C] */
@@ -298,7 +300,7 @@ typedef struct dfir_qrcan_params {
   float* const* up_b;    /* [n_up]    [r*r*C] */
   float* tail_w; float* tail_b; /* [out_feats][C][3][3], [out_feats] */
   float* head_w; float* head_b; /* [C][in_feats][3][3], [C] */
-  float* const* ca;      /* [n_groups*n_blocks*4] or NULL (style none) */
+  float* const* ca;      /* [n_groups*n_blocks*8] or NULL (style none) */
   float* const* meta;    /* [n_groups*n_blocks*4] or NULL (no q layers) */
 } dfir_qrcan_params;
 

@@ -19,7 +19,7 @@ from oracle.make_golden import CASES, GOLDEN_DIR, build_reference
 from oracle.synth import N_PROJ, grad_projections, synth_inputs, synth_state_dict, synth_target
 
 GRAD_CASES = ["qrcan_standard_g2b2", "qrcan_noq_scale2", "qrcan_modulate", "qrcan_max_concat_scale3", "qedsr_f64_b3",
-              "qedsr_f256_b2_nl", "rcan_g2b2", "edsr_f64_b3"]
+              "qedsr_f256_b2_nl", "rcan_g2b2", "edsr_f64_b3", "qrcan_softmax", "qrcan_mini_concat", "qrcan_extended_scale8"]
 
 
 def summarize(grads):

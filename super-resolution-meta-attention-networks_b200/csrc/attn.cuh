@@ -38,6 +38,47 @@ __host__ __device__ inline int attn_param_count(int style, int C, int R, int M) 
   }
 }
 
+// Every QCALayer style is a chain of fully connected layers on the pooled vector: layer l maps
+// [a_l (nin) ; attributes (M) if cat] -> nout, ReLU on every output but the last layer's, whose sigmoid (and, per style,
+// softmax over channels / multiplication by the attributes) gives the scale.  mini_concat applies its ReLU to the
+// concatenation [pre_concat(y); attributes], i.e. also to the attributes (cat_relu).  Parameters are stored layer by
+// layer as W[nout][nin (+M)], b[nout] — the order listed above.  Used by the backward kernels (train_kernels.cu).
+struct AttnChain {
+  int L;
+  int nin[4], nout[4], cat[4], cat_relu[4];
+  int woff[4], boff[4];  // offsets into the block's parameter blob
+  int aoff[4], doff[4];  // offsets of a_l and of the pre-activation gradients d_l inside a per-image signal record
+  int dzq_off, sig_size, n_params;
+};
+
+__host__ __device__ inline AttnChain make_attn_chain(int style, int C, int R, int M) {
+  AttnChain ch{};
+  auto layer = [&](int l, int nin, int nout, int cat, int cat_relu) {
+    ch.nin[l] = nin; ch.nout[l] = nout; ch.cat[l] = cat; ch.cat_relu[l] = cat_relu;
+  };
+  switch (style) {
+    case DFIR_STYLE_STANDARD:
+    case DFIR_STYLE_MODULATE: ch.L = 2; layer(0, C, R, 0, 0); layer(1, R, C, 0, 0); break;
+    case DFIR_STYLE_MAX_CONCAT:
+    case DFIR_STYLE_SOFTMAX: ch.L = 2; layer(0, C, R, 1, 0); layer(1, R, C, 0, 0); break;
+    case DFIR_STYLE_MINI_CONCAT: ch.L = 2; layer(0, C, R, 0, 0); layer(1, R, C, 1, 1); break;
+    case DFIR_STYLE_EXTENDED:
+      ch.L = 4; layer(0, C, C / 2, 1, 0); layer(1, C / 2, C / 4, 1, 0); layer(2, C / 4, R, 1, 0); layer(3, R, C, 0, 0); break;
+    default: ch.L = 0; break;
+  }
+  int off = 0, so = 0;
+  for (int l = 0; l < ch.L; ++l) {
+    ch.woff[l] = off; off += ch.nout[l] * (ch.nin[l] + (ch.cat[l] ? M : 0));
+    ch.boff[l] = off; off += ch.nout[l];
+    ch.aoff[l] = so; so += ch.nin[l];
+  }
+  for (int l = 0; l < ch.L; ++l) { ch.doff[l] = so; so += ch.nout[l]; }
+  ch.dzq_off = so;
+  ch.sig_size = so + C;
+  ch.n_params = off;
+  return ch;
+}
+
 template <class G>
 __device__ void fc_layer(const G& g, const float* __restrict__ w, const float* __restrict__ bias, const float* in_a,
                          int na, const float* in_b, int nb, float* out, int nout,

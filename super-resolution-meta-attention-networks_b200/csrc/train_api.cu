@@ -12,6 +12,7 @@
 // The data-gradient convs are the forward tensor-core kernel fed with transposed / rotated weights; the weight
 // gradients are csrc/wgrad_mma.cu (bf16) or wgrad_f32 (parity mode).
 #include "kernels.h"
+#include "attn.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -73,9 +74,7 @@ bool train_supported(const dfir_qrcan_net* n, int precision) {
   if (n->n_groups < 1 || n->n_blocks < 1) return false;
   if (n->pa_blob != nullptr) return false;  // pixel attention has no backward kernels yet
   if (n->no_group_conv && n->n_groups != 1) return false;
-  if (n->style != DFIR_STYLE_NONE && n->style != DFIR_STYLE_STANDARD && n->style != DFIR_STYLE_MODULATE &&
-      n->style != DFIR_STYLE_MAX_CONCAT)
-    return false;
+  if (n->style < DFIR_STYLE_NONE || n->style > DFIR_STYLE_EXTENDED) return false;
   if (precision == DFIR_PREC_BF16_TC) return n->n_feats == 64;
   if (precision != DFIR_PREC_FP32_SIMT) return false;
   return n->n_feats % 64 == 0 && n->n_feats <= 256 && 256 % n->n_feats == 0;
@@ -136,7 +135,7 @@ TrainWs carve_train(const dfir_qrcan_net* n, int B, int H, int W, int precision,
   w.red = c.take<float>(static_cast<size_t>(B) * 32 * C * 4);
   w.svec = c.take<float>(static_cast<size_t>(B) * C * 4);
   w.dyv = c.take<float>(static_cast<size_t>(B) * C * 4);
-  w.sig_stride = 3 * C + 2 * std::max(1, n->reduced);
+  w.sig_stride = make_attn_chain(n->style, C, std::max(1, n->reduced), n->num_metadata).sig_size;
   w.sig = c.take<float>(static_cast<size_t>(nblk) * B * w.sig_stride * 4);
   w.ymean = c.take<float>(static_cast<size_t>(nblk) * B * C * 4);
   w.tickets = c.take<unsigned int>(static_cast<size_t>(B) * 4);
@@ -600,15 +599,13 @@ int dfir_qrcan_repack(const dfir_qrcan_net* n, const dfir_qrcan_params* p, int p
   }
   if (n->style != DFIR_STYLE_NONE) {
     if (p->ca == nullptr) return DFIR_ERR_ARG;
-    const int R = std::max(1, n->reduced);
-    const int Cin = n->style == DFIR_STYLE_MAX_CONCAT || n->style == DFIR_STYLE_SOFTMAX ? C + n->num_metadata : C;
-    const int sizes[4] = {R * Cin, R, C * R, C};
+    const AttnChain ch = make_attn_chain(n->style, C, std::max(1, n->reduced), n->num_metadata);
     float* blob = const_cast<float*>(n->ca_blob);
     const float* const* ca = const_cast<const float* const*>(p->ca);
-    size_t off = 0;
-    for (int k = 0; k < 4; ++k) {
-      DFIR_TRY(gather_strided(ca, nullptr, 4, k, blob + off, nblk, sizes[k], 1, 1, n->ca_stride, st));
-      off += sizes[k];
+    for (int l = 0; l < ch.L; ++l) {  // table: 8 pointers per block = (W, b) of up to four chain layers
+      const int kin = ch.nin[l] + (ch.cat[l] ? n->num_metadata : 0);
+      DFIR_TRY(gather_strided(ca, nullptr, 8, 2 * l, blob + ch.woff[l], nblk, ch.nout[l] * kin, 1, 1, n->ca_stride, st));
+      DFIR_TRY(gather_strided(ca, nullptr, 8, 2 * l + 1, blob + ch.boff[l], nblk, ch.nout[l], 1, 1, n->ca_stride, st));
     }
   }
   if (n->any_q && p->meta != nullptr) {  // (no table: every block is scaled by the constant out_scale, e.g. EDSR)

@@ -149,10 +149,10 @@ __device__ __forceinline__ void bwd_reduce_gr_body(const float* __restrict__ g, 
 
 // ------------------------------------------------------------------------------------------------
 // Backward of the block's scale vector s = QCALayer(mean(r), attributes) * meta_scale for image b = blockIdx.x
-// (attention_manipulators/architectures.py:105-127, q_layer.py:39-43), styles NONE / STANDARD / MODULATE /
-// MAX_CONCAT.  Emits what the two full-tensor passes need (s and the constant dL/dr contribution of the mean) and
-// the per-image signals from which attn_param_grads_kernel forms the parameter gradients in a fixed order.
-//   sig[b] = { y[C], h[R], dz2[C], dh[R], dzq[C] }
+// (attention_manipulators/architectures.py:105-127, q_layer.py:39-43), every style (the MLP is walked as the generic
+// layer chain of attn.cuh).  Emits what the two full-tensor passes need (s and the constant dL/dr contribution of the
+// mean) and the per-image signals from which attn_param_grads_kernel forms the parameter gradients in a fixed order.
+//   sig[b] = { a_0 = y, a_1, .., a_{L-1} | d_0, .., d_{L-1} | dzq[C] }     (AttnChain::aoff / doff / dzq_off)
 // ------------------------------------------------------------------------------------------------
 struct CaBwdArgs {
   const float* part; int nchunk;
@@ -167,7 +167,7 @@ struct CaBwdArgs {
 };
 
 __device__ void ca_backward_image(const CaBwdArgs& a, const int b, const int tid, const int NT) {
-  __shared__ float ds[256], y[256], dz2[256], attr[512], h[64], dh[64], tmp[512];
+  __shared__ float ds[256], y[256], zl[256], sca[256], attr[512], tmp[512], dv[1024], red2[4];
   const int C = a.C, R = a.R;
   for (int c = tid; c < C; c += NT) {
     float t = 0.f;
@@ -181,12 +181,13 @@ __device__ void ca_backward_image(const CaBwdArgs& a, const int b, const int tid
       const float sqv = a.sq != nullptr ? a.sq[static_cast<size_t>(b) * C + c] : a.out_scale;
       a.svec[static_cast<size_t>(b) * C + c] = sqv;
       const float sg = sqv / a.out_scale;  // sigmoid output
-      sig[2 * C + 2 * R + c] = a.sq != nullptr ? ds[c] * a.out_scale * sg * (1.f - sg) : 0.f;
+      sig[c] = a.sq != nullptr ? ds[c] * a.out_scale * sg * (1.f - sg) : 0.f;  // style none: the record is dzq only
     }
     return;
   }
-  const int Cin = (a.style == DFIR_STYLE_MAX_CONCAT) ? C + a.M : C;
-  const float* W1 = a.ca; const float* b1 = W1 + R * Cin; const float* W2 = b1 + R; const float* b2 = W2 + C * R;
+  const AttnChain ch = make_attn_chain(a.style, C, R, a.M);
+  const int M = a.M;
+  float* av = tmp;   // activations a_0 .. a_{L-1}, laid out like the signal record (<= C + C/2 + C/4 + R floats)
   // pooled mean: saved by the forward, or rebuilt in the same fixed summation order as the forward streamer
   if (a.ymean != nullptr) {
     for (int c = tid; c < C; c += NT) y[c] = a.ymean[static_cast<size_t>(b) * C + c];
@@ -199,58 +200,96 @@ __device__ void ca_backward_image(const CaBwdArgs& a, const int b, const int tid
       const float* pr = a.pool_rows + static_cast<size_t>(b) * a.pool_nrows * C + c;
       float s = 0.f;
       for (int row = grp; row < a.pool_nrows; row += ngrp) s += pr[static_cast<size_t>(row) * C];
-      tmp[i] = s;
+      dv[i] = s;
     }
     for (int i = tid; i < a.A; i += NT) attr[i] = a.attributes[static_cast<size_t>(b) * a.A + i];
     __syncthreads();
     for (int c = tid; c < C; c += NT) {
       float t = 0.f;
-      for (int gI = 0; gI < ngrp; ++gI) t += tmp[gI * C + c];
+      for (int gI = 0; gI < ngrp; ++gI) t += dv[gI * C + c];
       y[c] = t / static_cast<float>(a.HW);
     }
     __syncthreads();
   }
-  for (int j = tid; j < R; j += NT) {
-    const float* wr = W1 + static_cast<size_t>(j) * Cin;
-    float s = b1[j];
-    for (int i = 0; i < C; ++i) s = fmaf(wr[i], y[i], s);
-    for (int i = C; i < Cin; ++i) s = fmaf(wr[i], attr[i - C], s);
-    h[j] = fmaxf(s, 0.f);
-  }
+  for (int c = tid; c < C; c += NT) av[ch.aoff[0] + c] = y[c];
   __syncthreads();
+  // ---- forward through the chain (hidden activations are needed by the backward)
+  for (int l = 0; l < ch.L; ++l) {
+    const int nin = ch.nin[l], kin = nin + (ch.cat[l] ? M : 0);
+    const float* W = a.ca + ch.woff[l];
+    const float* bias = a.ca + ch.boff[l];
+    const float* in = av + ch.aoff[l];
+    float* out = (l + 1 < ch.L) ? av + ch.aoff[l + 1] : zl;
+    for (int o = tid; o < ch.nout[l]; o += NT) {
+      const float* wr = W + static_cast<size_t>(o) * kin;
+      float s = bias[o];
+      for (int i = 0; i < nin; ++i) s = fmaf(wr[i], in[i], s);
+      if (ch.cat[l])
+        for (int m = 0; m < M; ++m) s = fmaf(wr[nin + m], ch.cat_relu[l] ? fmaxf(attr[m], 0.f) : attr[m], s);
+      out[o] = (l + 1 < ch.L) ? fmaxf(s, 0.f) : s;
+    }
+    __syncthreads();
+  }
+  // ---- scale of the block and the gradient arriving at the last layer's pre-activation
+  for (int c = tid; c < C; c += NT) zl[c] = 1.f / (1.f + expf(-zl[c]));  // sigmoid
+  __syncthreads();
+  if (a.style == DFIR_STYLE_SOFTMAX) {  // softmax over the channels AFTER the sigmoid (architectures.py:100-101)
+    if (tid == 0) {
+      float mx = -1e30f;
+      for (int c = 0; c < C; ++c) mx = fmaxf(mx, zl[c]);
+      float sum = 0.f;
+      for (int c = 0; c < C; ++c) sum += expf(zl[c] - mx);
+      red2[0] = mx;
+      red2[1] = sum;
+    }
+    __syncthreads();
+  }
+  float* dl = dv + ch.doff[ch.L - 1] - ch.doff[0];  // d_l stored contiguously from dv[0] in signal order
   for (int c = tid; c < C; c += NT) {
-    const float* wr = W2 + static_cast<size_t>(c) * R;
-    float s = b2[c];
-    for (int j = 0; j < R; ++j) s = fmaf(wr[j], h[j], s);
-    const float sg = 1.f / (1.f + expf(-s));
-    const float mod = a.style == DFIR_STYLE_MODULATE ? attr[c] : 1.f;
+    const float sg = zl[c];
     const float sqv = a.sq != nullptr ? a.sq[static_cast<size_t>(b) * C + c] : 1.f;
-    const float s_ca = sg * mod;
+    float s_ca = sg;
+    if (a.style == DFIR_STYLE_MODULATE) s_ca = sg * attr[c];
+    if (a.style == DFIR_STYLE_SOFTMAX) s_ca = expf(sg - red2[0]) / red2[1];
+    sca[c] = s_ca;
     a.svec[static_cast<size_t>(b) * C + c] = s_ca * sqv;
-    const float d_sca = ds[c] * sqv;
-    const float d_sq = ds[c] * s_ca;
     const float sgq = sqv / a.out_scale;
-    sig[2 * C + 2 * R + c] = a.sq != nullptr ? d_sq * a.out_scale * sgq * (1.f - sgq) : 0.f;
-    dz2[c] = d_sca * mod * sg * (1.f - sg);
+    sig[ch.dzq_off + c] = a.sq != nullptr ? ds[c] * s_ca * a.out_scale * sgq * (1.f - sgq) : 0.f;
+    ds[c] = ds[c] * sqv;  // now dL/d s_ca
   }
   __syncthreads();
-  for (int j = tid; j < R; j += NT) {
-    float s = 0.f;
-    for (int c = 0; c < C; ++c) s = fmaf(W2[static_cast<size_t>(c) * R + j], dz2[c], s);
-    dh[j] = h[j] > 0.f ? s : 0.f;
+  if (a.style == DFIR_STYLE_SOFTMAX) {
+    if (tid == 0) {
+      float dot = 0.f;
+      for (int c = 0; c < C; ++c) dot = fmaf(sca[c], ds[c], dot);
+      red2[2] = dot;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   for (int c = tid; c < C; c += NT) {
-    float s = 0.f;
-    for (int j = 0; j < R; ++j) s = fmaf(W1[static_cast<size_t>(j) * Cin + c], dh[j], s);
-    a.dyv[static_cast<size_t>(b) * C + c] = s / static_cast<float>(a.HW);
-    sig[c] = y[c];
-    sig[C + R + c] = dz2[c];
+    const float sg = zl[c];
+    float d_sg = ds[c];
+    if (a.style == DFIR_STYLE_MODULATE) d_sg *= attr[c];
+    if (a.style == DFIR_STYLE_SOFTMAX) d_sg = sca[c] * (ds[c] - red2[2]);
+    dl[c] = d_sg * sg * (1.f - sg);
   }
-  for (int j = tid; j < R; j += NT) {
-    sig[C + j] = h[j];
-    sig[2 * C + R + j] = dh[j];
+  __syncthreads();
+  // ---- backward through the chain: d_{l-1} = (W_l[:, :nin]^T d_l) * (a_l > 0);  dy = W_0[:, :C]^T d_0
+  for (int l = ch.L - 1; l >= 0; --l) {
+    const int nin = ch.nin[l], kin = nin + (ch.cat[l] ? M : 0), nout = ch.nout[l];
+    const float* W = a.ca + ch.woff[l];
+    const float* dcur = dv + ch.doff[l] - ch.doff[0];
+    for (int i = tid; i < nin; i += NT) {
+      float s = 0.f;
+      for (int o = 0; o < nout; ++o) s = fmaf(W[static_cast<size_t>(o) * kin + i], dcur[o], s);
+      if (l > 0) dv[ch.doff[l - 1] - ch.doff[0] + i] = av[ch.aoff[l] + i] > 0.f ? s : 0.f;
+      else a.dyv[static_cast<size_t>(b) * C + i] = s / static_cast<float>(a.HW);
+    }
+    __syncthreads();
   }
+  // ---- per-image signal record for attn_param_grads_kernel
+  for (int i = tid; i < ch.doff[0]; i += NT) sig[i] = av[i];
+  for (int i = tid; i < ch.dzq_off - ch.doff[0]; i += NT) sig[ch.doff[0] + i] = dv[i];
 }
 
 // One launch for "ds = sum g*r" and the attention-MLP backward: the chunk CTA that finishes an image last (atomic
@@ -555,7 +594,7 @@ struct AttnGradArgs {
   const float* attributes; int A;        // [B][A]
   const float* meta_w1; const float* meta_b1; const float* meta_w2;  // packed [nblk][Hid][M], [nblk][Hid], [nblk][C][Hid]
   const int* q_enabled;
-  float* const* ca_g;                    // [nblk*4] W1, b1, W2, b2 gradients (nullptr table = no channel attention)
+  float* const* ca_g;                    // [nblk*8] (W, b) gradients per chain layer (nullptr table = no channel attention)
   float* const* meta_g;                  // [nblk*4] FC1 w, b, FC2 w, b gradients (NULL entries where no q layer)
   int B, C, R, M, Hid, style, meta_relu;
 };
@@ -565,35 +604,32 @@ __global__ void __launch_bounds__(256) attn_param_grads_kernel(AttnGradArgs a) {
   const int blk = blockIdx.x, tid = threadIdx.x;
   const int B = a.B, C = a.C, R = a.R, M = a.M, Hid = a.Hid;
   const float* sig = a.sig + static_cast<size_t>(blk) * B * a.sig_stride;
-  const int o_y = 0, o_h = C, o_dz2 = C + R, o_dh = 2 * C + R, o_dzq = 2 * C + 2 * R;
+  const AttnChain ch = make_attn_chain(a.style, C, R, M);
+  const int o_dzq = ch.dzq_off;
   if (a.style != DFIR_STYLE_NONE && a.ca_g != nullptr) {
-    const int Cin = (a.style == DFIR_STYLE_MAX_CONCAT) ? C + M : C;
-    float* gW1 = a.ca_g[blk * 4 + 0]; float* gb1 = a.ca_g[blk * 4 + 1];
-    float* gW2 = a.ca_g[blk * 4 + 2]; float* gb2 = a.ca_g[blk * 4 + 3];
-    for (int e = tid; e < C * R; e += 256) {
-      const int c = e / R, j = e % R;
-      float t = 0.f;
-      for (int b = 0; b < B; ++b) t = fmaf(sig[b * a.sig_stride + o_dz2 + c], sig[b * a.sig_stride + o_h + j], t);
-      gW2[e] = t;
-    }
-    for (int c = tid; c < C; c += 256) {
-      float t = 0.f;
-      for (int b = 0; b < B; ++b) t += sig[b * a.sig_stride + o_dz2 + c];
-      gb2[c] = t;
-    }
-    for (int e = tid; e < R * Cin; e += 256) {
-      const int j = e / Cin, i = e % Cin;
-      float t = 0.f;
-      for (int b = 0; b < B; ++b) {
-        const float in = i < C ? sig[b * a.sig_stride + o_y + i] : a.attributes[static_cast<size_t>(b) * a.A + (i - C)];
-        t = fmaf(sig[b * a.sig_stride + o_dh + j], in, t);
+    for (int l = 0; l < ch.L; ++l) {  // dW_l[o][i] = sum_b d_l[b][o] * in_l[b][i],  db_l[o] = sum_b d_l[b][o]
+      float* gW = a.ca_g[blk * 8 + 2 * l];
+      float* gb = a.ca_g[blk * 8 + 2 * l + 1];
+      const int nin = ch.nin[l], kin = nin + (ch.cat[l] ? M : 0), nout = ch.nout[l];
+      for (int e = tid; e < nout * kin; e += 256) {
+        const int o = e / kin, i = e % kin;
+        float t = 0.f;
+        for (int b = 0; b < B; ++b) {
+          float in;
+          if (i < nin) in = sig[b * a.sig_stride + ch.aoff[l] + i];
+          else {
+            in = a.attributes[static_cast<size_t>(b) * a.A + (i - nin)];
+            if (ch.cat_relu[l]) in = fmaxf(in, 0.f);
+          }
+          t = fmaf(sig[b * a.sig_stride + ch.doff[l] + o], in, t);
+        }
+        gW[e] = t;
       }
-      gW1[e] = t;
-    }
-    for (int j = tid; j < R; j += 256) {
-      float t = 0.f;
-      for (int b = 0; b < B; ++b) t += sig[b * a.sig_stride + o_dh + j];
-      gb1[j] = t;
+      for (int o = tid; o < nout; o += 256) {
+        float t = 0.f;
+        for (int b = 0; b < B; ++b) t += sig[b * a.sig_stride + ch.doff[l] + o];
+        gb[o] = t;
+      }
     }
   }
   if (a.meta_g == nullptr || a.q_enabled == nullptr || a.q_enabled[blk] == 0) return;
@@ -684,9 +720,8 @@ int bwd_reduce_ca(const float* g, const void* r, int r_is_bf16, float* part, uns
   const int C = ap.C;
   if (C % 8 != 0 || C > 256 || 256 % (C / 8) != 0) return DFIR_ERR_ARG;
   if (ap.C > 256 || 256 % ap.C != 0 || ap.R > 64 || ap.A > 512) return DFIR_ERR_ARG;
-  if (ap.style != DFIR_STYLE_NONE && ap.style != DFIR_STYLE_STANDARD && ap.style != DFIR_STYLE_MODULATE &&
-      ap.style != DFIR_STYLE_MAX_CONCAT)
-    return DFIR_ERR_ARG;
+  if (ap.style < DFIR_STYLE_NONE || ap.style > DFIR_STYLE_EXTENDED) return DFIR_ERR_ARG;
+  if (sig_stride < make_attn_chain(ap.style, ap.C, ap.R, ap.M).sig_size) return DFIR_ERR_ARG;
   CaBwdArgs a{};
   a.part = part; a.nchunk = bwd_reduce_chunks(HW); a.pool_rows = pool_rows; a.pool_nrows = pool_nrows; a.HW = HW;
   a.style = ap.style; a.C = ap.C; a.R = ap.R; a.M = ap.M; a.A = ap.A; a.ca = ap.w[0];

@@ -483,14 +483,14 @@ class PackedQrcan:
         self.ws_owner = None
         # device pointer tables of the fp32 parameters: lets the C side refresh every kernel-format buffer in a few
         # launches (styles whose attention block has the 4-tensor layout; the others are rebuilt from Python)
-        self.can_repack = "ca_params" in spec and pa_blob is None and cfg["style"] in ("none", "standard", "modulate",
-                                                                                        "max_concat", "softmax")
+        self.can_repack = "ca_params" in spec and pa_blob is None
         if self.can_repack:
             self._spec_params = dict(
                 conv_w=[m.weight for m in trunk], conv_b=[m.bias for m in trunk],
                 up_w=[m.weight for m in ups], up_b=[m.bias for m in ups],
                 tail_w=tail.weight, tail_b=tail.bias, head_w=head.weight, head_b=head.bias,
-                ca=(None if ca_stride == 0 else [p for blk in spec["ca_params"] for p in blk]),
+                ca=(None if ca_stride == 0 else
+                    [p for blk in spec["ca_params"] for p in (list(blk) + [None] * (8 - len(blk)))]),
                 meta=(None if not any(q_flags) else
                       [t for m in metas for t in ((None,) * 4 if m is None else (m[0].weight, m[0].bias, m[1].weight, m[1].bias))]))
             self.param_tables, self.params_struct = self._make_tables(lambda p: p.data_ptr())
@@ -530,8 +530,8 @@ class PackedQrcan:
         """Buffers that only a training step needs: data-gradient weight layouts, one flat gradient buffer with a
         view per parameter, and the gradient pointer tables."""
         if not self.can_repack:
-            raise NotImplementedError("training on the B200 path supports the channel-attention styles "
-                                      "none/standard/modulate/max_concat")
+            raise NotImplementedError("this network has no training path on the B200 library (pixel attention, Q-SAN, "
+                                      "Q-HAN)")
         d = self.desc
         dev = self.device
         C_ = d.n_feats
