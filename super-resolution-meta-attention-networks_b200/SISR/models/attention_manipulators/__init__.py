@@ -26,6 +26,18 @@ class QModel(BaseModel):
             self.num_metadata = len(metadata) + extra
         super(QModel, self).__init__(**kwargs)
 
+    # every Q-handler ends its constructor the same way (ref handlers.py :31-35, :69-73, :90-94, :166-170): record the
+    # colour space / input convention, move the parameters to the device, create optimizer + scheduler, name the model
+    model_key = None
+    colour = 'rgb'
+
+    def finish_setup(self, lr, scheduler, scheduler_params, perceptual, device):
+        self.colorspace = self.colour
+        self.im_input = 'unmodified'
+        self.activate_device()
+        self.training_setup(lr, scheduler, scheduler_params, perceptual, device)
+        self.model_name = self.model_key
+
     def generate_channels(self, x, metadata, keys):
         """metadata (B, K) + keys (K tuples, DataLoader-collated) -> (B, M, 1, 1) fp32 (ref :30-51).
         Vectorised: one masked gather instead of the reference's per-image Python loop."""

@@ -1,11 +1,14 @@
-"""Handlers of the metadata-conditioned networks (reference:
-Code/SISR/models/attention_manipulators/handlers.py).  Same class names (the registry keys are derived from
-them), constructor arguments and attributes; the networks they own are the B200 implementations in
-`deepfir_b200`.  Extra optional `internal_params` keys understood here: `precision` ('bf16' | 'fp32') and
-`chunk_images`; reference configs that do not carry them load unchanged."""
+"""Handlers of the metadata-conditioned networks on the B200 path.
+
+API mirror of the reference's Code/SISR/models/attention_manipulators/handlers.py: the registry derives the model keys
+(`qrcan`, `qedsr`, `qsan`, `qhan`) from these class names, and `ModelInterface` / the training and evaluation loops rely
+on the constructor arguments and attributes kept here.  The networks the handlers own are the B200 implementations of
+`deepfir_b200`.  Optional extra `internal_params` keys: `precision` ('bf16' | 'fp32'), `schedule`, `chunk_images`;
+reference TOMLs that do not carry them load unchanged.
+"""
+import math
 import time
 
-import numpy as np
 import torch
 from torch import nn
 
@@ -13,108 +16,112 @@ from SISR.models.attention_manipulators import QModel
 from deepfir_b200.han_san import QHAN, QSAN
 from deepfir_b200.qrcan import QEDSR, QRCAN
 
+_B200_KEYS = ('precision', 'schedule')
+
 
 class QRCANHandler(QModel):
-    """Meta-attention RCAN: 10 residual groups x 20 RCABs by default.  `include_q_layer`,
-    `selective_meta_blocks` (one bool per group) and `num_q_layers_inner_residual` place the
-    meta-attention layers exactly as in the reference (handlers.py:7-40)."""
+    """Meta-attention RCAN (ref :7-54): 10 residual groups x 20 RCABs by default; `include_q_layer`,
+    `selective_meta_blocks` (one flag per group) and `num_q_layers_inner_residual` place the meta-attention layers;
+    `style` picks the QCALayer variant ('modulate' feeds a Gaussian bump built from the scalar metadata)."""
+
+    model_key = 'qrcan'
+    colour = 'augmented_rgb'
 
     def __init__(self, device, model_save_dir, eval_mode=False, lr=1e-4, scale=4, in_features=3, scheduler=None,
                  scheduler_params=None, style='modulate', perceptual=None, clamp=False, min_mu=-0.2,
                  max_mu=0.8, n_feats=64, **kwargs):
-        super(QRCANHandler, self).__init__(device=device, model_save_dir=model_save_dir, eval_mode=eval_mode,
-                                           **kwargs)
-        self.net = QRCAN(scale=scale, in_feats=in_features, num_metadata=self.num_metadata,
-                         n_feats=n_feats, style=style, **kwargs)
-        self.colorspace = 'augmented_rgb'
-        self.im_input = 'unmodified'
-        self.activate_device()
-        self.training_setup(lr, scheduler, scheduler_params, perceptual, device)
-        self.model_name = 'qrcan'
-        self.min_mu = min_mu
-        self.max_mu = max_mu
-        self.base_scaler = np.linspace(0, 1, n_feats)
-        self.clamp = clamp
+        super().__init__(device=device, model_save_dir=model_save_dir, eval_mode=eval_mode, **kwargs)
+        self.net = QRCAN(scale=scale, in_feats=in_features, num_metadata=self.num_metadata, n_feats=n_feats, style=style,
+                         **kwargs)
+        self.finish_setup(lr, scheduler, scheduler_params, perceptual, device)
         self.style = style
+        self.clamp = clamp
+        self.min_mu, self.max_mu = min_mu, max_mu
+        self.base_scaler = torch.linspace(0, 1, n_feats, dtype=torch.float64).numpy()
 
     @staticmethod
     def gaussian(x, mu, sig=0.2):
-        g = (1 / (np.sqrt(2 * np.pi) * sig)) * np.exp(-np.power(x - mu, 2.) / (2 * np.power(sig, 2.)))
-        return torch.from_numpy(g).type(torch.float32)
+        """normal density with mean `mu`, evaluated on the bin centres `x` (ref :37-40)"""
+        grid = torch.as_tensor(x, dtype=torch.float64)
+        mu = torch.as_tensor(mu, dtype=torch.float64)
+        dens = torch.exp(-(grid - mu) ** 2 / (2.0 * sig ** 2)) / (math.sqrt(2.0 * math.pi) * sig)
+        return dens.to(torch.float32)
 
     def scale_qpi(self, qpi):
-        """'modulate' style: each image's scalar becomes an n_feats-bin Gaussian bump (ref :42-54)."""
-        mu = (qpi * (self.max_mu - self.min_mu)) + self.min_mu
-        rows = torch.stack([self.gaussian(self.base_scaler, mu[i].squeeze().numpy()) for i in range(mu.size(0))])
+        """'modulate' style (ref :42-54): every image's scalar in [0,1] moves the centre of a Gaussian over the
+        n_feats bins; returns (B, n_feats, 1, 1).  Vectorised over the batch."""
+        centres = (qpi.reshape(qpi.size(0), 1) * (self.max_mu - self.min_mu) + self.min_mu).to(torch.float64)
+        bumps = self.gaussian(torch.as_tensor(self.base_scaler).reshape(1, -1), centres)
         if self.clamp:
-            rows = torch.clamp(rows, 0, 1)
-        return rows.unsqueeze(2).unsqueeze(3)
+            bumps = bumps.clamp(0, 1)
+        return bumps[:, :, None, None]
 
 
 class QEDSRHandler(QModel):
-    """Meta-attention EDSR (ref :57-76): ParamResBlock chain, every block scaled by its meta-attention vector."""
+    """Meta-attention EDSR (ref :57-76): a chain of ParamResBlocks, each scaled by its meta-attention vector."""
+
+    model_key = 'qedsr'
+    colour = 'augmented_rgb'
 
     def __init__(self, device, model_save_dir, eval_mode=False, lr=1e-4, scale=4, in_features=3, num_blocks=16,
                  num_features=64, res_scale=0.1, scheduler=None, scheduler_params=None, perceptual=None, **kwargs):
-        super(QEDSRHandler, self).__init__(device=device, model_save_dir=model_save_dir, eval_mode=eval_mode,
-                                           **kwargs)
-        if num_features % 64 != 0:  # the tensor-core kernels work on 64-channel planes; other widths run fp32
+        super().__init__(device=device, model_save_dir=model_save_dir, eval_mode=eval_mode, **kwargs)
+        if num_features % 64:  # the tensor-core kernels work on 64-channel planes; other widths take the fp32 kernels
             kwargs.setdefault('precision', 'fp32')
         self.net = QEDSR(scale=scale, in_features=in_features, num_features=num_features, num_blocks=num_blocks,
                          res_scale=res_scale, input_para=self.num_metadata, **kwargs)
-        self.colorspace = 'augmented_rgb'
-        self.im_input = 'unmodified'
-        self.activate_device()
-        self.model_name = 'qedsr'
         self.criterion = nn.L1Loss()
-        self.training_setup(lr, scheduler, scheduler_params, perceptual, device)
+        self.finish_setup(lr, scheduler, scheduler_params, perceptual, device)
 
 
 class QSANHandler(QModel):
-    """Meta-attention SAN (ref :79-153).  Evaluation always goes through `forward_chop`: four overlapping
-    quadrants (10 px of overlap), each run through the network if smaller than `max_combined_im_size`, else
-    chopped again; the inner halves are stitched back together."""
+    """Meta-attention SAN (ref :79-153).  Like the reference, evaluation never sees the whole image: it is cut into four
+    overlapping quadrants (recursively while a quadrant has `max_combined_im_size` pixels or more), each quadrant runs
+    through the network, and the non-overlapping parts are stitched together."""
+
+    model_key = 'qsan'
 
     def __init__(self, device, model_save_dir, eval_mode=False, lr=1e-4, scale=4, perceptual=None,
                  max_combined_im_size=160000, scheduler=None, scheduler_params=None, **kwargs):
-        super(QSANHandler, self).__init__(device=device, model_save_dir=model_save_dir, eval_mode=eval_mode,
-                                          **kwargs)
-        extra = {k: kwargs[k] for k in ('precision', 'schedule') if k in kwargs}
-        self.net = QSAN(scale=scale, input_para=self.num_metadata, **extra)  # like the reference: fixed 20 x 10 trunk
+        super().__init__(device=device, model_save_dir=model_save_dir, eval_mode=eval_mode, **kwargs)
+        self.net = QSAN(scale=scale, input_para=self.num_metadata, **{k: kwargs[k] for k in _B200_KEYS if k in kwargs})
         self.scale = scale
-        self.colorspace = 'rgb'
-        self.im_input = 'unmodified'
-        self.activate_device()
-        self.training_setup(lr, scheduler, scheduler_params, perceptual, device)
         self.max_combined_im_size = max_combined_im_size
-        self.model_name = 'qsan'
+        self.finish_setup(lr, scheduler, scheduler_params, perceptual, device)
 
     def forward_chop(self, x, extra_channels, shave=10):
-        b, c, h, w = x.size()
-        h_half, w_half = h // 2, w // 2
-        h_size, w_size = h_half + shave, w_half + shave
-        quadrants = [x[:, :, 0:h_size, 0:w_size], x[:, :, 0:h_size, (w - w_size):w],
-                     x[:, :, (h - h_size):h, 0:w_size], x[:, :, (h - h_size):h, (w - w_size):w]]
-        if w_size * h_size < self.max_combined_im_size:
-            sr = [self.run_chopped_eval(q, extra_channels) for q in quadrants]
-        else:
-            sr = [self.forward_chop(q, extra_channels, shave=shave) for q in quadrants]
+        """Quadrant (i, j) covers rows [0, h/2 + shave) or [h - h/2 - shave, h) (same for columns); of its SR result the
+        rows / columns nearest to its own image corner are kept: h/2 (or the remaining h - h/2) of them."""
+        batch, chans, height, width = x.shape
+        half = (height // 2, width // 2)
+        size = (half[0] + shave, half[1] + shave)
+        full = (height, width)
+
+        def span(axis, far):  # LR slice of a quadrant along one axis
+            return slice(full[axis] - size[axis], full[axis]) if far else slice(0, size[axis])
+
+        small = size[0] * size[1] < self.max_combined_im_size
         s = self.scale
-        h, w, h_half, w_half, h_size, w_size = s * h, s * w, s * h_half, s * w_half, s * h_size, s * w_size
-        output = x.new(b, c, h, w)
-        output[:, :, 0:h_half, 0:w_half] = sr[0][:, :, 0:h_half, 0:w_half]
-        output[:, :, 0:h_half, w_half:w] = sr[1][:, :, 0:h_half, (w_size - w + w_half):w_size]
-        output[:, :, h_half:h, 0:w_half] = sr[2][:, :, (h_size - h + h_half):h_size, 0:w_half]
-        output[:, :, h_half:h, w_half:w] = sr[3][:, :, (h_size - h + h_half):h_size, (w_size - w + w_half):w_size]
-        return output
+        out = x.new_empty(batch, chans, s * height, s * width)
+        for far_r in (0, 1):
+            for far_c in (0, 1):
+                quad = x[:, :, span(0, far_r), span(1, far_c)]
+                sr = self.run_chopped_eval(quad, extra_channels) if small else \
+                    self.forward_chop(quad, extra_channels, shave=shave)
+                dst, src = [], []
+                for axis, far in ((0, far_r), (1, far_c)):
+                    cut, whole, tile = s * half[axis], s * full[axis], s * size[axis]
+                    dst.append(slice(cut, whole) if far else slice(0, cut))
+                    src.append(slice(tile - (whole - cut), tile) if far else slice(0, cut))
+                out[:, :, dst[0], dst[1]] = sr[:, :, src[0], src[1]]
+        return out
 
     def run_eval(self, x, y=None, request_loss=False, metadata=None, metadata_keys=None, timing=False, *args, **kwargs):
-        extra_channels = self.generate_channels(x, metadata, metadata_keys).to(self.device)
-        tic = time.perf_counter()
-        sr_image = self.forward_chop(x, extra_channels)
-        elapsed = time.perf_counter() - tic
-        loss = self.criterion(sr_image, y) if request_loss else None
-        return sr_image, loss, elapsed if timing else None
+        attributes = self.generate_channels(x, metadata, metadata_keys).to(self.device)
+        started = time.perf_counter()
+        sr_image = self.forward_chop(x, attributes)
+        elapsed = time.perf_counter() - started
+        return sr_image, (self.criterion(sr_image, y) if request_loss else None), (elapsed if timing else None)
 
     def run_chopped_eval(self, x, extra_channels):
         return super().run_eval(x.contiguous(), y=None, request_loss=False, extra_channels=extra_channels)[0]
@@ -123,14 +130,10 @@ class QSANHandler(QModel):
 class QHANHandler(QModel):
     """Meta-attention HAN (ref :156-171): Q-RCAN groups + layer attention + channel-spatial attention."""
 
+    model_key = 'qhan'
+
     def __init__(self, device, model_save_dir, eval_mode=False, lr=1e-4, scale=4, perceptual=None,
                  scheduler=None, scheduler_params=None, **kwargs):
-        super(QHANHandler, self).__init__(device=device, model_save_dir=model_save_dir, eval_mode=eval_mode,
-                                          **kwargs)
-        extra = {k: kwargs[k] for k in ('precision', 'schedule') if k in kwargs}
-        self.net = QHAN(scale=scale, num_metadata=self.num_metadata, **extra)
-        self.colorspace = 'rgb'
-        self.im_input = 'unmodified'
-        self.activate_device()
-        self.training_setup(lr, scheduler, scheduler_params, perceptual, device)
-        self.model_name = 'qhan'
+        super().__init__(device=device, model_save_dir=model_save_dir, eval_mode=eval_mode, **kwargs)
+        self.net = QHAN(scale=scale, num_metadata=self.num_metadata, **{k: kwargs[k] for k in _B200_KEYS if k in kwargs})
+        self.finish_setup(lr, scheduler, scheduler_params, perceptual, device)
