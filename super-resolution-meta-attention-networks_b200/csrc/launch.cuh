@@ -13,7 +13,7 @@ namespace dfir {
 // DFIR_PDL is a bit mask: 1 tensor-core convs, 2 CUDA-core kernels of the training step / streamer, 4 weight gradient
 enum : int { PDL_CONV = 1, PDL_SIMT = 2, PDL_WGRAD = 4 };
 inline int pdl_mask() {
-  static const int m = getenv("DFIR_PDL") == nullptr ? PDL_CONV : atoi(getenv("DFIR_PDL"));
+  static const int m = getenv("DFIR_PDL") == nullptr ? (PDL_CONV | PDL_WGRAD) : atoi(getenv("DFIR_PDL"));
   return m;
 }
 

@@ -600,7 +600,7 @@ int scale_residual(const void* r, int r_is_bf16, const float* x_in, const float*
   if (C % 8 != 0 || C > 256 || 256 % C != 0 || ap.A > 512 || ap.M > 448) return DFIR_ERR_ARG;
   const long long nvec = static_cast<long long>(H) * W * (C / 8);
   long long per_img = (nvec + 256 * 8 - 1) / (256 * 8);
-  const long long cap = (296 + B - 1) / B;
+  const long long cap = std::max(1, 296 / std::max(1, B));  // 128 registers -> 2 CTAs per SM: stay within ONE wave of 296
   if (per_img > cap) per_img = cap;
   if (per_img < 1) per_img = 1;
   dim3 grid(static_cast<unsigned>(per_img), B);

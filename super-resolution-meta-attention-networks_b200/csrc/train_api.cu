@@ -680,6 +680,7 @@ int dfir_conv3x3_wgrad_c64(const void* dy, long long dps, long long drs, long lo
   int S_ = 0;
   float* sc = reinterpret_cast<float*>(scratch);
   DFIR_TRY(wgrad_c64(dy, dps, drs, dis, x, sc, B, H, W, std::min(sms, 160), S(stream), &S_));
+  if (getenv("DFIR_WGRAD_PROBE") != nullptr && (atoi(getenv("DFIR_WGRAD_PROBE")) & 8)) return DFIR_OK;  // timing only
   return wgrad_reduce(sc, sc + static_cast<size_t>(S_) * 9 * 64 * 64, S_, 64, 64, nullptr, 0, dw, nullptr, 0, db, co_begin,
                       co_stride, S(stream), wgrad_c64_co_major());
 }

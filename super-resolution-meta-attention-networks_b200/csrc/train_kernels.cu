@@ -789,7 +789,7 @@ int wgrad_reduce(const float* part, const float* dbpart, int S, int Cin, int n_r
                  float* w_direct, float* const* b_tbl, int b_idx, float* b_direct, int co_begin, int co_stride,
                  cudaStream_t s, int co_major) {
   const int total = 9 * Cin * n_rows + n_rows;
-  return launch_pdl(PDL_SIMT, wgrad_reduce_kernel, dim3((total + 63) / 64), dim3(256), 0, s, part, dbpart, S, Cin, n_rows, w_tbl,
+  return launch_pdl(PDL_WGRAD, wgrad_reduce_kernel, dim3((total + 63) / 64), dim3(256), 0, s, part, dbpart, S, Cin, n_rows, w_tbl,
                     w_idx, w_direct, b_tbl, b_idx, b_direct, co_begin, co_stride, co_major) == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
 }
 

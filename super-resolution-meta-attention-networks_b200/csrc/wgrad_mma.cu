@@ -223,7 +223,7 @@ int wgrad_c64_bf16(const void* dy, long long dy_pix, long long dy_row, long long
   a.part = scratch;
   a.dbpart = scratch + static_cast<size_t>(grid) * 9 * 64 * 64;
   a.B = B; a.H = H; a.W = W; a.nseg = (W + 127) / 128;
-  return launch_pdl(PDL_WGRAD, wgrad_c64_mma_kernel, dim3(grid), dim3(kWgThreads), kWgSmem, s, a) == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
+  return launch_pdl(PDL_SIMT, wgrad_c64_mma_kernel, dim3(grid), dim3(kWgThreads), kWgSmem, s, a) == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
 }
 
 }  // namespace dfir

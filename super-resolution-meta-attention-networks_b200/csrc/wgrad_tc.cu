@@ -43,6 +43,7 @@ struct WgradTcArgs {
   float* part;    // [grid][9][64 co][64 ci]
   float* dbpart;  // [grid][64]
   int B, H, W, nseg;
+  int probe;  // DFIR_WGRAD_PROBE (timing experiments, wrong results): 1 no partial stores, 2 no MMAs, 4 no bias sums
 };
 
 // MN-major SWIZZLE_128B shared-memory matrix descriptor
@@ -100,6 +101,9 @@ wgrad_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  // programmatic dependent launch: the set-up above overlaps the predecessor's tail; the partial-sum reduction that
+  // follows may become resident early (this grid is a single wave, so it cannot starve us) and waits for our exit
+  if (threadIdx.x == 0) grid_dep_launch();
   grid_dep_wait();  // dY / X are produced by the preceding kernels
 
   if (g0 < g1) {
@@ -147,7 +151,7 @@ wgrad_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const int ksteps = (npx + 15) >> 4;
         if (leader) {
           const uint32_t dbase = smem_u32(dring + ds * kDSlotB);
-          for (int ks = 0; ks < ksteps; ++ks) {
+          for (int ks = 0; ks < ((a.probe & 2) ? 0 : ksteps); ++ks) {
             const uint64_t bdesc = make_sw128_mnmajor_desc(dbase + ks * 16 * 128, 1024, 1024);
             const uint32_t accum = (it > 0 || ks > 0) ? 1u : 0u;
 #pragma unroll
@@ -181,7 +185,7 @@ wgrad_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           const int seg = (g / H) % nseg;
           const int npx = min(128, a.W - seg * 128);
           const uint8_t* base = dring + ds * kDSlotB;
-          for (int p = pl; p < npx; p += 16) {
+          for (int p = pl; p < ((a.probe & 4) ? 0 : npx); p += 16) {
             const uint4 raw = *reinterpret_cast<const uint4*>(base + p * 128 + ((ch ^ (p & 7)) << 4));
             const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
@@ -210,7 +214,7 @@ wgrad_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       // ci, so every store instruction writes one full 128-byte line
       float* pbase = a.part + static_cast<size_t>(blockIdx.x) * 9 * 64 * 64;
 #pragma unroll 1
-      for (int dy = 0; dy < 3; ++dy) {
+      for (int dy = 0; dy < ((a.probe & 1) ? 0 : 3); ++dy) {
         {  // 128-lane accumulator: lane = dx*64 + ci (dx in {0,1}), column = co
           float* dst = pbase + static_cast<size_t>(dy * 3 + (L >> 6)) * 64 * 64 + (L & 63);
 #pragma unroll
@@ -274,7 +278,8 @@ int wgrad_c64_tc(const void* dy, long long dy_pix, long long dy_row, long long d
   a.part = scratch;
   a.dbpart = scratch + static_cast<size_t>(grid) * 9 * 64 * 64;
   a.B = B; a.H = H; a.W = W; a.nseg = (W + 127) / 128;
-  return launch_pdl(0, wgrad_c64_tc_kernel, dim3(grid), dim3(kWtThreads), kWtSmem, s, tx, td, a) == cudaSuccess
+  a.probe = getenv("DFIR_WGRAD_PROBE") != nullptr ? atoi(getenv("DFIR_WGRAD_PROBE")) : 0;
+  return launch_pdl(PDL_WGRAD, wgrad_c64_tc_kernel, dim3(grid), dim3(kWtThreads), kWtSmem, s, tx, td, a) == cudaSuccess
              ? DFIR_OK
              : DFIR_ERR_CUDA;
 }

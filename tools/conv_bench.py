@@ -152,3 +152,24 @@ if "fwd" in which:
 if "one" in which:  # few launches of selected shapes, for ncu (BC=32 python tools/conv_bench.py one)
     NREP[:] = [4, 2]
     conv_sweep(int(os.environ.get("EPI", "1")))
+
+
+def wgrad_bench():
+    B, H, W = (int(t) for t in os.environ.get("WG", "16,64,64").split(","))
+    x = torch.randn(B, H, W, 64, device=dev).to(torch.bfloat16)
+    dy = torch.randn(B, H, W, 64, device=dev).to(torch.bfloat16)
+    n = lib.dfir_conv3x3_wgrad_scratch_bytes(B, H, W, 64, 64, 0)
+    scratch = torch.empty(n, dtype=torch.uint8, device=dev)
+    dw = torch.empty(64, 64, 3, 3, device=dev); db = torch.empty(64, device=dev)
+
+    def launch():
+        _lib.check(lib.dfir_conv3x3_wgrad_c64(dy.data_ptr(), 0, 0, 0, x.data_ptr(), B, H, W, dw.data_ptr(), db.data_ptr(), 0, 1,
+                                              scratch.data_ptr(), n, st()), "wgrad")
+    us = timeit(launch, 100, 10)
+    fl = B * H * W * 2 * 64 * 64 * 9
+    print("wgrad(+reduce unless probe&8) %dx%dx%d probe=%s: %7.2f us  %6.1f TFLOP/s" %
+          (B, H, W, os.environ.get("DFIR_WGRAD_PROBE", "0"), us, fl / us / 1e6))
+
+
+if "wgrad" in which:
+    wgrad_bench()
