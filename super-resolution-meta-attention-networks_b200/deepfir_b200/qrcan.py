@@ -178,6 +178,9 @@ class QRCAN(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("deepfir_b200.%s runs on a CUDA (sm_100a) device only: there is no CPU path"
                                % type(self).__name__)
+        if x.shape[0] == 0 or x.shape[2] == 0 or x.shape[3] == 0:  # empty batch / image: nothing to launch
+            return x.new_zeros(x.shape[0], self.cfg["out_feats"], x.shape[2] * self.scale, x.shape[3] * self.scale,
+                               dtype=torch.float32)
         from . import ops  # registers torch.ops.dfir.*
         training = torch.is_grad_enabled() and self.head_weight().requires_grad
         packed = self.packed(training=training)

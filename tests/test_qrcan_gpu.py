@@ -310,3 +310,44 @@ def test_rcan_handler_through_the_registry(tmp_path):
     for _ in range(8):
         l1, _ = h.run_train(x, y)
     assert float(l1) < float(l0)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (2, 1, 7), (1, 9, 1), (1, 3, 129), (3, 2, 257)])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_degenerate_and_ragged_image_shapes(shape, precision):
+    """single pixels, single rows / columns (first row == last row in the pool-by-linearity statistics) and widths one
+    pixel past a multiple of the 128-pixel tile, against the oracle"""
+    from deepfir_b200.qrcan import QRCAN
+    torch.manual_seed(11)
+    kw = dict(n_resgroups=1, n_resblocks=2, style="standard", num_metadata=10, include_q_layer=True, scale=2)
+    net = QRCAN(precision=precision, **kw)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    b, h, w = shape
+    g = torch.Generator().manual_seed(12)
+    x = torch.rand(b, 3, h, w, generator=g)
+    meta = torch.rand(b, 10, 1, 1, generator=g) * 0.4
+    with torch.no_grad():
+        want = O.qrcan_forward(x, meta, sd, style="standard")
+        out = net.cuda().eval()(x.cuda(), meta.cuda()).cpu()
+    assert out.shape == want.shape
+    if precision == "fp32":
+        assert max_norm_err(out, want) <= 1e-4
+    else:
+        pol = O.qrcan_forward(x, meta, sd, style="standard", nm=O.Numerics(torch.bfloat16))
+        assert max_norm_err(out, want) <= 2.0 * max_norm_err(pol, want) + 1e-4
+
+
+def test_empty_batch_returns_an_empty_result():
+    from deepfir_b200.qrcan import QRCAN
+    net = QRCAN(n_resgroups=1, n_resblocks=1, style="standard", num_metadata=10, include_q_layer=True, scale=4).cuda().eval()
+    with torch.no_grad():
+        out = net(torch.zeros(0, 3, 8, 8, device="cuda"), torch.zeros(0, 10, 1, 1, device="cuda"))
+    assert out.shape == (0, 3, 32, 32)
+
+
+def test_cpu_tensors_and_missing_library_fail_loudly():
+    """there is no CPU / eager fallback: a CPU tensor raises instead of silently running somewhere else"""
+    from deepfir_b200.qrcan import QRCAN
+    net = QRCAN(n_resgroups=1, n_resblocks=1, style="standard", num_metadata=10, include_q_layer=True, scale=4)
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 3, 8, 8), torch.zeros(1, 10, 1, 1))
