@@ -173,3 +173,26 @@ def wgrad_bench():
 
 if "wgrad" in which:
     wgrad_bench()
+
+
+def skip_direct_bench():
+    """EPI_BIAS_SKIP (epi 3): lane-major epilogue without the shared-memory transposition tile"""
+    wp = torch.empty(9 * 64 * 128, dtype=torch.uint8, device=dev)
+    w = (torch.randn(64, 64, 3, 3, device=dev) / 24).contiguous()
+    bias = torch.zeros(64, device=dev)
+    _lib.check(lib.dfir_pack_conv3x3_bf16(w.data_ptr(), wp.data_ptr(), 64, 64, 64, 0, 1, st()), "pack")
+    for bc in BCS:
+        t = torch.randn(bc, LR, LR, 64, device=dev).to(torch.bfloat16)
+        x = torch.randn(bc, LR, LR, 64, device=dev)
+        xb = torch.empty_like(t)
+
+        def launch():
+            _lib.check(lib.dfir_conv3x3_c64(t.data_ptr(), 64, 0, wp.data_ptr(), bias.data_ptr(), bc, LR, LR, 3, 64,
+                                            xb.data_ptr(), 128, LR * 128, LR * LR * 128, x.data_ptr(), x.data_ptr(), None,
+                                            0, st()), "conv epi3")
+        us = timeit(launch, NREP[0], NREP[1])
+        print("conv+bias_skip (lane-major, no tile) bc=%3d: %8.2f us   %7.1f GB/s (12 B/elem)" % (bc, us, bc * LR * LR * 64 * 12 / us / 1e3))
+
+
+if "skipdirect" in which:
+    skip_direct_bench()
