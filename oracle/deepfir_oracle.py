@@ -344,7 +344,8 @@ def qsan_forward(x: Tensor, meta: Tensor, sd: SD, nm: Numerics = EXACT) -> Tenso
         for b in range(nblocks):
             q = "%s.rcab.%d" % (p, b)
             y = conv3x3(F.relu(conv3x3(flow, sd, q + ".conv_first.0", nm)), sd, q + ".conv_first.2", nm)
-            y = y * para_ca_vector(meta, sd, q + ".q_layer")
+            if _has(sd, q + ".q_layer.attribute_integrator.0.weight"):  # absent in the non-meta SAN (RB, SAN_blocks.py:359-363)
+                y = y * para_ca_vector(meta, sd, q + ".q_layer")
             flow = y + flow
         flow = flow * soca_vector(flow, sd, p + ".soca")
         flow = conv3x3(flow, sd, p + ".conv_last", nm)
@@ -375,14 +376,36 @@ def csam(x: Tensor, sd: SD, prefix: str) -> Tensor:
     return x * out + x
 
 
+def _rcan_group(res: Tensor, sd: SD, gp: str, nm: Numerics) -> Tensor:
+    """ResidualGroup of the non-meta RCAN / HAN (advanced/architectures.py:94-110): RCABs, conv, `+= x`."""
+    nblocks = _count(sd, re.escape(gp) + r"\.body\.(\d+)\.body\.0\.weight$")
+    r = res
+    for b in range(nblocks):
+        p = "%s.body.%d.body" % (gp, b)
+        t = conv3x3(F.relu(conv3x3(r, sd, p + ".0", nm)), sd, p + ".2", nm)
+        y = t.mean(dim=(2, 3), keepdim=True)
+        y = torch.sigmoid(fc(F.relu(fc(y, sd, p + ".3.conv_du.0")), sd, p + ".3.conv_du.2"))
+        r = t * y + r
+    return conv3x3(r, sd, "%s.body.%d" % (gp, nblocks), nm) + res
+
+
+def san_forward(x: Tensor, sd: SD, nm: Numerics = EXACT) -> Tensor:
+    """SAN.forward (advanced/architectures.py:288-311): Q-SAN's data flow without the meta-attention scale."""
+    return qsan_forward(x, None, sd, nm)
+
+
 def qhan_forward(x: Tensor, meta: Tensor, sd: SD, nm: Numerics = EXACT) -> Tensor:
-    """QHAN.forward (attention_manipulators/architectures.py:514-540)."""
-    ngroups = _count(sd, r"body\.(\d+)\.final_body\.weight$")
+    """QHAN.forward (attention_manipulators/architectures.py:514-540); with meta = None the non-meta HAN.forward
+    (advanced/architectures.py:351-377), whose groups carry RCAN's key grammar."""
+    meta_net = any(k.endswith(".final_body.weight") for k in sd)
+    ngroups = _count(sd, r"body\.(\d+)\.final_body\.weight$") if meta_net else \
+        _count(sd, r"body\.(\d+)\.body\.0\.body\.0\.weight$")
     h = conv3x3(x, sd, "head.0", nm)
     res = h
     stack = []
     for g in range(ngroups):
-        res = qresidual_group(res, meta, sd, "body.%d" % g, "standard", nm)
+        res = qresidual_group(res, meta, sd, "body.%d" % g, "standard", nm) if meta_net else \
+            _rcan_group(res, sd, "body.%d" % g, nm)
         stack.insert(0, res)
     res = conv3x3(res, sd, "body.%d" % ngroups, nm)
     stack.insert(0, res)

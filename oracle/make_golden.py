@@ -55,13 +55,16 @@ CASES = {
     # non-meta baselines (advanced/architectures.py): same kernels with the meta scale == 1
     "rcan_g2b2": ("rcan", dict(n_resgroups=2, n_resblocks=2, scale=4), (2, 20, 24), 1),
     "edsr_f64_b3": ("edsr", dict(num_blocks=3, net_features=64, scale=2, res_scale=0.1), (2, 12, 20), 1),
+    "san_g2b2": ("san", dict(n_resgroups=2, n_resblocks=2, scale=4), (2, 16, 12), 1),
+    "han_b1": ("han", dict(n_resgroups=10, n_resblocks=1, scale=4), (1, 8, 8), 1),
 }
 
 
 def build_reference(model, kwargs):
     arch = import_reference_architectures()
     cls = {"qrcan": arch.QRCAN, "qedsr": arch.QEDSR, "qsan": arch.QSAN, "qhan": arch.QHAN,
-           "rcan": arch._ref_advanced.RCAN, "edsr": arch._ref_advanced.EDSR}[model]
+           "rcan": arch._ref_advanced.RCAN, "edsr": arch._ref_advanced.EDSR, "san": arch._ref_advanced.SAN,
+           "han": arch._ref_advanced.HAN}[model]
     torch.manual_seed(8)
     return cls(**kwargs).eval()
 
@@ -74,7 +77,7 @@ def run_case(name):
     net.load_state_dict(sd, strict=True)
     x, meta = synth_inputs(b, h, w, num_metadata=m_attr, seed=8)
     with torch.no_grad():
-        out = net(x) if model in ("rcan", "edsr") else net(x, meta)
+        out = net(x) if model in ("rcan", "edsr", "san", "han") else net(x, meta)
     return shapes, out
 
 

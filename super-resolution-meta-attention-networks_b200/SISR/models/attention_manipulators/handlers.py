@@ -107,7 +107,7 @@ class QSANHandler(QModel):
             for far_c in (0, 1):
                 quad = x[:, :, span(0, far_r), span(1, far_c)]
                 sr = self.run_chopped_eval(quad, extra_channels) if small else \
-                    self.forward_chop(quad, extra_channels, shave=shave)
+                    QSANHandler.forward_chop(self, quad, extra_channels, shave=shave)
                 dst, src = [], []
                 for axis, far in ((0, far_r), (1, far_c)):
                     cut, whole, tile = s * half[axis], s * full[axis], s * size[axis]

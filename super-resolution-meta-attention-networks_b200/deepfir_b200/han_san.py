@@ -277,7 +277,8 @@ class QSAN(_StagedNet):
         blocks = [blk for grp in self.RG for blk in grp.rcab]
         return dict(cfg=self.cfg, head=self.head[0], trunk=trunk,
                     ups=[m for m in self.tail[0] if isinstance(m, nn.Conv2d)], tail=self.tail[1],
-                    ca=[None for _ in blocks], meta=[tuple(blk.q_layer.fcs()) for blk in blocks])
+                    ca=[None for _ in blocks],
+                    meta=[tuple(blk.q_layer.fcs()) if hasattr(blk, "q_layer") else None for blk in blocks])
 
     def _nonlocal(self, x):
         lib = _lib.load_library()

@@ -62,6 +62,10 @@ def oracle_forward(info, sd, x, meta, nm=O.EXACT):
         return O.qhan_forward(x, meta, sd, nm=nm)
     if model == "rcan":
         return O.rcan_forward(x, sd, nm=nm)
+    if model == "san":
+        return O.san_forward(x, sd, nm=nm)
+    if model == "han":
+        return O.qhan_forward(x, None, sd, nm=nm)
     if model == "edsr":
         return O.edsr_forward(x, sd, res_scale=kw.get("res_scale", 0.1), nm=nm)
     raise KeyError(model)

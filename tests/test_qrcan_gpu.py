@@ -12,9 +12,10 @@ QRCAN_CASES = [n for n in golden_names() if n.startswith("qrcan")]  # incl. pixe
 
 def _build(info, precision, **extra):
     from deepfir_b200.han_san import QHAN, QSAN
-    from deepfir_b200.baselines import EDSR, RCAN
+    from deepfir_b200.baselines import EDSR, HAN, RCAN, SAN
     from deepfir_b200.qrcan import QEDSR, QRCAN
-    cls = {"qedsr": QEDSR, "qrcan": QRCAN, "qsan": QSAN, "qhan": QHAN, "rcan": RCAN, "edsr": EDSR}[info["model"]]
+    cls = {"qedsr": QEDSR, "qrcan": QRCAN, "qsan": QSAN, "qhan": QHAN, "rcan": RCAN, "edsr": EDSR, "san": SAN,
+           "han": HAN}[info["model"]]
     net = cls(precision=precision, **extra, **info["kwargs"])
     sd, x, meta = case_tensors(info)
     net.load_state_dict(sd, strict=True)
@@ -278,7 +279,7 @@ def test_net_run_and_process_device_postprocessing_is_bit_identical_to_the_host_
     assert np.array_equal(ycc, want_ycc)
 
 
-@pytest.mark.parametrize("name", ["rcan_g2b2", "edsr_f64_b3"])
+@pytest.mark.parametrize("name", ["rcan_g2b2", "edsr_f64_b3", "san_g2b2", "han_b1"])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_non_meta_baselines_match_reference_golden(name, precision):
     """RCAN / EDSR (advanced/architectures.py) through the Q-net kernels with the meta scale == 1:
@@ -351,3 +352,19 @@ def test_cpu_tensors_and_missing_library_fail_loudly():
     net = QRCAN(n_resgroups=1, n_resblocks=1, style="standard", num_metadata=10, include_q_layer=True, scale=4)
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 3, 8, 8), torch.zeros(1, 10, 1, 1))
+
+
+def test_san_handler_chops_like_the_reference(tmp_path):
+    """`san` through the registry: run_eval always goes through forward_chop (4 overlapping quadrants, shave 10)"""
+    from SISR.models import ModelInterface
+    ref, info = load_golden("san_g2b2")
+    h = ModelInterface.define_model("san", device=0, model_save_dir=str(tmp_path), eval_mode=True, precision="fp32",
+                                    max_combined_im_size=600)
+    x = torch.rand(1, 3, 28, 24, generator=torch.Generator().manual_seed(2))
+    out, _, _ = h.run_eval(x)
+    assert out.shape == (1, 3, 112, 96) and torch.isfinite(out).all()
+    sd = {k: v.detach().cpu() for k, v in h.net.state_dict().items()}
+    hs, ws = 14 + 10, 12 + 10
+    with torch.no_grad():
+        q0 = O.san_forward(x[:, :, :hs, :ws], sd)       # top-left quadrant as the reference would run it
+    assert max_norm_err(out[:, :, :56, :48], q0[:, :, :56, :48]) <= 1e-4
