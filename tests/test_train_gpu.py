@@ -276,3 +276,31 @@ def test_handler_run_train_reduces_the_loss(tmp_path):
         losses.append(float(loss))
     assert all(np.isfinite(losses))
     assert losses[-1] < 0.7 * losses[0], losses
+
+
+def test_training_with_selective_meta_blocks_and_changing_batch_shapes():
+    """q layers only in some groups / blocks (selective_meta_blocks, num_q_layers_inner_residual), and two batch shapes
+    alternating through the per-shape CUDA graphs: gradients against autograd through the oracle each time"""
+    from deepfir_b200.qrcan import QRCAN
+    from oracle import deepfir_oracle as O
+    torch.manual_seed(21)
+    kw = dict(n_resgroups=3, n_resblocks=3, style="max_concat", num_metadata=10, include_q_layer=True, scale=2,
+              selective_meta_blocks=[True, False, True], num_q_layers_inner_residual=2)
+    net = QRCAN(precision="fp32", **kw).cuda().train()
+    sd = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    assert sum(".q_node." in k for k in sd) == 2 * 2 * 4      # q layers in groups 0 and 2, blocks 0 and 1 only
+    g = torch.Generator().manual_seed(22)
+    batches = []
+    for b, h, w in [(2, 10, 12), (3, 8, 8)]:
+        batches.append((torch.rand(b, 3, h, w, generator=g), torch.rand(b, 10, 1, 1, generator=g) * 0.4,
+                        torch.rand(b, 3, 2 * h, 2 * w, generator=g)))
+    for rep in range(3):                                      # eager, graph capture, graph replay
+        for x, meta, y in batches:
+            leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+            F.l1_loss(O.qrcan_forward(x, meta, leaves, style="max_concat"), y).backward()
+            net.zero_grad(set_to_none=True)
+            F.l1_loss(net(x.cuda(), meta.cuda()), y.cuda()).backward()
+            gmax = max(float(v.grad.norm()) for v in leaves.values())
+            for k, p in net.named_parameters():
+                err = float((p.grad.cpu().double() - leaves[k].grad.double()).norm())
+                assert err <= 1e-3 * float(leaves[k].grad.norm()) + 1e-6 * gmax, (rep, k, err)
