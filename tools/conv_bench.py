@@ -196,3 +196,30 @@ def skip_direct_bench():
 
 if "skipdirect" in which:
     skip_direct_bench()
+
+
+def ss_stats_bench():
+    """RCAB conv2 as the default schedule launches it: attention vector evaluated in the kernel from conv1's statistics"""
+    wp = torch.empty(9 * 64 * 128, dtype=torch.uint8, device=dev)
+    w = (torch.randn(64, 64, 3, 3, device=dev) / 24).contiguous()
+    bias = torch.zeros(64, device=dev)
+    _lib.check(lib.dfir_pack_conv3x3_bf16(w.data_ptr(), wp.data_ptr(), 64, 64, 64, 0, 1, st()), "pack")
+    blob = torch.randn(4 * 64 + 4 + 64 * 4 + 64, device=dev) / 8
+    for bc in BCS:
+        t = torch.randn(bc, LR, LR, 64, device=dev).to(torch.bfloat16)
+        x = torch.randn(bc, LR, LR, 64, device=dev)
+        xb = torch.empty_like(t)
+        pool = torch.randn(bc, LR, 64, device=dev); cf = torch.randn(bc, LR, 64, device=dev); cl = torch.randn(bc, LR, 64, device=dev)
+        attr = torch.rand(bc, 10, device=dev); sq = torch.rand(bc, 64, device=dev)
+
+        def launch():
+            _lib.check(lib.dfir_conv3x3_c64_scale_skip(t.data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR, None,
+                                                       x.data_ptr(), x.data_ptr(), xb.data_ptr(), pool.data_ptr(),
+                                                       cf.data_ptr(), cl.data_ptr(), 1, blob.data_ptr(), 4, 10, 10,
+                                                       attr.data_ptr(), sq.data_ptr(), st()), "ss stats")
+        us = timeit(launch, NREP[0], NREP[1])
+        print("conv+scale_skip WITH in-kernel attention bc=%3d: %8.2f us" % (bc, us))
+
+
+if "ssstats" in which:
+    ss_stats_bench()
