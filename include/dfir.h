@@ -221,7 +221,8 @@ typedef struct dfir_qrcan_net {
   const int* q_enabled;             /* device int32 [n_groups*n_blocks]: block owns a q_node */
   int any_q;                        /* host-side: any block has a q_node */
   int chunk_images;                 /* images per L2-resident pass; 0 = choose automatically */
-  int schedule;                     /* block chain: 0 pool-by-linearity (default), 1 fused-in, 2 streamer */
+  int schedule;                     /* block chain: 0 pool-by-linearity (default), 1 fused-in, 2 streamer, 3 pool-by-linearity with
+                                       the attention vector from its own kernel */
   int no_group_conv;                /* 1: groups have no tail conv / group skip (Q-EDSR: one flat chain of blocks) */
   int meta_relu;                    /* ReLU between the two FC layers of the meta-attention MLP (q_layer.py:33-34) */
   float res_scale;                  /* ParamResBlock res_scale (style NONE only; QRCAB ignores it) */

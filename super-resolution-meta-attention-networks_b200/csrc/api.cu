@@ -174,7 +174,7 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
       const int blk = g * nb + b;
       const float* sq = n->any_q ? w.sq + (static_cast<size_t>(blk) * B + b0) * C : nullptr;
       // conv1: t = relu(conv(x_b))
-      ConvTcDesc c1 = base(g * per_group + 2 * b, (sched == 0 && has_ca) ? EPI_RELU_STATS : EPI_BIAS_RELU);
+      ConvTcDesc c1 = base(g * per_group + 2 * b, ((sched == 0 || sched == 3) && has_ca) ? EPI_RELU_STATS : EPI_BIAS_RELU);
       c1.out_bf16 = w.T; c1.col_first = w.colf; c1.col_last = w.coll;
       if (b == 0) {
         c1.in_bf16 = gin;
@@ -186,13 +186,18 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
         c1.in_bf16 = w.XBbf;
       }
       DFIR_TRY(conv3x3_c64_tc(c1, st));
-      if (sched == 0) {
+      if (sched == 0 || sched == 3) {
         const int w2 = g * per_group + 2 * b + 1;
         // conv2 + attention scale + residual: x_{b+1} = (conv(t) + b) * s + x_b (fp32, in place after block 0);
         // s is evaluated from the statistics of t inside the kernel while its pipeline fills.
         ConvTcDesc c2 = base(w2, EPI_SCALE_SKIP);
         c2.in_bf16 = w.T; c2.skip_f32 = b == 0 ? skip32 : w.XB; c2.out_f32 = w.XB; c2.out_bf16 = w.XBbf;
-        if (has_ca) {
+        if (has_ca && sched == 3) {
+          // schedule 3: the attention vector comes from its own small kernel instead of conv2's prologue
+          DFIR_TRY(ca_from_stats(w.pool, w.colf, w.coll, cw + static_cast<size_t>(w2) * wbytes, n->conv_b + static_cast<size_t>(w2) * 64,
+                                 make_ap(n, blk), attr_c, sq, w.svec, Bc, H, W, st));
+          c2.svec = w.svec;
+        } else if (has_ca) {
           c2.col_first = w.colf; c2.col_last = w.coll; c2.epi_stats = 1;
           c2.ca_style = n->style; c2.ca_R = n->reduced; c2.ca_M = n->num_metadata; c2.ca_A = n->attr_size;
           c2.ca_params = n->ca_blob + static_cast<size_t>(blk) * n->ca_stride; c2.attributes = attr_c; c2.sq = sq;
@@ -585,7 +590,7 @@ long long dfir_qrcan_launch_count(const dfir_qrcan_net* net, int B, int H, int W
   const long long nb = net->n_blocks, ng = net->n_groups;
   long long per_chunk;
   if (precision == DFIR_PREC_BF16_TC) {
-    per_chunk = 1 + ng * (nb * ((net->schedule == 2 || net->pa_blob != nullptr) ? 3 : 2) + (net->no_group_conv ? 0 : 1)) + 1 +
+    per_chunk = 1 + ng * (nb * ((net->schedule == 2 || (net->schedule == 3 && net->style != DFIR_STYLE_NONE) || net->pa_blob != nullptr) ? 3 : 2) + (net->no_group_conv ? 0 : 1)) + 1 +
                 static_cast<long long>(nup) * r * r + 1;
   } else {
     const long long pool = net->style != DFIR_STYLE_NONE ? 1 : 0;

@@ -20,7 +20,7 @@ from ._lib import QrcanNet
 STYLES = {"none": 0, "standard": 1, "modulate": 2, "max_concat": 3, "softmax": 4, "mini_concat": 5, "extended_attention": 6}
 PRECISIONS = {"bf16": 0, "fp32": 1}
 # block-chain schedules of the bf16 path (csrc/api.cu): pool-by-linearity, fused-in, streamer
-SCHEDULES = {"linear": 0, "fused": 1, "streamer": 2}
+SCHEDULES = {"linear": 0, "fused": 1, "streamer": 2, "linear3": 3}
 
 
 def _conv3(cin, cout):
