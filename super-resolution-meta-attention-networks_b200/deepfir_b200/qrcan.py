@@ -305,7 +305,13 @@ class QEDSR(QRCAN):
         if not x.is_cuda:
             raise RuntimeError("deepfir_b200.QEDSR runs on a CUDA (sm_100a) device only: there is no CPU path")
         if torch.is_grad_enabled() and self.head.weight.requires_grad:
-            raise NotImplementedError("training wide Q-EDSR on the tensor cores is not implemented; use precision='fp32'")
+            # the tensor-core training kernels are specialised for 64 features: a training step of a wide net runs the
+            # library's fp32 CUDA-core kernels (same schedule, any width); inference stays on the tensor cores
+            self.precision = "fp32"
+            try:
+                return super().forward(x, metadata)
+            finally:
+                self.precision = "bf16"
         from .wide import WideQEDSR
         params = self.__dict__.get("_plist")
         if params is None:

@@ -304,3 +304,27 @@ def test_training_with_selective_meta_blocks_and_changing_batch_shapes():
             for k, p in net.named_parameters():
                 err = float((p.grad.cpu().double() - leaves[k].grad.double()).norm())
                 assert err <= 1e-3 * float(leaves[k].grad.norm()) + 1e-6 * gmax, (rep, k, err)
+
+
+def test_wide_qedsr_trains_on_the_fp32_kernels_and_infers_on_the_tensor_cores(tmp_path):
+    """a 128-feature Q-EDSR built with the default precision: run_train uses the library's fp32 kernels (the tensor-core
+    training kernels are 64-feature), run_eval the 64-channel-plane tensor-core path; the loss goes down and the two
+    paths see the same (updated) weights"""
+    from SISR.models import ModelInterface
+    from oracle import deepfir_oracle as O
+    torch.manual_seed(8)
+    h = ModelInterface.define_model("qedsr", device=0, model_save_dir=str(tmp_path), eval_mode=False, lr=1e-3,
+                                    metadata=["blur_kernel"], num_features=128, num_blocks=2, scale=2)
+    assert h.net.precision == "bf16"
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(2, 3, 16, 16, generator=g)
+    y = F.interpolate(x, scale_factor=2, mode="bicubic", align_corners=False).clamp(0, 1)
+    meta = torch.rand(2, 10, generator=g, dtype=torch.float64) * 0.4
+    keys = [("blur_kernel",) * 2] * 10
+    losses = [float(h.run_train(x, y, metadata=meta, metadata_keys=keys)[0]) for _ in range(8)]
+    assert losses[-1] < losses[0]
+    out = h.run_eval(x, metadata=meta, metadata_keys=keys)[0]
+    sd = {k: v.detach().cpu() for k, v in h.net.state_dict().items()}
+    with torch.no_grad():
+        want = O.qedsr_forward(x, meta.float().reshape(2, 10, 1, 1), sd, res_scale=0.1)
+    assert float((out - want).abs().max() / want.abs().max()) <= 3e-2
