@@ -328,6 +328,12 @@ int dfir_qrcan_train_backward(const dfir_qrcan_net* net, const dfir_qrcan_params
 /* kernel launches of one forward + backward (bench.py's gpu_launches claim for the training step) */
 long long dfir_qrcan_train_launch_count(const dfir_qrcan_net* net, int B, int H, int W, int precision);
 
+/* Adam.step() (BaseModel.standard_update, models/__init__.py:481-489; optimizer defined at :291-299) over flat fp32
+ * buffers: n parameters (n % 4 == 0, 16-byte aligned), torch.optim.Adam arithmetic (L2 weight decay added to the
+ * gradient, bias corrections from `step` >= 1), one pass: 16 B read + 12 B written per parameter. */
+int dfir_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, long long step, void* stream);
+
 /* single operators of the backward, exercised one by one by tests/test_train_gpu.py */
 
 /* Weight + bias gradient of a 64 -> 64 3x3 conv on the tensor cores.  dy: bf16 NHWC with explicit byte strides

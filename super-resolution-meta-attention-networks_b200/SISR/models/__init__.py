@@ -259,12 +259,16 @@ class BaseModel(nn.Module):
         params = [p for p in self.net.parameters() if p.requires_grad]
         # same Adam as the reference (:291-299); on CUDA parameters the single-kernel ("fused") implementation is
         # selected: the default per-tensor loop costs ~10 ms per step over Q-RCAN's 1648 parameter tensors
-        extra = dict(fused=True) if params and all(p.is_cuda for p in params) else {}
-        if optimizer_params is not None:
-            self.optimizer = optim.Adam(params, lr=lr, betas=(optimizer_params['beta_1'], optimizer_params['beta_2']),
-                                        **extra)
+        # same Adam as the reference (:291-299).  On CUDA parameters: `FlatAdam`, a torch.optim.Adam subclass whose step is
+        # one kernel over flat buffers (the per-tensor implementations cost 2-10 ms per step over Q-RCAN's 1648 tensors)
+        if params and all(p.is_cuda for p in params):
+            from deepfir_b200.flat_adam import FlatAdam as adam_cls
         else:
-            self.optimizer = optim.Adam(params, lr=lr, **extra)
+            adam_cls = optim.Adam
+        if optimizer_params is not None:
+            self.optimizer = adam_cls(params, lr=lr, betas=(optimizer_params['beta_1'], optimizer_params['beta_2']))
+        else:
+            self.optimizer = adam_cls(params, lr=lr)
 
     def define_scheduler(self, scheduler, scheduler_params):
         sched = optim.lr_scheduler

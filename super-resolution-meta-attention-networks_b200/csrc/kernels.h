@@ -148,6 +148,8 @@ int form_dr(const float* g, const float* svec, const float* dyv, void* dr, int d
             cudaStream_t s);
 int add_f32(const float* a, const float* b, float* out, void* out_bf16, long long n, cudaStream_t s);
 int pixel_unshuffle_f32(const float* in, float* out, int B, int h, int w, int C, int r, cudaStream_t s);
+int adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,
+              long long step, cudaStream_t s);
 int wgrad_f32_chunks(int B, int H, int Cin, int Cout);
 size_t wgrad_scratch_floats(int S, int Cin, int Cout);
 int wgrad_f32(const float* dY, const float* X, float* scratch, int B, int H, int W, int Cin, int Cout, cudaStream_t s,

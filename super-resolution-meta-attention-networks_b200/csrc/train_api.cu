@@ -722,6 +722,12 @@ int dfir_pack_conv3x3_bf16_ex(const float* w, void* out, int cout, int nt_rows, 
   return pack_bf16_multi(nullptr, w, out, 1, cout, nt_rows, co_stride, transpose, S(stream), co_begin);
 }
 
+int dfir_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, long long step, void* stream) {
+  if (params == nullptr || grads == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr) return DFIR_ERR_ARG;
+  return adam_flat(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, S(stream));
+}
+
 size_t dfir_conv3x3_wgrad_small_scratch_bytes(int B, int H, int C) { return wgrad_small_scratch_floats(B, H, C) * 4; }
 
 int dfir_conv3x3_wgrad_small(const float* img, const void* feat, int feat_is_bf16, int B, int H, int W, int C, int C3,

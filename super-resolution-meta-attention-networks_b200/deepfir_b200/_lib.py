@@ -103,6 +103,7 @@ PROTOTYPES = {
     "dfir_qrcan_train_backward": (_i, [C.POINTER(QrcanNet), C.POINTER(QrcanParams), _vp, _vp, _vp, _i, _i, _i, _i, _vp,
                                        _sz, _vp]),
     "dfir_qrcan_train_launch_count": (C.c_longlong, [C.POINTER(QrcanNet), _i, _i, _i, _i]),
+    "dfir_adam_step": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _ll, _vp]),
     "dfir_conv3x3_wgrad_scratch_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "dfir_conv3x3_wgrad_c64": (_i, [_vp, _ll, _ll, _ll, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "dfir_conv3x3_wgrad_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -328,3 +328,49 @@ def test_wide_qedsr_trains_on_the_fp32_kernels_and_infers_on_the_tensor_cores(tm
     with torch.no_grad():
         want = O.qedsr_forward(x, meta.float().reshape(2, 10, 1, 1), sd, res_scale=0.1)
     assert float((out - want).abs().max() / want.abs().max()) <= 3e-2
+
+
+def test_flat_adam_matches_torch_adam_and_checkpoints_like_it(tmp_path):
+    """FlatAdam (one kernel over flat buffers) against torch.optim.Adam on the same network, data and steps; the
+    optimizer state_dict keeps torch's layout and survives a save / load into a fresh handler"""
+    from deepfir_b200.flat_adam import FlatAdam
+    from deepfir_b200.qrcan import QRCAN
+    kw = dict(n_resgroups=1, n_resblocks=2, style="standard", num_metadata=10, include_q_layer=True, scale=2)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(2, 3, 12, 12, generator=g).cuda(); y = torch.rand(2, 3, 24, 24, generator=g).cuda()
+    meta = (torch.rand(2, 10, 1, 1, generator=g) * 0.4).cuda()
+    nets, opts = [], []
+    for cls in (torch.optim.Adam, FlatAdam):
+        torch.manual_seed(9)
+        net = QRCAN(precision="fp32", **kw).cuda().train()
+        nets.append(net)
+        opts.append(cls(net.parameters(), lr=1e-3, betas=(0.9, 0.99)))
+
+    def step(net, opt):
+        opt.zero_grad()
+        F.l1_loss(net(x, meta), y).backward()
+        opt.step()
+
+    for _ in range(4):
+        for net, opt in zip(nets, opts):
+            step(net, opt)
+    for (k, a), (_, b) in zip(nets[0].named_parameters(), nets[1].named_parameters()):
+        assert float((a - b).detach().abs().max()) <= 2e-6 + 1e-5 * float(a.detach().abs().max()), k
+    # inference after the flat steps sees the updated weights
+    with torch.no_grad():
+        nets[0].eval(); nets[1].eval()
+        assert float((nets[0](x, meta) - nets[1](x, meta)).abs().max()) <= 1e-4
+        nets[0].train(); nets[1].train()
+    # checkpoint: torch's state_dict layout, interchangeable between the two optimizers
+    sd_flat, sd_ref = opts[1].state_dict(), opts[0].state_dict()
+    assert set(sd_flat["state"][0]) == set(sd_ref["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+    assert float(sd_flat["state"][0]["step"]) == float(sd_ref["state"][0]["step"]) == 4.0
+    torch.save(sd_flat, tmp_path / "opt.pt")
+    torch.manual_seed(9)
+    net3 = QRCAN(precision="fp32", **kw).cuda().train()
+    net3.load_state_dict(nets[1].state_dict())
+    opt3 = FlatAdam(net3.parameters(), lr=1e-3, betas=(0.9, 0.99))
+    opt3.load_state_dict(torch.load(tmp_path / "opt.pt"))
+    step(net3, opt3); step(nets[0], opts[0])
+    for (k, a), (_, b) in zip(nets[0].named_parameters(), net3.named_parameters()):
+        assert float((a - b).detach().abs().max()) <= 3e-6 + 1e-5 * float(a.detach().abs().max()), k
