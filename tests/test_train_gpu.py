@@ -374,3 +374,29 @@ def test_flat_adam_matches_torch_adam_and_checkpoints_like_it(tmp_path):
     step(net3, opt3); step(nets[0], opts[0])
     for (k, a), (_, b) in zip(nets[0].named_parameters(), net3.named_parameters()):
         assert float((a - b).detach().abs().max()) <= 3e-6 + 1e-5 * float(a.detach().abs().max()), k
+
+
+def test_full_depth_bf16_gradients_stay_aligned_with_the_reference():
+    """the published depth (10 groups x 20 RCABs): bf16 operands through 400+ layers forward and backward.  The gradient
+    of every parameter tensor must point where the fp32 reference gradient points (cosine) and have its size; the fp32
+    mode stays within the 1e-3 bar at this depth too."""
+    _, info = load_golden("qrcan_standard_full")
+    ref_loss, _, y, ref = None, None, None, None
+    for precision, cos_min, rel_max in (("fp32", 0.999999, 1e-3), ("bf16", 0.999, 5e-2)):
+        net, sd, x, meta = _build(info, precision)
+        if ref is None:
+            ref_loss, _, y, ref = oracle_grads(info, sd, x, meta)
+        loss, _, grads = _step_grads(net, x, meta, y)
+        assert abs(loss - ref_loss) <= (1e-5 if precision == "fp32" else 2e-3) * abs(ref_loss)
+        gmax = max(float(v.norm()) for v in ref.values())
+        worst_cos, worst_rel = 1.0, 0.0
+        for k, g in grads.items():
+            r = ref[k].double().reshape(-1)
+            gd = g.double().reshape(-1)
+            if float(r.norm()) < 1e-3 * gmax:
+                continue  # near-zero gradients (biases deep in the trunk) carry no direction worth comparing
+            cos = float(torch.dot(gd, r) / (gd.norm() * r.norm()))
+            rel = float((gd - r).norm() / r.norm())
+            worst_cos, worst_rel = min(worst_cos, cos), max(worst_rel, rel)
+        print("%s full depth: worst cosine %.6f, worst relative error %.3e" % (precision, worst_cos, worst_rel))
+        assert worst_cos >= cos_min and worst_rel <= rel_max, (precision, worst_cos, worst_rel)
