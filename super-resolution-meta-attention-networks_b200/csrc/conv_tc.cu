@@ -23,6 +23,17 @@
 //
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + tcgen05.mma issuer, warps 2-5 = epilogue
 // (TMEM -> registers -> fused bias/ReLU/skip/pool -> swizzled smem -> TMA store), warps 6-9 = A loaders.
+// EPI_SCALE_SKIP (the fp32 residual-stream epilogue: scale, skip add, fp32 + bf16 stores; also the fp32-accumulating
+// data-gradient conv of the backward pass) adds a second epilogue group, warps 10-13: the two groups drain alternate
+// accumulators, each in two 32-channel halves through a 16 KB fp32 transposition tile and a 16 KB cp.async skip buffer.
+//
+// The kernel is launched with the programmatic-dependent-launch attribute: after its set-up it lets the next kernel of
+// the stream become resident as CTAs retire (griddepcontrol.launch_dependents) and waits for its own predecessor
+// (griddepcontrol.wait) before touching anything that predecessor wrote; the weight load precedes the wait.
+//
+// Backward-pass use (csrc/train_api.cu): the data gradient of a conv is this kernel on the transposed, 180-degree
+// rotated weights — with EPI_RELU_MASK (times the saved ReLU mask) or EPI_SCALE_SKIP (fp32 accumulate); strided TMA
+// input views address one PixelShuffle phase of an output gradient.
 //
 // Input modes
 //   IN_TMA   : the input rows are bf16 NHWC in HBM/L2 and arrive by TMA (320 threads).
