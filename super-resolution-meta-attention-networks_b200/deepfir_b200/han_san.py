@@ -69,6 +69,40 @@ class _StagedNet(nn.Module):
             self._side[name] = w
         return w
 
+    def _conv(self, name, conv, x, skip=None):
+        """3x3 conv of an fp32 NHWC tensor outside the staged trunk (group / fusion convs of Q-SAN and Q-HAN).  bf16 mode
+        with 64 output channels and Cin a multiple of 64: the tensor-core kernel, one launch per 64-channel input chunk
+        with the fp32 running sum chained through its skip input (`dfir_conv3x3_c64_accumulate`); else CUDA cores."""
+        Cin = x.shape[-1]
+        if self.precision != "bf16" or conv.out_channels != 64 or Cin % 64 != 0:
+            return self._conv_f32(name, conv, x, skip=skip)
+        lib = _lib.load_library()
+        B, H, W, _ = x.shape
+        nc = Cin // 64
+        tiles = self._side.get(("tc", name))
+        if tiles is None:
+            tiles = []
+            wt = conv.weight.detach().float()
+            for i in range(nc):
+                wi = wt[:, i * 64:(i + 1) * 64].contiguous()
+                t = torch.empty(9 * 64 * 128, device=wt.device, dtype=torch.uint8)
+                _lib.check(lib.dfir_pack_conv3x3_bf16(wi.data_ptr(), t.data_ptr(), 64, 64, 64, 0, 1, _stream(wt.device)),
+                           "pack %s" % (name,))
+                tiles.append(t)
+            tiles.append(conv.bias.detach().float().contiguous())
+            self._side[("tc", name)] = tiles
+        out = torch.empty(B, H, W, 64, device=x.device, dtype=torch.float32)
+        junk = torch.empty(B, H, W, 64, device=x.device, dtype=torch.bfloat16)
+        xb = x.to(torch.bfloat16)
+        for i in range(nc):
+            chunk = xb if nc == 1 else xb[..., i * 64:(i + 1) * 64].contiguous()
+            prev = skip if i == 0 else out
+            _lib.check(lib.dfir_conv3x3_c64_accumulate(chunk.data_ptr(), tiles[i].data_ptr(),
+                                                       tiles[nc].data_ptr() if i == nc - 1 else None, B, H, W, None,
+                                                       prev.data_ptr() if prev is not None else None, out.data_ptr(),
+                                                       junk.data_ptr(), 0, _stream(x.device)), "conv %s" % (name,))
+        return out
+
     def _conv_f32(self, name, conv, x, skip=None):
         lib = _lib.load_library()
         B, H, W, Cin = x.shape
@@ -172,19 +206,19 @@ class QHAN(_StagedNet):
             self._stages(pk, 1, 0, 0, B, H, W, x=x, feat_out=head)
             stack = torch.empty(ng + 1, B, H, W, Cf, **f32)  # [g] = output of group g, [ng] = body.<ng> conv output
             self._stages(pk, 2, 0, ng, B, H, W, attr=attr, group_out=stack)
-            stack[ng] = self._conv_f32("body_tail", self.body[ng], stack[ng - 1])
+            stack[ng] = self._conv("body_tail", self.body[ng], stack[ng - 1])
             # LAM over the maps in the reference's order (newest first): map n = stack[ng - n]
             la = torch.empty(B, H, W, (ng + 1) * Cf, **f32)
             scratch = torch.empty(int(lib.dfir_lam_scratch_bytes(B, ng + 1)), device=dev, dtype=torch.uint8)
             per_map = B * H * W * Cf
             _lib.check(lib.dfir_lam(stack[ng].data_ptr(), -per_map, float(self.la.gamma), la.data_ptr(),
                                     scratch.data_ptr(), ng + 1, B, H * W, Cf, _stream(dev)), "lam")
-            out2 = self._conv_f32("last_conv", self.last_conv, la)
+            out2 = self._conv("last_conv", self.last_conv, la)
             out1 = torch.empty(B, H, W, Cf, **f32)
             _lib.check(lib.dfir_csam(stack[ng].data_ptr(), self.csa.conv.weight.detach().reshape(-1).data_ptr(),
                                      float(self.csa.conv.bias), float(self.csa.gamma), out1.data_ptr(), B, H, W, Cf,
                                      _stream(dev)), "csam")
-            res = self._conv_f32("last", self.last, torch.cat([out1, out2], dim=-1), skip=head)
+            res = self._conv("last", self.last, torch.cat([out1, out2], dim=-1), skip=head)
             out = torch.empty(B, self.cfg["out_feats"], H * self.scale, W * self.scale, **f32)
             self._stages(pk, 8, 0, 0, B, H, W, feat_in=res, out=out)
         return out
@@ -327,7 +361,7 @@ class QSAN(_StagedNet):
                 _lib.check(lib.dfir_soca(flow.data_ptr(), mlp.data_ptr(), grp.soca.conv_du[0].out_channels,
                                          svec.data_ptr(), soca_scratch.data_ptr(), B, H, W, Cf, _stream(dev)), "soca")
                 y = self._scale_add(flow, svec=svec)
-                f = self._conv_f32(("conv_last", g), grp.conv_last, y, skip=xx)   # + group input
+                f = self._conv(("conv_last", g), grp.conv_last, y, skip=xx)       # + group input
                 xx = self._scale_add(f, add=residual, alpha=gamma)                  # + gamma * share-source skip
             res = self._scale_add(self._nonlocal(xx), add=head, alpha=1.0)
             out = torch.empty(B, self.cfg["out_feats"], H * self.scale, W * self.scale, **f32)
