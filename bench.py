@@ -45,54 +45,88 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.
 
-    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    nvidia-smi needs 0.1-0.3 s before its first line, longer than a short timed region, so the sampler is started
+    ahead of the warm-up steps and only the lines whose timestamp falls inside [mark_begin, mark_end] are used."""
+
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
         self.proc = None
         self.path = None
+        self.t0 = self.t1 = None
+        self.t1_fallback = None
 
     def start(self):
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
+    def mark_fallback_end(self):
+        self.t1_fallback = time.time()
+
+    @staticmethod
+    def _stamp(text):
+        import datetime
+        return datetime.datetime.strptime(text, "%Y/%m/%d %H:%M:%S.%f").timestamp()
+
     def stop(self):
         if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.15)
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"], samples=0)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         with open(self.path) as fh:
             for line in fh:
                 parts = [t.strip() for t in line.split(",")]
-                if len(parts) < 6:
+                if len(parts) < 7:
                     continue
                 try:
-                    sm.append(float(parts[0]))
-                    mx = float(parts[1])
+                    rows.append((self._stamp(parts[0]), float(parts[1]), float(parts[2]), parts[3:7]))
                 except ValueError:
                     continue
-                for n, v in zip(names, parts[2:6]):
+        os.unlink(self.path)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+        def summarise(lo, hi, window):
+            sel = [r for r in rows if lo <= r[0] <= hi]
+            if not sel:
+                return None
+            sm = sorted(r[1] for r in sel)
+            reasons = set()
+            for r in sel:
+                for n, v in zip(names, r[3]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
-        os.unlink(self.path)
-        sm.sort()
-        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons),
-                    samples=len(sm))
+            return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=sel[-1][2], reasons=sorted(reasons), samples=len(sm),
+                        window=window)
+
+        out = None
+        if self.t0 is not None and self.t1 is not None:
+            out = summarise(self.t0, self.t1, "device-timed steps")
+            if out is None and self.t1_fallback is not None:
+                out = summarise(self.t0, self.t1_fallback, "device-timed steps + end-to-end steps (same load)")
+        if out is None:
+            out = dict(sm_mhz=None, sm_max_mhz=None, reasons=["no nvidia-smi sample inside the timed region"], samples=0)
+        return out
 
 
 def build_net(device):
@@ -264,14 +298,15 @@ def run_ours(args):
         out, _, _ = handler.run_eval(x_pin, metadata=meta, metadata_keys=keys)  # H2D + forward + D2H
         return out
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         out = step_device()
     torch.cuda.synchronize()
 
     # ---------------- device-resident timing: K steps, L2 flushed between steps (flush not timed)
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     evs = []
     wall0 = time.perf_counter()
     for _ in range(args.steps):
@@ -283,7 +318,7 @@ def run_ours(args):
         evs.append((e0, e1))
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
+    sampler.mark_end()
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
 
     # ---------------- end to end through the handler API with host buffers
@@ -295,6 +330,8 @@ def run_ours(args):
         out_host = step_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
+    sampler.mark_fallback_end()
+    clocks = sampler.stop()
 
     d2h_bytes = out_host.numel() * 4
     t = torch.tensor([dev_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)

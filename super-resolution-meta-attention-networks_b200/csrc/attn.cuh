@@ -83,14 +83,42 @@ template <class G>
 __device__ void fc_layer(const G& g, const float* __restrict__ w, const float* __restrict__ bias, const float* in_a,
                          int na, const float* in_b, int nb, float* out, int nout,
                          int act /*0 none, 1 relu, 2 sigmoid*/) {
-  for (int o = g.tid(); o < nout; o += g.size()) {
-    const float* wr = w + static_cast<size_t>(o) * (na + nb);
-    float s = bias[o];
-    for (int i = 0; i < na; ++i) s = fmaf(wr[i], in_a[i], s);
-    for (int i = 0; i < nb; ++i) s = fmaf(wr[na + i], in_b[i], s);
-    if (act == 1) s = fmaxf(s, 0.f);
-    if (act == 2) s = 1.f / (1.f + expf(-s));
-    out[o] = s;
+  const int nin = na + nb;
+  if (nin >= 32 && (g.size() & 31) == 0) {
+    // Squeeze layers (many inputs, few outputs): one thread per output would leave most of the group idle behind a
+    // chain of nin dependent loads.  Eight lanes share an output (inputs interleaved by 8, butterfly over the lanes);
+    // the summation order depends on the layer shape only, so every kernel that evaluates the layer gets the same bits.
+    const int sub = g.tid() & 7, per_pass = g.size() >> 3;
+    for (int o0 = 0; o0 < nout; o0 += per_pass) {
+      const int o = o0 + (g.tid() >> 3);
+      float s = 0.f;
+      if (o < nout) {
+        const float* wr = w + static_cast<size_t>(o) * nin;
+#pragma unroll 4
+        for (int i = sub; i < na; i += 8) s = fmaf(wr[i], in_a[i], s);
+#pragma unroll 4
+        for (int i = sub; i < nb; i += 8) s = fmaf(wr[na + i], in_b[i], s);
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      if (o < nout && sub == 0) {
+        s += bias[o];
+        if (act == 1) s = fmaxf(s, 0.f);
+        if (act == 2) s = 1.f / (1.f + expf(-s));
+        out[o] = s;
+      }
+    }
+  } else {
+    for (int o = g.tid(); o < nout; o += g.size()) {
+      const float* wr = w + static_cast<size_t>(o) * nin;
+      float s = bias[o];
+      for (int i = 0; i < na; ++i) s = fmaf(wr[i], in_a[i], s);
+      for (int i = 0; i < nb; ++i) s = fmaf(wr[na + i], in_b[i], s);
+      if (act == 1) s = fmaxf(s, 0.f);
+      if (act == 2) s = 1.f / (1.f + expf(-s));
+      out[o] = s;
+    }
   }
   g.sync();
 }

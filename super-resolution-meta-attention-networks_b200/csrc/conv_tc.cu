@@ -76,6 +76,8 @@ constexpr int kThreads = 320;                // IN_TMA: producer, MMA, 4 epilogu
 constexpr int kThreadsFused = 320 + 256;     // + two transform groups of 4 warps
 constexpr int kThreadsTwoEpi = 320 + 128;    // EPI_SCALE_SKIP (IN_TMA): + a second epilogue group (warps 10-13)
 constexpr int kMaxBandImages = 8;            // a CTA's row band may touch at most this many images (IN_FUSED)
+constexpr int kAttnScratchFloats = 64 + 64 + 512 + 1024 + 4;  // attention scratch of one epilogue group
+constexpr int kCaStageFloats = 704;          // QCALayer parameter blobs up to this size are staged in shared memory
 
 template <int NT>
 struct SmemLayout {
@@ -86,9 +88,10 @@ struct SmemLayout {
   static constexpr int off_skip = off_stage + 2 * kStageBytes;   // EPI_SCALE_SKIP: fp32 skip row (cp.async target)
   static constexpr int off_bias = off_skip + 128 * 64 * 4;
   static constexpr int off_pool = off_bias + 64 * 4;
-  static constexpr int off_attn = off_pool + 8 * 64 * 4;                         // y[64] s[64] attr[512] tmp[1024]
-  static constexpr int off_svec = off_attn + (64 + 64 + 512 + 1024 + 4) * 4;     // s of the images of this band
-  static constexpr int off_bars = off_svec + kMaxBandImages * 64 * 4;
+  static constexpr int off_attn = off_pool + 8 * 64 * 4;                         // per epilogue group: y[64] s[64] attr[512] tmp[1024]
+  static constexpr int off_svec = off_attn + 2 * kAttnScratchFloats * 4;         // s of the images of this band
+  static constexpr int off_cap = off_svec + kMaxBandImages * 64 * 4;             // this block's attention parameters (if they fit)
+  static constexpr int off_bars = off_cap + kCaStageFloats * 4;
   static constexpr int n_bars = 2 * kSlots + 2 * kARows + 2 * kAcc + 1;
   static constexpr int off_tmem = off_bars + n_bars * 8;
   static constexpr int total = off_tmem + 16;
@@ -139,6 +142,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   float* pool_s = reinterpret_cast<float*>(smem + L::off_pool);
   float* attn_s = reinterpret_cast<float*>(smem + L::off_attn);
   float* svec_s = reinterpret_cast<float*>(smem + L::off_svec);
+  float* cap_s = reinterpret_cast<float*>(smem + L::off_cap);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::off_bars);
   uint64_t* full = bars;                                   // ring slot filled      (producer/transform -> loaders)
   uint64_t* empty = full + kSlots;                         // ring slot drained     (loaders -> producer/transform)
@@ -479,49 +483,109 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       const int rows_img_e = nseg * H;
       const int bimg_first = g0 / rows_img_e;
       int cur_img = -1;
-      grid_dep_wait();
       if constexpr (EPI == EPI_SCALE_SKIP) {
-        // ---- pool-by-linearity (DESIGN.md 5.1): while the pipeline fills, the epilogue warps turn the sums of
+        // ---- pool-by-linearity (DESIGN.md 5.2): while the pipeline fills, the epilogue warps turn the sums of
         // t = relu(conv1(x)) left by the previous kernel into this block's attention vectors
         //   mean(conv2(t))[co] = b[co] + (1/HW) sum_{tap,ci} W[co][ci][tap] * S[tap][ci]
         // (W = this conv's weights, already on their way into shared memory), then QCALayer * meta scale.
-        if (a.epi_stats && egrp == 0) {
-          float* y_s = attn_s;
-          float* s_s = attn_s + 64;
-          float* attr_s = attn_s + 128;
-          float* tmp = attn_s + 128 + 512;  // 1024 floats
-          const NamedGroup grp{et, 128, 5};
+        // The two epilogue groups take alternate images of the band.  Everything that does not depend on the previous
+        // kernel (the block's attention parameters, staged into shared memory when they fit) is fetched before
+        // griddepcontrol.wait.
+        const float* cap = a.ca_params;
+        if (a.epi_stats) {
+          const int np = attn_param_count(a.ca_style, 64, a.ca_R, a.ca_M);
+          if (np <= kCaStageFloats) {
+            for (int i = et + egrp * 128; i < np; i += 128 * kEpiGroups) cap_s[i] = a.ca_params[i];
+            cap = cap_s;
+          }
+        }
+        grid_dep_wait();
+        if (a.epi_stats) {
+          if constexpr (kTwoEpi) named_bar_sync(6, 256); else named_bar_sync(5, 128);  // cap_s complete
+          float* scratch = attn_s + egrp * kAttnScratchFloats;
+          float* y_s = scratch;
+          float* s_s = scratch + 64;
+          float* attr_s = scratch + 128;
+          float* tmp = scratch + 128 + 512;  // 1024 floats
+          const NamedGroup grp{et, 128, egrp ? 7 : 5};
           const int bimg_last = (g1 - 1) / rows_img_e;
-          const int c = et & 63, half = et >> 6;
+          const int cq = et & 15, rg = et >> 4;  // channel quad, row group (8 groups: 2 per warp)
+          const float inv_hw = 1.f / (static_cast<float>(H) * static_cast<float>(a.W));
+          auto add4 = [](float4& d, const float4 v) { d.x += v.x; d.y += v.y; d.z += v.z; d.w += v.w; };
+          auto fold = [&](float4 v) {  // + the other row group of this warp (lane ^ 16)
+            v.x += __shfl_xor_sync(0xffffffffu, v.x, 16); v.y += __shfl_xor_sync(0xffffffffu, v.y, 16);
+            v.z += __shfl_xor_sync(0xffffffffu, v.z, 16); v.w += __shfl_xor_sync(0xffffffffu, v.w, 16);
+            return v;
+          };
           mbar_wait(wbar, 0, 9);  // conv weights have landed in smem (generic-proxy reads below)
-          for (int b = bimg_first; b <= bimg_last; ++b) {
-            const float* pr = a.pool_rows + static_cast<size_t>(b) * rows_img_e * 64;
-            const float* cf = a.col_first + static_cast<size_t>(b) * H * 64;
-            const float* cl = a.col_last + static_cast<size_t>(b) * H * 64;
-            float t = 0.f, c0 = 0.f, c1 = 0.f;
-#pragma unroll 8
-            for (int row = half; row < rows_img_e; row += 2) t += pr[static_cast<size_t>(row) * 64 + c];
-#pragma unroll 8
-            for (int yy = half; yy < H; yy += 2) {
-              c0 += cf[static_cast<size_t>(yy) * 64 + c];
-              c1 += cl[static_cast<size_t>(yy) * 64 + c];
+          for (int b = bimg_first + egrp; b <= bimg_last; b += kEpiGroups) {
+            const float4* pr = reinterpret_cast<const float4*>(a.pool_rows + static_cast<size_t>(b) * rows_img_e * 64) + cq;
+            const float4* cf = reinterpret_cast<const float4*>(a.col_first + static_cast<size_t>(b) * H * 64) + cq;
+            const float4* cl = reinterpret_cast<const float4*>(a.col_last + static_cast<size_t>(b) * H * 64) + cq;
+            // edge rows / corners of the stats (threads 0..63, one channel each): issued ahead of the row loops so
+            // that their latency overlaps, consumed after the first barrier
+            float r0v = 0.f, rlv = 0.f, k00 = 0.f, k0w = 0.f, kh0 = 0.f, khw = 0.f;
+            if (et < 64) {
+              const float* prs = a.pool_rows + static_cast<size_t>(b) * rows_img_e * 64 + et;
+              const float* cfs = a.col_first + static_cast<size_t>(b) * H * 64 + et;
+              const float* cls = a.col_last + static_cast<size_t>(b) * H * 64 + et;
+              r0v = prs[0];
+              rlv = prs[static_cast<size_t>(H - 1) * 64];
+              k00 = cfs[0]; k0w = cls[0];
+              kh0 = cfs[static_cast<size_t>(H - 1) * 64]; khw = cls[static_cast<size_t>(H - 1) * 64];
             }
-            tmp[half * 64 + c] = t;
-            tmp[128 + half * 64 + c] = c0;
-            tmp[256 + half * 64 + c] = c1;
+            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f), c04 = t4, c14 = t4;
+            {  // explicit batches of 8 independent 16-byte loads (fixed summation order)
+              int row = rg;
+              for (; row + 56 < rows_img_e; row += 64) {
+                float4 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = pr[static_cast<size_t>(row + 8 * k) * 16];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) add4(t4, v[k]);
+              }
+              for (; row < rows_img_e; row += 8) add4(t4, pr[static_cast<size_t>(row) * 16]);
+              int yy = rg;
+              for (; yy + 24 < H; yy += 32) {
+                float4 v[8];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  v[2 * k] = cf[static_cast<size_t>(yy + 8 * k) * 16];
+                  v[2 * k + 1] = cl[static_cast<size_t>(yy + 8 * k) * 16];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  add4(c04, v[2 * k]);
+                  add4(c14, v[2 * k + 1]);
+                }
+              }
+              for (; yy < H; yy += 8) {
+                add4(c04, cf[static_cast<size_t>(yy) * 16]);
+                add4(c14, cl[static_cast<size_t>(yy) * 16]);
+              }
+            }
+            t4 = fold(t4); c04 = fold(c04); c14 = fold(c14);
+            if ((lane & 16) == 0) {  // tmp: [3 sums][4 warps][64]
+              const int w4 = et >> 5;
+              reinterpret_cast<float4*>(tmp + (0 * 4 + w4) * 64)[cq] = t4;
+              reinterpret_cast<float4*>(tmp + (1 * 4 + w4) * 64)[cq] = c04;
+              reinterpret_cast<float4*>(tmp + (2 * 4 + w4) * 64)[cq] = c14;
+            }
             for (int i = et; i < a.ca_A; i += 128) attr_s[i] = a.attributes[static_cast<size_t>(b) * a.ca_A + i];
             grp.sync();
-            float* S = tmp + 384;  // [9][64]
+            float* S = tmp;  // [9][64], written once the partial sums have been consumed
+            float Sv[9];
             if (et < 64) {
-              const float T = tmp[c] + tmp[64 + c];
-              const float C0 = tmp[128 + c] + tmp[192 + c], CL = tmp[256 + c] + tmp[320 + c];
-              float R0 = 0.f, RL = 0.f;
-              for (int sg = 0; sg < nseg; ++sg) {
-                R0 += pr[(static_cast<size_t>(sg) * H) * 64 + c];
-                RL += pr[(static_cast<size_t>(sg) * H + (H - 1)) * 64 + c];
+              const int c = et;
+              const float T = (tmp[c] + tmp[64 + c]) + (tmp[128 + c] + tmp[192 + c]);
+              const float C0 = (tmp[256 + c] + tmp[320 + c]) + (tmp[384 + c] + tmp[448 + c]);
+              const float CL = (tmp[512 + c] + tmp[576 + c]) + (tmp[640 + c] + tmp[704 + c]);
+              float R0 = r0v, RL = rlv;
+              for (int sg = 1; sg < nseg; ++sg) {  // images wider than one 128-px segment
+                const float* prs = a.pool_rows + static_cast<size_t>(b) * rows_img_e * 64 + c;
+                R0 += prs[(static_cast<size_t>(sg) * H) * 64];
+                RL += prs[(static_cast<size_t>(sg) * H + (H - 1)) * 64];
               }
-              const float k00 = cf[c], k0w = cl[c];
-              const float kh0 = cf[static_cast<size_t>(H - 1) * 64 + c], khw = cl[static_cast<size_t>(H - 1) * 64 + c];
 #pragma unroll
               for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
@@ -533,14 +597,19 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
                   if (dy == 0 && dx == 2) corner = kh0;
                   if (dy == 2 && dx == 0) corner = k0w;
                   if (dy == 2 && dx == 2) corner = k00;
-                  S[(dy * 3 + dx) * 64 + c] = T - rowx - colx + corner;
+                  Sv[dy * 3 + dx] = T - rowx - colx + corner;
                 }
+            }
+            grp.sync();  // the partial sums are dead: S takes their place
+            if (et < 64) {
+#pragma unroll
+              for (int k = 0; k < 9; ++k) S[k * 64 + et] = Sv[k];
             }
             grp.sync();
             {
               // 2 threads per output channel split the taps; weights come from the swizzled smem tiles
               const int co = et >> 1, part2 = et & 1;
-              float acc = 0.f;
+              float acc0 = 0.f, acc1 = 0.f;
               for (int tap = part2; tap < 9; tap += 2) {
                 const uint8_t* wr = wsm + (tap * 64 + co) * 128;
 #pragma unroll
@@ -550,30 +619,32 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
                     const float2 f = __bfloat1622float2(h2[j]);
-                    acc = fmaf(f.x, S[tap * 64 + ch * 8 + 2 * j], acc);
-                    acc = fmaf(f.y, S[tap * 64 + ch * 8 + 2 * j + 1], acc);
+                    acc0 = fmaf(f.x, S[tap * 64 + ch * 8 + 2 * j], acc0);
+                    acc1 = fmaf(f.y, S[tap * 64 + ch * 8 + 2 * j + 1], acc1);
                   }
                 }
               }
-              tmp[et] = acc;  // tmp[0..127] (the T/C partials are dead by now)
+              tmp[640 + et] = acc0 + acc1;
             }
             grp.sync();
             if (et < 64) {
-              y_s[et] = bias_s[et] + (tmp[2 * et] + tmp[2 * et + 1]) / (static_cast<float>(H) * static_cast<float>(a.W));
+              y_s[et] = bias_s[et] + (tmp[640 + 2 * et] + tmp[640 + 2 * et + 1]) * inv_hw;
               // training forward: the backward needs the pooled mean (every CTA touching image b writes the same bits)
               if (a.ymean_out != nullptr) a.ymean_out[static_cast<size_t>(b) * 64 + et] = y_s[et];
             }
             grp.sync();
-            attn_vector(grp, a.ca_style, a.ca_params, 64, a.ca_R, a.ca_M, attr_s, y_s, s_s, tmp);
+            attn_vector(grp, a.ca_style, cap, 64, a.ca_R, a.ca_M, attr_s, y_s, s_s, tmp);
             if (et < 64)
               svec_s[(b - bimg_first) * 64 + et] =
                   s_s[et] * (a.sq != nullptr ? a.sq[static_cast<size_t>(b) * 64 + et] : 1.f);
             grp.sync();
           }
         }
+      } else {
+        grid_dep_wait();
       }
       if constexpr (kTwoEpi) {
-        if (a.epi_stats) named_bar_sync(6, 256);  // the attention vectors (svec_s) of group 0 are visible to group 1
+        if (a.epi_stats) named_bar_sync(6, 256);  // the attention vectors (svec_s) of both groups are complete
       }
       for (int g = g0 + egrp, it = egrp; g < g1; g += kEpiGroups, it += kEpiGroups) {
         const int col = g / H;
