@@ -52,6 +52,7 @@
 #include <cuda_bf16.h>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 namespace dfir {
 
@@ -74,7 +75,8 @@ constexpr int kTmemCols = 512;
 constexpr int kStageBytes = 128 * 128;       // one output row segment, bf16
 constexpr int kThreads = 320;                // IN_TMA: producer, MMA, 4 epilogue, 4 loader warps
 constexpr int kThreadsFused = 320 + 256;     // + two transform groups of 4 warps
-constexpr int kThreadsTwoEpi = 320 + 128;    // EPI_SCALE_SKIP (IN_TMA): + a second epilogue group (warps 10-13)
+constexpr int kThreadsTwoEpi = 320 + 128;    // EPI_SCALE_SKIP / EPI_RELU_STATS (IN_TMA): + a second epilogue group (warps 10-13)
+constexpr const char* kDefaultL2Policy = "nnnnnn";  // see conv3x3_c64_tc(): overridden by DFIR_L2_POLICY
 constexpr int kMaxBandImages = 8;            // a CTA's row band may touch at most this many images (IN_FUSED)
 constexpr int kAttnScratchFloats = 64 + 64 + 512 + 1024 + 4;  // attention scratch of one epilogue group
 constexpr int kCaStageFloats = 704;          // QCALayer parameter blobs up to this size are staged in shared memory
@@ -123,7 +125,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 template <int EPI, int INMODE>
 constexpr int conv_threads() {
-  return INMODE == IN_FUSED ? kThreadsFused : (EPI == EPI_SCALE_SKIP ? kThreadsTwoEpi : kThreads);
+  return INMODE == IN_FUSED ? kThreadsFused : ((EPI == EPI_SCALE_SKIP || EPI == EPI_RELU_STATS) ? kThreadsTwoEpi : kThreads);
 }
 
 template <int NT, int EPI, int INMODE>
@@ -226,7 +228,10 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             const int col = pr / Hp;
             const int yy = pr % Hp - 1;
             mbar_arrive_expect_tx(&full[slot], kRowBytes);
-            tma_load_4d(ring + slot * kSlotBytes, &tmap_in, &full[slot], a.cin_off, (col % nseg) * 128 - 1, yy,
+            if (a.use_hints)
+              tma_load_4d_hint(ring + slot * kSlotBytes, &tmap_in, &full[slot], a.cin_off, (col % nseg) * 128 - 1, yy,             col / nseg, a.pol_in);
+            else
+              tma_load_4d(ring + slot * kSlotBytes, &tmap_in, &full[slot], a.cin_off, (col % nseg) * 128 - 1, yy,
                         col / nseg);
           }
         }
@@ -354,7 +359,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           mbar_arrive(&empty[slot]);
         }
       }
-    } else if (warp >= 10 && !(EPI == EPI_SCALE_SKIP && INMODE == IN_TMA)) {
+    } else if (warp >= 10 && !((EPI == EPI_SCALE_SKIP || EPI == EPI_RELU_STATS) && INMODE == IN_TMA)) {
       // ===================== fused input transform (IN_FUSED only; warps 10..17) =====================
       if constexpr (INMODE == IN_FUSED) {
         grid_dep_wait();
@@ -471,10 +476,13 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         }
       }
     } else {
-      // ===================== epilogue (warps 2..5; EPI_SCALE_SKIP with TMA input: a second group, warps 10..13) ======
+      // ===================== epilogue (warps 2..5; EPI_SCALE_SKIP / EPI_RELU_STATS with TMA input: a second group,
+      // warps 10..13) ======
       // EPI_SCALE_SKIP moves 10 B per element through the epilogue and is latency bound in one group (measured
       // 3 us per row against 1.1 us of MMAs), so two groups take alternate rows (= alternate accumulators).
-      constexpr bool kTwoEpi = EPI == EPI_SCALE_SKIP && INMODE == IN_TMA;
+      // EPI_RELU_STATS: the per-row channel sums (62 shuffles per thread and row) take one group 1.76 us per row
+      // against 1.3 us of the MMA pipeline (conv1 48.7 us vs 38 us without the statistics), same remedy.
+      constexpr bool kTwoEpi = (EPI == EPI_SCALE_SKIP || EPI == EPI_RELU_STATS) && INMODE == IN_TMA;
       constexpr int kEpiGroups = kTwoEpi ? 2 : 1;
       const int egrp = (kTwoEpi && warp >= 10) ? 1 : 0;
       const int q = warp & 3;          // TMEM lane quarter this warp may read
@@ -643,7 +651,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       } else {
         grid_dep_wait();
       }
-      if constexpr (kTwoEpi) {
+      if constexpr (kTwoEpi && EPI == EPI_SCALE_SKIP) {
         if (a.epi_stats) named_bar_sync(6, 256);  // the attention vectors (svec_s) of both groups are complete
       }
       for (int g = g0 + egrp, it = egrp; g < g1; g += kEpiGroups, it += kEpiGroups) {
@@ -671,10 +679,16 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int idx = i * 128 + et;  // pixel idx >> 3, 16-byte chunk idx & 7
-            if ((idx >> 3) < npxg && !exp_no_skipld)
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(skipbuf_g + idx * 4)),
-                           "l"(src + static_cast<size_t>(idx >> 3) * 64 + (idx & 7) * 4)
-                           : "memory");
+            if ((idx >> 3) < npxg && !exp_no_skipld) {
+              if (a.use_hints)
+                asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(skipbuf_g + idx * 4)),
+                             "l"(src + static_cast<size_t>(idx >> 3) * 64 + (idx & 7) * 4), "l"(a.pol_skip)
+                             : "memory");
+              else
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(skipbuf_g + idx * 4)),
+                             "l"(src + static_cast<size_t>(idx >> 3) * 64 + (idx & 7) * 4)
+                             : "memory");
+            }
           }
           asm volatile("cp.async.commit_group;" ::: "memory");
         };
@@ -775,11 +789,16 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
                 if (a.relu_out) {
                   o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                 }
-                if (o32 != nullptr && !exp_no_f32st) *reinterpret_cast<float4*>(o32 + i * 1024) = o;
                 uint2 pk;
                 pk.x = pack_bf16x2(o.x, o.y);
                 pk.y = pack_bf16x2(o.z, o.w);
-                if (!exp_no_bfst) *reinterpret_cast<uint2*>(obf + i * 1024) = pk;
+                if (a.use_hints) {
+                  if (o32 != nullptr) st_global_v4_hint(o32 + i * 1024, o, a.pol_f32);
+                  st_global_v2_hint(obf + i * 1024, pk, a.pol_out);
+                } else {
+                  if (o32 != nullptr && !exp_no_f32st) *reinterpret_cast<float4*>(o32 + i * 1024) = o;
+                  if (!exp_no_bfst) *reinterpret_cast<uint2*>(obf + i * 1024) = pk;
+                }
               }
             }
           };
@@ -812,10 +831,15 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           pass(1);
           if (g + kEpiGroups < g1) issue_skip(g + kEpiGroups, 0);  // first half of the next row this group owns
         } else {
+          // one group: the two staging buffers alternate; two groups: it & 1 == egrp, each group owns one buffer
           const int sb = it & 1;
           uint8_t* st = stage + sb * kStageBytes;
-          if (et == 0) tma_store_wait_read<1>();  // the TMA store that read this staging buffer has drained it
-          named_bar_sync(1, 128);
+          float* pool_g = pool_s + egrp * 256;
+          const uint32_t bar_c = 1 + 2 * egrp, bar_d = 2 + 2 * egrp;
+          if (et == 0) {  // the TMA store that read this staging buffer has drained it
+            if constexpr (kTwoEpi) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+          }
+          named_bar_sync(bar_c, 128);
           const size_t pix = (static_cast<size_t>(b) * a.H + y) * a.W + x;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {  // two halves of 32 channels bound the register footprint
@@ -902,18 +926,19 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
                 for (int i = 0; i < 32; ++i) v[i] = 0.f;
               }
               warp_channel_sums32(v, lane);
-              pool_s[q * 64 + h * 32 + lane] = v[0];
+              pool_g[q * 64 + h * 32 + lane] = v[0];
             }
           }
           fence_proxy_async_smem();
-          named_bar_sync(2, 128);
+          named_bar_sync(bar_d, 128);
           if (et == 0 && !exp_skip_store) {
-            tma_store_4d(&tmap_out, st, 0, seg * 128, y, b);
+            if (a.use_hints) tma_store_4d_hint(&tmap_out, st, 0, seg * 128, y, b, a.pol_out);
+            else tma_store_4d(&tmap_out, st, 0, seg * 128, y, b);
             tma_store_commit();
           }
           if constexpr (EPI == EPI_BIAS_POOL || EPI == EPI_RELU_STATS) {
             if (et < 64) {
-              const float s = ((pool_s[et] + pool_s[64 + et]) + pool_s[128 + et]) + pool_s[192 + et];
+              const float s = ((pool_g[et] + pool_g[64 + et]) + pool_g[128 + et]) + pool_g[192 + et];
               a.pool_rows[(static_cast<size_t>(col) * a.H + y) * 64 + et] = s;
             }
           }
@@ -1085,6 +1110,26 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   a.res_scale = d.res_scale;
   a.epi_stats = d.epi_stats;
   a.debug_probe = getenv("DFIR_DEBUG_PROBE") != nullptr ? atoi(getenv("DFIR_DEBUG_PROBE")) : 0;
+  {
+    // L2 residency of the RCAB chain: t (conv1 -> conv2) and the bf16 copy of the stream (conv2 -> conv1) are consumed
+    // by the next launch and fit the 126 MB L2 together, the fp32 stream (read and written once per block) does not.
+    // DFIR_L2_POLICY = six letters n|f|l (normal / evict first / evict last):
+    //   conv1 input, conv1 output, conv2 input, conv2 bf16 output, conv2 fp32 skip, conv2 fp32 output
+    const char* pol_env = getenv("DFIR_L2_POLICY");
+    const char* pol = pol_env != nullptr ? pol_env : kDefaultL2Policy;
+    auto word = [](char c) -> unsigned long long {
+      return c == 'f' ? ptx::kL2EvictFirst : (c == 'l' ? ptx::kL2EvictLast : ptx::kL2EvictNormal);
+    };
+    const bool conv1_role = d.epi == EPI_RELU_STATS || d.epi == EPI_BIAS_RELU;
+    const bool conv2_role = d.epi == EPI_SCALE_SKIP;
+    if (pol != nullptr && strlen(pol) >= 6 && strncmp(pol, "nnnnnn", 6) != 0 && !fused && (conv1_role || conv2_role)) {
+      a.use_hints = 1;
+      a.pol_in = word(pol[conv1_role ? 0 : 2]);
+      a.pol_out = word(pol[conv1_role ? 1 : 3]);
+      a.pol_skip = word(pol[4]);
+      a.pol_f32 = word(pol[5]);
+    }
+  }
   a.ca_params = d.ca_params;
   a.attributes = d.attributes;
   a.sq = d.sq;

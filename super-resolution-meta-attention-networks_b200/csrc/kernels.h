@@ -53,6 +53,10 @@ struct ConvTcArgs {  // kernel argument block
   int ca_style, ca_R, ca_M, ca_A;
   int epi_stats;            // EPI_SCALE_SKIP: evaluate the attention vector from the statistics of t in-kernel
   int debug_probe;
+  // L2 eviction-priority policy words (ptx.cuh), all valid when use_hints != 0: TMA input rows, bf16 output,
+  // fp32 skip rows, fp32 output
+  int use_hints;
+  unsigned long long pol_in, pol_out, pol_skip, pol_f32;
 };
 
 struct ConvTcDesc {  // host-side launch description

@@ -313,11 +313,12 @@ def test_rcan_handler_through_the_registry(tmp_path):
     assert float(l1) < float(l0)
 
 
-@pytest.mark.parametrize("shape", [(1, 1, 1), (2, 1, 7), (1, 9, 1), (1, 3, 129), (3, 2, 257)])
+@pytest.mark.parametrize("shape", [(1, 1, 1), (2, 1, 7), (1, 9, 1), (1, 3, 129), (3, 2, 257), (300, 2, 5), (75, 4, 130)])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_degenerate_and_ragged_image_shapes(shape, precision):
-    """single pixels, single rows / columns (first row == last row in the pool-by-linearity statistics) and widths one
-    pixel past a multiple of the 128-pixel tile, against the oracle"""
+    """single pixels, single rows / columns (first row == last row in the pool-by-linearity statistics), widths one
+    pixel past a multiple of the 128-pixel tile, and many tiny images (a CTA's row band touches three or more images, so
+    both epilogue groups of conv2 evaluate attention vectors), against the oracle"""
     from deepfir_b200.qrcan import QRCAN
     torch.manual_seed(11)
     kw = dict(n_resgroups=1, n_resblocks=2, style="standard", num_metadata=10, include_q_layer=True, scale=2)

@@ -223,3 +223,52 @@ def ss_stats_bench():
 
 if "ssstats" in which:
     ss_stats_bench()
+
+
+def pair_bench():
+    """One RCAB exactly as the default schedule chains it: conv1 (+ReLU+statistics) xb -> t, then conv2 (+in-kernel
+    attention + scale + skip) t, x -> x, xb — versus each kernel alone on buffers rotated to defeat the L2."""
+    wp = torch.empty(9 * 64 * 128, dtype=torch.uint8, device=dev)
+    w = (torch.randn(64, 64, 3, 3, device=dev) / 48).contiguous()
+    bias = torch.zeros(64, device=dev)
+    _lib.check(lib.dfir_pack_conv3x3_bf16(w.data_ptr(), wp.data_ptr(), 64, 64, 64, 0, 1, st()), "pack")
+    blob = torch.randn(4 * 74 + 4 + 64 * 4 + 64, device=dev) / 8
+    for bc in BCS:
+        NB = 4
+        xs = [torch.randn(bc, LR, LR, 64, device=dev) for _ in range(NB)]
+        xbs = [x.to(torch.bfloat16) for x in xs]
+        ts = [torch.empty_like(xbs[0]) for _ in range(NB)]
+        pool = torch.empty(bc, LR, 64, device=dev); cf = torch.empty(bc, LR, 64, device=dev); cl = torch.empty(bc, LR, 64, device=dev)
+        attr = torch.rand(bc, 10, device=dev); sq = torch.rand(bc, 64, device=dev) * 0.1
+        k = [0]
+
+        def conv1(i):
+            _lib.check(lib.dfir_conv3x3_c64_stats(xbs[i].data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR,
+                                                  ts[i].data_ptr(), pool.data_ptr(), cf.data_ptr(), cl.data_ptr(), st()), "c1")
+
+        def conv2(i):
+            _lib.check(lib.dfir_conv3x3_c64_scale_skip(ts[i].data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR, None,
+                                                       xs[i].data_ptr(), xs[i].data_ptr(), xbs[i].data_ptr(), pool.data_ptr(),
+                                                       cf.data_ptr(), cl.data_ptr(), 3, blob.data_ptr(), 4, 10, 10,
+                                                       attr.data_ptr(), sq.data_ptr(), st()), "c2")
+
+        def pair_same():
+            conv1(0); conv2(0)
+
+        def c1_rot():
+            k[0] = (k[0] + 1) % NB; conv1(k[0])
+
+        def c2_rot():
+            k[0] = (k[0] + 1) % NB; conv2(k[0])
+
+        conv1(0)
+        for name, fn in (("conv1 same buffers", lambda: conv1(0)), ("conv1 rotating 4 buffers", c1_rot),
+                         ("conv2 same buffers", lambda: conv2(0)), ("conv2 rotating 4 buffers", c2_rot),
+                         ("pair conv1->conv2 (the chain)", pair_same)):
+            us = timeit(fn, NREP[0], NREP[1])
+            print("bc=%3d policy=%s pdl=%s  %-32s %8.2f us" % (bc, os.environ.get("DFIR_L2_POLICY", "default"),
+                                                             os.environ.get("DFIR_PDL", "default"), name, us), flush=True)
+
+
+if "pair" in which:
+    pair_bench()
