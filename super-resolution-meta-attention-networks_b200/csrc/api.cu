@@ -140,6 +140,7 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
     d.B = Bc; d.H = H; d.W = W; d.cin_total = 64; d.cin_off = 0; d.cout = 64; d.epi = epi; d.in_mode = IN_TMA;
     d.num_sms = num_sms;
     d.wpacked = cw + static_cast<size_t>(widx) * wbytes; d.bias = n->conv_b + static_cast<size_t>(widx) * 64;
+    if (widx + 1 < n_trunk) d.next_wpacked = cw + static_cast<size_t>(widx + 1) * wbytes;  // trunk convs run in index order
     d.out_pix_stride = pixB; d.out_row_stride = rowB; d.out_img_stride = imgB;
     d.pool_rows = w.pool;
     return d;

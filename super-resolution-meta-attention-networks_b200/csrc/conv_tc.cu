@@ -198,6 +198,14 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   // barrier set-up, TMEM allocation and weight load then overlap the tail of this grid.  Everything that reads what
   // the previous kernel wrote (activation rows, statistics, skip rows) sits behind grid_dep_wait().
   if (threadIdx.x == 0) grid_dep_launch();
+  // The activations of one RCAB (~0.5 GB at 32 images) flush the 126 MB L2 between two uses of a layer's weights, so
+  // each conv would start with 148 CTAs missing on the same 72 KB.  The first CTAs pull the next conv's weights into
+  // L2 while this one runs.
+  if (a.next_w != nullptr && warp == 2) {
+    const int nlines = a.next_w_bytes >> 7;
+    for (int line = blockIdx.x * 32 + lane; line < nlines; line += gridDim.x * 32)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(a.next_w) + static_cast<size_t>(line) * 128));
+  }
   const bool probe = (a.debug_probe & 1) != 0 && blockIdx.x == 0 && lane == 0;
   const bool exp_skip_store = (a.debug_probe & 2) != 0;  // timing experiments only (wrong results)
   const bool exp_one_copy = (a.debug_probe & 4) != 0;
@@ -1110,6 +1118,13 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   a.res_scale = d.res_scale;
   a.epi_stats = d.epi_stats;
   a.debug_probe = getenv("DFIR_DEBUG_PROBE") != nullptr ? atoi(getenv("DFIR_DEBUG_PROBE")) : 0;
+  {
+    const char* e = getenv("DFIR_WPREFETCH");  // next-layer weight prefetch: measured, no gain (31.6-32.7 ms either way), default off
+    if (d.next_wpacked != nullptr && e != nullptr && atoi(e) != 0) {
+      a.next_w = d.next_wpacked;
+      a.next_w_bytes = 9 * 64 * 128;
+    }
+  }
   {
     // L2 residency of the RCAB chain: t (conv1 -> conv2) and the bf16 copy of the stream (conv2 -> conv1) are consumed
     // by the next launch and fit the 126 MB L2 together, the fp32 stream (read and written once per block) does not.

@@ -57,6 +57,8 @@ struct ConvTcArgs {  // kernel argument block
   // fp32 skip rows, fp32 output
   int use_hints;
   unsigned long long pol_in, pol_out, pol_skip, pol_f32;
+  const void* next_w;       // packed weights of the NEXT conv of the chain (or nullptr): pulled into L2 at kernel start
+  int next_w_bytes;
 };
 
 struct ConvTcDesc {  // host-side launch description
@@ -91,6 +93,7 @@ struct ConvTcDesc {  // host-side launch description
   float res_scale;
   int ca_style, ca_R, ca_M, ca_A;
   int epi_stats;
+  const void* next_wpacked = nullptr;  // next conv's packed weights, prefetched into L2 (see ConvTcArgs::next_w)
 };
 
 int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream);

@@ -21,7 +21,10 @@ net = QRCAN(n_resgroups=10, n_resblocks=20, style="standard", num_metadata=10, i
 ref = None
 pols = sys.argv[1:] or ["nnnnnn", "flflff", "nlnlff", "nlnlnn", "nnnnff", "flflnn", "nlflff", "nnnlff", "nlnnff", "nnnnnn"]
 for pol in pols:
-    os.environ["DFIR_L2_POLICY"] = pol
+    if "=" in pol:  # any other A/B switch of the library, e.g. DFIR_WPREFETCH=0
+        k, v = pol.split("=", 1); os.environ[k] = v
+    else:
+        os.environ["DFIR_L2_POLICY"] = pol
     with torch.no_grad():
         ms = timeit(lambda: net(x, meta)); out = net(x, meta)
     if ref is None: ref = out.clone()
