@@ -62,7 +62,8 @@ using namespace ptx;
 
 namespace {
 
-constexpr int kSlots = 4;                    // smem input-row ring depth (producer -> A loaders)
+constexpr int kSlots = 3;                    // smem input-row ring depth (producer -> A loaders); the rows a conv needs
+                                             // live in the TMEM row slots, the ring is TMA look-ahead only
 constexpr int kSlotPix = 136;                // 130 px used (128 + 2 halo), rounded up to 8 px = 1024 B
 constexpr int kSlotBytes = kSlotPix * 128;   // 17408, multiple of 1024
 constexpr int kBoxPix = 130;
@@ -87,13 +88,17 @@ struct SmemLayout {
   static constexpr int off_w = 0;
   static constexpr int off_ring = off_w + ((w_bytes + 1023) / 1024) * 1024;
   static constexpr int off_stage = off_ring + kSlots * kSlotBytes;
-  static constexpr int off_skip = off_stage + 2 * kStageBytes;   // EPI_SCALE_SKIP: fp32 skip row (cp.async target)
-  static constexpr int off_bias = off_skip + 128 * 64 * 4;
+  // EPI_SCALE_SKIP: fp32 skip rows (cp.async targets): [half 0 | half 1] x [epilogue group] x [128 px][32 ch]
+  static constexpr int off_skip = off_stage + 2 * kStageBytes;
+  static constexpr int off_bias = off_skip + 2 * 128 * 64 * 4;
   static constexpr int off_pool = off_bias + 64 * 4;
-  static constexpr int off_attn = off_pool + 8 * 64 * 4;                         // per epilogue group: y[64] s[64] attr[512] tmp[1024]
-  static constexpr int off_svec = off_attn + 2 * kAttnScratchFloats * 4;         // s of the images of this band
-  static constexpr int off_cap = off_svec + kMaxBandImages * 64 * 4;             // this block's attention parameters (if they fit)
-  static constexpr int off_bars = off_cap + kCaStageFloats * 4;
+  // Attention scratch (per epilogue group: y[64] s[64] attr[512] tmp[1024]) and the staged attention parameters are
+  // only touched in the kernel prologue, before the first accumulator is drained: they alias the output staging tiles.
+  static constexpr int off_attn = off_stage;
+  static constexpr int off_cap = off_attn + 2 * kAttnScratchFloats * 4;
+  static_assert(off_cap + kCaStageFloats * 4 <= off_stage + 2 * kStageBytes, "prologue scratch must fit the staging tiles");
+  static constexpr int off_svec = off_pool + 8 * 64 * 4;                         // s of the images of this band
+  static constexpr int off_bars = off_svec + kMaxBandImages * 64 * 4;
   static constexpr int n_bars = 2 * kSlots + 2 * kARows + 2 * kAcc + 1;
   static constexpr int off_tmem = off_bars + n_bars * 8;
   static constexpr int total = off_tmem + 16;
@@ -672,14 +677,21 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         const int acc = it % kAcc;
         if (probe) g_dfir_progress[8 + q] = it + 1;
         // EPI_SCALE_SKIP: the fp32 skip row travels global -> smem with cp.async in two halves of 32 channels (8 x 16 B
-        // per thread and half, coalesced, no registers held): the copy for the next half is issued as soon as the
-        // current one has been consumed, so its latency hides behind the barriers, the TMEM read and the tile writes.
-        // Each thread later reads back exactly the 16-byte slots it copied itself, so no barrier is needed, only
-        // cp.async.wait_group.
+        // per thread and half, coalesced, no registers held).  Each thread later reads back exactly the 16-byte slots
+        // it copied itself, so no barrier is needed, only cp.async.wait_group.
         const bool has_skip = a.skip_f32 != nullptr;  // dgrad launches without a skip: out = acc * s + b * s
+        // Both 32-channel halves of a row have their own buffer, so the load of a half is issued a full pass (tile
+        // write + barriers + global pass) before it is consumed: the copy of half h of the next row goes out as soon as
+        // half h of this row has been read.  One commit group per call, also when nothing is left to load, so that
+        // cp.async.wait_group 1 always means "the older of the two outstanding halves has landed".
         float* skipbuf_g = skipbuf + egrp * (128 * 32);
         auto issue_skip = [&](int gg, int hh) {
           if (!has_skip) return;
+          if (gg >= g1) {
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            return;
+          }
+          float* sdst = skipbuf_g + hh * (2 * 128 * 32);
           const int colg = gg / H;
           const int segg = colg % nseg;
           const int npxg = min(128, a.W - segg * 128);
@@ -689,11 +701,11 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             const int idx = i * 128 + et;  // pixel idx >> 3, 16-byte chunk idx & 7
             if ((idx >> 3) < npxg && !exp_no_skipld) {
               if (a.use_hints)
-                asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(skipbuf_g + idx * 4)),
+                asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(sdst + idx * 4)),
                              "l"(src + static_cast<size_t>(idx >> 3) * 64 + (idx & 7) * 4), "l"(a.pol_skip)
                              : "memory");
               else
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(skipbuf_g + idx * 4)),
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst + idx * 4)),
                              "l"(src + static_cast<size_t>(idx >> 3) * 64 + (idx & 7) * 4)
                              : "memory");
             }
@@ -701,7 +713,10 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           asm volatile("cp.async.commit_group;" ::: "memory");
         };
         if constexpr (EPI == EPI_SCALE_SKIP) {
-          if (it == egrp) issue_skip(g, 0);
+          if (it == egrp) {
+            issue_skip(g, 0);
+            issue_skip(g, 1);
+          }
           if (has_skip && !exp_no_pf && g + 2 * kEpiGroups < g1) {  // pull the skip row this group needs two rows from now into L2
             const int g2 = g + 2 * kEpiGroups, col2 = g2 / H;
             const size_t e2 = ((static_cast<size_t>(col2 / nseg) * a.H + (g2 % H)) * a.W + (col2 % nseg) * 128) * 64;
@@ -770,11 +785,11 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             __nv_bfloat16* obf = a.out_bf16_direct + e0;
             __nv_bfloat16* rbf = save_r ? a.r_out + e0 : nullptr;
             const float4* t4 = reinterpret_cast<const float4*>(tile);
-            const float4* sk4 = reinterpret_cast<const float4*>(skipbuf_g) + et;
+            const float4* sk4 = reinterpret_cast<const float4*>(skipbuf_g + h * (2 * 128 * 32)) + et;
             const float4 s4 = reinterpret_cast<const float4*>(sc_s)[h * 8 + c4];
             const float4 b4 = reinterpret_cast<const float4*>(sc_s + 64)[h * 8 + c4];
             const float4 sr4 = reinterpret_cast<const float4*>(sc_s + 128)[h * 8 + c4];
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int p = i * 16 + pq;
@@ -832,12 +847,12 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           if (lane == 0) mbar_arrive(&tempty[acc]);  // accumulator back to the MMA warp
           named_bar_sync(bar_b, 128);
           pass(0);
-          issue_skip(g, 1);  // this thread's skip slots are free again: refill them with the second half
+          issue_skip(g + kEpiGroups, 0);  // this thread's half-0 slots are free again: next row of this group
           named_bar_sync(bar_a, 128);
           write_tile(1);
           named_bar_sync(bar_b, 128);
           pass(1);
-          if (g + kEpiGroups < g1) issue_skip(g + kEpiGroups, 0);  // first half of the next row this group owns
+          issue_skip(g + kEpiGroups, 1);
         } else {
           // one group: the two staging buffers alternate; two groups: it & 1 == egrp, each group owns one buffer
           const int sb = it & 1;
