@@ -53,6 +53,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 namespace dfir {
 
@@ -211,6 +212,9 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
     for (int line = blockIdx.x * 32 + lane; line < nlines; line += gridDim.x * 32)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(a.next_w) + static_cast<size_t>(line) * 128));
   }
+  // Timing experiments (wrong results) and progress probes are compiled in only with -DDFIR_PROBES (make PROBES=1):
+  // in the shipped kernel they are constant-false, so neither their branches nor their code reach the hot loops.
+#ifdef DFIR_PROBES
   const bool probe = (a.debug_probe & 1) != 0 && blockIdx.x == 0 && lane == 0;
   const bool exp_skip_store = (a.debug_probe & 2) != 0;  // timing experiments only (wrong results)
   const bool exp_one_copy = (a.debug_probe & 4) != 0;
@@ -224,6 +228,11 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   const bool exp_no_pf = (a.debug_probe & 2048) != 0;      // no L2 prefetch of the skip rows
   const bool exp_no_tile = (a.debug_probe & 4096) != 0;    // scale+skip epilogue: TMEM reads and barriers only
   const bool exp_no_pass = (a.debug_probe & 8192) != 0;    // scale+skip epilogue: no coalesced pass
+#else
+  constexpr bool probe = false, exp_skip_store = false, exp_one_copy = false, exp_no_copy = false, exp_no_epi = false,
+                 exp_n192 = false, exp_n128 = false, exp_no_skipld = false, exp_no_f32st = false, exp_no_bfst = false,
+                 exp_no_pf = false, exp_no_tile = false, exp_no_pass = false;
+#endif
 
   if (g0 < g1) {
     if (warp == 0) {
@@ -778,7 +787,13 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               trow[(c + m) & 7] = make_float4(__uint_as_float(rv[4 * c + 0]), __uint_as_float(rv[4 * c + 1]),
                                               __uint_as_float(rv[4 * c + 2]), __uint_as_float(rv[4 * c + 3]));
           };
-          auto pass = [&](int h) {
+          // `fast` (compile-time tag): the inference chain's case — full 128-px row, fp32 skip and fp32 output present,
+          // no saved r, no ReLU, no cache hints — as straight-line code; everything else takes the general form.  The
+          // epilogue loop is instruction-fetch sensitive (ncu: 11 % of its samples stall on no_inst).
+          const bool fast_pass = !save_r && has_skip && !a.relu_out && !a.use_hints && a.out_f32 != nullptr && npx == 128 &&
+                                 !exp_no_f32st && !exp_no_bfst && (a.debug_probe & 16384) == 0;  // bit 16384: A/B switch
+          auto pass_impl = [&](int h, auto fast) {
+            constexpr bool F = decltype(fast)::value;
             if (exp_no_tile || exp_no_pass) return;
             const size_t e0 = ((static_cast<size_t>(b) * a.H + y) * a.W + seg * 128 + pq) * 64 + h * 32 + c4 * 4;
             float* o32 = a.out_f32 != nullptr ? a.out_f32 + e0 : nullptr;
@@ -793,29 +808,32 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int p = i * 16 + pq;
-              if (p < npx) {
+              if (F || p < npx) {
                 const float4 tv = t4[p * 8 + ((c4 + p) & 7)];
                 float4 o;
                 o.x = fmaf(tv.x, s4.x, b4.x); o.y = fmaf(tv.y, s4.y, b4.y);
                 o.z = fmaf(tv.z, s4.z, b4.z); o.w = fmaf(tv.w, s4.w, b4.w);
-                if (save_r) {  // r = conv + b goes out as bf16 for the backward; the stream gets r * s + skip
+                if (!F && save_r) {  // r = conv + b goes out as bf16 for the backward; the stream gets r * s + skip
                   uint2 rk;
                   rk.x = pack_bf16x2(o.x, o.y);
                   rk.y = pack_bf16x2(o.z, o.w);
                   *reinterpret_cast<uint2*>(rbf + i * 1024) = rk;
                   o.x *= sr4.x; o.y *= sr4.y; o.z *= sr4.z; o.w *= sr4.w;
                 }
-                if (has_skip) {
+                if (F || has_skip) {
                   const float4 sk = sk4[i * 128];
                   o.x += sk.x; o.y += sk.y; o.z += sk.z; o.w += sk.w;
                 }
-                if (a.relu_out) {
+                if (!F && a.relu_out) {
                   o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                 }
                 uint2 pk;
                 pk.x = pack_bf16x2(o.x, o.y);
                 pk.y = pack_bf16x2(o.z, o.w);
-                if (a.use_hints) {
+                if (F) {
+                  *reinterpret_cast<float4*>(o32 + i * 1024) = o;
+                  *reinterpret_cast<uint2*>(obf + i * 1024) = pk;
+                } else if (a.use_hints) {
                   if (o32 != nullptr) st_global_v4_hint(o32 + i * 1024, o, a.pol_f32);
                   st_global_v2_hint(obf + i * 1024, pk, a.pol_out);
                 } else {
@@ -824,6 +842,10 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
                 }
               }
             }
+          };
+          auto pass = [&](int h) {
+            if (fast_pass) pass_impl(h, std::true_type{});
+            else pass_impl(h, std::false_type{});
           };
           named_bar_sync(bar_a, 128);  // the previous row's second pass has finished with the tile (and with sc_s)
           if (b != cur_img) {          // (uniform) new image: stage its scale vector
