@@ -51,42 +51,45 @@ __global__ void head_conv_kernel(const float* __restrict__ x, const float* __res
   const int nw = 9 * Cin * Cout;
   for (int i = threadIdx.x; i < nw; i += blockDim.x) ws[i] = wp[i];
   __syncthreads();
+  // grid-stride over (pixel, output octet) items: the 9*Cin*Cout weights are staged once per CTA, not once per 32 pixels
   const int oct_per_pix = Cout / 8;
-  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long npix = static_cast<long long>(B) * H * W;
-  const long long pix = gid / oct_per_pix;
-  const int oc = static_cast<int>(gid % oct_per_pix) * 8;
-  if (pix >= npix) return;
-  const int xw = static_cast<int>(pix % W);
-  const int y = static_cast<int>((pix / W) % H);
-  const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
-  float acc[8];
+  const long long nitems = npix * oct_per_pix;
+  for (long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; gid < nitems;
+       gid += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = gid / oct_per_pix;
+    const int oc = static_cast<int>(gid % oct_per_pix) * 8;
+    const int xw = static_cast<int>(pix % W);
+    const int y = static_cast<int>((pix / W) % H);
+    const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
+    float acc[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = bias != nullptr ? bias[oc + i] : 0.f;
-  for (int dy = 0; dy < 3; ++dy) {
-    const int yy = y + dy - 1;
-    if (yy < 0 || yy >= H) continue;
-    for (int dx = 0; dx < 3; ++dx) {
-      const int xx = xw + dx - 1;
-      if (xx < 0 || xx >= W) continue;
-      for (int ci = 0; ci < Cin; ++ci) {
-        const float v = x[((static_cast<size_t>(b) * Cin + ci) * H + yy) * W + xx];
-        const float* wr = ws + ((dy * 3 + dx) * Cin + ci) * Cout + oc;
+    for (int i = 0; i < 8; ++i) acc[i] = bias != nullptr ? bias[oc + i] : 0.f;
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = y + dy - 1;
+      if (yy < 0 || yy >= H) continue;
+      for (int dx = 0; dx < 3; ++dx) {
+        const int xx = xw + dx - 1;
+        if (xx < 0 || xx >= W) continue;
+        for (int ci = 0; ci < Cin; ++ci) {
+          const float v = x[((static_cast<size_t>(b) * Cin + ci) * H + yy) * W + xx];
+          const float* wr = ws + ((dy * 3 + dx) * Cin + ci) * Cout + oc;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(v, wr[i], acc[i]);
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(v, wr[i], acc[i]);
+        }
       }
     }
-  }
-  const size_t o = static_cast<size_t>(pix) * Cout + oc;
-  if (out_f32 != nullptr) {
-    *reinterpret_cast<float4*>(out_f32 + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    *reinterpret_cast<float4*>(out_f32 + o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-  }
-  if (out_bf16 != nullptr) {
-    __align__(16) __nv_bfloat162 pk[4];
+    const size_t o = static_cast<size_t>(pix) * Cout + oc;
+    if (out_f32 != nullptr) {
+      *reinterpret_cast<float4*>(out_f32 + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(out_f32 + o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    if (out_bf16 != nullptr) {
+      __align__(16) __nv_bfloat162 pk[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pk[i] = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
-    *reinterpret_cast<uint4*>(out_bf16 + o) = *reinterpret_cast<uint4*>(pk);
+      for (int i = 0; i < 4; ++i) pk[i] = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
+      *reinterpret_cast<uint4*>(out_bf16 + o) = *reinterpret_cast<uint4*>(pk);
+    }
   }
 }
 
@@ -541,7 +544,8 @@ int head_conv(const float* x, const float* wp, const float* bias, float* out_f32
   if (Cout % 8 != 0 || 9 * Cin * Cout * 4 > 48 * 1024) return DFIR_ERR_ARG;
   const long long nthreads = static_cast<long long>(B) * H * W * (Cout / 8);
   if (nthreads == 0) return DFIR_OK;
-  head_conv_kernel<<<static_cast<unsigned>((nthreads + 255) / 256), 256, 9 * Cin * Cout * 4, s>>>(
+  const long long nblocks = std::min<long long>((nthreads + 255) / 256, 148 * 8);  // 8 resident CTAs per SM
+  head_conv_kernel<<<static_cast<unsigned>(nblocks), 256, 9 * Cin * Cout * 4, s>>>(
       x, wp, bias, out_f32, out_bf16, B, Cin, H, W, Cout);
   return ok_or_cuda();
 }
