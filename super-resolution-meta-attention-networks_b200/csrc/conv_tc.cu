@@ -25,7 +25,15 @@
 // (TMEM -> registers -> fused bias/ReLU/skip/pool -> swizzled smem -> TMA store), warps 6-9 = A loaders.
 // EPI_SCALE_SKIP (the fp32 residual-stream epilogue: scale, skip add, fp32 + bf16 stores; also the fp32-accumulating
 // data-gradient conv of the backward pass) adds a second epilogue group, warps 10-13: the two groups drain alternate
-// accumulators, each in two 32-channel halves through a 16 KB fp32 transposition tile and a 16 KB cp.async skip buffer.
+// accumulators, each in two 32-channel halves through a 16 KB fp32 transposition tile; both halves of the fp32 skip row
+// have their own 16 KB cp.async buffer per group, so a half is requested a full pass before it is read.  The inference
+// case (full row, skip + fp32 output, nothing else) runs a straight-line specialisation of the pass: the loop is
+// instruction-fetch sensitive.  EPI_RELU_STATS (conv1 + the statistics of pool-by-linearity) uses the same two groups:
+// its 62 shuffles per thread and row do not fit one group's share of the MMA pace.
+//
+// Environment switches (A/B measurements): DFIR_PDL, DFIR_L2_POLICY (L2 eviction-priority hints, default
+// none), DFIR_WPREFETCH (next layer's weights into L2, default off), DFIR_NUM_SMS; DFIR_DEBUG_PROBE timing experiments
+// exist only in a `make PROBES=1` build (bit 16384, fast path off, always).
 //
 // The kernel is launched with the programmatic-dependent-launch attribute: after its set-up it lets the next kernel of
 // the stream become resident as CTAs retire (griddepcontrol.launch_dependents) and waits for its own predecessor
