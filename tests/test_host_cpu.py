@@ -259,3 +259,49 @@ def test_two_rank_gradient_allreduce_equals_full_batch_gradient_on_gloo():
         os.unlink(script)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert res.stdout.count("ok") == 2
+
+
+def test_bench_clock_sampler_uses_only_lines_inside_the_timed_region(tmp_path):
+    """bench.py starts nvidia-smi ahead of the warm-up; only the lines stamped inside [mark_begin, mark_end] may reach
+    the `clocks` object, throttle reasons included (a warm-up line must not leak a reason into the timed region)."""
+    import datetime
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class _Done:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+
+    def stamp(t):
+        return datetime.datetime.fromtimestamp(t).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+
+    t0 = 1_792_000_000.0
+    lines = [(t0 - 0.30, 1200, "Active", "Not Active"),      # warm-up: ignored
+             (t0 + 0.02, 1950, "Not Active", "Not Active"),
+             (t0 + 0.04, 1905, "Not Active", "Active"),
+             (t0 + 0.06, 1965, "Not Active", "Not Active"),
+             (t0 + 0.50, 1000, "Active", "Active")]           # after the timed steps: ignored
+    path = tmp_path / "smi.csv"
+    path.write_text("".join("%s, %d, 1965, %s, Not Active, Not Active, %s\n" % (stamp(t), mhz, hw, cap)
+                            for t, mhz, hw, cap in lines) + "garbage line\n")
+    s = bench.ClockSampler(0)
+    s.proc, s.path, s.t0, s.t1 = _Done(), str(path), t0, t0 + 0.1
+    out = s.stop()
+    assert out["samples"] == 3 and out["sm_mhz"] == 1950.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"] and out["window"] == "device-timed steps"
+    # nothing inside the window: falls back to the window that also covers the end-to-end steps, else says so
+    path.write_text("%s, 1800, 1965, Not Active, Not Active, Not Active, Not Active\n" % stamp(t0 + 0.3))
+    s = bench.ClockSampler(0)
+    s.proc, s.path, s.t0, s.t1, s.t1_fallback = _Done(), str(path), t0, t0 + 0.1, t0 + 0.4
+    out = s.stop()
+    assert out["samples"] == 1 and "end-to-end" in out["window"]
+    path.write_text("")
+    s = bench.ClockSampler(0)
+    s.proc, s.path, s.t0, s.t1 = _Done(), str(path), t0, t0 + 0.1
+    out = s.stop()
+    assert out["samples"] == 0 and out["sm_mhz"] is None
