@@ -421,15 +421,15 @@ def conv_roofline(lib, dev, net):
     achieved = flops / (ms / 1e3) / 1e12
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full capture
     # summarised in profiles/r01_conv_ts_mode_ncu.md (32 images per launch; algorithmic bytes = 2 x 67.1 MB)
-    # profiles/r01_tc_kernels_ncu.md (conv1 with statistics, 32 images per launch): 71.7 MB read + 20.9 MB written
-    traffic = 92612352 if bc == 32 else None
+    # profiles/r01c_tc_kernels_ncu.md (conv1 with statistics, 32 images per launch): 71.8 MB read + 21.6 MB written
+    traffic = 93349888 if bc == 32 else None
     conv1 = {"bound": "tensor", "kernel": "conv3x3_c64_tc_kernel<64, bias+relu> (RCAB conv1)", "achieved": round(achieved, 2),
              "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": round(achieved / pk["tf_burst"], 4),
              "traffic": traffic, "launch_us": round(ms * 1e3, 3), "images_per_launch": bc,
              "algorithmic_flops_per_launch": flops, "peak_source": pk["source"] + ", burst (kernel timed alone)"}
 
     # RCAB conv2 + channel/meta attention scale + residual add (EPI_SCALE_SKIP): the kernel with the largest share of
-    # the step (profiles/r01_launches_infer_summary.md: 62 %).  It moves the fp32 residual stream and is bound by
+    # the step (profiles/r01c_launches_infer_32x128.csv: 64 %).  It moves the fp32 residual stream and is bound by
     # memory traffic: algorithmic bytes per element = t 2 (in) + x 4 (in) + x 4 (out) + bf16(x) 2 (out) = 12 B.
     t_in = torch.randn(bc, LR, LR, 64, device=dev).to(torch.bfloat16)
     x32 = torch.randn(bc, LR, LR, 64, device=dev)
@@ -452,10 +452,14 @@ def conv_roofline(lib, dev, net):
     ms2 = e0.elapsed_time(e1) / n
     byt = bc * LR * LR * 64 * 12
     gbs = byt / (ms2 / 1e3) / 1e9
-    # same capture file (conv2_ss): dram 251.7 MB read + 154.8 MB written per launch = the algorithmic bytes
+    # same capture file (conv2_ss): dram 231.6 MB read + 152.7 MB written per launch (ncu replay, cold L2 except the lines
+    # the preceding conv1 left there) — below the 402.7 MB of algorithmic bytes, i.e. no wasted re-reads.
+    # in_step_us_ncu / share_of_step_ncu: the same kernel inside the real forward, from the committed launch list
+    # profiles/r01c_launches_infer_32x128.csv (serialised, cold caches: 211 launches x 85.4 us = 64.3 % of the step).
     conv2 = {"bound": "hbm", "kernel": "conv3x3_c64_tc_kernel<64, scale+skip> (RCAB conv2 + attention scale + residual)",
              "achieved": round(gbs, 1), "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(gbs / pk["hbm_gbs"], 4),
-             "traffic": 406514688 if bc == 32 else None, "launch_us": round(ms2 * 1e3, 3), "images_per_launch": bc,
+             "traffic": 384265728 if bc == 32 else None, "launch_us": round(ms2 * 1e3, 3), "images_per_launch": bc,
+             "in_step_us_ncu": 85.4 if bc == 32 else None, "share_of_step_ncu": 0.643 if bc == 32 else None,
              "algorithmic_bytes_per_launch": byt, "tensor_tflops": round(flops / (ms2 / 1e3) / 1e12, 1),
              "peak_source": pk["source"] + " (STREAM-style copy)"}
     return conv2, conv1
