@@ -137,9 +137,18 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 }  // namespace
 
+// Epilogues that one group of four warps cannot drain at the MMA pace get a second group (warps 10-13) working on the
+// alternate accumulator: the fp32 stream epilogue, and the ones with per-row channel sums (62 shuffles per thread and
+// row) or a global-memory mask read per pixel.
+template <int EPI, int INMODE>
+constexpr bool two_epilogue_groups() {
+  return INMODE == IN_TMA &&
+         (EPI == EPI_SCALE_SKIP || EPI == EPI_RELU_STATS || EPI == EPI_BIAS_POOL || EPI == EPI_RELU_MASK);
+}
+
 template <int EPI, int INMODE>
 constexpr int conv_threads() {
-  return INMODE == IN_FUSED ? kThreadsFused : ((EPI == EPI_SCALE_SKIP || EPI == EPI_RELU_STATS) ? kThreadsTwoEpi : kThreads);
+  return INMODE == IN_FUSED ? kThreadsFused : (two_epilogue_groups<EPI, INMODE>() ? kThreadsTwoEpi : kThreads);
 }
 
 template <int NT, int EPI, int INMODE>
@@ -389,7 +398,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           mbar_arrive(&empty[slot]);
         }
       }
-    } else if (warp >= 10 && !((EPI == EPI_SCALE_SKIP || EPI == EPI_RELU_STATS) && INMODE == IN_TMA)) {
+    } else if (warp >= 10 && !two_epilogue_groups<EPI, INMODE>()) {
       // ===================== fused input transform (IN_FUSED only; warps 10..17) =====================
       if constexpr (INMODE == IN_FUSED) {
         grid_dep_wait();
@@ -512,7 +521,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       // 3 us per row against 1.1 us of MMAs), so two groups take alternate rows (= alternate accumulators).
       // EPI_RELU_STATS: the per-row channel sums (62 shuffles per thread and row) take one group 1.76 us per row
       // against 1.3 us of the MMA pipeline (conv1 48.7 us vs 38 us without the statistics), same remedy.
-      constexpr bool kTwoEpi = (EPI == EPI_SCALE_SKIP || EPI == EPI_RELU_STATS) && INMODE == IN_TMA;
+      constexpr bool kTwoEpi = two_epilogue_groups<EPI, INMODE>();
       constexpr int kEpiGroups = kTwoEpi ? 2 : 1;
       const int egrp = (kTwoEpi && warp >= 10) ? 1 : 0;
       const int q = warp & 3;          // TMEM lane quarter this warp may read
