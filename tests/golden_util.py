@@ -18,6 +18,15 @@ def grad_golden_names():
     return sorted(f[6:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f.startswith("grads_"))
 
 
+# networks that have gradient fingerprints (the oracle's backward is pinned for them) but no training path in the B200
+# library yet: pixel attention, Q-SAN / SAN, Q-HAN / HAN.  Training them must raise NotImplementedError.
+NO_TRAINING_PATH = ("qrcan_pa_selective", "qsan_g2b2", "qhan_b1", "san_g2b2", "han_b1")
+
+
+def trainable_grad_golden_names():
+    return [n for n in grad_golden_names() if n not in NO_TRAINING_PATH]
+
+
 def load_grad_golden(name):
     """(loss, {parameter name: (norm, projections[8])}) of the reference's own backward pass"""
     z = np.load(os.path.join(GOLDEN_DIR, "grads_" + name + ".npz"))

@@ -8,7 +8,8 @@ import torch
 import torch.nn.functional as F
 
 from deepfir_b200 import _lib
-from tests.golden_util import case_tensors, grad_golden_names, load_golden, oracle_grads
+from tests.golden_util import (NO_TRAINING_PATH, case_tensors, load_golden, oracle_grads,
+                               trainable_grad_golden_names)
 from tests.gpu_util import bf16_round, lib, nhwc_bf16, nhwc_f32, stream, sync
 
 pytestmark = pytest.mark.gpu
@@ -170,7 +171,7 @@ def _step_grads(net, x, meta, y):
     return float(loss.detach()), out.detach().cpu(), {k: p.grad.detach().cpu().clone() for k, p in net.named_parameters()}
 
 
-@pytest.mark.parametrize("name", grad_golden_names())
+@pytest.mark.parametrize("name", trainable_grad_golden_names())
 def test_train_step_fp32_gradients_match_oracle(name):
     """per-parameter ||g - g_ref|| / ||g_ref|| <= 1e-3 in fp32 mode (g_ref = autograd through the oracle,
     itself pinned to the reference's loss.backward() by tests/test_train_cpu.py)"""
@@ -186,7 +187,7 @@ def test_train_step_fp32_gradients_match_oracle(name):
         assert err <= 1e-3 * float(ref[k].norm()) + 1e-6 * gmax, (k, err, float(ref[k].norm()))
 
 
-@pytest.mark.parametrize("name", [n for n in grad_golden_names() if "f256" not in n])
+@pytest.mark.parametrize("name", [n for n in trainable_grad_golden_names() if "f256" not in n])
 def test_train_step_bf16_gradients_close_to_oracle(name):
     """tensor-core path: bf16 operands (activations, weights and gradients), fp32 accumulation and fp32 gradient
     stream.  Bar: loss within 1e-3 relative, every gradient within 4e-2 of its norm (+ a floor of 1e-3 of the largest
@@ -400,3 +401,14 @@ def test_full_depth_bf16_gradients_stay_aligned_with_the_reference():
             worst_cos, worst_rel = min(worst_cos, cos), max(worst_rel, rel)
         print("%s full depth: worst cosine %.6f, worst relative error %.3e" % (precision, worst_cos, worst_rel))
         assert worst_cos >= cos_min and worst_rel <= rel_max, (precision, worst_cos, worst_rel)
+
+
+def test_training_a_network_without_backward_kernels_fails_loudly():
+    """pixel attention has forward kernels only: a training step must raise NotImplementedError, not fall back to
+    anything (its gradient fingerprints in tests/golden/ pin the oracle's backward for the kernels to come)"""
+    assert "qrcan_pa_selective" in NO_TRAINING_PATH
+    _, info = load_golden("qrcan_pa_selective")
+    net, sd, x, meta = _build(info, "bf16")
+    with pytest.raises(NotImplementedError):
+        out = net(x.cuda(), meta.cuda())
+        F.l1_loss(out, torch.zeros_like(out)).backward()
