@@ -57,6 +57,9 @@ int dfir_check_device(void);
 /* Synchronises the device and copies the 8-word pipeline watchdog record to out8_host ({0,...} = no barrier wait
  * ever timed out; else {1, wait tag, blockIdx, threadIdx, parity, barrier lo, barrier hi, 0}); optionally clears it. */
 int dfir_debug_watchdog(unsigned int* out8_host, int reset);
+/* Synchronises the device and copies the pipeline time-stamp record of the conv kernel ([16 event kinds][64 rows] SM clock
+ * values of one CTA) to out1024_host.  Only a `make PROBES=1` build with DFIR_DEBUG_PROBE bit 32768 fills it. */
+int dfir_debug_trace(unsigned long long* out1024_host);
 
 /* ------------------------------------------------------------------------------------------------
  * weight packing (derived caches of the fp32 OIHW nn.Parameters; never serialised)

@@ -378,6 +378,7 @@ const char* dfir_error_string(int code) {
 }
 
 int dfir_debug_watchdog(unsigned int* out8_host, int reset) { return debug_watchdog(out8_host, reset); }
+int dfir_debug_trace(unsigned long long* out1024_host) { return debug_trace(out1024_host); }
 
 int dfir_check_device(void) {
   int dev = 0;

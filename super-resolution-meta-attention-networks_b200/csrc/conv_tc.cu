@@ -66,6 +66,22 @@
 namespace dfir {
 
 __device__ unsigned int g_dfir_progress[16];
+// `make PROBES=1` + DFIR_DEBUG_PROBE bit 32768: clock64 time stamps of one CTA's pipeline events, [16 kinds][64 rows]
+// (dfir_debug_trace reads them back; tools/trace_conv.py prints who waits for whom).
+__device__ unsigned long long g_dfir_trace[16 * 64];
+#ifdef DFIR_PROBES
+#define DFIR_TRACE(kind, idx)                                                                   \
+  do {                                                                                          \
+    if (trace_on && lane == 0 && (idx) >= 0 && (idx) < 64) g_dfir_trace[(kind) * 64 + (idx)] = clock64(); \
+  } while (0)
+#define DFIR_TRACE1(kind, idx)                                                                  \
+  do {                                                                                          \
+    if (trace_on && (idx) >= 0 && (idx) < 64) g_dfir_trace[(kind) * 64 + (idx)] = clock64();   \
+  } while (0)
+#else
+#define DFIR_TRACE(kind, idx) do { } while (0)
+#define DFIR_TRACE1(kind, idx) do { } while (0)
+#endif
 
 using namespace ptx;
 
@@ -108,7 +124,7 @@ struct SmemLayout {
   static_assert(off_cap + kCaStageFloats * 4 <= off_stage + 2 * kStageBytes, "prologue scratch must fit the staging tiles");
   static constexpr int off_svec = off_pool + 8 * 64 * 4;                         // s of the images of this band
   static constexpr int off_bars = off_svec + kMaxBandImages * 64 * 4;
-  static constexpr int n_bars = 2 * kSlots + 2 * kARows + 2 * kAcc + 1;
+  static constexpr int n_bars = 2 * kSlots + kARows + 2 * kAcc + 1;
   static constexpr int off_tmem = off_bars + n_bars * 8;
   static constexpr int total = off_tmem + 16;
 };
@@ -171,11 +187,11 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::off_bars);
   uint64_t* full = bars;                                   // ring slot filled      (producer/transform -> loaders)
   uint64_t* empty = full + kSlots;                         // ring slot drained     (loaders -> producer/transform)
-  uint64_t* afull = empty + kSlots;                        // TMEM A row slot ready (loaders -> MMA)
-  uint64_t* aempty = afull + kARows;                       // TMEM A row slot free  (MMA commit -> loaders)
+  uint64_t* aempty = empty + kSlots;                       // TMEM A row slot free  (MMA commit -> loaders)
   uint64_t* tfull = aempty + kARows;                       // accumulator ready     (MMA commit -> epilogue)
-  uint64_t* tempty = tfull + kAcc;                         // accumulator drained   (epilogue -> MMA)
-  uint64_t* wbar = tempty + kAcc;                          // weights landed
+  uint64_t* go = tfull + kAcc;                             // output row may start: its bottom A row is in TMEM (4 loader
+                                                           // warps) and its accumulator is drained (4 epilogue warps)
+  uint64_t* wbar = go + kAcc;                              // weights landed
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + L::off_tmem);
 
   const int warp = threadIdx.x >> 5;
@@ -200,13 +216,10 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       mbar_init(&full[i], INMODE == IN_FUSED ? 128 : 1);
       mbar_init(&empty[i], 4);
     }
-    for (int i = 0; i < kARows; ++i) {
-      mbar_init(&afull[i], 4);
-      mbar_init(&aempty[i], 1);
-    }
+    for (int i = 0; i < kARows; ++i) mbar_init(&aempty[i], 1);
     for (int i = 0; i < kAcc; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&go[i], 8);
     }
     mbar_init(wbar, 1);
     fence_barrier_init();
@@ -245,9 +258,10 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   const bool exp_no_pf = (a.debug_probe & 2048) != 0;      // no L2 prefetch of the skip rows
   const bool exp_no_tile = (a.debug_probe & 4096) != 0;    // scale+skip epilogue: TMEM reads and barriers only
   const bool exp_no_pass = (a.debug_probe & 8192) != 0;    // scale+skip epilogue: no coalesced pass
+  const bool trace_on = (a.debug_probe & 32768) != 0 && blockIdx.x == gridDim.x / 2;
 #else
   constexpr bool probe = false, exp_skip_store = false, exp_one_copy = false, exp_no_copy = false, exp_no_epi = false,
-                 exp_n192 = false, exp_n128 = false, exp_no_skipld = false, exp_no_f32st = false, exp_no_bfst = false,
+                 exp_no_skipld = false, exp_no_f32st = false, exp_no_bfst = false,
                  exp_no_pf = false, exp_no_tile = false, exp_no_pass = false;
 #endif
 
@@ -259,104 +273,123 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         bulk_load_1d(wsm, a.wpacked, L::w_bytes, wbar);  // weights are not produced by the previous kernel
         grid_dep_wait();
         if constexpr (INMODE == IN_TMA) {
+          int col = pr_first / Hp, yy = pr_first % Hp - 1;  // advanced without divisions
+          int cseg = col % nseg, cimg = col / nseg;
           for (int n = 0; n <= n_last; ++n) {
-            const int pr = pr_first + n;
             const int slot = n % kSlots;
             if (probe) g_dfir_progress[0] = n + 1;
             mbar_wait(&empty[slot], ((n / kSlots) & 1) ^ 1, 1);
-            const int col = pr / Hp;
-            const int yy = pr % Hp - 1;
+            DFIR_TRACE(0, n);  // producer: ring slot free, TMA load of row n issued
             mbar_arrive_expect_tx(&full[slot], kRowBytes);
             if (a.use_hints)
-              tma_load_4d_hint(ring + slot * kSlotBytes, &tmap_in, &full[slot], a.cin_off, (col % nseg) * 128 - 1, yy,             col / nseg, a.pol_in);
+              tma_load_4d_hint(ring + slot * kSlotBytes, &tmap_in, &full[slot], a.cin_off, cseg * 128 - 1, yy, cimg, a.pol_in);
             else
-              tma_load_4d(ring + slot * kSlotBytes, &tmap_in, &full[slot], a.cin_off, (col % nseg) * 128 - 1, yy,
-                        col / nseg);
+              tma_load_4d(ring + slot * kSlotBytes, &tmap_in, &full[slot], a.cin_off, cseg * 128 - 1, yy, cimg);
+            if (++yy > H) {  // past the bottom pad row: next column segment / image
+              yy = -1;
+              if (++cseg == nseg) {
+                cseg = 0;
+                ++cimg;
+              }
+            }
           }
         }
       }
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
-      // The whole warp runs the loop so that control flow and address arithmetic stay warp-uniform; only the
-      // elected lane issues tcgen05 instructions.
-      const bool leader = elect_one();
-      constexpr uint32_t idesc = make_idesc_bf16_f32(128, NT);
-      const uint64_t db_base = make_sw128_kmajor_desc(smem_u32(wsm), 1024, 0);
-      mbar_wait(wbar, 0, 2);
-      int released = 0;  // next A-row sequence index to hand back to the loaders
-      for (int g = g0, it = 0; g < g1; ++g, ++it) {
-        const int nc = padded(g) - pr_first;  // sequence index of the centre row
-        const int nc_next = (g + 1 < g1) ? padded(g + 1) - pr_first : n_last + 2;
-        const int acc = it % kAcc;
-        if (probe) g_dfir_progress[1] = it + 1;
-        mbar_wait(&tempty[acc], (((it / kAcc) & 1) ^ 1), 3);
-        if (probe) g_dfir_progress[2] = it + 1;
-        uint32_t a_col[3];
+      // Measured (tools/mma_probe.cu, tools/trace_conv.py; profiles/r02_mma_issue.md): a cta_group::1 TS-mode 128x64x16
+      // MMA stream runs at its 32-clk floor, but the MMA queue is only ~2 instructions deep, so every clock the issuing
+      // thread spends on anything else (an mbarrier test costs 90-230 clk even when the phase completed long ago, a
+      // divergent-branch reconvergence, integer divisions, bursts of R2UR) is tensor-pipe idle time.  Hence: ONE elected
+      // thread runs the whole loop, one mbarrier wait per output row (`go[acc]`: the row's bottom A row has been copied
+      // into tensor memory by the four loader warps AND the accumulator has been drained by the four epilogue warps that
+      // own it: 8 arrivals), the 36 MMAs and the two commits of a row in one basic block, no division.
+      if (elect_one()) {
+        constexpr uint32_t idesc = make_idesc_bf16_f32(128, NT);
+        const uint64_t db_base = make_sw128_kmajor_desc(smem_u32(wsm), 1024, 0);
+        mbar_wait(wbar, 0, 2);
+        int y_cur = g0 % H;
+        int nc = padded(g0) - pr_first;  // sequence index of the centre row
+        for (int g = g0, it = 0; g < g1; ++g, ++it) {
+          const bool img_end = y_cur == H - 1;  // the next output row starts a new image (or column segment)
+          const int acc = it & 1;
+          const uint32_t d_tmem = tmem_base + acc * NT;
+          uint32_t a_col[3];
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-          const int n = nc - 1 + dy;
-          mbar_wait(&afull[n % kARows], (n / kARows) & 1, 4);
-          a_col[dy] = tmem_base + kAColBase + (n % kARows) * kAColsPerRow;
-        }
-        tcgen05_fence_after();
-        if (probe) g_dfir_progress[3] = it + 1;
-        if (leader && (exp_n192 || exp_n128)) {
-          if constexpr (NT == 64) {
-            constexpr uint32_t id192 = make_idesc_bf16_f32(128, 192);
-            constexpr uint32_t id128 = make_idesc_bf16_f32(128, 128);
-            const int reps = exp_n192 ? 1 : 2;
-            for (int rpt = 0; rpt < reps; ++rpt)
+          for (int dy = 0; dy < 3; ++dy) a_col[dy] = tmem_base + kAColBase + ((nc - 1 + dy) & (kARows - 1)) * kAColsPerRow;
+          uint64_t* const rel_bar = &aempty[(nc - 1) & (kARows - 1)];
+          if (probe) g_dfir_progress[1] = it + 1;
+          DFIR_TRACE1(4, it);  // MMA thread: top of row
+          mbar_wait(&go[acc], (it >> 1) & 1, 3);
+          tcgen05_fence_after();
+          DFIR_TRACE1(5, it);  // MMA thread: row may start
+#ifdef DFIR_PROBES
+          if (exp_n192 || exp_n128) {
+            if constexpr (NT == 64) {
+              constexpr uint32_t id192 = make_idesc_bf16_f32(128, 192);
+              constexpr uint32_t id128 = make_idesc_bf16_f32(128, 128);
+              const int reps = exp_n192 ? 1 : 2;
+              for (int rpt = 0; rpt < reps; ++rpt)
 #pragma unroll
-              for (int dx = 0; dx < 3; ++dx)
+                for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const uint64_t db = db_base + static_cast<uint32_t>(((dx * 3) * NT * 128 + k * 32) >> 4);
+                    umma_f16_ts(tmem_base, a_col[1] + dx * 32 + k * 8, db, exp_n192 ? id192 : id128, 1u);
+                  }
+              if (!exp_n192)
+                for (int k = 0; k < 6; ++k)
+                  umma_f16_ts(tmem_base, a_col[1] + k * 8, db_base + static_cast<uint32_t>((k * 32) >> 4), id128, 1u);
+            }
+            umma_commit(rel_bar);
+          } else
+#endif
+          {
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  const uint64_t db = db_base + static_cast<uint32_t>(((dx * 3) * NT * 128 + k * 32) >> 4);
-                  umma_f16_ts(tmem_base, a_col[1] + dx * 32 + k * 8, db, exp_n192 ? id192 : id128, 1u);
+                  const uint64_t db = db_base + static_cast<uint32_t>(((dy * 3 + dx) * NT * 128 + k * 32) >> 4);
+                  umma_f16_ts(d_tmem, a_col[dy] + dx * 32 + k * 8, db, idesc, (dy | dx | k) != 0 ? 1u : 0u);
                 }
-            if (!exp_n192)
-              for (int k = 0; k < 6; ++k)
-                umma_f16_ts(tmem_base, a_col[1] + k * 8, db_base + static_cast<uint32_t>((k * 32) >> 4), id128, 1u);
-            for (int rel = released; rel <= nc - 1; ++rel) umma_commit(&aempty[rel % kARows]);
-            umma_commit(&tfull[acc]);
-            for (int rel = (released > nc ? released : nc); rel <= nc_next - 2; ++rel) umma_commit(&aempty[rel % kARows]);
-          }
-        } else if (leader) {
-          const uint32_t d_tmem = tmem_base + acc * NT;
-#pragma unroll
-          for (int dy = 0; dy < 3; ++dy) {
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t db = db_base + static_cast<uint32_t>(((dy * 3 + dx) * NT * 128 + k * 32) >> 4);
-                umma_f16_ts(d_tmem, a_col[dy] + dx * 32 + k * 8, db, idesc, (dy | dx | k) != 0 ? 1u : 0u);
               }
-            }
-            if (dy == 0) {
-              // the top row (and anything older) is dead as soon as the dy = 0 taps have executed: hand its TMEM
-              // slot back now so that the loaders refill it while the remaining 24 MMAs of this row run
-              for (int rel = released; rel <= nc - 1; ++rel) umma_commit(&aempty[rel % kARows]);
+              // the top row is dead as soon as the dy = 0 taps have executed: hand its TMEM slot back now so that the
+              // loaders refill it while the remaining 24 MMAs of this row run
+              if (dy == 0) umma_commit(rel_bar);
             }
           }
           umma_commit(&tfull[acc]);
-          // at an image boundary the next centre also skips the last row and the bottom pad row of the finished
-          // image — keeping them would deadlock the 4-slot TMEM row ring
-          for (int rel = (released > nc ? released : nc); rel <= nc_next - 2; ++rel) umma_commit(&aempty[rel % kARows]);
+          DFIR_TRACE1(7, it);  // MMA thread: 36 MMAs + commits issued
+          if (img_end || g + 1 == g1) {
+            // at an image boundary the next centre also skips the last row and the bottom pad row of the finished
+            // image — keeping them would deadlock the 4-slot TMEM row ring
+            umma_commit(&aempty[nc & (kARows - 1)]);
+            umma_commit(&aempty[(nc + 1) & (kARows - 1)]);
+          }
+          nc += img_end ? 3 : 1;
+          y_cur = img_end ? 0 : y_cur + 1;
         }
-        released = nc > released ? nc : released;
-        released = nc_next - 1 > released ? nc_next - 1 : released;
-        __syncwarp();
       }
+      __syncwarp();
     } else if (warp >= 6 && warp < 10) {
       // ===================== A loaders: smem ring row -> 3 dx-shifted copies in TMEM =====================
       const int q = warp & 3;        // TMEM lane quarter this warp may access (warps 6,7,8,9 -> 2,3,0,1)
       const int m = q * 32 + lane;   // output pixel = TMEM lane
+      // Row n is the LAST A row some output row waits for (its bottom row) iff it is at least the third row of its
+      // padded image and of this band; the rows complete in order, so that output row's `go` barrier gets this warp's
+      // arrival here and nothing else has to be signalled to the MMA thread.
+      int p_img = pr_first % Hp;     // padded row index of ring row n inside its image: 0 = top pad row .. H + 1 = bottom pad
+      int n_out = 0;                 // output rows of this band signalled so far
       for (int n = 0; n <= n_last; ++n) {
         const int slot = n % kSlots;
         const int as = n % kARows;
         if (probe) g_dfir_progress[4 + q] = n + 1;
         mbar_wait(&full[slot], (n / kSlots) & 1, 5);
+        if (q == 0) DFIR_TRACE(1, n);  // loader: row n has landed in the ring
         mbar_wait(&aempty[as], ((n / kARows) & 1) ^ 1, 6);
+        if (q == 0) DFIR_TRACE(2, n);  // loader: TMEM row slot free
         tcgen05_fence_after();
         const uint8_t* srow = ring + slot * kSlotBytes;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kAColBase + as * kAColsPerRow;
@@ -391,12 +424,15 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         }
         }
         tmem_st_wait();
+        if (q == 0) DFIR_TRACE(3, n);  // loader: the three TMEM copies of row n are complete
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&afull[as]);
+          if (n >= 2 && p_img >= 2) mbar_arrive(&go[n_out & 1]);
           mbar_arrive(&empty[slot]);
         }
+        if (n >= 2 && p_img >= 2) ++n_out;
+        if (++p_img == Hp) p_img = 0;
       }
     } else if (warp >= 10 && !two_epilogue_groups<EPI, INMODE>()) {
       // ===================== fused input transform (IN_FUSED only; warps 10..17) =====================
@@ -527,6 +563,15 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       const int q = warp & 3;          // TMEM lane quarter this warp may read
       const int m = q * 32 + lane;     // pixel within the 128-px row segment
       const int et = egrp ? threadIdx.x - 320 : threadIdx.x - 64;  // 0..127 within the group
+      // both accumulators start out drained: the first use of each must not wait for an epilogue arrival on `go`
+      if (lane == 0) {
+        if (kEpiGroups == 1) {
+          mbar_arrive(&go[0]);
+          mbar_arrive(&go[1]);
+        } else {
+          mbar_arrive(&go[egrp]);
+        }
+      }
       const int rows_img_e = nseg * H;
       const int bimg_first = g0 / rows_img_e;
       int cur_img = -1;
@@ -693,11 +738,21 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       if constexpr (kTwoEpi && EPI == EPI_SCALE_SKIP) {
         if (a.epi_stats) named_bar_sync(6, 256);  // the attention vectors (svec_s) of both groups are complete
       }
-      for (int g = g0 + egrp, it = egrp; g < g1; g += kEpiGroups, it += kEpiGroups) {
-        const int col = g / H;
-        const int y = g % H;
-        const int b = col / nseg;
-        const int seg = col % nseg;
+      // (col, y, b, seg) of output row g, advanced without integer divisions (they cost ~130 clk each per row)
+      int col = (g0 + egrp) / H, y = (g0 + egrp) % H;
+      int b = col / nseg, seg = col % nseg;
+      auto next_row = [&]() {
+        y += kEpiGroups;
+        while (y >= H) {
+          y -= H;
+          ++col;
+          if (++seg == nseg) {
+            seg = 0;
+            ++b;
+          }
+        }
+      };
+      for (int g = g0 + egrp, it = egrp; g < g1; g += kEpiGroups, it += kEpiGroups, next_row()) {
         const int x = seg * 128 + m;
         const bool valid = x < a.W;
         const int acc = it % kAcc;
@@ -755,12 +810,14 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             }
           }
         }
+        if (q == 0) DFIR_TRACE(8 + 3 * egrp, it >> (kTwoEpi ? 1 : 0));  // epilogue: waiting for the accumulator
         mbar_wait(&tfull[acc], (it / kAcc) & 1, 8);
+        if (q == 0) DFIR_TRACE(9 + 3 * egrp, it >> (kTwoEpi ? 1 : 0));  // epilogue: accumulator complete
         tcgen05_fence_after();
         if (exp_no_epi) {
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (lane == 0) mbar_arrive(&go[acc]);
           continue;
         }
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * NT;
@@ -771,7 +828,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           tmem_ld_wait();
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (lane == 0) mbar_arrive(&go[acc]);
           if (valid) {  // fp32 NCHW output, a.cout real channels (<= NT)
             const size_t plane = static_cast<size_t>(a.H) * a.W;
             float* o = a.out_f32 + (static_cast<size_t>(b) * a.cout) * plane + static_cast<size_t>(y) * a.W + x;
@@ -883,7 +940,8 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           tmem_ld_wait();
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);  // accumulator back to the MMA warp
+          if (lane == 0) mbar_arrive(&go[acc]);  // accumulator back to the MMA warp
+          if (q == 0) DFIR_TRACE(10 + 3 * egrp, it >> 1);
           named_bar_sync(bar_b, 128);
           pass(0);
           issue_skip(g + kEpiGroups, 0);  // this thread's half-0 slots are free again: next row of this group
@@ -892,6 +950,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           named_bar_sync(bar_b, 128);
           pass(1);
           issue_skip(g + kEpiGroups, 1);
+          if (q == 0) DFIR_TRACE(14 + egrp, it >> 1);
         } else {
           // one group: the two staging buffers alternate; two groups: it & 1 == egrp, each group owns one buffer
           const int sb = it & 1;
@@ -911,7 +970,8 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             if (h == 1) {  // accumulator fully read: hand it back to the MMA warp
               tcgen05_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&tempty[acc]);
+              if (lane == 0) mbar_arrive(&go[acc]);
+              if (q == 0) DFIR_TRACE(10 + 3 * egrp, it >> (kTwoEpi ? 1 : 0));
             }
             float v[32];
 #pragma unroll
@@ -1004,6 +1064,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               a.pool_rows[(static_cast<size_t>(col) * a.H + y) * 64 + et] = s;
             }
           }
+          if (q == 0) DFIR_TRACE(14 + egrp, it >> (kTwoEpi ? 1 : 0));
         }
       }
       if (EPI != EPI_TAIL_NCHW && EPI != EPI_SCALE_SKIP && et == 0) tma_store_wait<0>();
@@ -1079,6 +1140,12 @@ static int launch_one(const CUtensorMap& tin, const CUtensorMap& tout, const Con
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, tin, tout, a) == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
+}
+
+int debug_trace(unsigned long long* out1024) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return DFIR_ERR_CUDA;
+  return cudaMemcpyFromSymbol(out1024, g_dfir_trace, sizeof(unsigned long long) * 16 * 64) == cudaSuccess ? DFIR_OK
+                                                                                                           : DFIR_ERR_CUDA;
 }
 
 int debug_watchdog(unsigned int* out8, int reset) {

@@ -98,6 +98,7 @@ struct ConvTcDesc {  // host-side launch description
 
 int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream);
 int debug_watchdog(unsigned int* out8, int reset);
+int debug_trace(unsigned long long* out1024);
 
 // ---- SIMT kernels (simt.cu)
 struct AttnParams {  // one RCAB's channel-attention parameters (fp32, device pointers into the packed blob)

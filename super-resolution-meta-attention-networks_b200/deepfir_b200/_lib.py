@@ -66,6 +66,7 @@ PROTOTYPES = {
     "dfir_error_string": (C.c_char_p, [_i]),
     "dfir_check_device": (_i, []),
     "dfir_debug_watchdog": (_i, [C.POINTER(C.c_uint * 8), _i]),
+    "dfir_debug_trace": (_i, [C.POINTER(C.c_ulonglong * 1024)]),
     "dfir_pack_conv3x3_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "dfir_pack_conv3x3_f32": (_i, [_vp, _vp, _i, _i, _vp]),
     "dfir_conv3x3_c64": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _ll, _ll, _ll, _vp, _vp, _vp, _i, _vp]),

@@ -1,0 +1,66 @@
+"""Pipeline trace of one CTA of the conv kernel (needs `make PROBES=1`): python tools/trace_conv.py [conv1|stats|ss]
+Prints, per row, when each role reached its events (SM clocks relative to the first event) and the row period."""
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "super-resolution-meta-attention-networks_b200"))
+os.environ["DFIR_DEBUG_PROBE"] = str(32768 | int(os.environ.get("EXTRA_PROBE", "0")))
+import torch
+from deepfir_b200 import _lib
+
+lib = _lib.load_library()
+dev = torch.device("cuda")
+st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
+mode = (sys.argv[1:] or ["conv1"])[0]
+bc, LR = int(os.environ.get("BC", "32")), 128
+wp = torch.empty(9 * 64 * 128, dtype=torch.uint8, device=dev)
+w = (torch.randn(64, 64, 3, 3, device=dev) / 24).contiguous()
+bias = torch.zeros(64, device=dev)
+_lib.check(lib.dfir_pack_conv3x3_bf16(w.data_ptr(), wp.data_ptr(), 64, 64, 64, 0, 1, st()), "pack")
+a = torch.randn(bc, LR, LR, 64, device=dev).to(torch.bfloat16)
+b = torch.empty_like(a)
+x = torch.randn(bc, LR, LR, 64, device=dev)
+pool = torch.empty(bc, LR, 64, device=dev); cf = torch.empty(bc, LR, 64, device=dev); cl = torch.empty(bc, LR, 64, device=dev)
+sv = torch.rand(bc, 64, device=dev)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def launch():
+    if mode == "conv1":
+        _lib.check(lib.dfir_conv3x3_c64(a.data_ptr(), 64, 0, wp.data_ptr(), bias.data_ptr(), bc, LR, LR, 1, 64, b.data_ptr(),
+                                        128, LR * 128, LR * LR * 128, None, None, pool.data_ptr(), 0, st()), "conv")
+    elif mode == "stats":
+        _lib.check(lib.dfir_conv3x3_c64_stats(a.data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR, b.data_ptr(),
+                                              pool.data_ptr(), cf.data_ptr(), cl.data_ptr(), st()), "c1")
+    else:
+        _lib.check(lib.dfir_conv3x3_c64_scale_skip(a.data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR, sv.data_ptr(),
+                                                   x.data_ptr(), x.data_ptr(), b.data_ptr(), None, None, None, 0, None, 4,
+                                                   10, 10, None, None, st()), "ss")
+
+
+for _ in range(3):
+    launch()
+if os.environ.get("FLUSH", "1") == "1":
+    flush.zero_()
+torch.cuda.synchronize()
+launch()
+buf = (C.c_ulonglong * 1024)()
+_lib.check(lib.dfir_debug_trace(C.byref(buf)), "trace")
+tr = [[buf[k * 64 + i] for i in range(64)] for k in range(16)]
+t0 = min(v for row in tr for v in row if v)
+names = ["tma_issue", "ld_full", "ld_aempty", "ld_done", "mma_top", "mma_24", "mma_waited", "mma_36", "e0_wait", "e0_tfull",
+         "e0_release", "e1_wait", "e1_tfull", "e1_release", "e0_end", "e1_end"]
+if mode == "conv1":
+    names[11:14] = ["mma_1", "mma_12", "mma_commit"]
+    names[15] = "mma_tfullc"
+print("mode %s bc %d (SM clocks relative to the first event; 0 = not recorded)" % (mode, bc))
+print("row " + " ".join("%10s" % n for n in names))
+for i in range(34):
+    print("%3d " % i + " ".join("%10d" % (tr[k][i] - t0 if tr[k][i] else 0) for k in range(16)))
+for k in (0, 3, 4, 7):
+    v = [tr[k][i] for i in range(4, 27) if tr[k][i]]
+    if len(v) > 2:
+        print("%-10s mean period over rows 4..26: %.0f clk" % (names[k], (v[-1] - v[0]) / (len(v) - 1)))
