@@ -272,6 +272,14 @@ int main(int argc, char** argv) {
   unsigned long long* dout = nullptr;
   cudaMalloc(&dout, 148 * 16 + 148 * 8);
   const int only_ld = argc > 2 ? atoi(argv[2]) : 0;
+  if (only_ld == 2) {  // issue cost: tiny N keeps the tensor pipe nearly idle, so clk/MMA = cost of issuing one UTCHMMA
+    run<1, true, 8>("cg1 TS N=8 (issue cost)", 148, iters, 0, dout);
+    run<1, true, 16>("cg1 TS N=16", 148, iters, 0, dout);
+    run<1, true, 32>("cg1 TS N=32", 148, iters, 0, dout);
+    run<1, true, 64>("cg1 TS N=64", 148, iters, 0, dout);
+    run<1, true, 192>("cg1 TS N=192", 148, iters, 0, dout);
+    return 0;
+  }
   if (only_ld) {
     for (int lm : {0, 3, 4}) {
       run<1, true, 64>("cg1 TS N=64", 148, iters, lm, dout);
