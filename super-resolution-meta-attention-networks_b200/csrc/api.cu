@@ -2,6 +2,8 @@
 #include "kernels.h"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 using namespace dfir;
 
@@ -129,9 +131,19 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
   const uint8_t* cw = reinterpret_cast<const uint8_t*>(n->conv_w_bf16);
   const long long pixB = C * 2, rowB = static_cast<long long>(W) * C * 2, imgB = rowB * H;
 
+  // Residual-stream format of the default (pool-by-linearity) schedule when the whole network runs in one call: two bf16
+  // planes, x = hi + lo (16 significant bits; the hi plane is the conv operand).  conv2 then moves 10 instead of 12 bytes
+  // per element.  The lo planes live in the memory of the fp32 stream buffers.  Everything that exposes the fp32 stream
+  // (staged execution, per-group copies, the other schedules) keeps the fp32 format; DFIR_STREAM=f32 forces it.
+  static const bool hl_allowed = getenv("DFIR_STREAM") == nullptr || strcmp(getenv("DFIR_STREAM"), "f32") != 0;
+  const int sched0 = n->pa_blob != nullptr ? 2 : n->schedule;
+  const bool hl = hl_allowed && sched0 == 0 && sa.stages == ST_ALL && sa.group_out == nullptr && !sa.from_xa;
+  __nv_bfloat16* const Hlo = reinterpret_cast<__nv_bfloat16*>(w.Hh);
+  __nv_bfloat16* const XAlo = reinterpret_cast<__nv_bfloat16*>(w.XA);
+  __nv_bfloat16* const XBlo = reinterpret_cast<__nv_bfloat16*>(w.XB);
   if (sa.stages & ST_HEAD)
-    DFIR_TRY(head_conv(x + static_cast<size_t>(b0) * n->in_feats * H * W, n->head_w_f32, n->head_b, w.Hh, w.Hbf, Bc,
-                       n->in_feats, H, W, C, st));
+    DFIR_TRY(head_conv(x + static_cast<size_t>(b0) * n->in_feats * H * W, n->head_w_f32, n->head_b, hl ? nullptr : w.Hh, w.Hbf,
+                       Bc, n->in_feats, H, W, C, st, hl ? Hlo : nullptr));
   const size_t feat_bytes = static_cast<size_t>(Bc) * H * W * C * 4;
 
   // One launch description shared by all trunk convs; the lambdas below fill in what differs.
@@ -191,8 +203,13 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
         const int w2 = g * per_group + 2 * b + 1;
         // conv2 + attention scale + residual: x_{b+1} = (conv(t) + b) * s + x_b (fp32, in place after block 0);
         // s is evaluated from the statistics of t inside the kernel while its pipeline fills.
-        ConvTcDesc c2 = base(w2, EPI_SCALE_SKIP);
+        ConvTcDesc c2 = base(w2, hl ? EPI_SCALE_SKIP_HL : EPI_SCALE_SKIP);
         c2.in_bf16 = w.T; c2.skip_f32 = b == 0 ? skip32 : w.XB; c2.out_f32 = w.XB; c2.out_bf16 = w.XBbf;
+        if (hl) {
+          c2.skip_hi = b == 0 ? gin : w.XBbf;
+          c2.skip_lo = b == 0 ? (from_head ? Hlo : XAlo) : XBlo;
+          c2.out_lo = XBlo;
+        }
         if (has_ca && sched == 3) {
           // schedule 3: the attention vector comes from its own small kernel instead of conv2's prologue
           DFIR_TRY(ca_from_stats(w.pool, w.colf, w.coll, cw + static_cast<size_t>(w2) * wbytes, n->conv_b + static_cast<size_t>(w2) * 64,
@@ -226,8 +243,13 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
       continue;
     }
     // group tail conv + `res += x` (group input)
-    ConvTcDesc ct = base(g * per_group + 2 * nb, EPI_SCALE_SKIP);
+    ConvTcDesc ct = base(g * per_group + 2 * nb, hl ? EPI_SCALE_SKIP_HL : EPI_SCALE_SKIP);
     ct.out_bf16 = w.XAbf; ct.skip_f32 = skip32; ct.out_f32 = w.XA; ct.svec = nullptr;
+    if (hl) {
+      ct.skip_hi = gin;
+      ct.skip_lo = from_head ? Hlo : XAlo;
+      ct.out_lo = XAlo;
+    }
     if (nb == 0) {
       ct.in_bf16 = gin;
     } else if (sched == 1) {
@@ -241,18 +263,26 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
                         cudaMemcpyDeviceToDevice, st) != cudaSuccess)
       return DFIR_ERR_CUDA;
   }
+  __nv_bfloat16* trunk_out = w.XBbf;
   if (sa.stages & ST_TRUNK_TAIL) {
-    ConvTcDesc cf = base(ng * per_group, EPI_SCALE_SKIP);
+    ConvTcDesc cf = base(ng * per_group, hl ? EPI_SCALE_SKIP_HL : EPI_SCALE_SKIP);
+    if (hl) {
+      cf.skip_hi = w.Hbf;
+      cf.skip_lo = Hlo;
+      cf.out_lo = nullptr;  // the trunk output only feeds the upsampler convs
+    }
     cf.in_bf16 = (ng == 0 || (n->no_group_conv && nb == 0)) ? w.Hbf : (n->no_group_conv ? w.XBbf : w.XAbf);
     if (sched == 1 && n->no_group_conv && ng > 0 && nb > 0) fuse_in(cf, ng * nb - 1, xcur, nullptr);  // last x never materialised
-    cf.out_bf16 = w.XBbf; cf.skip_f32 = w.Hh; cf.out_f32 = nullptr;
+    // never in place: a band's first output row is another band's halo row
+    trunk_out = cf.in_bf16 == w.XBbf ? w.XAbf : w.XBbf;
+    cf.out_bf16 = trunk_out; cf.skip_f32 = w.Hh; cf.out_f32 = nullptr;
     DFIR_TRY(conv3x3_c64_tc(cf, st));
   }
   if (!(sa.stages & ST_UPSAMPLE)) return DFIR_OK;
   // upsampler: conv C -> r*r*C with PixelShuffle(r) folded into the TMA store strides
   int r = 0;
   const int nup = up_stages(n->scale, &r);
-  const void* cur = w.XBbf;
+  const void* cur = trunk_out;
   int h = H, wd = W;
   for (int t = 0; t < nup; ++t) {
     uint8_t* U = reinterpret_cast<uint8_t*>(w.U[t]);
@@ -484,6 +514,31 @@ int dfir_conv3x3_c64_scale_skip(const void* in_bf16, const void* wpacked, const 
   d.out_pix_stride = 128; d.out_row_stride = static_cast<long long>(W) * 128;
   d.out_img_stride = static_cast<long long>(H) * W * 128;
   d.svec = svec; d.skip_f32 = skip_f32; d.out_f32 = out_f32;
+  d.pool_rows = const_cast<float*>(pool_rows); d.col_first = const_cast<float*>(col_first);
+  d.col_last = const_cast<float*>(col_last);
+  d.ca_style = style; d.ca_params = ca_params; d.ca_R = R; d.ca_M = M; d.ca_A = A; d.attributes = attributes; d.sq = sq;
+  d.epi_stats = style != DFIR_STYLE_NONE ? 1 : 0;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return DFIR_ERR_CUDA;
+  d.num_sms = sms;
+  return conv3x3_c64_tc(d, S(stream));
+}
+
+int dfir_conv3x3_c64_scale_skip_hl(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
+                                   const float* svec, const void* skip_hi, const void* skip_lo, void* out_hi, void* out_lo,
+                                   const float* pool_rows, const float* col_first, const float* col_last, int style,
+                                   const float* ca_params, int R, int M, int A, const float* attributes,
+                                   const float* sq, void* stream) {
+  if (in_bf16 == nullptr || out_hi == nullptr || skip_hi == nullptr || skip_lo == nullptr) return DFIR_ERR_ARG;
+  ConvTcDesc d{};
+  d.B = B; d.H = H; d.W = W; d.cin_total = 64; d.cin_off = 0; d.cout = 64; d.epi = EPI_SCALE_SKIP_HL; d.in_mode = IN_TMA;
+  d.in_bf16 = in_bf16; d.wpacked = wpacked; d.bias = bias; d.out_bf16 = out_hi; d.out_lo = out_lo;
+  d.skip_hi = skip_hi; d.skip_lo = skip_lo;
+  d.out_pix_stride = 128; d.out_row_stride = static_cast<long long>(W) * 128;
+  d.out_img_stride = static_cast<long long>(H) * W * 128;
+  d.svec = svec;
   d.pool_rows = const_cast<float*>(pool_rows); d.col_first = const_cast<float*>(col_first);
   d.col_last = const_cast<float*>(col_last);
   d.ca_style = style; d.ca_params = ca_params; d.ca_R = R; d.ca_M = M; d.ca_A = A; d.attributes = attributes; d.sq = sq;

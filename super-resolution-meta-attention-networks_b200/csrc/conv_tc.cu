@@ -103,6 +103,8 @@ constexpr int kThreads = 320;                // IN_TMA: producer, MMA, 4 epilogu
 constexpr int kThreadsFused = 320 + 256;     // + two transform groups of 4 warps
 constexpr int kThreadsTwoEpi = 320 + 128;    // EPI_SCALE_SKIP / EPI_RELU_STATS (IN_TMA): + a second epilogue group (warps 10-13)
 constexpr const char* kDefaultL2Policy = "nnnnnn";  // see conv3x3_c64_tc(): overridden by DFIR_L2_POLICY
+constexpr int kHlSlots = 3;                  // EPI_SCALE_SKIP_HL: stream-tile buffers per epilogue warp (1 in use, 2 in flight)
+constexpr int kHlItemBytes = 4096;           // one tile: 16 px x 64 ch bf16 hi (2 KB) + lo (2 KB)
 constexpr int kMaxBandImages = 8;            // a CTA's row band may touch at most this many images (IN_FUSED)
 constexpr int kAttnScratchFloats = 64 + 64 + 512 + 1024 + 4;  // attention scratch of one epilogue group
 constexpr int kCaStageFloats = 704;          // QCALayer parameter blobs up to this size are staged in shared memory
@@ -124,7 +126,12 @@ struct SmemLayout {
   static_assert(off_cap + kCaStageFloats * 4 <= off_stage + 2 * kStageBytes, "prologue scratch must fit the staging tiles");
   static constexpr int off_svec = off_pool + 8 * 64 * 4;                         // s of the images of this band
   static constexpr int off_bars = off_svec + kMaxBandImages * 64 * 4;
-  static constexpr int n_bars = 2 * kSlots + kARows + 2 * kAcc + 1;
+  static constexpr int n_bars = 2 * kSlots + kARows + 2 * kAcc + 1 + 8 * kHlSlots;
+  // EPI_SCALE_SKIP_HL: the 96 KB of the staging tiles + skip buffers hold, slot-major, kHlSlots x 8 warps x (2 KB hi +
+  // 2 KB lo) stream tiles of 16 pixels; the prologue scratch aliases the last slot (first used after the prologue)
+  static constexpr int off_hl = off_stage;
+  static constexpr int hl_scratch_shift = (kHlSlots - 1) * 8 * kHlItemBytes;
+  static_assert(kHlSlots * 8 * kHlItemBytes <= 2 * kStageBytes + 2 * 128 * 64 * 4, "stream tiles must fit the epilogue buffers");
   static constexpr int off_tmem = off_bars + n_bars * 8;
   static constexpr int total = off_tmem + 16;
 };
@@ -169,7 +176,7 @@ constexpr int conv_threads() {
 template <int NT, int EPI, int INMODE>
 __global__ void __launch_bounds__(conv_threads<EPI, INMODE>(), 1)
 conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
-                      ConvTcArgs a) {
+                      const __grid_constant__ ConvHlMaps hl, ConvTcArgs a) {
   using L = SmemLayout<NT>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms (TMA and UMMA) need 1024-byte alignment of every tile base
@@ -180,9 +187,11 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   float* skipbuf = reinterpret_cast<float*>(smem + L::off_skip);
   float* bias_s = reinterpret_cast<float*>(smem + L::off_bias);
   float* pool_s = reinterpret_cast<float*>(smem + L::off_pool);
-  float* attn_s = reinterpret_cast<float*>(smem + L::off_attn);
+  constexpr bool kScaleSkip = EPI == EPI_SCALE_SKIP || EPI == EPI_SCALE_SKIP_HL;
+  constexpr int kScratchShift = EPI == EPI_SCALE_SKIP_HL ? L::hl_scratch_shift : 0;
+  float* attn_s = reinterpret_cast<float*>(smem + L::off_attn + kScratchShift);
   float* svec_s = reinterpret_cast<float*>(smem + L::off_svec);
-  float* cap_s = reinterpret_cast<float*>(smem + L::off_cap);
+  float* cap_s = reinterpret_cast<float*>(smem + L::off_cap + kScratchShift);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::off_bars);
   uint64_t* full = bars;                                   // ring slot filled      (producer/transform -> loaders)
   uint64_t* empty = full + kSlots;                         // ring slot drained     (loaders -> producer/transform)
@@ -191,6 +200,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   uint64_t* go = tfull + kAcc;                             // output row may start: its bottom A row is in TMEM (4 loader
                                                            // warps) and its accumulator is drained (4 epilogue warps)
   uint64_t* wbar = go + kAcc;                              // weights landed
+  uint64_t* sbar = wbar + 1;                               // EPI_SCALE_SKIP_HL: stream tile landed, [8 warps][kHlSlots]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + L::off_tmem);
 
   // Physical warp order: [epilogue group 0: 0-3][A loaders: 4-7][epilogue group 1 or input transform: 8..][TMA producer]
@@ -219,7 +229,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
 
   if (threadIdx.x == 0) {
     if (INMODE == IN_TMA) prefetch_tmap(&tmap_in);
-    if (EPI != EPI_TAIL_NCHW && EPI != EPI_SCALE_SKIP) prefetch_tmap(&tmap_out);
+    if (EPI != EPI_TAIL_NCHW && !kScaleSkip) prefetch_tmap(&tmap_out);
     for (int i = 0; i < kSlots; ++i) {
       mbar_init(&full[i], INMODE == IN_FUSED ? 128 : 1);
       mbar_init(&empty[i], 4);
@@ -230,6 +240,10 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       mbar_init(&go[i], 8);
     }
     mbar_init(wbar, 1);
+    if constexpr (EPI == EPI_SCALE_SKIP_HL) {
+      for (int i = 0; i < 8 * kHlSlots; ++i) mbar_init(&sbar[i], 1);
+      for (int i = 0; i < 4; ++i) prefetch_tmap(&hl.m[i]);
+    }
     fence_barrier_init();
   }
   if (tid >= 64 && tid < 64 + NT) bias_s[tid - 64] = a.bias != nullptr ? a.bias[tid - 64] : 0.f;
@@ -316,21 +330,35 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         constexpr uint32_t idesc = make_idesc_bf16_f32(128, NT);
         const uint64_t db_base = make_sw128_kmajor_desc(smem_u32(wsm), 1024, 0);
         mbar_wait(wbar, 0, 2);
+        // Row state, computed one row ahead: the queue of issued-but-unfinished MMAs is only ~4 deep (~130 clk of tensor
+        // work), so the ~30 integer instructions and the barrier test (~100 clk) that separate two rows are issued in
+        // front of the LAST eight MMAs of the previous row, while those MMAs wait for queue slots anyway.
         int y_cur = g0 % H;
         int nc = padded(g0) - pr_first;  // sequence index of the centre row
+        auto row_cols = [&](int ncv, uint32_t (&cols)[3]) {
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) cols[dy] = tmem_base + kAColBase + ((ncv - 1 + dy) & (kARows - 1)) * kAColsPerRow;
+        };
+        uint32_t a_col[3];
+        row_cols(nc, a_col);
+        mbar_wait(&go[0], 0, 3);
         for (int g = g0, it = 0; g < g1; ++g, ++it) {
           const bool img_end = y_cur == H - 1;  // the next output row starts a new image (or column segment)
+          const bool last = g + 1 == g1;
           const int acc = it & 1;
           const uint32_t d_tmem = tmem_base + acc * NT;
-          uint32_t a_col[3];
-#pragma unroll
-          for (int dy = 0; dy < 3; ++dy) a_col[dy] = tmem_base + kAColBase + ((nc - 1 + dy) & (kARows - 1)) * kAColsPerRow;
           uint64_t* const rel_bar = &aempty[(nc - 1) & (kARows - 1)];
           if (probe) g_dfir_progress[1] = it + 1;
-          DFIR_TRACE1(4, it);  // MMA thread: top of row
-          mbar_wait(&go[acc], (it >> 1) & 1, 3);
           tcgen05_fence_after();
-          DFIR_TRACE1(5, it);  // MMA thread: row may start
+          DFIR_TRACE1(5, it);  // MMA thread: row starts
+          auto issue = [&](int first, int count) {  // MMAs [first, first + count) of the row, in (dy, dx, k) order
+#pragma unroll
+            for (int j = first; j < first + count; ++j) {
+              const int dy = j / 12, dx = (j / 4) % 3, k = j & 3;
+              const uint64_t db = db_base + static_cast<uint32_t>(((dy * 3 + dx) * NT * 128 + k * 32) >> 4);
+              umma_f16_ts(d_tmem, a_col[dy] + dx * 32 + k * 8, db, idesc, j != 0 ? 1u : 0u);
+            }
+          };
 #ifdef DFIR_PROBES
           if (exp_n192 || exp_n128) {
             if constexpr (NT == 64) {
@@ -353,30 +381,37 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           } else
 #endif
           {
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-#pragma unroll
-              for (int dx = 0; dx < 3; ++dx) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint64_t db = db_base + static_cast<uint32_t>(((dy * 3 + dx) * NT * 128 + k * 32) >> 4);
-                  umma_f16_ts(d_tmem, a_col[dy] + dx * 32 + k * 8, db, idesc, (dy | dx | k) != 0 ? 1u : 0u);
-                }
-              }
-              // the top row is dead as soon as the dy = 0 taps have executed: hand its TMEM slot back now so that the
-              // loaders refill it while the remaining 24 MMAs of this row run
-              if (dy == 0) umma_commit(rel_bar);
-            }
+            issue(0, 12);
+            // the top row is dead as soon as the dy = 0 taps have executed: hand its TMEM slot back now so that the
+            // loaders refill it while the remaining 24 MMAs of this row run
+            umma_commit(rel_bar);
+            issue(12, 16);
           }
+          // ---- next row's state and barrier, behind the MMAs queued so far
+          const int nc_next = nc + (img_end ? 3 : 1);
+          uint32_t a_col_next[3];
+          row_cols(nc_next, a_col_next);
+          bool next_ready = true;
+          if (!last) next_ready = mbar_try_wait(&go[acc ^ 1], ((it + 1) >> 1) & 1);
+#ifdef DFIR_PROBES
+          if (!(exp_n192 || exp_n128))
+#endif
+            issue(28, 8);
           umma_commit(&tfull[acc]);
           DFIR_TRACE1(7, it);  // MMA thread: 36 MMAs + commits issued
-          if (img_end || g + 1 == g1) {
+          if (img_end || last) {
             // at an image boundary the next centre also skips the last row and the bottom pad row of the finished
             // image — keeping them would deadlock the 4-slot TMEM row ring
             umma_commit(&aempty[nc & (kARows - 1)]);
             umma_commit(&aempty[(nc + 1) & (kARows - 1)]);
           }
-          nc += img_end ? 3 : 1;
+          if (!next_ready) {
+            DFIR_TRACE1(4, it);  // MMA thread: the early test failed, blocking wait for the next row
+            mbar_wait(&go[acc ^ 1], ((it + 1) >> 1) & 1, 3);
+          }
+          nc = nc_next;
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) a_col[dy] = a_col_next[dy];
           y_cur = img_end ? 0 : y_cur + 1;
         }
       }
@@ -583,7 +618,40 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       const int rows_img_e = nseg * H;
       const int bimg_first = g0 / rows_img_e;
       int cur_img = -1;
-      if constexpr (EPI == EPI_SCALE_SKIP) {
+      // ---- EPI_SCALE_SKIP_HL: every epilogue warp streams the residual tiles of its own 32 pixels through kHlSlots
+      // private 4 KB buffers (TMA load -> in-place update -> TMA store), two tiles of 16 pixels per output row, loads
+      // issued two tiles ahead.  No barrier other than the tile's own mbarrier: the warps never wait for each other.
+      const int hl_w = egrp * 4 + q;                       // buffer column of this warp
+      uint8_t* const hl_base = smem + L::off_hl + hl_w * kHlItemBytes;
+      uint64_t* const hl_bar = sbar + hl_w * kHlSlots;
+      int hl_ly = (g0 + egrp) % H, hl_lcol = (g0 + egrp) / H;  // load cursor: next row whose tiles are requested
+      int hl_lb = hl_lcol / nseg, hl_lseg = hl_lcol % nseg;
+      int hl_lg = g0 + egrp, hl_lhalf = 0, hl_lslot = 0;
+      auto hl_issue = [&]() {  // lane 0: request the next tile (if any) into the next slot
+        if (hl_lg < g1) {
+          uint8_t* dst = hl_base + hl_lslot * (8 * kHlItemBytes);
+          const int xs = hl_lseg * 128 + q * 32 + hl_lhalf * 16;
+          mbar_arrive_expect_tx(&hl_bar[hl_lslot], kHlItemBytes);
+          tma_load_4d(dst, &hl.m[0], &hl_bar[hl_lslot], 0, xs, hl_ly, hl_lb);
+          tma_load_4d(dst + 2048, &hl.m[1], &hl_bar[hl_lslot], 0, xs, hl_ly, hl_lb);
+        }
+        if (++hl_lslot == kHlSlots) hl_lslot = 0;
+        if (++hl_lhalf == 2) {
+          hl_lhalf = 0;
+          hl_lg += kEpiGroups;
+          hl_ly += kEpiGroups;
+          while (hl_ly >= H) {
+            hl_ly -= H;
+            if (++hl_lseg == nseg) {
+              hl_lseg = 0;
+              ++hl_lb;
+            }
+          }
+        }
+      };
+      int hl_slot = 0, hl_phase = 0;                        // consume cursor
+      float hl_s[16], hl_bs[16];                            // scale and bias * scale of this thread's 16 channels
+      if constexpr (kScaleSkip) {
         // ---- pool-by-linearity: while the pipeline fills, the epilogue warps turn the sums of
         // t = relu(conv1(x)) left by the previous kernel into this block's attention vectors
         //   mean(conv2(t))[co] = b[co] + (1/HW) sum_{tap,ci} W[co][ci][tap] * S[tap][ci]
@@ -600,6 +668,12 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           }
         }
         grid_dep_wait();
+        if constexpr (EPI == EPI_SCALE_SKIP_HL) {
+          if (lane == 0) {  // the first two tiles travel while the attention vector is evaluated
+            hl_issue();
+            hl_issue();
+          }
+        }
         if (a.epi_stats) {
           if constexpr (kTwoEpi) named_bar_sync(6, 256); else named_bar_sync(5, 128);  // cap_s complete
           float* scratch = attn_s + egrp * kAttnScratchFloats;
@@ -743,7 +817,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       } else {
         grid_dep_wait();
       }
-      if constexpr (kTwoEpi && EPI == EPI_SCALE_SKIP) {
+      if constexpr (kTwoEpi && kScaleSkip) {
         if (a.epi_stats) named_bar_sync(6, 256);  // the attention vectors (svec_s) of both groups are complete
       }
       // (col, y, b, seg) of output row g, advanced without integer divisions (they cost ~130 clk each per row)
@@ -844,6 +918,68 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             for (int c = 0; c < NT; ++c)
               if (c < a.cout) o[c * plane] = __uint_as_float(r0[c]) + bias_s[c] + (a.tail_accumulate ? o[c * plane] : 0.f);
           }
+        } else if constexpr (EPI == EPI_SCALE_SKIP_HL) {
+          uint32_t ra[32], rb[32];  // 16x256b fragments: pixels pr, pr + 8 (ra) and pr + 16, pr + 24 (rb), 16 channels each
+          tmem_ld_16x256b_x8(taddr, ra);
+          tmem_ld_16x256b_x8(taddr + (16u << 16), rb);
+          tmem_ld_wait();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&go[acc]);  // accumulator back to the MMA thread
+          if (q == 0) DFIR_TRACE(10 + 3 * egrp, it >> 1);
+          const int pr = lane >> 2, cq = lane & 3;
+          if (b != cur_img) {  // (uniform) new image: this thread's 16 scale / bias * scale values
+#pragma unroll
+            for (int n = 0; n < 8; ++n)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int c = 8 * n + 2 * cq + e;
+                const float sc = a.epi_stats ? svec_s[(b - bimg_first) * 64 + c]
+                                             : (a.svec != nullptr ? a.svec[static_cast<size_t>(b) * 64 + c] : 1.f);
+                hl_s[2 * n + e] = sc;
+                hl_bs[2 * n + e] = bias_s[c] * sc;
+              }
+            cur_img = b;
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint8_t* buf = hl_base + hl_slot * (8 * kHlItemBytes);
+            mbar_wait(&hl_bar[hl_slot], hl_phase, 10);
+            // word (pixel p, channels 8 n + 2 cq + {0,1}) of a tile: p * 128 + ((n ^ (p & 7)) << 4) + 4 cq (TMA 128B swizzle)
+            uint8_t* wbase = buf + pr * 128 + 4 * cq;
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+#pragma unroll
+              for (int n = 0; n < 8; ++n) {
+                uint32_t* ph = reinterpret_cast<uint32_t*>(wbase + sl * 1024 + ((n ^ pr) << 4));
+                uint32_t* pl = reinterpret_cast<uint32_t*>(wbase + 2048 + sl * 1024 + ((n ^ pr) << 4));
+                const uint32_t hw = *ph, lw = *pl;
+                const uint32_t* src = half ? rb : ra;
+                const float x0 = __uint_as_float(hw << 16) + __uint_as_float(lw << 16);
+                const float x1 = __uint_as_float(hw & 0xffff0000u) + __uint_as_float(lw & 0xffff0000u);
+                const float o0 = fmaf(__uint_as_float(src[4 * n + 2 * sl]), hl_s[2 * n], hl_bs[2 * n]) + x0;
+                const float o1 = fmaf(__uint_as_float(src[4 * n + 2 * sl + 1]), hl_s[2 * n + 1], hl_bs[2 * n + 1]) + x1;
+                const uint32_t nh = pack_bf16x2(o0, o1);
+                *ph = nh;
+                *pl = pack_bf16x2(o0 - __uint_as_float(nh << 16), o1 - __uint_as_float(nh & 0xffff0000u));
+              }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              const int xs = seg * 128 + q * 32 + half * 16;
+              tma_store_4d(&hl.m[2], buf, 0, xs, y, b);
+              if (a.hl_store_lo) tma_store_4d(&hl.m[3], buf + 2048, 0, xs, y, b);
+              tma_store_commit();
+              tma_store_wait_read<1>();  // the tile before this one has left its buffer: that buffer takes the next load
+              hl_issue();
+            }
+            if (++hl_slot == kHlSlots) {
+              hl_slot = 0;
+              hl_phase ^= 1;
+            }
+          }
+          if (q == 0) DFIR_TRACE(14 + egrp, it >> 1);
         } else if constexpr (EPI == EPI_SCALE_SKIP) {
           // Per half of 32 channels: v = acc * s + bias * s (or r = acc + bias when the training forward saves r) into
           // an fp32 tile in smem (chunk-rotated: conflict free for the pixel-major writes and the coalesced reads),
@@ -1172,7 +1308,8 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           if (q == 0) DFIR_TRACE(14 + egrp, it >> (kTwoEpi ? 1 : 0));
         }
       }
-      if (EPI != EPI_TAIL_NCHW && EPI != EPI_SCALE_SKIP && et == 0) tma_store_wait<0>();
+      if (EPI != EPI_TAIL_NCHW && EPI != EPI_SCALE_SKIP && EPI != EPI_SCALE_SKIP_HL && et == 0) tma_store_wait<0>();
+      if (EPI == EPI_SCALE_SKIP_HL && lane == 0) tma_store_wait<0>();
     }
   }
 
@@ -1221,7 +1358,7 @@ int make_tmap_nhwc_bf16(CUtensorMap* m, const void* base, int C, int W, int H, i
 }
 
 template <int NT, int EPI, int INMODE>
-static int launch_one(const CUtensorMap& tin, const CUtensorMap& tout, const ConvTcArgs& a, int grid,
+static int launch_one(const CUtensorMap& tin, const CUtensorMap& tout, const ConvHlMaps& hl, const ConvTcArgs& a, int grid,
                       cudaStream_t stream) {
   using L = SmemLayout<NT>;
   static bool configured[64] = {};  // per device: the attribute lives in the device's context
@@ -1244,7 +1381,7 @@ static int launch_one(const CUtensorMap& tin, const CUtensorMap& tout, const Con
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, tin, tout, a) == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
+  return cudaLaunchKernelEx(&cfg, kern, tin, tout, hl, a) == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
 }
 
 int debug_trace(unsigned long long* out1024) {
@@ -1290,7 +1427,11 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   if (d.epi == EPI_SCALE_SKIP && (d.out_bf16 == nullptr || d.out_pix_stride != 128 ||
                                   d.out_row_stride != static_cast<long long>(d.W) * 128))
     return DFIR_ERR_ARG;  // the direct-store epilogue writes dense NHWC
-  if (d.epi == EPI_SCALE_SKIP && d.epi_stats &&
+  const bool hl_mode = d.epi == EPI_SCALE_SKIP_HL;
+  if (hl_mode && (fused || d.out_bf16 == nullptr || d.skip_hi == nullptr || d.skip_lo == nullptr || d.out_pix_stride != 128 ||
+                  d.out_row_stride != static_cast<long long>(d.W) * 128 || d.r_out != nullptr || d.relu_out))
+    return DFIR_ERR_ARG;  // the stream planes are dense NHWC; training extras live on the fp32-stream epilogue
+  if ((d.epi == EPI_SCALE_SKIP || hl_mode) && d.epi_stats &&
       (fused || d.ca_style == DFIR_STYLE_NONE || d.pool_rows == nullptr || d.col_first == nullptr || d.col_last == nullptr || d.ca_params == nullptr ||
        d.ca_A > 512 || d.ca_M > 448 || (d.ca_A > 0 && d.attributes == nullptr)))
     return DFIR_ERR_ARG;
@@ -1317,7 +1458,19 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
     if (fused) return DFIR_ERR_ARG;
     tout = tin;
   }
+  ConvHlMaps hl{};
+  if (hl_mode) {
+    const long long rowB = static_cast<long long>(d.W) * 128, imgB = rowB * d.H;
+    const void* planes[4] = {d.skip_hi, d.skip_lo, d.out_bf16, d.out_lo != nullptr ? d.out_lo : d.out_bf16};
+    for (int i = 0; i < 4; ++i) {
+      rc = make_tmap_nhwc_bf16(&hl.m[i], planes[i], 64, d.W, d.H, d.B, 128, rowB, imgB, 16);
+      if (rc != DFIR_OK) return rc;
+    }
+  } else {
+    for (int i = 0; i < 4; ++i) hl.m[i] = tout;  // unused, but must be valid descriptors
+  }
   ConvTcArgs a{};
+  a.hl_store_lo = d.out_lo != nullptr ? 1 : 0;
   a.B = d.B;
   a.H = d.H;
   a.W = d.W;
@@ -1383,26 +1536,27 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   if (const char* e = getenv("DFIR_NUM_SMS")) grid = atoi(e) > 0 ? atoi(e) : grid;  // debugging aid
   if (G < grid) grid = static_cast<int>(G);
   // IN_FUSED keeps the attention vectors of every image a band touches in shared memory
-  if ((fused || (d.epi == EPI_SCALE_SKIP && d.epi_stats)) &&
+  if ((fused || ((d.epi == EPI_SCALE_SKIP || hl_mode) && d.epi_stats)) &&
       (G + grid - 1) / grid > static_cast<long long>(kMaxBandImages - 1) * a.nseg * d.H)
     return DFIR_ERR_ARG;
   if (fused) {
     switch (d.epi) {
-      case EPI_BIAS_RELU: return launch_one<64, EPI_BIAS_RELU, IN_FUSED>(tin, tout, a, grid, stream);
-      case EPI_BIAS_SKIP: return launch_one<64, EPI_BIAS_SKIP, IN_FUSED>(tin, tout, a, grid, stream);
-      case EPI_SCALE_SKIP: return launch_one<64, EPI_SCALE_SKIP, IN_FUSED>(tin, tout, a, grid, stream);
+      case EPI_BIAS_RELU: return launch_one<64, EPI_BIAS_RELU, IN_FUSED>(tin, tout, hl, a, grid, stream);
+      case EPI_BIAS_SKIP: return launch_one<64, EPI_BIAS_SKIP, IN_FUSED>(tin, tout, hl, a, grid, stream);
+      case EPI_SCALE_SKIP: return launch_one<64, EPI_SCALE_SKIP, IN_FUSED>(tin, tout, hl, a, grid, stream);
       default: return DFIR_ERR_ARG;
     }
   }
   switch (d.epi) {
-    case EPI_BIAS: return launch_one<64, EPI_BIAS, IN_TMA>(tin, tout, a, grid, stream);
-    case EPI_BIAS_RELU: return launch_one<64, EPI_BIAS_RELU, IN_TMA>(tin, tout, a, grid, stream);
-    case EPI_BIAS_POOL: return launch_one<64, EPI_BIAS_POOL, IN_TMA>(tin, tout, a, grid, stream);
-    case EPI_BIAS_SKIP: return launch_one<64, EPI_BIAS_SKIP, IN_TMA>(tin, tout, a, grid, stream);
-    case EPI_RELU_STATS: return launch_one<64, EPI_RELU_STATS, IN_TMA>(tin, tout, a, grid, stream);
-    case EPI_RELU_MASK: return launch_one<64, EPI_RELU_MASK, IN_TMA>(tin, tout, a, grid, stream);
-    case EPI_SCALE_SKIP: return launch_one<64, EPI_SCALE_SKIP, IN_TMA>(tin, tout, a, grid, stream);
-    case EPI_TAIL_NCHW: return launch_one<16, EPI_TAIL_NCHW, IN_TMA>(tin, tout, a, grid, stream);
+    case EPI_BIAS: return launch_one<64, EPI_BIAS, IN_TMA>(tin, tout, hl, a, grid, stream);
+    case EPI_BIAS_RELU: return launch_one<64, EPI_BIAS_RELU, IN_TMA>(tin, tout, hl, a, grid, stream);
+    case EPI_BIAS_POOL: return launch_one<64, EPI_BIAS_POOL, IN_TMA>(tin, tout, hl, a, grid, stream);
+    case EPI_BIAS_SKIP: return launch_one<64, EPI_BIAS_SKIP, IN_TMA>(tin, tout, hl, a, grid, stream);
+    case EPI_RELU_STATS: return launch_one<64, EPI_RELU_STATS, IN_TMA>(tin, tout, hl, a, grid, stream);
+    case EPI_RELU_MASK: return launch_one<64, EPI_RELU_MASK, IN_TMA>(tin, tout, hl, a, grid, stream);
+    case EPI_SCALE_SKIP: return launch_one<64, EPI_SCALE_SKIP, IN_TMA>(tin, tout, hl, a, grid, stream);
+    case EPI_TAIL_NCHW: return launch_one<16, EPI_TAIL_NCHW, IN_TMA>(tin, tout, hl, a, grid, stream);
+    case EPI_SCALE_SKIP_HL: return launch_one<64, EPI_SCALE_SKIP_HL, IN_TMA>(tin, tout, hl, a, grid, stream);
     default: return DFIR_ERR_ARG;
   }
 }

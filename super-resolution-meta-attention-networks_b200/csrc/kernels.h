@@ -1,6 +1,7 @@
 // Internal declarations shared by the CUDA translation units (not part of the public C ABI — that is
 // include/dfir.h).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -21,6 +22,10 @@ enum : int {
   EPI_SCALE_SKIP = 6, // RCAB conv2 / group conv: out_f32 = (acc + b) * s[b][c] + skip ; out_bf16 = bf16(out_f32)
                       // i.e. QCALayer/ParaCALayer `x * y` and `res += x` in the epilogue (:127,179; q_layer.py:43)
   EPI_RELU_MASK = 7,  // backward of conv-ReLU: out_bf16 = (acc + b) where the saved activation mask_bf16 > 0, else 0
+  EPI_SCALE_SKIP_HL = 8,  // EPI_SCALE_SKIP of the inference chain on the bf16 hi + bf16 lo residual stream (x = hi + lo,
+                          // 16 significant bits): out = (acc + b) * s + (skip_hi + skip_lo) -> out_hi = bf16(out),
+                          // out_lo = bf16(out - out_hi).  10 instead of 12 bytes per element (the hi plane IS the next
+                          // conv's operand); skip and result tiles travel by TMA, 16 pixels x 64 channels at a time.
 };
 
 enum : int { IN_TMA = 0, IN_FUSED = 1 };  // input modes of the tensor-core conv (see conv_tc.cu)
@@ -59,6 +64,13 @@ struct ConvTcArgs {  // kernel argument block
   unsigned long long pol_in, pol_out, pol_skip, pol_f32;
   const void* next_w;       // packed weights of the NEXT conv of the chain (or nullptr): pulled into L2 at kernel start
   int next_w_bytes;
+  int hl_store_lo;          // EPI_SCALE_SKIP_HL: also write the lo plane (0 = the result only feeds a conv: hi suffices)
+};
+
+// EPI_SCALE_SKIP_HL: tensor maps of the stream planes (box = 64 channels x 16 pixels, SWIZZLE_128B):
+// 0 skip hi, 1 skip lo, 2 out hi, 3 out lo
+struct ConvHlMaps {
+  CUtensorMap m[4];
 };
 
 struct ConvTcDesc {  // host-side launch description
@@ -80,6 +92,9 @@ struct ConvTcDesc {  // host-side launch description
   long long out_pix_stride, out_row_stride, out_img_stride;  // bytes (pixel-shuffle folds into these)
   const float* skip_f32;
   float* out_f32;
+  const void* skip_hi = nullptr;  // EPI_SCALE_SKIP_HL: dense NHWC bf16 planes of the stream (out hi = out_bf16)
+  const void* skip_lo = nullptr;
+  void* out_lo = nullptr;         // nullptr: hi only
   float* pool_rows;
   float* col_first;
   float* col_last;
@@ -111,7 +126,7 @@ int pack_conv_weights_bf16(const float* w_oihw, void* out, int cout, int cin, in
                            int co_stride, cudaStream_t s);
 int pack_conv_weights_f32(const float* w_oihw, float* out, int cout, int cin, cudaStream_t s);
 int head_conv(const float* x_nchw, const float* w_packed, const float* bias, float* out_f32, __nv_bfloat16* out_bf16,
-              int B, int Cin, int H, int W, int Cout, cudaStream_t s);
+              int B, int Cin, int H, int W, int Cout, cudaStream_t s, __nv_bfloat16* out_lo = nullptr);
 int conv3x3_f32(const float* in, const float* w_packed, const float* bias, const float* skip, float* out, int B, int H,
                 int W, int Cin, int Cout, int relu, int ps_r, int out_nchw, cudaStream_t s, const float* mask = nullptr);
 int pool_rows_f32(const float* in, float* pool_rows, int B, int H, int W, int C, cudaStream_t s);

@@ -46,7 +46,8 @@ __global__ void pack_conv_f32_kernel(const float* __restrict__ w, float* __restr
 // ------------------------------------------------------------------------------------------------
 __global__ void head_conv_kernel(const float* __restrict__ x, const float* __restrict__ wp,
                                  const float* __restrict__ bias, float* __restrict__ out_f32,
-                                 __nv_bfloat16* __restrict__ out_bf16, int B, int Cin, int H, int W, int Cout) {
+                                 __nv_bfloat16* __restrict__ out_bf16, int B, int Cin, int H, int W, int Cout,
+                                 __nv_bfloat16* __restrict__ out_lo) {
   extern __shared__ float ws[];  // [9*Cin][Cout]
   const int nw = 9 * Cin * Cout;
   for (int i = threadIdx.x; i < nw; i += blockDim.x) ws[i] = wp[i];
@@ -89,6 +90,15 @@ __global__ void head_conv_kernel(const float* __restrict__ x, const float* __res
 #pragma unroll
       for (int i = 0; i < 4; ++i) pk[i] = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
       *reinterpret_cast<uint4*>(out_bf16 + o) = *reinterpret_cast<uint4*>(pk);
+      if (out_lo != nullptr) {  // hi + lo residual stream: lo = bf16(value - hi)
+        __align__(16) __nv_bfloat162 lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 h = __bfloat1622float2(pk[i]);
+          lo[i] = __floats2bfloat162_rn(acc[2 * i] - h.x, acc[2 * i + 1] - h.y);
+        }
+        *reinterpret_cast<uint4*>(out_lo + o) = *reinterpret_cast<uint4*>(lo);
+      }
     }
   }
 }
@@ -540,13 +550,13 @@ int pack_conv_weights_f32(const float* w, float* out, int cout, int cin, cudaStr
 }
 
 int head_conv(const float* x, const float* wp, const float* bias, float* out_f32, __nv_bfloat16* out_bf16, int B,
-              int Cin, int H, int W, int Cout, cudaStream_t s) {
+              int Cin, int H, int W, int Cout, cudaStream_t s, __nv_bfloat16* out_lo) {
   if (Cout % 8 != 0 || 9 * Cin * Cout * 4 > 48 * 1024) return DFIR_ERR_ARG;
   const long long nthreads = static_cast<long long>(B) * H * W * (Cout / 8);
   if (nthreads == 0) return DFIR_OK;
   const long long nblocks = std::min<long long>((nthreads + 255) / 256, 148 * 8);  // 8 resident CTAs per SM
   head_conv_kernel<<<static_cast<unsigned>(nblocks), 256, 9 * Cin * Cout * 4, s>>>(
-      x, wp, bias, out_f32, out_bf16, B, Cin, H, W, Cout);
+      x, wp, bias, out_f32, out_bf16, B, Cin, H, W, Cout, out_lo);
   return ok_or_cuda();
 }
 

@@ -206,6 +206,26 @@ def test_pool_by_linearity_trio(shape, style):
     assert torch.allclose(svec.cpu(), sv, rtol=1e-3, atol=1e-5), (svec.cpu() - sv).abs().max()
     assert G.max_norm_err(G.to_nchw(out32), want) < 1e-3
     assert torch.equal(outbf.cpu(), out32.cpu().to(torch.bfloat16))
+    # the same block on the bf16 hi + lo residual stream (x = hi + lo): result planes against the fp32-stream epilogue
+    x_hi = x32.to(torch.bfloat16)
+    x_lo = (x32 - x_hi.float()).to(torch.bfloat16)
+    o_hi = torch.full((B, H, W, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    o_lo = torch.full((B, H, W, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    assert L.dfir_conv3x3_c64_scale_skip_hl(t_d.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), B, H, W, None, x_hi.data_ptr(),
+                                            x_lo.data_ptr(), o_hi.data_ptr(), o_lo.data_ptr(), pool.data_ptr(),
+                                            cf.data_ptr(), cl.data_ptr(), STYLE_ID[style], blob.data_ptr(), 4, M, A,
+                                            attr_d.data_ptr(), sq_d.data_ptr(), G.stream()) == 0
+    G.sync()
+    got = o_hi.float() + o_lo.float()
+    scale = out32.abs().max().item()
+    assert (got - out32).abs().max().item() <= 2.0 ** -15 * scale, (got - out32).abs().max().item() / scale
+    assert (o_hi.float() - out32).abs().max().item() <= 2.0 ** -8 * scale   # hi alone is the bf16 rounding of the stream
+    # in place, scale vector from memory, hi plane only as output of a second call
+    assert L.dfir_conv3x3_c64_scale_skip_hl(t_d.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), B, H, W, svec.data_ptr(),
+                                            x_hi.data_ptr(), x_lo.data_ptr(), x_hi.data_ptr(), x_lo.data_ptr(), None, None,
+                                            None, 0, None, 4, M, A, None, None, G.stream()) == 0
+    G.sync()
+    assert ((x_hi.float() + x_lo.float()) - out32).abs().max().item() <= 2.0 ** -15 * scale
     # group-conv use: no scale vector, in-place stream update
     assert L.dfir_conv3x3_c64_scale_skip(t_d.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), B, H, W, None,
                                          x32.data_ptr(), x32.data_ptr(), outbf.data_ptr(), None, None, None, 0,

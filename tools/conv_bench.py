@@ -104,6 +104,27 @@ def ss_sweep():
         print("conv+scale_skip bc=%3d: %8.2f us  %7.1f GB/s (12 B/elem)" % (bc, us, byt / us / 1e3))
 
 
+def ss_hl_sweep():
+    wp = torch.empty(9 * 64 * 128, dtype=torch.uint8, device=dev)
+    w = (torch.randn(64, 64, 3, 3, device=dev) / 24).contiguous()
+    bias = torch.zeros(64, device=dev)
+    _lib.check(lib.dfir_pack_conv3x3_bf16(w.data_ptr(), wp.data_ptr(), 64, 64, 64, 0, 1, st()), "pack")
+    for bc in BCS:
+        t = torch.randn(bc, LR, LR, 64, device=dev).to(torch.bfloat16)
+        xh = torch.randn(bc, LR, LR, 64, device=dev).to(torch.bfloat16)
+        xl = (torch.randn(bc, LR, LR, 64, device=dev) * 1e-3).to(torch.bfloat16)
+        sv = torch.rand(bc, 64, device=dev) * 0.1
+
+        def launch():
+            _lib.check(lib.dfir_conv3x3_c64_scale_skip_hl(t.data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR,
+                                                          sv.data_ptr(), xh.data_ptr(), xl.data_ptr(), xh.data_ptr(),
+                                                          xl.data_ptr(), None, None, None, 0, None, 4, 10, 10, None, None,
+                                                          st()), "ss hl")
+        us = timeit(launch, NREP[0], NREP[1])
+        byt = bc * LR * LR * 64 * 10
+        print("conv+scale_skip hi/lo stream bc=%3d: %8.2f us  %7.1f GB/s (10 B/elem)" % (bc, us, byt / us / 1e3))
+
+
 def sr_sweep():
     for bc in (1, 4, 7, 8, 16, 32):
         r = torch.randn(bc, LR, LR, 64, device=dev).to(torch.bfloat16)
@@ -143,6 +164,8 @@ if "conv" in which:
     conv_sweep(2)
 if "ss" in which:
     ss_sweep()
+if "sshl" in which:
+    ss_hl_sweep()
 if "fused" in which:
     fused_sweep()
 if "sr" in which:
