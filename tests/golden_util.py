@@ -11,11 +11,50 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("grads_"))
+    """full-output fixtures (small shapes); the BASELINE-shape fingerprints big_*.npz have their own loader"""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR)
+                  if f.endswith(".npz") and not f.startswith("grads_") and not f.startswith("big_"))
 
 
 def grad_golden_names():
-    return sorted(f[6:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f.startswith("grads_"))
+    return sorted(f[6:-4] for f in os.listdir(GOLDEN_DIR)
+                  if f.endswith(".npz") and f.startswith("grads_") and not f.startswith("grads_big_"))
+
+
+def big_golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f.startswith("big_"))
+
+
+def load_big_golden(name):
+    """fingerprint of the reference output at a BASELINE.json shape (oracle/make_golden_big.py): the output sampled every
+    `stride` pixels, 8 seeded projections of the full output, its norm and max"""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    info = json.loads(bytes(z["meta"]).decode())
+    return dict(sub=torch.from_numpy(z["sub"]), proj=z["proj"], norm=float(z["norm"]), amax=float(z["amax"])), info
+
+
+def big_fingerprint_errors(out, fp, info):
+    """(max |out - ref| / max |ref| over the sampled pixels, worst |projection error| / ||ref||, PSNR over the sampled
+    pixels with peak 1.0)"""
+    st = info["stride"]
+    sub = out[:, :, ::st, ::st].double()
+    ref = fp["sub"].double()
+    err_sub = float((sub - ref).abs().max() / fp["amax"])
+    rs = np.random.RandomState(4242)
+    flat = out.detach().double().reshape(-1).numpy()
+    worst = 0.0
+    for i in range(len(fp["proj"])):
+        worst = max(worst, abs(float(np.dot(rs.standard_normal(flat.size), flat)) - fp["proj"][i]) / fp["norm"])
+    mse = float(((sub - ref) ** 2).mean())
+    psnr = 10.0 * np.log10(1.0 / max(mse, 1e-30))
+    return err_sub, worst, psnr
+
+
+def load_big_grad_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, "grads_" + name + ".npz"))
+    names = json.loads(bytes(z["names"]).decode())
+    info = json.loads(bytes(z["meta"]).decode())
+    return float(z["loss"]), {k: (float(z["norms"][i]), z["proj"][i]) for i, k in enumerate(names)}, info
 
 
 # networks that have gradient fingerprints (the oracle's backward is pinned for them) but no training path in the B200

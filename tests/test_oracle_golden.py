@@ -74,3 +74,16 @@ def test_generate_channels_and_scale_qpi_semantics():
     base = np.linspace(0, 1, 64)
     want = (1 / (np.sqrt(2 * np.pi) * 0.2)) * np.exp(-(base - mu) ** 2 / (2 * 0.04))
     np.testing.assert_allclose(g.flatten().numpy(), want.astype(np.float32), rtol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["big_qrcan_full_2x128", "big_qsan_g2b2_128"])
+def test_oracle_matches_reference_fingerprint_at_baseline_shape(name):
+    """the oracle at the BASELINE.json shapes against fingerprints of the live reference (oracle/make_golden_big.py):
+    sampled pixels and projections of the full output"""
+    from tests.golden_util import big_fingerprint_errors, load_big_golden
+    fp, info = load_big_golden(name)
+    sd, x, meta = case_tensors(info)
+    with torch.no_grad():
+        out = oracle_forward(info, sd, x, meta)
+    err_sub, err_proj, _ = big_fingerprint_errors(out, fp, info)
+    assert err_sub <= 2e-5 and err_proj <= 2e-5, (err_sub, err_proj)
