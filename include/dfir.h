@@ -137,12 +137,14 @@ int dfir_conv3x3_c64_scale_skip(const void* in_bf16, const void* wpacked, const 
  * plane is the operand of the next conv): out = (conv(in) + b) * s + (skip_hi + skip_lo), out_hi = bf16(out), out_lo =
  * bf16(out - out_hi) (out_lo may be NULL when the result only feeds a conv).  All planes dense NHWC bf16; out may alias
  * skip (in place).  10 instead of 12 bytes of HBM traffic per element; tiles travel by TMA.  Reference: the same lines as
- * dfir_conv3x3_c64_scale_skip (architectures.py:105-127,172-180; q_layer.py:39-43). */
+ * dfir_conv3x3_c64_scale_skip (architectures.py:105-127,172-180; q_layer.py:39-43).
+ * descending != 0 (W <= 128 only): images and rows are traversed from the last to the first — same result up to the fp32
+ * summation order of the taps; use it after an ascending producer of `in` so that its last rows are read from L2. */
 int dfir_conv3x3_c64_scale_skip_hl(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
                                    const float* svec, const void* skip_hi, const void* skip_lo, void* out_hi, void* out_lo,
                                    const float* pool_rows, const float* col_first, const float* col_last, int style,
                                    const float* ca_params, int R, int M, int A, const float* attributes,
-                                   const float* sq, void* stream);
+                                   const float* sq, int descending, void* stream);
 
 /* K-chunked convolutions for feature widths above 64 (Q-EDSR with 128/192/256 features, architectures.py:359-399):
  * a C -> C conv is a (C/64) x (C/64) block matrix of 64 -> 64 convs over 64-channel planes; the input-chunk sums are

@@ -138,6 +138,7 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
   static const bool hl_allowed = getenv("DFIR_STREAM") == nullptr || strcmp(getenv("DFIR_STREAM"), "f32") != 0;
   const int sched0 = n->pa_blob != nullptr ? 2 : n->schedule;
   const bool hl = hl_allowed && sched0 == 0 && sa.stages == ST_ALL && sa.group_out == nullptr && !sa.from_xa;
+  static const int hl_flip = getenv("DFIR_FLIP") == nullptr ? 1 : atoi(getenv("DFIR_FLIP"));
   __nv_bfloat16* const Hlo = reinterpret_cast<__nv_bfloat16*>(w.Hh);
   __nv_bfloat16* const XAlo = reinterpret_cast<__nv_bfloat16*>(w.XA);
   __nv_bfloat16* const XBlo = reinterpret_cast<__nv_bfloat16*>(w.XB);
@@ -209,6 +210,7 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
           c2.skip_hi = b == 0 ? gin : w.XBbf;
           c2.skip_lo = b == 0 ? (from_head ? Hlo : XAlo) : XBlo;
           c2.out_lo = XBlo;
+          c2.flip = hl_flip;  // conv1 walked its band downwards: conv2 walks it upwards, through what is still in L2
         }
         if (has_ca && sched == 3) {
           // schedule 3: the attention vector comes from its own small kernel instead of conv2's prologue
@@ -530,12 +532,12 @@ int dfir_conv3x3_c64_scale_skip_hl(const void* in_bf16, const void* wpacked, con
                                    const float* svec, const void* skip_hi, const void* skip_lo, void* out_hi, void* out_lo,
                                    const float* pool_rows, const float* col_first, const float* col_last, int style,
                                    const float* ca_params, int R, int M, int A, const float* attributes,
-                                   const float* sq, void* stream) {
+                                   const float* sq, int descending, void* stream) {
   if (in_bf16 == nullptr || out_hi == nullptr || skip_hi == nullptr || skip_lo == nullptr) return DFIR_ERR_ARG;
   ConvTcDesc d{};
   d.B = B; d.H = H; d.W = W; d.cin_total = 64; d.cin_off = 0; d.cout = 64; d.epi = EPI_SCALE_SKIP_HL; d.in_mode = IN_TMA;
   d.in_bf16 = in_bf16; d.wpacked = wpacked; d.bias = bias; d.out_bf16 = out_hi; d.out_lo = out_lo;
-  d.skip_hi = skip_hi; d.skip_lo = skip_lo;
+  d.skip_hi = skip_hi; d.skip_lo = skip_lo; d.flip = descending ? 1 : 0;
   d.out_pix_stride = 128; d.out_row_stride = static_cast<long long>(W) * 128;
   d.out_img_stride = static_cast<long long>(H) * W * 128;
   d.svec = svec;

@@ -188,6 +188,9 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   float* bias_s = reinterpret_cast<float*>(smem + L::off_bias);
   float* pool_s = reinterpret_cast<float*>(smem + L::off_pool);
   constexpr bool kScaleSkip = EPI == EPI_SCALE_SKIP || EPI == EPI_SCALE_SKIP_HL;
+  // Descending traversal (EPI_SCALE_SKIP_HL, nseg == 1): the pipeline runs on VIRTUAL coordinates (image B-1-b, row H-1-y,
+  // kernel row 2-dy: a vertically flipped problem, ascending); only the addresses at the edges are mirrored.
+  const bool flip = EPI == EPI_SCALE_SKIP_HL && a.flip != 0;
   constexpr int kScratchShift = EPI == EPI_SCALE_SKIP_HL ? L::hl_scratch_shift : 0;
   float* attn_s = reinterpret_cast<float*>(smem + L::off_attn + kScratchShift);
   float* svec_s = reinterpret_cast<float*>(smem + L::off_svec);
@@ -303,10 +306,11 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             mbar_wait(&empty[slot], ((n / kSlots) & 1) ^ 1, 1);
             DFIR_TRACE(0, n);  // producer: ring slot free, TMA load of row n issued
             mbar_arrive_expect_tx(&full[slot], kRowBytes);
+            const int yy_a = flip ? H - 1 - yy : yy, cimg_a = flip ? a.B - 1 - cimg : cimg;
             if (a.use_hints)
-              tma_load_4d_hint(ring + slot * kSlotBytes, &tmap_in, &full[slot], a.cin_off, cseg * 128 - 1, yy, cimg, a.pol_in);
+              tma_load_4d_hint(ring + slot * kSlotBytes, &tmap_in, &full[slot], a.cin_off, cseg * 128 - 1, yy_a, cimg_a, a.pol_in);
             else
-              tma_load_4d(ring + slot * kSlotBytes, &tmap_in, &full[slot], a.cin_off, cseg * 128 - 1, yy, cimg);
+              tma_load_4d(ring + slot * kSlotBytes, &tmap_in, &full[slot], a.cin_off, cseg * 128 - 1, yy_a, cimg_a);
             if (++yy > H) {  // past the bottom pad row: next column segment / image
               yy = -1;
               if (++cseg == nseg) {
@@ -329,6 +333,10 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       if (elect_one()) {
         constexpr uint32_t idesc = make_idesc_bf16_f32(128, NT);
         const uint64_t db_base = make_sw128_kmajor_desc(smem_u32(wsm), 1024, 0);
+        uint64_t tap_row[3];  // weight descriptors of the kernel row that meets the window's top / centre / bottom A row
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+          tap_row[dy] = db_base + static_cast<uint32_t>((((flip ? 2 - dy : dy) * 3) * NT * 128) >> 4);
         mbar_wait(wbar, 0, 2);
         // Row state, computed one row ahead: the queue of issued-but-unfinished MMAs is only ~4 deep (~130 clk of tensor
         // work), so the ~30 integer instructions and the barrier test (~100 clk) that separate two rows are issued in
@@ -355,7 +363,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
 #pragma unroll
             for (int j = first; j < first + count; ++j) {
               const int dy = j / 12, dx = (j / 4) % 3, k = j & 3;
-              const uint64_t db = db_base + static_cast<uint32_t>(((dy * 3 + dx) * NT * 128 + k * 32) >> 4);
+              const uint64_t db = tap_row[dy] + static_cast<uint32_t>((dx * NT * 128 + k * 32) >> 4);
               umma_f16_ts(d_tmem, a_col[dy] + dx * 32 + k * 8, db, idesc, j != 0 ? 1u : 0u);
             }
           };
@@ -632,8 +640,17 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           uint8_t* dst = hl_base + hl_lslot * (8 * kHlItemBytes);
           const int xs = hl_lseg * 128 + q * 32 + hl_lhalf * 16;
           mbar_arrive_expect_tx(&hl_bar[hl_lslot], kHlItemBytes);
-          tma_load_4d(dst, &hl.m[0], &hl_bar[hl_lslot], 0, xs, hl_ly, hl_lb);
-          tma_load_4d(dst + 2048, &hl.m[1], &hl_bar[hl_lslot], 0, xs, hl_ly, hl_lb);
+          const int ya = flip ? H - 1 - hl_ly : hl_ly, ba = flip ? a.B - 1 - hl_lb : hl_lb;
+          tma_load_4d(dst, &hl.m[0], &hl_bar[hl_lslot], 0, xs, ya, ba);
+          if (a.use_hints) tma_load_4d_hint(dst + 2048, &hl.m[1], &hl_bar[hl_lslot], 0, xs, ya, ba, a.pol_skip);
+          else tma_load_4d(dst + 2048, &hl.m[1], &hl_bar[hl_lslot], 0, xs, ya, ba);
+          // A/B (DFIR_DEBUG_PROBE bit 65536): L2 prefetch of the tile two rows of this warp further down.  Measured: 62.2 ->
+          // 67.9 us per launch — the kernel is HBM-bandwidth bound, not latency bound; default off.
+          if ((a.debug_probe & 65536) != 0 && hl_ly + 2 * kEpiGroups < H && hl_lg + 2 * kEpiGroups < g1) {
+            const int yp = flip ? H - 1 - (hl_ly + 2 * kEpiGroups) : hl_ly + 2 * kEpiGroups;
+            tma_prefetch_4d(&hl.m[0], 0, xs, yp, ba);
+            tma_prefetch_4d(&hl.m[1], 0, xs, yp, ba);
+          }
         }
         if (++hl_lslot == kHlSlots) hl_lslot = 0;
         if (++hl_lhalf == 2) {
@@ -693,16 +710,17 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           };
           mbar_wait(wbar, 0, 9);  // conv weights have landed in smem (generic-proxy reads below)
           for (int b = bimg_first + egrp; b <= bimg_last; b += kEpiGroups) {
-            const float4* pr = reinterpret_cast<const float4*>(a.pool_rows + static_cast<size_t>(b) * rows_img_e * 64) + cq;
-            const float4* cf = reinterpret_cast<const float4*>(a.col_first + static_cast<size_t>(b) * H * 64) + cq;
-            const float4* cl = reinterpret_cast<const float4*>(a.col_last + static_cast<size_t>(b) * H * 64) + cq;
+            const int ba = flip ? a.B - 1 - b : b;  // the image the statistics, attributes and meta scale belong to
+            const float4* pr = reinterpret_cast<const float4*>(a.pool_rows + static_cast<size_t>(ba) * rows_img_e * 64) + cq;
+            const float4* cf = reinterpret_cast<const float4*>(a.col_first + static_cast<size_t>(ba) * H * 64) + cq;
+            const float4* cl = reinterpret_cast<const float4*>(a.col_last + static_cast<size_t>(ba) * H * 64) + cq;
             // edge rows / corners of the stats (threads 0..63, one channel each): issued ahead of the row loops so
             // that their latency overlaps, consumed after the first barrier
             float r0v = 0.f, rlv = 0.f, k00 = 0.f, k0w = 0.f, kh0 = 0.f, khw = 0.f;
             if (et < 64) {
-              const float* prs = a.pool_rows + static_cast<size_t>(b) * rows_img_e * 64 + et;
-              const float* cfs = a.col_first + static_cast<size_t>(b) * H * 64 + et;
-              const float* cls = a.col_last + static_cast<size_t>(b) * H * 64 + et;
+              const float* prs = a.pool_rows + static_cast<size_t>(ba) * rows_img_e * 64 + et;
+              const float* cfs = a.col_first + static_cast<size_t>(ba) * H * 64 + et;
+              const float* cls = a.col_last + static_cast<size_t>(ba) * H * 64 + et;
               r0v = prs[0];
               rlv = prs[static_cast<size_t>(H - 1) * 64];
               k00 = cfs[0]; k0w = cls[0];
@@ -745,7 +763,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               reinterpret_cast<float4*>(tmp + (1 * 4 + w4) * 64)[cq] = c04;
               reinterpret_cast<float4*>(tmp + (2 * 4 + w4) * 64)[cq] = c14;
             }
-            for (int i = et; i < a.ca_A; i += 128) attr_s[i] = a.attributes[static_cast<size_t>(b) * a.ca_A + i];
+            for (int i = et; i < a.ca_A; i += 128) attr_s[i] = a.attributes[static_cast<size_t>(ba) * a.ca_A + i];
             grp.sync();
             float* S = tmp;  // [9][64], written once the partial sums have been consumed
             float Sv[9];
@@ -756,7 +774,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               const float CL = (tmp[512 + c] + tmp[576 + c]) + (tmp[640 + c] + tmp[704 + c]);
               float R0 = r0v, RL = rlv;
               for (int sg = 1; sg < nseg; ++sg) {  // images wider than one 128-px segment
-                const float* prs = a.pool_rows + static_cast<size_t>(b) * rows_img_e * 64 + c;
+                const float* prs = a.pool_rows + static_cast<size_t>(ba) * rows_img_e * 64 + c;
                 R0 += prs[(static_cast<size_t>(sg) * H) * 64];
                 RL += prs[(static_cast<size_t>(sg) * H + (H - 1)) * 64];
               }
@@ -804,13 +822,13 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             if (et < 64) {
               y_s[et] = bias_s[et] + (tmp[640 + 2 * et] + tmp[640 + 2 * et + 1]) * inv_hw;
               // training forward: the backward needs the pooled mean (every CTA touching image b writes the same bits)
-              if (a.ymean_out != nullptr) a.ymean_out[static_cast<size_t>(b) * 64 + et] = y_s[et];
+              if (a.ymean_out != nullptr) a.ymean_out[static_cast<size_t>(ba) * 64 + et] = y_s[et];
             }
             grp.sync();
             attn_vector(grp, a.ca_style, cap, 64, a.ca_R, a.ca_M, attr_s, y_s, s_s, tmp);
             if (et < 64)
               svec_s[(b - bimg_first) * 64 + et] =
-                  s_s[et] * (a.sq != nullptr ? a.sq[static_cast<size_t>(b) * 64 + et] : 1.f);
+                  s_s[et] * (a.sq != nullptr ? a.sq[static_cast<size_t>(ba) * 64 + et] : 1.f);
             grp.sync();
           }
         }
@@ -935,7 +953,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               for (int e = 0; e < 2; ++e) {
                 const int c = 8 * n + 2 * cq + e;
                 const float sc = a.epi_stats ? svec_s[(b - bimg_first) * 64 + c]
-                                             : (a.svec != nullptr ? a.svec[static_cast<size_t>(b) * 64 + c] : 1.f);
+                                             : (a.svec != nullptr ? a.svec[static_cast<size_t>(flip ? a.B - 1 - b : b) * 64 + c] : 1.f);
                 hl_s[2 * n + e] = sc;
                 hl_bs[2 * n + e] = bias_s[c] * sc;
               }
@@ -944,35 +962,59 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint8_t* buf = hl_base + hl_slot * (8 * kHlItemBytes);
+            const bool late_issue = (a.debug_probe & 131072) != 0;  // A/B switch (DFIR_DEBUG_PROBE)
+            if (lane == 0 && !late_issue) {
+              tma_store_wait_read<0>();  // the previous tile has left its buffer: that buffer takes the tile after next
+              hl_issue();
+            }
             mbar_wait(&hl_bar[hl_slot], hl_phase, 10);
             // word (pixel p, channels 8 n + 2 cq + {0,1}) of a tile: p * 128 + ((n ^ (p & 7)) << 4) + 4 cq (TMA 128B swizzle)
             uint8_t* wbase = buf + pr * 128 + 4 * cq;
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl) {
+              // all 16 loads of a pixel first, then the arithmetic, then the 16 stores: written as load / update / store
+              // per word the compiler must keep every load behind the previous word's store (same buffer), which
+              // serialises 16 shared-memory round trips (measured: 3000 clk per tile instead of ~700)
+              uint32_t hw[8], lw[8];
 #pragma unroll
               for (int n = 0; n < 8; ++n) {
-                uint32_t* ph = reinterpret_cast<uint32_t*>(wbase + sl * 1024 + ((n ^ pr) << 4));
-                uint32_t* pl = reinterpret_cast<uint32_t*>(wbase + 2048 + sl * 1024 + ((n ^ pr) << 4));
-                const uint32_t hw = *ph, lw = *pl;
+                hw[n] = *reinterpret_cast<const uint32_t*>(wbase + sl * 1024 + ((n ^ pr) << 4));
+                lw[n] = *reinterpret_cast<const uint32_t*>(wbase + 2048 + sl * 1024 + ((n ^ pr) << 4));
+              }
+#pragma unroll
+              for (int n = 0; n < 8; ++n) {
                 const uint32_t* src = half ? rb : ra;
-                const float x0 = __uint_as_float(hw << 16) + __uint_as_float(lw << 16);
-                const float x1 = __uint_as_float(hw & 0xffff0000u) + __uint_as_float(lw & 0xffff0000u);
+                const float x0 = __uint_as_float(hw[n] << 16) + __uint_as_float(lw[n] << 16);
+                const float x1 = __uint_as_float(hw[n] & 0xffff0000u) + __uint_as_float(lw[n] & 0xffff0000u);
                 const float o0 = fmaf(__uint_as_float(src[4 * n + 2 * sl]), hl_s[2 * n], hl_bs[2 * n]) + x0;
                 const float o1 = fmaf(__uint_as_float(src[4 * n + 2 * sl + 1]), hl_s[2 * n + 1], hl_bs[2 * n + 1]) + x1;
                 const uint32_t nh = pack_bf16x2(o0, o1);
-                *ph = nh;
-                *pl = pack_bf16x2(o0 - __uint_as_float(nh << 16), o1 - __uint_as_float(nh & 0xffff0000u));
+                hw[n] = nh;
+                lw[n] = pack_bf16x2(o0 - __uint_as_float(nh << 16), o1 - __uint_as_float(nh & 0xffff0000u));
+              }
+#pragma unroll
+              for (int n = 0; n < 8; ++n) {
+                *reinterpret_cast<uint32_t*>(wbase + sl * 1024 + ((n ^ pr) << 4)) = hw[n];
+                *reinterpret_cast<uint32_t*>(wbase + 2048 + sl * 1024 + ((n ^ pr) << 4)) = lw[n];
               }
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
               const int xs = seg * 128 + q * 32 + half * 16;
-              tma_store_4d(&hl.m[2], buf, 0, xs, y, b);
-              if (a.hl_store_lo) tma_store_4d(&hl.m[3], buf + 2048, 0, xs, y, b);
+              const int ya = flip ? H - 1 - y : y, ba = flip ? a.B - 1 - b : b;
+              if (a.use_hints) {
+                tma_store_4d_hint(&hl.m[2], buf, 0, xs, ya, ba, a.pol_out);
+                if (a.hl_store_lo) tma_store_4d_hint(&hl.m[3], buf + 2048, 0, xs, ya, ba, a.pol_f32);
+              } else {
+                tma_store_4d(&hl.m[2], buf, 0, xs, ya, ba);
+                if (a.hl_store_lo) tma_store_4d(&hl.m[3], buf + 2048, 0, xs, ya, ba);
+              }
               tma_store_commit();
-              tma_store_wait_read<1>();  // the tile before this one has left its buffer: that buffer takes the next load
-              hl_issue();
+              if (late_issue) {
+                tma_store_wait_read<1>();
+                hl_issue();
+              }
             }
             if (++hl_slot == kHlSlots) {
               hl_slot = 0;
@@ -1471,6 +1513,7 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   }
   ConvTcArgs a{};
   a.hl_store_lo = d.out_lo != nullptr ? 1 : 0;
+  a.flip = (hl_mode && d.flip && d.W <= 128) ? 1 : 0;
   a.B = d.B;
   a.H = d.H;
   a.W = d.W;
@@ -1515,7 +1558,7 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
       return c == 'f' ? ptx::kL2EvictFirst : (c == 'l' ? ptx::kL2EvictLast : ptx::kL2EvictNormal);
     };
     const bool conv1_role = d.epi == EPI_RELU_STATS || d.epi == EPI_BIAS_RELU;
-    const bool conv2_role = d.epi == EPI_SCALE_SKIP;
+    const bool conv2_role = d.epi == EPI_SCALE_SKIP || d.epi == EPI_SCALE_SKIP_HL;  // HL: letters 5, 6 = lo plane in / out
     if (pol != nullptr && strlen(pol) >= 6 && strncmp(pol, "nnnnnn", 6) != 0 && !fused && (conv1_role || conv2_role)) {
       a.use_hints = 1;
       a.pol_in = word(pol[conv1_role ? 0 : 2]);

@@ -65,6 +65,8 @@ struct ConvTcArgs {  // kernel argument block
   const void* next_w;       // packed weights of the NEXT conv of the chain (or nullptr): pulled into L2 at kernel start
   int next_w_bytes;
   int hl_store_lo;          // EPI_SCALE_SKIP_HL: also write the lo plane (0 = the result only feeds a conv: hi suffices)
+  int flip;                 // EPI_SCALE_SKIP_HL: traverse images and rows in DESCENDING order (the rows the previous,
+                            // ascending, kernel touched last are still in L2); requires W <= 128
 };
 
 // EPI_SCALE_SKIP_HL: tensor maps of the stream planes (box = 64 channels x 16 pixels, SWIZZLE_128B):
@@ -95,6 +97,7 @@ struct ConvTcDesc {  // host-side launch description
   const void* skip_hi = nullptr;  // EPI_SCALE_SKIP_HL: dense NHWC bf16 planes of the stream (out hi = out_bf16)
   const void* skip_lo = nullptr;
   void* out_lo = nullptr;         // nullptr: hi only
+  int flip = 0;                   // EPI_SCALE_SKIP_HL: descending traversal (see ConvTcArgs::flip)
   float* pool_rows;
   float* col_first;
   float* col_last;

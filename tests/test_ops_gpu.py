@@ -214,16 +214,24 @@ def test_pool_by_linearity_trio(shape, style):
     assert L.dfir_conv3x3_c64_scale_skip_hl(t_d.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), B, H, W, None, x_hi.data_ptr(),
                                             x_lo.data_ptr(), o_hi.data_ptr(), o_lo.data_ptr(), pool.data_ptr(),
                                             cf.data_ptr(), cl.data_ptr(), STYLE_ID[style], blob.data_ptr(), 4, M, A,
-                                            attr_d.data_ptr(), sq_d.data_ptr(), G.stream()) == 0
+                                            attr_d.data_ptr(), sq_d.data_ptr(), 0, G.stream()) == 0
     G.sync()
     got = o_hi.float() + o_lo.float()
     scale = out32.abs().max().item()
     assert (got - out32).abs().max().item() <= 2.0 ** -15 * scale, (got - out32).abs().max().item() / scale
     assert (o_hi.float() - out32).abs().max().item() <= 2.0 ** -8 * scale   # hi alone is the bf16 rounding of the stream
-    # in place, scale vector from memory, hi plane only as output of a second call
+    # descending traversal (images and rows from the last to the first), in-kernel attention: same values
+    d_hi, d_lo = torch.empty_like(o_hi), torch.empty_like(o_lo)
+    assert L.dfir_conv3x3_c64_scale_skip_hl(t_d.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), B, H, W, None, x_hi.data_ptr(),
+                                            x_lo.data_ptr(), d_hi.data_ptr(), d_lo.data_ptr(), pool.data_ptr(),
+                                            cf.data_ptr(), cl.data_ptr(), STYLE_ID[style], blob.data_ptr(), 4, M, A,
+                                            attr_d.data_ptr(), sq_d.data_ptr(), 1, G.stream()) == 0
+    G.sync()
+    assert ((d_hi.float() + d_lo.float()) - out32).abs().max().item() <= 2.0 ** -15 * scale
+    # in place, scale vector from memory, descending
     assert L.dfir_conv3x3_c64_scale_skip_hl(t_d.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), B, H, W, svec.data_ptr(),
                                             x_hi.data_ptr(), x_lo.data_ptr(), x_hi.data_ptr(), x_lo.data_ptr(), None, None,
-                                            None, 0, None, 4, M, A, None, None, G.stream()) == 0
+                                            None, 0, None, 4, M, A, None, None, 1, G.stream()) == 0
     G.sync()
     assert ((x_hi.float() + x_lo.float()) - out32).abs().max().item() <= 2.0 ** -15 * scale
     # group-conv use: no scale vector, in-place stream update

@@ -119,7 +119,7 @@ def ss_hl_sweep():
             _lib.check(lib.dfir_conv3x3_c64_scale_skip_hl(t.data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR,
                                                           sv.data_ptr(), xh.data_ptr(), xl.data_ptr(), xh.data_ptr(),
                                                           xl.data_ptr(), None, None, None, 0, None, 4, 10, 10, None, None,
-                                                          st()), "ss hl")
+                                                          int(os.environ.get("DESC", "0")), st()), "ss hl")
         us = timeit(launch, NREP[0], NREP[1])
         byt = bc * LR * LR * 64 * 10
         print("conv+scale_skip hi/lo stream bc=%3d: %8.2f us  %7.1f GB/s (10 B/elem)" % (bc, us, byt / us / 1e3))
@@ -149,11 +149,11 @@ def forward_sweep():
     B = 32
     x = torch.rand(B, 3, LR, LR, device=dev)
     meta = torch.rand(B, 10, 1, 1, device=dev) * 0.4
-    for chunk in (4, 7, 8, 9, 16, 32):
+    for chunk in tuple(int(t) for t in os.environ.get("CHUNKS", "8,12,16,24,32").split(",")):
         net = QRCAN(n_resgroups=10, n_resblocks=20, style="standard", num_metadata=10, include_q_layer=True,
                     precision="bf16", chunk_images=chunk).to(dev).eval()
         with torch.no_grad():
-            us = timeit(lambda: net(x, meta), n=3, warm=2)
+            us = timeit(lambda: net(x, meta), n=5, warm=2)
         print("forward B=32 chunk=%2d: %8.2f ms  %7.1f MPix/s" % (chunk, us / 1e3, B * (4 * LR) ** 2 / us))
         del net
 

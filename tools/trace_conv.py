@@ -25,6 +25,11 @@ b = torch.empty_like(a)
 x = torch.randn(bc, LR, LR, 64, device=dev)
 pool = torch.empty(bc, LR, 64, device=dev); cf = torch.empty(bc, LR, 64, device=dev); cl = torch.empty(bc, LR, 64, device=dev)
 sv = torch.rand(bc, 64, device=dev)
+xh = torch.randn(bc, LR, LR, 64, device=dev).to(torch.bfloat16)
+xl = (torch.randn(bc, LR, LR, 64, device=dev) * 1e-3).to(torch.bfloat16)
+pool.normal_(); cf.normal_(); cl.normal_()
+blob = torch.randn(4 * 74 + 4 + 64 * 4 + 64, device=dev) / 8
+attr = torch.rand(bc, 10, device=dev); sq = torch.rand(bc, 64, device=dev) * 0.1
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
@@ -35,6 +40,15 @@ def launch():
     elif mode == "stats":
         _lib.check(lib.dfir_conv3x3_c64_stats(a.data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR, b.data_ptr(),
                                               pool.data_ptr(), cf.data_ptr(), cl.data_ptr(), st()), "c1")
+    elif mode in ("sshl", "sshlstats"):
+        stats = mode == "sshlstats"
+        _lib.check(lib.dfir_conv3x3_c64_scale_skip_hl(a.data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR,
+                                                      None if stats else sv.data_ptr(), xh.data_ptr(), xl.data_ptr(),
+                                                      xh.data_ptr(), xl.data_ptr(), pool.data_ptr() if stats else None,
+                                                      cf.data_ptr() if stats else None, cl.data_ptr() if stats else None,
+                                                      1 if stats else 0, blob.data_ptr() if stats else None, 4, 10, 10,
+                                                      attr.data_ptr() if stats else None, sq.data_ptr() if stats else None,
+                                                      int(os.environ.get("DESC", "0")), st()), "sshl")
     else:
         _lib.check(lib.dfir_conv3x3_c64_scale_skip(a.data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR, sv.data_ptr(),
                                                    x.data_ptr(), x.data_ptr(), b.data_ptr(), None, None, None, 0, None, 4,
