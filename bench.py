@@ -243,8 +243,8 @@ def workload_config(n_img=None):
     n_img = n_img or IMAGES_PER_GPU
     return {"workload": "Q-RCAN x4 (10x20 RCAB, 64 ch, 10-D blur metadata) batched inference, "
                         "%d synthetic 128x128 LR images per GPU" % n_img,
-            "images_per_gpu": n_img, "lr_size": [LR, LR], "scale": SCALE, "precision": "bf16 operands, "
-            "fp32 accumulate + fp32 residual stream", "l2": "192 MiB buffer rewritten between timed steps",
+            "images_per_gpu": n_img, "lr_size": [LR, LR], "scale": SCALE, "precision": "bf16 operands, fp32 accumulate, "
+            "residual stream = bf16 hi + bf16 lo planes (16 significant bits)", "l2": "192 MiB buffer rewritten between timed steps",
             "sharding": "by image, no data-path collective"}
 
 
@@ -266,10 +266,17 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
+    # rank 0 times the CPU baselines BEFORE the process group exists: the other ranks then wait in the rendezvous (idle),
+    # not in an NCCL barrier that keeps their GPUs spinning
+    cpu = cpu_train = None
+    if rank == 0:
+        cpu = cpu_baseline(sample_images=2)
+        cpu_train = cpu_train_baseline()
     if world > 1:
+        import datetime
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(minutes=30))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     lib = _lib.load_library()
@@ -354,7 +361,7 @@ def run_ours(args):
         pk = peaks()
         ms_step = dev_ms / args.steps
         value = out_mpix_step / (ms_step / 1e3)
-        cpu = cpu_baseline(sample_images=2)
+        extra = other_configs(dev) if world == 1 else {}
         line = {
             "metric": "Q-RCAN x4 output MPix/s", "value": round(value, 3), "unit": "MPix/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4),
@@ -369,100 +376,174 @@ def run_ours(args):
             "roofline": roof,
             "roofline_conv1": roof_conv1,
             "cpu_baseline": cpu,
-            "train": dict(train, cpu_baseline=cpu_train_baseline()),
+            "train": dict(train, cpu_baseline=cpu_train),
             "tflops_conv_algorithmic": round(world * n_img * LR * LR * FLOP_PER_LR_PIXEL / (ms_step / 1e3) / 1e12, 2),
             "wall_s_timed_region": round(wall, 3),
             "peaks": pk["source"],
         }
+        line.update(extra)
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+# ncu evidence for the two trunk kernels at the bench shape (32 images per launch), committed under profiles/: DRAM bytes per
+# launch from the `--set full` captures, in-step duration and share of the step from the launch list of one forward
+NCU = {"source": "profiles/r02_tc_kernels_ncu.md, profiles/r02_launches_infer_32x128.csv",
+       "conv2_traffic": None, "conv2_in_step_us": None, "conv2_share": None, "conv1_traffic": None, "conv1_in_step_us": None,
+       "conv1_share": None}
+_ncu_path = os.path.join(ROOT, "profiles", "r02_ncu_numbers.json")
+if os.path.isfile(_ncu_path):
+    with open(_ncu_path) as _fh:
+        NCU.update(json.load(_fh))
+
+
 def conv_roofline(lib, dev, net):
-    """Times the trunk conv kernel alone (CUDA events on the launching stream) at the shape one launch of
-    the forward schedule sees: `chunk` images of 128x128x64, bias+ReLU epilogue."""
+    """Times the two trunk kernels alone (CUDA events on the launching stream), each in the form the default schedule
+    launches it at 32 images x 128x128x64:
+      conv1 = conv3x3 + bias + ReLU + the statistics of pool-by-linearity (dfir_conv3x3_c64_stats): tensor bound,
+      conv2 = conv3x3 + in-kernel channel/meta attention + scale + residual on the hi/lo stream, descending traversal
+              (dfir_conv3x3_c64_scale_skip_hl): HBM bound, 10 algorithmic bytes per element."""
     import ctypes as C
     from deepfir_b200 import _lib
     pk = peaks()
-    packed = net.packed()
-    ws_bytes = lib.dfir_qrcan_workspace_bytes(C.byref(packed.desc), IMAGES_PER_GPU, LR, LR, 0)
-    # chunk size the schedule uses (images per L2-resident pass): recover it from the launch count
-    launches = lib.dfir_qrcan_launch_count(C.byref(packed.desc), IMAGES_PER_GPU, LR, LR, 0)
-    per_chunk = 1 + 10 * (20 * 2 + 1) + 1 + 2 * 4 + 1  # default schedule: 2 launches per RCAB
-    chunks = max(1, (launches - 1) // per_chunk)
-    bc = (IMAGES_PER_GPU + chunks - 1) // chunks
-    a = torch.randn(bc, LR, LR, 64, device=dev).to(torch.bfloat16)
-    b = torch.empty_like(a)
+    bc = IMAGES_PER_GPU
     wp = torch.empty(9 * 64 * 128, dtype=torch.uint8, device=dev)
-    w = (torch.randn(64, 64, 3, 3, device=dev) / 24).contiguous()
+    w = (torch.randn(64, 64, 3, 3, device=dev) / 48).contiguous()
     bias = torch.zeros(64, device=dev)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     _lib.check(lib.dfir_pack_conv3x3_bf16(w.data_ptr(), wp.data_ptr(), 64, 64, 64, 0, 1, st), "pack")
+    NB = 3  # rotate over three buffer sets (3 x 200 MB > L2): every launch streams from HBM like in the real chain
+    xh = [torch.randn(bc, LR, LR, 64, device=dev).to(torch.bfloat16) for _ in range(NB)]
+    xl = [(torch.randn(bc, LR, LR, 64, device=dev) * 1e-3).to(torch.bfloat16) for _ in range(NB)]
+    t = [torch.empty(bc, LR, LR, 64, device=dev, dtype=torch.bfloat16) for _ in range(NB)]
+    pool = torch.empty(bc, LR, 64, device=dev)
+    cf, cl = torch.empty(bc, LR, 64, device=dev), torch.empty(bc, LR, 64, device=dev)
+    blob = torch.randn(4 * 74 + 4 + 64 * 4 + 64, device=dev) / 8   # QCALayer 'standard' + meta: the bench network's style
+    attr = torch.rand(bc, 10, device=dev)
+    sq = torch.rand(bc, 64, device=dev) * 0.1
+    k = [0]
 
-    def launch(src, dst):
-        _lib.check(lib.dfir_conv3x3_c64(src.data_ptr(), 64, 0, wp.data_ptr(), bias.data_ptr(), bc, LR, LR, 1, 64,
-                                        dst.data_ptr(), 128, LR * 128, LR * LR * 128, None, None, None, 0, st), "conv")
-    for _ in range(10):
-        launch(a, b)
-        launch(b, a)
-    torch.cuda.synchronize()
-    n = 100
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n // 2):
-        launch(a, b)
-        launch(b, a)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
+    def conv1():
+        i = k[0] = (k[0] + 1) % NB
+        _lib.check(lib.dfir_conv3x3_c64_stats(xh[i].data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR, t[i].data_ptr(),
+                                              pool.data_ptr(), cf.data_ptr(), cl.data_ptr(), st), "conv1")
+
+    def conv2():
+        i = k[0] = (k[0] + 1) % NB
+        _lib.check(lib.dfir_conv3x3_c64_scale_skip_hl(t[i].data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR, None,
+                                                      xh[i].data_ptr(), xl[i].data_ptr(), xh[i].data_ptr(), xl[i].data_ptr(),
+                                                      pool.data_ptr(), cf.data_ptr(), cl.data_ptr(), 1, blob.data_ptr(), 4,
+                                                      10, 10, attr.data_ptr(), sq.data_ptr(), 1, st), "conv2")
+
+    def timeit(fn, n=90):
+        for _ in range(9):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    for i in range(NB):
+        k[0] = i
+        conv1()
+    ms1 = timeit(conv1)
+    ms2 = timeit(conv2)
     flops = bc * LR * LR * CONV64_FLOP_PER_PIXEL
-    achieved = flops / (ms / 1e3) / 1e12
-    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full capture
-    # summarised in profiles/r01_conv_ts_mode_ncu.md (32 images per launch; algorithmic bytes = 2 x 67.1 MB)
-    # profiles/r01c_tc_kernels_ncu.md (conv1 with statistics, 32 images per launch): 71.8 MB read + 21.6 MB written
-    traffic = 93349888 if bc == 32 else None
-    conv1 = {"bound": "tensor", "kernel": "conv3x3_c64_tc_kernel<64, bias+relu> (RCAB conv1)", "achieved": round(achieved, 2),
-             "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": round(achieved / pk["tf_burst"], 4),
-             "traffic": traffic, "launch_us": round(ms * 1e3, 3), "images_per_launch": bc,
-             "algorithmic_flops_per_launch": flops, "peak_source": pk["source"] + ", burst (kernel timed alone)"}
-
-    # RCAB conv2 + channel/meta attention scale + residual add (EPI_SCALE_SKIP): the kernel with the largest share of
-    # the step (profiles/r01c_launches_infer_32x128.csv: 64 %).  It moves the fp32 residual stream and is bound by
-    # memory traffic: algorithmic bytes per element = t 2 (in) + x 4 (in) + x 4 (out) + bf16(x) 2 (out) = 12 B.
-    t_in = torch.randn(bc, LR, LR, 64, device=dev).to(torch.bfloat16)
-    x32 = torch.randn(bc, LR, LR, 64, device=dev)
-    xbf = torch.empty_like(t_in)
-    sv = torch.rand(bc, 64, device=dev)
-
-    def launch2():
-        _lib.check(lib.dfir_conv3x3_c64_scale_skip(t_in.data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR,
-                                                   sv.data_ptr(), x32.data_ptr(), x32.data_ptr(), xbf.data_ptr(), None,
-                                                   None, None, 0, None, 4, 10, 10, None, None, st), "scale_skip")
-    for _ in range(10):
-        launch2()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n):
-        launch2()
-    e1.record()
-    torch.cuda.synchronize()
-    ms2 = e0.elapsed_time(e1) / n
-    byt = bc * LR * LR * 64 * 12
+    achieved = flops / (ms1 / 1e3) / 1e12
+    conv1_d = {"bound": "tensor", "kernel": "conv3x3_c64_tc_kernel<64, bias+ReLU+statistics> (RCAB conv1, as the schedule launches it)",
+               "achieved": round(achieved, 2), "peak": pk["tf_burst"], "unit": "TFLOP/s",
+               "frac": round(achieved / pk["tf_burst"], 4), "traffic": NCU["conv1_traffic"],
+               "launch_us": round(ms1 * 1e3, 3), "images_per_launch": bc, "in_step_us_ncu": NCU["conv1_in_step_us"],
+               "share_of_step_ncu": NCU["conv1_share"], "algorithmic_flops_per_launch": flops,
+               "algorithmic_bytes_per_launch": bc * LR * LR * 64 * 4,
+               "hbm_gbs": round(bc * LR * LR * 64 * 4 / (ms1 / 1e3) / 1e9, 1),
+               "source": NCU["source"], "peak_source": pk["source"] + ", burst (kernel timed alone)"}
+    byt = bc * LR * LR * 64 * 10   # t 2 in, hi 2 + lo 2 in, hi 2 + lo 2 out
     gbs = byt / (ms2 / 1e3) / 1e9
-    # same capture file (conv2_ss): dram 231.6 MB read + 152.7 MB written per launch (ncu replay, cold L2 except the lines
-    # the preceding conv1 left there) — below the 402.7 MB of algorithmic bytes, i.e. no wasted re-reads.
-    # in_step_us_ncu / share_of_step_ncu: the same kernel inside the real forward, from the committed launch list
-    # profiles/r01c_launches_infer_32x128.csv (serialised, cold caches: 211 launches x 85.4 us = 64.3 % of the step).
-    conv2 = {"bound": "hbm", "kernel": "conv3x3_c64_tc_kernel<64, scale+skip> (RCAB conv2 + attention scale + residual)",
-             "achieved": round(gbs, 1), "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(gbs / pk["hbm_gbs"], 4),
-             "traffic": 384265728 if bc == 32 else None, "launch_us": round(ms2 * 1e3, 3), "images_per_launch": bc,
-             "in_step_us_ncu": 85.4 if bc == 32 else None, "share_of_step_ncu": 0.643 if bc == 32 else None,
-             "algorithmic_bytes_per_launch": byt, "tensor_tflops": round(flops / (ms2 / 1e3) / 1e12, 1),
-             "peak_source": pk["source"] + " (STREAM-style copy)"}
-    return conv2, conv1
+    conv2_d = {"bound": "hbm", "kernel": "conv3x3_c64_tc_kernel<64, scale+skip on the hi/lo stream> (RCAB conv2 + in-kernel "
+                                          "channel/meta attention + scale + residual, as the schedule launches it)",
+               "achieved": round(gbs, 1), "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(gbs / pk["hbm_gbs"], 4),
+               "traffic": NCU["conv2_traffic"], "launch_us": round(ms2 * 1e3, 3), "images_per_launch": bc,
+               "in_step_us_ncu": NCU["conv2_in_step_us"], "share_of_step_ncu": NCU["conv2_share"],
+               "algorithmic_bytes_per_launch": byt, "tensor_tflops": round(flops / (ms2 / 1e3) / 1e12, 1),
+               "source": NCU["source"], "peak_source": pk["source"] + " (STREAM-style copy)"}
+    return conv2_d, conv1_d
+
+
+def other_configs(dev):
+    """BASELINE.json configs[2] (Q-EDSR x4, 32 blocks x 256 features, one 480x270 frame) and configs[4] (Q-SAN x4 on
+    128x128 images, direct and through the handler's quadrant chop): device time per step, a few steps each, so that the
+    driver sees them (N = 1 only)."""
+    from SISR.models import ModelInterface
+    from deepfir_b200.qrcan import QEDSR
+    out = {}
+
+    def timeit(fn, n):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    try:
+        torch.manual_seed(8)
+        g = torch.Generator().manual_seed(8)
+        net = QEDSR(precision="bf16", num_blocks=32, num_features=256, input_para=10, scale=4, res_scale=0.1,
+                    q_layer_nonlinearity=False).to(dev).eval()
+        x = torch.rand(1, 3, 270, 480, generator=g).to(dev)
+        meta = (torch.rand(1, 10, 1, 1, generator=g) * 0.4).to(dev)
+        with torch.no_grad():
+            ms = timeit(lambda: net(x, meta), 5)
+        flop = 100505088 * 270 * 480
+        out["qedsr_c3"] = {"workload": "Q-EDSR x4 (32 resblocks, 256 ch) inference, one synthetic 480x270 LR frame",
+                           "ms_per_frame": round(ms, 3), "fps": round(1e3 / ms, 2),
+                           "output_mpix_s": round(1080 * 1920 / 1e6 / (ms / 1e3), 2),
+                           "tflops_algorithmic": round(flop / ms / 1e9, 1),
+                           "frac_of_bf16_peak": round(flop / ms / 1e9 / peaks()["tf_burst"], 4)}
+        del net
+        torch.cuda.empty_cache()
+    except Exception as e:  # an auxiliary section must never take the headline line down
+        out["qedsr_c3"] = {"error": repr(e)[:200]}
+    try:
+        torch.manual_seed(8)
+        B = 8
+        h = ModelInterface.define_model("qsan", device=dev.index or 0, model_save_dir=tempfile.gettempdir(), eval_mode=True,
+                                        scale=4, metadata=["blur_kernel"], max_combined_im_size=20000)
+        with torch.no_grad():
+            for p in (h.net.gamma, h.net.non_local.non_local.W.weight, h.net.non_local.non_local.W.bias):
+                p.normal_(0, 0.1)  # the reference zero-initialises these branches; they must do real work here
+        g = torch.Generator().manual_seed(8)
+        x = torch.rand(B, 3, 128, 128, generator=g)
+        meta = torch.rand(B, 10, generator=g, dtype=torch.float64) * 0.4
+        keys = [("blur_kernel",) * B] * 10
+        xd = x.to(dev)
+        attr = h.generate_channels(x, meta, keys).to(dev)
+        with torch.no_grad():
+            ms_direct = timeit(lambda: h.net(xd, attr), 3)
+        xp = x.pin_memory()
+        ms_chop = timeit(lambda: h.run_eval(xp, metadata=meta, metadata_keys=keys), 3)
+        out["qsan_c5"] = {"workload": "Q-SAN x4 (20 groups x 10 blocks, covariance pooling + Newton-Schulz, region non-local), "
+                                      "%d synthetic 128x128 LR images" % B,
+                          "ms_direct_forward": round(ms_direct, 3),
+                          "output_mpix_s_direct": round(B * 512 * 512 / 1e6 / (ms_direct / 1e3), 2),
+                          "ms_handler_run_eval_chop": round(ms_chop, 3),
+                          "output_mpix_s_handler": round(B * 512 * 512 / 1e6 / (ms_chop / 1e3), 2),
+                          "api": "QSANHandler.run_eval (4 overlapping 74x74 quadrants, host in / host out)"}
+        del h
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["qsan_c5"] = {"error": repr(e)[:200]}
+    return out
 
 
 def cpu_baseline(sample_images=2, threads=None):

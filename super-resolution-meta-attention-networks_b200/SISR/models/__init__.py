@@ -305,9 +305,19 @@ class BaseModel(nn.Module):
             raise NotImplementedError('perceptual loss (VGG feature extractors) is outside the B200 hot path')
 
     def set_multi_gpu(self, device_ids=None):
-        self.net = nn.DataParallel(self.net, device_ids=device_ids)
-        if len(self.net.device_ids) > 1:
-            print('Model sent to multiple GPUs:', ', '.join([str(d_id) for d_id in self.net.device_ids]))
+        """The reference wraps the network in nn.DataParallel (models/__init__.py:307).  The B200 networks keep device
+        pointer tables, a workspace and a flat gradient buffer per device and cannot be replicated by DataParallel's
+        shallow module copies, so more than one device is refused here: multi-GPU runs are one process per GPU
+        (torchrun; inference sharded by image with deepfir_b200.sharding, training with the NCCL gradient all-reduce of
+        QModel.run_train — see INTEGRATION.md).  A single device keeps the reference's wrapper-free behaviour."""
+        ids = list(device_ids) if device_ids is not None else list(range(torch.cuda.device_count()))
+        if len(ids) > 1:
+            raise NotImplementedError(
+                "gpu='multi' (nn.DataParallel) is not supported by the B200 path: launch one process per GPU "
+                "(python -m torch.distributed.run --nproc-per-node N ...); see INTEGRATION.md, 'Multi-GPU'")
+        if ids and isinstance(self.device, int) and ids[0] != self.device:
+            self.device = ids[0]
+            self.net.to(self.device)
 
     # -- checkpoints -------------------------------------------------------------------------
     def save_model(self, model_save_name, model_idx, extract_state_only=False):

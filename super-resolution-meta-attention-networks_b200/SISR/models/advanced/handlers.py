@@ -82,10 +82,10 @@ class SANHandler(BaseModel):
         return QSANHandler.forward_chop(self, x, None, shave=shave)
 
     def run_chopped_eval(self, x, extra_channels=None):
-        return BaseModel.run_eval(self, x.contiguous(), request_loss=False)[0]
+        return BaseModel.run_eval(self, x.contiguous(), request_loss=False, keep_on_device=True)[0]
 
     def run_eval(self, x, y=None, request_loss=False, metadata=None, metadata_keys=None, timing=False, *args, **kwargs):
         started = time.perf_counter()
-        sr_image = self.forward_chop(x)
+        sr_image = self._to_host(self.forward_chop(x.to(self.device)))  # four quadrants as one batch, one H2D, one D2H
         elapsed = time.perf_counter() - started
         return sr_image, (self.criterion(sr_image, y) if request_loss else None), (elapsed if timing else None)

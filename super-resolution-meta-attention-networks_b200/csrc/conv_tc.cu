@@ -1138,8 +1138,10 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           issue_skip(g + kEpiGroups, 1);
           if (q == 0) DFIR_TRACE(14 + egrp, it >> 1);
         } else {
-          // one group: the two staging buffers alternate; two groups: it & 1 == egrp, each group owns one buffer
-          const int sb = it & 1;
+          // one group: the two staging buffers alternate.  Two groups: each group alternates between two buffers of its
+          // own (the skip buffers of the scale+skip epilogue are free here), so a row never waits for the TMA store of the
+          // group's previous row to drain its staging tile (measured: ~800 clk per row on the epilogue's critical path)
+          const int sb = kTwoEpi ? (egrp * 2 + ((it >> 1) & 1)) : (it & 1);
           uint8_t* st = stage + sb * kStageBytes;
           float* pool_g = pool_s + egrp * 256;
           const uint32_t bar_c = 1 + 2 * egrp, bar_d = 2 + 2 * egrp;
@@ -1158,9 +1160,10 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             if (lane == 0) mbar_arrive(&go[acc]);
             if (q == 0) DFIR_TRACE(10 + 3 * egrp, it >> (kTwoEpi ? 1 : 0));
             if (et == 0) {  // the TMA store that read this staging buffer has drained it
-              if constexpr (kTwoEpi) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+              tma_store_wait_read<1>();
             }
             named_bar_sync(bar_c, 128);
+            if (q == 0 && egrp == 0) DFIR_TRACE(11, it >> 1);  // staging tile free
             const int pr = lane >> 2, cq = lane & 3;       // pixel row of the fragment, channel pair within a block of 8
             float bias_r[16];
 #pragma unroll
@@ -1218,6 +1221,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
                 }
               }
             }
+            if (q == 0 && egrp == 0) DFIR_TRACE(12, it >> 1);  // values computed and staged
             if constexpr (EPI == EPI_BIAS_POOL || EPI == EPI_RELU_STATS) {
               // transposing butterfly over the 8 pixel rows of the fragment (lane bits 2..4): 8 + 4 + 2 shuffles; on exit
               // sums[0], sums[1] are the warp's 32-pixel sums of channels 8 n + 2 cq + {0, 1}, n = lane bits (4, 3, 2)
@@ -1248,7 +1252,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           if (lane == 0) mbar_arrive(&go[acc]);
           if (q == 0) DFIR_TRACE(10 + 3 * egrp, it >> (kTwoEpi ? 1 : 0));
           if (et == 0) {  // the TMA store that read this staging buffer has drained it
-            if constexpr (kTwoEpi) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+            tma_store_wait_read<1>();
           }
           named_bar_sync(bar_c, 128);
           const size_t pix = (static_cast<size_t>(b) * a.H + y) * a.W + x;
@@ -1334,8 +1338,10 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             }
           }
           }  // !kQuad
+          if (q == 0 && egrp == 0) DFIR_TRACE(13, it >> 1);  // channel sums done
           fence_proxy_async_smem();
           named_bar_sync(bar_d, 128);
+          if (q == 0 && egrp == 0) DFIR_TRACE(15, it >> 1);  // whole group past the second barrier
           if (et == 0 && !exp_skip_store) {
             if (a.use_hints) tma_store_4d_hint(&tmap_out, st, 0, seg * 128, y, b, a.pol_out);
             else tma_store_4d(&tmap_out, st, 0, seg * 128, y, b);

@@ -158,7 +158,7 @@ size_t soca_scratch_floats(int B);
 int nonlocal_forward(const float* x, const float* wq, const float* bq, const float* wW, const float* bW, float* out,
                      float* scratch, int B, int H, int W, int C, cudaStream_t s);
 size_t nonlocal_scratch_floats(int B, int H, int W);
-// ---- training step (train_kernels.cu, wgrad_mma.cu)
+// ---- training step (train_kernels.cu, wgrad_tc.cu)
 int pack_bf16_multi(const float* const* tbl, const float* direct, void* out, int n_tiles, int cout, int nt_rows,
                     int per_src, int transpose, cudaStream_t s, int j0 = 0);
 int pack_f32_multi(const float* const* tbl, const float* direct, float* out, int n, int cout, int cin, int transpose,
@@ -192,12 +192,9 @@ int attn_param_grads(const float* sig, int sig_stride, const float* attributes, 
                      float* const* meta_g, int nblk, int B, int C, int R, int M, int Hid, int style, int meta_relu,
                      cudaStream_t s);
 int wgrad_c64_grid(int B, int H, int W, int num_sms);
-int wgrad_c64_bf16(const void* dy, long long dy_pix, long long dy_row, long long dy_img, const void* x, float* scratch,
-                   int B, int H, int W, int num_sms, cudaStream_t s, int* S_out);   // mma.sync version
 int wgrad_c64_tc(const void* dy, long long dy_pix, long long dy_row, long long dy_img, const void* x, float* scratch, int B,
                  int H, int W, int num_sms, cudaStream_t s, int* S_out);            // tcgen05 version (default)
 int wgrad_tc_watchdog(unsigned int* out8, int reset);
-// dispatcher: DFIR_WGRAD=mma selects the mma.sync kernel
 int wgrad_c64(const void* dy, long long dy_pix, long long dy_row, long long dy_img, const void* x, float* scratch, int B,
               int H, int W, int num_sms, cudaStream_t s, int* S_out);
 int nchw_to_nhwc_bf16(const float* in, __nv_bfloat16* out, int B, int C, int H, int W, cudaStream_t s);

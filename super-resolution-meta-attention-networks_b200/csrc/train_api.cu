@@ -10,7 +10,7 @@
 //   dW2,db2 = wgrad(dr, t);   dz = dgrad(dr, W2) masked by t > 0
 //   dW1,db1 = wgrad(dz, x);   g  = dgrad(dz, W1) + g
 // The data-gradient convs are the forward tensor-core kernel fed with transposed / rotated weights; the weight
-// gradients are csrc/wgrad_mma.cu (bf16) or wgrad_f32 (parity mode).
+// gradients are csrc/wgrad_tc.cu (bf16, tcgen05) or wgrad_f32 (parity mode).
 #include "kernels.h"
 #include "attn.cuh"
 
@@ -680,7 +680,9 @@ int dfir_conv3x3_wgrad_c64(const void* dy, long long dps, long long drs, long lo
   int S_ = 0;
   float* sc = reinterpret_cast<float*>(scratch);
   DFIR_TRY(wgrad_c64(dy, dps, drs, dis, x, sc, B, H, W, std::min(sms, 160), S(stream), &S_));
+#ifdef DFIR_PROBES
   if (getenv("DFIR_WGRAD_PROBE") != nullptr && (atoi(getenv("DFIR_WGRAD_PROBE")) & 8)) return DFIR_OK;  // timing only
+#endif
   return wgrad_reduce(sc, sc + static_cast<size_t>(S_) * 9 * 64 * 64, S_, 64, 64, nullptr, 0, dw, nullptr, 0, db, co_begin,
                       co_stride, S(stream), wgrad_c64_co_major());
 }

@@ -252,7 +252,7 @@ wgrad_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 
 }  // namespace
 
-// Same contract as wgrad_c64_bf16 (wgrad_mma.cu): partial sums + bias partials into scratch, reduced by wgrad_reduce.
+// Contract: partial sums + bias partials into scratch, reduced by wgrad_reduce.
 int wgrad_c64_tc(const void* dy, long long dy_pix, long long dy_row, long long dy_img, const void* x, float* scratch, int B,
                  int H, int W, int num_sms, cudaStream_t s, int* S_out) {
   if (B <= 0 || H <= 0 || W <= 0) return DFIR_ERR_ARG;
@@ -278,7 +278,11 @@ int wgrad_c64_tc(const void* dy, long long dy_pix, long long dy_row, long long d
   a.part = scratch;
   a.dbpart = scratch + static_cast<size_t>(grid) * 9 * 64 * 64;
   a.B = B; a.H = H; a.W = W; a.nseg = (W + 127) / 128;
+#ifdef DFIR_PROBES  // timing experiments (wrong results) exist only in a `make PROBES=1` build
   a.probe = getenv("DFIR_WGRAD_PROBE") != nullptr ? atoi(getenv("DFIR_WGRAD_PROBE")) : 0;
+#else
+  a.probe = 0;
+#endif
   return launch_pdl(PDL_WGRAD, wgrad_c64_tc_kernel, dim3(grid), dim3(kWtThreads), kWtSmem, s, tx, td, a) == cudaSuccess
              ? DFIR_OK
              : DFIR_ERR_CUDA;
@@ -293,17 +297,19 @@ int wgrad_tc_watchdog(unsigned int* out8, int reset) {
   return DFIR_OK;
 }
 
-static bool wgrad_use_mma() {
-  static const bool use_mma = getenv("DFIR_WGRAD") != nullptr && getenv("DFIR_WGRAD")[0] == 'm';
-  return use_mma;
+// number of partial-sum CTAs (= scratch slices) of a weight-gradient launch
+int wgrad_c64_grid(int B, int H, int W, int num_sms) {
+  const long long G = static_cast<long long>(B) * ((W + 127) / 128) * H;
+  int grid = num_sms > 0 ? num_sms : 148;
+  if (G < grid) grid = static_cast<int>(G);
+  return grid < 1 ? 1 : grid;
 }
-int wgrad_c64_co_major() { return wgrad_use_mma() ? 0 : 1; }
+
+int wgrad_c64_co_major() { return 1; }
 
 int wgrad_c64(const void* dy, long long dy_pix, long long dy_row, long long dy_img, const void* x, float* scratch, int B,
               int H, int W, int num_sms, cudaStream_t s, int* S_out) {
-  const bool use_mma = wgrad_use_mma();
-  return use_mma ? wgrad_c64_bf16(dy, dy_pix, dy_row, dy_img, x, scratch, B, H, W, num_sms, s, S_out)
-                 : wgrad_c64_tc(dy, dy_pix, dy_row, dy_img, x, scratch, B, H, W, num_sms, s, S_out);
+  return wgrad_c64_tc(dy, dy_pix, dy_row, dy_img, x, scratch, B, H, W, num_sms, s, S_out);
 }
 
 }  // namespace dfir

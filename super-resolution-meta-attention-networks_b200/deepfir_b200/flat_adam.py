@@ -92,9 +92,10 @@ class FlatAdam(torch.optim.Adam):
         if g0 is None or not g0.is_cuda or g0.dtype != torch.float32:
             return None
         base = g0.data_ptr()
-        for idx in (len(ps) // 2, len(ps) - 1):
+        offs = f["offsets"]
+        for idx in range(1, len(ps)):  # every gradient must be the slice of the flat buffer at its parameter's offset
             g = ps[idx].grad
-            if g is None or g.data_ptr() != base + 4 * f["offsets"][idx]:
+            if g is None or g.data_ptr() != base + 4 * offs[idx]:
                 return None
         root = g0._base if g0._base is not None else g0
         if root.numel() < f["total"] or root.data_ptr() != base or not root.is_contiguous():
@@ -142,6 +143,16 @@ class FlatAdam(torch.optim.Adam):
             st["step"] = f["step_t"]
         f["step_t"].fill_(float(f["step"]))
         return loss
+
+    def state_dict(self):
+        """torch.optim.Adam's layout with an INDEPENDENT `step` tensor per parameter: internally all parameters share
+        one step tensor, and a checkpoint that kept the aliasing would make a stock Adam advance the step once per
+        parameter and iteration after loading it (torch.save preserves storage sharing)."""
+        sd = super().state_dict()
+        for st in sd["state"].values():
+            if "step" in st:
+                st["step"] = torch.tensor(float(st["step"]), dtype=torch.float32)
+        return sd
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)

@@ -45,6 +45,23 @@ class _StagedNet(nn.Module):
         self._packed = None
         return super()._apply(fn, *a, **k)
 
+    def invalidate_packed(self):
+        """rebuild the kernel-format parameters on the next forward (see QRCAN.invalidate_packed: needed after in-place
+        writes through `.data`, which `Parameter._version` does not see)"""
+        if self._packed is not None:
+            self._packed.close()
+        self._packed = None
+
+    def train(self, mode=True):
+        if self.training and not mode:
+            self.invalidate_packed()
+        return super().train(mode)
+
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)
+        self.invalidate_packed()
+        return out
+
     # -- staged trunk -------------------------------------------------------------------------------
     def _stages(self, pk, stages, g0, g1, B, H, W, x=None, attr=None, feat_in=None, group_out=None, feat_out=None,
                 out=None):

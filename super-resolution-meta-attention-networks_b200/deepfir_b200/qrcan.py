@@ -252,9 +252,29 @@ class QRCAN(nn.Module):
         self.__dict__.pop("_plist", None)
         return super()._apply(fn, *a, **k)
 
+    def invalidate_packed(self):
+        """Forces the kernel-format copies of the parameters (packed bf16 tiles, attention blobs, the wide-net planes) to
+        be rebuilt from the nn.Parameters on the next forward.  The cache follows `Parameter._version`, which in-place
+        writes through `.data` or any other alias do NOT bump (`p.data.copy_()`, weight averaging / EMA code, kernels that
+        write the storage directly): call this after such a write.  `load_state_dict`, `.to()` and a train() -> eval()
+        transition call it themselves."""
+        pk = self.__dict__.get("_packed")
+        if pk is None:
+            pk = getattr(self, "_packed", None)
+        if pk is not None:
+            pk.versions = None
+        self.__dict__.pop("_wide_key", None)
+
+    def train(self, mode=True):
+        if self.training and not mode:
+            self.invalidate_packed()  # whatever trained the parameters may have written them behind autograd's back
+        return super().train(mode)
+
     def load_state_dict(self, *a, **k):
         self.__dict__.pop("_plist", None)  # (assign=True replaces the Parameter objects)
-        return super().load_state_dict(*a, **k)
+        out = super().load_state_dict(*a, **k)
+        self.invalidate_packed()
+        return out
 
 
 class QEDSRBlockParams(nn.Module):
@@ -277,6 +297,11 @@ class QEDSR(QRCAN):
         nn.Module.__init__(self)
         if precision not in PRECISIONS:
             raise RuntimeError("precision must be 'bf16' or 'fp32'")
+        if num_features % 8 or num_features > 256 or 256 % num_features:
+            # the CUDA-core kernels (fp32 parity mode, training of wide nets) split 256-thread blocks by channel
+            raise RuntimeError("Q-EDSR feature width %d is not supported: use a divisor of 256 that is a multiple of 8 "
+                               "(64 = tensor-core kernels for inference and training, 128 / 256 = tensor-core inference as "
+                               "64-channel planes + fp32 training; 192 is not available)" % num_features)
         if schedule not in SCHEDULES:
             raise RuntimeError("schedule must be one of %s" % sorted(SCHEDULES))
         self.style = "none"
@@ -301,7 +326,7 @@ class QEDSR(QRCAN):
         wide = self.precision == "bf16" and self.cfg["n_feats"] > 64 and self.cfg["n_feats"] % 64 == 0
         if not wide:
             return super().forward(x, metadata)
-        # 128 / 192 / 256 features: 64-channel planes through the tensor-core kernels (deepfir_b200/wide.py)
+        # 128 / 256 features: 64-channel planes through the tensor-core kernels (deepfir_b200/wide.py)
         if not x.is_cuda:
             raise RuntimeError("deepfir_b200.QEDSR runs on a CUDA (sm_100a) device only: there is no CPU path")
         if torch.is_grad_enabled() and self.head.weight.requires_grad:

@@ -143,6 +143,12 @@ class _QrcanTrain(torch.autograd.Function):
 
 
 def qrcan_train_apply(net, packed, x, attr):
+    if x.requires_grad or attr.requires_grad:
+        # the backward pass of the library produces parameter gradients only (the reference's training loop never asks
+        # for more, models/__init__.py:466-489): refuse instead of silently returning no gradient for the inputs
+        raise RuntimeError("the B200 training path does not compute gradients with respect to the input image or the "
+                           "metadata: detach them (x.requires_grad=%s, metadata.requires_grad=%s)"
+                           % (x.requires_grad, attr.requires_grad))
     anchor = getattr(net, "_train_anchor", None)
     if anchor is None or anchor.device != x.device:
         anchor = torch.zeros(1, device=x.device, requires_grad=True)

@@ -305,3 +305,36 @@ def test_bench_clock_sampler_uses_only_lines_inside_the_timed_region(tmp_path):
     s.proc, s.path, s.t0, s.t1 = _Done(), str(path), t0, t0 + 0.1
     out = s.stop()
     assert out["samples"] == 0 and out["sm_mhz"] is None
+
+
+def test_set_multi_gpu_refuses_data_parallel_replication():
+    """the reference wraps the net in nn.DataParallel (models/__init__.py:307); the B200 networks hold per-device pointer
+    tables and must not be replicated that way: more than one device raises and points at one process per GPU"""
+    import tempfile
+    from SISR.models import ModelInterface
+    h = ModelInterface.define_model("qrcan", device=torch.device("cpu"), model_save_dir=tempfile.gettempdir(), eval_mode=True,
+                                    metadata=["blur_kernel"], n_resgroups=1, n_resblocks=1)
+    with pytest.raises(NotImplementedError, match="one process per GPU"):
+        h.set_multi_gpu(device_ids=[0, 1])
+    h.set_multi_gpu(device_ids=[])          # nothing to do: no wrapper module appears
+    assert not isinstance(h.net, torch.nn.DataParallel)
+
+
+def test_unsupported_qedsr_width_fails_loudly():
+    from deepfir_b200.qrcan import QEDSR
+    with pytest.raises(RuntimeError, match="192 is not available"):
+        QEDSR(num_features=192, num_blocks=1, input_para=10)
+    QEDSR(num_features=128, num_blocks=1, input_para=10)
+
+
+def test_flat_adam_state_dict_has_one_step_tensor_per_parameter():
+    """the checkpoint must be loadable by a stock torch.optim.Adam: independent step tensors"""
+    from deepfir_b200.flat_adam import FlatAdam
+    ps = [torch.nn.Parameter(torch.randn(3, 3)) for _ in range(4)]
+    opt = FlatAdam(ps, lr=1e-3)
+    sum((p ** 2).sum() for p in ps).backward()
+    opt.step()
+    sd = opt.state_dict()
+    steps = [st["step"] for st in sd["state"].values()]
+    assert len(steps) == 4 and all(float(t) == 1.0 for t in steps)
+    assert len({id(t) for t in steps}) == 4 and len({t.untyped_storage().data_ptr() for t in steps}) == 4

@@ -367,6 +367,18 @@ def test_flat_adam_matches_torch_adam_and_checkpoints_like_it(tmp_path):
     assert set(sd_flat["state"][0]) == set(sd_ref["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
     assert float(sd_flat["state"][0]["step"]) == float(sd_ref["state"][0]["step"]) == 4.0
     torch.save(sd_flat, tmp_path / "opt.pt")
+    # a STOCK Adam resumes from the checkpoint: every parameter has its own step tensor (the flat optimizer shares one
+    # internally; a checkpoint that kept the aliasing would advance the step once per parameter and iteration)
+    loaded = torch.load(tmp_path / "opt.pt")
+    steps = [st["step"] for st in loaded["state"].values()]
+    assert len({t.untyped_storage().data_ptr() for t in steps}) == len(steps)
+    torch.manual_seed(9)
+    net4 = QRCAN(precision="fp32", **kw).cuda().train()
+    net4.load_state_dict(nets[1].state_dict())
+    opt4 = torch.optim.Adam(net4.parameters(), lr=1e-3, betas=(0.9, 0.99))
+    opt4.load_state_dict(loaded)
+    step(net4, opt4)
+    assert all(float(st["step"]) == 5.0 for st in opt4.state.values())
     torch.manual_seed(9)
     net3 = QRCAN(precision="fp32", **kw).cuda().train()
     net3.load_state_dict(nets[1].state_dict())
@@ -412,3 +424,39 @@ def test_training_a_network_without_backward_kernels_fails_loudly():
     with pytest.raises(NotImplementedError):
         out = net(x.cuda(), meta.cuda())
         F.l1_loss(out, torch.zeros_like(out)).backward()
+
+
+def test_inputs_that_require_grad_are_refused():
+    """the library's backward produces parameter gradients only: an input that asks for a gradient must raise, not get
+    a silent None"""
+    _, info = load_golden("qrcan_noq_scale2")
+    net, sd, x, meta = _build(info, "fp32")
+    xg = x.cuda().requires_grad_(True)
+    with pytest.raises(RuntimeError, match="gradients with respect to the input"):
+        net(xg, meta.cuda())
+
+
+def test_invalidate_packed_after_a_write_through_data():
+    """`p.data.mul_()` does not bump Parameter._version, so the packed kernel weights would go stale: the documented
+    remedy is net.invalidate_packed() (load_state_dict and train() -> eval() call it themselves)"""
+    _, info = load_golden("qrcan_noq_scale2")
+    for precision in ("fp32", "bf16"):
+        net, sd, x, meta = _build(info, precision)
+        net.eval()
+        with torch.no_grad():
+            a = net(x.cuda(), meta.cuda()).clone()
+            tail = [p for k, p in net.named_parameters() if k.endswith("tail.1.weight")][0]
+            v = tail._version
+            tail.data.mul_(2.0)
+            assert tail._version == v          # the write is invisible to the version counter
+            net.invalidate_packed()
+            b = net(x.cuda(), meta.cuda())
+            bias = [p for k, p in net.named_parameters() if k.endswith("tail.1.bias")][0]
+            want = 2.0 * (a - bias.reshape(1, -1, 1, 1)) + bias.reshape(1, -1, 1, 1)
+        assert float((b - want).abs().max()) <= 2e-2 * float(want.abs().max()) + 1e-6, precision
+        # train() -> eval() transition repacks as well
+        with torch.no_grad():
+            tail.data.mul_(0.5)
+            net.train(); net.eval()
+            c = net(x.cuda(), meta.cuda())
+        assert float((c - a).abs().max()) <= 1e-5 + 1e-5 * float(a.abs().max()), precision

@@ -67,9 +67,9 @@ tr = [[buf[k * 64 + i] for i in range(64)] for k in range(16)]
 t0 = min(v for row in tr for v in row if v)
 names = ["tma_issue", "ld_full", "ld_aempty", "ld_done", "mma_top", "mma_24", "mma_waited", "mma_36", "e0_wait", "e0_tfull",
          "e0_release", "e1_wait", "e1_tfull", "e1_release", "e0_end", "e1_end"]
-if mode == "conv1":
-    names[11:14] = ["mma_1", "mma_12", "mma_commit"]
-    names[15] = "mma_tfullc"
+if mode in ("conv1", "stats"):
+    names[11:14] = ["e0_stfree", "e0_staged", "e0_sums"]
+    names[15] = "e0_bar2"
 print("mode %s bc %d (SM clocks relative to the first event; 0 = not recorded)" % (mode, bc))
 print("row " + " ".join("%10s" % n for n in names))
 for i in range(34):
