@@ -297,11 +297,12 @@ class QEDSR(QRCAN):
         nn.Module.__init__(self)
         if precision not in PRECISIONS:
             raise RuntimeError("precision must be 'bf16' or 'fp32'")
-        if num_features % 8 or num_features > 256 or 256 % num_features:
+        bf16_planes = precision == 'bf16' and num_features % 64 == 0 and num_features <= 256
+        if num_features % 8 or num_features > 256 or (256 % num_features and not bf16_planes):
             # the CUDA-core kernels (fp32 parity mode, training of wide nets) split 256-thread blocks by channel
-            raise RuntimeError("Q-EDSR feature width %d is not supported: use a divisor of 256 that is a multiple of 8 "
-                               "(64 = tensor-core kernels for inference and training, 128 / 256 = tensor-core inference as "
-                               "64-channel planes + fp32 training; 192 is not available)" % num_features)
+            raise RuntimeError("Q-EDSR feature width %d is not supported in %s mode: fp32 mode and training need a divisor "
+                               "of 256 that is a multiple of 8; bf16 inference also takes 192 (64-channel planes on the "
+                               "tensor-core kernels)" % (num_features, precision))
         if schedule not in SCHEDULES:
             raise RuntimeError("schedule must be one of %s" % sorted(SCHEDULES))
         self.style = "none"
@@ -331,7 +332,10 @@ class QEDSR(QRCAN):
             raise RuntimeError("deepfir_b200.QEDSR runs on a CUDA (sm_100a) device only: there is no CPU path")
         if torch.is_grad_enabled() and self.head.weight.requires_grad:
             # the tensor-core training kernels are specialised for 64 features: a training step of a wide net runs the
-            # library's fp32 CUDA-core kernels (same schedule, any width); inference stays on the tensor cores
+            # library's fp32 CUDA-core kernels (same schedule, divisors of 256); inference stays on the tensor cores
+            if 256 % self.cfg["n_feats"]:
+                raise NotImplementedError("training a %d-feature Q-EDSR is not supported (the fp32 training kernels need a "
+                                          "divisor of 256): use 64, 128 or 256 features" % self.cfg["n_feats"])
             self.precision = "fp32"
             try:
                 return super().forward(x, metadata)

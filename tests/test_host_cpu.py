@@ -322,9 +322,10 @@ def test_set_multi_gpu_refuses_data_parallel_replication():
 
 def test_unsupported_qedsr_width_fails_loudly():
     from deepfir_b200.qrcan import QEDSR
-    with pytest.raises(RuntimeError, match="192 is not available"):
-        QEDSR(num_features=192, num_blocks=1, input_para=10)
-    QEDSR(num_features=128, num_blocks=1, input_para=10)
+    with pytest.raises(RuntimeError, match="not supported in fp32 mode"):
+        QEDSR(num_features=192, num_blocks=1, input_para=10, precision="fp32")
+    QEDSR(num_features=192, num_blocks=1, input_para=10)  # bf16 inference: three 64-channel planes
+    QEDSR(num_features=128, num_blocks=1, input_para=10, precision="fp32")
 
 
 def test_flat_adam_state_dict_has_one_step_tensor_per_parameter():
