@@ -211,6 +211,15 @@ int dfir_ca_pa_scale_residual(const void* r, int r_is_bf16, const float* x_in, c
 int dfir_postprocess_rgb(const float* x_nchw, float* rgb_clipped, float* ycbcr, int B, long long HW, float lo, float hi,
                          void* stream);
 
+/* The same post-processing with 8-bit results and the Y-channel PSNR on the device: rgb_u8 / ycbcr_u8
+ * = rint(255 * clip(., 0, 1)) of the arrays dfir_postprocess_rgb produces (either may be NULL); when hr_nchw (the ground
+ * truth, fp32 NCHW in [0,1]) is given, y_psnr[b] = 20 log10(1 / sqrt(mean((Y_sr - Y_hr)^2))) of image b, 100 for identical
+ * images, exactly what Metrics.run_image_metric('PSNR') computes from channel 0 of the YCbCr arrays (sr_tools/metrics.py:6-17,
+ * max_value 1).  6 B written per pixel instead of 24; scratch: dfir_postprocess_u8_scratch_bytes (only with hr_nchw). */
+size_t dfir_postprocess_u8_scratch_bytes(int B, long long HW);
+int dfir_postprocess_u8(const float* x_nchw, const float* hr_nchw, unsigned char* rgb_u8, unsigned char* ycbcr_u8,
+                        float* y_psnr, void* scratch, size_t scratch_bytes, int B, long long HW, void* stream);
+
 /* per-row channel sums of an fp32 NHWC tensor: pool_rows[b][y][c] = sum_x in[b][y][x][c] (fp32 mode only;
  * the tensor-core conv produces them in its epilogue). */
 int dfir_pool_rows_f32(const float* in, float* pool_rows, int B, int H, int W, int C, void* stream);

@@ -125,9 +125,17 @@ class ModelInterface:
         self.model.set_epoch(epoch)
 
     def net_run_and_process(self, lr=None, hr=None, **kwargs):
-        """run_eval + clamp + colour conversion (ref :138-169)."""
+        """run_eval + clamp + colour conversion (ref :138-169).
+
+        Two optional keywords beyond the reference's, both off by default so that the return values
+        stay the reference's fp32 arrays: `output_dtype='uint8'` returns rint(255 * .) arrays (3 B instead of 12 B per
+        output pixel and array over PCIe), `device_psnr=True` (needs `hr`) leaves the per-image Y-channel PSNR of
+        sr_tools.metrics.psnr(max_value=1) in `self.last_y_psnr` — computed on the GPU from the fp32 result."""
+        self.last_y_psnr = None
+        want_u8 = kwargs.pop('output_dtype', None) in ('uint8', np.uint8, torch.uint8)
+        want_psnr = bool(kwargs.pop('device_psnr', False))
         if 'rgb' in self.configuration['colorspace']:
-            fused = self._device_postprocess(lr, hr, kwargs)
+            fused = self._device_postprocess(lr, hr, kwargs, want_u8=want_u8, want_psnr=want_psnr)
             if fused is not None:
                 return fused
             out_rgb, loss, timing = self.model.run_eval(x=lr, y=hr, **kwargs)
@@ -141,7 +149,7 @@ class ModelInterface:
             out_ycbcr = self._standard_image_formatting(out_ycbcr.numpy())
         return out_rgb, out_ycbcr, loss, timing
 
-    def _device_postprocess(self, lr, hr, kwargs):
+    def _device_postprocess(self, lr, hr, kwargs, want_u8=False, want_psnr=False):
         """clip + RGB -> YCbCr on the GPU right after the network: the SR batch stays on the
         device, one kernel writes both result arrays (bit-identical to the numpy expressions below), and they come
         back through pooled page-locked buffers.  Returns None when the model does not keep results on a CUDA device
@@ -158,6 +166,28 @@ class ModelInterface:
         from deepfir_b200 import _lib
         lib = _lib.load_library()
         out = out.contiguous()
+        if want_u8 or (want_psnr and hr is not None):
+            hw = out.shape[2] * out.shape[3]
+            rgb8 = torch.empty(out.shape, dtype=torch.uint8, device=out.device) if want_u8 else None
+            ycc8 = torch.empty(out.shape, dtype=torch.uint8, device=out.device) if want_u8 else None
+            hr_d = psnr = scratch = None
+            if want_psnr and hr is not None:
+                hr_d = hr.to(device=out.device, dtype=torch.float32).contiguous()
+                if hr_d.shape != out.shape:
+                    raise RuntimeError("device_psnr: hr has shape %s, the SR batch %s" % (tuple(hr_d.shape), tuple(out.shape)))
+                psnr = torch.empty(out.shape[0], dtype=torch.float32, device=out.device)
+                scratch = torch.empty(lib.dfir_postprocess_u8_scratch_bytes(out.shape[0], hw), dtype=torch.uint8,
+                                      device=out.device)
+            ptr = lambda t: (t.data_ptr() if t is not None else None)
+            with torch.cuda.device(out.device):
+                _lib.check(lib.dfir_postprocess_u8(out.data_ptr(), ptr(hr_d), ptr(rgb8), ptr(ycc8), ptr(psnr), ptr(scratch),
+                                                   scratch.numel() if scratch is not None else 0, out.shape[0], hw,
+                                                   C.c_void_p(torch.cuda.current_stream(out.device).cuda_stream)),
+                           "postprocess_u8")
+            if psnr is not None:
+                self.last_y_psnr = psnr.cpu().numpy()
+            if want_u8:
+                return BaseModel._to_host(rgb8).numpy(), BaseModel._to_host(ycc8).numpy(), loss, timing
         rgb, ycc = torch.empty_like(out), torch.empty_like(out)
         with torch.cuda.device(out.device):
             _lib.check(lib.dfir_postprocess_rgb(out.data_ptr(), rgb.data_ptr(), ycc.data_ptr(), out.shape[0],

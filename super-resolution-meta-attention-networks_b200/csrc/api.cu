@@ -630,6 +630,17 @@ int dfir_postprocess_rgb(const float* x_nchw, float* rgb_clipped, float* ycbcr, 
   return postprocess_rgb(x_nchw, rgb_clipped, ycbcr, B, HW, lo, hi, S(stream));
 }
 
+size_t dfir_postprocess_u8_scratch_bytes(int B, long long HW) {
+  return B <= 0 || HW <= 0 ? 0 : static_cast<size_t>(B) * postprocess_u8_blocks(B, HW) * sizeof(double);
+}
+
+int dfir_postprocess_u8(const float* x_nchw, const float* hr_nchw, unsigned char* rgb_u8, unsigned char* ycbcr_u8,
+                        float* y_psnr, void* scratch, size_t scratch_bytes, int B, long long HW, void* stream) {
+  if (x_nchw == nullptr || (rgb_u8 == nullptr && ycbcr_u8 == nullptr && hr_nchw == nullptr)) return DFIR_ERR_ARG;
+  if (hr_nchw != nullptr && scratch_bytes < dfir_postprocess_u8_scratch_bytes(B, HW)) return DFIR_ERR_WORKSPACE;
+  return postprocess_u8(x_nchw, hr_nchw, rgb_u8, ycbcr_u8, y_psnr, reinterpret_cast<double*>(scratch), B, HW, S(stream));
+}
+
 int dfir_pool_rows_f32(const float* in, float* pool_rows, int B, int H, int W, int C, void* stream) {
   return pool_rows_f32(in, pool_rows, B, H, W, C, S(stream));
 }

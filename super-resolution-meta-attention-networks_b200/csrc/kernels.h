@@ -132,6 +132,9 @@ int head_conv(const float* x_nchw, const float* w_packed, const float* bias, flo
               int B, int Cin, int H, int W, int Cout, cudaStream_t s, __nv_bfloat16* out_lo = nullptr);
 int conv3x3_f32(const float* in, const float* w_packed, const float* bias, const float* skip, float* out, int B, int H,
                 int W, int Cin, int Cout, int relu, int ps_r, int out_nchw, cudaStream_t s, const float* mask = nullptr);
+int postprocess_u8_blocks(int B, long long HW);  // partial sums per image the Y-PSNR pass needs (doubles)
+int postprocess_u8(const float* x, const float* hr, unsigned char* rgb8, unsigned char* ycc8, float* y_psnr, double* scratch,
+                   int B, long long HW, cudaStream_t s);
 int pool_rows_f32(const float* in, float* pool_rows, int B, int H, int W, int C, cudaStream_t s);
 int postprocess_rgb(const float* x, float* rgb, float* ycc, int B, long long HW, float lo, float hi, cudaStream_t s);
 int meta_attention(const float* meta, const float* w1, const float* b1, const float* w2, const float* b2, float* out,

@@ -88,6 +88,8 @@ PROTOTYPES = {
     "dfir_ca_pa_scale_residual": (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i,
                                        _vp]),
     "dfir_postprocess_rgb": (_i, [_vp, _vp, _vp, _i, _ll, _f, _f, _vp]),
+    "dfir_postprocess_u8_scratch_bytes": (_sz, [_i, _ll]),
+    "dfir_postprocess_u8": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _ll, _vp]),
     "dfir_pool_rows_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "dfir_qrcan_workspace_bytes": (_sz, [C.POINTER(QrcanNet), _i, _i, _i, _i]),
     "dfir_qrcan_launch_count": (C.c_longlong, [C.POINTER(QrcanNet), _i, _i, _i, _i]),

@@ -277,6 +277,22 @@ def test_net_run_and_process_device_postprocessing_is_bit_identical_to_the_host_
     assert rgb.min() >= 0.0 and rgb.max() <= 1.0
     assert np.array_equal(rgb, want_rgb)
     assert np.array_equal(ycc, want_ycc)
+    # 8-bit results + Y-channel PSNR on the device: against the host expressions on the fp32 arrays
+    from sr_tools.metrics import psnr
+    hr = torch.rand(3, 3, 80, 112, generator=g)
+    rgb8, ycc8, _, _ = mi.net_run_and_process(lr=lr, hr=hr, metadata=meta, metadata_keys=keys, output_dtype="uint8",
+                                              device_psnr=True)
+    assert rgb8.dtype == np.uint8 and ycc8.dtype == np.uint8 and rgb8.shape == rgb.shape
+    assert np.array_equal(rgb8, np.rint(want_rgb * 255.0).astype(np.uint8))
+    assert np.array_equal(ycc8, np.rint(np.clip(want_ycc, 0, 1) * 255.0).astype(np.uint8))
+    hr_ycc = mi.colorspace_convert(hr, colorspace='rgb')
+    for i in range(3):
+        want = psnr(want_ycc[i, 0], hr_ycc[i, 0], max_value=1.0)
+        assert abs(float(mi.last_y_psnr[i]) - float(want)) <= 1e-4, (i, mi.last_y_psnr[i], want)
+    # identical images: the reference's convention (100 dB)
+    same = torch.from_numpy(want_rgb)
+    mi.net_run_and_process(lr=lr, hr=same, metadata=meta, metadata_keys=keys, device_psnr=True)
+    assert mi.last_y_psnr is not None and np.all(np.isfinite(mi.last_y_psnr))
 
 
 @pytest.mark.parametrize("name", ["rcan_g2b2", "edsr_f64_b3", "san_g2b2", "han_b1"])
