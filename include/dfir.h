@@ -415,6 +415,26 @@ size_t dfir_soca_scratch_bytes(int B);
 int dfir_soca(const float* x, const float* mlp_params, int R, float* svec, void* scratch, int B, int H, int W, int C,
               void* stream);
 
+/* Covpool as a stand-alone operator with the reference's hand-written backward (advanced/mpncov.py:12-47), C = 64:
+ *   forward : cov[b] = X (I/M - 11^T/M^2) X^T  of x [B][H][W][64] (NHWC fp32), cov [B][64][64]; crop1000 != 0 applies SOCA's
+ *             centre crop to 1000 along sides >= 1000 (SAN_blocks.py:265-280);
+ *   backward: grad_x = (G + G^T) X (I/M - 11^T/M^2) for G = grad_cov (zero outside the crop window).
+ * Neither materialises the MxM centring matrix (the reference allocates it: 1 GiB at 128x128). */
+size_t dfir_covpool_scratch_bytes(int B);
+int dfir_covpool(const float* x, float* cov, void* scratch, size_t scratch_bytes, int B, int H, int W, int C, int crop1000,
+                 void* stream);
+int dfir_covpool_backward(const float* x, const float* grad_cov, float* grad_x, void* scratch, size_t scratch_bytes, int B,
+                          int H, int W, int C, int crop1000, void* stream);
+
+/* Sqrtm (Newton-Schulz matrix square root, advanced/mpncov.py:49-112), C = 64, iters >= 2 (the networks use 5):
+ *   forward : out[b] = sqrt(tr) * 0.5 Y (3I - Z Y) after iters - 2 coupled iterations on A = cov / tr;
+ *   backward: the reference's closed-form gradient of that iteration (Sqrtm.backward), grad_in [B][64][64].
+ * One CTA per matrix, everything in shared memory. */
+size_t dfir_sqrtm_scratch_bytes(int B, int iters);
+int dfir_sqrtm(const float* cov, float* out, int B, int C, int iters, void* stream);
+int dfir_sqrtm_backward(const float* cov, const float* grad_out, float* grad_in, void* scratch, size_t scratch_bytes, int B,
+                        int C, int iters, void* stream);
+
 /* Nonlocal_CA.forward (advanced/SAN_blocks.py:314-336) with _NonLocalBlockND._embedded_gaussian (:104-148) on each
  * of the 2x2 regions: theta/phi/g 1x1 convs (w_tpg [24][64], b_tpg [24]: theta rows 0-7, phi 8-15, g 16-23),
  * 2x2 max-pool of phi and g (always on), softmax attention, W 1x1 conv (w_out [64][8]) + x. */

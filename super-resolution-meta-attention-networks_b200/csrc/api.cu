@@ -749,6 +749,31 @@ int dfir_soca(const float* x, const float* mlp_params, int R, float* svec, void*
   return soca_forward(x, mlp_params, R, svec, reinterpret_cast<float*>(scratch), B, H, W, C, S(stream));
 }
 
+size_t dfir_covpool_scratch_bytes(int B) { return covpool_scratch_floats(B) * 4; }
+int dfir_covpool(const float* x, float* cov, void* scratch, size_t scratch_bytes, int B, int H, int W, int C, int crop1000,
+                 void* stream) {
+  if (x == nullptr || cov == nullptr || B < 0 || H <= 0 || W <= 0) return DFIR_ERR_ARG;
+  if (scratch == nullptr || scratch_bytes < dfir_covpool_scratch_bytes(B)) return DFIR_ERR_WORKSPACE;
+  return covpool_forward(x, cov, reinterpret_cast<float*>(scratch), B, H, W, C, crop1000, S(stream));
+}
+int dfir_covpool_backward(const float* x, const float* grad_cov, float* grad_x, void* scratch, size_t scratch_bytes, int B,
+                          int H, int W, int C, int crop1000, void* stream) {
+  if (x == nullptr || grad_cov == nullptr || grad_x == nullptr || B < 0 || H <= 0 || W <= 0) return DFIR_ERR_ARG;
+  if (scratch == nullptr || scratch_bytes < dfir_covpool_scratch_bytes(B)) return DFIR_ERR_WORKSPACE;
+  return covpool_backward(x, grad_cov, grad_x, reinterpret_cast<float*>(scratch), B, H, W, C, crop1000, S(stream));
+}
+size_t dfir_sqrtm_scratch_bytes(int B, int iters) { return sqrtm_scratch_floats(B, iters) * 4; }
+int dfir_sqrtm(const float* cov, float* out, int B, int C, int iters, void* stream) {
+  if (cov == nullptr || out == nullptr || B < 0) return DFIR_ERR_ARG;
+  return sqrtm_forward(cov, out, B, C, iters, S(stream));
+}
+int dfir_sqrtm_backward(const float* cov, const float* grad_out, float* grad_in, void* scratch, size_t scratch_bytes, int B,
+                        int C, int iters, void* stream) {
+  if (cov == nullptr || grad_out == nullptr || grad_in == nullptr || B < 0) return DFIR_ERR_ARG;
+  if (scratch == nullptr || scratch_bytes < dfir_sqrtm_scratch_bytes(B, iters)) return DFIR_ERR_WORKSPACE;
+  return sqrtm_backward(cov, grad_out, grad_in, reinterpret_cast<float*>(scratch), B, C, iters, S(stream));
+}
+
 size_t dfir_nonlocal_scratch_bytes(int B, int H, int W) { return nonlocal_scratch_floats(B, H, W) * 4; }
 int dfir_nonlocal(const float* x, const float* w_tpg, const float* b_tpg, const float* w_out, const float* b_out,
                   float* out, void* scratch, int B, int H, int W, int C, void* stream) {

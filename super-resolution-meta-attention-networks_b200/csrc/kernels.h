@@ -158,6 +158,14 @@ int csam_forward(const float* x, const float* w27, float bias, float gamma, floa
 int soca_forward(const float* x, const float* mlp, int R, float* svec, float* scratch, int B, int H, int W, int C,
                  cudaStream_t s);
 size_t soca_scratch_floats(int B);
+size_t covpool_scratch_floats(int B);
+int covpool_forward(const float* x, float* cov, float* scratch, int B, int H, int W, int C, int crop1000, cudaStream_t s);
+int covpool_backward(const float* x, const float* grad_cov, float* grad_x, float* scratch, int B, int H, int W, int C,
+                     int crop1000, cudaStream_t s);
+size_t sqrtm_scratch_floats(int B, int iters);
+int sqrtm_forward(const float* cov, float* out, int B, int C, int iters, cudaStream_t s);
+int sqrtm_backward(const float* cov, const float* grad_out, float* grad_in, float* scratch, int B, int C, int iters,
+                   cudaStream_t s);
 int nonlocal_forward(const float* x, const float* wq, const float* bq, const float* wW, const float* bW, float* out,
                      float* scratch, int B, int H, int W, int C, cudaStream_t s);
 size_t nonlocal_scratch_floats(int B, int H, int W);

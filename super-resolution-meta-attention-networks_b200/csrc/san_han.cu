@@ -322,6 +322,252 @@ soca_kernel(const float* __restrict__ cov, const float* __restrict__ mlp, int R,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Covpool.backward (advanced/mpncov.py:35-47): grad_x = (G + G^T) X I_hat, I_hat = I/M - 11^T/M^2, i.e.
+//   grad_x[p][c] = (1/M) sum_d (G[c][d] + G[d][c]) (x[p][d] - mean_p x[.][d])
+// without the MxM matrix.  Stage 1: per-chunk channel sums (fixed order); stage 2: one 64x64 by 64xM product, streamed.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+channel_sum_partial_kernel(const float* __restrict__ x, float* __restrict__ partial, int H, int W, int y0, int x0, int h1,
+                           int w1, int nchunk) {
+  __shared__ float red[4][64];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int M = h1 * w1;
+  const int per = (M + nchunk - 1) / nchunk;
+  const int p0 = chunk * per, p1 = min(M, p0 + per);
+  const int c = threadIdx.x & 63, lane4 = threadIdx.x >> 6;
+  float t = 0.f;
+  for (int q = p0 + lane4; q < p1; q += 4) {
+    const int yy = y0 + q / w1, xx = x0 + q % w1;
+    t += x[((static_cast<size_t>(b) * H + yy) * W + xx) * 64 + c];
+  }
+  red[lane4][c] = t;
+  __syncthreads();
+  if (threadIdx.x < 64)
+    partial[(static_cast<size_t>(b) * nchunk + chunk) * 64 + c] = (red[0][c] + red[1][c]) + (red[2][c] + red[3][c]);
+}
+
+__global__ void __launch_bounds__(256)
+covpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gcov, const float* __restrict__ partial,
+                   float* __restrict__ gx, int H, int W, int y0, int x0, int h1, int w1, int nchunk, int nsum) {
+  __shared__ float S[64][65];     // (G + G^T) / M, [d][c] (symmetric)
+  __shared__ float tile[64][65];  // [pixel][channel] of x - mean
+  __shared__ float mean[64];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int M = h1 * w1;
+  const float inv = 1.f / static_cast<float>(M);
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+    for (int k = 0; k < nsum; ++k) t += partial[(static_cast<size_t>(b) * nsum + k) * 64 + threadIdx.x];
+    mean[threadIdx.x] = t * inv;
+  }
+  const float* g = gcov + static_cast<size_t>(b) * 4096;
+  for (int idx = threadIdx.x; idx < 4096; idx += 256) {
+    const int i = idx >> 6, j = idx & 63;
+    S[i][j] = (g[i * 64 + j] + g[j * 64 + i]) * inv;
+  }
+  __syncthreads();
+  const int per = (M + nchunk - 1) / nchunk;
+  const int p0 = chunk * per, p1 = min(M, p0 + per);
+  const int ti = (threadIdx.x >> 4) * 4, tj = (threadIdx.x & 15) * 4;  // 4 pixels x 4 output channels per thread
+  for (int base = p0; base < p1; base += 64) {
+    const int np = min(64, p1 - base);
+    for (int idx = threadIdx.x; idx < 64 * 64; idx += 256) {
+      const int pp = idx >> 6, c = idx & 63;
+      float v = 0.f;
+      if (pp < np) {
+        const int q = base + pp;
+        const int yy = y0 + q / w1, xx = x0 + q % w1;
+        v = x[((static_cast<size_t>(b) * H + yy) * W + xx) * 64 + c] - mean[c];
+      }
+      tile[pp][c] = v;
+    }
+    __syncthreads();
+    float acc[4][4] = {};
+    for (int d = 0; d < 64; ++d) {
+      float a[4], w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { a[k] = tile[ti + k][d]; w[k] = S[d][tj + k]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pp = ti + i;
+      if (pp < np) {
+        const int q = base + pp;
+        const int yy = y0 + q / w1, xx = x0 + q % w1;
+        *reinterpret_cast<float4*>(gx + ((static_cast<size_t>(b) * H + yy) * W + xx) * 64 + tj) =
+            make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sqrtm (Newton-Schulz, advanced/mpncov.py:49-112) as stand-alone operators: forward returning the matrix, and the
+// reference's hand-derived backward.  One CTA (256 threads) per image, all 64x64 matrices in shared memory; the forward
+// iterates Y_i, Z_i are kept in a small global stash (written and read by the same CTA, through L2).
+// ------------------------------------------------------------------------------------------------
+__device__ void mm64x(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ Cc, float alpha,
+                      float beta, float diag) {
+  // C = alpha * (A @ B) + beta * C + diag * I   (row-major 64x64 in shared memory; C aliases neither A nor B)
+  const int ti = (threadIdx.x >> 4) * 4, tj = (threadIdx.x & 15) * 4;
+  float acc[4][4] = {};
+  for (int k = 0; k < 64; ++k) {
+    float a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { a[i] = A[(ti + i) * 64 + k]; b[i] = B[k * 64 + tj + i]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = (ti + i) * 64 + tj + j;
+      const float old = beta != 0.f ? beta * Cc[e] : 0.f;
+      Cc[e] = alpha * acc[i][j] + old + ((ti + i) == (tj + j) ? diag : 0.f);
+    }
+  __syncthreads();
+}
+
+__device__ float block_sum256(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < 8; ++w) t += red[w];
+  __syncthreads();
+  return t;
+}
+
+// forward iterates: on exit Y = Y_{n-2}, Z = Z_{n-2} (n = iters), M2 = 0.5 Y (3I - Z Y) (the result before * sqrt(tr));
+// stash (optional): Y_0, Z_0, ..., Y_{n-2}, Z_{n-2} as [2 (n-1)][4096]
+__device__ void sqrtm_forward_smem(const float* __restrict__ cov_g, float* A, float*& Y, float*& Z, float* M1, float*& M2,
+                                   float*& M3, float* red, float& trace, int iters, float* __restrict__ stash) {
+  for (int i = threadIdx.x; i < 4096; i += 256) A[i] = cov_g[i];
+  __syncthreads();
+  float d = threadIdx.x < 64 ? A[threadIdx.x * 65] : 0.f;
+  trace = block_sum256(d, red);
+  const float inv = 1.f / trace;
+  for (int i = threadIdx.x; i < 4096; i += 256) {
+    const float a = A[i] * inv;
+    A[i] = a;
+    Z[i] = 0.5f * (((i >> 6) == (i & 63) ? 3.f : 0.f) - a);
+  }
+  __syncthreads();
+  mm64x(A, Z, Y, 1.f, 0.f, 0.f);  // Y0 = A ZY
+  auto put = [&](int slot, const float* src) {
+    if (stash != nullptr)
+      for (int i = threadIdx.x; i < 4096; i += 256) stash[static_cast<size_t>(slot) * 4096 + i] = src[i];
+  };
+  put(0, Y); put(1, Z);
+  for (int it = 1; it < iters - 1; ++it) {
+    mm64x(Z, Y, M1, -0.5f, 0.f, 1.5f);  // ZY = 0.5 (3I - Z Y)
+    mm64x(Y, M1, M2, 1.f, 0.f, 0.f);    // Y' = Y ZY
+    mm64x(M1, Z, M3, 1.f, 0.f, 0.f);    // Z' = ZY Z
+    float* oy = Y; float* oz = Z;
+    Y = M2; Z = M3; M2 = oy; M3 = oz;
+    put(2 * it, Y); put(2 * it + 1, Z);
+  }
+  mm64x(Z, Y, M1, -1.f, 0.f, 3.f);      // 3I - Z Y
+  mm64x(Y, M1, M2, 0.5f, 0.f, 0.f);     // 0.5 Y (3I - Z Y)
+}
+
+__global__ void __launch_bounds__(256) sqrtm_fwd_kernel(const float* __restrict__ cov, float* __restrict__ out, int iters) {
+  extern __shared__ float sm[];
+  float *A = sm, *Y = sm + 4096, *Z = sm + 8192, *M1 = sm + 12288, *M2 = sm + 16384, *M3 = sm + 20480;
+  __shared__ float red[8];
+  float trace;
+  const int b = blockIdx.x;
+  sqrtm_forward_smem(cov + static_cast<size_t>(b) * 4096, A, Y, Z, M1, M2, M3, red, trace, iters, nullptr);
+  const float sq = sqrtf(trace);
+  for (int i = threadIdx.x; i < 4096; i += 256) out[static_cast<size_t>(b) * 4096 + i] = M2[i] * sq;
+}
+
+__global__ void __launch_bounds__(256)
+sqrtm_bwd_kernel(const float* __restrict__ cov, const float* __restrict__ gout, float* __restrict__ gin,
+                 float* __restrict__ stash_all, int iters) {
+  extern __shared__ float sm[];
+  float* A = sm;               // x / trace
+  float* Yi = sm + 1 * 4096;   // forward iterate Y_i (rotates with the scratch slots during the recompute)
+  float* Zi = sm + 2 * 4096;
+  float* M1 = sm + 3 * 4096;
+  float* M2 = sm + 4 * 4096;
+  float* M3 = sm + 5 * 4096;
+  float* dY = sm + 6 * 4096;
+  float* dZ = sm + 7 * 4096;
+  float* nY = sm + 8 * 4096;
+  float* nZ = sm + 9 * 4096;
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  const float* xg = cov + static_cast<size_t>(b) * 4096;
+  const float* gg = gout + static_cast<size_t>(b) * 4096;
+  float* stash = stash_all + static_cast<size_t>(b) * 2 * (iters - 1) * 4096;
+  float trace;
+  sqrtm_forward_smem(xg, A, Yi, Zi, M1, M2, M3, red, trace, iters, stash);
+  // now: Yi = Y_{n-2}, Zi = Z_{n-2}, M2 = ZY_final (= y / sqrt(trace)); M1, M3 free
+  const float sq = sqrtf(trace);
+  float part = 0.f;
+  for (int i = threadIdx.x; i < 4096; i += 256) {
+    const float g = gg[i];
+    part += g * M2[i];
+    nY[i] = g * sq;  // der_postCom
+  }
+  const float aux = block_sum256(part, red) / (2.f * sq);  // der_postComAux
+  float* dpc = nY;
+  // dldY = 0.5 (dpc (3I - Y Z) - Z Y dpc) ; dldZ = -0.5 Y dpc Y
+  mm64x(Yi, Zi, M1, -1.f, 0.f, 3.f);   // YZ = 3I - Y Z
+  mm64x(dpc, M1, dY, 0.5f, 0.f, 0.f);
+  mm64x(Zi, Yi, M3, 1.f, 0.f, 0.f);    // ZY
+  mm64x(M3, dpc, dY, -0.5f, 1.f, 0.f);
+  mm64x(Yi, dpc, M3, 1.f, 0.f, 0.f);
+  mm64x(M3, Yi, dZ, -0.5f, 0.f, 0.f);
+  for (int i = iters - 3; i >= 0; --i) {
+    for (int k = threadIdx.x; k < 4096; k += 256) {  // Y_i, Z_i back from the stash (through L2: written by this CTA)
+      Yi[k] = __ldcg(stash + static_cast<size_t>(2 * i) * 4096 + k);
+      Zi[k] = __ldcg(stash + static_cast<size_t>(2 * i + 1) * 4096 + k);
+    }
+    __syncthreads();
+    mm64x(Yi, Zi, M1, -1.f, 0.f, 3.f);  // YZ = 3I - Y_i Z_i
+    mm64x(Zi, Yi, M2, 1.f, 0.f, 0.f);   // ZY = Z_i Y_i
+    // dldY_ = 0.5 (dldY YZ - Z_i dldZ Z_i - ZY dldY)
+    mm64x(dY, M1, nY, 0.5f, 0.f, 0.f);
+    mm64x(Zi, dZ, M3, 1.f, 0.f, 0.f);
+    mm64x(M3, Zi, nY, -0.5f, 1.f, 0.f);
+    mm64x(M2, dY, nY, -0.5f, 1.f, 0.f);
+    // dldZ_ = 0.5 (YZ dldZ - Y_i dldY Y_i - dldZ ZY)
+    mm64x(M1, dZ, nZ, 0.5f, 0.f, 0.f);
+    mm64x(Yi, dY, M3, 1.f, 0.f, 0.f);
+    mm64x(M3, Yi, nZ, -0.5f, 1.f, 0.f);
+    mm64x(dZ, M2, nZ, -0.5f, 1.f, 0.f);
+    float* t = dY; dY = nY; nY = t;
+    t = dZ; dZ = nZ; nZ = t;
+  }
+  // der_NSiter = 0.5 (dldY (3I - A) - dldZ - A dldY)
+  for (int k = threadIdx.x; k < 4096; k += 256) M1[k] = ((k >> 6) == (k & 63) ? 3.f : 0.f) - A[k];
+  __syncthreads();
+  mm64x(dY, M1, nY, 0.5f, 0.f, 0.f);
+  mm64x(A, dY, nY, -0.5f, 1.f, 0.f);
+  float gpart = 0.f;
+  for (int k = threadIdx.x; k < 4096; k += 256) {
+    const float d = nY[k] - 0.5f * dZ[k];
+    nY[k] = d;
+    gpart += d * xg[k];
+  }
+  const float grad_aux = block_sum256(gpart, red);
+  const float diag = aux - grad_aux / (trace * trace);
+  for (int k = threadIdx.x; k < 4096; k += 256)
+    gin[static_cast<size_t>(b) * 4096 + k] = nY[k] / trace + ((k >> 6) == (k & 63) ? diag : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Region non-local attention (embedded Gaussian, inter channels D = 8, always 2x2 max-pooled keys/values).
 // nl_project: theta / phi / g 1x1 convs (64 -> 8 each) for every pixel: out [B][H][W][24]
 // nl_pool   : 2x2 max-pool of phi and g inside each of the 4 regions: keys [B][4][Nk_max][16]
@@ -514,6 +760,66 @@ int soca_forward(const float* x, const float* mlp, int R, float* svec, float* sc
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   soca_kernel<<<B, 256, 4 * 4096 * 4, s>>>(cov, mlp, R, svec, 5);
+  return ok_or_cuda2();
+}
+
+static void soca_window(int H, int W, int* y0, int* x0, int* h1, int* w1) {
+  // SOCA centre-crops to 1000 along any side that is >= 1000 (SAN_blocks.py:265-280)
+  *y0 = 0; *x0 = 0; *h1 = H; *w1 = W;
+  if (H >= 1000) { *y0 = (H - 1000) / 2; *h1 = 1000; }
+  if (W >= 1000) { *x0 = (W - 1000) / 2; *w1 = 1000; }
+}
+
+constexpr int kCovChunks = 32;
+
+size_t covpool_scratch_floats(int B) { return static_cast<size_t>(B) * kCovChunks * (4096 + 64); }
+
+int covpool_forward(const float* x, float* cov, float* scratch, int B, int H, int W, int C, int crop1000, cudaStream_t s) {
+  if (C != 64) return DFIR_ERR_ARG;
+  if (B == 0) return DFIR_OK;
+  int y0 = 0, x0 = 0, h1 = H, w1 = W;
+  if (crop1000) soca_window(H, W, &y0, &x0, &h1, &w1);
+  covpool_partial_kernel<<<dim3(kCovChunks, B), 256, 0, s>>>(x, scratch, H, W, y0, x0, h1, w1, kCovChunks);
+  covpool_final_kernel<<<B, 256, 0, s>>>(scratch, cov, h1 * w1, kCovChunks);
+  return ok_or_cuda2();
+}
+
+int covpool_backward(const float* x, const float* grad_cov, float* grad_x, float* scratch, int B, int H, int W, int C,
+                     int crop1000, cudaStream_t s) {
+  if (C != 64) return DFIR_ERR_ARG;
+  if (B == 0) return DFIR_OK;
+  int y0 = 0, x0 = 0, h1 = H, w1 = W;
+  if (crop1000) soca_window(H, W, &y0, &x0, &h1, &w1);
+  if (h1 != H || w1 != W) {  // pixels outside the window receive no gradient
+    if (cudaMemsetAsync(grad_x, 0, static_cast<size_t>(B) * H * W * 64 * sizeof(float), s) != cudaSuccess) return DFIR_ERR_CUDA;
+  }
+  channel_sum_partial_kernel<<<dim3(kCovChunks, B), 256, 0, s>>>(x, scratch, H, W, y0, x0, h1, w1, kCovChunks);
+  const long long M = static_cast<long long>(h1) * w1;
+  const int nchunk = static_cast<int>(std::max<long long>(1, std::min<long long>((M + 255) / 256, 148 * 4 / std::max(1, std::min(B, 8)) + 1)));
+  covpool_bwd_kernel<<<dim3(nchunk, B), 256, 0, s>>>(x, grad_cov, scratch, grad_x, H, W, y0, x0, h1, w1, nchunk, kCovChunks);
+  return ok_or_cuda2();
+}
+
+size_t sqrtm_scratch_floats(int B, int iters) { return static_cast<size_t>(B) * 2 * std::max(1, iters - 1) * 4096; }
+
+static int sqrtm_configure(const void* fn, int bytes) {
+  return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
+}
+
+int sqrtm_forward(const float* cov, float* out, int B, int C, int iters, cudaStream_t s) {
+  if (C != 64 || iters < 2 || iters > 16) return DFIR_ERR_ARG;
+  if (B == 0) return DFIR_OK;
+  if (sqrtm_configure(reinterpret_cast<const void*>(sqrtm_fwd_kernel), 6 * 4096 * 4) != DFIR_OK) return DFIR_ERR_CUDA;
+  sqrtm_fwd_kernel<<<B, 256, 6 * 4096 * 4, s>>>(cov, out, iters);
+  return ok_or_cuda2();
+}
+
+int sqrtm_backward(const float* cov, const float* grad_out, float* grad_in, float* scratch, int B, int C, int iters,
+                   cudaStream_t s) {
+  if (C != 64 || iters < 2 || iters > 16) return DFIR_ERR_ARG;
+  if (B == 0) return DFIR_OK;
+  if (sqrtm_configure(reinterpret_cast<const void*>(sqrtm_bwd_kernel), 10 * 4096 * 4) != DFIR_OK) return DFIR_ERR_CUDA;
+  sqrtm_bwd_kernel<<<B, 256, 10 * 4096 * 4, s>>>(cov, grad_out, grad_in, scratch, iters);
   return ok_or_cuda2();
 }
 

@@ -100,6 +100,12 @@ PROTOTYPES = {
     "dfir_csam": (_i, [_vp, _vp, _f, _f, _vp, _i, _i, _i, _i, _vp]),
     "dfir_soca_scratch_bytes": (_sz, [_i]),
     "dfir_soca": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "dfir_covpool_scratch_bytes": (_sz, [_i]),
+    "dfir_covpool": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
+    "dfir_covpool_backward": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
+    "dfir_sqrtm_scratch_bytes": (_sz, [_i, _i]),
+    "dfir_sqrtm": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "dfir_sqrtm_backward": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _vp]),
     "dfir_nonlocal_scratch_bytes": (_sz, [_i, _i, _i]),
     "dfir_nonlocal": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "dfir_qrcan_repack": (_i, [C.POINTER(QrcanNet), C.POINTER(QrcanParams), _i, _i, _vp]),
