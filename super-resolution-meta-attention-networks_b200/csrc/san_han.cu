@@ -233,7 +233,7 @@ covpool_partial_kernel(const float* __restrict__ x, float* __restrict__ partial,
 
 __global__ void covpool_final_kernel(const float* __restrict__ partial, float* __restrict__ cov, int M, int nchunk) {
   __shared__ float s[64];
-  const int b = blockIdx.x;
+  const int b = blockIdx.x;  // blockIdx.y: slice of 256 of the 4096 matrix entries (fixed summation order per entry)
   if (threadIdx.x < 64) {
     float t = 0.f;
     for (int c = 0; c < nchunk; ++c) t += partial[(static_cast<size_t>(b) * nchunk + c) * (64 * 64 + 64) + 64 * 64 + threadIdx.x];
@@ -241,7 +241,7 @@ __global__ void covpool_final_kernel(const float* __restrict__ partial, float* _
   }
   __syncthreads();
   const float inv = 1.f / static_cast<float>(M);
-  for (int idx = threadIdx.x; idx < 64 * 64; idx += blockDim.x) {
+  for (int idx = blockIdx.y * 256 + threadIdx.x; idx < 64 * 64; idx += gridDim.y * 256) {
     float t = 0.f;
     for (int c = 0; c < nchunk; ++c) t += partial[(static_cast<size_t>(b) * nchunk + c) * (64 * 64 + 64) + idx];
     cov[static_cast<size_t>(b) * 4096 + idx] = t * inv - (s[idx >> 6] * inv) * (s[idx & 63] * inv);
@@ -750,7 +750,7 @@ int soca_forward(const float* x, const float* mlp, int R, float* svec, float* sc
   float* partial = scratch;                                            // [B][nchunk][4096+64]
   float* cov = scratch + static_cast<size_t>(B) * nchunk * (4096 + 64); // [B][4096]
   covpool_partial_kernel<<<dim3(nchunk, B), 256, 0, s>>>(x, partial, H, W, y0, x0, h1, w1, nchunk);
-  covpool_final_kernel<<<B, 256, 0, s>>>(partial, cov, h1 * w1, nchunk);
+  covpool_final_kernel<<<dim3(B, 16), 256, 0, s>>>(partial, cov, h1 * w1, nchunk);
   static bool configured[64] = {};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return DFIR_ERR_CUDA;
@@ -780,7 +780,7 @@ int covpool_forward(const float* x, float* cov, float* scratch, int B, int H, in
   int y0 = 0, x0 = 0, h1 = H, w1 = W;
   if (crop1000) soca_window(H, W, &y0, &x0, &h1, &w1);
   covpool_partial_kernel<<<dim3(kCovChunks, B), 256, 0, s>>>(x, scratch, H, W, y0, x0, h1, w1, kCovChunks);
-  covpool_final_kernel<<<B, 256, 0, s>>>(scratch, cov, h1 * w1, kCovChunks);
+  covpool_final_kernel<<<dim3(B, 16), 256, 0, s>>>(scratch, cov, h1 * w1, kCovChunks);
   return ok_or_cuda2();
 }
 
