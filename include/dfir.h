@@ -415,6 +415,18 @@ size_t dfir_soca_scratch_bytes(int B);
 int dfir_soca(const float* x, const float* mlp_params, int R, float* svec, void* scratch, int B, int H, int W, int C,
               void* stream);
 
+/* Online degradation of the training input pipeline (Code/sr_tools/gaussian_utils.py:333-424):
+ * dfir_batch_blur = BatchBlur.forward (+ the noise / clamp of SRMDPreprocessing.__call__): out[b][c] = reflect-padded
+ * x[b][c] cross-correlated with kernels[b] (kernel_per_image != 0, [B][l][l]) or with the one shared kernel ([l][l]),
+ * optionally + noise_sigma[b] * noise[b][c] (noise: standard normal samples, same shape as x) and clamped to [0, 1].
+ * x, noise, out: fp32 NCHW, out must not alias x; l <= 33, l/2 < min(H, W).
+ * dfir_pca_encode = PCAEncoder.__call__: code[b][0..k) = flatten(kernels[b]) @ pca_matrix ([l*l][k], k <= 32); with
+ * noise_sigma the code has k + 1 entries and code[b][k] = 10 * noise_sigma[b] (SRMDPreprocessing's `re_code`). */
+int dfir_batch_blur(const float* x_nchw, const float* kernels, int kernel_per_image, const float* noise,
+                    const float* noise_sigma, float* out_nchw, int B, int C, int H, int W, int l, int clamp01, void* stream);
+int dfir_pca_encode(const float* kernels, const float* pca_matrix, const float* noise_sigma, float* code, int B, int l,
+                    int k, void* stream);
+
 /* Covpool as a stand-alone operator with the reference's hand-written backward (advanced/mpncov.py:12-47), C = 64:
  *   forward : cov[b] = X (I/M - 11^T/M^2) X^T  of x [B][H][W][64] (NHWC fp32), cov [B][64][64]; crop1000 != 0 applies SOCA's
  *             centre crop to 1000 along sides >= 1000 (SAN_blocks.py:265-280);

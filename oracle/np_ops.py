@@ -46,3 +46,28 @@ def covpool_np(x):
     ihat = np.full((m, m), -1.0 / m / m)
     ihat[np.diag_indices(m)] += 1.0 / m
     return np.einsum("bcm,mn,bdn->bcd", xf, ihat, xf)
+
+
+def batch_blur_np(x, kernels):
+    """Literal restatement of BatchBlur.forward (Code/sr_tools/gaussian_utils.py:346-368): reflection pad (l//2 on the low
+    side, l//2 or l//2 - 1 on the high side), then every plane of image b cross-correlated with kernels[b] (or the single
+    shared kernel)."""
+    x = np.asarray(x, dtype=np.float64)
+    k = np.asarray(kernels, dtype=np.float64)
+    b, c, h, w = x.shape
+    l = k.shape[-1]
+    lo, hi = l // 2, (l // 2 if l % 2 == 1 else l // 2 - 1)
+    xp = np.pad(x, ((0, 0), (0, 0), (lo, hi), (lo, hi)), mode="reflect")
+    out = np.zeros_like(x)
+    for i in range(b):
+        kk = k[i] if k.ndim == 3 else k
+        for dy in range(l):
+            for dx in range(l):
+                out[i] += kk[dy, dx] * xp[i, :, dy:dy + h, dx:dx + w]
+    return out
+
+
+def pca_encode_np(kernels, pca):
+    """PCAEncoder.__call__ (:333-343): [B, l*l] @ [l*l, k]"""
+    k = np.asarray(kernels, dtype=np.float64)
+    return k.reshape(k.shape[0], -1) @ np.asarray(pca, dtype=np.float64)

@@ -749,6 +749,18 @@ int dfir_soca(const float* x, const float* mlp_params, int R, float* svec, void*
   return soca_forward(x, mlp_params, R, svec, reinterpret_cast<float*>(scratch), B, H, W, C, S(stream));
 }
 
+int dfir_batch_blur(const float* x_nchw, const float* kernels, int kernel_per_image, const float* noise,
+                    const float* noise_sigma, float* out_nchw, int B, int C, int H, int W, int l, int clamp01, void* stream) {
+  if (x_nchw == nullptr || kernels == nullptr || out_nchw == nullptr || x_nchw == out_nchw) return DFIR_ERR_ARG;
+  if ((noise == nullptr) != (noise_sigma == nullptr)) return DFIR_ERR_ARG;
+  return batch_blur(x_nchw, kernels, kernel_per_image, noise, noise_sigma, out_nchw, B, C, H, W, l, clamp01, S(stream));
+}
+int dfir_pca_encode(const float* kernels, const float* pca_matrix, const float* noise_sigma, float* code, int B, int l,
+                    int k, void* stream) {
+  if (kernels == nullptr || pca_matrix == nullptr || code == nullptr) return DFIR_ERR_ARG;
+  return pca_encode(kernels, pca_matrix, noise_sigma, code, B, l * l, k, S(stream));
+}
+
 size_t dfir_covpool_scratch_bytes(int B) { return covpool_scratch_floats(B) * 4; }
 int dfir_covpool(const float* x, float* cov, void* scratch, size_t scratch_bytes, int B, int H, int W, int C, int crop1000,
                  void* stream) {

@@ -132,6 +132,10 @@ int head_conv(const float* x_nchw, const float* w_packed, const float* bias, flo
               int B, int Cin, int H, int W, int Cout, cudaStream_t s, __nv_bfloat16* out_lo = nullptr);
 int conv3x3_f32(const float* in, const float* w_packed, const float* bias, const float* skip, float* out, int B, int H,
                 int W, int Cin, int Cout, int relu, int ps_r, int out_nchw, cudaStream_t s, const float* mask = nullptr);
+// ---- training input pipeline (degrade.cu)
+int batch_blur(const float* x, const float* kernels, int kernel_per_image, const float* noise, const float* sigma, float* out,
+               int B, int C, int H, int W, int l, int clamp01, cudaStream_t s);
+int pca_encode(const float* kernels, const float* pca, const float* sigma, float* code, int B, int n, int k, cudaStream_t s);
 int postprocess_u8_blocks(int B, long long HW);  // partial sums per image the Y-PSNR pass needs (doubles)
 int postprocess_u8(const float* x, const float* hr, unsigned char* rgb8, unsigned char* ycc8, float* y_psnr, double* scratch,
                    int B, long long HW, cudaStream_t s);

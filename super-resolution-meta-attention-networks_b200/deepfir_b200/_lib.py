@@ -100,6 +100,8 @@ PROTOTYPES = {
     "dfir_csam": (_i, [_vp, _vp, _f, _f, _vp, _i, _i, _i, _i, _vp]),
     "dfir_soca_scratch_bytes": (_sz, [_i]),
     "dfir_soca": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "dfir_batch_blur": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "dfir_pca_encode": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "dfir_covpool_scratch_bytes": (_sz, [_i]),
     "dfir_covpool": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "dfir_covpool_backward": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),

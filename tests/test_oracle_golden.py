@@ -87,3 +87,30 @@ def test_oracle_matches_reference_fingerprint_at_baseline_shape(name):
         out = oracle_forward(info, sd, x, meta)
     err_sub, err_proj, _ = big_fingerprint_errors(out, fp, info)
     assert err_sub <= 2e-5 and err_proj <= 2e-5, (err_sub, err_proj)
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference not mounted")
+def test_blur_and_pca_restatements_match_the_live_reference():
+    """oracle/np_ops.batch_blur_np / pca_encode_np against the reference's own BatchBlur / PCAEncoder
+    (Code/sr_tools/gaussian_utils.py:333-368), odd and even kernel sizes, per-image and shared kernels"""
+    import importlib.util
+    import os
+    from oracle.ref_shim import REFERENCE_CODE
+    spec = importlib.util.spec_from_file_location("_ref_gaussian_utils", os.path.join(REFERENCE_CODE, "sr_tools", "gaussian_utils.py"))
+    try:
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    except Exception as e:  # optional third-party imports of that file (scipy, PIL, torchvision)
+        pytest.skip("reference gaussian_utils not importable here: %r" % (e,))
+    g = torch.Generator().manual_seed(2)
+    for l, shape in ((21, (2, 3, 30, 41)), (20, (2, 1, 25, 25)), (7, (1, 3, 9, 16))):
+        x = torch.rand(*shape, generator=g)
+        k = torch.rand(shape[0], l, l, generator=g)
+        k = k / k.sum(dim=(1, 2), keepdim=True)
+        ref = mod.BatchBlur(l=l)(x, k).numpy()
+        assert np.abs(np_ops.batch_blur_np(x.numpy(), k.numpy()) - ref).max() <= 1e-6
+        ref1 = mod.BatchBlur(l=l)(x, k[0]).numpy()
+        assert np.abs(np_ops.batch_blur_np(x.numpy(), k[0].numpy()) - ref1).max() <= 1e-6
+    pca = torch.randn(441, 10, generator=g)
+    k = torch.rand(3, 21, 21, generator=g)
+    assert np.abs(np_ops.pca_encode_np(k.numpy(), pca.numpy()) - mod.PCAEncoder(pca)(k).numpy()).max() <= 1e-4
