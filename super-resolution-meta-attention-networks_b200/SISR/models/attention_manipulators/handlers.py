@@ -125,7 +125,18 @@ class QSANHandler(QModel):
     def run_eval(self, x, y=None, request_loss=False, metadata=None, metadata_keys=None, timing=False, *args, **kwargs):
         attributes = self.generate_channels(x, metadata, metadata_keys).to(self.device)
         started = time.perf_counter()
-        sr_image = self._to_host(self.forward_chop(x.to(self.device), attributes))  # one H2D, one D2H
+        if kwargs.pop('shard_tiles', False):
+            # one process per GPU (torchrun): the 4 * B quadrants are spread over the ranks, one all-reduce stitches them
+            from deepfir_b200.sharding import env_rank_world, run_chopped_sharded
+            rank, world, _ = env_rank_world()
+            size = (x.shape[2] // 2 + 10) * (x.shape[3] // 2 + 10)
+            if size >= self.max_combined_im_size:
+                raise NotImplementedError("shard_tiles: quadrants of %d pixels need a second chop level (max_combined_im_size "
+                                          "= %d); only one level is sharded" % (size, self.max_combined_im_size))
+            sr_image = self._to_host(run_chopped_sharded(self.run_chopped_eval, x.to(self.device), attributes, self.scale,
+                                                         rank, world, out_channels=x.shape[1]))
+        else:
+            sr_image = self._to_host(self.forward_chop(x.to(self.device), attributes))  # one H2D, one D2H
         elapsed = time.perf_counter() - started
         return sr_image, (self.criterion(sr_image, y) if request_loss else None), (elapsed if timing else None)
 

@@ -339,3 +339,47 @@ def test_flat_adam_state_dict_has_one_step_tensor_per_parameter():
     steps = [st["step"] for st in sd["state"].values()]
     assert len(steps) == 4 and all(float(t) == 1.0 for t in steps)
     assert len({id(t) for t in steps}) == 4 and len({t.untyped_storage().data_ptr() for t in steps}) == 4
+
+
+_CHOP_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "super-resolution-meta-attention-networks_b200"))
+from deepfir_b200.sharding import env_rank_world, quadrant_geometry, run_chopped_sharded
+from tests.golden_util import load_golden, case_tensors, oracle_forward
+rank, world, _ = env_rank_world()
+dist.init_process_group("gloo", rank=rank, world_size=world)
+ref, info = load_golden("qrcan_noq_scale2")      # scale 2, 1 group x 2 blocks: cheap on the CPU
+sd, _, _ = case_tensors(info)
+g = torch.Generator().manual_seed(4)
+x = torch.rand(3, 3, 25, 30, generator=g)          # odd height: unequal kept parts
+meta = torch.rand(3, 10, 1, 1, generator=g) * 0.4
+fwd = lambda xs, ms: oracle_forward(info, sd, xs, ms)
+with torch.no_grad():
+    sharded = run_chopped_sharded(fwd, x, meta, 2, rank, world, shave=10, out_channels=3)
+    single = run_chopped_sharded(fwd, x, meta, 2, 0, 1, shave=10)
+    # the single-process result is the reference's quadrant loop
+    want = torch.empty_like(single)
+    for lr_r, lr_c, dr, dc, sr_r, sr_c in quadrant_geometry(25, 30, 2, 10):
+        want[:, :, dr, dc] = fwd(x[:, :, lr_r, lr_c].contiguous(), meta)[:, :, sr_r, sr_c]
+assert torch.equal(single, want)
+assert float((sharded - single).abs().max()) <= 1e-6, float((sharded - single).abs().max())
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_rank_tile_sharding_of_one_image_on_gloo():
+    """inference sharded by LR tile (north_star): the reference's four overlapping quadrants of a batch spread over two
+    ranks, stitched with one all-reduce, equal the single-process chop (SURVEY.md 8e; handlers.py:99-137)"""
+    with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as fh:
+        fh.write(_CHOP_WORKER.format(root=ROOT))
+        script = fh.name
+    try:
+        res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                              "--master-addr", "127.0.0.1", "--master-port", "29535", script],
+                             capture_output=True, text=True, timeout=300,
+                             env=dict(os.environ, OMP_NUM_THREADS="2", PYTHONDONTWRITEBYTECODE="1"))
+    finally:
+        os.unlink(script)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count("ok") == 2
