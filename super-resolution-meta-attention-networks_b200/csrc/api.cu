@@ -46,6 +46,7 @@ int auto_chunk(int B, int H, int W, int precision) {
 
 struct QrcanWs {
   float *Hh, *XA, *XB, *XB1, *pool, *sq, *colf, *coll, *svec;
+  long long* istats[2];  // fixed-point image statistics of pool-by-linearity, double buffered by block parity
   __nv_bfloat16 *Hbf, *XAbf, *XBbf, *T, *R;
   float *T32, *R32;
   void* U[3];
@@ -66,6 +67,8 @@ QrcanWs carve_qrcan(const dfir_qrcan_net* n, int B, int Bc, int H, int W, int pr
   w.colf = c.take<float>(static_cast<size_t>(Bc) * H * C * 4);
   w.coll = c.take<float>(static_cast<size_t>(Bc) * H * C * 4);
   w.svec = c.take<float>(static_cast<size_t>(Bc) * C * 4);
+  w.istats[0] = c.take<long long>(static_cast<size_t>(Bc) * 576 * 8);
+  w.istats[1] = c.take<long long>(static_cast<size_t>(Bc) * 576 * 8);
   int r = 0;
   const int nup = up_stages(n->scale, &r);
   if (precision == DFIR_PREC_BF16_TC) {
@@ -139,6 +142,10 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
   const int sched0 = n->pa_blob != nullptr ? 2 : n->schedule;
   const bool hl = hl_allowed && sched0 == 0 && sa.stages == ST_ALL && sa.group_out == nullptr && !sa.from_xa;
   static const int hl_flip = getenv("DFIR_FLIP") == nullptr ? 1 : atoi(getenv("DFIR_FLIP"));
+  static const int hl_fixed_stats = getenv("DFIR_FIXED_STATS") == nullptr ? 1 : atoi(getenv("DFIR_FIXED_STATS"));
+  if (hl && hl_fixed_stats && (sa.stages & ST_GROUPS) &&
+      cudaMemsetAsync(w.istats[0], 0, static_cast<size_t>(Bc) * 576 * 8 * 2, st) != cudaSuccess)
+    return DFIR_ERR_CUDA;  // both buffers start at zero; afterwards every conv1 clears the buffer of the next block
   __nv_bfloat16* const Hlo = reinterpret_cast<__nv_bfloat16*>(w.Hh);
   __nv_bfloat16* const XAlo = reinterpret_cast<__nv_bfloat16*>(w.XA);
   __nv_bfloat16* const XBlo = reinterpret_cast<__nv_bfloat16*>(w.XB);
@@ -190,6 +197,11 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
       // conv1: t = relu(conv(x_b))
       ConvTcDesc c1 = base(g * per_group + 2 * b, ((sched == 0 || sched == 3) && has_ca) ? EPI_RELU_STATS : EPI_BIAS_RELU);
       c1.out_bf16 = w.T; c1.col_first = w.colf; c1.col_last = w.coll;
+      const bool fx = hl && hl_fixed_stats && has_ca && sched == 0;  // statistics as fixed-point sums (see ConvTcArgs::istats)
+      if (fx) {
+        c1.istats = w.istats[blk & 1];
+        c1.istats_clear = w.istats[(blk + 1) & 1];
+      }
       if (b == 0) {
         c1.in_bf16 = gin;
       } else if (sched == 1) {
@@ -218,7 +230,8 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
                                  make_ap(n, blk), attr_c, sq, w.svec, Bc, H, W, st));
           c2.svec = w.svec;
         } else if (has_ca) {
-          c2.col_first = w.colf; c2.col_last = w.coll; c2.epi_stats = 1;
+          c2.col_first = w.colf; c2.col_last = w.coll; c2.epi_stats = fx ? 2 : 1;
+          c2.istats = fx ? w.istats[blk & 1] : nullptr;
           c2.ca_style = n->style; c2.ca_R = n->reduced; c2.ca_M = n->num_metadata; c2.ca_A = n->attr_size;
           c2.ca_params = n->ca_blob + static_cast<size_t>(blk) * n->ca_stride; c2.attributes = attr_c; c2.sq = sq;
         } else {

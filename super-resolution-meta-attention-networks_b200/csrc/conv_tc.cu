@@ -124,7 +124,7 @@ struct SmemLayout {
   static constexpr int off_attn = off_stage;
   static constexpr int off_cap = off_attn + 2 * kAttnScratchFloats * 4;
   static_assert(off_cap + kCaStageFloats * 4 <= off_stage + 2 * kStageBytes, "prologue scratch must fit the staging tiles");
-  static constexpr int off_svec = off_pool + 8 * 64 * 4;                         // s of the images of this band
+  static constexpr int off_svec = off_pool + 12 * 64 * 4;  // (2 groups x [4 warp sums | first column | last column] x 64)
   static constexpr int off_bars = off_svec + kMaxBandImages * 64 * 4;
   static constexpr int n_bars = 2 * kSlots + kARows + 2 * kAcc + 1 + 8 * kHlSlots;
   // EPI_SCALE_SKIP_HL: the 96 KB of the staging tiles + skip buffers hold, slot-major, kHlSlots x 8 warps x (2 KB hi +
@@ -626,6 +626,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       const int rows_img_e = nseg * H;
       const int bimg_first = g0 / rows_img_e;
       int cur_img = -1;
+      long long fx_t = 0, fx_c0 = 0, fx_cl = 0;  // EPI_RELU_STATS fixed-point mode: this thread's channel, current image
       // ---- EPI_SCALE_SKIP_HL: every epilogue warp streams the residual tiles of its own 32 pixels through kHlSlots
       // private 4 KB buffers (TMA load -> in-place update -> TMA store), two tiles of 16 pixels per output row, loads
       // issued two tiles ahead.  No barrier other than the tile's own mbarrier: the warps never wait for each other.
@@ -711,12 +712,23 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           mbar_wait(wbar, 0, 9);  // conv weights have landed in smem (generic-proxy reads below)
           for (int b = bimg_first + egrp; b <= bimg_last; b += kEpiGroups) {
             const int ba = flip ? a.B - 1 - b : b;  // the image the statistics, attributes and meta scale belong to
+            // statistics source: per-row arrays written by conv1 (summed here in a fixed order), or the nine 64-bit fixed-point
+            // sums per channel that conv1 accumulated with atomics (epi_stats == 2: one 72-byte read per thread)
+            const bool fixed_stats = a.epi_stats == 2;
+            float r0v = 0.f, rlv = 0.f, k00 = 0.f, k0w = 0.f, kh0 = 0.f, khw = 0.f;
+            float fxv[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (fixed_stats) {
+              if (et < 64) {
+                const long long* st = a.istats + static_cast<size_t>(ba) * 576 + et;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) fxv[k] = __ll2float_rn(__ldcg(st + 64 * k)) * (1.f / 16777216.f);
+              }
+            } else {
             const float4* pr = reinterpret_cast<const float4*>(a.pool_rows + static_cast<size_t>(ba) * rows_img_e * 64) + cq;
             const float4* cf = reinterpret_cast<const float4*>(a.col_first + static_cast<size_t>(ba) * H * 64) + cq;
             const float4* cl = reinterpret_cast<const float4*>(a.col_last + static_cast<size_t>(ba) * H * 64) + cq;
             // edge rows / corners of the stats (threads 0..63, one channel each): issued ahead of the row loops so
             // that their latency overlaps, consumed after the first barrier
-            float r0v = 0.f, rlv = 0.f, k00 = 0.f, k0w = 0.f, kh0 = 0.f, khw = 0.f;
             if (et < 64) {
               const float* prs = a.pool_rows + static_cast<size_t>(ba) * rows_img_e * 64 + et;
               const float* cfs = a.col_first + static_cast<size_t>(ba) * H * 64 + et;
@@ -763,20 +775,27 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               reinterpret_cast<float4*>(tmp + (1 * 4 + w4) * 64)[cq] = c04;
               reinterpret_cast<float4*>(tmp + (2 * 4 + w4) * 64)[cq] = c14;
             }
+            }
             for (int i = et; i < a.ca_A; i += 128) attr_s[i] = a.attributes[static_cast<size_t>(ba) * a.ca_A + i];
             grp.sync();
             float* S = tmp;  // [9][64], written once the partial sums have been consumed
             float Sv[9];
             if (et < 64) {
               const int c = et;
-              const float T = (tmp[c] + tmp[64 + c]) + (tmp[128 + c] + tmp[192 + c]);
-              const float C0 = (tmp[256 + c] + tmp[320 + c]) + (tmp[384 + c] + tmp[448 + c]);
-              const float CL = (tmp[512 + c] + tmp[576 + c]) + (tmp[640 + c] + tmp[704 + c]);
-              float R0 = r0v, RL = rlv;
-              for (int sg = 1; sg < nseg; ++sg) {  // images wider than one 128-px segment
-                const float* prs = a.pool_rows + static_cast<size_t>(ba) * rows_img_e * 64 + c;
-                R0 += prs[(static_cast<size_t>(sg) * H) * 64];
-                RL += prs[(static_cast<size_t>(sg) * H + (H - 1)) * 64];
+              float T, C0, CL, R0, RL;
+              if (fixed_stats) {
+                T = fxv[0]; C0 = fxv[1]; CL = fxv[2]; R0 = fxv[3]; RL = fxv[4];
+                k00 = fxv[5]; k0w = fxv[6]; kh0 = fxv[7]; khw = fxv[8];
+              } else {
+                T = (tmp[c] + tmp[64 + c]) + (tmp[128 + c] + tmp[192 + c]);
+                C0 = (tmp[256 + c] + tmp[320 + c]) + (tmp[384 + c] + tmp[448 + c]);
+                CL = (tmp[512 + c] + tmp[576 + c]) + (tmp[640 + c] + tmp[704 + c]);
+                R0 = r0v; RL = rlv;
+                for (int sg = 1; sg < nseg; ++sg) {  // images wider than one 128-px segment
+                  const float* prs = a.pool_rows + static_cast<size_t>(ba) * rows_img_e * 64 + c;
+                  R0 += prs[(static_cast<size_t>(sg) * H) * 64];
+                  RL += prs[(static_cast<size_t>(sg) * H + (H - 1)) * 64];
+                }
               }
 #pragma unroll
               for (int dy = 0; dy < 3; ++dy)
@@ -834,6 +853,13 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         }
       } else {
         grid_dep_wait();
+        if constexpr (EPI == EPI_RELU_STATS) {
+          // the statistics buffer the NEXT block's conv1 accumulates into: its last reader (the previous conv2) is complete
+          if (a.istats_clear != nullptr) {
+            const int nth = 128 * kEpiGroups;
+            for (int i = blockIdx.x * nth + egrp * 128 + et; i < a.B * 576; i += gridDim.x * nth) a.istats_clear[i] = 0;
+          }
+        }
       }
       if constexpr (kTwoEpi && kScaleSkip) {
         if (a.epi_stats) named_bar_sync(6, 256);  // the attention vectors (svec_s) of both groups are complete
@@ -1143,7 +1169,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           // group's previous row to drain its staging tile (measured: ~800 clk per row on the epilogue's critical path)
           const int sb = kTwoEpi ? (egrp * 2 + ((it >> 1) & 1)) : (it & 1);
           uint8_t* st = stage + sb * kStageBytes;
-          float* pool_g = pool_s + egrp * 256;
+          float* pool_g = pool_s + egrp * 384;
           const uint32_t bar_c = 1 + 2 * egrp, bar_d = 2 + 2 * egrp;
           // Inference epilogues (bias / ReLU / per-row channel sums): the accumulator is read in the 16x256b fragment
           // layout — a thread owns 4 pixels x 16 channels instead of 1 pixel x 64 channels — so the per-row channel sums
@@ -1195,7 +1221,18 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
                 // over the image (relative effect on the pooled mean ~1e-5) and the fp32 value is what the
                 // reference's own pooled mean is made of
                 const int xs = x0 + 8 * sl;
-                if (ok && (xs == 0 || xs == a.W - 1)) {
+                if (a.istats != nullptr) {  // first / last column of the row go to the 64 accumulating threads via smem
+                  if (ok && xs == 0) {
+#pragma unroll
+                    for (int n = 0; n < 8; ++n)
+                      *reinterpret_cast<float2*>(pool_g + 256 + 8 * n + 2 * cq) = make_float2(v[2 * n], v[2 * n + 1]);
+                  }
+                  if (ok && xs == a.W - 1) {
+#pragma unroll
+                    for (int n = 0; n < 8; ++n)
+                      *reinterpret_cast<float2*>(pool_g + 320 + 8 * n + 2 * cq) = make_float2(v[2 * n], v[2 * n + 1]);
+                  }
+                } else if (ok && (xs == 0 || xs == a.W - 1)) {
                   const size_t ro = (static_cast<size_t>(b) * a.H + y) * 64 + 2 * cq;
                   if (xs == 0) {
 #pragma unroll
@@ -1350,10 +1387,49 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           if constexpr (EPI == EPI_BIAS_POOL || EPI == EPI_RELU_STATS) {
             if (et < 64) {
               const float s = ((pool_g[et] + pool_g[64 + et]) + pool_g[128 + et]) + pool_g[192 + et];
-              a.pool_rows[(static_cast<size_t>(col) * a.H + y) * 64 + et] = s;
+              if (EPI == EPI_RELU_STATS && a.istats != nullptr) {
+                if (b != cur_img) {  // (uniform) image change: flush the previous image's accumulators
+                  if (cur_img >= 0) {
+                    unsigned long long* dst = reinterpret_cast<unsigned long long*>(a.istats) + static_cast<size_t>(cur_img) * 576 + et;
+                    atomicAdd(dst, static_cast<unsigned long long>(fx_t));
+                    atomicAdd(dst + 64, static_cast<unsigned long long>(fx_c0));
+                    atomicAdd(dst + 128, static_cast<unsigned long long>(fx_cl));
+                  }
+                  fx_t = fx_c0 = fx_cl = 0;
+                  cur_img = b;
+                }
+                constexpr float kFx = 16777216.f;  // 2^24
+                const long long fs = __float2ll_rn(s * kFx);
+                fx_t += fs;
+                unsigned long long* dst = reinterpret_cast<unsigned long long*>(a.istats) + static_cast<size_t>(b) * 576 + et;
+                if (y == 0) atomicAdd(dst + 192, static_cast<unsigned long long>(fs));
+                if (y == a.H - 1) atomicAdd(dst + 256, static_cast<unsigned long long>(fs));
+                if (seg == 0) {
+                  const long long f0 = __float2ll_rn(pool_g[256 + et] * kFx);
+                  fx_c0 += f0;
+                  if (y == 0) atomicAdd(dst + 320, static_cast<unsigned long long>(f0));          // K00
+                  if (y == a.H - 1) atomicAdd(dst + 448, static_cast<unsigned long long>(f0));    // KH0
+                }
+                if (seg == nseg - 1) {
+                  const long long fl = __float2ll_rn(pool_g[320 + et] * kFx);
+                  fx_cl += fl;
+                  if (y == 0) atomicAdd(dst + 384, static_cast<unsigned long long>(fl));          // K0W
+                  if (y == a.H - 1) atomicAdd(dst + 512, static_cast<unsigned long long>(fl));    // KHW
+                }
+              } else {
+                a.pool_rows[(static_cast<size_t>(col) * a.H + y) * 64 + et] = s;
+              }
             }
           }
           if (q == 0) DFIR_TRACE(14 + egrp, it >> (kTwoEpi ? 1 : 0));
+        }
+      }
+      if constexpr (EPI == EPI_RELU_STATS) {
+        if (a.istats != nullptr && et < 64 && cur_img >= 0) {
+          unsigned long long* dst = reinterpret_cast<unsigned long long*>(a.istats) + static_cast<size_t>(cur_img) * 576 + et;
+          atomicAdd(dst, static_cast<unsigned long long>(fx_t));
+          atomicAdd(dst + 64, static_cast<unsigned long long>(fx_c0));
+          atomicAdd(dst + 128, static_cast<unsigned long long>(fx_cl));
         }
       }
       if (EPI != EPI_TAIL_NCHW && EPI != EPI_SCALE_SKIP && EPI != EPI_SCALE_SKIP_HL && et == 0) tma_store_wait<0>();
@@ -1479,12 +1555,13 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   if (hl_mode && (fused || d.out_bf16 == nullptr || d.skip_hi == nullptr || d.skip_lo == nullptr || d.out_pix_stride != 128 ||
                   d.out_row_stride != static_cast<long long>(d.W) * 128 || d.r_out != nullptr || d.relu_out))
     return DFIR_ERR_ARG;  // the stream planes are dense NHWC; training extras live on the fp32-stream epilogue
+  if (d.epi_stats == 2 && (!hl_mode || d.istats == nullptr)) return DFIR_ERR_ARG;
   if ((d.epi == EPI_SCALE_SKIP || hl_mode) && d.epi_stats &&
-      (fused || d.ca_style == DFIR_STYLE_NONE || d.pool_rows == nullptr || d.col_first == nullptr || d.col_last == nullptr || d.ca_params == nullptr ||
+      (fused || d.ca_style == DFIR_STYLE_NONE || (d.epi_stats != 2 && (d.pool_rows == nullptr || d.col_first == nullptr || d.col_last == nullptr)) || d.ca_params == nullptr ||
        d.ca_A > 512 || d.ca_M > 448 || (d.ca_A > 0 && d.attributes == nullptr)))
     return DFIR_ERR_ARG;
   if (d.epi == EPI_RELU_MASK && d.mask_bf16 == nullptr) return DFIR_ERR_ARG;
-  if (d.epi == EPI_RELU_STATS && (d.pool_rows == nullptr || d.col_first == nullptr || d.col_last == nullptr))
+  if (d.epi == EPI_RELU_STATS && d.istats == nullptr && (d.pool_rows == nullptr || d.col_first == nullptr || d.col_last == nullptr))
     return DFIR_ERR_ARG;
   CUtensorMap tin, tout;
   int rc = DFIR_OK;
@@ -1520,6 +1597,8 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   ConvTcArgs a{};
   a.hl_store_lo = d.out_lo != nullptr ? 1 : 0;
   a.flip = (hl_mode && d.flip && d.W <= 128) ? 1 : 0;
+  a.istats = d.istats;
+  a.istats_clear = d.istats_clear;
   a.B = d.B;
   a.H = d.H;
   a.W = d.W;

@@ -65,6 +65,14 @@ struct ConvTcArgs {  // kernel argument block
   const void* next_w;       // packed weights of the NEXT conv of the chain (or nullptr): pulled into L2 at kernel start
   int next_w_bytes;
   int hl_store_lo;          // EPI_SCALE_SKIP_HL: also write the lo plane (0 = the result only feeds a conv: hi suffices)
+  // Image statistics of pool-by-linearity as 64-bit FIXED-POINT sums (2^-24 units) accumulated with atomics: integer
+  // addition is associative, so the result does not depend on how rows are grouped into CTA bands — an image's statistics
+  // (hence its output) stay bit-identical whatever else is in the batch — and conv2's prologue reads 9 x 64 numbers per
+  // image instead of summing three per-row arrays.  Layout [B][9][64] long long: T, C0, CL, R0, RL, K00, K0W, KH0, KHW
+  // (total, first / last column sums, first / last row sums, the four corner pixels).
+  long long* istats;        // EPI_RELU_STATS: accumulate here instead of writing pool_rows / col_first / col_last;
+                            // EPI_SCALE_SKIP_HL with epi_stats == 2: read the statistics from here
+  long long* istats_clear;  // EPI_RELU_STATS: [B][9][64] buffer to zero for the NEXT block's conv1 (or nullptr)
   int flip;                 // EPI_SCALE_SKIP_HL: traverse images and rows in DESCENDING order (the rows the previous,
                             // ascending, kernel touched last are still in L2); requires W <= 128
 };
@@ -98,6 +106,8 @@ struct ConvTcDesc {  // host-side launch description
   const void* skip_lo = nullptr;
   void* out_lo = nullptr;         // nullptr: hi only
   int flip = 0;                   // EPI_SCALE_SKIP_HL: descending traversal (see ConvTcArgs::flip)
+  long long* istats = nullptr;        // see ConvTcArgs
+  long long* istats_clear = nullptr;
   float* pool_rows;
   float* col_first;
   float* col_last;
