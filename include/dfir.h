@@ -454,6 +454,74 @@ size_t dfir_nonlocal_scratch_bytes(int B, int H, int W);
 int dfir_nonlocal(const float* x, const float* w_tpg, const float* b_tpg, const float* w_out, const float* b_out,
                   float* out, void* scratch, int B, int H, int W, int C, void* stream);
 
+/* ---- training of the Q-SAN / Q-HAN specific layers (csrc/san_han_bwd.cu).  The reference trains these layers through
+ * autograd over the forward code cited at each forward operator above; the functions below restate the derivatives
+ * autograd produces.  All tensors fp32, feature maps NHWC, C = 64 unless a C argument says otherwise. */
+
+/* out[b][c] = sum_p a[b][p][c] * b[b][p][c]  (gradient of a per-image channel scale, SAN_blocks.py:302); total (optional,
+ * one float) = sum of out over (b, c), added to its previous value when accumulate_total != 0 (gradient of the scalar
+ * `gamma` of `x + gamma * residual`, attention_manipulators/architectures.py:459).  out may be NULL. */
+size_t dfir_channel_dot_scratch_bytes(int B, int C);
+int dfir_channel_dot(const float* a, const float* b, float* out, float* total, int accumulate_total, void* scratch,
+                     size_t scratch_bytes, int B, long long HW, int C, void* stream);
+
+/* Tail of SOCA.forward (SAN_blocks.py:290-300) on the square root S [B][64][64]: v = mean over dim 1, svec =
+ * sigmoid(W2 relu(W1 v + b1) + b2), and its backward: grad_S [B][64][64], grad_mlp (same flat layout as mlp_params,
+ * overwritten; summed over the batch in index order). */
+int dfir_soca_mlp(const float* S, const float* mlp_params, int R, float* svec, int B, void* stream);
+int dfir_soca_mlp_backward(const float* S, const float* grad_svec, const float* mlp_params, int R, float* grad_S,
+                           float* grad_mlp, int B, void* stream);
+
+/* Backward of dfir_lam: fwd_scratch is the scratch buffer of the forward call, unmodified (it holds the attention matrix);
+ * grad_out [B][HW][N*C]; grad_stack: map n at grad_stack + n * grad_map_stride_elems; grad_gamma: one float (overwritten). */
+size_t dfir_lam_backward_scratch_bytes(int B, int N);
+int dfir_lam_backward(const float* stack, long long map_stride_elems, const void* fwd_scratch, float gamma,
+                      const float* grad_out, float* grad_stack, long long grad_map_stride_elems, float* grad_gamma,
+                      void* scratch, size_t scratch_bytes, int N, int B, int HW, int C, void* stream);
+
+/* Backward of dfir_csam: grad_x [B][H][W][C], grad_w27 [27], grad_bias [1], grad_gamma [1] (all overwritten). */
+size_t dfir_csam_backward_scratch_bytes(int B, int H, int W, int C);
+int dfir_csam_backward(const float* x, const float* grad_out, const float* w27, float bias, float gamma, float* grad_x,
+                       float* grad_w27, float* grad_bias, float* grad_gamma, void* scratch, size_t scratch_bytes, int B,
+                       int H, int W, int C, void* stream);
+
+/* Backward of dfir_nonlocal: grad_x [B][H][W][64]; grad_w_tpg [24][64], grad_b_tpg [24], grad_w_out [64][8], grad_b_out
+ * [64] are overwritten, or added to when accumulate != 0 (Q-SAN applies the one non-local block twice).  Max-pool
+ * gradients go to the first maximum of each 2x2 window, as torch's max_pool2d backward does. */
+size_t dfir_nonlocal_backward_scratch_bytes(int B, int H, int W);
+int dfir_nonlocal_backward(const float* x, const float* grad_out, const float* w_tpg, const float* b_tpg,
+                           const float* w_out, float* grad_x, float* grad_w_tpg, float* grad_b_tpg, float* grad_w_out,
+                           float* grad_b_out, int accumulate, void* scratch, size_t scratch_bytes, int B, int H, int W,
+                           int C, void* stream);
+
+/* dfir_pack_conv3x3_f32 with the data-gradient option: transpose != 0 packs the 180-degree-rotated, channel-transposed
+ * filter, so that dfir_conv3x3_f32(dy, packed, bias = NULL, ..., Cin = cout, Cout = cin) is the data gradient of the conv. */
+int dfir_pack_conv3x3_f32_ex(const float* w_oihw, float* out, int cout, int cin, int transpose, void* stream);
+
+/* Staged training step (Q-SAN / Q-HAN put their own layers between the stages of the Q-RCAN trunk; reference:
+ * attention_manipulators/architectures.py:447-467, 514-540 under BaseModel.run_train, models/__init__.py:466-489).
+ * One stage per call, feature maps between stages fp32 NHWC [B][H][W][C] owned by the caller, activations stashed in
+ * the same workspace as dfir_qrcan_train_forward (dfir_qrcan_train_workspace_bytes):
+ *   DFIR_TRAIN_HEAD   forward : x_nchw -> feat_out (also evaluates the meta-attention scales of every block);
+ *                     backward: grad_feat_out -> head conv weight / bias gradients
+ *   DFIR_TRAIN_GROUPS forward : feat_in -> groups [g_begin, g_end) -> feat_out (+ group_out[g - g_begin] after every
+ *                     group, optional); backward: grad_feat_out -> grad_feat_in + the groups' conv gradients.  Networks
+ *                     without group convs (Q-SAN) run one group per call
+ *   DFIR_TRAIN_TAIL   forward : feat_in -> upsampler + tail conv -> out_nchw; backward: grad_out_nchw -> grad_feat_in
+ *   DFIR_TRAIN_ATTN   backward only, after every GROUPS stage: channel- / meta-attention parameter gradients */
+#define DFIR_TRAIN_HEAD 1
+#define DFIR_TRAIN_GROUPS 2
+#define DFIR_TRAIN_TAIL 8
+#define DFIR_TRAIN_ATTN 16
+int dfir_qrcan_train_stage_forward(const dfir_qrcan_net* net, int stage, int g_begin, int g_end, const float* x_nchw,
+                                   const float* attributes, const float* feat_in, float* feat_out, float* group_out,
+                                   float* out_nchw, int B, int H, int W, int precision, void* workspace,
+                                   size_t workspace_bytes, void* stream);
+int dfir_qrcan_train_stage_backward(const dfir_qrcan_net* net, const dfir_qrcan_params* grads, int stage, int g_begin,
+                                    int g_end, const float* x_nchw, const float* attributes, const float* grad_out_nchw,
+                                    const float* grad_feat_out, float* grad_feat_in, int B, int H, int W, int precision,
+                                    void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,12 +4,14 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 using namespace dfir;
 
 namespace {
 
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+constexpr int kDefaultSplit = 1;
 inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
 struct Carver {
@@ -121,7 +123,50 @@ struct StageArgs {
   int g_begin = 0, g_end = 0;     // groups to run (ST_GROUPS)
   int from_xa = 0;                // the stream entering g_begin is in XA/XAbf (external features), not the head output
   float* group_out = nullptr;     // optional: fp32 NHWC copy of the stream after every executed group
+  // concurrent sub-passes (see SplitCtx): the first trunk conv waits for `phase_wait`, `phase_record` is recorded right
+  // after it, so that consecutive sub-passes start one kernel apart and stay in anti-phase
+  cudaEvent_t phase_wait = nullptr, phase_record = nullptr;
 };
+
+// Concurrent sub-passes.  An RCAB alternates a tensor-pipe-bound kernel (conv1: 134 MB, 38.7 GFLOP per 32 images) with an
+// HBM-bound one (conv2: 335 MB for the same FLOPs).  Run back to back on all SMs each leaves the other resource idle; run
+// as `ways` independent sub-passes (disjoint images, private workspaces, grids of #SMs / ways CTAs, one stream each,
+// staggered by one kernel) the conv1 of one sub-pass overlaps the conv2 of another.  The streams and events are created
+// once per device and live for the life of the process; fork / join are event edges, so the pattern is graph-capturable.
+struct SplitCtx {
+  static constexpr int kMaxWays = 4;
+  cudaStream_t side[kMaxWays - 1] = {};
+  cudaEvent_t fork = nullptr, join[kMaxWays - 1] = {}, phase[kMaxWays - 1] = {};
+  bool ok = false;
+};
+
+SplitCtx* split_ctx(int dev) {
+  static std::mutex mu;
+  static SplitCtx ctx[64];
+  if (dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  SplitCtx& c = ctx[dev];
+  if (!c.ok) {
+    bool good = cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < SplitCtx::kMaxWays - 1 && good; ++i)
+      good = cudaStreamCreateWithFlags(&c.side[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c.join[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c.phase[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!good) return nullptr;
+    c.ok = true;
+  }
+  return &c;
+}
+
+// Number of concurrent sub-passes of one pass of Bc images (DFIR_SPLIT overrides; 1 = off).
+int split_ways(const dfir_qrcan_net* n, int Bc, int precision) {
+  static const int env = getenv("DFIR_SPLIT") == nullptr ? 0 : atoi(getenv("DFIR_SPLIT"));
+  int ways = env > 0 ? env : kDefaultSplit;
+  if (precision != DFIR_PREC_BF16_TC || n->n_feats != 64) return 1;
+  if (ways > SplitCtx::kMaxWays) ways = SplitCtx::kMaxWays;
+  while (ways > 1 && Bc < 2 * ways) --ways;  // at least two images per sub-pass
+  return ways < 1 ? 1 : ways;
+}
 
 int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* attr, float* out, int B, int Bc, int b0,
                        int H, int W, const QrcanWs& w, int num_sms, const StageArgs& sa, cudaStream_t st) {
@@ -186,6 +231,14 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
 
   const float* xcur = w.Hh;
   const int gb = (sa.stages & ST_GROUPS) ? sa.g_begin : 0, ge = (sa.stages & ST_GROUPS) ? sa.g_end : 0;
+  bool first_trunk = true;
+  auto trunk_conv = [&](const ConvTcDesc& d) -> int {
+    if (first_trunk && sa.phase_wait != nullptr && cudaStreamWaitEvent(st, sa.phase_wait, 0) != cudaSuccess) return DFIR_ERR_CUDA;
+    DFIR_TRY(conv3x3_c64_tc(d, st));
+    if (first_trunk && sa.phase_record != nullptr && cudaEventRecord(sa.phase_record, st) != cudaSuccess) return DFIR_ERR_CUDA;
+    first_trunk = false;
+    return DFIR_OK;
+  };
   for (int g = gb; g < ge; ++g) {
     const bool from_head = g == 0 && !sa.from_xa;
     const float* skip32 = from_head ? w.Hh : w.XA;         // group input (fp32 stream), kept for `res += x`
@@ -211,7 +264,7 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
       } else {
         c1.in_bf16 = w.XBbf;
       }
-      DFIR_TRY(conv3x3_c64_tc(c1, st));
+      DFIR_TRY(trunk_conv(c1));
       if (sched == 0 || sched == 3) {
         const int w2 = g * per_group + 2 * b + 1;
         // conv2 + attention scale + residual: x_{b+1} = (conv(t) + b) * s + x_b (fp32, in place after block 0);
@@ -661,7 +714,9 @@ int dfir_pool_rows_f32(const float* in, float* pool_rows, int B, int H, int W, i
 size_t dfir_qrcan_workspace_bytes(const dfir_qrcan_net* net, int B, int H, int W, int precision) {
   if (net == nullptr || B <= 0 || H <= 0 || W <= 0) return 0;
   const int Bc = net->chunk_images > 0 ? std::min(net->chunk_images, B) : auto_chunk(B, H, W, precision);
-  return carve_qrcan(net, B, Bc, H, W, precision, nullptr).total;
+  const int ways = split_ways(net, Bc, precision);
+  const int Bs = (Bc + ways - 1) / ways;
+  return ways * align256(carve_qrcan(net, B, Bs, H, W, precision, nullptr).total);
 }
 
 long long dfir_qrcan_launch_count(const dfir_qrcan_net* net, int B, int H, int W, int precision) {
@@ -816,8 +871,11 @@ int dfir_qrcan_forward(const dfir_qrcan_net* net, const float* x_nchw, const flo
   if (precision != DFIR_PREC_BF16_TC && precision != DFIR_PREC_FP32_SIMT) return DFIR_ERR_ARG;
   DFIR_TRY(dfir_check_device());
   const int Bc = net->chunk_images > 0 ? std::min(net->chunk_images, B) : auto_chunk(B, H, W, precision);
-  QrcanWs w = carve_qrcan(net, B, Bc, H, W, precision, workspace);
-  if (workspace == nullptr || w.total > workspace_bytes) return DFIR_ERR_WORKSPACE;
+  const int ways = split_ways(net, Bc, precision);
+  const int Bs = (Bc + ways - 1) / ways;  // images per concurrent sub-pass
+  QrcanWs w = carve_qrcan(net, B, Bs, H, W, precision, workspace);
+  const size_t sub_bytes = align256(w.total);
+  if (workspace == nullptr || ways * sub_bytes > workspace_bytes) return DFIR_ERR_WORKSPACE;
   cudaStream_t st = S(stream);
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess ||
@@ -830,6 +888,36 @@ int dfir_qrcan_forward(const dfir_qrcan_net* net, const float* x_nchw, const flo
   }
   StageArgs all;
   all.g_end = net->n_groups;
+  if (ways > 1) {
+    SplitCtx* sc = split_ctx(dev);
+    if (sc == nullptr) return DFIR_ERR_CUDA;
+    QrcanWs ws[SplitCtx::kMaxWays];
+    for (int i = 0; i < ways; ++i) {
+      ws[i] = carve_qrcan(net, B, Bs, H, W, precision, reinterpret_cast<uint8_t*>(workspace) + i * sub_bytes);
+      ws[i].sq = w.sq;  // the meta-attention vectors of the whole batch, written once above
+    }
+    const int sub_sms = std::max(1, sms / ways);
+    for (int b0 = 0; b0 < B; b0 += Bc) {
+      const int bc = std::min(Bc, B - b0);
+      if (cudaEventRecord(sc->fork, st) != cudaSuccess) return DFIR_ERR_CUDA;
+      int used = 0;
+      for (int i = 0; i < ways; ++i) {
+        const int s0 = i * Bs, sn = std::min(Bs, bc - s0);
+        if (sn <= 0) break;
+        cudaStream_t si = i == 0 ? st : sc->side[i - 1];
+        if (i > 0 && cudaStreamWaitEvent(si, sc->fork, 0) != cudaSuccess) return DFIR_ERR_CUDA;
+        StageArgs sa = all;
+        sa.phase_wait = i > 0 ? sc->phase[i - 1] : nullptr;
+        sa.phase_record = (i + 1 < ways && (i + 1) * Bs < bc) ? sc->phase[i] : nullptr;
+        DFIR_TRY(qrcan_forward_bf16(net, x_nchw, attributes, out_nchw, B, sn, b0 + s0, H, W, ws[i], sub_sms, sa, si));
+        if (i > 0 && cudaEventRecord(sc->join[i - 1], si) != cudaSuccess) return DFIR_ERR_CUDA;
+        used = i + 1;
+      }
+      for (int i = 1; i < used; ++i)
+        if (cudaStreamWaitEvent(st, sc->join[i - 1], 0) != cudaSuccess) return DFIR_ERR_CUDA;
+    }
+    return DFIR_OK;
+  }
   for (int b0 = 0; b0 < B; b0 += Bc) {
     const int bc = std::min(Bc, B - b0);
     if (precision == DFIR_PREC_BF16_TC)

@@ -183,6 +183,28 @@ int sqrtm_backward(const float* cov, const float* grad_out, float* grad_in, floa
 int nonlocal_forward(const float* x, const float* wq, const float* bq, const float* wW, const float* bW, float* out,
                      float* scratch, int B, int H, int W, int C, cudaStream_t s);
 size_t nonlocal_scratch_floats(int B, int H, int W);
+int nonlocal_project_pool(const float* x, const float* wq, const float* bq, float* proj, float* keys, int B, int H, int W,
+                          cudaStream_t s);
+// ---- backward of the Q-HAN / Q-SAN layers (san_han_bwd.cu)
+size_t channel_dot_scratch_floats(int B, int C);
+int channel_dot(const float* a, const float* b, float* out, float* total, int accumulate_total, float* scratch, int B,
+                long long HW, int C, cudaStream_t s);
+size_t outer_reduce_scratch_floats(int Ao, int Bi);
+int outer_reduce(const float* A, int Ao, const float* Bm, int Bi, long long npix, float* out, float* colsum,
+                 int accumulate, float* scratch, cudaStream_t s);
+int soca_mlp_forward(const float* S, const float* mlp, int R, float* svec, int B, cudaStream_t s);
+int soca_mlp_backward(const float* S, const float* dsvec, const float* mlp, int R, float* dS, float* dmlp, int B,
+                      cudaStream_t s);
+size_t lam_bwd_scratch_floats(int B, int N);
+int lam_backward(const float* stack, long long map_stride, const float* att, float gamma, const float* dout, float* dstack,
+                 long long dmap_stride, float* dgamma, float* scratch, int N, int B, int HW, int C, cudaStream_t s);
+size_t csam_bwd_scratch_floats(int B, int H, int W, int C);
+int csam_backward(const float* x, const float* dout, const float* w27, float bias, float gamma, float* dx, float* dw27,
+                  float* dbias, float* dgamma, float* scratch, int B, int H, int W, int C, cudaStream_t s);
+size_t nonlocal_bwd_scratch_floats(int B, int H, int W);
+int nonlocal_backward(const float* x, const float* dz, const float* wq, const float* bq, const float* wW, float* dx,
+                      float* dwq, float* dbq, float* dwW, float* dbW, int accumulate, float* scratch, int B, int H, int W,
+                      int C, cudaStream_t s);
 // ---- training step (train_kernels.cu, wgrad_tc.cu)
 int pack_bf16_multi(const float* const* tbl, const float* direct, void* out, int n_tiles, int cout, int nt_rows,
                     int per_src, int transpose, cudaStream_t s, int j0 = 0);

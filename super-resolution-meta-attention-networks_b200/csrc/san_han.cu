@@ -842,6 +842,19 @@ int nonlocal_forward(const float* x, const float* wq, const float* bq, const flo
   return ok_or_cuda2();
 }
 
+// theta / phi / g projections and the pooled keys only (the backward pass rebuilds them instead of stashing them)
+int nonlocal_project_pool(const float* x, const float* wq, const float* bq, float* proj, float* keys, int B, int H, int W,
+                          cudaStream_t s) {
+  if (B == 0) return DFIR_OK;
+  if (H < 2 || W < 2) return DFIR_ERR_ARG;
+  const long long npix = static_cast<long long>(B) * H * W;
+  const int nk_max = ((H - H / 2) / 2) * ((W - W / 2) / 2) + 1;
+  nl_project_kernel<<<static_cast<unsigned>(std::min<long long>((npix + 255) / 256, 148 * 8)), 256, 0, s>>>(x, wq, bq, proj,
+                                                                                                            npix);
+  nl_pool_kernel<<<dim3(std::max(1, (nk_max + 127) / 128), 4, B), 128, 0, s>>>(proj, keys, B, H, W, nk_max);
+  return ok_or_cuda2();
+}
+
 size_t nonlocal_scratch_floats(int B, int H, int W) {
   const size_t npix = static_cast<size_t>(B) * H * W;
   const size_t nk_max = static_cast<size_t>((H - H / 2) / 2) * ((W - W / 2) / 2) + 1;

@@ -68,12 +68,27 @@ struct TrainWs {
   size_t total;
 };
 
-bool train_supported(const dfir_qrcan_net* n, int precision) {
+// Stages of a training step.  dfir_qrcan_train_forward / _backward run all of them on the library's own buffers; the staged
+// entry points (dfir_qrcan_train_stage_*) run ONE per call with the feature maps between stages owned by the caller
+// (fp32 NHWC), so that Q-SAN / Q-HAN can put their own layers between the head, the residual groups and the tail.
+enum : int { T_HEAD = 1, T_GROUPS = 2, T_TRUNK_CONV = 4, T_TAIL = 8, T_ATTN = 16, T_ALL = 31 };
+struct TrainStage {
+  int stages = T_ALL;
+  int g0 = 0, g1 = 0;
+  const float* feat_in = nullptr;    // forward: input feature map of the stage (GROUPS, TAIL)
+  float* feat_out = nullptr;         // forward: output feature map of the stage (HEAD, GROUPS)
+  float* group_out = nullptr;        // forward, GROUPS: [g1 - g0][B][H][W][C] stream after every group (optional)
+  const float* gfeat_out = nullptr;  // backward: gradient of the stage's output feature map (HEAD, GROUPS)
+  float* gfeat_in = nullptr;         // backward: gradient of the stage's input feature map (GROUPS, TAIL)
+  bool all() const { return stages == T_ALL; }
+};
+
+bool train_supported(const dfir_qrcan_net* n, int precision, bool staged = false) {
   int r = 0;
   if (n == nullptr || up_stages(n->scale, &r) < 0) return false;
   if (n->n_groups < 1 || n->n_blocks < 1) return false;
   if (n->pa_blob != nullptr) return false;  // pixel attention has no backward kernels yet
-  if (n->no_group_conv && n->n_groups != 1) return false;
+  if (n->no_group_conv && n->n_groups != 1 && !staged) return false;
   if (n->style < DFIR_STYLE_NONE || n->style > DFIR_STYLE_EXTENDED) return false;
   if (precision == DFIR_PREC_BF16_TC) return n->n_feats == 64;
   if (precision != DFIR_PREC_FP32_SIMT) return false;
@@ -178,8 +193,9 @@ struct Ctx {
   float* ymean(int k) const { return w.ymean + static_cast<size_t>(k) * B * C; }
 };
 
-int make_ctx(Ctx& c, const dfir_qrcan_net* n, int B, int H, int W, int precision, void* ws, size_t ws_bytes, void* stream) {
-  if (!train_supported(n, precision) || B <= 0 || H <= 0 || W <= 0) return DFIR_ERR_ARG;
+int make_ctx(Ctx& c, const dfir_qrcan_net* n, int B, int H, int W, int precision, void* ws, size_t ws_bytes, void* stream,
+             bool staged = false) {
+  if (!train_supported(n, precision, staged) || B <= 0 || H <= 0 || W <= 0) return DFIR_ERR_ARG;
   if (dfir_check_device() != DFIR_OK) return DFIR_ERR_ARCH;
   c.n = n;
   c.w = carve_train(n, B, H, W, precision, ws);
@@ -231,15 +247,31 @@ bool train_linear_schedule(int B, int H, int W, int sms) {
 }
 
 // =============================================================================================== forward
-int train_forward_tc(const Ctx& c, const float* x, const float* attr, float* out) {
+int copy_f32(float* dst, const float* src, size_t n, cudaStream_t st) {
+  return cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, st) == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
+}
+
+int train_forward_tc(const Ctx& c, const float* x, const float* attr, float* out, const TrainStage& ts) {
   const dfir_qrcan_net* n = c.n;
   const TrainWs& w = c.w;
   const int H = c.H, W = c.W, C = 64;
-  DFIR_TRY(head_conv(x, n->head_w_f32, n->head_b, w.Hh, reinterpret_cast<__nv_bfloat16*>(c.XIN(0)), c.B, n->in_feats, H,
-                     W, C, c.st));
+  const size_t feat = static_cast<size_t>(c.B) * H * W * C;
+  if (ts.stages & T_HEAD) {
+    if (ts.all())
+      DFIR_TRY(head_conv(x, n->head_w_f32, n->head_b, w.Hh, reinterpret_cast<__nv_bfloat16*>(c.XIN(0)), c.B, n->in_feats,
+                         H, W, C, c.st));
+    else
+      DFIR_TRY(head_conv(x, n->head_w_f32, n->head_b, ts.feat_out, nullptr, c.B, n->in_feats, H, W, C, c.st));
+  }
   const bool linear = train_linear_schedule(c.B, H, W, c.sms);
-  for (int g = 0; g < c.ng; ++g) {
-    const float* skip32 = g == 0 ? w.Hh : w.XA;
+  const float* first_skip = w.Hh;
+  const int g0 = (ts.stages & T_GROUPS) ? ts.g0 : 0, g1 = (ts.stages & T_GROUPS) ? ts.g1 : 0;
+  if ((ts.stages & T_GROUPS) && !ts.all()) {
+    DFIR_TRY(f32_to_bf16(ts.feat_in, reinterpret_cast<__nv_bfloat16*>(c.XIN(g0 * c.nb)), static_cast<long long>(feat), c.st));
+    first_skip = ts.feat_in;
+  }
+  for (int g = g0; g < g1; ++g) {
+    const float* skip32 = g == g0 ? first_skip : w.XA;
     for (int b = 0; b < c.nb; ++b) {
       const int k = g * c.nb + b;
       const int w1 = g * c.per_group + 2 * b, w2 = w1 + 1;
@@ -284,13 +316,19 @@ int train_forward_tc(const Ctx& c, const float* x, const float* attr, float* out
       ct.out_bf16 = (g + 1 < c.ng) ? c.XIN((g + 1) * c.nb) : c.TRUNK_IN();
       DFIR_TRY(conv3x3_c64_tc(ct, c.st));
     }
+    if (ts.group_out != nullptr)
+      DFIR_TRY(copy_f32(ts.group_out + static_cast<size_t>(g - g0) * feat, n->no_group_conv ? w.XB : w.XA, feat, c.st));
   }
-  {
+  if ((ts.stages & T_GROUPS) && !ts.all() && ts.feat_out != nullptr && g1 > g0)
+    DFIR_TRY(copy_f32(ts.feat_out, n->no_group_conv ? w.XB : w.XA, feat, c.st));
+  if (ts.stages & T_TRUNK_CONV) {
     const int wf = c.ng * c.per_group;
     ConvTcDesc cf = tc_desc(c, tc_w(c, wf), tc_b(c, wf), EPI_SCALE_SKIP, H, W);
     cf.in_bf16 = c.TRUNK_IN(); cf.skip_f32 = w.Hh; cf.out_f32 = nullptr; cf.out_bf16 = c.F();
     DFIR_TRY(conv3x3_c64_tc(cf, c.st));
   }
+  if (!(ts.stages & T_TAIL)) return DFIR_OK;
+  if (!ts.all()) DFIR_TRY(f32_to_bf16(ts.feat_in, reinterpret_cast<__nv_bfloat16*>(c.F()), static_cast<long long>(feat), c.st));
   const void* cur = c.F();
   int h = H, wd = W;
   const int r = c.r;
@@ -317,18 +355,23 @@ int train_forward_tc(const Ctx& c, const float* x, const float* attr, float* out
   return conv3x3_c64_tc(d, c.st);
 }
 
-int train_forward_f32(const Ctx& c, const float* x, const float* attr, float* out) {
+int train_forward_f32(const Ctx& c, const float* x, const float* attr, float* out, const TrainStage& ts) {
   const dfir_qrcan_net* n = c.n;
   const TrainWs& w = c.w;
   const int H = c.H, W = c.W, C = c.C, B = c.B;
   const size_t wsz = static_cast<size_t>(9) * C * C;
+  const size_t feat = static_cast<size_t>(B) * H * W * C;
   auto F32 = [](uint8_t* p) { return reinterpret_cast<float*>(p); };
   auto conv = [&](const float* in, int widx, int relu, const float* skip, float* o) {
     return conv3x3_f32(in, n->conv_w_f32 + widx * wsz, n->conv_b + static_cast<size_t>(widx) * C, skip, o, B, H, W, C, C,
                        relu, 1, 0, c.st);
   };
-  DFIR_TRY(head_conv(x, n->head_w_f32, n->head_b, F32(c.XIN(0)), nullptr, B, n->in_feats, H, W, C, c.st));
-  for (int g = 0; g < c.ng; ++g) {
+  if (ts.stages & T_HEAD)
+    DFIR_TRY(head_conv(x, n->head_w_f32, n->head_b, ts.all() ? F32(c.XIN(0)) : ts.feat_out, nullptr, B, n->in_feats, H, W, C,
+                       c.st));
+  const int g0 = (ts.stages & T_GROUPS) ? ts.g0 : 0, g1 = (ts.stages & T_GROUPS) ? ts.g1 : 0;
+  if ((ts.stages & T_GROUPS) && !ts.all()) DFIR_TRY(copy_f32(F32(c.XIN(g0 * c.nb)), ts.feat_in, feat, c.st));
+  for (int g = g0; g < g1; ++g) {
     const float* gin = F32(c.XIN(g * c.nb));
     for (int b = 0; b < c.nb; ++b) {
       const int k = g * c.nb + b;
@@ -340,12 +383,19 @@ int train_forward_f32(const Ctx& c, const float* x, const float* attr, float* ou
       DFIR_TRY(scale_residual(c.R(k), 0, F32(c.XIN(k)), c.pool(k), H, make_ap(n, k), attr, c.sq(k), 1.f, next, nullptr, B,
                               H, W, C, c.st, c.ymean(k)));
     }
+    const float* gres = F32(c.XLAST(g));
     if (!n->no_group_conv) {
       float* o = (g + 1 < c.ng) ? F32(c.XIN((g + 1) * c.nb)) : F32(c.TRUNK_IN());
       DFIR_TRY(conv(F32(c.XLAST(g)), g * c.per_group + 2 * c.nb, 0, gin, o));
+      gres = o;
     }
+    if (ts.group_out != nullptr) DFIR_TRY(copy_f32(ts.group_out + static_cast<size_t>(g - g0) * feat, gres, feat, c.st));
+    if (!ts.all() && g + 1 == g1 && ts.feat_out != nullptr) DFIR_TRY(copy_f32(ts.feat_out, gres, feat, c.st));
   }
-  DFIR_TRY(conv(F32(c.TRUNK_IN()), c.ng * c.per_group, 0, F32(c.XIN(0)), F32(c.F())));
+  if (ts.stages & T_TRUNK_CONV)
+    DFIR_TRY(conv(F32(c.TRUNK_IN()), c.ng * c.per_group, 0, F32(c.XIN(0)), F32(c.F())));
+  if (!(ts.stages & T_TAIL)) return DFIR_OK;
+  if (!ts.all()) DFIR_TRY(copy_f32(F32(c.F()), ts.feat_in, feat, c.st));
   const float* cur = F32(c.F());
   int h = H, wd = W;
   const int r = c.r;
@@ -380,13 +430,16 @@ int wgrad_f(const Ctx& c, const dfir_qrcan_params* gr, const float* dy, const fl
                       gr->conv_b, widx, nullptr, 0, 1, c.st);
 }
 
-int train_backward_tc(const Ctx& c, const dfir_qrcan_params* gr, const float* x, const float* attr, const float* gout) {
+int train_backward_tc(const Ctx& c, const dfir_qrcan_params* gr, const float* x, const float* attr, const float* gout,
+                      const TrainStage& ts) {
   const dfir_qrcan_net* n = c.n;
   const TrainWs& w = c.w;
   const int H = c.H, W = c.W, C = 64, B = c.B, r = c.r;
   const int HW = H * W;
+  const size_t feat = static_cast<size_t>(B) * HW * C;
   const float out_scale = n->style == DFIR_STYLE_NONE ? n->res_scale : 1.f;
   int h = H * n->scale, wd = W * n->scale;
+  if (ts.stages & T_TAIL) {
   // ---- tail conv C -> out_feats
   DFIR_TRY(wgrad_small(gout, w.U[c.nup - 1], 1, w.small, B, h, wd, C, n->out_feats, 1, gr->tail_w, gr->tail_b, c.st));
   DFIR_TRY(head_conv(gout, n->tail_wT_f32, nullptr, nullptr, reinterpret_cast<__nv_bfloat16*>(w.DUop[0]), B, n->out_feats,
@@ -418,15 +471,22 @@ int train_backward_tc(const Ctx& c, const dfir_qrcan_params* gr, const float* x,
     h = hh;
     wd = ww;
   }
+  if (!ts.all()) DFIR_TRY(copy_f32(ts.gfeat_in, w.dF32, feat, c.st));
+  }
   // ---- trunk tail conv: F = conv_f(trunk_in) + head
-  const int wf = c.ng * c.per_group;
-  DFIR_TRY(wgrad_tc(c, gr, w.DFop, c.TRUNK_IN(), wf));
-  {
+  if (ts.stages & T_TRUNK_CONV) {
+    const int wf = c.ng * c.per_group;
+    DFIR_TRY(wgrad_tc(c, gr, w.DFop, c.TRUNK_IN(), wf));
     ConvTcDesc d = tc_desc(c, tc_wT(c, wf), nullptr, EPI_SCALE_SKIP, H, W);
     d.in_bf16 = w.DFop; d.out_f32 = w.G; d.out_bf16 = w.Gop;
     DFIR_TRY(conv3x3_c64_tc(d, c.st));
   }
-  for (int g = c.ng - 1; g >= 0; --g) {
+  const int g0 = (ts.stages & T_GROUPS) ? ts.g0 : 0, g1 = (ts.stages & T_GROUPS) ? ts.g1 : 0;
+  if ((ts.stages & T_GROUPS) && !ts.all()) {
+    DFIR_TRY(copy_f32(w.G, ts.gfeat_out, feat, c.st));
+    DFIR_TRY(f32_to_bf16(w.G, reinterpret_cast<__nv_bfloat16*>(w.Gop), static_cast<long long>(feat), c.st));
+  }
+  for (int g = g1 - 1; g >= g0; --g) {
     float* gsp = n->no_group_conv ? w.G : w.gs;
     if (!n->no_group_conv) {
       const int wg = g * c.per_group + 2 * c.nb;
@@ -456,19 +516,26 @@ int train_backward_tc(const Ctx& c, const dfir_qrcan_params* gr, const float* x,
     }
     if (!n->no_group_conv) DFIR_TRY(add_f32(w.G, w.gs, w.G, w.Gop, static_cast<long long>(B) * HW * C, c.st));
   }
+  if ((ts.stages & T_GROUPS) && !ts.all()) DFIR_TRY(copy_f32(ts.gfeat_in, w.G, feat, c.st));
   // ---- head conv: dL/d head output = dL/dF (trunk skip) + dL/d (group 0 input)
-  DFIR_TRY(add_f32(w.dF32, w.G, w.G, nullptr, static_cast<long long>(B) * HW * C, c.st));
-  DFIR_TRY(wgrad_small(x, w.G, 0, w.small, B, H, W, C, n->in_feats, 0, gr->head_w, gr->head_b, c.st));
+  if (ts.stages & T_HEAD) {
+    if (ts.all()) DFIR_TRY(add_f32(w.dF32, w.G, w.G, nullptr, static_cast<long long>(B) * HW * C, c.st));
+    DFIR_TRY(wgrad_small(x, ts.all() ? w.G : ts.gfeat_out, 0, w.small, B, H, W, C, n->in_feats, 0, gr->head_w, gr->head_b,
+                         c.st));
+  }
+  if (!(ts.stages & T_ATTN)) return DFIR_OK;
   return attn_param_grads(w.sig, w.sig_stride, attr, n->attr_size, n->meta_w1, n->meta_b1, n->meta_w2, n->q_enabled,
                           c.has_ca ? gr->ca : nullptr, n->any_q ? gr->meta : nullptr, c.nblk, B, C,
                           std::max(1, n->reduced), n->num_metadata, n->meta_hidden, n->style, n->meta_relu, c.st);
 }
 
-int train_backward_f32(const Ctx& c, const dfir_qrcan_params* gr, const float* x, const float* attr, const float* gout) {
+int train_backward_f32(const Ctx& c, const dfir_qrcan_params* gr, const float* x, const float* attr, const float* gout,
+                       const TrainStage& ts) {
   const dfir_qrcan_net* n = c.n;
   const TrainWs& w = c.w;
   const int H = c.H, W = c.W, C = c.C, B = c.B, r = c.r;
   const int HW = H * W;
+  const size_t feat = static_cast<size_t>(B) * HW * C;
   const size_t wsz = static_cast<size_t>(9) * C * C;
   const float out_scale = n->style == DFIR_STYLE_NONE ? n->res_scale : 1.f;
   auto F32 = [](uint8_t* p) { return reinterpret_cast<float*>(p); };
@@ -476,6 +543,7 @@ int train_backward_f32(const Ctx& c, const dfir_qrcan_params* gr, const float* x
     return conv3x3_f32(dy, n->conv_wT_f32 + widx * wsz, nullptr, skip, o, B, H, W, C, C, 0, 1, 0, c.st, mask);
   };
   int h = H * n->scale, wd = W * n->scale;
+  if (ts.stages & T_TAIL) {
   DFIR_TRY(wgrad_small(gout, w.U[c.nup - 1], 0, w.small, B, h, wd, C, n->out_feats, 1, gr->tail_w, gr->tail_b, c.st));
   DFIR_TRY(head_conv(gout, n->tail_wT_f32, nullptr, F32(w.DUop[0]), nullptr, B, n->out_feats, h, wd, C, c.st));
   float* cur = F32(w.DUop[0]);
@@ -496,10 +564,16 @@ int train_backward_f32(const Ctx& c, const dfir_qrcan_params* gr, const float* x
     h = hh;
     wd = ww;
   }
-  const int wf = c.ng * c.per_group;
-  DFIR_TRY(wgrad_f(c, gr, w.dF32, F32(c.TRUNK_IN()), wf));
-  DFIR_TRY(dgrad(w.dF32, wf, nullptr, nullptr, w.G));
-  for (int g = c.ng - 1; g >= 0; --g) {
+  if (!ts.all()) DFIR_TRY(copy_f32(ts.gfeat_in, w.dF32, feat, c.st));
+  }
+  if (ts.stages & T_TRUNK_CONV) {
+    const int wf = c.ng * c.per_group;
+    DFIR_TRY(wgrad_f(c, gr, w.dF32, F32(c.TRUNK_IN()), wf));
+    DFIR_TRY(dgrad(w.dF32, wf, nullptr, nullptr, w.G));
+  }
+  const int g0 = (ts.stages & T_GROUPS) ? ts.g0 : 0, g1 = (ts.stages & T_GROUPS) ? ts.g1 : 0;
+  if ((ts.stages & T_GROUPS) && !ts.all()) DFIR_TRY(copy_f32(w.G, ts.gfeat_out, feat, c.st));
+  for (int g = g1 - 1; g >= g0; --g) {
     float* gsp = n->no_group_conv ? w.G : w.gs;
     if (!n->no_group_conv) {
       const int wg = g * c.per_group + 2 * c.nb;
@@ -519,8 +593,13 @@ int train_backward_f32(const Ctx& c, const dfir_qrcan_params* gr, const float* x
     }
     if (!n->no_group_conv) DFIR_TRY(add_f32(w.G, w.gs, w.G, nullptr, static_cast<long long>(B) * HW * C, c.st));
   }
-  DFIR_TRY(add_f32(w.dF32, w.G, w.G, nullptr, static_cast<long long>(B) * HW * C, c.st));
-  DFIR_TRY(wgrad_small(x, w.G, 0, w.small, B, H, W, C, n->in_feats, 0, gr->head_w, gr->head_b, c.st));
+  if ((ts.stages & T_GROUPS) && !ts.all()) DFIR_TRY(copy_f32(ts.gfeat_in, w.G, feat, c.st));
+  if (ts.stages & T_HEAD) {
+    if (ts.all()) DFIR_TRY(add_f32(w.dF32, w.G, w.G, nullptr, static_cast<long long>(B) * HW * C, c.st));
+    DFIR_TRY(wgrad_small(x, ts.all() ? w.G : ts.gfeat_out, 0, w.small, B, H, W, C, n->in_feats, 0, gr->head_w, gr->head_b,
+                         c.st));
+  }
+  if (!(ts.stages & T_ATTN)) return DFIR_OK;
   return attn_param_grads(w.sig, w.sig_stride, attr, n->attr_size, n->meta_w1, n->meta_b1, n->meta_w2, n->q_enabled,
                           c.has_ca ? gr->ca : nullptr, n->any_q ? gr->meta : nullptr, c.nblk, B, C,
                           std::max(1, n->reduced), n->num_metadata, n->meta_hidden, n->style, n->meta_relu, c.st);
@@ -620,7 +699,7 @@ int dfir_qrcan_repack(const dfir_qrcan_net* n, const dfir_qrcan_params* p, int p
 }
 
 size_t dfir_qrcan_train_workspace_bytes(const dfir_qrcan_net* net, int B, int H, int W, int precision) {
-  if (!train_supported(net, precision) || B <= 0 || H <= 0 || W <= 0) return 0;
+  if (!train_supported(net, precision, true) || B <= 0 || H <= 0 || W <= 0) return 0;
   return carve_train(net, B, H, W, precision, nullptr).total;
 }
 
@@ -647,7 +726,58 @@ int dfir_qrcan_train_forward(const dfir_qrcan_net* net, const float* x, const fl
   Ctx c;
   DFIR_TRY(make_ctx(c, net, B, H, W, precision, workspace, workspace_bytes, stream));
   DFIR_TRY(meta_scales(c, attributes));
-  return c.tc ? train_forward_tc(c, x, attributes, out) : train_forward_f32(c, x, attributes, out);
+  TrainStage ts;
+  ts.g1 = c.ng;
+  return c.tc ? train_forward_tc(c, x, attributes, out, ts) : train_forward_f32(c, x, attributes, out, ts);
+}
+
+int dfir_qrcan_train_stage_forward(const dfir_qrcan_net* net, int stage, int g_begin, int g_end, const float* x,
+                                   const float* attributes, const float* feat_in, float* feat_out, float* group_out,
+                                   float* out, int B, int H, int W, int precision, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  if (stage != T_HEAD && stage != T_GROUPS && stage != T_TAIL) return DFIR_ERR_ARG;
+  Ctx c;
+  DFIR_TRY(make_ctx(c, net, B, H, W, precision, workspace, workspace_bytes, stream, true));
+  TrainStage ts;
+  ts.stages = stage; ts.g0 = g_begin; ts.g1 = g_end; ts.feat_in = feat_in; ts.feat_out = feat_out; ts.group_out = group_out;
+  if (stage == T_HEAD) {
+    if (x == nullptr || feat_out == nullptr || attributes == nullptr) return DFIR_ERR_ARG;
+    DFIR_TRY(meta_scales(c, attributes));  // the scales of every block of the trunk, kept in the workspace
+  } else if (stage == T_GROUPS) {
+    if (feat_in == nullptr || attributes == nullptr || g_begin < 0 || g_end > c.ng || g_begin >= g_end) return DFIR_ERR_ARG;
+    if (net->no_group_conv && g_end != g_begin + 1) return DFIR_ERR_ARG;  // such groups chain through the caller
+  } else if (feat_in == nullptr || out == nullptr) {
+    return DFIR_ERR_ARG;
+  }
+  return c.tc ? train_forward_tc(c, x, attributes, out, ts) : train_forward_f32(c, x, attributes, out, ts);
+}
+
+int dfir_qrcan_train_stage_backward(const dfir_qrcan_net* net, const dfir_qrcan_params* grads, int stage, int g_begin,
+                                    int g_end, const float* x, const float* attributes, const float* grad_out,
+                                    const float* grad_feat_out, float* grad_feat_in, int B, int H, int W, int precision,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  if (grads == nullptr || (stage != T_HEAD && stage != T_GROUPS && stage != T_TAIL && stage != T_ATTN)) return DFIR_ERR_ARG;
+  Ctx c;
+  DFIR_TRY(make_ctx(c, net, B, H, W, precision, workspace, workspace_bytes, stream, true));
+  if (c.tc && (net->conv_wT_bf16 == nullptr || net->tail_wT_f32 == nullptr)) return DFIR_ERR_ARG;
+  if (!c.tc && (net->conv_wT_f32 == nullptr || net->up_wT_f32 == nullptr || net->tail_wT_f32 == nullptr)) return DFIR_ERR_ARG;
+  TrainStage ts;
+  ts.stages = stage; ts.g0 = g_begin; ts.g1 = g_end; ts.gfeat_out = grad_feat_out; ts.gfeat_in = grad_feat_in;
+  if (stage == T_HEAD) {
+    if (x == nullptr || grad_feat_out == nullptr) return DFIR_ERR_ARG;
+  } else if (stage == T_GROUPS) {
+    if (grad_feat_out == nullptr || grad_feat_in == nullptr || attributes == nullptr || g_begin < 0 || g_end > c.ng ||
+        g_begin >= g_end)
+      return DFIR_ERR_ARG;
+    if (net->no_group_conv && g_end != g_begin + 1) return DFIR_ERR_ARG;
+    if (cudaMemsetAsync(c.w.tickets, 0, static_cast<size_t>(B) * 4, c.st) != cudaSuccess) return DFIR_ERR_CUDA;
+  } else if (stage == T_TAIL) {
+    if (grad_out == nullptr || grad_feat_in == nullptr) return DFIR_ERR_ARG;
+  } else if (attributes == nullptr) {
+    return DFIR_ERR_ARG;
+  }
+  return c.tc ? train_backward_tc(c, grads, x, attributes, grad_out, ts)
+              : train_backward_f32(c, grads, x, attributes, grad_out, ts);
 }
 
 int dfir_qrcan_train_backward(const dfir_qrcan_net* net, const dfir_qrcan_params* grads, const float* x,
@@ -659,7 +789,10 @@ int dfir_qrcan_train_backward(const dfir_qrcan_net* net, const dfir_qrcan_params
   if (cudaMemsetAsync(c.w.tickets, 0, static_cast<size_t>(B) * 4, c.st) != cudaSuccess) return DFIR_ERR_CUDA;
   if (c.tc && (net->conv_wT_bf16 == nullptr || net->tail_wT_f32 == nullptr)) return DFIR_ERR_ARG;
   if (!c.tc && (net->conv_wT_f32 == nullptr || net->up_wT_f32 == nullptr || net->tail_wT_f32 == nullptr)) return DFIR_ERR_ARG;
-  return c.tc ? train_backward_tc(c, grads, x, attributes, grad_out) : train_backward_f32(c, grads, x, attributes, grad_out);
+  TrainStage ts;
+  ts.g1 = c.ng;
+  return c.tc ? train_backward_tc(c, grads, x, attributes, grad_out, ts)
+              : train_backward_f32(c, grads, x, attributes, grad_out, ts);
 }
 
 size_t dfir_conv3x3_wgrad_scratch_bytes(int B, int H, int W, int Cin, int Cout, int precision) {

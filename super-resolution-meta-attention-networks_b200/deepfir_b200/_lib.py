@@ -125,6 +125,21 @@ PROTOTYPES = {
     "dfir_conv3x3_wgrad_small_scratch_bytes": (_sz, [_i, _i, _i]),
     "dfir_conv3x3_wgrad_small": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "dfir_qrcan_forward": (_i, [C.POINTER(QrcanNet), _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "dfir_channel_dot_scratch_bytes": (_sz, [_i, _i]),
+    "dfir_channel_dot": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _sz, _i, _ll, _i, _vp]),
+    "dfir_soca_mlp": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
+    "dfir_soca_mlp_backward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "dfir_lam_backward_scratch_bytes": (_sz, [_i, _i]),
+    "dfir_lam_backward": (_i, [_vp, _ll, _vp, _f, _vp, _vp, _ll, _vp, _vp, _sz, _i, _i, _i, _i, _vp]),
+    "dfir_csam_backward_scratch_bytes": (_sz, [_i, _i, _i, _i]),
+    "dfir_csam_backward": (_i, [_vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _vp]),
+    "dfir_nonlocal_backward_scratch_bytes": (_sz, [_i, _i, _i]),
+    "dfir_nonlocal_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _i, _i, _i, _i, _vp]),
+    "dfir_pack_conv3x3_f32_ex": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "dfir_qrcan_train_stage_forward": (_i, [C.POINTER(QrcanNet), _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
+                                            _vp, _sz, _vp]),
+    "dfir_qrcan_train_stage_backward": (_i, [C.POINTER(QrcanNet), C.POINTER(QrcanParams), _i, _i, _i, _vp, _vp, _vp, _vp,
+                                             _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
 }
 
 

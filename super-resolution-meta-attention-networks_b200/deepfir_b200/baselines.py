@@ -210,7 +210,8 @@ class HAN(QHAN):
         trunk.append(self.body[ng])
         return dict(cfg=cfg, head=self.head[0], trunk=trunk,
                     ups=[m for m in self.tail[0] if isinstance(m, nn.Conv2d)], tail=self.tail[1],
-                    ca=[blk.flat_params() for blk in blocks], meta=[None for _ in blocks])
+                    ca=[blk.flat_params() for blk in blocks], ca_params=[blk.param_list() for blk in blocks],
+                    meta=[None for _ in blocks])
 
     def forward(self, x, metadata=None):
         if metadata is None:

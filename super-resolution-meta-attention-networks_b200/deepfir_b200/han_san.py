@@ -29,21 +29,51 @@ class _StagedNet(nn.Module):
     chunk_images = 1 << 20  # staged execution keeps its state in the workspace: always one pass
     _packed = None
 
-    def _param_versions(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
-
-    def packed(self):
-        key = (self._param_versions(), self.precision, self.schedule)
-        if self._packed is None or self._packed.key != key:
-            if self._packed is not None:
-                self._packed.close()
-            self._packed = PackedQrcan(self, key)
+    def packed(self, training=False):
+        """Kernel-format parameters of the conv trunk (see QRCAN.packed): rebuilt when a parameter's storage moved,
+        refreshed in place by `dfir_qrcan_repack` when only values changed (optimizer.step()); the cached kernel-format
+        copies of the layers outside the trunk (`_side`) are dropped with either."""
+        params = self.__dict__.get("_plist")
+        if params is None:
+            params = self.__dict__["_plist"] = list(self.parameters())
+        skey = (tuple(p.data_ptr() for p in params), self.precision, self.schedule)
+        vers = tuple(p._version for p in params)
+        pk = self._packed
+        if pk is None or pk.key != skey or (pk.versions != vers and not pk.can_repack):
+            if pk is not None:
+                pk.close()
+            pk = self._packed = PackedQrcan(self, skey)
+            pk.versions = vers
             self._side = {}
-        return self._packed
+        if training and not pk.train_ready:
+            pk.enable_training(self)
+            pk.versions = None
+        if training:
+            pk.versions = None          # the training forward re-packs the parameters itself
+        elif pk.versions != vers:
+            pk.repack()
+            pk.versions = vers
+            self._side = {}
+        return pk
 
     def _apply(self, fn, *a, **k):
         self._packed = None
+        self.__dict__.pop("_plist", None)
         return super()._apply(fn, *a, **k)
+
+    def unused_parameter_ids(self):
+        """parameters the reference constructs and serialises but never calls in forward: their .grad stays None"""
+        return set()
+
+    def _training_step(self, x):
+        return torch.is_grad_enabled() and self.head[0].weight.requires_grad
+
+    def _train_forward(self, x, metadata, kind):
+        from .train_staged import staged_train_apply
+        pk = self.packed(training=True)
+        B = x.shape[0]
+        attr = metadata.reshape(B, -1).to(device=x.device, dtype=torch.float32).contiguous()
+        return staged_train_apply(self, pk, x.to(torch.float32).contiguous(), attr, kind)
 
     def invalidate_packed(self):
         """rebuild the kernel-format parameters on the next forward (see QRCAN.invalidate_packed: needed after in-place
@@ -60,6 +90,7 @@ class _StagedNet(nn.Module):
     def load_state_dict(self, *a, **k):
         out = super().load_state_dict(*a, **k)
         self.invalidate_packed()
+        self.__dict__.pop("_plist", None)
         return out
 
     # -- staged trunk -------------------------------------------------------------------------------
@@ -206,10 +237,13 @@ class QHAN(_StagedNet):
         return dict(cfg=cfg, head=self.head[0], trunk=trunk,
                     ups=[m for m in self.tail[0] if isinstance(m, nn.Conv2d)], tail=self.tail[1],
                     ca=[blk.final_body.flat_params() for blk in blocks],
+                    ca_params=[blk.final_body.param_list() for blk in blocks],
                     meta=[tuple(blk.q_node.fcs()) if blk.q_layer else None for blk in blocks])
 
     def forward(self, x, metadata):
         self._check_input(x)
+        if self._training_step(x):  # forward with saved activations; backward fills every .grad (train_staged.py)
+            return self._train_forward(x, metadata, "han")
         lib = _lib.load_library()
         pk = self.packed()
         ng, Cf = self.cfg["n_resgroups"], self.cfg["n_feats"]
@@ -328,8 +362,13 @@ class QSAN(_StagedNet):
         blocks = [blk for grp in self.RG for blk in grp.rcab]
         return dict(cfg=self.cfg, head=self.head[0], trunk=trunk,
                     ups=[m for m in self.tail[0] if isinstance(m, nn.Conv2d)], tail=self.tail[1],
-                    ca=[None for _ in blocks],
+                    ca=[None for _ in blocks], ca_params=[None for _ in blocks],
                     meta=[tuple(blk.q_layer.fcs()) if hasattr(blk, "q_layer") else None for blk in blocks])
+
+    def unused_parameter_ids(self):
+        mods = [self.conv_last, self.non_local.soca]
+        ids = {id(p) for m in mods for p in m.parameters()}
+        return ids | {id(grp.gamma) for grp in self.RG}
 
     def _nonlocal(self, x):
         lib = _lib.load_library()
@@ -351,6 +390,8 @@ class QSAN(_StagedNet):
 
     def forward(self, x, metadata):
         self._check_input(x)
+        if self._training_step(x):  # forward with saved activations; backward fills every .grad (train_staged.py)
+            return self._train_forward(x, metadata, "san")
         lib = _lib.load_library()
         pk = self.packed()
         Cf = self.cfg["n_feats"]

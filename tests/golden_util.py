@@ -58,8 +58,8 @@ def load_big_grad_golden(name):
 
 
 # networks that have gradient fingerprints (the oracle's backward is pinned for them) but no training path in the B200
-# library yet: pixel attention, Q-SAN / SAN, Q-HAN / HAN.  Training them must raise NotImplementedError.
-NO_TRAINING_PATH = ("qrcan_pa_selective", "qsan_g2b2", "qhan_b1", "san_g2b2", "han_b1")
+# library yet: pixel attention.  Training them must raise NotImplementedError.
+NO_TRAINING_PATH = ("qrcan_pa_selective",)
 
 
 def trainable_grad_golden_names():

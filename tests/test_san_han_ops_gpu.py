@@ -173,3 +173,171 @@ def test_channel_spatial_attention(shape):
                        64, G.stream()) == 0
     G.sync()
     assert _rel(G.to_nchw(out), want) <= 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ backward operators
+def _relg(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 12), (1, 9, 7), (1, 26, 30), (2, 4, 5), (1, 32, 32)])
+def test_region_nonlocal_attention_backward(shape):
+    """dfir_nonlocal_backward against fp64 autograd through the oracle's Nonlocal_CA (input, theta/phi/g, W gradients),
+    odd regions included (pixels no pooling window covers get no phi / g gradient); a second call accumulates"""
+    B, H, W = shape
+    g = torch.Generator().manual_seed(H * 5 + W + 1)
+    x = torch.randn(B, 64, H, W, generator=g)
+    p = "n.non_local"
+    sd = {}
+    for name, (co, ci) in {"theta": (8, 64), "phi.0": (8, 64), "g.0": (8, 64), "W": (64, 8)}.items():
+        sd["%s.%s.weight" % (p, name)] = torch.randn(co, ci, 1, 1, generator=g) * 0.2
+        sd["%s.%s.bias" % (p, name)] = torch.randn(co, generator=g) * 0.1
+    leaves = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    xr = x.double().requires_grad_(True)
+    gout = torch.randn(B, 64, H, W, generator=g)
+    O.nonlocal_ca(xr, leaves, "n").backward(gout.double())
+    w_tpg = torch.cat([sd[p + ".theta.weight"].reshape(8, 64), sd[p + ".phi.0.weight"].reshape(8, 64),
+                       sd[p + ".g.0.weight"].reshape(8, 64)]).contiguous().cuda()
+    b_tpg = torch.cat([sd[p + ".theta.bias"], sd[p + ".phi.0.bias"], sd[p + ".g.0.bias"]]).contiguous().cuda()
+    w_out = sd[p + ".W.weight"].reshape(64, 8).contiguous().cuda()
+    want_w = torch.cat([leaves[p + ".theta.weight"].grad.reshape(8, 64), leaves[p + ".phi.0.weight"].grad.reshape(8, 64),
+                        leaves[p + ".g.0.weight"].grad.reshape(8, 64)])
+    want_b = torch.cat([leaves[p + ".theta.bias"].grad, leaves[p + ".phi.0.bias"].grad, leaves[p + ".g.0.bias"].grad])
+    L = G.lib()
+    xd, gd = G.nhwc_f32(x), G.nhwc_f32(gout)
+    nan = lambda *s: torch.full(s, float("nan"), device="cuda")
+    dx, gw, gb, gwo, gbo = nan(B, H, W, 64), nan(24, 64), nan(24), nan(64, 8), nan(64)
+    sc = _scratch(L.dfir_nonlocal_backward_scratch_bytes(B, H, W))
+    for rep in range(2):
+        assert L.dfir_nonlocal_backward(xd.data_ptr(), gd.data_ptr(), w_tpg.data_ptr(), b_tpg.data_ptr(), w_out.data_ptr(),
+                                        dx.data_ptr(), gw.data_ptr(), gb.data_ptr(), gwo.data_ptr(), gbo.data_ptr(), rep,
+                                        sc.data_ptr(), sc.numel(), B, H, W, 64, G.stream()) == 0
+        G.sync()
+        k = rep + 1
+        assert _relg(G.to_nchw(dx), xr.grad) <= 2e-5
+        assert _relg(gw.cpu(), k * want_w) <= 2e-5 and _relg(gb.cpu(), k * want_b) <= 2e-5
+        assert _relg(gwo.cpu(), k * leaves[p + ".W.weight"].grad.reshape(64, 8)) <= 2e-5
+        assert _relg(gbo.cpu(), k * leaves[p + ".W.bias"].grad) <= 2e-5
+
+
+@pytest.mark.parametrize("N,shape", [(11, (2, 8, 8)), (3, (1, 5, 9)), (1, (1, 4, 4)), (11, (1, 32, 32))])
+def test_layer_attention_backward(N, shape):
+    B, H, W = shape
+    g = torch.Generator().manual_seed(N + H + 3)
+    x5 = torch.randn(B, N, 64, H, W, generator=g) * 0.3
+    gamma = torch.tensor(0.37)
+    xr = x5.double().requires_grad_(True)
+    gr = gamma.double().requires_grad_(True)
+    gout = torch.randn(B, N * 64, H, W, generator=g)
+    O.lam(xr, gr).backward(gout.double())
+    stack = torch.stack([G.nhwc_f32(x5[:, n]) for n in range(N)])
+    rev = torch.flip(stack, dims=[0]).contiguous()
+    out = torch.empty(B, H, W, N * 64, device="cuda")
+    L = G.lib()
+    fsc = _scratch(L.dfir_lam_scratch_bytes(B, N))
+    per_map = B * H * W * 64
+    assert L.dfir_lam(rev[N - 1].data_ptr(), -per_map, float(gamma), out.data_ptr(), fsc.data_ptr(), N, B, H * W, 64,
+                      G.stream()) == 0
+    gd = G.nhwc_f32(gout)
+    drev = torch.full_like(rev, float("nan"))
+    dgamma = torch.full((1,), float("nan"), device="cuda")
+    sc = _scratch(L.dfir_lam_backward_scratch_bytes(B, N))
+    assert L.dfir_lam_backward(rev[N - 1].data_ptr(), -per_map, fsc.data_ptr(), float(gamma), gd.data_ptr(),
+                               drev[N - 1].data_ptr(), -per_map, dgamma.data_ptr(), sc.data_ptr(), sc.numel(), N, B, H * W, 64,
+                               G.stream()) == 0
+    G.sync()
+    got = torch.stack([G.to_nchw(drev[N - 1 - n]) for n in range(N)], dim=1)     # [B][N][64][H][W]
+    assert _relg(got, xr.grad) <= 5e-5
+    assert abs(float(dgamma.cpu()) - float(gr.grad)) <= 5e-5 * max(1.0, abs(float(gr.grad)))
+
+
+@pytest.mark.parametrize("shape", [(2, 6, 9), (1, 1, 1), (1, 17, 5)])
+def test_channel_spatial_attention_backward(shape):
+    B, H, W = shape
+    g = torch.Generator().manual_seed(H * 3 + W + 7)
+    x = torch.randn(B, 64, H, W, generator=g)
+    sd = {"c.conv.weight": torch.randn(1, 1, 3, 3, 3, generator=g) * 0.3, "c.conv.bias": torch.randn(1, generator=g) * 0.1,
+          "c.gamma": torch.tensor([0.6])}
+    leaves = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    xr = x.double().requires_grad_(True)
+    gout = torch.randn(B, 64, H, W, generator=g)
+    O.csam(xr, leaves, "c").backward(gout.double())
+    L = G.lib()
+    xd, gd = G.nhwc_f32(x), G.nhwc_f32(gout)
+    w27 = sd["c.conv.weight"].reshape(-1).contiguous().cuda()
+    nan = lambda *s: torch.full(s, float("nan"), device="cuda")
+    dx, dw, db, dg = nan(B, H, W, 64), nan(27), nan(1), nan(1)
+    sc = _scratch(L.dfir_csam_backward_scratch_bytes(B, H, W, 64))
+    assert L.dfir_csam_backward(xd.data_ptr(), gd.data_ptr(), w27.data_ptr(), float(sd["c.conv.bias"]), float(sd["c.gamma"]),
+                                dx.data_ptr(), dw.data_ptr(), db.data_ptr(), dg.data_ptr(), sc.data_ptr(), sc.numel(), B, H, W,
+                                64, G.stream()) == 0
+    G.sync()
+    assert _relg(G.to_nchw(dx), xr.grad) <= 2e-5
+    assert _relg(dw.cpu(), leaves["c.conv.weight"].grad.reshape(-1)) <= 2e-5
+    assert _relg(db.cpu(), leaves["c.conv.bias"].grad) <= 2e-5
+    assert _relg(dg.cpu(), leaves["c.gamma"].grad) <= 2e-5
+
+
+@pytest.mark.parametrize("B,R", [(3, 4), (1, 8)])
+def test_soca_mlp_forward_and_backward(B, R):
+    g = torch.Generator().manual_seed(B * 10 + R)
+    S = torch.randn(B, 64, 64, generator=g)
+    w1, b1 = torch.randn(R, 64, generator=g) * 0.3, torch.randn(R, generator=g) * 0.1
+    w2, b2 = torch.randn(64, R, generator=g) * 0.3, torch.randn(64, generator=g) * 0.1
+    leaves = [t.double().requires_grad_(True) for t in (S, w1, b1, w2, b2)]
+    v = leaves[0].mean(dim=1)
+    want = torch.sigmoid(torch.relu(v @ leaves[1].t() + leaves[2]) @ leaves[3].t() + leaves[4])
+    gs = torch.randn(B, 64, generator=g)
+    want.backward(gs.double())
+    L = G.lib()
+    mlp = torch.cat([t.reshape(-1) for t in (w1, b1, w2, b2)]).contiguous().cuda()
+    Sd, gsd = S.cuda(), gs.cuda()
+    sv = torch.full((B, 64), float("nan"), device="cuda")
+    assert L.dfir_soca_mlp(Sd.data_ptr(), mlp.data_ptr(), R, sv.data_ptr(), B, G.stream()) == 0
+    dS = torch.full((B, 64, 64), float("nan"), device="cuda")
+    dm = torch.full_like(mlp, float("nan"))
+    assert L.dfir_soca_mlp_backward(Sd.data_ptr(), gsd.data_ptr(), mlp.data_ptr(), R, dS.data_ptr(), dm.data_ptr(), B,
+                                    G.stream()) == 0
+    G.sync()
+    assert _rel(sv.cpu(), want.detach()) <= 1e-5
+    assert _relg(dS.cpu(), leaves[0].grad) <= 1e-5
+    assert _relg(dm.cpu(), torch.cat([t.grad.reshape(-1) for t in leaves[1:]])) <= 1e-5
+
+
+@pytest.mark.parametrize("B,HW,C", [(2, 37, 64), (1, 4096, 64), (3, 5, 128), (1, 9, 704)])
+def test_channel_dot(B, HW, C):
+    g = torch.Generator().manual_seed(HW + C)
+    a, b = torch.randn(B, HW, C, generator=g), torch.randn(B, HW, C, generator=g)
+    want = (a.double() * b.double()).sum(dim=1)
+    L = G.lib()
+    ad, bd = a.cuda(), b.cuda()
+    out = torch.full((B, C), float("nan"), device="cuda")
+    tot = torch.full((1,), 2.5, device="cuda")
+    sc = _scratch(L.dfir_channel_dot_scratch_bytes(B, C))
+    assert L.dfir_channel_dot(ad.data_ptr(), bd.data_ptr(), out.data_ptr(), tot.data_ptr(), 1, sc.data_ptr(), sc.numel(), B, HW,
+                              C, G.stream()) == 0
+    G.sync()
+    assert _relg(out.cpu(), want) <= 1e-5
+    assert abs(float(tot.cpu()) - 2.5 - float(want.sum())) <= 1e-4 * float(want.abs().sum())
+
+
+def test_conv_data_gradient_through_the_transposed_fp32_pack():
+    """dfir_pack_conv3x3_f32_ex(transpose=1) + dfir_conv3x3_f32 = data gradient of a 3x3 conv with Cin != Cout (the fusion
+    convs of Q-HAN: 704 -> 64 and 128 -> 64)"""
+    import torch.nn.functional as F
+    B, H, W, cin, cout = 1, 6, 7, 128, 64
+    g = torch.Generator().manual_seed(11)
+    w = torch.randn(cout, cin, 3, 3, generator=g) * 0.1
+    x = torch.randn(B, cin, H, W, generator=g).double().requires_grad_(True)
+    gout = torch.randn(B, cout, H, W, generator=g)
+    F.conv2d(x, w.double(), padding=1).backward(gout.double())
+    L = G.lib()
+    wT = torch.empty(9 * cin * cout, device="cuda")
+    wd = w.contiguous().cuda()
+    assert L.dfir_pack_conv3x3_f32_ex(wd.data_ptr(), wT.data_ptr(), cout, cin, 1, G.stream()) == 0
+    gd = G.nhwc_f32(gout)
+    dx = torch.full((B, H, W, cin), float("nan"), device="cuda")
+    assert L.dfir_conv3x3_f32(gd.data_ptr(), wT.data_ptr(), None, None, dx.data_ptr(), B, H, W, cout, cin, 0, 1, 0,
+                              G.stream()) == 0
+    G.sync()
+    assert _relg(G.to_nchw(dx), x.grad) <= 1e-5

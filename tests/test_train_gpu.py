@@ -154,9 +154,11 @@ def test_wgrad_small_head_and_tail(tail_mode, feat_bf16):
 
 # ------------------------------------------------------------------------------------------------ whole step
 def _build(info, precision):
-    from deepfir_b200.baselines import EDSR, RCAN
+    from deepfir_b200.baselines import EDSR, HAN, RCAN, SAN
+    from deepfir_b200.han_san import QHAN, QSAN
     from deepfir_b200.qrcan import QEDSR, QRCAN
-    cls = {"qedsr": QEDSR, "qrcan": QRCAN, "rcan": RCAN, "edsr": EDSR}[info["model"]]
+    cls = {"qedsr": QEDSR, "qrcan": QRCAN, "rcan": RCAN, "edsr": EDSR, "qsan": QSAN, "qhan": QHAN, "san": SAN,
+           "han": HAN}[info["model"]]
     net = cls(precision=precision, **info["kwargs"])
     sd, x, meta = case_tensors(info)
     net.load_state_dict(sd, strict=True)
@@ -168,7 +170,10 @@ def _step_grads(net, x, meta, y):
     out = net(x.cuda(), meta.cuda())
     loss = F.l1_loss(out, y.cuda())
     loss.backward()
-    return float(loss.detach()), out.detach().cpu(), {k: p.grad.detach().cpu().clone() for k, p in net.named_parameters()}
+    # (parameters a network owns but never calls -- Q-SAN's `conv_last`, `RG.*.gamma`, `non_local.soca` -- keep .grad None,
+    # as under the reference's autograd)
+    return float(loss.detach()), out.detach().cpu(), {k: p.grad.detach().cpu().clone() for k, p in net.named_parameters()
+                                                      if p.grad is not None}
 
 
 @pytest.mark.parametrize("name", trainable_grad_golden_names())
