@@ -327,6 +327,8 @@ typedef struct dfir_qrcan_params {
   float* head_w; float* head_b; /* [C][in_feats][3][3], [C] */
   float* const* ca;      /* [n_groups*n_blocks*8] or NULL (style none) */
   float* const* meta;    /* [n_groups*n_blocks*4] or NULL (no q layers) */
+  float* const* pa;      /* [n_groups*n_blocks*4] PALayer.pa {conv 0 weight [8][C], bias [8], conv 2 weight [8], bias [1]}
+                            (architectures.py:13-26), or NULL (no pixel attention) */
 } dfir_qrcan_params;
 
 /* Rebuilds every kernel-format buffer of `net` (the pointers inside dfir_qrcan_net, written although declared const)

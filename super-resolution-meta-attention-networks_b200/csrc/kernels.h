@@ -219,6 +219,14 @@ int bwd_reduce_ca(const float* g, const void* r, int r_is_bf16, float* part, uns
                   int sig_stride, int B, cudaStream_t s);
 int form_dr(const float* g, const float* svec, const float* dyv, void* dr, int dr_is_bf16, int B, int HW, int C,
             cudaStream_t s);
+// pixel attention backward: du = gradient entering the channel-attention backward, part = per-CTA partial sums
+int pa_backward_ctas(int B, int HW);
+size_t pa_backward_part_floats(int B, int HW);
+int pa_backward(const float* g, const void* r, int r_is_bf16, const float* ymean, const AttnParams& ap,
+                const float* attributes, const float* sq, const float* pa, float* du, float* part, int B, int HW,
+                cudaStream_t s);
+int pa_finish(const float* part, const float* sq, float out_scale, float* sig, int sig_stride, int dzq_off,
+              float* const* gpa, int B, int HW, cudaStream_t s);
 int add_f32(const float* a, const float* b, float* out, void* out_bf16, long long n, cudaStream_t s);
 int pixel_unshuffle_f32(const float* in, float* out, int B, int h, int w, int C, int r, cudaStream_t s);
 int adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,

@@ -63,6 +63,7 @@ struct TrainWs {
   float* wpart; size_t wpart_floats; // weight-gradient partial sums
   float *red, *svec, *dyv, *sig; int sig_stride;
   float* ymean; unsigned int* tickets;   // [nblk][B][C] pooled means saved by the forward; per-image tickets
+  float *PAdu, *papart;                  // pixel attention backward: gradient after the PALayer, per-CTA partial sums
   uint8_t* DUop[2]; float* DU32; float* DYF;
   float* small;
   size_t total;
@@ -87,7 +88,7 @@ bool train_supported(const dfir_qrcan_net* n, int precision, bool staged = false
   int r = 0;
   if (n == nullptr || up_stages(n->scale, &r) < 0) return false;
   if (n->n_groups < 1 || n->n_blocks < 1) return false;
-  if (n->pa_blob != nullptr) return false;  // pixel attention has no backward kernels yet
+  if (n->pa_blob != nullptr && (n->n_feats != 64 || n->style == DFIR_STYLE_NONE)) return false;
   if (n->no_group_conv && n->n_groups != 1 && !staged) return false;
   if (n->style < DFIR_STYLE_NONE || n->style > DFIR_STYLE_EXTENDED) return false;
   if (precision == DFIR_PREC_BF16_TC) return n->n_feats == 64;
@@ -154,6 +155,10 @@ TrainWs carve_train(const dfir_qrcan_net* n, int B, int H, int W, int precision,
   w.sig = c.take<float>(static_cast<size_t>(nblk) * B * w.sig_stride * 4);
   w.ymean = c.take<float>(static_cast<size_t>(nblk) * B * C * 4);
   w.tickets = c.take<unsigned int>(static_cast<size_t>(B) * 4);
+  if (n->pa_blob != nullptr) {
+    w.PAdu = c.take<float>(feat * 4);
+    w.papart = c.take<float>(pa_backward_part_floats(B, H * W) * 4);
+  }
   w.DUop[0] = c.take<uint8_t>(top * elt);
   w.DUop[1] = c.take<uint8_t>(top / (static_cast<size_t>(r) * r) * elt);
   if (tc) w.DU32 = c.take<float>(top / (static_cast<size_t>(r) * r) * 4);
@@ -177,7 +182,7 @@ AttnParams make_ap(const dfir_qrcan_net* n, int blk) {
 struct Ctx {
   const dfir_qrcan_net* n;
   TrainWs w;
-  int B, H, W, C, nb, ng, nblk, per_group, n_trunk, nup, r, nseg, sms;
+  int B, H, W, C, nb, ng, nblk, per_group, n_trunk, nup, r, nseg, sms, dzq_off;
   bool tc, has_ca;
   cudaStream_t st;
   uint8_t* slot(int i) const { return w.act + static_cast<size_t>(i) * w.slot_bytes; }
@@ -191,6 +196,7 @@ struct Ctx {
   const float* sq(int k) const { return n->any_q ? w.sq + static_cast<size_t>(k) * B * C : nullptr; }
   float* sig(int k) const { return w.sig + static_cast<size_t>(k) * B * w.sig_stride; }
   float* ymean(int k) const { return w.ymean + static_cast<size_t>(k) * B * C; }
+  const float* pa(int k) const { return n->pa_blob != nullptr ? n->pa_blob + static_cast<size_t>(k) * n->pa_stride : nullptr; }
 };
 
 int make_ctx(Ctx& c, const dfir_qrcan_net* n, int B, int H, int W, int precision, void* ws, size_t ws_bytes, void* stream,
@@ -207,6 +213,7 @@ int make_ctx(Ctx& c, const dfir_qrcan_net* n, int B, int H, int W, int precision
   c.nseg = (W + 127) / 128;
   c.tc = precision == DFIR_PREC_BF16_TC;
   c.has_ca = n->style != DFIR_STYLE_NONE;
+  c.dzq_off = make_attn_chain(n->style, n->n_feats, std::max(1, n->reduced), n->num_metadata).dzq_off;
   c.st = S(stream);
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess ||
@@ -263,7 +270,7 @@ int train_forward_tc(const Ctx& c, const float* x, const float* attr, float* out
     else
       DFIR_TRY(head_conv(x, n->head_w_f32, n->head_b, ts.feat_out, nullptr, c.B, n->in_feats, H, W, C, c.st));
   }
-  const bool linear = train_linear_schedule(c.B, H, W, c.sms);
+  const bool linear = train_linear_schedule(c.B, H, W, c.sms) && n->pa_blob == nullptr;  // (PALayer lives in the streamer)
   const float* first_skip = w.Hh;
   const int g0 = (ts.stages & T_GROUPS) ? ts.g0 : 0, g1 = (ts.stages & T_GROUPS) ? ts.g1 : 0;
   if ((ts.stages & T_GROUPS) && !ts.all()) {
@@ -287,7 +294,7 @@ int train_forward_tc(const Ctx& c, const float* x, const float* attr, float* out
         c2.in_bf16 = c.T(k); c2.out_bf16 = c.R(k); c2.pool_rows = w.pool;
         DFIR_TRY(conv3x3_c64_tc(c2, c.st));
         DFIR_TRY(scale_residual(c.R(k), 1, b == 0 ? skip32 : w.XB, w.pool, c.nseg * H, make_ap(n, k), attr, c.sq(k), 1.f,
-                                w.XB, reinterpret_cast<__nv_bfloat16*>(next_bf), c.B, H, W, C, c.st, c.ymean(k)));
+                                w.XB, reinterpret_cast<__nv_bfloat16*>(next_bf), c.B, H, W, C, c.st, c.ymean(k), c.pa(k)));
         continue;
       }
       // pool-by-linearity, as in inference: conv1 emits the statistics of t, conv2's prologue turns
@@ -381,7 +388,7 @@ int train_forward_f32(const Ctx& c, const float* x, const float* attr, float* ou
       if (c.has_ca) DFIR_TRY(pool_rows_f32(F32(c.R(k)), c.pool(k), B, H, W, C, c.st));
       float* next = (b + 1 < c.nb) ? F32(c.XIN(k + 1)) : F32(c.XLAST(g));
       DFIR_TRY(scale_residual(c.R(k), 0, F32(c.XIN(k)), c.pool(k), H, make_ap(n, k), attr, c.sq(k), 1.f, next, nullptr, B,
-                              H, W, C, c.st, c.ymean(k)));
+                              H, W, C, c.st, c.ymean(k), c.pa(k)));
     }
     const float* gres = F32(c.XLAST(g));
     if (!n->no_group_conv) {
@@ -498,9 +505,17 @@ int train_backward_tc(const Ctx& c, const dfir_qrcan_params* gr, const float* x,
     for (int b = c.nb - 1; b >= 0; --b) {
       const int k = g * c.nb + b;
       const int w1 = g * c.per_group + 2 * b, w2 = w1 + 1;
-      DFIR_TRY(bwd_reduce_ca(gsp, c.R(k), 1, w.red, w.tickets, c.pool(k), c.nseg * H, c.has_ca ? c.ymean(k) : nullptr, HW,
-                             make_ap(n, k), attr, c.sq(k), out_scale, w.svec, w.dyv, c.sig(k), w.sig_stride, B, c.st));
-      DFIR_TRY(form_dr(gsp, w.svec, c.has_ca ? w.dyv : nullptr, w.DR, 1, B, HW, C, c.st));
+      const float* gblk = gsp;  // gradient entering the block's scale (after the pixel attention backward, if any)
+      if (c.pa(k) != nullptr) {
+        DFIR_TRY(pa_backward(gsp, c.R(k), 1, c.ymean(k), make_ap(n, k), attr, c.sq(k), c.pa(k), w.PAdu, w.papart, B, HW, c.st));
+        gblk = w.PAdu;
+      }
+      DFIR_TRY(bwd_reduce_ca(gblk, c.R(k), 1, w.red, w.tickets, c.pool(k), c.nseg * H, c.has_ca ? c.ymean(k) : nullptr, HW,
+                             make_ap(n, k), attr, c.pa(k) != nullptr ? nullptr : c.sq(k), out_scale, w.svec, w.dyv, c.sig(k),
+                             w.sig_stride, B, c.st));
+      if (c.pa(k) != nullptr)
+        DFIR_TRY(pa_finish(w.papart, c.sq(k), out_scale, c.sig(k), w.sig_stride, c.dzq_off, gr->pa + 4 * k, B, HW, c.st));
+      DFIR_TRY(form_dr(gblk, w.svec, c.has_ca ? w.dyv : nullptr, w.DR, 1, B, HW, C, c.st));
       DFIR_TRY(wgrad_tc(c, gr, w.DR, c.T(k), w2));
       {
         ConvTcDesc d = tc_desc(c, tc_wT(c, w2), nullptr, EPI_RELU_MASK, H, W);
@@ -583,9 +598,17 @@ int train_backward_f32(const Ctx& c, const dfir_qrcan_params* gr, const float* x
     for (int b = c.nb - 1; b >= 0; --b) {
       const int k = g * c.nb + b;
       const int w1 = g * c.per_group + 2 * b, w2 = w1 + 1;
-      DFIR_TRY(bwd_reduce_ca(gsp, c.R(k), 0, w.red, w.tickets, c.pool(k), H, c.has_ca ? c.ymean(k) : nullptr, HW,
-                             make_ap(n, k), attr, c.sq(k), out_scale, w.svec, w.dyv, c.sig(k), w.sig_stride, B, c.st));
-      DFIR_TRY(form_dr(gsp, w.svec, c.has_ca ? w.dyv : nullptr, w.DR, 0, B, HW, C, c.st));
+      const float* gblk = gsp;
+      if (c.pa(k) != nullptr) {
+        DFIR_TRY(pa_backward(gsp, c.R(k), 0, c.ymean(k), make_ap(n, k), attr, c.sq(k), c.pa(k), w.PAdu, w.papart, B, HW, c.st));
+        gblk = w.PAdu;
+      }
+      DFIR_TRY(bwd_reduce_ca(gblk, c.R(k), 0, w.red, w.tickets, c.pool(k), H, c.has_ca ? c.ymean(k) : nullptr, HW,
+                             make_ap(n, k), attr, c.pa(k) != nullptr ? nullptr : c.sq(k), out_scale, w.svec, w.dyv, c.sig(k),
+                             w.sig_stride, B, c.st));
+      if (c.pa(k) != nullptr)
+        DFIR_TRY(pa_finish(w.papart, c.sq(k), out_scale, c.sig(k), w.sig_stride, c.dzq_off, gr->pa + 4 * k, B, HW, c.st));
+      DFIR_TRY(form_dr(gblk, w.svec, c.has_ca ? w.dyv : nullptr, w.DR, 0, B, HW, C, c.st));
       DFIR_TRY(wgrad_f(c, gr, F32(w.DR), F32(c.T(k)), w2));
       DFIR_TRY(dgrad(F32(w.DR), w2, nullptr, F32(c.T(k)), F32(w.DZ)));
       DFIR_TRY(wgrad_f(c, gr, F32(w.DZ), F32(c.XIN(k)), w1));
@@ -687,6 +710,14 @@ int dfir_qrcan_repack(const dfir_qrcan_net* n, const dfir_qrcan_params* p, int p
       DFIR_TRY(gather_strided(ca, nullptr, 8, 2 * l + 1, blob + ch.boff[l], nblk, ch.nout[l], 1, 1, n->ca_stride, st));
     }
   }
+  if (n->pa_blob != nullptr) {  // PALayer rows: W1[8][64] b1[8] W2[8] b2
+    if (p->pa == nullptr || n->pa_stride < 529) return DFIR_ERR_ARG;
+    const float* const* pt = const_cast<const float* const*>(p->pa);
+    float* blob = const_cast<float*>(n->pa_blob);
+    const int sizes[4] = {512, 8, 8, 1}, offs[4] = {0, 512, 520, 528};
+    for (int i = 0; i < 4; ++i)
+      DFIR_TRY(gather_strided(pt, nullptr, 4, i, blob + offs[i], nblk, sizes[i], 1, 1, n->pa_stride, st));
+  }
   if (n->any_q && p->meta != nullptr) {  // (no table: every block is scaled by the constant out_scale, e.g. EDSR)
     const float* const* mt = const_cast<const float* const*>(p->meta);
     const int hid = n->meta_hidden, M = n->num_metadata;
@@ -711,12 +742,14 @@ long long dfir_qrcan_train_launch_count(const dfir_qrcan_net* n, int B, int H, i
   const long long ngc = n->no_group_conv ? 0 : n->n_groups;
   const long long ca = n->style != DFIR_STYLE_NONE ? 1 : 0;
   if (precision == DFIR_PREC_BF16_TC) {
-    const long long fwd = 1 + (n->any_q ? 1 : 0) + nblk * (train_linear_schedule(B, H, W, 148) ? 2 : 3) + ngc + 1 + nup * r * r + 1;
-    const long long bwd = 3 + nup * r * r * 3 + 3 + ngc * 4 + nblk * 8 + 1 + 2 + 1;
+    const long long pa = n->pa_blob != nullptr ? 1 : 0;
+    const long long fwd = 1 + (n->any_q ? 1 : 0) + nblk * ((train_linear_schedule(B, H, W, 148) && !pa) ? 2 : 3) + ngc + 1 + nup * r * r + 1;
+    const long long bwd = 3 + nup * r * r * 3 + 3 + ngc * 4 + nblk * (8 + 2 * pa) + 1 + 2 + 1;
     return fwd + bwd;
   }
+  const long long pa = n->pa_blob != nullptr ? 1 : 0;
   const long long fwd = 1 + (n->any_q ? 1 : 0) + nblk * (3 + ca) + ngc + 1 + nup + 1;
-  const long long bwd = 3 + nup * 4 + 3 + ngc * 4 + nblk * 8 + 1 + 2 + 1;
+  const long long bwd = 3 + nup * 4 + 3 + ngc * 4 + nblk * (8 + 2 * pa) + 1 + 2 + 1;
   return fwd + bwd;
 }
 
@@ -784,6 +817,7 @@ int dfir_qrcan_train_backward(const dfir_qrcan_net* net, const dfir_qrcan_params
                               const float* attributes, const float* grad_out, int B, int H, int W, int precision,
                               void* workspace, size_t workspace_bytes, void* stream) {
   if (grads == nullptr || x == nullptr || attributes == nullptr || grad_out == nullptr) return DFIR_ERR_ARG;
+  if (net != nullptr && net->pa_blob != nullptr && grads->pa == nullptr) return DFIR_ERR_ARG;
   Ctx c;
   DFIR_TRY(make_ctx(c, net, B, H, W, precision, workspace, workspace_bytes, stream));
   if (cudaMemsetAsync(c.w.tickets, 0, static_cast<size_t>(B) * 4, c.st) != cudaSuccess) return DFIR_ERR_CUDA;

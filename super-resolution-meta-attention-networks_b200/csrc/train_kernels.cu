@@ -349,6 +349,165 @@ form_dr_kernel(const float* __restrict__ g, const float* __restrict__ svec, cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pixel attention backward (PALayer, attention_manipulators/architectures.py:13-26, inside QRCAB.forward :172-180):
+//   u = r * s_ca,  pm = sigmoid(w2 . relu(W1 u + b1) + b2),  v = u * pm,  x' = v * sq + x        (C = 64, hidden 8)
+// given g = dL/dx':  dv = g * sq;  A = sum_c dv_c u_c;  dz = A pm (1 - pm);  dh_j = dz w2_j [h_j > 0];
+//   du_c = dv_c pm + sum_j W1[j][c] dh_j      -> written out: it is the `g` of the channel-attention backward that follows
+//   dsq_c = sum_p g_c v_c;  dW1[j][c] = sum dh_j u_c;  db1 = sum dh;  dw2_j = sum dz relu(h_j);  db2 = sum dz
+// Each CTA writes one record of partial sums { dW1[8][64], db1[8], dw2[8], db2, dsq[64] }; pa_finish_kernel combines them in
+// a fixed order.  The 8 threads of a pixel hold 8 channels each (butterfly over the lanes, as in the forward streamer).
+// ------------------------------------------------------------------------------------------------
+constexpr int kPaParams = 8 * 64 + 8 + 8 + 1;
+constexpr int kPaRec = kPaParams + 64;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+pa_backward_kernel(const float* __restrict__ g, const T* __restrict__ r, const float* __restrict__ ymean, AttnParams ap,
+                   const float* __restrict__ attributes, const float* __restrict__ sq, const float* __restrict__ pa,
+                   float* __restrict__ du, float* __restrict__ part, int HW) {
+  constexpr int C = 64;
+  __shared__ float y_s[256], s_s[256], attr_s[512], tmp[4 * 256];
+  __shared__ float pa_s[kPaParams + 3];
+  __shared__ float red[32 * 64];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < kPaParams; i += 256) pa_s[i] = pa[i];
+  for (int i = tid; i < ap.A; i += 256) attr_s[i] = attributes[static_cast<size_t>(b) * ap.A + i];
+  if (tid < C) y_s[tid] = ymean[static_cast<size_t>(b) * C + tid];
+  __syncthreads();
+  attn_vector(BlockGroup{}, ap.style, ap.w[0], C, ap.R, ap.M, attr_s, y_s, s_s, tmp);
+  __syncthreads();
+  const int lane8 = tid & 7, pg = tid >> 3;
+  const int c0 = lane8 * 8;
+  float sc[8], sqv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sc[i] = s_s[c0 + i];
+    sqv[i] = sq != nullptr ? sq[static_cast<size_t>(b) * C + c0 + i] : 1.f;
+  }
+  float aW1[8][8], ab1[8], aw2[8], ab2 = 0.f, adsq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ab1[j] = 0.f; aw2[j] = 0.f; adsq[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) aW1[j][i] = 0.f;
+  }
+  const size_t img_off = static_cast<size_t>(b) * HW * C;
+  const long long nvec = static_cast<long long>(HW) * 8;
+  for (long long base = static_cast<long long>(blockIdx.x) * 256; base < nvec; base += static_cast<long long>(gridDim.x) * 256) {
+    const long long vi = base + tid;
+    const bool active = vi < nvec;
+    const size_t e = img_off + static_cast<size_t>(active ? vi : 0) * 8;
+    float u[8], gv[8];
+    load8<T>(r + e, u);
+    load8<float>(g + e, gv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      u[i] *= sc[i];
+      if (!active) gv[i] = 0.f;
+    }
+    float h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t = fmaf(pa_s[j * 64 + c0 + i], u[i], t);
+      h[j] = t;
+    }
+#pragma unroll
+    for (int mask = 1; mask < 8; mask <<= 1)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] += __shfl_xor_sync(0xffffffffu, h[j], mask);
+    float z = pa_s[8 * 64 + 16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      h[j] += pa_s[8 * 64 + j];
+      z = fmaf(pa_s[8 * 64 + 8 + j], fmaxf(h[j], 0.f), z);
+    }
+    const float pm = 1.f / (1.f + expf(-z));
+    float A = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) A = fmaf(gv[i] * sqv[i], u[i], A);
+#pragma unroll
+    for (int mask = 1; mask < 8; mask <<= 1) A += __shfl_xor_sync(0xffffffffu, A, mask);
+    const float dz = A * pm * (1.f - pm);
+    float dh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dh[j] = h[j] > 0.f ? dz * pa_s[8 * 64 + 8 + j] : 0.f;
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float t = gv[i] * sqv[i] * pm;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t = fmaf(pa_s[j * 64 + c0 + i], dh[j], t);
+      o[i] = t;
+      adsq[i] = fmaf(gv[i] * u[i], pm, adsq[i]);
+    }
+    if (active) store8<float>(du + e, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) aW1[j][i] = fmaf(dh[j], u[i], aW1[j][i]);
+      if (lane8 == 0) {
+        ab1[j] += dh[j];
+        aw2[j] = fmaf(dz, fmaxf(h[j], 0.f), aw2[j]);
+      }
+    }
+    if (lane8 == 0) ab2 += dz;
+  }
+  // ---- CTA reduction over the 32 pixel groups, fixed order
+  float* rec = part + (static_cast<size_t>(b) * gridDim.x + blockIdx.x) * kPaRec;
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[pg * 64 + c0 + i] = j < 8 ? aW1[j < 8 ? j : 0][i] : adsq[i];
+    __syncthreads();
+    if (tid < 64) {
+      float t = 0.f;
+      for (int k = 0; k < 32; ++k) t += red[k * 64 + tid];
+      rec[j < 8 ? j * 64 + tid : kPaParams + tid] = t;
+    }
+  }
+  __syncthreads();
+  if (lane8 == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[pg * 17 + j] = ab1[j];
+      red[pg * 17 + 8 + j] = aw2[j];
+    }
+    red[pg * 17 + 16] = ab2;
+  }
+  __syncthreads();
+  if (tid < 17) {
+    float t = 0.f;
+    for (int k = 0; k < 32; ++k) t += red[k * 17 + tid];
+    rec[8 * 64 + tid] = t;
+  }
+}
+
+// parameter gradients (summed over images and CTAs in index order) and the meta-attention signal dzq of the block's record
+__global__ void __launch_bounds__(128)
+pa_finish_kernel(const float* __restrict__ part, int ncta, int B, const float* __restrict__ sq, float out_scale,
+                 float* __restrict__ sig, int sig_stride, int dzq_off, float* const* __restrict__ gpa) {
+  const int idx = blockIdx.x * 128 + threadIdx.x;
+  if (idx < kPaParams) {
+    float t = 0.f;
+    for (int k = 0; k < B * ncta; ++k) t += part[static_cast<size_t>(k) * kPaRec + idx];
+    float* dst = idx < 512 ? gpa[0] + idx : (idx < 520 ? gpa[1] + (idx - 512) : (idx < 528 ? gpa[2] + (idx - 520) : gpa[3]));
+    if (dst != nullptr) *dst = t;
+  } else if (idx < kPaParams + 64) {
+    const int c = idx - kPaParams;
+    for (int b = 0; b < B; ++b) {
+      float t = 0.f;
+      for (int k = 0; k < ncta; ++k) t += part[(static_cast<size_t>(b) * ncta + k) * kPaRec + idx];
+      const float sqv = sq != nullptr ? sq[static_cast<size_t>(b) * 64 + c] : out_scale;
+      const float sgq = sqv / out_scale;
+      sig[static_cast<size_t>(b) * sig_stride + dzq_off + c] = sq != nullptr ? t * out_scale * sgq * (1.f - sgq) : 0.f;
+    }
+  }
+}
+
 // out32 = a + b (either may alias out32), optional bf16 copy
 __global__ void add_f32_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out,
                                uint2* __restrict__ out_bf16, long long n4) {
@@ -762,6 +921,35 @@ int bwd_reduce_ca(const float* g, const void* r, int r_is_bf16, float* part, uns
                       part, HW, C, nchunk, a, tickets) == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
   return launch_pdl(PDL_SIMT, bwd_reduce_ca_kernel<float>, grid, dim3(256), 0, s, g, reinterpret_cast<const float*>(r), part, HW, C,
                     nchunk, a, tickets) == cudaSuccess ? DFIR_OK : DFIR_ERR_CUDA;
+}
+
+int pa_backward_ctas(int B, int HW) {
+  const long long nvec = static_cast<long long>(HW) * 8;
+  return static_cast<int>(std::max<long long>(1, std::min<long long>((nvec + 2047) / 2048, (592 + B - 1) / B)));
+}
+size_t pa_backward_part_floats(int B, int HW) { return static_cast<size_t>(B) * pa_backward_ctas(B, HW) * kPaRec; }
+
+int pa_backward(const float* g, const void* r, int r_is_bf16, const float* ymean, const AttnParams& ap,
+                const float* attributes, const float* sq, const float* pa, float* du, float* part, int B, int HW,
+                cudaStream_t s) {
+  if (ap.C != 64 || ap.style == DFIR_STYLE_NONE || ap.A > 512 || ymean == nullptr || pa == nullptr) return DFIR_ERR_ARG;
+  if (B <= 0 || HW <= 0) return DFIR_OK;
+  dim3 grid(pa_backward_ctas(B, HW), B);
+  if (r_is_bf16)
+    pa_backward_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(g, reinterpret_cast<const __nv_bfloat16*>(r), ymean, ap, attributes,
+                                                          sq, pa, du, part, HW);
+  else
+    pa_backward_kernel<float><<<grid, 256, 0, s>>>(g, reinterpret_cast<const float*>(r), ymean, ap, attributes, sq, pa, du,
+                                                  part, HW);
+  return ok_or_cuda3();
+}
+
+int pa_finish(const float* part, const float* sq, float out_scale, float* sig, int sig_stride, int dzq_off,
+              float* const* gpa, int B, int HW, cudaStream_t s) {
+  if (B <= 0 || HW <= 0) return DFIR_OK;
+  pa_finish_kernel<<<(kPaRec + 127) / 128, 128, 0, s>>>(part, pa_backward_ctas(B, HW), B, sq, out_scale, sig, sig_stride,
+                                                       dzq_off, gpa);
+  return ok_or_cuda3();
 }
 
 int form_dr(const float* g, const float* svec, const float* dyv, void* dr, int dr_is_bf16, int B, int HW, int C,

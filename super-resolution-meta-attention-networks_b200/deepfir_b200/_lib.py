@@ -54,7 +54,7 @@ class QrcanParams(C.Structure):
     _fields_ = [
         ("conv_w", C.c_void_p), ("conv_b", C.c_void_p), ("up_w", C.c_void_p), ("up_b", C.c_void_p),
         ("tail_w", C.c_void_p), ("tail_b", C.c_void_p), ("head_w", C.c_void_p), ("head_b", C.c_void_p),
-        ("ca", C.c_void_p), ("meta", C.c_void_p),
+        ("ca", C.c_void_p), ("meta", C.c_void_p), ("pa", C.c_void_p),
     ]
 
 

@@ -521,7 +521,7 @@ class PackedQrcan:
         self.ws_owner = None
         # device pointer tables of the fp32 parameters: lets the C side refresh every kernel-format buffer in a few
         # launches (styles whose attention block has the 4-tensor layout; the others are rebuilt from Python)
-        self.can_repack = "ca_params" in spec and pa_blob is None
+        self.can_repack = "ca_params" in spec
         if self.can_repack:
             self._spec_params = dict(
                 conv_w=[m.weight for m in trunk], conv_b=[m.bias for m in trunk],
@@ -530,7 +530,9 @@ class PackedQrcan:
                 ca=(None if ca_stride == 0 else
                     [p for blk in spec["ca_params"] for p in (list(blk) + [None] * (8 - len(blk)))]),
                 meta=(None if not any(q_flags) else
-                      [t for m in metas for t in ((None,) * 4 if m is None else (m[0].weight, m[0].bias, m[1].weight, m[1].bias))]))
+                      [t for m in metas for t in ((None,) * 4 if m is None else (m[0].weight, m[0].bias, m[1].weight, m[1].bias))]),
+                pa=(None if pa_blob is None else
+                    [t for f1, f2 in pas for t in (f1.weight, f1.bias, f2.weight, f2.bias)]))
             self.param_tables, self.params_struct = self._make_tables(lambda p: p.data_ptr())
         self.handle = _NEXT[0]
         _NEXT[0] += 1
@@ -550,7 +552,7 @@ class PackedQrcan:
             return t
 
         ps = _lib.QrcanParams()
-        for name in ("conv_w", "conv_b", "up_w", "up_b", "ca", "meta"):
+        for name in ("conv_w", "conv_b", "up_w", "up_b", "ca", "meta", "pa"):
             keep[name] = table(sp[name])
             setattr(ps, name, None if keep[name] is None else keep[name].data_ptr())
         for name in ("tail_w", "tail_b", "head_w", "head_b"):
@@ -568,8 +570,7 @@ class PackedQrcan:
         """Buffers that only a training step needs: data-gradient weight layouts, one flat gradient buffer with a
         view per parameter, and the gradient pointer tables."""
         if not self.can_repack:
-            raise NotImplementedError("this network has no training path on the B200 library (pixel attention, Q-SAN, "
-                                      "Q-HAN)")
+            raise NotImplementedError("this network has no training path on the B200 library")
         d = self.desc
         dev = self.device
         C_ = d.n_feats

@@ -58,8 +58,8 @@ def load_big_grad_golden(name):
 
 
 # networks that have gradient fingerprints (the oracle's backward is pinned for them) but no training path in the B200
-# library yet: pixel attention.  Training them must raise NotImplementedError.
-NO_TRAINING_PATH = ("qrcan_pa_selective",)
+# library: none since round 2 (pixel attention, Q-SAN / SAN and Q-HAN / HAN train through the library).
+NO_TRAINING_PATH = ()
 
 
 def trainable_grad_golden_names():

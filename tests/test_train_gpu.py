@@ -421,13 +421,16 @@ def test_full_depth_bf16_gradients_stay_aligned_with_the_reference():
 
 
 def test_training_a_network_without_backward_kernels_fails_loudly():
-    """pixel attention has forward kernels only: a training step must raise NotImplementedError, not fall back to
-    anything (its gradient fingerprints in tests/golden/ pin the oracle's backward for the kernels to come)"""
-    assert "qrcan_pa_selective" in NO_TRAINING_PATH
-    _, info = load_golden("qrcan_pa_selective")
-    net, sd, x, meta = _build(info, "bf16")
+    """every golden network now trains (NO_TRAINING_PATH is empty); what is left without a training path is a
+    192-feature Q-EDSR (bf16 inference only: the fp32 training kernels need a divisor of 256): a training step must
+    raise NotImplementedError, not fall back to anything"""
+    from deepfir_b200.qrcan import QEDSR
+    assert NO_TRAINING_PATH == ()
+    net = QEDSR(num_features=192, num_blocks=1, input_para=10, scale=2).cuda().train()
+    x = torch.rand(1, 3, 8, 8).cuda()
+    meta = torch.rand(1, 10, 1, 1).cuda()
     with pytest.raises(NotImplementedError):
-        out = net(x.cuda(), meta.cuda())
+        out = net(x, meta)
         F.l1_loss(out, torch.zeros_like(out)).backward()
 
 
@@ -465,3 +468,29 @@ def test_invalidate_packed_after_a_write_through_data():
             net.train(); net.eval()
             c = net(x.cuda(), meta.cuda())
         assert float((c - a).abs().max()) <= 1e-5 + 1e-5 * float(a.abs().max()), precision
+
+
+@pytest.mark.parametrize("model,kw", [
+    ("qsan", dict(n_resgroups=2, n_resblocks=2, n_feats=64, scale=2)),
+    ("qhan", dict(n_resgroups=10, n_resblocks=1, n_feats=64, scale=2)),
+])
+def test_handler_run_train_of_qsan_and_qhan_reduces_the_loss(tmp_path, model, kw):
+    """BaseModel.run_train through the registry for the staged networks (models/__init__.py:466-479): L1 + Adam; Q-SAN's
+    unused parameters keep .grad None (as under the reference's autograd), so its Adam skips them"""
+    from SISR.models import ModelInterface
+    torch.manual_seed(8)
+    h = ModelInterface.define_model(model, device=0, model_save_dir=str(tmp_path), eval_mode=False, lr=2e-4,
+                                    metadata=["blur_kernel"], precision="bf16", **kw)
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(2, 3, 16, 16, generator=g)
+    y = F.interpolate(x, scale_factor=2, mode="bicubic", align_corners=False).clamp(0, 1)
+    meta = torch.rand(2, 10, generator=g, dtype=torch.float64) * 0.4
+    keys = [("blur_kernel",) * 2] * 10
+    losses = []
+    for _ in range(10):
+        loss, out = h.run_train(x, y, metadata=meta, metadata_keys=keys)
+        assert out.shape == y.shape
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)) and losses[-1] < 0.9 * losses[0], losses
+    if model == "qsan":
+        assert h.net.conv_last.weight.grad is None and h.net.RG[0].conv_last.weight.grad is not None
