@@ -186,6 +186,9 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
   static const bool hl_allowed = getenv("DFIR_STREAM") == nullptr || strcmp(getenv("DFIR_STREAM"), "f32") != 0;
   const int sched0 = n->pa_blob != nullptr ? 2 : n->schedule;
   const bool hl = hl_allowed && sched0 == 0 && sa.stages == ST_ALL && sa.group_out == nullptr && !sa.from_xa;
+  // 8-bit lo plane (x = hi + q * 2^(e - 15)): conv2 moves 8 instead of 10 bytes per element; DFIR_LO8=0 keeps the bf16 lo plane
+  static const int hl_lo8 = getenv("DFIR_LO8") == nullptr ? 1 : atoi(getenv("DFIR_LO8"));
+  const int EPI_HL = hl_lo8 ? EPI_SCALE_SKIP_HL8 : EPI_SCALE_SKIP_HL;
   static const int hl_flip = getenv("DFIR_FLIP") == nullptr ? 1 : atoi(getenv("DFIR_FLIP"));
   static const int hl_fixed_stats = getenv("DFIR_FIXED_STATS") == nullptr ? 1 : atoi(getenv("DFIR_FIXED_STATS"));
   if (hl && hl_fixed_stats && (sa.stages & ST_GROUPS) &&
@@ -196,7 +199,7 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
   __nv_bfloat16* const XBlo = reinterpret_cast<__nv_bfloat16*>(w.XB);
   if (sa.stages & ST_HEAD)
     DFIR_TRY(head_conv(x + static_cast<size_t>(b0) * n->in_feats * H * W, n->head_w_f32, n->head_b, hl ? nullptr : w.Hh, w.Hbf,
-                       Bc, n->in_feats, H, W, C, st, hl ? Hlo : nullptr));
+                       Bc, n->in_feats, H, W, C, st, hl ? Hlo : nullptr, hl_lo8));
   const size_t feat_bytes = static_cast<size_t>(Bc) * H * W * C * 4;
 
   // One launch description shared by all trunk convs; the lambdas below fill in what differs.
@@ -269,7 +272,7 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
         const int w2 = g * per_group + 2 * b + 1;
         // conv2 + attention scale + residual: x_{b+1} = (conv(t) + b) * s + x_b (fp32, in place after block 0);
         // s is evaluated from the statistics of t inside the kernel while its pipeline fills.
-        ConvTcDesc c2 = base(w2, hl ? EPI_SCALE_SKIP_HL : EPI_SCALE_SKIP);
+        ConvTcDesc c2 = base(w2, hl ? EPI_HL : EPI_SCALE_SKIP);
         c2.in_bf16 = w.T; c2.skip_f32 = b == 0 ? skip32 : w.XB; c2.out_f32 = w.XB; c2.out_bf16 = w.XBbf;
         if (hl) {
           c2.skip_hi = b == 0 ? gin : w.XBbf;
@@ -311,7 +314,7 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
       continue;
     }
     // group tail conv + `res += x` (group input)
-    ConvTcDesc ct = base(g * per_group + 2 * nb, hl ? EPI_SCALE_SKIP_HL : EPI_SCALE_SKIP);
+    ConvTcDesc ct = base(g * per_group + 2 * nb, hl ? EPI_HL : EPI_SCALE_SKIP);
     ct.out_bf16 = w.XAbf; ct.skip_f32 = skip32; ct.out_f32 = w.XA; ct.svec = nullptr;
     if (hl) {
       ct.skip_hi = gin;
@@ -333,7 +336,7 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
   }
   __nv_bfloat16* trunk_out = w.XBbf;
   if (sa.stages & ST_TRUNK_TAIL) {
-    ConvTcDesc cf = base(ng * per_group, hl ? EPI_SCALE_SKIP_HL : EPI_SCALE_SKIP);
+    ConvTcDesc cf = base(ng * per_group, hl ? EPI_HL : EPI_SCALE_SKIP);
     if (hl) {
       cf.skip_hi = w.Hbf;
       cf.skip_lo = Hlo;
@@ -594,14 +597,14 @@ int dfir_conv3x3_c64_scale_skip(const void* in_bf16, const void* wpacked, const 
   return conv3x3_c64_tc(d, S(stream));
 }
 
-int dfir_conv3x3_c64_scale_skip_hl(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
+static int scale_skip_hl_any(int epi, const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
                                    const float* svec, const void* skip_hi, const void* skip_lo, void* out_hi, void* out_lo,
                                    const float* pool_rows, const float* col_first, const float* col_last, int style,
                                    const float* ca_params, int R, int M, int A, const float* attributes,
                                    const float* sq, int descending, void* stream) {
   if (in_bf16 == nullptr || out_hi == nullptr || skip_hi == nullptr || skip_lo == nullptr) return DFIR_ERR_ARG;
   ConvTcDesc d{};
-  d.B = B; d.H = H; d.W = W; d.cin_total = 64; d.cin_off = 0; d.cout = 64; d.epi = EPI_SCALE_SKIP_HL; d.in_mode = IN_TMA;
+  d.B = B; d.H = H; d.W = W; d.cin_total = 64; d.cin_off = 0; d.cout = 64; d.epi = epi; d.in_mode = IN_TMA;
   d.in_bf16 = in_bf16; d.wpacked = wpacked; d.bias = bias; d.out_bf16 = out_hi; d.out_lo = out_lo;
   d.skip_hi = skip_hi; d.skip_lo = skip_lo; d.flip = descending ? 1 : 0;
   d.out_pix_stride = 128; d.out_row_stride = static_cast<long long>(W) * 128;
@@ -617,6 +620,24 @@ int dfir_conv3x3_c64_scale_skip_hl(const void* in_bf16, const void* wpacked, con
     return DFIR_ERR_CUDA;
   d.num_sms = sms;
   return conv3x3_c64_tc(d, S(stream));
+}
+
+int dfir_conv3x3_c64_scale_skip_hl(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
+                                   const float* svec, const void* skip_hi, const void* skip_lo, void* out_hi, void* out_lo,
+                                   const float* pool_rows, const float* col_first, const float* col_last, int style,
+                                   const float* ca_params, int R, int M, int A, const float* attributes,
+                                   const float* sq, int descending, void* stream) {
+  return scale_skip_hl_any(EPI_SCALE_SKIP_HL, in_bf16, wpacked, bias, B, H, W, svec, skip_hi, skip_lo, out_hi, out_lo, pool_rows,
+                           col_first, col_last, style, ca_params, R, M, A, attributes, sq, descending, stream);
+}
+
+int dfir_conv3x3_c64_scale_skip_hl8(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
+                                    const float* svec, const void* skip_hi, const void* skip_lo8, void* out_hi, void* out_lo8,
+                                    const float* pool_rows, const float* col_first, const float* col_last, int style,
+                                    const float* ca_params, int R, int M, int A, const float* attributes,
+                                    const float* sq, int descending, void* stream) {
+  return scale_skip_hl_any(EPI_SCALE_SKIP_HL8, in_bf16, wpacked, bias, B, H, W, svec, skip_hi, skip_lo8, out_hi, out_lo8,
+                           pool_rows, col_first, col_last, style, ca_params, R, M, A, attributes, sq, descending, stream);
 }
 
 int dfir_conv3x3_c64_accumulate(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,

@@ -187,11 +187,14 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   float* skipbuf = reinterpret_cast<float*>(smem + L::off_skip);
   float* bias_s = reinterpret_cast<float*>(smem + L::off_bias);
   float* pool_s = reinterpret_cast<float*>(smem + L::off_pool);
-  constexpr bool kScaleSkip = EPI == EPI_SCALE_SKIP || EPI == EPI_SCALE_SKIP_HL;
-  // Descending traversal (EPI_SCALE_SKIP_HL, nseg == 1): the pipeline runs on VIRTUAL coordinates (image B-1-b, row H-1-y,
+  constexpr bool kHL = EPI == EPI_SCALE_SKIP_HL || EPI == EPI_SCALE_SKIP_HL8;  // hi + lo stream epilogue
+  constexpr bool kLo8 = EPI == EPI_SCALE_SKIP_HL8;                             // ... with the 8-bit lo plane
+  constexpr int kHlLoBytes = kLo8 ? 1024 : 2048;                               // lo part of a stream tile
+  constexpr bool kScaleSkip = EPI == EPI_SCALE_SKIP || kHL;
+  // Descending traversal (hi + lo stream, nseg == 1): the pipeline runs on VIRTUAL coordinates (image B-1-b, row H-1-y,
   // kernel row 2-dy: a vertically flipped problem, ascending); only the addresses at the edges are mirrored.
-  const bool flip = EPI == EPI_SCALE_SKIP_HL && a.flip != 0;
-  constexpr int kScratchShift = EPI == EPI_SCALE_SKIP_HL ? L::hl_scratch_shift : 0;
+  const bool flip = kHL && a.flip != 0;
+  constexpr int kScratchShift = kHL ? L::hl_scratch_shift : 0;
   float* attn_s = reinterpret_cast<float*>(smem + L::off_attn + kScratchShift);
   float* svec_s = reinterpret_cast<float*>(smem + L::off_svec);
   float* cap_s = reinterpret_cast<float*>(smem + L::off_cap + kScratchShift);
@@ -243,7 +246,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       mbar_init(&go[i], 8);
     }
     mbar_init(wbar, 1);
-    if constexpr (EPI == EPI_SCALE_SKIP_HL) {
+    if constexpr (kHL) {
       for (int i = 0; i < 8 * kHlSlots; ++i) mbar_init(&sbar[i], 1);
       for (int i = 0; i < 4; ++i) prefetch_tmap(&hl.m[i]);
     }
@@ -640,7 +643,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         if (hl_lg < g1) {
           uint8_t* dst = hl_base + hl_lslot * (8 * kHlItemBytes);
           const int xs = hl_lseg * 128 + q * 32 + hl_lhalf * 16;
-          mbar_arrive_expect_tx(&hl_bar[hl_lslot], kHlItemBytes);
+          mbar_arrive_expect_tx(&hl_bar[hl_lslot], 2048 + kHlLoBytes);
           const int ya = flip ? H - 1 - hl_ly : hl_ly, ba = flip ? a.B - 1 - hl_lb : hl_lb;
           tma_load_4d(dst, &hl.m[0], &hl_bar[hl_lslot], 0, xs, ya, ba);
           if (a.use_hints) tma_load_4d_hint(dst + 2048, &hl.m[1], &hl_bar[hl_lslot], 0, xs, ya, ba, a.pol_skip);
@@ -686,7 +689,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           }
         }
         grid_dep_wait();
-        if constexpr (EPI == EPI_SCALE_SKIP_HL) {
+        if constexpr (kHL) {
           if (lane == 0) {  // the first two tiles travel while the attention vector is evaluated
             hl_issue();
             hl_issue();
@@ -962,7 +965,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             for (int c = 0; c < NT; ++c)
               if (c < a.cout) o[c * plane] = __uint_as_float(r0[c]) + bias_s[c] + (a.tail_accumulate ? o[c * plane] : 0.f);
           }
-        } else if constexpr (EPI == EPI_SCALE_SKIP_HL) {
+        } else if constexpr (kHL) {
           uint32_t ra[32], rb[32];  // 16x256b fragments: pixels pr, pr + 8 (ra) and pr + 16, pr + 24 (rb), 16 channels each
           tmem_ld_16x256b_x8(taddr, ra);
           tmem_ld_16x256b_x8(taddr + (16u << 16), rb);
@@ -1002,6 +1005,49 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               // per word the compiler must keep every load behind the previous word's store (same buffer), which
               // serialises 16 shared-memory round trips (measured: 3000 clk per tile instead of ~700)
               uint32_t hw[8], lw[8];
+              if constexpr (kLo8) {
+                // 8-bit lo plane: x = hi + q * 2^(e - 15), e = exponent of hi, q in [-128, 127] (16 significant bits).
+                // Tile of 16 px x 64 B, TMA SWIZZLE_64B: pixel p, byte c at p * 64 + (((c >> 4) ^ ((p >> 1) & 3)) << 4) + (c & 15);
+                // this thread's two channels 8 n + 2 cq + {0, 1} of pixel p = pr + 8 sl are one 16-bit word.
+                const int p = pr + 8 * sl;
+                uint8_t* lbase = buf + 2048 + p * 64 + 2 * cq;
+                const int sw = (p >> 1) & 3;
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                  hw[n] = *reinterpret_cast<const uint32_t*>(wbase + sl * 1024 + ((n ^ pr) << 4));
+                  lw[n] = *reinterpret_cast<const uint16_t*>(lbase + (((n >> 1) ^ sw) << 4) + 8 * (n & 1));
+                }
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                  const uint32_t* src = half ? rb : ra;
+                  const uint32_t h0 = hw[n] << 16, h1 = hw[n] & 0xffff0000u;
+                  // q as a float without I2F: 1.5 * 2^23 + q has q in its low mantissa bits
+                  const float q0 = __uint_as_float(0x4B400000u + static_cast<uint32_t>(static_cast<int>(static_cast<int8_t>(lw[n] & 0xffu)))) - 12582912.f;
+                  const float q1 = __uint_as_float(0x4B400000u + static_cast<uint32_t>(static_cast<int>(static_cast<int8_t>(lw[n] >> 8)))) - 12582912.f;
+                  const uint32_t e0 = h0 & 0x7f800000u, e1 = h1 & 0x7f800000u;  // 2^e as a float (0 for zero / subnormal hi)
+                  const float p0 = __uint_as_float(e0 > 0x07800000u ? e0 - 0x07800000u : 0u);  // 2^(e - 15)
+                  const float p1 = __uint_as_float(e1 > 0x07800000u ? e1 - 0x07800000u : 0u);
+                  const float x0 = fmaf(q0, p0, __uint_as_float(h0));
+                  const float x1 = fmaf(q1, p1, __uint_as_float(h1));
+                  const float o0 = fmaf(__uint_as_float(src[4 * n + 2 * sl]), hl_s[2 * n], hl_bs[2 * n]) + x0;
+                  const float o1 = fmaf(__uint_as_float(src[4 * n + 2 * sl + 1]), hl_s[2 * n + 1], hl_bs[2 * n + 1]) + x1;
+                  const uint32_t nh = pack_bf16x2(o0, o1);
+                  hw[n] = nh;
+                  const uint32_t g0 = (nh << 16) & 0x7f800000u, g1 = nh & 0x7f800000u;
+                  // 2^(15 - e') (exponent field 269 - E'); 0 when hi is too small to carry a lo part
+                  const float i0 = __uint_as_float(g0 > 0x07800000u ? 0x86800000u - g0 : 0u);
+                  const float i1 = __uint_as_float(g1 > 0x07800000u ? 0x86800000u - g1 : 0u);
+                  // round to nearest without F2I: adding 1.5 * 2^23 leaves the integer in the low mantissa bits
+                  const int r0 = static_cast<int>(__float_as_uint(fmaf(o0 - __uint_as_float(nh << 16), i0, 12582912.f))) - 0x4B400000;
+                  const int r1 = static_cast<int>(__float_as_uint(fmaf(o1 - __uint_as_float(nh & 0xffff0000u), i1, 12582912.f))) - 0x4B400000;
+                  lw[n] = (static_cast<uint32_t>(min(r0, 127)) & 0xffu) | ((static_cast<uint32_t>(min(r1, 127)) & 0xffu) << 8);
+                }
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                  *reinterpret_cast<uint32_t*>(wbase + sl * 1024 + ((n ^ pr) << 4)) = hw[n];
+                  *reinterpret_cast<uint16_t*>(lbase + (((n >> 1) ^ sw) << 4) + 8 * (n & 1)) = static_cast<uint16_t>(lw[n]);
+                }
+              } else {
 #pragma unroll
               for (int n = 0; n < 8; ++n) {
                 hw[n] = *reinterpret_cast<const uint32_t*>(wbase + sl * 1024 + ((n ^ pr) << 4));
@@ -1022,6 +1068,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               for (int n = 0; n < 8; ++n) {
                 *reinterpret_cast<uint32_t*>(wbase + sl * 1024 + ((n ^ pr) << 4)) = hw[n];
                 *reinterpret_cast<uint32_t*>(wbase + 2048 + sl * 1024 + ((n ^ pr) << 4)) = lw[n];
+              }
               }
             }
             fence_proxy_async_smem();
@@ -1432,8 +1479,8 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           atomicAdd(dst + 128, static_cast<unsigned long long>(fx_cl));
         }
       }
-      if (EPI != EPI_TAIL_NCHW && EPI != EPI_SCALE_SKIP && EPI != EPI_SCALE_SKIP_HL && et == 0) tma_store_wait<0>();
-      if (EPI == EPI_SCALE_SKIP_HL && lane == 0) tma_store_wait<0>();
+      if (EPI != EPI_TAIL_NCHW && EPI != EPI_SCALE_SKIP && !kHL && et == 0) tma_store_wait<0>();
+      if (kHL && lane == 0) tma_store_wait<0>();
     }
   }
 
@@ -1477,6 +1524,21 @@ int make_tmap_nhwc_bf16(CUtensorMap* m, const void* base, int C, int W, int H, i
   cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? DFIR_OK : DFIR_ERR_TMAP;
+}
+
+// dense NHWC uint8 plane (the 8-bit lo plane of the residual stream): box = 64 channels x box_w pixels, SWIZZLE_64B
+int make_tmap_nhwc_u8(CUtensorMap* m, const void* base, int C, int W, int H, int B, int box_w) {
+  PFN_encodeTiled enc = get_encode();
+  if (enc == nullptr) return DFIR_ERR_DRIVER;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(C) * W, static_cast<cuuint64_t>(C) * W * H};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(C), static_cast<cuuint32_t>(box_w), 1u, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? DFIR_OK : DFIR_ERR_TMAP;
 }
@@ -1551,7 +1613,8 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   if (d.epi == EPI_SCALE_SKIP && (d.out_bf16 == nullptr || d.out_pix_stride != 128 ||
                                   d.out_row_stride != static_cast<long long>(d.W) * 128))
     return DFIR_ERR_ARG;  // the direct-store epilogue writes dense NHWC
-  const bool hl_mode = d.epi == EPI_SCALE_SKIP_HL;
+  const bool hl_mode = d.epi == EPI_SCALE_SKIP_HL || d.epi == EPI_SCALE_SKIP_HL8;
+  const bool lo8 = d.epi == EPI_SCALE_SKIP_HL8;
   if (hl_mode && (fused || d.out_bf16 == nullptr || d.skip_hi == nullptr || d.skip_lo == nullptr || d.out_pix_stride != 128 ||
                   d.out_row_stride != static_cast<long long>(d.W) * 128 || d.r_out != nullptr || d.relu_out))
     return DFIR_ERR_ARG;  // the stream planes are dense NHWC; training extras live on the fp32-stream epilogue
@@ -1588,7 +1651,9 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
     const long long rowB = static_cast<long long>(d.W) * 128, imgB = rowB * d.H;
     const void* planes[4] = {d.skip_hi, d.skip_lo, d.out_bf16, d.out_lo != nullptr ? d.out_lo : d.out_bf16};
     for (int i = 0; i < 4; ++i) {
-      rc = make_tmap_nhwc_bf16(&hl.m[i], planes[i], 64, d.W, d.H, d.B, 128, rowB, imgB, 16);
+      const bool lo_plane = (i & 1) != 0 && !(i == 3 && d.out_lo == nullptr);
+      rc = (lo8 && lo_plane) ? make_tmap_nhwc_u8(&hl.m[i], planes[i], 64, d.W, d.H, d.B, 16)
+                             : make_tmap_nhwc_bf16(&hl.m[i], planes[i], 64, d.W, d.H, d.B, 128, rowB, imgB, 16);
       if (rc != DFIR_OK) return rc;
     }
   } else {
@@ -1643,7 +1708,7 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
       return c == 'f' ? ptx::kL2EvictFirst : (c == 'l' ? ptx::kL2EvictLast : ptx::kL2EvictNormal);
     };
     const bool conv1_role = d.epi == EPI_RELU_STATS || d.epi == EPI_BIAS_RELU;
-    const bool conv2_role = d.epi == EPI_SCALE_SKIP || d.epi == EPI_SCALE_SKIP_HL;  // HL: letters 5, 6 = lo plane in / out
+    const bool conv2_role = d.epi == EPI_SCALE_SKIP || hl_mode;  // HL: letters 5, 6 = lo plane in / out
     if (pol != nullptr && strlen(pol) >= 6 && strncmp(pol, "nnnnnn", 6) != 0 && !fused && (conv1_role || conv2_role)) {
       a.use_hints = 1;
       a.pol_in = word(pol[conv1_role ? 0 : 2]);
@@ -1685,6 +1750,7 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
     case EPI_SCALE_SKIP: return launch_one<64, EPI_SCALE_SKIP, IN_TMA>(tin, tout, hl, a, grid, stream);
     case EPI_TAIL_NCHW: return launch_one<16, EPI_TAIL_NCHW, IN_TMA>(tin, tout, hl, a, grid, stream);
     case EPI_SCALE_SKIP_HL: return launch_one<64, EPI_SCALE_SKIP_HL, IN_TMA>(tin, tout, hl, a, grid, stream);
+    case EPI_SCALE_SKIP_HL8: return launch_one<64, EPI_SCALE_SKIP_HL8, IN_TMA>(tin, tout, hl, a, grid, stream);
     default: return DFIR_ERR_ARG;
   }
 }

@@ -26,6 +26,8 @@ enum : int {
                           // 16 significant bits): out = (acc + b) * s + (skip_hi + skip_lo) -> out_hi = bf16(out),
                           // out_lo = bf16(out - out_hi).  10 instead of 12 bytes per element (the hi plane IS the next
                           // conv's operand); skip and result tiles travel by TMA, 16 pixels x 64 channels at a time.
+  EPI_SCALE_SKIP_HL8 = 9, // the same with an 8-BIT lo plane: x = hi + q * 2^(e - 15), e = exponent of hi, q = int8 (still 16
+                          // significant bits): 8 bytes per element (t 2, hi in/out 4, lo in/out 2)
 };
 
 enum : int { IN_TMA = 0, IN_FUSED = 1 };  // input modes of the tensor-core conv (see conv_tc.cu)
@@ -139,7 +141,7 @@ int pack_conv_weights_bf16(const float* w_oihw, void* out, int cout, int cin, in
                            int co_stride, cudaStream_t s);
 int pack_conv_weights_f32(const float* w_oihw, float* out, int cout, int cin, cudaStream_t s);
 int head_conv(const float* x_nchw, const float* w_packed, const float* bias, float* out_f32, __nv_bfloat16* out_bf16,
-              int B, int Cin, int H, int W, int Cout, cudaStream_t s, __nv_bfloat16* out_lo = nullptr);
+              int B, int Cin, int H, int W, int Cout, cudaStream_t s, __nv_bfloat16* out_lo = nullptr, int lo8 = 0);
 int conv3x3_f32(const float* in, const float* w_packed, const float* bias, const float* skip, float* out, int B, int H,
                 int W, int Cin, int Cout, int relu, int ps_r, int out_nchw, cudaStream_t s, const float* mask = nullptr);
 // ---- training input pipeline (degrade.cu)

@@ -54,7 +54,7 @@ constexpr int kHeadPatchStride = 136;  // floats per patch row: 130 used, 16-byt
 __global__ void __launch_bounds__(256)
 head_conv_kernel(const float* __restrict__ x, const float* __restrict__ wp, const float* __restrict__ bias,
                  float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, int B, int Cin, int H, int W, int Cout,
-                 __nv_bfloat16* __restrict__ out_lo) {
+                 __nv_bfloat16* __restrict__ out_lo, int lo8) {
   extern __shared__ __align__(16) float ws[];  // [9*Cin][Cout] weights, then [Cin][3][kHeadPatchStride] input patch
   const int nw = 9 * Cin * Cout;
   float* patch = ws + ((nw + 3) & ~3);
@@ -115,7 +115,22 @@ head_conv_kernel(const float* __restrict__ x, const float* __restrict__ wp, cons
 #pragma unroll
           for (int i = 0; i < 4; ++i) pk[i] = __floats2bfloat162_rn(acc[p][2 * i], acc[p][2 * i + 1]);
           *reinterpret_cast<uint4*>(out_bf16 + o) = *reinterpret_cast<uint4*>(pk);
-          if (out_lo != nullptr) {  // hi + lo residual stream: lo = bf16(value - hi)
+          if (out_lo != nullptr && lo8) {  // 8-bit lo plane: q = rint((value - hi) * 2^(15 - e)), e = exponent of hi
+            __align__(8) unsigned char qb[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 h = __bfloat1622float2(pk[i]);
+              const float hv[2] = {h.x, h.y};
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const uint32_t ex = __float_as_uint(hv[e]) & 0x7f800000u;
+                const float inv = __uint_as_float(ex > 0x07800000u ? 0x86800000u - ex : 0u);
+                const int r = __float2int_rn((acc[p][2 * i + e] - hv[e]) * inv);
+                qb[2 * i + e] = static_cast<unsigned char>(min(r, 127) & 0xff);
+              }
+            }
+            *reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(out_lo) + o) = *reinterpret_cast<uint2*>(qb);
+          } else if (out_lo != nullptr) {  // hi + lo residual stream: lo = bf16(value - hi)
             __align__(16) __nv_bfloat162 lo[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -652,7 +667,7 @@ int pack_conv_weights_f32(const float* w, float* out, int cout, int cin, cudaStr
 }
 
 int head_conv(const float* x, const float* wp, const float* bias, float* out_f32, __nv_bfloat16* out_bf16, int B,
-              int Cin, int H, int W, int Cout, cudaStream_t s, __nv_bfloat16* out_lo) {
+              int Cin, int H, int W, int Cout, cudaStream_t s, __nv_bfloat16* out_lo, int lo8) {
   const int smem = (((9 * Cin * Cout + 3) & ~3) + Cin * 3 * kHeadPatchStride) * 4;
   if (Cout % 8 != 0 || smem > 48 * 1024) return DFIR_ERR_ARG;
   const long long nitems = static_cast<long long>(B) * H * ((W + 127) / 128);
@@ -660,7 +675,7 @@ int head_conv(const float* x, const float* wp, const float* bias, float* out_f32
   if (nitems > 0x7fffffffll) return DFIR_ERR_ARG;
   const long long nblocks = std::min<long long>(nitems, 148 * 4);
   head_conv_kernel<<<static_cast<unsigned>(nblocks), 256, smem, s>>>(x, wp, bias, out_f32, out_bf16, B, Cin, H, W, Cout,
-                                                                      out_lo);
+                                                                      out_lo, lo8);
   return ok_or_cuda();
 }
 

@@ -78,6 +78,8 @@ PROTOTYPES = {
                                          _i, _vp, _vp, _vp]),
     "dfir_conv3x3_c64_scale_skip_hl": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i,
                                             _i, _i, _vp, _vp, _i, _vp]),
+    "dfir_conv3x3_c64_scale_skip_hl8": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i,
+                                             _i, _i, _vp, _vp, _i, _vp]),
     "dfir_conv3x3_c64_accumulate": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "dfir_conv3x3_c64_tail": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "dfir_conv3x3_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -234,6 +234,36 @@ def test_pool_by_linearity_trio(shape, style):
                                             None, 0, None, 4, M, A, None, None, 1, G.stream()) == 0
     G.sync()
     assert ((x_hi.float() + x_lo.float()) - out32).abs().max().item() <= 2.0 ** -15 * scale
+    # ---- the same on the 8-BIT lo plane (the format of dfir_qrcan_forward): x = hi + q * 2^(e - 15), e = exponent of hi
+    def enc8(v32):
+        hi = v32.to(torch.bfloat16)
+        e = (torch.frexp(hi.float())[1] - 1).float()           # |hi| = m * 2^(e + 1), m in [0.5, 1)
+        q = torch.round((v32 - hi.float()) * torch.exp2(15 - e)).clamp(-128, 127)
+        q = torch.where(hi.float() == 0, torch.zeros_like(q), q)
+        return hi, q.to(torch.int8)
+
+    def dec8(hi, q):
+        e = (torch.frexp(hi.float())[1] - 1).float()
+        return hi.float() + q.float() * torch.exp2(e - 15)
+
+    y_hi, y_q = enc8(x32)
+    assert (dec8(y_hi, y_q) - x32).abs().max().item() <= 2.0 ** -16 * x32.abs().max().item()
+    for desc in (0, 1):
+        p_hi = torch.full((B, H, W, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+        p_q = torch.full((B, H, W, 64), 77, device="cuda", dtype=torch.int8)
+        assert L.dfir_conv3x3_c64_scale_skip_hl8(t_d.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), B, H, W, None, y_hi.data_ptr(),
+                                                 y_q.data_ptr(), p_hi.data_ptr(), p_q.data_ptr(), pool.data_ptr(),
+                                                 cf.data_ptr(), cl.data_ptr(), STYLE_ID[style], blob.data_ptr(), 4, M, A,
+                                                 attr_d.data_ptr(), sq_d.data_ptr(), desc, G.stream()) == 0
+        G.sync()
+        assert (dec8(p_hi, p_q) - out32).abs().max().item() <= 2.0 ** -14 * scale, desc
+        assert (p_hi.float() - out32).abs().max().item() <= 2.0 ** -8 * scale
+    # in place, scale vector from memory
+    assert L.dfir_conv3x3_c64_scale_skip_hl8(t_d.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), B, H, W, svec.data_ptr(),
+                                             y_hi.data_ptr(), y_q.data_ptr(), y_hi.data_ptr(), y_q.data_ptr(), None, None,
+                                             None, 0, None, 4, M, A, None, None, 1, G.stream()) == 0
+    G.sync()
+    assert (dec8(y_hi, y_q) - out32).abs().max().item() <= 2.0 ** -14 * scale
     # group-conv use: no scale vector, in-place stream update
     assert L.dfir_conv3x3_c64_scale_skip(t_d.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), B, H, W, None,
                                          x32.data_ptr(), x32.data_ptr(), outbf.data_ptr(), None, None, None, 0,
