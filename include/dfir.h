@@ -145,10 +145,12 @@ int dfir_conv3x3_c64_scale_skip_hl(const void* in_bf16, const void* wpacked, con
                                    const float* pool_rows, const float* col_first, const float* col_last, int style,
                                    const float* ca_params, int R, int M, int A, const float* attributes,
                                    const float* sq, int descending, void* stream);
-/* The same with an 8-BIT lo plane (the format dfir_qrcan_forward uses by default): x = hi + q * 2^(e - 15), e = the unbiased
- * exponent of hi, q = int8 in [-128, 127] = rint((x - hi) * 2^(15 - e)) (x - hi never exceeds half an ulp of hi = 2^(e - 8),
- * so q fits; +128 saturates to 127) - still 16 significant bits, 8 bytes of HBM traffic per element (t 2, hi 2 + 2, lo 1 + 1).
- * skip_lo8 / out_lo8: dense NHWC int8 planes [B][H][W][64]; q = 0 where hi is zero or below 2^-111. */
+/* The same with an 8-BIT lo plane (the format dfir_qrcan_forward uses by default).  The stream value is a 24-bit float X
+ * (sign, 8 exponent bits, 15 mantissa bits: 16 significant bits, like hi + lo above) stored as two planes whose BIT PATTERNS
+ * add up: bits(X) = (hi << 16) + (q << 8) with hi = the bf16 nearest to X (ties away from zero) and q = int8 in [-128, 127].
+ * X = the result rounded to 24 bits (ties away from zero).  The integer form is exact across binade boundaries and needs no
+ * exponent arithmetic in the epilogue.  8 bytes of HBM traffic per element (t 2, hi 2 + 2, lo 1 + 1).
+ * skip_lo8 / out_lo8: dense NHWC int8 planes [B][H][W][64]. */
 int dfir_conv3x3_c64_scale_skip_hl8(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
                                    const float* svec, const void* skip_hi, const void* skip_lo8, void* out_hi, void* out_lo8,
                                    const float* pool_rows, const float* col_first, const float* col_last, int style,

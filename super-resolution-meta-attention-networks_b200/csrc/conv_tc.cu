@@ -1006,9 +1006,12 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               // serialises 16 shared-memory round trips (measured: 3000 clk per tile instead of ~700)
               uint32_t hw[8], lw[8];
               if constexpr (kLo8) {
-                // 8-bit lo plane: x = hi + q * 2^(e - 15), e = exponent of hi, q in [-128, 127] (16 significant bits).
-                // Tile of 16 px x 64 B, TMA SWIZZLE_64B: pixel p, byte c at p * 64 + (((c >> 4) ^ ((p >> 1) & 3)) << 4) + (c & 15);
-                // this thread's two channels 8 n + 2 cq + {0, 1} of pixel p = pr + 8 sl are one 16-bit word.
+                // 8-bit lo plane: the stream value is a 24-BIT float X (sign, exponent, 15 mantissa bits = 16 significant bits);
+                // hi = the bf16 nearest to X (ties away from zero), q = (X - hi) in units of X's last bit, taken on the BIT
+                // PATTERNS: bits(X) = (hi << 16) + (q << 8), q in [-128, 127] - exact across binade boundaries, no exponent
+                // arithmetic, no conversions.  Tile of 16 px x 64 B, TMA SWIZZLE_64B: pixel p, byte c at
+                // p * 64 + (((c >> 4) ^ ((p >> 1) & 3)) << 4) + (c & 15); this thread's two channels 8 n + 2 cq + {0, 1} of pixel
+                // p = pr + 8 sl are one 16-bit word.
                 const int p = pr + 8 * sl;
                 uint8_t* lbase = buf + 2048 + p * 64 + 2 * cq;
                 const int sw = (p >> 1) & 3;
@@ -1020,27 +1023,15 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
                   const uint32_t* src = half ? rb : ra;
-                  const uint32_t h0 = hw[n] << 16, h1 = hw[n] & 0xffff0000u;
-                  // q as a float without I2F: 1.5 * 2^23 + q has q in its low mantissa bits
-                  const float q0 = __uint_as_float(0x4B400000u + static_cast<uint32_t>(static_cast<int>(static_cast<int8_t>(lw[n] & 0xffu)))) - 12582912.f;
-                  const float q1 = __uint_as_float(0x4B400000u + static_cast<uint32_t>(static_cast<int>(static_cast<int8_t>(lw[n] >> 8)))) - 12582912.f;
-                  const uint32_t e0 = h0 & 0x7f800000u, e1 = h1 & 0x7f800000u;  // 2^e as a float (0 for zero / subnormal hi)
-                  const float p0 = __uint_as_float(e0 > 0x07800000u ? e0 - 0x07800000u : 0u);  // 2^(e - 15)
-                  const float p1 = __uint_as_float(e1 > 0x07800000u ? e1 - 0x07800000u : 0u);
-                  const float x0 = fmaf(q0, p0, __uint_as_float(h0));
-                  const float x1 = fmaf(q1, p1, __uint_as_float(h1));
+                  // (sign-extended q) << 8 by one byte permute each: bytes [0, q, sign, sign]
+                  const float x0 = __uint_as_float((hw[n] << 16) + __byte_perm(lw[n], 0u, 0x8802u));
+                  const float x1 = __uint_as_float((hw[n] & 0xffff0000u) + __byte_perm(lw[n], 0u, 0x9912u));
                   const float o0 = fmaf(__uint_as_float(src[4 * n + 2 * sl]), hl_s[2 * n], hl_bs[2 * n]) + x0;
                   const float o1 = fmaf(__uint_as_float(src[4 * n + 2 * sl + 1]), hl_s[2 * n + 1], hl_bs[2 * n + 1]) + x1;
-                  const uint32_t nh = pack_bf16x2(o0, o1);
-                  hw[n] = nh;
-                  const uint32_t g0 = (nh << 16) & 0x7f800000u, g1 = nh & 0x7f800000u;
-                  // 2^(15 - e') (exponent field 269 - E'); 0 when hi is too small to carry a lo part
-                  const float i0 = __uint_as_float(g0 > 0x07800000u ? 0x86800000u - g0 : 0u);
-                  const float i1 = __uint_as_float(g1 > 0x07800000u ? 0x86800000u - g1 : 0u);
-                  // round to nearest without F2I: adding 1.5 * 2^23 leaves the integer in the low mantissa bits
-                  const int r0 = static_cast<int>(__float_as_uint(fmaf(o0 - __uint_as_float(nh << 16), i0, 12582912.f))) - 0x4B400000;
-                  const int r1 = static_cast<int>(__float_as_uint(fmaf(o1 - __uint_as_float(nh & 0xffff0000u), i1, 12582912.f))) - 0x4B400000;
-                  lw[n] = (static_cast<uint32_t>(min(r0, 127)) & 0xffu) | ((static_cast<uint32_t>(min(r1, 127)) & 0xffu) << 8);
+                  const uint32_t t0 = __float_as_uint(o0) + 0x80u, t1 = __float_as_uint(o1) + 0x80u;  // round to 24 bits
+                  const uint32_t b0 = (t0 + 0x8000u) & 0xffff0000u, b1 = (t1 + 0x8000u) & 0xffff0000u;   // nearest bf16
+                  hw[n] = __byte_perm(b0, b1, 0x7632u);
+                  lw[n] = __byte_perm(t0 - b0, t1 - b1, 0x0051u);   // byte 1 of each difference
                 }
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {

@@ -26,8 +26,9 @@ enum : int {
                           // 16 significant bits): out = (acc + b) * s + (skip_hi + skip_lo) -> out_hi = bf16(out),
                           // out_lo = bf16(out - out_hi).  10 instead of 12 bytes per element (the hi plane IS the next
                           // conv's operand); skip and result tiles travel by TMA, 16 pixels x 64 channels at a time.
-  EPI_SCALE_SKIP_HL8 = 9, // the same with an 8-BIT lo plane: x = hi + q * 2^(e - 15), e = exponent of hi, q = int8 (still 16
-                          // significant bits): 8 bytes per element (t 2, hi in/out 4, lo in/out 2)
+  EPI_SCALE_SKIP_HL8 = 9, // the same with an 8-BIT lo plane: the stream value is a 24-bit float X (16 significant bits) whose
+                          // bit pattern is (hi << 16) + (q << 8), hi = nearest bf16, q = int8: 8 bytes per element (t 2, hi
+                          // in/out 4, lo in/out 2) and no more epilogue arithmetic than the bf16 lo plane needs
 };
 
 enum : int { IN_TMA = 0, IN_FUSED = 1 };  // input modes of the tensor-core conv (see conv_tc.cu)

@@ -115,20 +115,19 @@ head_conv_kernel(const float* __restrict__ x, const float* __restrict__ wp, cons
 #pragma unroll
           for (int i = 0; i < 4; ++i) pk[i] = __floats2bfloat162_rn(acc[p][2 * i], acc[p][2 * i + 1]);
           *reinterpret_cast<uint4*>(out_bf16 + o) = *reinterpret_cast<uint4*>(pk);
-          if (out_lo != nullptr && lo8) {  // 8-bit lo plane: q = rint((value - hi) * 2^(15 - e)), e = exponent of hi
+          if (out_lo != nullptr && lo8) {
+            // 8-bit lo plane (see EPI_SCALE_SKIP_HL8 in conv_tc.cu): the stream value is the 24-bit float X nearest to the
+            // result, bits(X) = (hi << 16) + (q << 8); hi = nearest bf16 with ties away from zero REPLACES the RN-even hi
+            __align__(16) unsigned short hb[8];
             __align__(8) unsigned char qb[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 h = __bfloat1622float2(pk[i]);
-              const float hv[2] = {h.x, h.y};
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const uint32_t ex = __float_as_uint(hv[e]) & 0x7f800000u;
-                const float inv = __uint_as_float(ex > 0x07800000u ? 0x86800000u - ex : 0u);
-                const int r = __float2int_rn((acc[p][2 * i + e] - hv[e]) * inv);
-                qb[2 * i + e] = static_cast<unsigned char>(min(r, 127) & 0xff);
-              }
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t t = __float_as_uint(acc[p][i]) + 0x80u;
+              const uint32_t bh = (t + 0x8000u) & 0xffff0000u;
+              hb[i] = static_cast<unsigned short>(bh >> 16);
+              qb[i] = static_cast<unsigned char>(((t - bh) >> 8) & 0xffu);
             }
+            *reinterpret_cast<uint4*>(out_bf16 + o) = *reinterpret_cast<uint4*>(hb);
             *reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(out_lo) + o) = *reinterpret_cast<uint2*>(qb);
           } else if (out_lo != nullptr) {  // hi + lo residual stream: lo = bf16(value - hi)
             __align__(16) __nv_bfloat162 lo[4];

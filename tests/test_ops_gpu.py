@@ -234,17 +234,21 @@ def test_pool_by_linearity_trio(shape, style):
                                             None, 0, None, 4, M, A, None, None, 1, G.stream()) == 0
     G.sync()
     assert ((x_hi.float() + x_lo.float()) - out32).abs().max().item() <= 2.0 ** -15 * scale
-    # ---- the same on the 8-BIT lo plane (the format of dfir_qrcan_forward): x = hi + q * 2^(e - 15), e = exponent of hi
+    # ---- the same on the 8-BIT lo plane (the format of dfir_qrcan_forward): the stream value is a 24-bit float X,
+    # bits(X) = (hi << 16) + (q << 8), hi = nearest bf16 (ties away from zero), q = int8
     def enc8(v32):
-        hi = v32.to(torch.bfloat16)
-        e = (torch.frexp(hi.float())[1] - 1).float()           # |hi| = m * 2^(e + 1), m in [0.5, 1)
-        q = torch.round((v32 - hi.float()) * torch.exp2(15 - e)).clamp(-128, 127)
-        q = torch.where(hi.float() == 0, torch.zeros_like(q), q)
-        return hi, q.to(torch.int8)
+        bits = v32.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+        t = bits + 0x80
+        hb = (t + 0x8000) & 0xFFFF0000
+        q = ((t - hb) >> 8) & 0xFF
+        hi = (hb >> 16).to(torch.int32).to(torch.int16).view(torch.bfloat16)      # (wraps to the signed 16-bit pattern)
+        return hi.contiguous(), q.to(torch.uint8).view(torch.int8).contiguous()
 
     def dec8(hi, q):
-        e = (torch.frexp(hi.float())[1] - 1).float()
-        return hi.float() + q.float() * torch.exp2(e - 15)
+        hb = (hi.contiguous().view(torch.int16).to(torch.int64) & 0xFFFF) << 16
+        bits = (hb + (q.to(torch.int64) << 8)) & 0xFFFFFFFF
+        bits = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32)
+        return bits.view(torch.float32)
 
     y_hi, y_q = enc8(x32)
     assert (dec8(y_hi, y_q) - x32).abs().max().item() <= 2.0 ** -16 * x32.abs().max().item()
