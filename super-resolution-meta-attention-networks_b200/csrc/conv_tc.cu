@@ -153,6 +153,14 @@ __device__ __forceinline__ void warp_channel_sums32(float (&v)[32], int lane) {
   }
 }
 
+// prmt.b32 with the full 4-bit selectors (bit 3 of a selector replicates the sign of the selected byte; __byte_perm only
+// honours the low 3 bits)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -1024,14 +1032,14 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
                 for (int n = 0; n < 8; ++n) {
                   const uint32_t* src = half ? rb : ra;
                   // (sign-extended q) << 8 by one byte permute each: bytes [0, q, sign, sign]
-                  const float x0 = __uint_as_float((hw[n] << 16) + __byte_perm(lw[n], 0u, 0x8802u));
-                  const float x1 = __uint_as_float((hw[n] & 0xffff0000u) + __byte_perm(lw[n], 0u, 0x9912u));
+                  const float x0 = __uint_as_float((hw[n] << 16) + prmt(lw[n], 0u, 0x8802u));
+                  const float x1 = __uint_as_float((hw[n] & 0xffff0000u) + prmt(lw[n], 0u, 0x9912u));
                   const float o0 = fmaf(__uint_as_float(src[4 * n + 2 * sl]), hl_s[2 * n], hl_bs[2 * n]) + x0;
                   const float o1 = fmaf(__uint_as_float(src[4 * n + 2 * sl + 1]), hl_s[2 * n + 1], hl_bs[2 * n + 1]) + x1;
                   const uint32_t t0 = __float_as_uint(o0) + 0x80u, t1 = __float_as_uint(o1) + 0x80u;  // round to 24 bits
                   const uint32_t b0 = (t0 + 0x8000u) & 0xffff0000u, b1 = (t1 + 0x8000u) & 0xffff0000u;   // nearest bf16
-                  hw[n] = __byte_perm(b0, b1, 0x7632u);
-                  lw[n] = __byte_perm(t0 - b0, t1 - b1, 0x0051u);   // byte 1 of each difference
+                  hw[n] = prmt(b0, b1, 0x7632u);
+                  lw[n] = prmt(t0 - b0, t1 - b1, 0x0051u);   // byte 1 of each difference
                 }
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
