@@ -94,6 +94,7 @@ class WideQEDSR:
                     w2[k], b2[k] = f2.weight.reshape(F, hid)[j * 64:(j + 1) * 64], f2.bias[j * 64:(j + 1) * 64]
                 self.meta.append((w1, b1, w2, b2))
         self._buf = {}
+        self._graphs = {}
 
     # -------------------------------------------------------------------------------------------------
     def _buffers(self, B, H, W):
@@ -119,6 +120,33 @@ class WideQEDSR:
         return b
 
     def forward(self, x, attr):
+        """One frame batch through the plane loops.  A forward is ~1200 launches of 12-25 us: issued from Python they are
+        host-bound (28.7 ms per 270x480 frame), so from the second call of a shape on the launches are replayed from a CUDA
+        graph (static input / output buffers; `cuda_graphs = False` on the object turns it off)."""
+        if not getattr(self, "cuda_graphs", True) or torch.cuda.is_current_stream_capturing():
+            return self._forward(x, attr)
+        key = (tuple(x.shape), tuple(attr.shape))
+        g = self._graphs.get(key)
+        if g is None:  # first call of this shape: eager (also sets the kernels' attributes, which capture must not do)
+            self._graphs.clear()
+            self._graphs[key] = dict(graph=None)
+            return self._forward(x, attr)
+        with torch.cuda.device(x.device):
+            if g["graph"] is None:
+                g["x"], g["attr"] = torch.empty_like(x), torch.empty_like(attr)
+                g["x"].copy_(x)
+                g["attr"].copy_(attr)
+                torch.cuda.synchronize(x.device)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    g["out"] = self._forward(g["x"], g["attr"])
+                g["graph"] = graph
+            g["x"].copy_(x)
+            g["attr"].copy_(attr)
+            g["graph"].replay()
+            return g["out"].clone()
+
+    def _forward(self, x, attr):
         lib = _lib.load_library()
         nc, r = self.nc, self.r
         B, _, H, W = x.shape
