@@ -105,6 +105,8 @@ constexpr int kThreadsTwoEpi = 320 + 128;    // EPI_SCALE_SKIP / EPI_RELU_STATS 
 constexpr const char* kDefaultL2Policy = "nnnnnn";  // see conv3x3_c64_tc(): overridden by DFIR_L2_POLICY
 constexpr int kHlSlots = 3;                  // EPI_SCALE_SKIP_HL: stream-tile buffers per epilogue warp (1 in use, 2 in flight)
 constexpr int kHlItemBytes = 4096;           // one tile: 16 px x 64 ch bf16 hi (2 KB) + lo (2 KB)
+constexpr int kHl8Slots = 4;                 // EPI_SCALE_SKIP_HL8: the 3 KB tiles (hi 2 KB + 8-bit lo 1 KB) leave room for a 4th
+constexpr int kHl8ItemBytes = 3072;          //   buffer: a store may still drain while two loads are in flight
 constexpr int kMaxBandImages = 8;            // a CTA's row band may touch at most this many images (IN_FUSED)
 constexpr int kAttnScratchFloats = 64 + 64 + 512 + 1024 + 4;  // attention scratch of one epilogue group
 constexpr int kCaStageFloats = 704;          // QCALayer parameter blobs up to this size are staged in shared memory
@@ -126,12 +128,15 @@ struct SmemLayout {
   static_assert(off_cap + kCaStageFloats * 4 <= off_stage + 2 * kStageBytes, "prologue scratch must fit the staging tiles");
   static constexpr int off_svec = off_pool + 12 * 64 * 4;  // (2 groups x [4 warp sums | first column | last column] x 64)
   static constexpr int off_bars = off_svec + kMaxBandImages * 64 * 4;
-  static constexpr int n_bars = 2 * kSlots + kARows + 2 * kAcc + 1 + 8 * kHlSlots;
+  static constexpr int n_bars = 2 * kSlots + kARows + 2 * kAcc + 1 + 8 * kHl8Slots;
   // EPI_SCALE_SKIP_HL: the 96 KB of the staging tiles + skip buffers hold, slot-major, kHlSlots x 8 warps x (2 KB hi +
   // 2 KB lo) stream tiles of 16 pixels; the prologue scratch aliases the last slot (first used after the prologue)
   static constexpr int off_hl = off_stage;
   static constexpr int hl_scratch_shift = (kHlSlots - 1) * 8 * kHlItemBytes;
+  static constexpr int hl8_scratch_shift = (kHl8Slots - 1) * 8 * kHl8ItemBytes;
   static_assert(kHlSlots * 8 * kHlItemBytes <= 2 * kStageBytes + 2 * 128 * 64 * 4, "stream tiles must fit the epilogue buffers");
+  static_assert(kHl8Slots * 8 * kHl8ItemBytes <= 2 * kStageBytes + 2 * 128 * 64 * 4, "stream tiles must fit the epilogue buffers");
+  static_assert(2 * kAttnScratchFloats * 4 + kCaStageFloats * 4 <= 8 * kHl8ItemBytes, "prologue scratch must fit one slot");
   static constexpr int off_tmem = off_bars + n_bars * 8;
   static constexpr int total = off_tmem + 16;
 };
@@ -202,7 +207,9 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   // Descending traversal (hi + lo stream, nseg == 1): the pipeline runs on VIRTUAL coordinates (image B-1-b, row H-1-y,
   // kernel row 2-dy: a vertically flipped problem, ascending); only the addresses at the edges are mirrored.
   const bool flip = kHL && a.flip != 0;
-  constexpr int kScratchShift = kHL ? L::hl_scratch_shift : 0;
+  constexpr int kHS = kLo8 ? kHl8Slots : kHlSlots;            // stream-tile buffers per epilogue warp
+  constexpr int kHI = kLo8 ? kHl8ItemBytes : kHlItemBytes;    // bytes of one buffer
+  constexpr int kScratchShift = kHL ? (kLo8 ? L::hl8_scratch_shift : L::hl_scratch_shift) : 0;
   float* attn_s = reinterpret_cast<float*>(smem + L::off_attn + kScratchShift);
   float* svec_s = reinterpret_cast<float*>(smem + L::off_svec);
   float* cap_s = reinterpret_cast<float*>(smem + L::off_cap + kScratchShift);
@@ -255,7 +262,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
     }
     mbar_init(wbar, 1);
     if constexpr (kHL) {
-      for (int i = 0; i < 8 * kHlSlots; ++i) mbar_init(&sbar[i], 1);
+      for (int i = 0; i < 8 * kHS; ++i) mbar_init(&sbar[i], 1);
       for (int i = 0; i < 4; ++i) prefetch_tmap(&hl.m[i]);
     }
     fence_barrier_init();
@@ -642,14 +649,14 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       // private 4 KB buffers (TMA load -> in-place update -> TMA store), two tiles of 16 pixels per output row, loads
       // issued two tiles ahead.  No barrier other than the tile's own mbarrier: the warps never wait for each other.
       const int hl_w = egrp * 4 + q;                       // buffer column of this warp
-      uint8_t* const hl_base = smem + L::off_hl + hl_w * kHlItemBytes;
-      uint64_t* const hl_bar = sbar + hl_w * kHlSlots;
+      uint8_t* const hl_base = smem + L::off_hl + hl_w * kHI;
+      uint64_t* const hl_bar = sbar + hl_w * kHS;
       int hl_ly = (g0 + egrp) % H, hl_lcol = (g0 + egrp) / H;  // load cursor: next row whose tiles are requested
       int hl_lb = hl_lcol / nseg, hl_lseg = hl_lcol % nseg;
       int hl_lg = g0 + egrp, hl_lhalf = 0, hl_lslot = 0;
       auto hl_issue = [&]() {  // lane 0: request the next tile (if any) into the next slot
         if (hl_lg < g1) {
-          uint8_t* dst = hl_base + hl_lslot * (8 * kHlItemBytes);
+          uint8_t* dst = hl_base + hl_lslot * (8 * kHI);
           const int xs = hl_lseg * 128 + q * 32 + hl_lhalf * 16;
           mbar_arrive_expect_tx(&hl_bar[hl_lslot], 2048 + kHlLoBytes);
           const int ya = flip ? H - 1 - hl_ly : hl_ly, ba = flip ? a.B - 1 - hl_lb : hl_lb;
@@ -664,7 +671,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             tma_prefetch_4d(&hl.m[1], 0, xs, yp, ba);
           }
         }
-        if (++hl_lslot == kHlSlots) hl_lslot = 0;
+        if (++hl_lslot == kHS) hl_lslot = 0;
         if (++hl_lhalf == 2) {
           hl_lhalf = 0;
           hl_lg += kEpiGroups;
@@ -698,9 +705,10 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         }
         grid_dep_wait();
         if constexpr (kHL) {
-          if (lane == 0) {  // the first two tiles travel while the attention vector is evaluated
+          if (lane == 0) {  // the first two (three) tiles travel while the attention vector is evaluated
             hl_issue();
             hl_issue();
+            if (kLo8 && a.hl_ahead3) hl_issue();
           }
         }
         if (a.epi_stats) {
@@ -998,10 +1006,13 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           }
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            uint8_t* buf = hl_base + hl_slot * (8 * kHlItemBytes);
-            const bool late_issue = (a.debug_probe & 131072) != 0;  // A/B switch (DFIR_DEBUG_PROBE)
+            uint8_t* buf = hl_base + hl_slot * (8 * kHI);
+            const bool late_issue = !kLo8 && (a.debug_probe & 131072) != 0;  // A/B switch (DFIR_DEBUG_PROBE)
             if (lane == 0 && !late_issue) {
-              tma_store_wait_read<0>();  // the previous tile has left its buffer: that buffer takes the tile after next
+              // three buffers: the previous tile must have left its buffer, which takes the tile after next.  Four buffers
+              // (8-bit lo): the buffer to refill was stored two tiles ago, so the latest store may still be draining - or,
+              // with three loads in flight (hl_ahead3), the same rule as with three buffers.
+              if (kLo8 && !a.hl_ahead3) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
               hl_issue();
             }
             mbar_wait(&hl_bar[hl_slot], hl_phase, 10);
@@ -1088,7 +1099,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
                 hl_issue();
               }
             }
-            if (++hl_slot == kHlSlots) {
+            if (++hl_slot == kHS) {
               hl_slot = 0;
               hl_phase ^= 1;
             }
@@ -1660,6 +1671,8 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   }
   ConvTcArgs a{};
   a.hl_store_lo = d.out_lo != nullptr ? 1 : 0;
+  static const int hl_ahead = getenv("DFIR_HL_AHEAD") == nullptr ? 2 : atoi(getenv("DFIR_HL_AHEAD"));
+  a.hl_ahead3 = hl_ahead >= 3 ? 1 : 0;
   a.flip = (hl_mode && d.flip && d.W <= 128) ? 1 : 0;
   a.istats = d.istats;
   a.istats_clear = d.istats_clear;
