@@ -480,10 +480,11 @@ int dfir_channel_dot(const float* a, const float* b, float* out, float* total, i
 
 /* Tail of SOCA.forward (SAN_blocks.py:290-300) on the square root S [B][64][64]: v = mean over dim 1, svec =
  * sigmoid(W2 relu(W1 v + b1) + b2), and its backward: grad_S [B][64][64], grad_mlp (same flat layout as mlp_params,
- * overwritten; summed over the batch in index order). */
+ * overwritten; one CTA per image, contributions summed over the batch in index order). */
 int dfir_soca_mlp(const float* S, const float* mlp_params, int R, float* svec, int B, void* stream);
+size_t dfir_soca_mlp_backward_scratch_bytes(int B, int R);
 int dfir_soca_mlp_backward(const float* S, const float* grad_svec, const float* mlp_params, int R, float* grad_S,
-                           float* grad_mlp, int B, void* stream);
+                           float* grad_mlp, void* scratch, size_t scratch_bytes, int B, void* stream);
 
 /* Backward of dfir_lam: fwd_scratch is the scratch buffer of the forward call, unmodified (it holds the attention matrix);
  * grad_out [B][HW][N*C]; grad_stack: map n at grad_stack + n * grad_map_stride_elems; grad_gamma: one float (overwritten). */

@@ -197,8 +197,9 @@ size_t outer_reduce_scratch_floats(int Ao, int Bi);
 int outer_reduce(const float* A, int Ao, const float* Bm, int Bi, long long npix, float* out, float* colsum,
                  int accumulate, float* scratch, cudaStream_t s);
 int soca_mlp_forward(const float* S, const float* mlp, int R, float* svec, int B, cudaStream_t s);
-int soca_mlp_backward(const float* S, const float* dsvec, const float* mlp, int R, float* dS, float* dmlp, int B,
-                      cudaStream_t s);
+size_t soca_mlp_bwd_scratch_floats(int B, int R);
+int soca_mlp_backward(const float* S, const float* dsvec, const float* mlp, int R, float* dS, float* dmlp, float* scratch,
+                      int B, cudaStream_t s);
 size_t lam_bwd_scratch_floats(int B, int N);
 int lam_backward(const float* stack, long long map_stride, const float* att, float gamma, const float* dout, float* dstack,
                  long long dmap_stride, float* dgamma, float* scratch, int N, int B, int HW, int C, cudaStream_t s);

@@ -173,47 +173,44 @@ __global__ void __launch_bounds__(64) soca_mlp_fwd_kernel(const float* __restric
   svec[blockIdx.x * 64 + threadIdx.x] = sg[threadIdx.x];
 }
 
-// one CTA walks the batch in order (deterministic parameter gradients); dS[b][i][j] = dv[j] / 64
+// one CTA per image: dS[b][i][j] = dv[j] / 64 and the image's parameter-gradient contribution part[b][W1 | b1 | W2 | b2];
+// soca_mlp_bwd_sum_kernel adds the contributions in batch order (deterministic)
 __global__ void __launch_bounds__(64)
 soca_mlp_bwd_kernel(const float* __restrict__ S, const float* __restrict__ dsvec, const float* __restrict__ mlp, int R,
-                    float* __restrict__ dS, float* __restrict__ dmlp, int B) {
+                    float* __restrict__ dS, float* __restrict__ part) {
   __shared__ float v[64], h[kSocaMaxR], sg[64], dpre[64], dh[kSocaMaxR];
-  __shared__ float gW1[kSocaMaxR * 64], gb1[kSocaMaxR], gW2[64 * kSocaMaxR], gb2[64];
-  const int t = threadIdx.x;
-  for (int i = t; i < R * 64; i += 64) { gW1[i] = 0.f; gW2[i] = 0.f; }
-  if (t < R) gb1[t] = 0.f;
-  gb2[t] = 0.f;
-  __syncthreads();
+  const int t = threadIdx.x, b = blockIdx.x;
+  const int npar = 2 * R * 64 + R + 64;
+  float* g = part + static_cast<size_t>(b) * npar;
   const float* w2 = mlp + R * 64 + R;
-  for (int b = 0; b < B; ++b) {
-    soca_mlp_eval(S + static_cast<size_t>(b) * 4096, mlp, R, v, h, sg);
-    dpre[t] = dsvec[b * 64 + t] * sg[t] * (1.f - sg[t]);
-    __syncthreads();
-    gb2[t] += dpre[t];
-    for (int r = 0; r < R; ++r) gW2[t * R + r] = fmaf(dpre[t], h[r], gW2[t * R + r]);
-    if (t < R) {
-      float a = 0.f;
-      for (int c = 0; c < 64; ++c) a = fmaf(w2[c * R + t], dpre[c], a);
-      dh[t] = h[t] > 0.f ? a : 0.f;
-    }
-    __syncthreads();
-    if (t < R) gb1[t] += dh[t];
-    float dv = 0.f;
-    for (int r = 0; r < R; ++r) {
-      gW1[r * 64 + t] = fmaf(dh[r], v[t], gW1[r * 64 + t]);
-      dv = fmaf(mlp[r * 64 + t], dh[r], dv);
-    }
-    dv *= (1.f / 64.f);
-    float* o = dS + static_cast<size_t>(b) * 4096;
-    for (int i = 0; i < 64; ++i) o[i * 64 + t] = dv;
-    __syncthreads();
+  soca_mlp_eval(S + static_cast<size_t>(b) * 4096, mlp, R, v, h, sg);
+  dpre[t] = dsvec[b * 64 + t] * sg[t] * (1.f - sg[t]);
+  __syncthreads();
+  g[R * 64 + R + 64 * R + t] = dpre[t];                                   // db2
+  for (int r = 0; r < R; ++r) g[R * 64 + R + t * R + r] = dpre[t] * h[r];  // dW2[t][r]
+  if (t < R) {
+    float a = 0.f;
+    for (int c = 0; c < 64; ++c) a = fmaf(w2[c * R + t], dpre[c], a);
+    dh[t] = h[t] > 0.f ? a : 0.f;
+    g[R * 64 + t] = dh[t];                                                 // db1
   }
-  for (int i = t; i < R * 64; i += 64) {
-    dmlp[i] = gW1[i];
-    dmlp[R * 64 + R + i] = gW2[i];
+  __syncthreads();
+  float dv = 0.f;
+  for (int r = 0; r < R; ++r) {
+    g[r * 64 + t] = dh[r] * v[t];                                          // dW1[r][t]
+    dv = fmaf(mlp[r * 64 + t], dh[r], dv);
   }
-  if (t < R) dmlp[R * 64 + t] = gb1[t];
-  dmlp[R * 64 + R + 64 * R + t] = gb2[t];
+  dv *= (1.f / 64.f);
+  float* o = dS + static_cast<size_t>(b) * 4096;
+  for (int i = 0; i < 64; ++i) o[i * 64 + t] = dv;
+}
+
+__global__ void soca_mlp_bwd_sum_kernel(const float* __restrict__ part, float* __restrict__ dmlp, int npar, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npar) return;
+  float t = 0.f;
+  for (int b = 0; b < B; ++b) t += part[static_cast<size_t>(b) * npar + i];
+  dmlp[i] = t;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -660,11 +657,15 @@ int soca_mlp_forward(const float* S, const float* mlp, int R, float* svec, int B
   return ok_or_cuda3();
 }
 
-int soca_mlp_backward(const float* S, const float* dsvec, const float* mlp, int R, float* dS, float* dmlp, int B,
-                      cudaStream_t s) {
+size_t soca_mlp_bwd_scratch_floats(int B, int R) { return static_cast<size_t>(B) * (2 * R * 64 + R + 64); }
+
+int soca_mlp_backward(const float* S, const float* dsvec, const float* mlp, int R, float* dS, float* dmlp, float* scratch,
+                      int B, cudaStream_t s) {
   if (R < 1 || R > kSocaMaxR) return DFIR_ERR_ARG;
   if (B <= 0) return DFIR_OK;
-  soca_mlp_bwd_kernel<<<1, 64, 0, s>>>(S, dsvec, mlp, R, dS, dmlp, B);
+  const int npar = 2 * R * 64 + R + 64;
+  soca_mlp_bwd_kernel<<<B, 64, 0, s>>>(S, dsvec, mlp, R, dS, scratch);
+  soca_mlp_bwd_sum_kernel<<<(npar + 255) / 256, 256, 0, s>>>(scratch, dmlp, npar, B);
   return ok_or_cuda3();
 }
 
@@ -759,10 +760,12 @@ int dfir_soca_mlp(const float* S, const float* mlp, int R, float* svec, int B, v
   if (S == nullptr || mlp == nullptr || svec == nullptr) return DFIR_ERR_ARG;
   return soca_mlp_forward(S, mlp, R, svec, B, SS(stream));
 }
+size_t dfir_soca_mlp_backward_scratch_bytes(int B, int R) { return soca_mlp_bwd_scratch_floats(B, R) * 4; }
 int dfir_soca_mlp_backward(const float* S, const float* grad_svec, const float* mlp, int R, float* grad_S, float* grad_mlp,
-                           int B, void* stream) {
+                           void* scratch, size_t scratch_bytes, int B, void* stream) {
   if (S == nullptr || grad_svec == nullptr || mlp == nullptr || grad_S == nullptr || grad_mlp == nullptr) return DFIR_ERR_ARG;
-  return soca_mlp_backward(S, grad_svec, mlp, R, grad_S, grad_mlp, B, SS(stream));
+  if (scratch == nullptr || scratch_bytes < dfir_soca_mlp_backward_scratch_bytes(B, R)) return DFIR_ERR_WORKSPACE;
+  return soca_mlp_backward(S, grad_svec, mlp, R, grad_S, grad_mlp, FP(scratch), B, SS(stream));
 }
 
 size_t dfir_lam_backward_scratch_bytes(int B, int N) { return lam_bwd_scratch_floats(B, N) * 4; }

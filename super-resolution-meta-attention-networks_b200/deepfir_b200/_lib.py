@@ -130,7 +130,8 @@ PROTOTYPES = {
     "dfir_channel_dot_scratch_bytes": (_sz, [_i, _i]),
     "dfir_channel_dot": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _sz, _i, _ll, _i, _vp]),
     "dfir_soca_mlp": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
-    "dfir_soca_mlp_backward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "dfir_soca_mlp_backward_scratch_bytes": (_sz, [_i, _i]),
+    "dfir_soca_mlp_backward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "dfir_lam_backward_scratch_bytes": (_sz, [_i, _i]),
     "dfir_lam_backward": (_i, [_vp, _ll, _vp, _f, _vp, _vp, _ll, _vp, _vp, _sz, _i, _i, _i, _i, _vp]),
     "dfir_csam_backward_scratch_bytes": (_sz, [_i, _i, _i, _i]),

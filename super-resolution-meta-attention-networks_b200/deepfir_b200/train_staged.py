@@ -158,8 +158,9 @@ class _Ops:
         """returns dL/dflow through the covariance path; gmlp: flat gradient of (W1, b1, W2, b2)"""
         B = self.B
         dS = torch.empty(B, 64, 64, **self.f32)
+        sc = self.scratch("socamlp", self.lib.dfir_soca_mlp_backward_scratch_bytes(B, R))
         _lib.check(self.lib.dfir_soca_mlp_backward(S.data_ptr(), dsvec.data_ptr(), mlp.data_ptr(), R, dS.data_ptr(),
-                                                   gmlp.data_ptr(), B, self.st), "soca mlp bwd")
+                                                   gmlp.data_ptr(), sc.data_ptr(), sc.numel(), B, self.st), "soca mlp bwd")
         dcov = torch.empty(B, 64, 64, **self.f32)
         sc = self.scratch("sqrtm", self.lib.dfir_sqrtm_scratch_bytes(B, 5))
         _lib.check(self.lib.dfir_sqrtm_backward(cov.data_ptr(), dS.data_ptr(), dcov.data_ptr(), sc.data_ptr(), sc.numel(), B,

@@ -297,8 +297,9 @@ def test_soca_mlp_forward_and_backward(B, R):
     assert L.dfir_soca_mlp(Sd.data_ptr(), mlp.data_ptr(), R, sv.data_ptr(), B, G.stream()) == 0
     dS = torch.full((B, 64, 64), float("nan"), device="cuda")
     dm = torch.full_like(mlp, float("nan"))
-    assert L.dfir_soca_mlp_backward(Sd.data_ptr(), gsd.data_ptr(), mlp.data_ptr(), R, dS.data_ptr(), dm.data_ptr(), B,
-                                    G.stream()) == 0
+    sc = _scratch(L.dfir_soca_mlp_backward_scratch_bytes(B, R))
+    assert L.dfir_soca_mlp_backward(Sd.data_ptr(), gsd.data_ptr(), mlp.data_ptr(), R, dS.data_ptr(), dm.data_ptr(), sc.data_ptr(),
+                                    sc.numel(), B, G.stream()) == 0
     G.sync()
     assert _rel(sv.cpu(), want.detach()) <= 1e-5
     assert _relg(dS.cpu(), leaves[0].grad) <= 1e-5
