@@ -10,8 +10,8 @@ pooling + Newton-Schulz square root + SOCA MLP, LAM, CSAM, the group / fusion co
 the flat gradient buffer of `PackedQrcan.enable_training`; `.grad` tensors are views of it and the optimizer, criterion and
 schedulers stay the reference's own torch objects.  Feature maps between stages are fp32 NHWC device tensors.
 
-The layers outside the trunk run fp32 kernels in both precision modes (they are < 5 % of the FLOPs); the trunk convs
-follow the network's `precision`.
+The trunk convs follow the network's `precision`; so do the 3x3 convs outside the trunk (bf16 mode: tensor-core operators per
+64-channel input chunk, fp32 mode: CUDA-core kernels).  The attention layers outside the trunk are fp32 in both modes.
 """
 import ctypes as C
 
@@ -69,9 +69,34 @@ class _Ops:
                                                       pk.precision, self.ws.data_ptr(), self.ws.numel(), self.st)
         _lib.check(rc, "qrcan_train_stage_backward(%d)" % stage)
 
-    # ---- 3x3 convs outside the trunk (fp32 kernels)
+    # ---- 3x3 convs outside the trunk.  bf16 mode, 64 output channels, Cin a multiple of 64: the tensor-core operators, one
+    # launch per 64-channel input chunk (forward: fp32 running sum chained through the skip input; data gradient: one
+    # transposed-weight conv per chunk; weight gradient: one tcgen05 wgrad per chunk).  Otherwise the fp32 CUDA-core kernels.
+    def _tc(self, conv):
+        return self.pk.precision == 0 and conv.out_channels == 64 and conv.in_channels % 64 == 0
+
+    def _chunks_bf16(self, x):
+        nc = x.shape[-1] // 64
+        xb = x.to(torch.bfloat16)
+        return [xb] if nc == 1 else [xb[..., i * 64:(i + 1) * 64].contiguous() for i in range(nc)]
+
     def conv_fwd(self, conv, x, skip=None):
         cin, cout = conv.in_channels, conv.out_channels
+        if self._tc(conv):
+            nc = cin // 64
+            w = conv.weight.detach()
+            out = self.feat(64)
+            junk = torch.empty(self.B, self.H, self.W, 64, device=self.dev, dtype=torch.bfloat16)
+            for i, chunk in enumerate(self._chunks_bf16(x)):
+                wi = w[:, i * 64:(i + 1) * 64].contiguous()
+                t = torch.empty(9 * 64 * 128, device=self.dev, dtype=torch.uint8)
+                _lib.check(self.lib.dfir_pack_conv3x3_bf16(wi.data_ptr(), t.data_ptr(), 64, 64, 64, 0, 1, self.st), "pack")
+                prev = skip if i == 0 else out
+                _lib.check(self.lib.dfir_conv3x3_c64_accumulate(chunk.data_ptr(), t.data_ptr(),
+                                                                conv.bias.detach().data_ptr() if i == nc - 1 else None,
+                                                                self.B, self.H, self.W, None, _ptr(prev), out.data_ptr(),
+                                                                junk.data_ptr(), 0, self.st), "conv tc")
+            return out
         w = torch.empty(9 * cin * cout, **self.f32)
         _lib.check(self.lib.dfir_pack_conv3x3_f32(conv.weight.detach().contiguous().data_ptr(), w.data_ptr(), cout, cin,
                                                   self.st), "pack")
@@ -83,6 +108,35 @@ class _Ops:
     def conv_bwd(self, conv, x, dy, gw, gb, need_dx=True):
         """weight / bias gradients into gw / gb (views of the flat gradient buffer), returns dL/dx"""
         cin, cout = conv.in_channels, conv.out_channels
+        if self._tc(conv):
+            nc = cin // 64
+            w = conv.weight.detach()
+            dyb = dy.to(torch.bfloat16)
+            n = self.lib.dfir_conv3x3_wgrad_scratch_bytes(self.B, self.H, self.W, 64, 64, 0)
+            sc = self.scratch("wgrad_tc", n)
+            junk = torch.empty(self.B, self.H, self.W, 64, device=self.dev, dtype=torch.bfloat16)
+            jb = torch.empty(64, **self.f32)
+            dxs = []
+            for i, chunk in enumerate(self._chunks_bf16(x)):
+                gwi = gw if nc == 1 else torch.empty(64, 64, 3, 3, **self.f32)
+                _lib.check(self.lib.dfir_conv3x3_wgrad_c64(dyb.data_ptr(), 0, 0, 0, chunk.data_ptr(), self.B, self.H, self.W,
+                                                           gwi.data_ptr(), (gb if i == 0 else jb).data_ptr(), 0, 1,
+                                                           sc.data_ptr(), sc.numel(), self.st), "wgrad tc")
+                if nc > 1:
+                    gw[:, i * 64:(i + 1) * 64].copy_(gwi)
+                if need_dx:
+                    wi = w[:, i * 64:(i + 1) * 64].contiguous()
+                    t = torch.empty(9 * 64 * 128, device=self.dev, dtype=torch.uint8)
+                    _lib.check(self.lib.dfir_pack_conv3x3_bf16_ex(wi.data_ptr(), t.data_ptr(), 64, 64, 0, 1, 1, self.st),
+                               "pack T")
+                    dxi = self.feat(64)
+                    _lib.check(self.lib.dfir_conv3x3_c64_dgrad(dyb.data_ptr(), 0, 0, 0, t.data_ptr(), None, None,
+                                                               dxi.data_ptr(), junk.data_ptr(), self.B, self.H, self.W,
+                                                               self.st), "dgrad tc")
+                    dxs.append(dxi)
+            if not need_dx:
+                return None
+            return dxs[0] if nc == 1 else torch.cat(dxs, dim=-1)
         n = self.lib.dfir_conv3x3_wgrad_scratch_bytes(self.B, self.H, self.W, cin, cout, 1)
         sc = self.scratch("wgrad", n)
         _lib.check(self.lib.dfir_conv3x3_wgrad_f32(dy.data_ptr(), x.data_ptr(), self.B, self.H, self.W, cin, cout,
