@@ -545,6 +545,31 @@ def other_configs(dev):
         torch.cuda.empty_cache()
     except Exception as e:
         out["qsan_c5"] = {"error": repr(e)[:200]}
+    # training step of the staged networks (Q-SAN 20 x 10, Q-HAN 10 x 20) at configs[3]'s batch shape, through run_train
+    for model in ("qsan", "qhan"):
+        key = model + "_train"
+        try:
+            torch.manual_seed(8)
+            h = ModelInterface.define_model(model, device=dev.index or 0, model_save_dir=tempfile.gettempdir(), eval_mode=False,
+                                            lr=1e-4, scale=4, metadata=["blur_kernel"], precision="bf16")
+            g = torch.Generator().manual_seed(8)
+            x = torch.rand(16, 3, 64, 64, generator=g).pin_memory()
+            y = torch.rand(16, 3, 256, 256, generator=g).pin_memory()
+            meta = torch.rand(16, 10, generator=g, dtype=torch.float64) * 0.4
+            keys = [("blur_kernel",) * 16] * 10
+            losses = []
+            step = lambda: losses.append(float(h.run_train(x, y, metadata=meta, metadata_keys=keys)[0]))
+            step()
+            step()   # (the optimizer re-homes the parameters in its first step: the second forward re-packs once more)
+            ms = timeit(step, 3)
+            out[key] = {"workload": "%s x4 bf16 training step (published depth), batch 16 x 64x64 LR patches, L1, Adam"
+                                    % ("Q-SAN" if model == "qsan" else "Q-HAN"),
+                        "ms_per_step": round(ms, 3), "loss_first_last": [round(losses[0], 5), round(losses[-1], 5)],
+                        "api": "%sHandler.run_train(x_pinned, y_pinned, metadata=, metadata_keys=)" % model.upper()}
+            del h
+            torch.cuda.empty_cache()
+        except Exception as e:
+            out[key] = {"error": repr(e)[:200]}
     return out
 
 
