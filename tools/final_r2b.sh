@@ -7,6 +7,7 @@ set -u
 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke_final.log 2>&1
 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_final.json 2> gpurun_out/bench_ref_final.err
+if [ -n "${NO_NCU:-}" ]; then tail -4 gpurun_out/pytest_final.log; tail -3 gpurun_out/smoke_final.log; cut -c1-400 gpurun_out/bench_final.json; exit 0; fi
 python tools/fwd_once.py 32 32 2 > gpurun_out/fwd_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r02b_launches_infer_32x128.csv \
   python tools/fwd_once.py 32 32 2 > gpurun_out/ncu_launches_b.log 2>&1
