@@ -414,10 +414,12 @@ class BaseModel(nn.Module):
         if self.learning_rate_scheduler is not None:
             self.learning_rate_scheduler.step()  # per batch, as in the reference (:488-489)
 
-    # run_eval returns a HOST tensor: with at least this many images the batch runs as two halves and the device -> host copy
-    # of the first half overlaps the forward of the second (an image's result does not depend on the rest of its batch,
-    # so the values are bit-identical).  100 MB of fp32 SR output per 32 x 512x512 images is 1.8 ms over PCIe.
-    overlap_d2h_min_batch = 16
+    # run_eval returns a HOST tensor.  Opt-in (set to a batch size): with at least this many images the batch runs as two
+    # halves and the device -> host copy of the first half overlaps the forward of the second (an image's result does not
+    # depend on the rest of its batch, so the values are bit-identical).  OFF by default: measured on B200 at 32 x 128x128 the
+    # copy that is hidden (0.9 of 1.8 ms) costs less than the second pass adds (421 more launches with their fill / drain:
+    # 327 -> 315 MPix/s end to end).  Worth it only where a forward is short against its result copy.
+    overlap_d2h_min_batch = None
 
     def run_eval(self, x, y=None, request_loss=False, tag=None, timing=False, keep_on_device=False, *args, **kwargs):
         if self.net.training:
@@ -451,7 +453,7 @@ class BaseModel(nn.Module):
         """[(x_half, tag_half, kwargs_half)] x 2 when the batch is large enough to overlap copy and compute, else None;
         tensors / lists in kwargs whose first dimension is the batch are split with it"""
         n = x.shape[0]
-        if n < self.overlap_d2h_min_batch or n % 2:
+        if self.overlap_d2h_min_batch is None or n < self.overlap_d2h_min_batch or n % 2:
             return None
         h = n // 2
         parts = []
