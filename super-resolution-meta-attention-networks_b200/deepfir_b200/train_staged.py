@@ -327,15 +327,13 @@ class _QsanTrain(torch.autograd.Function):
             g_res = op.feat()
             op.stage_bwd(gstruct, T_TAIL, gout=gout, gfeat_in=g_res)
             d_xx = op.nl_bwd(xx_last, g_res, prm, gprm, accumulate=False)
-            d_residual = None
+            d_residual = torch.zeros_like(d_xx)     # gradient of the share-source skip: sum over groups of gamma * d_xx
             ggamma = gv[id(net.gamma)]
             for g in reversed(range(len(net.RG))):
                 grp = net.RG[g]
                 xx, flow, cov, S, svec, mlp, R = saved[g]
                 # xx_next = f + gamma * residual,  f = conv_last(flow * svec) + xx
                 op.dot(d_xx, residual, total=ggamma, accumulate=True)   # (the flat buffer was zeroed above)
-                if d_residual is None:
-                    d_residual = torch.zeros_like(d_xx)
                 op.scale_add(d_residual, add=d_xx, alpha=gamma, out=d_residual)
                 y = op.scale_add(flow, svec=svec)
                 d_y = op.conv_bwd(grp.conv_last, y, d_xx, gv[id(grp.conv_last.weight)], gv[id(grp.conv_last.bias)])
@@ -350,7 +348,7 @@ class _QsanTrain(torch.autograd.Function):
                 d_in = op.feat()
                 op.stage_bwd(gstruct, T_GROUPS, g, g + 1, attr=attr, gfeat_out=d_flow, gfeat_in=d_in)
                 d_xx = op.scale_add(d_in, add=d_xx, alpha=1.0)
-            d_xx0 = op.scale_add(d_xx, add=d_residual, alpha=1.0) if d_residual is not None else d_xx
+            d_xx0 = op.scale_add(d_xx, add=d_residual, alpha=1.0)
             d_head = op.nl_bwd(head, d_xx0, prm, gprm, accumulate=True)
             d_head = op.scale_add(d_head, add=g_res, alpha=1.0)
             op.stage_bwd(gstruct, T_HEAD, x=x, gfeat_out=d_head)
