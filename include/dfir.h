@@ -157,6 +157,11 @@ int dfir_conv3x3_c64_scale_skip_hl8(const void* in_bf16, const void* wpacked, co
                                    const float* ca_params, int R, int M, int A, const float* attributes,
                                    const float* sq, int descending, void* stream);
 
+/* fp32 <-> the hi / 8-bit lo stream format above: hi [n] bf16, lo8 [n] int8, x [n] fp32 (n a multiple of 4).  decode(encode(x))
+ * = x rounded to 24 bits (ties away from zero). */
+int dfir_stream_encode_hl8(const float* x, void* hi, void* lo8, long long n, void* stream);
+int dfir_stream_decode_hl8(const void* hi, const void* lo8, float* x, long long n, void* stream);
+
 /* K-chunked convolutions for feature widths above 64 (Q-EDSR with 128/192/256 features, architectures.py:359-399):
  * a C -> C conv is a (C/64) x (C/64) block matrix of 64 -> 64 convs over 64-channel planes; the input-chunk sums are
  * accumulated in fp32 by re-launching the tensor-core kernel with the running sum as its skip input:
@@ -164,6 +169,13 @@ int dfir_conv3x3_c64_scale_skip_hl8(const void* in_bf16, const void* wpacked, co
  *     out_bf16 = bf16(out_f32)       (dense NHWC, 64 channels; out_f32 may be NULL and may alias skip_f32)
  * With svec = res_scale * meta scale and skip = the fp32 stream this is ParamResBlock's `res * y + x` (:352-355)
  * accumulated in place. */
+/* dfir_conv3x3_c64_accumulate with the running sum kept in the hi / 8-bit lo stream format (16 significant bits per
+ * accumulation step instead of fp32, 8 instead of 14 bytes of HBM traffic per element and the TMA-tile epilogue of
+ * dfir_conv3x3_c64_scale_skip_hl8):   out = conv(in) * svec[b] + bias * svec[b] + (skip_hi, skip_lo8)  [ReLU];
+ * out_hi = the bf16 operand of the next conv, out_lo8 may be NULL when only that is needed; out may alias skip. */
+int dfir_conv3x3_c64_accumulate_hl8(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
+                                    const float* svec, const void* skip_hi, const void* skip_lo8, void* out_hi, void* out_lo8,
+                                    int relu, void* stream);
 int dfir_conv3x3_c64_accumulate(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
                                 const float* svec, const float* skip_f32, float* out_f32, void* out_bf16, int relu,
                                 void* stream);

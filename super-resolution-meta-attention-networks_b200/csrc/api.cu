@@ -631,6 +631,36 @@ int dfir_conv3x3_c64_scale_skip_hl(const void* in_bf16, const void* wpacked, con
                            col_first, col_last, style, ca_params, R, M, A, attributes, sq, descending, stream);
 }
 
+int dfir_conv3x3_c64_accumulate_hl8(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
+                                    const float* svec, const void* skip_hi, const void* skip_lo8, void* out_hi, void* out_lo8,
+                                    int relu, void* stream) {
+  if (in_bf16 == nullptr || out_hi == nullptr || skip_hi == nullptr || skip_lo8 == nullptr) return DFIR_ERR_ARG;
+  ConvTcDesc d{};
+  d.B = B; d.H = H; d.W = W; d.cin_total = 64; d.cin_off = 0; d.cout = 64; d.epi = EPI_SCALE_SKIP_HL8; d.in_mode = IN_TMA;
+  d.in_bf16 = in_bf16; d.wpacked = wpacked; d.bias = bias; d.out_bf16 = out_hi; d.out_lo = out_lo8;
+  d.skip_hi = skip_hi; d.skip_lo = skip_lo8; d.relu_out = relu ? 1 : 0;
+  d.out_pix_stride = 128; d.out_row_stride = static_cast<long long>(W) * 128;
+  d.out_img_stride = static_cast<long long>(H) * W * 128;
+  d.svec = svec;
+  DFIR_TRY(dfir_check_device());
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return DFIR_ERR_CUDA;
+  d.num_sms = sms;
+  return conv3x3_c64_tc(d, S(stream));
+}
+
+int dfir_stream_encode_hl8(const float* x, void* hi, void* lo8, long long n, void* stream) {
+  if (x == nullptr || hi == nullptr || lo8 == nullptr) return DFIR_ERR_ARG;
+  return stream_encode_hl8(x, hi, lo8, n, S(stream));
+}
+
+int dfir_stream_decode_hl8(const void* hi, const void* lo8, float* x, long long n, void* stream) {
+  if (x == nullptr || hi == nullptr || lo8 == nullptr) return DFIR_ERR_ARG;
+  return stream_decode_hl8(hi, lo8, x, n, S(stream));
+}
+
 int dfir_conv3x3_c64_scale_skip_hl8(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
                                     const float* svec, const void* skip_hi, const void* skip_lo8, void* out_hi, void* out_lo8,
                                     const float* pool_rows, const float* col_first, const float* col_last, int style,

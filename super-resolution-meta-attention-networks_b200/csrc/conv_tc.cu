@@ -1045,8 +1045,12 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
                   // (sign-extended q) << 8 by one byte permute each: bytes [0, q, sign, sign]
                   const float x0 = __uint_as_float((hw[n] << 16) + prmt(lw[n], 0u, 0x8802u));
                   const float x1 = __uint_as_float((hw[n] & 0xffff0000u) + prmt(lw[n], 0u, 0x9912u));
-                  const float o0 = fmaf(__uint_as_float(src[4 * n + 2 * sl]), hl_s[2 * n], hl_bs[2 * n]) + x0;
-                  const float o1 = fmaf(__uint_as_float(src[4 * n + 2 * sl + 1]), hl_s[2 * n + 1], hl_bs[2 * n + 1]) + x1;
+                  float o0 = fmaf(__uint_as_float(src[4 * n + 2 * sl]), hl_s[2 * n], hl_bs[2 * n]) + x0;
+                  float o1 = fmaf(__uint_as_float(src[4 * n + 2 * sl + 1]), hl_s[2 * n + 1], hl_bs[2 * n + 1]) + x1;
+                  if (a.relu_out) {  // (last K-chunk of a wide conv + ReLU)
+                    o0 = fmaxf(o0, 0.f);
+                    o1 = fmaxf(o1, 0.f);
+                  }
                   const uint32_t t0 = __float_as_uint(o0) + 0x80u, t1 = __float_as_uint(o1) + 0x80u;  // round to 24 bits
                   const uint32_t b0 = (t0 + 0x8000u) & 0xffff0000u, b1 = (t1 + 0x8000u) & 0xffff0000u;   // nearest bf16
                   hw[n] = prmt(b0, b1, 0x7632u);
@@ -1626,7 +1630,7 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   const bool hl_mode = d.epi == EPI_SCALE_SKIP_HL || d.epi == EPI_SCALE_SKIP_HL8;
   const bool lo8 = d.epi == EPI_SCALE_SKIP_HL8;
   if (hl_mode && (fused || d.out_bf16 == nullptr || d.skip_hi == nullptr || d.skip_lo == nullptr || d.out_pix_stride != 128 ||
-                  d.out_row_stride != static_cast<long long>(d.W) * 128 || d.r_out != nullptr || d.relu_out))
+                  d.out_row_stride != static_cast<long long>(d.W) * 128 || d.r_out != nullptr || (d.relu_out && !lo8)))
     return DFIR_ERR_ARG;  // the stream planes are dense NHWC; training extras live on the fp32-stream epilogue
   if (d.epi_stats == 2 && (!hl_mode || d.istats == nullptr)) return DFIR_ERR_ARG;
   if ((d.epi == EPI_SCALE_SKIP || hl_mode) && d.epi_stats &&

@@ -166,6 +166,8 @@ int ca_from_stats(const float* pool_rows, const float* col_first, const float* c
                   const float* bias2, const AttnParams& ap, const float* attributes, const float* sq, float* svec, int B,
                   int H, int W, cudaStream_t s);
 // ---- Q-HAN / Q-SAN layers (san_han.cu)
+int stream_encode_hl8(const float* in, void* hi, void* lo8, long long n, cudaStream_t s);
+int stream_decode_hl8(const void* hi, const void* lo8, float* out, long long n, cudaStream_t s);
 int channel_scale(const float* x, const float* svec, const float* add, float alpha, float* out, int B, long long HW,
                   int C, cudaStream_t s);
 int lam_forward(const float* stack, long long map_stride, float gamma, float* out, float* scratch, int N, int B, int HW,

@@ -80,6 +80,9 @@ PROTOTYPES = {
                                             _i, _i, _vp, _vp, _i, _vp]),
     "dfir_conv3x3_c64_scale_skip_hl8": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i,
                                              _i, _i, _vp, _vp, _i, _vp]),
+    "dfir_conv3x3_c64_accumulate_hl8": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "dfir_stream_encode_hl8": (_i, [_vp, _vp, _vp, _ll, _vp]),
+    "dfir_stream_decode_hl8": (_i, [_vp, _vp, _vp, _ll, _vp]),
     "dfir_conv3x3_c64_accumulate": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "dfir_conv3x3_c64_tail": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "dfir_conv3x3_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -4,9 +4,11 @@ tensor cores.
 Reference: QEDSR / ParamResBlock (/root/reference/Code/SISR/models/attention_manipulators/architectures.py:332-399).
 Every activation is kept as C/64 planes of 64 channels (NHWC bf16 for the conv operands, fp32 for the residual stream),
 so a C -> C convolution is a (C/64) x (C/64) block matrix of the 64 -> 64 tcgen05 convolution; the sums over input
-chunks are accumulated in fp32 by chaining launches through the kernel's skip input (`dfir_conv3x3_c64_accumulate`).
-ParamResBlock's `conv2(.) * res_scale * meta + x` is accumulated in place on the fp32 stream, the upsampler's
-PixelShuffle is folded into the TMA store of the last chunk, the 256 -> 3 tail accumulates into the NCHW output.
+chunks are accumulated by chaining launches through the kernel's skip input — in the trunk on the hi / 8-bit lo stream format
+(`dfir_conv3x3_c64_accumulate_hl8`: 24-bit floats, 8 instead of 14 B per element and the TMA-tile epilogue), in the upsampler in
+fp32 (`dfir_conv3x3_c64_accumulate`).  ParamResBlock's `conv2(.) * res_scale * meta + x` is accumulated in place on the stream
+planes, the upsampler's PixelShuffle is folded into the TMA store of the last chunk, the 256 -> 3 tail accumulates into the NCHW
+output.
 No weights or activations take a detour through the CPU; all launches go to the caller's stream.
 """
 import ctypes as C
@@ -105,8 +107,15 @@ class WideQEDSR:
             dev, nc, r = self.dev, self.nc, self.r
             f32 = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
             bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
-            b = dict(Hs=[f32(B, H, W, 64) for _ in range(nc)], Hbf=[bf(B, H, W, 64) for _ in range(nc)],
-                     Xs=[f32(B, H, W, 64) for _ in range(nc)], Xbf=[bf(B, H, W, 64) for _ in range(nc)],
+            i8 = lambda *s: torch.empty(*s, device=dev, dtype=torch.int8)
+            # residual stream and partial sums in the hi / 8-bit lo format (24-bit floats: DESIGN.md section 3): H = head output,
+            # X = stream, P = partial sums of a K-chunk chain, Z = zeros (skip of a chain's first chunk)
+            b = dict(Hs=[f32(B, H, W, 64) for _ in range(nc)],
+                     Hhi=[bf(B, H, W, 64) for _ in range(nc)], Hlo=[i8(B, H, W, 64) for _ in range(nc)],
+                     Xhi=[bf(B, H, W, 64) for _ in range(nc)], Xlo=[i8(B, H, W, 64) for _ in range(nc)],
+                     Phi=bf(B, H, W, 64), Plo=i8(B, H, W, 64),
+                     Zhi=torch.zeros(B, H, W, 64, device=dev, dtype=torch.bfloat16),
+                     Zlo=torch.zeros(B, H, W, 64, device=dev, dtype=torch.int8),
                      T=[bf(B, H, W, 64) for _ in range(nc)], Fbf=[bf(B, H, W, 64) for _ in range(nc)],
                      sq=[f32(len(self.blocks), B, 64) for _ in range(nc)], U=[])
             h, w = H, W
@@ -153,41 +162,50 @@ class WideQEDSR:
         dev = x.device
         st = _st(dev)
         bufs = self._buffers(B, H, W)
-        Hs, Hbf, Xs, Xbf, T, Fbf, P, junk = (bufs[k] for k in ("Hs", "Hbf", "Xs", "Xbf", "T", "Fbf", "P", "junk"))
+        Hs, Hhi, Hlo, Xhi, Xlo, T, Fbf, P, junk = (bufs[k] for k in ("Hs", "Hhi", "Hlo", "Xhi", "Xlo", "T", "Fbf", "P", "junk"))
+        Phi, Plo, Zhi, Zlo = bufs["Phi"], bufs["Plo"], bufs["Zhi"], bufs["Zlo"]
         ptr = lambda t: None if t is None else t.data_ptr()
 
-        def acc(inp, w, bias, svec, skip, out32, outbf, relu, h, wd):
+        def acc(inp, w, bias, svec, skip, out32, outbf, relu, h, wd):   # fp32 running sum (upsampler stages)
             _lib.check(lib.dfir_conv3x3_c64_accumulate(inp.data_ptr(), w.data_ptr(), ptr(bias), B, h, wd, ptr(svec), ptr(skip),
                                                        ptr(out32), outbf.data_ptr(), relu, st), "wide conv")
 
+        def acc8(inp, w, bias, svec, skip, out, relu):   # running sum in the hi / 8-bit lo format; skip, out = (hi, lo8)
+            _lib.check(lib.dfir_conv3x3_c64_accumulate_hl8(inp.data_ptr(), w.data_ptr(), ptr(bias), B, H, W, ptr(svec),
+                                                           skip[0].data_ptr(), skip[1].data_ptr(), out[0].data_ptr(),
+                                                           ptr(out[1]), relu, st), "wide conv hl8")
+
         nblk = len(self.blocks)
+        npl = B * H * W * 64
         for j in range(nc):
             _lib.check(lib.dfir_head_conv(x.data_ptr(), self.head_w[j].data_ptr(), self.head_b[j].data_ptr(),
-                                          Hs[j].data_ptr(), Hbf[j].data_ptr(), B, self.in_feats, H, W, 64, st), "wide head")
+                                          Hs[j].data_ptr(), None, B, self.in_feats, H, W, 64, st), "wide head")
+            _lib.check(lib.dfir_stream_encode_hl8(Hs[j].data_ptr(), Hhi[j].data_ptr(), Hlo[j].data_ptr(), npl, st), "encode")
             w1, b1, w2, b2 = self.meta[j]
             _lib.check(lib.dfir_meta_attention(attr.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
                                                bufs["sq"][j].data_ptr(), nblk, B, self.M, self.hid, 64, self.meta_relu,
                                                None, self.res_scale, st), "wide meta")
+        Pp, Zp = (Phi, Plo), (Zhi, Zlo)
         for k, ((w1t, b1), (w2t, b2)) in enumerate(self.blocks):
-            xin = Hbf if k == 0 else Xbf
-            xskip = Hs if k == 0 else Xs
+            xin = Hhi if k == 0 else Xhi
             for j in range(nc):  # t_j = relu(sum_i conv(x_i, W1[j][i]) + b1_j)
                 for i in range(nc):
                     last = i == nc - 1
-                    acc(xin[i], w1t[j][i], b1[j] if last else None, None, None if i == 0 else P,
-                        None if last else P, T[j] if last else junk, 1 if last else 0, H, W)
-            for j in range(nc):  # x_j <- sum_i conv(t_i, W2[j][i]) * s_j + b2_j * s_j + x_j  (in place, fp32)
+                    acc8(xin[i], w1t[j][i], b1[j] if last else None, None, Zp if i == 0 else Pp,
+                         (T[j], None) if last else Pp, 1 if last else 0)
+            for j in range(nc):  # x_j <- sum_i conv(t_i, W2[j][i]) * s_j + b2_j * s_j + x_j  (in place on the stream planes)
                 s_j = bufs["sq"][j][k]
+                xj = (Xhi[j], Xlo[j])
                 for i in range(nc):
-                    acc(T[i], w2t[j][i], b2[j] if i == nc - 1 else None, s_j, xskip[j] if i == 0 else Xs[j], Xs[j], Xbf[j],
-                        0, H, W)
+                    acc8(T[i], w2t[j][i], b2[j] if i == nc - 1 else None, s_j,
+                         ((Hhi[j], Hlo[j]) if k == 0 else xj) if i == 0 else xj, xj, 0)
         wft, bfin = self.final
-        src = Xbf if nblk > 0 else Hbf
+        src = Xhi if nblk > 0 else Hhi
         for j in range(nc):  # trunk tail conv + head skip
             for i in range(nc):
                 last = i == nc - 1
-                acc(src[i], wft[j][i], bfin[j] if last else None, None, Hs[j] if i == 0 else P, None if last else P,
-                    Fbf[j] if last else junk, 0, H, W)
+                acc8(src[i], wft[j][i], bfin[j] if last else None, None, (Hhi[j], Hlo[j]) if i == 0 else Pp,
+                     (Fbf[j], None) if last else Pp, 0)
         cur, h, wd = Fbf, H, W
         for (wu, bu), U in zip(self.ups, bufs["U"]):
             oh, ow = h * r, wd * r
@@ -210,4 +228,4 @@ class WideQEDSR:
 
     def launch_count(self):
         nc, rr = self.nc, self.r * self.r
-        return 2 * nc + len(self.blocks) * 2 * nc * nc + nc * nc + len(self.ups) * nc * rr * nc + nc
+        return 3 * nc + len(self.blocks) * 2 * nc * nc + nc * nc + len(self.ups) * nc * rr * nc + nc
