@@ -207,6 +207,11 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   // Descending traversal (hi + lo stream, nseg == 1): the pipeline runs on VIRTUAL coordinates (image B-1-b, row H-1-y,
   // kernel row 2-dy: a vertically flipped problem, ascending); only the addresses at the edges are mirrored.
   const bool flip = kHL && a.flip != 0;
+  // Register reallocation (setmaxnreg): the kernel launches with 128 registers per thread (448 threads); the four loader
+  // warps (physical warps 4-7, one aligned warpgroup) give registers back, the two epilogue groups (physical warps 0-3 and
+  // 8-11) take them: 8192 unallocated + 4 x 32 x (128 - 72) released = 15360 >= 8 x 32 x (184 - 128) = 14336.
+  constexpr bool kRegRealloc = kLo8 && two_epilogue_groups<EPI, INMODE>();
+  constexpr int kLoaderRegs = 72, kEpilogueRegs = 184;
   constexpr int kHS = kLo8 ? kHl8Slots : kHlSlots;            // stream-tile buffers per epilogue warp
   constexpr int kHI = kLo8 ? kHl8ItemBytes : kHlItemBytes;    // bytes of one buffer
   constexpr int kScratchShift = kHL ? (kLo8 ? L::hl8_scratch_shift : L::hl_scratch_shift) : 0;
@@ -302,10 +307,12 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   const bool exp_no_tile = (a.debug_probe & 4096) != 0;    // scale+skip epilogue: TMEM reads and barriers only
   const bool exp_no_pass = (a.debug_probe & 8192) != 0;    // scale+skip epilogue: no coalesced pass
   const bool trace_on = (a.debug_probe & 32768) != 0 && blockIdx.x == gridDim.x / 2;
+  // (PROBES build) bit 262144: the columns of epilogue group 1 record the tile loop of group 0 instead (HL epilogues)
+  const bool tile_probe = (a.debug_probe & 262144) != 0;
 #else
   constexpr bool probe = false, exp_skip_store = false, exp_one_copy = false, exp_no_copy = false, exp_no_epi = false,
                  exp_no_skipld = false, exp_no_f32st = false, exp_no_bfst = false,
-                 exp_no_pf = false, exp_no_tile = false, exp_no_pass = false;
+                 exp_no_pf = false, exp_no_tile = false, exp_no_pass = false, tile_probe = false;
 #endif
 
   if (g0 < g1) {
@@ -444,6 +451,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       __syncwarp();
     } else if (warp >= 6 && warp < 10) {
       // ===================== A loaders: smem ring row -> 3 dx-shifted copies in TMEM =====================
+      if constexpr (kRegRealloc) setmaxnreg_dec<kLoaderRegs>();
       const int q = pwarp & 3;       // TMEM lane quarter this warp may access
       const int m = q * 32 + lane;   // output pixel = TMEM lane
       // Row n is the LAST A row some output row waits for (its bottom row) iff it is at least the third row of its
@@ -628,6 +636,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       // against 1.3 us of the MMA pipeline (conv1 48.7 us vs 38 us without the statistics), same remedy.
       constexpr bool kTwoEpi = two_epilogue_groups<EPI, INMODE>();
       constexpr int kEpiGroups = kTwoEpi ? 2 : 1;
+      if constexpr (kRegRealloc) setmaxnreg_inc<kEpilogueRegs>();
       const int egrp = (kTwoEpi && warp >= 10) ? 1 : 0;
       const int q = pwarp & 3;         // TMEM lane quarter this warp may read
       const int m = q * 32 + lane;     // pixel within the 128-px row segment
@@ -955,9 +964,9 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             }
           }
         }
-        if (q == 0) DFIR_TRACE(8 + 3 * egrp, it >> (kTwoEpi ? 1 : 0));  // epilogue: waiting for the accumulator
+        if (q == 0 && !(tile_probe && egrp == 1)) DFIR_TRACE(8 + 3 * egrp, it >> (kTwoEpi ? 1 : 0));  // epilogue: waiting for the accumulator
         mbar_wait(&tfull[acc], (it / kAcc) & 1, 8);
-        if (q == 0) DFIR_TRACE(9 + 3 * egrp, it >> (kTwoEpi ? 1 : 0));  // epilogue: accumulator complete
+        if (q == 0 && !(tile_probe && egrp == 1)) DFIR_TRACE(9 + 3 * egrp, it >> (kTwoEpi ? 1 : 0));  // epilogue: accumulator complete
         tcgen05_fence_after();
         if (exp_no_epi) {
           tcgen05_fence_before();
@@ -989,7 +998,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&go[acc]);  // accumulator back to the MMA thread
-          if (q == 0) DFIR_TRACE(10 + 3 * egrp, it >> 1);
+          if (q == 0 && !(tile_probe && egrp == 1)) DFIR_TRACE(10 + 3 * egrp, it >> 1);
           const int pr = lane >> 2, cq = lane & 3;
           if (b != cur_img) {  // (uniform) new image: this thread's 16 scale / bias * scale values
 #pragma unroll
@@ -1015,7 +1024,9 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               if (kLo8 && !a.hl_ahead3) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
               hl_issue();
             }
+            if (tile_probe && q == 0 && egrp == 0 && half == 0) DFIR_TRACE(11, it >> 1);  // next load issued
             mbar_wait(&hl_bar[hl_slot], hl_phase, 10);
+            if (tile_probe && q == 0 && egrp == 0 && half == 0) DFIR_TRACE(12, it >> 1);  // tile landed
             // word (pixel p, channels 8 n + 2 cq + {0,1}) of a tile: p * 128 + ((n ^ (p & 7)) << 4) + 4 cq (TMA 128B swizzle)
             uint8_t* wbase = buf + pr * 128 + 4 * cq;
 #pragma unroll
@@ -1085,8 +1096,10 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               }
               }
             }
+            if (tile_probe && q == 0 && egrp == 0 && half == 0) DFIR_TRACE(13, it >> 1);  // tile updated
             fence_proxy_async_smem();
             __syncwarp();
+            if (tile_probe && q == 0 && egrp == 0 && half == 1) DFIR_TRACE(15, it >> 1);  // second tile fenced
             if (lane == 0) {
               const int xs = seg * 128 + q * 32 + half * 16;
               const int ya = flip ? H - 1 - y : y, ba = flip ? a.B - 1 - b : b;
@@ -1108,7 +1121,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               hl_phase ^= 1;
             }
           }
-          if (q == 0) DFIR_TRACE(14 + egrp, it >> 1);
+          if (q == 0 && !(tile_probe && egrp == 1)) DFIR_TRACE(14 + egrp, it >> 1);
         } else if constexpr (EPI == EPI_SCALE_SKIP) {
           // Per half of 32 channels: v = acc * s + bias * s (or r = acc + bias when the training forward saves r) into
           // an fp32 tile in smem (chunk-rotated: conflict free for the pixel-major writes and the coalesced reads),

@@ -288,4 +288,15 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int m, int n) {
 }
 
 }  // namespace ptx
+// Register reallocation between the warpgroups of a warp-specialised kernel (sm_90+): every warp of an aligned group of four
+// warps executes the same instruction; .inc blocks until other warpgroups have released enough registers with .dec.
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 }  // namespace dfir

@@ -27,6 +27,7 @@ pool = torch.empty(bc, LR, 64, device=dev); cf = torch.empty(bc, LR, 64, device=
 sv = torch.rand(bc, 64, device=dev)
 xh = torch.randn(bc, LR, LR, 64, device=dev).to(torch.bfloat16)
 xl = (torch.randn(bc, LR, LR, 64, device=dev) * 1e-3).to(torch.bfloat16)
+xl8 = torch.randint(-128, 128, (bc, LR, LR, 64), device=dev, dtype=torch.int8)
 pool.normal_(); cf.normal_(); cl.normal_()
 blob = torch.randn(4 * 74 + 4 + 64 * 4 + 64, device=dev) / 8
 attr = torch.rand(bc, 10, device=dev); sq = torch.rand(bc, 64, device=dev) * 0.1
@@ -40,6 +41,15 @@ def launch():
     elif mode == "stats":
         _lib.check(lib.dfir_conv3x3_c64_stats(a.data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR, b.data_ptr(),
                                               pool.data_ptr(), cf.data_ptr(), cl.data_ptr(), st()), "c1")
+    elif mode in ("sshl8", "sshl8stats"):
+        stats = mode == "sshl8stats"
+        _lib.check(lib.dfir_conv3x3_c64_scale_skip_hl8(a.data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR,
+                                                       None if stats else sv.data_ptr(), xh.data_ptr(), xl8.data_ptr(),
+                                                       xh.data_ptr(), xl8.data_ptr(), pool.data_ptr() if stats else None,
+                                                       cf.data_ptr() if stats else None, cl.data_ptr() if stats else None,
+                                                       1 if stats else 0, blob.data_ptr() if stats else None, 4, 10, 10,
+                                                       attr.data_ptr() if stats else None, sq.data_ptr() if stats else None,
+                                                       int(os.environ.get("DESC", "0")), st()), "sshl8")
     elif mode in ("sshl", "sshlstats"):
         stats = mode == "sshlstats"
         _lib.check(lib.dfir_conv3x3_c64_scale_skip_hl(a.data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR,
@@ -67,6 +77,9 @@ tr = [[buf[k * 64 + i] for i in range(64)] for k in range(16)]
 t0 = min(v for row in tr for v in row if v)
 names = ["tma_issue", "ld_full", "ld_aempty", "ld_done", "mma_top", "mma_24", "mma_waited", "mma_36", "e0_wait", "e0_tfull",
          "e0_release", "e1_wait", "e1_tfull", "e1_release", "e0_end", "e1_end"]
+if int(os.environ.get("EXTRA_PROBE", "0")) & 262144:   # tile loop of epilogue group 0 (first tile of each row)
+    names[11:14] = ["t_issued", "t_landed", "t_updated"]
+    names[15] = "t2_fenced"
 if mode in ("conv1", "stats"):
     names[11:14] = ["e0_stfree", "e0_staged", "e0_sums"]
     names[15] = "e0_bar2"
