@@ -208,10 +208,12 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   // kernel row 2-dy: a vertically flipped problem, ascending); only the addresses at the edges are mirrored.
   const bool flip = kHL && a.flip != 0;
   // Register reallocation (setmaxnreg): the kernel launches with 128 registers per thread (448 threads); the four loader
-  // warps (physical warps 4-7, one aligned warpgroup) give registers back, the two epilogue groups (physical warps 0-3 and
-  // 8-11) take them: 8192 unallocated + 4 x 32 x (128 - 72) released = 15360 >= 8 x 32 x (184 - 128) = 14336.
+  // warps (physical warps 4-7, one aligned warpgroup) give registers back to the CTA's pool, the two epilogue groups
+  // (physical warps 0-3 and 8-11) take them.  The pool is the CTA's own allocation (registers the SM has left over are NOT
+  // in it: a first version that counted on them deadlocked in setmaxnreg.inc), so the books must balance inside the CTA:
+  // 4 x 32 x (128 - 64) released = 8192 = 8 x 32 x (160 - 128) taken.
   constexpr bool kRegRealloc = kLo8 && two_epilogue_groups<EPI, INMODE>();
-  constexpr int kLoaderRegs = 72, kEpilogueRegs = 184;
+  constexpr int kLoaderRegs = 64, kEpilogueRegs = 160;
   constexpr int kHS = kLo8 ? kHl8Slots : kHlSlots;            // stream-tile buffers per epilogue warp
   constexpr int kHI = kLo8 ? kHl8ItemBytes : kHlItemBytes;    // bytes of one buffer
   constexpr int kScratchShift = kHL ? (kLo8 ? L::hl8_scratch_shift : L::hl_scratch_shift) : 0;
