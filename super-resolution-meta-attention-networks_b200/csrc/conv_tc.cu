@@ -105,8 +105,8 @@ constexpr int kThreadsTwoEpi = 320 + 128;    // EPI_SCALE_SKIP / EPI_RELU_STATS 
 constexpr const char* kDefaultL2Policy = "nnnnnn";  // see conv3x3_c64_tc(): overridden by DFIR_L2_POLICY
 constexpr int kHlSlots = 3;                  // EPI_SCALE_SKIP_HL: stream-tile buffers per epilogue warp (1 in use, 2 in flight)
 constexpr int kHlItemBytes = 4096;           // one tile: 16 px x 64 ch bf16 hi (2 KB) + lo (2 KB)
-constexpr int kHl8Slots = 4;                 // EPI_SCALE_SKIP_HL8: the 3 KB tiles (hi 2 KB + 8-bit lo 1 KB) leave room for a 4th
-constexpr int kHl8ItemBytes = 3072;          //   buffer: a store may still drain while two loads are in flight
+constexpr int kHl8Slots = 2;                 // EPI_SCALE_SKIP_HL8: ONE tile per warp and row (its 32 pixels: hi 4 KB + 8-bit lo 2 KB),
+constexpr int kHl8ItemBytes = 6144;          //   two buffers: issuing a TMA operation costs the warp ~200 clk, so half as many
 constexpr int kMaxBandImages = 8;            // a CTA's row band may touch at most this many images (IN_FUSED)
 constexpr int kAttnScratchFloats = 64 + 64 + 512 + 1024 + 4;  // attention scratch of one epilogue group
 constexpr int kCaStageFloats = 704;          // QCALayer parameter blobs up to this size are staged in shared memory
@@ -128,7 +128,7 @@ struct SmemLayout {
   static_assert(off_cap + kCaStageFloats * 4 <= off_stage + 2 * kStageBytes, "prologue scratch must fit the staging tiles");
   static constexpr int off_svec = off_pool + 12 * 64 * 4;  // (2 groups x [4 warp sums | first column | last column] x 64)
   static constexpr int off_bars = off_svec + kMaxBandImages * 64 * 4;
-  static constexpr int n_bars = 2 * kSlots + kARows + 2 * kAcc + 1 + 8 * kHl8Slots;
+  static constexpr int n_bars = 2 * kSlots + kARows + 2 * kAcc + 1 + 8 * (kHlSlots > kHl8Slots ? kHlSlots : kHl8Slots);
   // EPI_SCALE_SKIP_HL: the 96 KB of the staging tiles + skip buffers hold, slot-major, kHlSlots x 8 warps x (2 KB hi +
   // 2 KB lo) stream tiles of 16 pixels; the prologue scratch aliases the last slot (first used after the prologue)
   static constexpr int off_hl = off_stage;
@@ -202,7 +202,9 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   float* pool_s = reinterpret_cast<float*>(smem + L::off_pool);
   constexpr bool kHL = EPI == EPI_SCALE_SKIP_HL || EPI == EPI_SCALE_SKIP_HL8;  // hi + lo stream epilogue
   constexpr bool kLo8 = EPI == EPI_SCALE_SKIP_HL8;                             // ... with the 8-bit lo plane
-  constexpr int kHlLoBytes = kLo8 ? 1024 : 2048;                               // lo part of a stream tile
+  constexpr int kTilePx = kLo8 ? 32 : 16;                                      // pixels of a stream tile
+  constexpr int kHlHiBytes = kTilePx * 128;                                    // hi part of a stream tile
+  constexpr int kHlLoBytes = kLo8 ? kTilePx * 64 : kTilePx * 128;              // lo part of a stream tile
   constexpr bool kScaleSkip = EPI == EPI_SCALE_SKIP || kHL;
   // Descending traversal (hi + lo stream, nseg == 1): the pipeline runs on VIRTUAL coordinates (image B-1-b, row H-1-y,
   // kernel row 2-dy: a vertically flipped problem, ascending); only the addresses at the edges are mirrored.
@@ -668,12 +670,12 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       auto hl_issue = [&]() {  // lane 0: request the next tile (if any) into the next slot
         if (hl_lg < g1) {
           uint8_t* dst = hl_base + hl_lslot * (8 * kHI);
-          const int xs = hl_lseg * 128 + q * 32 + hl_lhalf * 16;
-          mbar_arrive_expect_tx(&hl_bar[hl_lslot], 2048 + kHlLoBytes);
+          const int xs = hl_lseg * 128 + q * 32 + hl_lhalf * kTilePx;
+          mbar_arrive_expect_tx(&hl_bar[hl_lslot], kHlHiBytes + kHlLoBytes);
           const int ya = flip ? H - 1 - hl_ly : hl_ly, ba = flip ? a.B - 1 - hl_lb : hl_lb;
           tma_load_4d(dst, &hl.m[0], &hl_bar[hl_lslot], 0, xs, ya, ba);
-          if (a.use_hints) tma_load_4d_hint(dst + 2048, &hl.m[1], &hl_bar[hl_lslot], 0, xs, ya, ba, a.pol_skip);
-          else tma_load_4d(dst + 2048, &hl.m[1], &hl_bar[hl_lslot], 0, xs, ya, ba);
+          if (a.use_hints) tma_load_4d_hint(dst + kHlHiBytes, &hl.m[1], &hl_bar[hl_lslot], 0, xs, ya, ba, a.pol_skip);
+          else tma_load_4d(dst + kHlHiBytes, &hl.m[1], &hl_bar[hl_lslot], 0, xs, ya, ba);
           // A/B (DFIR_DEBUG_PROBE bit 65536): L2 prefetch of the tile two rows of this warp further down.  Measured: 62.2 ->
           // 67.9 us per launch — the kernel is HBM-bandwidth bound, not latency bound; default off.
           if ((a.debug_probe & 65536) != 0 && hl_ly + 2 * kEpiGroups < H && hl_lg + 2 * kEpiGroups < g1) {
@@ -683,7 +685,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           }
         }
         if (++hl_lslot == kHS) hl_lslot = 0;
-        if (++hl_lhalf == 2) {
+        if (++hl_lhalf == 32 / kTilePx) {
           hl_lhalf = 0;
           hl_lg += kEpiGroups;
           hl_ly += kEpiGroups;
@@ -716,10 +718,9 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         }
         grid_dep_wait();
         if constexpr (kHL) {
-          if (lane == 0) {  // the first two (three) tiles travel while the attention vector is evaluated
-            hl_issue();
-            hl_issue();
-            if (kLo8 && a.hl_ahead3) hl_issue();
+          if (lane == 0) {  // the first tiles travel while the attention vector is evaluated (8-bit lo: one tile = one row;
+            hl_issue();     // the second buffer is the prologue's scratch until the barrier that ends the prologue)
+            if (!kLo8) hl_issue();
           }
         }
         if (a.epi_stats) {
@@ -1017,20 +1018,23 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           }
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
+            // 16-pixel tiles (bf16 lo): a tile per half; 32-pixel tiles (8-bit lo): one tile per row, entered at half 0
+            const bool tile_start = kTilePx == 16 || half == 0, tile_end = kTilePx == 16 || half == 1;
             uint8_t* buf = hl_base + hl_slot * (8 * kHI);
             const bool late_issue = !kLo8 && (a.debug_probe & 131072) != 0;  // A/B switch (DFIR_DEBUG_PROBE)
-            if (lane == 0 && !late_issue) {
-              // three buffers: the previous tile must have left its buffer, which takes the tile after next.  Four buffers
-              // (8-bit lo): the buffer to refill was stored two tiles ago, so the latest store may still be draining - or,
-              // with three loads in flight (hl_ahead3), the same rule as with three buffers.
-              if (kLo8 && !a.hl_ahead3) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
-              hl_issue();
+            if (tile_start) {
+              if (lane == 0 && !late_issue) {
+                // the previous tile must have left its buffer (its store has read it), which takes the tile after next
+                // (three buffers of 16 pixels) / the next row's tile (two buffers of 32 pixels)
+                tma_store_wait_read<0>();
+                hl_issue();
+              }
+              if (tile_probe && q == 0 && egrp == 0 && half == 0) DFIR_TRACE(11, it >> 1);  // next load issued
+              mbar_wait(&hl_bar[hl_slot], hl_phase, 10);
+              if (tile_probe && q == 0 && egrp == 0 && half == 0) DFIR_TRACE(12, it >> 1);  // tile landed
             }
-            if (tile_probe && q == 0 && egrp == 0 && half == 0) DFIR_TRACE(11, it >> 1);  // next load issued
-            mbar_wait(&hl_bar[hl_slot], hl_phase, 10);
-            if (tile_probe && q == 0 && egrp == 0 && half == 0) DFIR_TRACE(12, it >> 1);  // tile landed
             // word (pixel p, channels 8 n + 2 cq + {0,1}) of a tile: p * 128 + ((n ^ (p & 7)) << 4) + 4 cq (TMA 128B swizzle)
-            uint8_t* wbase = buf + pr * 128 + 4 * cq;
+            uint8_t* wbase = buf + pr * 128 + 4 * cq + (kTilePx == 32 ? half * 2048 : 0);
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl) {
               // all 16 loads of a pixel first, then the arithmetic, then the 16 stores: written as load / update / store
@@ -1044,8 +1048,8 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
                 // arithmetic, no conversions.  Tile of 16 px x 64 B, TMA SWIZZLE_64B: pixel p, byte c at
                 // p * 64 + (((c >> 4) ^ ((p >> 1) & 3)) << 4) + (c & 15); this thread's two channels 8 n + 2 cq + {0, 1} of pixel
                 // p = pr + 8 sl are one 16-bit word.
-                const int p = pr + 8 * sl;
-                uint8_t* lbase = buf + 2048 + p * 64 + 2 * cq;
+                const int p = pr + 8 * sl + (kTilePx == 32 ? 16 * half : 0);
+                uint8_t* lbase = buf + kHlHiBytes + p * 64 + 2 * cq;
                 const int sw = (p >> 1) & 3;
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
@@ -1098,19 +1102,20 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               }
               }
             }
-            if (tile_probe && q == 0 && egrp == 0 && half == 0) DFIR_TRACE(13, it >> 1);  // tile updated
+            if (tile_probe && q == 0 && egrp == 0 && half == 0) DFIR_TRACE(13, it >> 1);  // tile (half) updated
+            if (!tile_end) continue;
             fence_proxy_async_smem();
             __syncwarp();
-            if (tile_probe && q == 0 && egrp == 0 && half == 1) DFIR_TRACE(15, it >> 1);  // second tile fenced
+            if (tile_probe && q == 0 && egrp == 0 && half == 1) DFIR_TRACE(15, it >> 1);  // last tile of the row fenced
             if (lane == 0) {
-              const int xs = seg * 128 + q * 32 + half * 16;
+              const int xs = seg * 128 + q * 32 + (kTilePx == 16 ? half * 16 : 0);
               const int ya = flip ? H - 1 - y : y, ba = flip ? a.B - 1 - b : b;
               if (a.use_hints) {
                 tma_store_4d_hint(&hl.m[2], buf, 0, xs, ya, ba, a.pol_out);
-                if (a.hl_store_lo) tma_store_4d_hint(&hl.m[3], buf + 2048, 0, xs, ya, ba, a.pol_f32);
+                if (a.hl_store_lo) tma_store_4d_hint(&hl.m[3], buf + kHlHiBytes, 0, xs, ya, ba, a.pol_f32);
               } else {
                 tma_store_4d(&hl.m[2], buf, 0, xs, ya, ba);
-                if (a.hl_store_lo) tma_store_4d(&hl.m[3], buf + 2048, 0, xs, ya, ba);
+                if (a.hl_store_lo) tma_store_4d(&hl.m[3], buf + kHlHiBytes, 0, xs, ya, ba);
               }
               tma_store_commit();
               if (late_issue) {
@@ -1681,8 +1686,8 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
     const void* planes[4] = {d.skip_hi, d.skip_lo, d.out_bf16, d.out_lo != nullptr ? d.out_lo : d.out_bf16};
     for (int i = 0; i < 4; ++i) {
       const bool lo_plane = (i & 1) != 0 && !(i == 3 && d.out_lo == nullptr);
-      rc = (lo8 && lo_plane) ? make_tmap_nhwc_u8(&hl.m[i], planes[i], 64, d.W, d.H, d.B, 16)
-                             : make_tmap_nhwc_bf16(&hl.m[i], planes[i], 64, d.W, d.H, d.B, 128, rowB, imgB, 16);
+      rc = (lo8 && lo_plane) ? make_tmap_nhwc_u8(&hl.m[i], planes[i], 64, d.W, d.H, d.B, 32)
+                             : make_tmap_nhwc_bf16(&hl.m[i], planes[i], 64, d.W, d.H, d.B, 128, rowB, imgB, lo8 ? 32 : 16);
       if (rc != DFIR_OK) return rc;
     }
   } else {
