@@ -214,7 +214,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   // (physical warps 0-3 and 8-11) take them.  The pool is the CTA's own allocation (registers the SM has left over are NOT
   // in it: a first version that counted on them deadlocked in setmaxnreg.inc), so the books must balance inside the CTA:
   // 4 x 32 x (128 - 64) released = 8192 = 8 x 32 x (160 - 128) taken.
-  constexpr bool kRegRealloc = kLo8 && two_epilogue_groups<EPI, INMODE>();
+  constexpr bool kRegRealloc = two_epilogue_groups<EPI, INMODE>();
   constexpr int kLoaderRegs = 64, kEpilogueRegs = 160;
   constexpr int kHS = kLo8 ? kHl8Slots : kHlSlots;            // stream-tile buffers per epilogue warp
   constexpr int kHI = kLo8 ? kHl8ItemBytes : kHlItemBytes;    // bytes of one buffer
