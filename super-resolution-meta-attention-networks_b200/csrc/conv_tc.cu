@@ -1695,8 +1695,6 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   }
   ConvTcArgs a{};
   a.hl_store_lo = d.out_lo != nullptr ? 1 : 0;
-  static const int hl_ahead = getenv("DFIR_HL_AHEAD") == nullptr ? 2 : atoi(getenv("DFIR_HL_AHEAD"));
-  a.hl_ahead3 = hl_ahead >= 3 ? 1 : 0;
   a.flip = (hl_mode && d.flip && d.W <= 128) ? 1 : 0;
   a.istats = d.istats;
   a.istats_clear = d.istats_clear;

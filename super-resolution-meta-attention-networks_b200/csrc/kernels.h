@@ -68,7 +68,6 @@ struct ConvTcArgs {  // kernel argument block
   const void* next_w;       // packed weights of the NEXT conv of the chain (or nullptr): pulled into L2 at kernel start
   int next_w_bytes;
   int hl_store_lo;          // EPI_SCALE_SKIP_HL: also write the lo plane (0 = the result only feeds a conv: hi suffices)
-  int hl_ahead3;            // EPI_SCALE_SKIP_HL8: three stream tiles in flight per epilogue warp instead of two (DFIR_HL_AHEAD=3)
   // Image statistics of pool-by-linearity as 64-bit FIXED-POINT sums (2^-24 units) accumulated with atomics: integer
   // addition is associative, so the result does not depend on how rows are grouped into CTA bands — an image's statistics
   // (hence its output) stay bit-identical whatever else is in the batch — and conv2's prologue reads 9 x 64 numbers per
