@@ -1068,10 +1068,11 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
                     o0 = fmaxf(o0, 0.f);
                     o1 = fmaxf(o1, 0.f);
                   }
-                  const uint32_t t0 = __float_as_uint(o0) + 0x80u, t1 = __float_as_uint(o1) + 0x80u;  // round to 24 bits
-                  const uint32_t b0 = (t0 + 0x8000u) & 0xffff0000u, b1 = (t1 + 0x8000u) & 0xffff0000u;   // nearest bf16
-                  hw[n] = prmt(b0, b1, 0x7632u);
-                  lw[n] = prmt(t0 - b0, t1 - b1, 0x0051u);   // byte 1 of each difference
+                  // round to 24 bits (+0x80) and to the nearest bf16 (+0x8000) in one add: u = bits(o) + 0x8080.  hi = the top
+                  // half of u; q = byte 1 of (u & 0xffff) - 0x8000 = byte 1 of u with its top bit flipped (v - 128 = v ^ 0x80 mod 256)
+                  const uint32_t u0 = __float_as_uint(o0) + 0x8080u, u1 = __float_as_uint(o1) + 0x8080u;
+                  hw[n] = prmt(u0, u1, 0x7632u);
+                  lw[n] = prmt(u0, u1, 0x0051u) ^ 0x8080u;
                 }
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
