@@ -313,10 +313,12 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
   const bool trace_on = (a.debug_probe & 32768) != 0 && blockIdx.x == gridDim.x / 2;
   // (PROBES build) bit 262144: the columns of epilogue group 1 record the tile loop of group 0 instead (HL epilogues)
   const bool tile_probe = (a.debug_probe & 262144) != 0;
+  const bool exp_no_lo = (a.debug_probe & 524288) != 0;   // HL8 update without the lo-plane shared-memory accesses (wrong results)
+  const bool exp_no_hi = (a.debug_probe & 1048576) != 0;  // ... without the hi-plane accesses
 #else
   constexpr bool probe = false, exp_skip_store = false, exp_one_copy = false, exp_no_copy = false, exp_no_epi = false,
                  exp_no_skipld = false, exp_no_f32st = false, exp_no_bfst = false,
-                 exp_no_pf = false, exp_no_tile = false, exp_no_pass = false, tile_probe = false;
+                 exp_no_pf = false, exp_no_tile = false, exp_no_pass = false, tile_probe = false, exp_no_lo = false, exp_no_hi = false;
 #endif
 
   if (g0 < g1) {
@@ -1053,8 +1055,10 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
                 const int sw = (p >> 1) & 3;
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
-                  hw[n] = *reinterpret_cast<const uint32_t*>(wbase + sl * 1024 + ((n ^ pr) << 4));
-                  lw[n] = *reinterpret_cast<const uint16_t*>(lbase + (((n >> 1) ^ sw) << 4) + 8 * (n & 1));
+                  hw[n] = exp_no_hi ? 0x3f803f80u
+                                                              : *reinterpret_cast<const uint32_t*>(wbase + sl * 1024 + ((n ^ pr) << 4));
+                  lw[n] = exp_no_lo ? 0u
+                                                             : *reinterpret_cast<const uint16_t*>(lbase + (((n >> 1) ^ sw) << 4) + 8 * (n & 1));
                 }
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
@@ -1076,8 +1080,9 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
                 }
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
-                  *reinterpret_cast<uint32_t*>(wbase + sl * 1024 + ((n ^ pr) << 4)) = hw[n];
-                  *reinterpret_cast<uint16_t*>(lbase + (((n >> 1) ^ sw) << 4) + 8 * (n & 1)) = static_cast<uint16_t>(lw[n]);
+                  if (!exp_no_hi) *reinterpret_cast<uint32_t*>(wbase + sl * 1024 + ((n ^ pr) << 4)) = hw[n];
+                  if (!exp_no_lo)
+                    *reinterpret_cast<uint16_t*>(lbase + (((n >> 1) ^ sw) << 4) + 8 * (n & 1)) = static_cast<uint16_t>(lw[n]);
                 }
               } else {
 #pragma unroll
