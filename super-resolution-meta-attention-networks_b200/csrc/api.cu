@@ -257,6 +257,10 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
       if (fx) {
         c1.istats = w.istats[blk & 1];
         c1.istats_clear = w.istats[(blk + 1) & 1];
+        // warp-autonomous epilogue (private staging buffers / TMA stores, per-thread accumulators); DFIR_STATS_W=0: the
+        // group-synchronous epilogue of EPI_RELU_STATS
+        static const int stats_w = getenv("DFIR_STATS_W") == nullptr ? 1 : atoi(getenv("DFIR_STATS_W"));
+        if (stats_w) c1.epi = EPI_RELU_STATS_W;
       }
       if (b == 0) {
         c1.in_bf16 = gin;

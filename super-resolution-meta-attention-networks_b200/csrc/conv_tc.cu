@@ -660,6 +660,12 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       const int bimg_first = g0 / rows_img_e;
       int cur_img = -1;
       long long fx_t = 0, fx_c0 = 0, fx_cl = 0;  // EPI_RELU_STATS fixed-point mode: this thread's channel, current image
+      // EPI_RELU_STATS_W: the sums of this thread's 16 channels over its pixels of the current image, in 2^-12 units
+      int w_t[16];
+      if constexpr (EPI == EPI_RELU_STATS_W) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w_t[j] = 0;
+      }
       // ---- EPI_SCALE_SKIP_HL: every epilogue warp streams the residual tiles of its own 32 pixels through kHlSlots
       // private 4 KB buffers (TMA load -> in-place update -> TMA store), two tiles of 16 pixels per output row, loads
       // issued two tiles ahead.  No barrier other than the tile's own mbarrier: the warps never wait for each other.
@@ -886,7 +892,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
         }
       } else {
         grid_dep_wait();
-        if constexpr (EPI == EPI_RELU_STATS) {
+        if constexpr (EPI == EPI_RELU_STATS || EPI == EPI_RELU_STATS_W) {
           // the statistics buffer the NEXT block's conv1 accumulates into: its last reader (the previous conv2) is complete
           if (a.istats_clear != nullptr) {
             const int nth = 128 * kEpiGroups;
@@ -1135,6 +1141,119 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             }
           }
           if (q == 0 && !(tile_probe && egrp == 1)) DFIR_TRACE(14 + egrp, it >> 1);
+        } else if constexpr (EPI == EPI_RELU_STATS_W) {
+          // ---- conv1 + ReLU + image statistics, WARP-AUTONOMOUS (no block-level barrier): every epilogue warp stages its own
+          // 32 pixels (4 KB, two private buffers) and stores them with its own TMA operation; the statistics of
+          // pool-by-linearity are accumulated per THREAD in 32-bit fixed point (2^-12 units, integer addition: independent of
+          // how rows are grouped into bands, hence still batch-invariant) and reduced over the warp only when the image
+          // changes.  Rows y = 0 / H - 1 (first / last row sums, corners) add their parts with atomics directly.
+          uint32_t ra[32], rb[32];  // pixels pr, pr + 8 (ra) and pr + 16, pr + 24 (rb) of this warp's quarter
+          tmem_ld_16x256b_x8(taddr, ra);
+          tmem_ld_16x256b_x8(taddr + (16u << 16), rb);
+          tmem_ld_wait();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&go[acc]);
+          if (q == 0) DFIR_TRACE(10 + 3 * egrp, it >> 1);
+          const int pr = lane >> 2, cq = lane & 3;
+          auto flush_image = [&](int img) {  // this thread's accumulators -> the image's 64-bit sums (2^-24 units)
+            // transposing butterfly over the 8 pixel rows of the fragment (lane bits 2..4), on integers: on exit w_t[0], w_t[1]
+            // are the warp's sums of channels 8 n + 2 cq + {0, 1}, n = lane bits (4, 3, 2)
+#pragma unroll
+            for (int step = 0; step < 3; ++step) {
+              const int nv = 16 >> step;
+              const int mask = 16 >> step;
+              const bool upper = (lane & mask) != 0;
+#pragma unroll
+              for (int i = 0; i < nv / 2; ++i) {
+                const int send = upper ? w_t[i] : w_t[i + nv / 2];
+                const int keep = upper ? w_t[i + nv / 2] : w_t[i];
+                w_t[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+              }
+            }
+            const int nblk = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(a.istats) + static_cast<size_t>(img) * 576;
+            atomicAdd(dst + 8 * nblk + 2 * cq, static_cast<unsigned long long>(static_cast<long long>(w_t[0]) << 12));
+            atomicAdd(dst + 8 * nblk + 2 * cq + 1, static_cast<unsigned long long>(static_cast<long long>(w_t[1]) << 12));
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w_t[j] = 0;
+          };
+          if (b != cur_img) {  // (uniform) image change
+            if (cur_img >= 0) flush_image(cur_img);
+            cur_img = b;
+          }
+          float bias_r[16];
+#pragma unroll
+          for (int n = 0; n < 8; ++n) {
+            bias_r[2 * n] = bias_s[8 * n + 2 * cq];
+            bias_r[2 * n + 1] = bias_s[8 * n + 2 * cq + 1];
+          }
+          uint8_t* wbuf = stage + (egrp * 4 + q) * 8192 + ((it >> 1) & 1) * 4096;   // this warp's staging buffer of this row
+          if (lane == 0) tma_store_wait_read<1>();   // the store that used this buffer two rows ago has read it
+          __syncwarp();
+          float sums[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sums[j] = 0.f;
+          const int x0 = seg * 128 + q * 32 + pr;
+          const bool edge_row = y == 0 || y == a.H - 1;
+          unsigned long long* irow = reinterpret_cast<unsigned long long*>(a.istats) + static_cast<size_t>(b) * 576;
+          uint8_t* strow = wbuf + pr * 128 + 4 * cq;   // (pixel & 7) == pr for all four pixels of the thread
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl) {   // pixel slots pr, pr + 8, pr + 16, pr + 24
+            const int xs = x0 + 8 * sl;
+            const bool ok = xs < a.W;
+            float v[16];
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+              const uint32_t* src = sl < 2 ? ra : rb;
+              v[2 * n] = fmaxf(__uint_as_float(src[4 * n + 2 * (sl & 1)]) + bias_r[2 * n], 0.f);
+              v[2 * n + 1] = fmaxf(__uint_as_float(src[4 * n + 2 * (sl & 1) + 1]) + bias_r[2 * n + 1], 0.f);
+            }
+#pragma unroll
+            for (int n = 0; n < 8; ++n)
+              *reinterpret_cast<uint32_t*>(strow + sl * 1024 + ((n ^ pr) << 4)) = pack_bf16x2(v[2 * n], v[2 * n + 1]);
+            if (ok) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) sums[j] += v[j];
+              if (xs == 0 || xs == a.W - 1) {  // first / last column: this lane owns 16 channels of that pixel; its values go
+                const bool first = xs == 0, last = xs == a.W - 1;   // straight to the image's sums (a few lanes per row)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int ch = 8 * (j >> 1) + 2 * cq + (j & 1);
+                  const unsigned long long fv =
+                      static_cast<unsigned long long>(static_cast<long long>(__float2int_rn(v[j] * 4096.f)) << 12);
+                  if (first) atomicAdd(irow + 64 + ch, fv);                            // C0
+                  if (last) atomicAdd(irow + 128 + ch, fv);                            // CL
+                  if (y == 0 && first) atomicAdd(irow + 320 + ch, fv);                 // K00
+                  if (y == 0 && last) atomicAdd(irow + 384 + ch, fv);                  // K0W
+                  if (y == a.H - 1 && first) atomicAdd(irow + 448 + ch, fv);           // KH0
+                  if (y == a.H - 1 && last) atomicAdd(irow + 512 + ch, fv);            // KHW
+                }
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&hl.m[0], wbuf, 0, seg * 128 + q * 32, y, b);
+            tma_store_commit();
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int f = __float2int_rn(sums[j] * 4096.f);
+            w_t[j] += f;
+            if (edge_row) {  // first / last row sums R0 / RL
+              const int ch = 8 * (j >> 1) + 2 * cq + (j & 1);
+              const unsigned long long fv = static_cast<unsigned long long>(static_cast<long long>(f) << 12);
+              if (y == 0) atomicAdd(irow + 192 + ch, fv);
+              if (y == a.H - 1) atomicAdd(irow + 256 + ch, fv);
+            }
+          }
+          if (g + kEpiGroups >= g1 && cur_img >= 0) {  // last row of this warp: flush
+            flush_image(cur_img);
+            cur_img = -1;
+          }
+          if (q == 0) DFIR_TRACE(14 + egrp, it >> 1);
         } else if constexpr (EPI == EPI_SCALE_SKIP) {
           // Per half of 32 channels: v = acc * s + bias * s (or r = acc + bias when the training forward saves r) into
           // an fp32 tile in smem (chunk-rotated: conflict free for the pixel-major writes and the coalesced reads),
@@ -1519,8 +1638,8 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           atomicAdd(dst + 128, static_cast<unsigned long long>(fx_cl));
         }
       }
-      if (EPI != EPI_TAIL_NCHW && EPI != EPI_SCALE_SKIP && !kHL && et == 0) tma_store_wait<0>();
-      if (kHL && lane == 0) tma_store_wait<0>();
+      if (EPI != EPI_TAIL_NCHW && EPI != EPI_SCALE_SKIP && EPI != EPI_RELU_STATS_W && !kHL && et == 0) tma_store_wait<0>();
+      if ((kHL || EPI == EPI_RELU_STATS_W) && lane == 0) tma_store_wait<0>();
     }
   }
 
@@ -1666,6 +1785,7 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   if (d.epi == EPI_RELU_MASK && d.mask_bf16 == nullptr) return DFIR_ERR_ARG;
   if (d.epi == EPI_RELU_STATS && d.istats == nullptr && (d.pool_rows == nullptr || d.col_first == nullptr || d.col_last == nullptr))
     return DFIR_ERR_ARG;
+  if (d.epi == EPI_RELU_STATS_W && (d.istats == nullptr || fused)) return DFIR_ERR_ARG;
   CUtensorMap tin, tout;
   int rc = DFIR_OK;
   if (!fused) {
@@ -1698,6 +1818,10 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
     }
   } else {
     for (int i = 0; i < 4; ++i) hl.m[i] = tout;  // unused, but must be valid descriptors
+    if (d.epi == EPI_RELU_STATS_W) {  // the warps store 32 pixels each
+      rc = make_tmap_nhwc_bf16(&hl.m[0], d.out_bf16, 64, d.W, d.H, d.B, d.out_pix_stride, d.out_row_stride, d.out_img_stride, 32);
+      if (rc != DFIR_OK) return rc;
+    }
   }
   ConvTcArgs a{};
   a.hl_store_lo = d.out_lo != nullptr ? 1 : 0;
@@ -1747,7 +1871,7 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
     auto word = [](char c) -> unsigned long long {
       return c == 'f' ? ptx::kL2EvictFirst : (c == 'l' ? ptx::kL2EvictLast : ptx::kL2EvictNormal);
     };
-    const bool conv1_role = d.epi == EPI_RELU_STATS || d.epi == EPI_BIAS_RELU;
+    const bool conv1_role = d.epi == EPI_RELU_STATS || d.epi == EPI_RELU_STATS_W || d.epi == EPI_BIAS_RELU;
     const bool conv2_role = d.epi == EPI_SCALE_SKIP || hl_mode;  // HL: letters 5, 6 = lo plane in / out
     if (pol != nullptr && strlen(pol) >= 6 && strncmp(pol, "nnnnnn", 6) != 0 && !fused && (conv1_role || conv2_role)) {
       a.use_hints = 1;
@@ -1786,6 +1910,7 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
     case EPI_BIAS_POOL: return launch_one<64, EPI_BIAS_POOL, IN_TMA>(tin, tout, hl, a, grid, stream);
     case EPI_BIAS_SKIP: return launch_one<64, EPI_BIAS_SKIP, IN_TMA>(tin, tout, hl, a, grid, stream);
     case EPI_RELU_STATS: return launch_one<64, EPI_RELU_STATS, IN_TMA>(tin, tout, hl, a, grid, stream);
+    case EPI_RELU_STATS_W: return launch_one<64, EPI_RELU_STATS_W, IN_TMA>(tin, tout, hl, a, grid, stream);
     case EPI_RELU_MASK: return launch_one<64, EPI_RELU_MASK, IN_TMA>(tin, tout, hl, a, grid, stream);
     case EPI_SCALE_SKIP: return launch_one<64, EPI_SCALE_SKIP, IN_TMA>(tin, tout, hl, a, grid, stream);
     case EPI_TAIL_NCHW: return launch_one<16, EPI_TAIL_NCHW, IN_TMA>(tin, tout, hl, a, grid, stream);

@@ -29,6 +29,8 @@ enum : int {
   EPI_SCALE_SKIP_HL8 = 9, // the same with an 8-BIT lo plane: the stream value is a 24-bit float X (16 significant bits) whose
                           // bit pattern is (hi << 16) + (q << 8), hi = nearest bf16, q = int8: 8 bytes per element (t 2, hi
                           // in/out 4, lo in/out 2) and no more epilogue arithmetic than the bf16 lo plane needs
+  EPI_RELU_STATS_W = 10,  // EPI_RELU_STATS with the image statistics in fixed point (istats) and warp-autonomous epilogue warps:
+                          // private staging buffers and TMA stores of 32 pixels, per-thread 32-bit accumulators, no block barrier
 };
 
 enum : int { IN_TMA = 0, IN_FUSED = 1 };  // input modes of the tensor-core conv (see conv_tc.cu)
