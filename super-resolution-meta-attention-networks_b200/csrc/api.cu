@@ -260,7 +260,8 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
         // warp-autonomous epilogue (private staging buffers / TMA stores, per-thread accumulators); DFIR_STATS_W=0: the
         // group-synchronous epilogue of EPI_RELU_STATS
         static const int stats_w = getenv("DFIR_STATS_W") == nullptr ? 1 : atoi(getenv("DFIR_STATS_W"));
-        if (stats_w) c1.epi = EPI_RELU_STATS_W;
+        const int lastpx = (W - 1) % 128;   // (see the host check in conv3x3_c64_tc: one column accumulator per thread)
+        if (stats_w && !(lastpx < 32 && lastpx % 8 == 0)) c1.epi = EPI_RELU_STATS_W;
       }
       if (b == 0) {
         c1.in_bf16 = gin;

@@ -661,10 +661,10 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       int cur_img = -1;
       long long fx_t = 0, fx_c0 = 0, fx_cl = 0;  // EPI_RELU_STATS fixed-point mode: this thread's channel, current image
       // EPI_RELU_STATS_W: the sums of this thread's 16 channels over its pixels of the current image, in 2^-12 units
-      int w_t[16];
+      int w_t[16], w_c[16], w_cw = 0;   // w_c: this lane's pixel of the first (w_cw = 1) or last (2) column, if it owns one
       if constexpr (EPI == EPI_RELU_STATS_W) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) w_t[j] = 0;
+        for (int j = 0; j < 16; ++j) w_t[j] = w_c[j] = 0;
       }
       // ---- EPI_SCALE_SKIP_HL: every epilogue warp streams the residual tiles of its own 32 pixels through kHlSlots
       // private 4 KB buffers (TMA load -> in-place update -> TMA store), two tiles of 16 pixels per output row, loads
@@ -1175,8 +1175,15 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             unsigned long long* dst = reinterpret_cast<unsigned long long*>(a.istats) + static_cast<size_t>(img) * 576;
             atomicAdd(dst + 8 * nblk + 2 * cq, static_cast<unsigned long long>(static_cast<long long>(w_t[0]) << 12));
             atomicAdd(dst + 8 * nblk + 2 * cq + 1, static_cast<unsigned long long>(static_cast<long long>(w_t[1]) << 12));
+            if (w_cw != 0) {  // this lane owns the first (1) or last (2) column of the image's rows it saw
+              unsigned long long* cdst = dst + (w_cw == 1 ? 64 : 128);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) w_t[j] = 0;
+              for (int j = 0; j < 16; ++j)
+                atomicAdd(cdst + 8 * (j >> 1) + 2 * cq + (j & 1), static_cast<unsigned long long>(static_cast<long long>(w_c[j]) << 12));
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w_t[j] = w_c[j] = 0;
+            w_cw = 0;
           };
           if (b != cur_img) {  // (uniform) image change
             if (cur_img >= 0) flush_image(cur_img);
@@ -1215,19 +1222,21 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             if (ok) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) sums[j] += v[j];
-              if (xs == 0 || xs == a.W - 1) {  // first / last column: this lane owns 16 channels of that pixel; its values go
-                const bool first = xs == 0, last = xs == a.W - 1;   // straight to the image's sums (a few lanes per row)
+              if (xs == 0 || xs == a.W - 1) {  // first / last column: this lane owns 16 channels of that pixel and keeps their
+                const bool first = xs == 0, last = xs == a.W - 1;   // sums in registers (a thread never owns both: host check)
+                w_cw = first ? 1 : 2;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                  const int ch = 8 * (j >> 1) + 2 * cq + (j & 1);
-                  const unsigned long long fv =
-                      static_cast<unsigned long long>(static_cast<long long>(__float2int_rn(v[j] * 4096.f)) << 12);
-                  if (first) atomicAdd(irow + 64 + ch, fv);                            // C0
-                  if (last) atomicAdd(irow + 128 + ch, fv);                            // CL
-                  if (y == 0 && first) atomicAdd(irow + 320 + ch, fv);                 // K00
-                  if (y == 0 && last) atomicAdd(irow + 384 + ch, fv);                  // K0W
-                  if (y == a.H - 1 && first) atomicAdd(irow + 448 + ch, fv);           // KH0
-                  if (y == a.H - 1 && last) atomicAdd(irow + 512 + ch, fv);            // KHW
+                  const int f = __float2int_rn(v[j] * 4096.f);
+                  w_c[j] += f;
+                  if (edge_row) {  // corners
+                    const int ch = 8 * (j >> 1) + 2 * cq + (j & 1);
+                    const unsigned long long fv = static_cast<unsigned long long>(static_cast<long long>(f) << 12);
+                    if (y == 0 && first) atomicAdd(irow + 320 + ch, fv);                 // K00
+                    if (y == 0 && last) atomicAdd(irow + 384 + ch, fv);                  // K0W
+                    if (y == a.H - 1 && first) atomicAdd(irow + 448 + ch, fv);           // KH0
+                    if (y == a.H - 1 && last) atomicAdd(irow + 512 + ch, fv);            // KHW
+                  }
                 }
               }
             }
@@ -1785,7 +1794,10 @@ int conv3x3_c64_tc(const ConvTcDesc& d, cudaStream_t stream) {
   if (d.epi == EPI_RELU_MASK && d.mask_bf16 == nullptr) return DFIR_ERR_ARG;
   if (d.epi == EPI_RELU_STATS && d.istats == nullptr && (d.pool_rows == nullptr || d.col_first == nullptr || d.col_last == nullptr))
     return DFIR_ERR_ARG;
-  if (d.epi == EPI_RELU_STATS_W && (d.istats == nullptr || fused)) return DFIR_ERR_ARG;
+  // (a thread of the warp-autonomous statistics epilogue keeps ONE column accumulator: it must not own both the first and
+  // the last column, i.e. the last pixel of the last row segment must not fall on pixel 0, 8, 16 or 24 of warp 0)
+  if (d.epi == EPI_RELU_STATS_W && (d.istats == nullptr || fused || ((d.W - 1) % 128 < 32 && ((d.W - 1) % 128) % 8 == 0)))
+    return DFIR_ERR_ARG;
   CUtensorMap tin, tout;
   int rc = DFIR_OK;
   if (!fused) {
