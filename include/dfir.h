@@ -125,6 +125,13 @@ int dfir_conv3x3_c64_fused(const void* r_bf16, const float* x_in, float* x_out, 
  *   dfir_ca_from_stats computes, times sq) while the pipeline fills; else svec[B][64] if not NULL; else 1. */
 int dfir_conv3x3_c64_stats(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
                            void* out_bf16, float* pool_rows, float* col_first, float* col_last, void* stream);
+/* dfir_conv3x3_c64_stats with the statistics as the 64-bit FIXED-POINT image sums dfir_qrcan_forward uses (2^-24 units,
+ * accumulated with integer atomics, so independent of how rows are grouped: batch-invariant).  istats [B][9][64] int64,
+ * zeroed by the caller, entries: total, first / last column sums, first / last row sums, the four corner pixels (0,0), (0,W-1),
+ * (H-1,0), (H-1,W-1).  warp_autonomous != 0: the epilogue warps stage and store 32 pixels each and keep 32-bit per-thread
+ * sums (2^-12 units) that are reduced when the image changes (not for W with (W - 1) % 128 in {0, 8, 16, 24}). */
+int dfir_conv3x3_c64_stats_fx(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
+                              void* out_bf16, long long* istats, int warp_autonomous, void* stream);
 int dfir_ca_from_stats(const float* pool_rows, const float* col_first, const float* col_last, const void* w2_packed,
                        const float* bias2, int style, const float* ca_params, int R, int M, int A,
                        const float* attributes, const float* sq, float* svec, int B, int H, int W, void* stream);

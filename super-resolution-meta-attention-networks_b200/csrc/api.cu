@@ -567,6 +567,24 @@ int dfir_conv3x3_c64_stats(const void* in_bf16, const void* wpacked, const float
   return conv3x3_c64_tc(d, S(stream));
 }
 
+int dfir_conv3x3_c64_stats_fx(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
+                              void* out_bf16, long long* istats, int warp_autonomous, void* stream) {
+  if (in_bf16 == nullptr || out_bf16 == nullptr || istats == nullptr) return DFIR_ERR_ARG;
+  ConvTcDesc d{};
+  d.B = B; d.H = H; d.W = W; d.cin_total = 64; d.cin_off = 0; d.cout = 64; d.in_mode = IN_TMA;
+  d.epi = warp_autonomous ? EPI_RELU_STATS_W : EPI_RELU_STATS;
+  d.in_bf16 = in_bf16; d.wpacked = wpacked; d.bias = bias; d.out_bf16 = out_bf16;
+  d.out_pix_stride = 128; d.out_row_stride = static_cast<long long>(W) * 128;
+  d.out_img_stride = static_cast<long long>(H) * W * 128;
+  d.istats = istats;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return DFIR_ERR_CUDA;
+  d.num_sms = sms;
+  return conv3x3_c64_tc(d, S(stream));
+}
+
 int dfir_ca_from_stats(const float* pool_rows, const float* col_first, const float* col_last, const void* w2_packed,
                        const float* bias2, int style, const float* ca_params, int R, int M, int A,
                        const float* attributes, const float* sq, float* svec, int B, int H, int W, void* stream) {

@@ -1223,21 +1223,9 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
 #pragma unroll
               for (int j = 0; j < 16; ++j) sums[j] += v[j];
               if (xs == 0 || xs == a.W - 1) {  // first / last column: this lane owns 16 channels of that pixel and keeps their
-                const bool first = xs == 0, last = xs == a.W - 1;   // sums in registers (a thread never owns both: host check)
-                w_cw = first ? 1 : 2;
+                w_cw = xs == 0 ? 1 : 2;        // sums in registers (a thread never owns both columns: host check)
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int f = __float2int_rn(v[j] * 4096.f);
-                  w_c[j] += f;
-                  if (edge_row) {  // corners
-                    const int ch = 8 * (j >> 1) + 2 * cq + (j & 1);
-                    const unsigned long long fv = static_cast<unsigned long long>(static_cast<long long>(f) << 12);
-                    if (y == 0 && first) atomicAdd(irow + 320 + ch, fv);                 // K00
-                    if (y == 0 && last) atomicAdd(irow + 384 + ch, fv);                  // K0W
-                    if (y == a.H - 1 && first) atomicAdd(irow + 448 + ch, fv);           // KH0
-                    if (y == a.H - 1 && last) atomicAdd(irow + 512 + ch, fv);            // KHW
-                  }
-                }
+                for (int j = 0; j < 16; ++j) w_c[j] += __float2int_rn(v[j] * 4096.f);
               }
             }
           }
@@ -1248,14 +1236,35 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             tma_store_commit();
           }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int f = __float2int_rn(sums[j] * 4096.f);
-            w_t[j] += f;
-            if (edge_row) {  // first / last row sums R0 / RL
-              const int ch = 8 * (j >> 1) + 2 * cq + (j & 1);
-              const unsigned long long fv = static_cast<unsigned long long>(static_cast<long long>(f) << 12);
-              if (y == 0) atomicAdd(irow + 192 + ch, fv);
-              if (y == a.H - 1) atomicAdd(irow + 256 + ch, fv);
+          for (int j = 0; j < 16; ++j) w_t[j] += __float2int_rn(sums[j] * 4096.f);
+          if (edge_row) {
+            // (uniform, two rows per image) first / last row sums R0 / RL and the corner pixels K00, K0W, KH0, KHW: straight to
+            // the image's sums.  Kept out of the per-row path: ~200 conditional atomics in the unrolled loops cost every row
+            // ~1000 instructions of predicates and branches (measured: conv1 36 -> 59 us).
+            for (int e = 0; e < 2; ++e) {
+              if ((e == 0 && y != 0) || (e == 1 && y != a.H - 1)) continue;
+              unsigned long long* rdst = irow + (e == 0 ? 192 : 256);
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                atomicAdd(rdst + 8 * (j >> 1) + 2 * cq + (j & 1),
+                          static_cast<unsigned long long>(static_cast<long long>(__float2int_rn(sums[j] * 4096.f)) << 12));
+#pragma unroll
+              for (int sl = 0; sl < 4; ++sl) {   // (static indices into the fragment registers: no local-memory copy)
+                const int xs = x0 + 8 * sl;
+                if (xs >= a.W || (xs != 0 && xs != a.W - 1)) continue;
+                const bool kfirst = xs == 0, klast = xs == a.W - 1;   // (W == 1: both)
+                unsigned long long* kdst = irow + 320 + 128 * e;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const uint32_t* src = sl < 2 ? ra : rb;
+                  const float val = fmaxf(__uint_as_float(src[4 * (j >> 1) + 2 * (sl & 1) + (j & 1)]) + bias_r[j], 0.f);
+                  const unsigned long long fv =
+                      static_cast<unsigned long long>(static_cast<long long>(__float2int_rn(val * 4096.f)) << 12);
+                  const int ch = 8 * (j >> 1) + 2 * cq + (j & 1);
+                  if (kfirst) atomicAdd(kdst + ch, fv);
+                  if (klast) atomicAdd(kdst + 64 + ch, fv);
+                }
+              }
             }
           }
           if (g + kEpiGroups >= g1 && cur_img >= 0) {  // last row of this warp: flush

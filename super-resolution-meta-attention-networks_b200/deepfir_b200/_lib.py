@@ -73,6 +73,7 @@ PROTOTYPES = {
     "dfir_conv3x3_c64_fused": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _i,
                                     _vp, _vp, _vp, _vp]),
     "dfir_conv3x3_c64_stats": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "dfir_conv3x3_c64_stats_fx": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "dfir_ca_from_stats": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "dfir_conv3x3_c64_scale_skip": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i,
                                          _i, _vp, _vp, _vp]),

@@ -28,6 +28,7 @@ sv = torch.rand(bc, 64, device=dev)
 xh = torch.randn(bc, LR, LR, 64, device=dev).to(torch.bfloat16)
 xl = (torch.randn(bc, LR, LR, 64, device=dev) * 1e-3).to(torch.bfloat16)
 xl8 = torch.randint(-128, 128, (bc, LR, LR, 64), device=dev, dtype=torch.int8)
+ist = torch.zeros(bc, 9, 64, device=dev, dtype=torch.int64)
 pool.normal_(); cf.normal_(); cl.normal_()
 blob = torch.randn(4 * 74 + 4 + 64 * 4 + 64, device=dev) / 8
 attr = torch.rand(bc, 10, device=dev); sq = torch.rand(bc, 64, device=dev) * 0.1
@@ -41,6 +42,10 @@ def launch():
     elif mode == "stats":
         _lib.check(lib.dfir_conv3x3_c64_stats(a.data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR, b.data_ptr(),
                                               pool.data_ptr(), cf.data_ptr(), cl.data_ptr(), st()), "c1")
+    elif mode in ("statsfx", "statsw"):
+        ist.zero_()
+        _lib.check(lib.dfir_conv3x3_c64_stats_fx(a.data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR, b.data_ptr(),
+                                                 ist.data_ptr(), 1 if mode == "statsw" else 0, st()), "c1fx")
     elif mode in ("sshl8", "sshl8stats"):
         stats = mode == "sshl8stats"
         _lib.check(lib.dfir_conv3x3_c64_scale_skip_hl8(a.data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR,
@@ -80,7 +85,7 @@ names = ["tma_issue", "ld_full", "ld_aempty", "ld_done", "mma_top", "mma_24", "m
 if int(os.environ.get("EXTRA_PROBE", "0")) & 262144:   # tile loop of epilogue group 0 (first tile of each row)
     names[11:14] = ["t_issued", "t_landed", "t_updated"]
     names[15] = "t2_fenced"
-if mode in ("conv1", "stats"):
+if mode in ("conv1", "stats", "statsfx"):
     names[11:14] = ["e0_stfree", "e0_staged", "e0_sums"]
     names[15] = "e0_bar2"
 print("mode %s bc %d (SM clocks relative to the first event; 0 = not recorded)" % (mode, bc))
