@@ -434,3 +434,45 @@ def test_bad_arguments_return_error_codes():
                               2048, None, None, None, 1, None) == -1  # reserved desc_mode
     assert L.dfir_conv3x3_c64_fused(x.data_ptr(), None, None, None, 0, None, 4, 10, 10, None, None, 1.0, x.data_ptr(),
                                     x.data_ptr(), 1, 4, 4, 1, x.data_ptr(), None, None, None) == -1  # no x_in
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 128), (3, 5, 40), (1, 7, 200), (2, 1, 64), (1, 128, 128), (5, 24, 96)])
+@pytest.mark.parametrize("warp_autonomous", [0, 1])
+def test_conv1_fixed_point_image_statistics(shape, warp_autonomous):
+    """dfir_conv3x3_c64_stats_fx: t = relu(conv(x) + b) in bf16 plus the nine image sums of pool-by-linearity (total, first /
+    last column, first / last row, four corners) as 64-bit fixed-point integers; both epilogues (group-synchronous and
+    warp-autonomous); the sums of an image do not depend on the rest of the batch (integer accumulation)"""
+    B, H, W = shape
+    g = torch.Generator().manual_seed(H * 17 + W)
+    x = G.bf16_round(torch.randn(B, 64, H, W, generator=g))
+    w = (torch.rand(64, 64, 3, 3, generator=g) - 0.5) / 12
+    b = torch.rand(64, generator=g) - 0.5
+    t = F.relu(_ref_conv(x, w, b)).double()                       # [B][64][H][W]
+    want = torch.stack([t.sum(dim=(2, 3)), t[:, :, :, 0].sum(dim=2), t[:, :, :, -1].sum(dim=2), t[:, :, 0, :].sum(dim=2),
+                        t[:, :, -1, :].sum(dim=2), t[:, :, 0, 0], t[:, :, 0, -1], t[:, :, -1, 0], t[:, :, -1, -1]], dim=1)
+    L = G.lib()
+    xd, wp, bd = G.nhwc_bf16(x), G.pack_bf16(w), b.cuda()
+
+    def run(xdev, nb):
+        out = torch.empty(nb, H, W, 64, device="cuda", dtype=torch.bfloat16)
+        ist = torch.zeros(nb, 9, 64, device="cuda", dtype=torch.int64)
+        rc = L.dfir_conv3x3_c64_stats_fx(xdev.data_ptr(), wp.data_ptr(), bd.data_ptr(), nb, H, W, out.data_ptr(), ist.data_ptr(),
+                                         warp_autonomous, G.stream())
+        return rc, out, ist
+
+    rc, out, ist = run(xd, B)
+    if warp_autonomous and (W - 1) % 128 < 32 and ((W - 1) % 128) % 8 == 0:
+        assert rc != 0        # one column accumulator per thread: such widths take the group-synchronous epilogue
+        return
+    assert rc == 0
+    G.sync()
+    assert torch.allclose(G.to_nchw(out), t.float(), rtol=2 ** -7, atol=1e-3)
+    got = ist.cpu().double() / 2 ** 24
+    # quantisation: 2^-13 per (thread, row) partial in the warp-autonomous form, 2^-25 per row otherwise; fp32 sums of a row
+    tol = 1e-4 * want.abs().max().item() + H * W * 2.0 ** -13 / 4
+    assert (got - want).abs().max().item() <= tol, (got - want).abs().max().item()
+    # an image alone == the same image inside the batch, bit for bit
+    rc1, _, ist1 = run(xd[B - 1:].contiguous(), 1)
+    assert rc1 == 0
+    G.sync()
+    assert torch.equal(ist1[0].cpu(), ist[B - 1].cpu())
