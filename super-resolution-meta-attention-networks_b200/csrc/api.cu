@@ -257,9 +257,9 @@ int qrcan_forward_bf16(const dfir_qrcan_net* n, const float* x, const float* att
       if (fx) {
         c1.istats = w.istats[blk & 1];
         c1.istats_clear = w.istats[(blk + 1) & 1];
-        // warp-autonomous epilogue (private staging buffers / TMA stores, per-thread accumulators); DFIR_STATS_W=0: the
-        // group-synchronous epilogue of EPI_RELU_STATS
-        static const int stats_w = getenv("DFIR_STATS_W") == nullptr ? 1 : atoi(getenv("DFIR_STATS_W"));
+        // DFIR_STATS_W=1: warp-autonomous epilogue (private staging buffers / TMA stores, per-thread accumulators) instead of
+        // the group-synchronous epilogue of EPI_RELU_STATS (default until it is measured faster)
+        static const int stats_w = getenv("DFIR_STATS_W") == nullptr ? 0 : atoi(getenv("DFIR_STATS_W"));
         const int lastpx = (W - 1) % 128;   // (see the host check in conv3x3_c64_tc: one column accumulator per thread)
         if (stats_w && !(lastpx < 32 && lastpx % 8 == 0)) c1.epi = EPI_RELU_STATS_W;
       }
