@@ -157,7 +157,10 @@ int dfir_conv3x3_c64_scale_skip_hl(const void* in_bf16, const void* wpacked, con
  * add up: bits(X) = (hi << 16) + (q << 8) with hi = the bf16 nearest to X (ties away from zero) and q = int8 in [-128, 127].
  * X = the result rounded to 24 bits (ties away from zero).  The integer form is exact across binade boundaries and needs no
  * exponent arithmetic in the epilogue.  8 bytes of HBM traffic per element (t 2, hi 2 + 2, lo 1 + 1).
- * skip_lo8 / out_lo8: dense NHWC int8 planes [B][H][W][64]. */
+ * skip_lo8 / out_lo8: dense int8 planes [B][H][W][64] whose 64 bytes per pixel are stored in the order of the accumulator
+ * fragment: byte cq * 16 + 2 n + e holds channel 8 n + 2 cq + e (n = 0..7, cq = 0..3, e = 0..1), so that a thread of the
+ * epilogue reads its 16 channels of a pixel as one 16-byte word.  The plane is private to the library (dfir_stream_encode_hl8 /
+ * dfir_stream_decode_hl8 convert from / to fp32). */
 int dfir_conv3x3_c64_scale_skip_hl8(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
                                    const float* svec, const void* skip_hi, const void* skip_lo8, void* out_hi, void* out_lo8,
                                    const float* pool_rows, const float* col_first, const float* col_last, int style,

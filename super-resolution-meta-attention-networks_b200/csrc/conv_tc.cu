@@ -1053,25 +1053,27 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
                 // 8-bit lo plane: the stream value is a 24-BIT float X (sign, exponent, 15 mantissa bits = 16 significant bits);
                 // hi = the bf16 nearest to X (ties away from zero), q = (X - hi) in units of X's last bit, taken on the BIT
                 // PATTERNS: bits(X) = (hi << 16) + (q << 8), q in [-128, 127] - exact across binade boundaries, no exponent
-                // arithmetic, no conversions.  Tile of 16 px x 64 B, TMA SWIZZLE_64B: pixel p, byte c at
-                // p * 64 + (((c >> 4) ^ ((p >> 1) & 3)) << 4) + (c & 15); this thread's two channels 8 n + 2 cq + {0, 1} of pixel
-                // p = pr + 8 sl are one 16-bit word.
+                // arithmetic, no conversions.  The lo plane is private to these kernels, so its 64 bytes per pixel are stored in
+                // the order the accumulator fragment wants: byte cq * 16 + 2 n + e holds channel 8 n + 2 cq + e, i.e. the 16
+                // channels of a thread are ONE 16-byte word (one 128-bit shared-memory access per pixel instead of eight 16-bit
+                // ones).  Tile of 32 px x 64 B, TMA SWIZZLE_64B: pixel p, 16-byte chunk k at p * 64 + ((k ^ ((p >> 1) & 3)) << 4).
                 const int p = pr + 8 * sl + (kTilePx == 32 ? 16 * half : 0);
-                uint8_t* lbase = buf + kHlHiBytes + p * 64 + 2 * cq;
-                const int sw = (p >> 1) & 3;
-#pragma unroll
-                for (int n = 0; n < 8; ++n) {
-                  hw[n] = exp_no_hi ? 0x3f803f80u
-                                                              : *reinterpret_cast<const uint32_t*>(wbase + sl * 1024 + ((n ^ pr) << 4));
-                  lw[n] = exp_no_lo ? 0u
-                                                             : *reinterpret_cast<const uint16_t*>(lbase + (((n >> 1) ^ sw) << 4) + 8 * (n & 1));
+                uint4* lptr = reinterpret_cast<uint4*>(buf + kHlHiBytes + p * 64 + ((cq ^ ((p >> 1) & 3)) << 4));
+                uint32_t lq[4] = {0u, 0u, 0u, 0u};
+                if (!exp_no_lo) {
+                  const uint4 t4 = *lptr;
+                  lq[0] = t4.x; lq[1] = t4.y; lq[2] = t4.z; lq[3] = t4.w;
                 }
+#pragma unroll
+                for (int n = 0; n < 8; ++n)
+                  hw[n] = exp_no_hi ? 0x3f803f80u : *reinterpret_cast<const uint32_t*>(wbase + sl * 1024 + ((n ^ pr) << 4));
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
                   const uint32_t* src = half ? rb : ra;
-                  // (sign-extended q) << 8 by one byte permute each: bytes [0, q, sign, sign]
-                  const float x0 = __uint_as_float((hw[n] << 16) + prmt(lw[n], 0u, 0x8802u));
-                  const float x1 = __uint_as_float((hw[n] & 0xffff0000u) + prmt(lw[n], 0u, 0x9912u));
+                  // (sign-extended q) << 8 by one byte permute each: bytes [0, q, sign, sign]; q pair n = half (n & 1) of lq[n >> 1]
+                  const uint32_t qw = lq[n >> 1];
+                  const float x0 = __uint_as_float((hw[n] << 16) + prmt(qw, 0u, (n & 1) ? 0xAA24u : 0x8804u));
+                  const float x1 = __uint_as_float((hw[n] & 0xffff0000u) + prmt(qw, 0u, (n & 1) ? 0xBB34u : 0x9914u));
                   float o0 = fmaf(__uint_as_float(src[4 * n + 2 * sl]), hl_s[2 * n], hl_bs[2 * n]) + x0;
                   float o1 = fmaf(__uint_as_float(src[4 * n + 2 * sl + 1]), hl_s[2 * n + 1], hl_bs[2 * n + 1]) + x1;
                   if (a.relu_out) {  // (last K-chunk of a wide conv + ReLU)
@@ -1082,13 +1084,18 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
                   // half of u; q = byte 1 of (u & 0xffff) - 0x8000 = byte 1 of u with its top bit flipped (v - 128 = v ^ 0x80 mod 256)
                   const uint32_t u0 = __float_as_uint(o0) + 0x8080u, u1 = __float_as_uint(o1) + 0x8080u;
                   hw[n] = prmt(u0, u1, 0x7632u);
-                  lw[n] = prmt(u0, u1, 0x0051u) ^ 0x8080u;
+                  lw[n] = prmt(u0, u1, 0x0051u);   // (low 16 bits: the q pair before the sign flip)
                 }
 #pragma unroll
-                for (int n = 0; n < 8; ++n) {
+                for (int n = 0; n < 8; ++n)
                   if (!exp_no_hi) *reinterpret_cast<uint32_t*>(wbase + sl * 1024 + ((n ^ pr) << 4)) = hw[n];
-                  if (!exp_no_lo)
-                    *reinterpret_cast<uint16_t*>(lbase + (((n >> 1) ^ sw) << 4) + 8 * (n & 1)) = static_cast<uint16_t>(lw[n]);
+                if (!exp_no_lo) {
+                  uint4 o4;
+                  o4.x = prmt(lw[0], lw[1], 0x5410u) ^ 0x80808080u;
+                  o4.y = prmt(lw[2], lw[3], 0x5410u) ^ 0x80808080u;
+                  o4.z = prmt(lw[4], lw[5], 0x5410u) ^ 0x80808080u;
+                  o4.w = prmt(lw[6], lw[7], 0x5410u) ^ 0x80808080u;
+                  *lptr = o4;
                 }
               } else {
 #pragma unroll

@@ -30,36 +30,44 @@ __global__ void f32_to_bf16_kernel(const float4* __restrict__ in, uint2* __restr
   }
 }
 
-// fp32 <-> the hi / 8-bit lo stream format (kernels.h, EPI_SCALE_SKIP_HL8): bits(X) = (hi << 16) + (q << 8), X = x rounded to 24 bits
-__global__ void stream_encode_hl8_kernel(const float4* __restrict__ in, uint2* __restrict__ hi, uint32_t* __restrict__ lo,
+// fp32 <-> the hi / 8-bit lo stream format (kernels.h, EPI_SCALE_SKIP_HL8): bits(X) = (hi << 16) + (q << 8), X = x rounded to 24
+// bits; 64-channel pixels; the lo plane stores a pixel's bytes in accumulator-fragment order: byte cq * 16 + 2 n + e holds
+// channel 8 n + 2 cq + e.  One thread = 4 consecutive channels 4 m .. 4 m + 3 of a pixel (n = m >> 1, cq = 2 (m & 1) + {0, 1}).
+__global__ void stream_encode_hl8_kernel(const float4* __restrict__ in, uint2* __restrict__ hi, unsigned char* __restrict__ lo,
                                          long long n4) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 v = in[i];
     const float f[4] = {v.x, v.y, v.z, v.w};
-    uint32_t hb[4], q = 0;
+    uint32_t hb[4], q[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const uint32_t t = __float_as_uint(f[k]) + 0x80u;
       hb[k] = (t + 0x8000u) & 0xffff0000u;
-      q |= (((t - hb[k]) >> 8) & 0xffu) << (8 * k);
+      q[k] = ((t - hb[k]) >> 8) & 0xffu;
     }
     hi[i] = make_uint2((hb[0] >> 16) | hb[1], (hb[2] >> 16) | hb[3]);
-    lo[i] = q;
+    const int m = static_cast<int>(i & 15);
+    unsigned char* px = lo + (i >> 4) * 64 + 2 * (m >> 1) + 32 * (m & 1);
+    *reinterpret_cast<unsigned short*>(px) = static_cast<unsigned short>(q[0] | (q[1] << 8));
+    *reinterpret_cast<unsigned short*>(px + 16) = static_cast<unsigned short>(q[2] | (q[3] << 8));
   }
 }
 
-__global__ void stream_decode_hl8_kernel(const uint2* __restrict__ hi, const uint32_t* __restrict__ lo, float4* __restrict__ out,
-                                         long long n4) {
+__global__ void stream_decode_hl8_kernel(const uint2* __restrict__ hi, const unsigned char* __restrict__ lo,
+                                         float4* __restrict__ out, long long n4) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const uint2 h = hi[i];
-    const uint32_t q = lo[i];
+    const int m = static_cast<int>(i & 15);
+    const unsigned char* px = lo + (i >> 4) * 64 + 2 * (m >> 1) + 32 * (m & 1);
+    const uint32_t qa = *reinterpret_cast<const unsigned short*>(px), qb = *reinterpret_cast<const unsigned short*>(px + 16);
+    const uint32_t q[4] = {qa & 0xffu, qa >> 8, qb & 0xffu, qb >> 8};
     const uint32_t hb[4] = {h.x << 16, h.x & 0xffff0000u, h.y << 16, h.y & 0xffff0000u};
     float f[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int qs = static_cast<int>(static_cast<int8_t>((q >> (8 * k)) & 0xffu));
+      const int qs = static_cast<int>(static_cast<int8_t>(q[k]));
       f[k] = __uint_as_float(hb[k] + static_cast<uint32_t>(qs << 8));
     }
     out[i] = make_float4(f[0], f[1], f[2], f[3]);
@@ -736,20 +744,20 @@ int f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t s
 }
 
 int stream_encode_hl8(const float* in, void* hi, void* lo8, long long n, cudaStream_t s) {
-  if (n % 4 != 0) return DFIR_ERR_ARG;
+  if (n % 64 != 0) return DFIR_ERR_ARG;  // whole 64-channel pixels
   if (n == 0) return DFIR_OK;
   const long long n4 = n / 4;
   stream_encode_hl8_kernel<<<static_cast<unsigned>(std::min<long long>((n4 + 255) / 256, 148 * 8)), 256, 0, s>>>(
-      reinterpret_cast<const float4*>(in), reinterpret_cast<uint2*>(hi), reinterpret_cast<uint32_t*>(lo8), n4);
+      reinterpret_cast<const float4*>(in), reinterpret_cast<uint2*>(hi), reinterpret_cast<unsigned char*>(lo8), n4);
   return ok_or_cuda2();
 }
 
 int stream_decode_hl8(const void* hi, const void* lo8, float* out, long long n, cudaStream_t s) {
-  if (n % 4 != 0) return DFIR_ERR_ARG;
+  if (n % 64 != 0) return DFIR_ERR_ARG;
   if (n == 0) return DFIR_OK;
   const long long n4 = n / 4;
   stream_decode_hl8_kernel<<<static_cast<unsigned>(std::min<long long>((n4 + 255) / 256, 148 * 8)), 256, 0, s>>>(
-      reinterpret_cast<const uint2*>(hi), reinterpret_cast<const uint32_t*>(lo8), reinterpret_cast<float4*>(out), n4);
+      reinterpret_cast<const uint2*>(hi), reinterpret_cast<const unsigned char*>(lo8), reinterpret_cast<float4*>(out), n4);
   return ok_or_cuda2();
 }
 

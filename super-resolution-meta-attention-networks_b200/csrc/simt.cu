@@ -119,7 +119,7 @@ head_conv_kernel(const float* __restrict__ x, const float* __restrict__ wp, cons
             // 8-bit lo plane (see EPI_SCALE_SKIP_HL8 in conv_tc.cu): the stream value is the 24-bit float X nearest to the
             // result, bits(X) = (hi << 16) + (q << 8); hi = nearest bf16 with ties away from zero REPLACES the RN-even hi
             __align__(16) unsigned short hb[8];
-            __align__(8) unsigned char qb[8];
+            unsigned char qb[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const uint32_t t = __float_as_uint(acc[p][i]) + 0x80u;
@@ -128,7 +128,13 @@ head_conv_kernel(const float* __restrict__ x, const float* __restrict__ wp, cons
               qb[i] = static_cast<unsigned char>(((t - bh) >> 8) & 0xffu);
             }
             *reinterpret_cast<uint4*>(out_bf16 + o) = *reinterpret_cast<uint4*>(hb);
-            *reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(out_lo) + o) = *reinterpret_cast<uint2*>(qb);
+            // the lo plane keeps a pixel's 64 bytes in accumulator-fragment order: byte cq * 16 + 2 n + e = channel 8 n + 2 cq + e
+            // (this thread: n = oc / 8, channels oc + 2 cq + e)
+            unsigned char* lo_px = reinterpret_cast<unsigned char*>(out_lo) + (o - oc) + 2 * (oc >> 3);
+#pragma unroll
+            for (int cqi = 0; cqi < 4; ++cqi)
+              *reinterpret_cast<unsigned short*>(lo_px + 16 * cqi) =
+                  static_cast<unsigned short>(qb[2 * cqi] | (static_cast<unsigned short>(qb[2 * cqi + 1]) << 8));
           } else if (out_lo != nullptr) {  // hi + lo residual stream: lo = bf16(value - hi)
             __align__(16) __nv_bfloat162 lo[4];
 #pragma unroll

@@ -236,22 +236,35 @@ def test_pool_by_linearity_trio(shape, style):
     assert ((x_hi.float() + x_lo.float()) - out32).abs().max().item() <= 2.0 ** -15 * scale
     # ---- the same on the 8-BIT lo plane (the format of dfir_qrcan_forward): the stream value is a 24-bit float X,
     # bits(X) = (hi << 16) + (q << 8), hi = nearest bf16 (ties away from zero), q = int8
+    # the lo plane stores a pixel's 64 bytes in accumulator-fragment order: byte cq * 16 + 2 n + e holds channel 8 n + 2 cq + e
+    kk = torch.arange(64)
+    chan_of_byte = (8 * ((kk % 16) // 2) + 2 * (kk // 16) + (kk % 2)).cuda()
+
     def enc8(v32):
         bits = v32.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
         t = bits + 0x80
         hb = (t + 0x8000) & 0xFFFF0000
         q = ((t - hb) >> 8) & 0xFF
         hi = (hb >> 16).to(torch.int32).to(torch.int16).view(torch.bfloat16)      # (wraps to the signed 16-bit pattern)
-        return hi.contiguous(), q.to(torch.uint8).view(torch.int8).contiguous()
+        return hi.contiguous(), q.to(torch.uint8).view(torch.int8)[..., chan_of_byte].contiguous()
 
     def dec8(hi, q):
+        qc = torch.empty_like(q)
+        qc[..., chan_of_byte] = q                                                   # back to channel order
         hb = (hi.contiguous().view(torch.int16).to(torch.int64) & 0xFFFF) << 16
-        bits = (hb + (q.to(torch.int64) << 8)) & 0xFFFFFFFF
+        bits = (hb + (qc.to(torch.int64) << 8)) & 0xFFFFFFFF
         bits = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32)
         return bits.view(torch.float32)
 
     y_hi, y_q = enc8(x32)
     assert (dec8(y_hi, y_q) - x32).abs().max().item() <= 2.0 ** -16 * x32.abs().max().item()
+    # the library's own codec operators agree with that definition, bit for bit
+    c_hi = torch.empty_like(y_hi); c_q = torch.empty_like(y_q); c_x = torch.empty_like(x32)
+    assert L.dfir_stream_encode_hl8(x32.data_ptr(), c_hi.data_ptr(), c_q.data_ptr(), x32.numel(), G.stream()) == 0
+    assert L.dfir_stream_decode_hl8(c_hi.data_ptr(), c_q.data_ptr(), c_x.data_ptr(), x32.numel(), G.stream()) == 0
+    G.sync()
+    assert torch.equal(c_hi.view(torch.int16), y_hi.view(torch.int16)) and torch.equal(c_q, y_q)
+    assert torch.equal(c_x, dec8(y_hi, y_q))
     for desc in (0, 1):
         p_hi = torch.full((B, H, W, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
         p_q = torch.full((B, H, W, 64), 77, device="cuda", dtype=torch.int8)
