@@ -637,6 +637,13 @@ static int scale_skip_hl_any(int epi, const void* in_bf16, const void* wpacked, 
   d.col_last = const_cast<float*>(col_last);
   d.ca_style = style; d.ca_params = ca_params; d.ca_R = R; d.ca_M = M; d.ca_A = A; d.attributes = attributes; d.sq = sq;
   d.epi_stats = style != DFIR_STYLE_NONE ? 1 : 0;
+  // statistics as the 64-bit fixed-point image sums of dfir_conv3x3_c64_stats_fx (what the network schedule uses):
+  // col_first == col_last == NULL and `pool_rows` points at the [B][9][64] int64 sums
+  if (d.epi_stats && pool_rows != nullptr && col_first == nullptr && col_last == nullptr) {
+    d.epi_stats = 2;
+    d.istats = reinterpret_cast<long long*>(const_cast<float*>(pool_rows));
+    d.pool_rows = nullptr;
+  }
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess ||
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)

@@ -725,6 +725,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           }
         }
         grid_dep_wait();
+        if (q == 0 && egrp == 0) DFIR_TRACE(8, 40);  // (PROBES build) prologue time stamps of epilogue group 0
         if constexpr (kHL) {
           if (lane == 0) {  // the first tiles travel while the attention vector is evaluated (8-bit lo: one tile = one row;
             hl_issue();     // the second buffer is the prologue's scratch until the barrier that ends the prologue)
@@ -732,7 +733,25 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
           }
         }
         if (a.epi_stats) {
+          const bool fixed_stats = a.epi_stats == 2;
+          const int b_mine = bimg_first + egrp;                     // first image of this group
+          const bool have_mine = b_mine <= (g1 - 1) / rows_img_e;
+          float fxv[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          float sqv = 1.f;                                          // meta scale of the image (channel et)
+          auto load_fixed = [&](int bimg) {  // threads 0..63: the nine fixed-point sums of one channel, the meta scale
+            if (et < 64) {
+              const long long* st = a.istats + static_cast<size_t>(bimg) * 576 + et;
+              long long raw[9];
+#pragma unroll
+              for (int k = 0; k < 9; ++k) raw[k] = __ldcg(st + 64 * k);
+              if (a.sq != nullptr) sqv = a.sq[static_cast<size_t>(bimg) * 64 + et];
+#pragma unroll
+              for (int k = 0; k < 9; ++k) fxv[k] = __ll2float_rn(raw[k]) * (1.f / 16777216.f);
+            }
+          };
+          if (fixed_stats && have_mine) load_fixed(flip ? a.B - 1 - b_mine : b_mine);
           if constexpr (kTwoEpi) named_bar_sync(6, 256); else named_bar_sync(5, 128);  // cap_s complete
+          if (q == 0 && egrp == 0) DFIR_TRACE(8, 41);
           float* scratch = attn_s + egrp * kAttnScratchFloats;
           float* y_s = scratch;
           float* s_s = scratch + 64;
@@ -749,20 +768,17 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             return v;
           };
           mbar_wait(wbar, 0, 9);  // conv weights have landed in smem (generic-proxy reads below)
+          if (q == 0 && egrp == 0) DFIR_TRACE(8, 42);
           for (int b = bimg_first + egrp; b <= bimg_last; b += kEpiGroups) {
             const int ba = flip ? a.B - 1 - b : b;  // the image the statistics, attributes and meta scale belong to
             // statistics source: per-row arrays written by conv1 (summed here in a fixed order), or the nine 64-bit fixed-point
-            // sums per channel that conv1 accumulated with atomics (epi_stats == 2: one 72-byte read per thread)
-            const bool fixed_stats = a.epi_stats == 2;
+            // sums per channel that conv1 accumulated with atomics (epi_stats == 2: one 72-byte read per thread, issued
+            // ahead of everything else for the group's first image)
             float r0v = 0.f, rlv = 0.f, k00 = 0.f, k0w = 0.f, kh0 = 0.f, khw = 0.f;
-            float fxv[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (fixed_stats) {
-              if (et < 64) {
-                const long long* st = a.istats + static_cast<size_t>(ba) * 576 + et;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) fxv[k] = __ll2float_rn(__ldcg(st + 64 * k)) * (1.f / 16777216.f);
-              }
+              if (b != b_mine) load_fixed(ba);
             } else {
+              if (et < 64 && a.sq != nullptr) sqv = a.sq[static_cast<size_t>(ba) * 64 + et];
             const float4* pr = reinterpret_cast<const float4*>(a.pool_rows + static_cast<size_t>(ba) * rows_img_e * 64) + cq;
             const float4* cf = reinterpret_cast<const float4*>(a.col_first + static_cast<size_t>(ba) * H * 64) + cq;
             const float4* cl = reinterpret_cast<const float4*>(a.col_last + static_cast<size_t>(ba) * H * 64) + cq;
@@ -816,8 +832,9 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             }
             }
             for (int i = et; i < a.ca_A; i += 128) attr_s[i] = a.attributes[static_cast<size_t>(ba) * a.ca_A + i];
-            grp.sync();
-            float* S = tmp;  // [9][64], written once the partial sums have been consumed
+            if (!fixed_stats) grp.sync();
+            if (q == 0 && egrp == 0 && !fixed_stats) DFIR_TRACE(8, 43);
+            float* S = tmp;  // [9][64], written once the partial sums have been consumed (fixed-point sums: no partial sums)
             float Sv[9];
             if (et < 64) {
               const int c = et;
@@ -850,44 +867,55 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
                   Sv[dy * 3 + dx] = T - rowx - colx + corner;
                 }
             }
-            grp.sync();  // the partial sums are dead: S takes their place
+            if (!fixed_stats) grp.sync();  // the partial sums are dead: S takes their place
             if (et < 64) {
 #pragma unroll
               for (int k = 0; k < 9; ++k) S[k * 64 + et] = Sv[k];
             }
             grp.sync();
+            if (q == 0 && egrp == 0) DFIR_TRACE(8, 44);
             {
-              // 2 threads per output channel split the taps; weights come from the swizzled smem tiles
-              const int co = et >> 1, part2 = et & 1;
-              float acc0 = 0.f, acc1 = 0.f;
+              // 2 threads per output channel split the taps (warps 0-1: even taps, warps 2-3: odd taps, so that a warp reads
+              // one S chunk - a pure broadcast - and 32 consecutive weight rows - conflict-free through the 128B swizzle: the
+              // phase is bound by shared-memory wavefronts, 72 KB of weights per image); eight independent chains (one per
+              // position inside a 16-byte weight chunk), summed in a fixed order - the result depends on the layer only,
+              // never on the band or the CTA
+              const int co = et & 63, part2 = et >> 6;
+              float ac[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              const float4* S4 = reinterpret_cast<const float4*>(S);
               for (int tap = part2; tap < 9; tap += 2) {
                 const uint8_t* wr = wsm + (tap * 64 + co) * 128;
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
                   const uint4 raw = *reinterpret_cast<const uint4*>(wr + ((ch ^ (co & 7)) << 4));
-                  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float2 f = __bfloat1622float2(h2[j]);
-                    acc0 = fmaf(f.x, S[tap * 64 + ch * 8 + 2 * j], acc0);
-                    acc1 = fmaf(f.y, S[tap * 64 + ch * 8 + 2 * j + 1], acc1);
-                  }
+                  const float4 sa = S4[tap * 16 + ch * 2], sb = S4[tap * 16 + ch * 2 + 1];
+                  ac[0] = fmaf(__uint_as_float(raw.x << 16), sa.x, ac[0]);
+                  ac[1] = fmaf(__uint_as_float(raw.x & 0xffff0000u), sa.y, ac[1]);
+                  ac[2] = fmaf(__uint_as_float(raw.y << 16), sa.z, ac[2]);
+                  ac[3] = fmaf(__uint_as_float(raw.y & 0xffff0000u), sa.w, ac[3]);
+                  ac[4] = fmaf(__uint_as_float(raw.z << 16), sb.x, ac[4]);
+                  ac[5] = fmaf(__uint_as_float(raw.z & 0xffff0000u), sb.y, ac[5]);
+                  ac[6] = fmaf(__uint_as_float(raw.w << 16), sb.z, ac[6]);
+                  ac[7] = fmaf(__uint_as_float(raw.w & 0xffff0000u), sb.w, ac[7]);
                 }
               }
+              const float acc0 = (ac[0] + ac[2]) + (ac[4] + ac[6]), acc1 = (ac[1] + ac[3]) + (ac[5] + ac[7]);
               tmp[640 + et] = acc0 + acc1;
             }
             grp.sync();
+            if (q == 0 && egrp == 0) DFIR_TRACE(8, 45);
             if (et < 64) {
-              y_s[et] = bias_s[et] + (tmp[640 + 2 * et] + tmp[640 + 2 * et + 1]) * inv_hw;
+              y_s[et] = bias_s[et] + (tmp[640 + et] + tmp[640 + 64 + et]) * inv_hw;
               // training forward: the backward needs the pooled mean (every CTA touching image b writes the same bits)
               if (a.ymean_out != nullptr) a.ymean_out[static_cast<size_t>(ba) * 64 + et] = y_s[et];
             }
             grp.sync();
+            if (q == 0 && egrp == 0) DFIR_TRACE(8, 46);
             attn_vector(grp, a.ca_style, cap, 64, a.ca_R, a.ca_M, attr_s, y_s, s_s, tmp);
-            if (et < 64)
-              svec_s[(b - bimg_first) * 64 + et] =
-                  s_s[et] * (a.sq != nullptr ? a.sq[static_cast<size_t>(ba) * 64 + et] : 1.f);
+            if (q == 0 && egrp == 0) DFIR_TRACE(8, 47);
+            if (et < 64) svec_s[(b - bimg_first) * 64 + et] = s_s[et] * sqv;
             grp.sync();
+            if (q == 0 && egrp == 0) DFIR_TRACE(8, 48);
           }
         }
       } else {
@@ -902,6 +930,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       }
       if constexpr (kTwoEpi && kScaleSkip) {
         if (a.epi_stats) named_bar_sync(6, 256);  // the attention vectors (svec_s) of both groups are complete
+        if (q == 0 && egrp == 0) DFIR_TRACE(8, 49);
       }
       // (col, y, b, seg) of output row g, advanced without integer divisions (they cost ~130 clk each per row)
       int col = (g0 + egrp) / H, y = (g0 + egrp) % H;

@@ -46,6 +46,11 @@ def launch():
         ist.zero_()
         _lib.check(lib.dfir_conv3x3_c64_stats_fx(a.data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR, b.data_ptr(),
                                                  ist.data_ptr(), 1 if mode == "statsw" else 0, st()), "c1fx")
+    elif mode == "sshl8fx":   # statistics as the fixed-point image sums (what the network schedule launches)
+        _lib.check(lib.dfir_conv3x3_c64_scale_skip_hl8(a.data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR,
+                                                       None, xh.data_ptr(), xl8.data_ptr(), xh.data_ptr(), xl8.data_ptr(),
+                                                       ist.data_ptr(), None, None, 1, blob.data_ptr(), 4, 10, 10,
+                                                       attr.data_ptr(), sq.data_ptr(), int(os.environ.get("DESC", "0")), st()), "sshl8fx")
     elif mode in ("sshl8", "sshl8stats"):
         stats = mode == "sshl8stats"
         _lib.check(lib.dfir_conv3x3_c64_scale_skip_hl8(a.data_ptr(), wp.data_ptr(), bias.data_ptr(), bc, LR, LR,
@@ -92,6 +97,11 @@ print("mode %s bc %d (SM clocks relative to the first event; 0 = not recorded)" 
 print("row " + " ".join("%10s" % n for n in names))
 for i in range(34):
     print("%3d " % i + " ".join("%10d" % (tr[k][i] - t0 if tr[k][i] else 0) for k in range(16)))
+pro = [tr[8][i] for i in range(40, 50)]
+if any(pro):
+    print("prologue of epilogue group 0 (clk after griddepcontrol.wait): " + " ".join(
+        "%s=%d" % (n, v - pro[0]) for n, v in zip(["cap_bar", "weights", "stats_loaded", "S_stored", "matvec", "y", "attn", "img_done",
+                                                   "both_groups"], pro[1:]) if v) + "  first_row_wait=%d" % (tr[8][0] - pro[0]))
 for k in (0, 3, 4, 7):
     v = [tr[k][i] for i in range(4, 27) if tr[k][i]]
     if len(v) > 2:
