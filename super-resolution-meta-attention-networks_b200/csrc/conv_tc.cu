@@ -166,6 +166,25 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   return d;
 }
 
+// shared-memory accesses by 32-bit shared-window address (the update loop of the stream epilogue: through generic pointers
+// the compiler rebuilt the shared window base - S2UR SR_CgaCtaId + ULEA - in front of every group of accesses)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -671,6 +690,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
       // issued two tiles ahead.  No barrier other than the tile's own mbarrier: the warps never wait for each other.
       const int hl_w = egrp * 4 + q;                       // buffer column of this warp
       uint8_t* const hl_base = smem + L::off_hl + hl_w * kHI;
+      const uint32_t hl_sbase = smem_u32(hl_base);
       uint64_t* const hl_bar = sbar + hl_w * kHS;
       int hl_ly = (g0 + egrp) % H, hl_lcol = (g0 + egrp) / H;  // load cursor: next row whose tiles are requested
       int hl_lb = hl_lcol / nseg, hl_lseg = hl_lcol % nseg;
@@ -1072,6 +1092,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
             }
             // word (pixel p, channels 8 n + 2 cq + {0,1}) of a tile: p * 128 + ((n ^ (p & 7)) << 4) + 4 cq (TMA 128B swizzle)
             uint8_t* wbase = buf + pr * 128 + 4 * cq + (kTilePx == 32 ? half * 2048 : 0);
+            const uint32_t sbuf = hl_sbase + hl_slot * (8 * kHI);   // the buffer as a shared-window address
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl) {
               // all 16 loads of a pixel first, then the arithmetic, then the 16 stores: written as load / update / store
@@ -1087,15 +1108,16 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
                 // channels of a thread are ONE 16-byte word (one 128-bit shared-memory access per pixel instead of eight 16-bit
                 // ones).  Tile of 32 px x 64 B, TMA SWIZZLE_64B: pixel p, 16-byte chunk k at p * 64 + ((k ^ ((p >> 1) & 3)) << 4).
                 const int p = pr + 8 * sl + (kTilePx == 32 ? 16 * half : 0);
-                uint4* lptr = reinterpret_cast<uint4*>(buf + kHlHiBytes + p * 64 + ((cq ^ ((p >> 1) & 3)) << 4));
+                const uint32_t lo_a = sbuf + kHlHiBytes + p * 64 + ((cq ^ ((p >> 1) & 3)) << 4);
+                // hi word n of the pixel: the buffer is 1024-byte aligned, so + ((n ^ pr) << 4) is ^ (pr << 4) ^ (n << 4)
+                const uint32_t hi_a = (sbuf + pr * 128 + 4 * cq + half * 2048 + sl * 1024) ^ (pr << 4);
                 uint32_t lq[4] = {0u, 0u, 0u, 0u};
                 if (!exp_no_lo) {
-                  const uint4 t4 = *lptr;
+                  const uint4 t4 = lds_v4(lo_a);
                   lq[0] = t4.x; lq[1] = t4.y; lq[2] = t4.z; lq[3] = t4.w;
                 }
 #pragma unroll
-                for (int n = 0; n < 8; ++n)
-                  hw[n] = exp_no_hi ? 0x3f803f80u : *reinterpret_cast<const uint32_t*>(wbase + sl * 1024 + ((n ^ pr) << 4));
+                for (int n = 0; n < 8; ++n) hw[n] = exp_no_hi ? 0x3f803f80u : lds_u32(hi_a ^ (n << 4));
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
                   const uint32_t* src = half ? rb : ra;
@@ -1117,14 +1139,14 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
                 }
 #pragma unroll
                 for (int n = 0; n < 8; ++n)
-                  if (!exp_no_hi) *reinterpret_cast<uint32_t*>(wbase + sl * 1024 + ((n ^ pr) << 4)) = hw[n];
+                  if (!exp_no_hi) sts_u32(hi_a ^ (n << 4), hw[n]);
                 if (!exp_no_lo) {
                   uint4 o4;
                   o4.x = prmt(lw[0], lw[1], 0x5410u) ^ 0x80808080u;
                   o4.y = prmt(lw[2], lw[3], 0x5410u) ^ 0x80808080u;
                   o4.z = prmt(lw[4], lw[5], 0x5410u) ^ 0x80808080u;
                   o4.w = prmt(lw[6], lw[7], 0x5410u) ^ 0x80808080u;
-                  *lptr = o4;
+                  sts_v4(lo_a, o4);
                 }
               } else {
 #pragma unroll

@@ -12,6 +12,6 @@ for l in sys.stdin:
     elif t and t[0].isdigit() and names and int(t[9])>0:
         v=dict(zip(names,map(int,t[1:])))
         print(' '.join('%9d'%x for x in [int(t[0]), v['e0_tfull']-v['e0_wait'], v['e0_release']-v['e0_tfull'], v['t_issued']-v['e0_release'], v['t_landed']-v['t_issued'], v['t_updated']-v['t_landed'], v['t2_fenced']-v['t_updated'], v['e0_end']-v['t2_fenced'], 0]))
-    elif 'period' in l or 'prologue' in l: print(l.strip())
+    elif 'period' in l or 'prologue' in l or l.startswith('update') or l.startswith('  urow'): print(l.rstrip())
 "
 cp /tmp/libdfir_ship.so $P/libdfir_b200.so

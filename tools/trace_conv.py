@@ -102,6 +102,17 @@ if any(pro):
     print("prologue of epilogue group 0 (clk after griddepcontrol.wait): " + " ".join(
         "%s=%d" % (n, v - pro[0]) for n, v in zip(["cap_bar", "weights", "stats_loaded", "S_stored", "matvec", "y", "attn", "img_done",
                                                    "both_groups"], pro[1:]) if v) + "  first_row_wait=%d" % (tr[8][0] - pro[0]))
+if int(os.environ.get("EXTRA_PROBE", "0")) & 262144 and any(tr[2][i] for i in range(32, 46)):
+    # stamps inside the update of the first pixel slot of a row (epilogue group 0, warp 0): kinds 0 / 2 / 3 / 5 at rows 32..,
+    # kind 1 = loads issued of the LAST pixel slot
+    print("update of pixel slot 0 (clk after the tile landed): loads issued, loads landed, arithmetic done, stores issued | "
+          "slot 3 loads issued | half 0 done, row fenced")
+    for r in range(14):
+        if tr[2][32 + r] and tr[12][r]:
+            base = tr[12][r]
+            print("  urow %2d: %5d %5d %5d %5d | %5d | %5d %5d" % (r, tr[0][32 + r] - base, tr[2][32 + r] - base, tr[3][32 + r] - base,
+                                                               tr[5][32 + r] - base, tr[1][32 + r] - base, tr[13][r] - base,
+                                                               tr[15][r] - base))
 for k in (0, 3, 4, 7):
     v = [tr[k][i] for i in range(4, 27) if tr[k][i]]
     if len(v) > 2:
