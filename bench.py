@@ -393,9 +393,8 @@ def run_ours(args):
 NCU = {"source": "profiles/r02_tc_kernels_ncu.md, profiles/r02_launches_infer_32x128.csv",
        "conv2_traffic": None, "conv2_in_step_us": None, "conv2_share": None, "conv1_traffic": None, "conv1_in_step_us": None,
        "conv1_share": None}
-_ncu_path = os.path.join(ROOT, "profiles", "r02b_ncu_numbers.json")
-if not os.path.isfile(_ncu_path):
-    _ncu_path = os.path.join(ROOT, "profiles", "r02_ncu_numbers.json")
+_ncu_path = next((p for p in (os.path.join(ROOT, "profiles", n) for n in ("r02c_ncu_numbers.json", "r02b_ncu_numbers.json",
+                                                                         "r02_ncu_numbers.json")) if os.path.isfile(p)), "")
 if os.path.isfile(_ncu_path):
     with open(_ncu_path) as _fh:
         NCU.update(json.load(_fh))

@@ -16,16 +16,5 @@ python tools/profile_small.py infer > gpurun_out/prof_plain.log 2>&1 && {
 $N -k regex:'conv3x3_c64_tc_kernel<\(int\)64, \(int\)5, \(int\)0>' -s 2 -c 1 -o gpurun_out/r02c_conv1_stats -f python tools/profile_small.py infer > gpurun_out/ncu_conv1_stats_b.log 2>&1
 $N -k regex:'conv3x3_c64_tc_kernel<\(int\)64, \(int\)9, \(int\)0>' -s 4 -c 1 -o gpurun_out/r02c_conv2_hl8 -f python tools/profile_small.py infer > gpurun_out/ncu_conv2_hl8_b.log 2>&1
 }
-tail -4 gpurun_out/pytest_final.log; tail -3 gpurun_out/smoke_final.log; cut -c1-400 gpurun_out/bench_final.json; exit 0; fi
-python tools/fwd_once.py 32 32 2 > gpurun_out/fwd_plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r02c_launches_infer_32x128.csv \
-  python tools/fwd_once.py 32 32 2 > gpurun_out/ncu_launches_b.log 2>&1
-N="ncu --set full --clock-control none --import-source on --kernel-name-base demangled"
-python tools/profile_small.py infer > gpurun_out/prof_plain.log 2>&1 && {
-$N -k regex:'conv3x3_c64_tc_kernel<\(int\)64, \(int\)5, \(int\)0>' -s 2 -c 1 -o gpurun_out/r02c_conv1_stats -f python tools/profile_small.py infer > gpurun_out/ncu_conv1_stats_b.log 2>&1
-$N -k regex:'conv3x3_c64_tc_kernel<\(int\)64, \(int\)9, \(int\)0>' -s 4 -c 1 -o gpurun_out/r02c_conv2_hl8 -f python tools/profile_small.py infer > gpurun_out/ncu_conv2_hl8_b.log 2>&1
-}
-python tools/profile_staged_train.py > gpurun_out/prof_staged_plain.log 2>&1 && \
-$N -k regex:'nl_bwd|lam_bwd|csam_bwd|pa_backward|soca_mlp_bwd|channel_dot_partial|outer_reduce_partial' -c 14 -o gpurun_out/r02c_bwd_kernels -f python tools/profile_staged_train.py > gpurun_out/ncu_bwd_b.log 2>&1
 tail -4 gpurun_out/pytest_final.log; cat gpurun_out/smoke_final.log | tail -3; cat gpurun_out/bench_final.json | cut -c1-400; cat gpurun_out/bench_ref_final.json | cut -c1-200; ls -la gpurun_out/*r02c*
 bash tools/run_tile_trace.sh > gpurun_out/r02c_trace_conv2_fx_final.log 2>&1; tail -6 gpurun_out/r02c_trace_conv2_fx_final.log
