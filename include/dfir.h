@@ -160,7 +160,10 @@ int dfir_conv3x3_c64_scale_skip_hl(const void* in_bf16, const void* wpacked, con
  * skip_lo8 / out_lo8: dense int8 planes [B][H][W][64] whose 64 bytes per pixel are stored in the order of the accumulator
  * fragment: byte cq * 16 + 2 n + e holds channel 8 n + 2 cq + e (n = 0..7, cq = 0..3, e = 0..1), so that a thread of the
  * epilogue reads its 16 channels of a pixel as one 16-byte word.  The plane is private to the library (dfir_stream_encode_hl8 /
- * dfir_stream_decode_hl8 convert from / to fp32). */
+ * dfir_stream_decode_hl8 convert from / to fp32).
+ * Statistics for the in-kernel attention (style != NONE), two forms: the three per-row arrays of dfir_conv3x3_c64_stats
+ * (pool_rows, col_first, col_last), or - what dfir_qrcan_forward launches - the [B][9][64] int64 fixed-point image sums of
+ * dfir_conv3x3_c64_stats_fx passed through `pool_rows` with col_first == col_last == NULL (both hl entry points). */
 int dfir_conv3x3_c64_scale_skip_hl8(const void* in_bf16, const void* wpacked, const float* bias, int B, int H, int W,
                                    const float* svec, const void* skip_hi, const void* skip_lo8, void* out_hi, void* out_lo8,
                                    const float* pool_rows, const float* col_first, const float* col_last, int style,

@@ -275,6 +275,24 @@ def test_pool_by_linearity_trio(shape, style):
         G.sync()
         assert (dec8(p_hi, p_q) - out32).abs().max().item() <= 2.0 ** -14 * scale, desc
         assert (p_hi.float() - out32).abs().max().item() <= 2.0 ** -8 * scale
+    # the statistics as the network schedule passes them: the 64-bit fixed-point image sums of dfir_conv3x3_c64_stats_fx through
+    # `pool_rows` with col_first == col_last == NULL (the per-row arrays and the fixed-point sums differ by the rounding of the
+    # sums only: same result within the stream's precision)
+    t_fx = torch.empty_like(t_d)
+    ist = torch.zeros(B, 9, 64, device="cuda", dtype=torch.int64)
+    assert L.dfir_conv3x3_c64_stats_fx(x_bf.data_ptr(), w1p.data_ptr(), b1d.data_ptr(), B, H, W, t_fx.data_ptr(), ist.data_ptr(),
+                                       0, G.stream()) == 0
+    G.sync()
+    assert torch.equal(t_fx, t_d)
+    for desc in (0, 1):
+        p_hi = torch.full((B, H, W, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+        p_q = torch.full((B, H, W, 64), 77, device="cuda", dtype=torch.int8)
+        assert L.dfir_conv3x3_c64_scale_skip_hl8(t_d.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), B, H, W, None, y_hi.data_ptr(),
+                                                 y_q.data_ptr(), p_hi.data_ptr(), p_q.data_ptr(), ist.data_ptr(), None, None,
+                                                 STYLE_ID[style], blob.data_ptr(), 4, M, A, attr_d.data_ptr(), sq_d.data_ptr(),
+                                                 desc, G.stream()) == 0
+        G.sync()
+        assert (dec8(p_hi, p_q) - out32).abs().max().item() <= 2.0 ** -14 * scale + 1e-5 * scale, desc
     # in place, scale vector from memory
     assert L.dfir_conv3x3_c64_scale_skip_hl8(t_d.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), B, H, W, svec.data_ptr(),
                                              y_hi.data_ptr(), y_q.data_ptr(), y_hi.data_ptr(), y_q.data_ptr(), None, None,
