@@ -1483,7 +1483,9 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
 #pragma unroll
             for (int j = 0; j < 16; ++j) sums[j] = 0.f;
             const int x0 = seg * 128 + q * 32 + pr;         // image column of this thread's first pixel
-            uint8_t* strow = st + (q * 32 + pr) * 128 + 4 * cq;  // (pixel & 7) == pr for all four pixels of the thread
+            // staging word (pixel slot sl, channel block n) by shared-window address: the tile is 1024-byte aligned, so
+            // + ((n ^ pr) << 4) is ^ (pr << 4) ^ (n << 4); (pixel & 7) == pr for all four pixels of the thread
+            const uint32_t st_a = (smem_u32(st) + (q * 32 + pr) * 128 + 4 * cq) ^ (pr << 4);
 #pragma unroll
             for (int sl = 0; sl < 4; ++sl) {                // pixel slots: pr, pr + 8, pr + 16, pr + 24
               const bool ok = x0 + 8 * sl < a.W;
@@ -1530,8 +1532,7 @@ conv3x3_c64_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_
               }
               if (!exp_skip_store) {
 #pragma unroll
-                for (int n = 0; n < 8; ++n)
-                  *reinterpret_cast<uint32_t*>(strow + sl * 1024 + ((n ^ pr) << 4)) = pack_bf16x2(v[2 * n], v[2 * n + 1]);
+                for (int n = 0; n < 8; ++n) sts_u32((st_a + sl * 1024) ^ (n << 4), pack_bf16x2(v[2 * n], v[2 * n + 1]));
               }
               if constexpr (EPI == EPI_BIAS_POOL || EPI == EPI_RELU_STATS) {
                 if (ok) {
